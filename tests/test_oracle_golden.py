@@ -1,0 +1,97 @@
+"""CPU: the oracle (numpy float64 arbiter, torch float32 full-size checker) against the golden
+vectors produced by executing the reference's own source (tests/golden/make_golden.py)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import hgru_oracle_np as onp
+from oracle import hgru_oracle_torch as otorch
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+HGRU_FILES = sorted(glob.glob(os.path.join(GOLDEN, "hgru_ref_*.npz")))
+
+
+def _params(z, scope="contextual_circuit/"):
+    return {n: z["var:" + scope + n] for n in onp.HGRU_PARAM_NAMES}
+
+
+def test_golden_files_present():
+    assert len(HGRU_FILES) >= 3
+    assert os.path.exists(os.path.join(GOLDEN, "pose_layers_ref.npz"))
+
+
+@pytest.mark.parametrize("path", HGRU_FILES, ids=[os.path.basename(p) for p in HGRU_FILES])
+def test_numpy_oracle_matches_reference_every_timestep(path):
+    z = np.load(path)
+    T = int(z["T"])
+    out, H1s, H2s = onp.hgru_forward(z["X"], z["O0"], _params(z), T, trace=True)
+    for t in range(T):
+        np.testing.assert_allclose(H1s[t], z["I_steps"][:, t], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(H2s[t], z["O_steps"][:, t], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(out, z["O_final"], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("path", HGRU_FILES, ids=[os.path.basename(p) for p in HGRU_FILES])
+def test_initial_I_is_dead_on_configured_path(path):
+    """gru_gates=True: the reference's I_0 draw never reaches the output."""
+    z = np.load(path)
+    a = onp.hgru_forward(z["X"], z["O0"], _params(z), int(z["T"]))
+    np.testing.assert_allclose(a, z["O_final"], rtol=0, atol=1e-12)   # oracle takes no I_0 at all
+
+
+@pytest.mark.parametrize("path", HGRU_FILES, ids=[os.path.basename(p) for p in HGRU_FILES])
+def test_torch_oracle_matches_reference(path):
+    z = np.load(path)
+    T = int(z["T"])
+    out, H1s, H2s = otorch.hgru_forward(z["X"], z["O0"], _params(z), T, trace=True)
+    for t in range(T):
+        assert onp.rel_err(H1s[t].numpy(), z["I_steps"][:, t])[0] < 2e-6
+        assert onp.rel_err(H2s[t].numpy(), z["O_steps"][:, t])[0] < 2e-6
+    assert onp.rel_err(out.numpy(), z["O_final"])[0] < 2e-6
+
+
+def test_weights_dict_keys_of_reference():
+    """`build()` returns (O, weights, activities) with these keys (hgru_module.py:863-870,939-954)."""
+    z = np.load(HGRU_FILES[0])
+    assert set(z["weights_keys"].tolist()) == {
+        "P_r", "I_r", "O_r", "xi_r", "beta_r", "nu_r", "zeta_r", "gamma_r", "kappa_r", "rho_r", "p_t"}
+
+
+def test_pose_layers_match_reference():
+    z = np.load(os.path.join(GOLDEN, "pose_layers_ref.npz"))
+    c1 = onp.conv_layer(z["x"], z["var:conv_1/conv_1_filters"], z["var:conv_1/conv_1_biases"])
+    np.testing.assert_allclose(c1, z["conv1"], rtol=0, atol=1e-12)
+    p1 = onp.max_pool_2x2(c1)
+    np.testing.assert_allclose(p1, z["pool1"], rtol=0, atol=1e-12)
+    c2 = onp.conv_layer(p1, z["var:conv_2/conv_2_filters"], z["var:conv_2/conv_2_biases"])
+    np.testing.assert_allclose(c2, z["conv2"], rtol=0, atol=1e-12)
+    fc = onp.fc_layer(c2, z["var:fc_1/fc_1_weights"], z["var:fc_1/fc_1_biases"])
+    np.testing.assert_allclose(fc, z["fc1"], rtol=0, atol=1e-12)
+    hg = onp.hgru_forward(c2, z["hgru_O0"], _params(z), 8)
+    np.testing.assert_allclose(hg, z["hgru_O"], rtol=0, atol=1e-12)
+    assert set(z["var_dict_keys"].tolist()) == {
+        "conv_1|0", "conv_1|1", "conv_2|0", "conv_2|1", "fc_1|0", "fc_1|1"}
+
+
+def test_numpy_and_torch_pose_forward_agree():
+    from monkey_pose_b200 import initialization as init
+    P = init.pose_params(channels=8, S=5, T=3, hw=8, fc_hidden=32, out=69, seed=3, stress=4.0,
+                         random_bn=True)
+    depth = init.synthetic_depth(2, seed=0, size=16)
+    h0 = init.hidden_init((2, 8, 8, 8), seed=5)
+    a, acts = onp.pose_forward(depth, P, h0, timesteps=3, trace=True)
+    b = otorch.pose_forward(depth, P, h0, timesteps=3).numpy()
+    assert a.shape == (2, 69)
+    assert np.abs(acts["hgru"]).max() > 1e-3
+    assert onp.rel_err(b, a)[0] < 1e-5
+    assert onp.mean_joint_error_mm(b, a) < 1e-2
+
+
+def test_metric_restatement():
+    """getMeanError_np (pose_evaluation.py:10-15) on x600 mm scaling (train_cnn_networks_hgru.py:154-156)."""
+    a = np.zeros((2, 69))
+    b = np.zeros((2, 69))
+    b[:, 0:3] = [3.0 / 600, 4.0 / 600, 0.0]        # one joint off by 5 mm in each frame
+    assert abs(onp.mean_joint_error_mm(a, b) - 5.0 / 23) < 1e-12
