@@ -1,0 +1,243 @@
+// Implicit-GEMM SxS "SAME" convolution on tcgen05 tensor cores (sm_100a), bf16 operands, fp32
+// accumulation in TMEM.  This is kernel K8 of SURVEY.md 2b: the 15x15 horizontal convolutions
+// C1 = W * (G1 . H2) and C2 = W * H1 of the hGRU step (reference: hgru_module.py:615-624 via
+// tf.nn.conv2d at :531-535), and it also serves the 3x3 stem convs (hgru_pose.py:146).
+//
+// GEMM view: M = output pixels, N = output channels, K = (tap, input channel).
+//
+// Data layout in HBM
+//   activations (operand copy): bf16 "chunked NHWC"  [n][cg][y][x][8]   (cg = channel / 8)
+//       -> one TMA box load brings a (rows+S-1) x (cols+S-1) halo window of 2 channel-chunks into
+//          shared memory as [cg][row][col][16 B]; out-of-image pixels are zero-filled by TMA,
+//          which IS the SAME padding.
+//   weights: bf16 packed per (kstep, tap) as [2 chunks][CO_PAD][8 ci]  (2 KB at CO_PAD = 64)
+//       -> streamed with 1-D bulk copies through a small ring.
+//
+// Shared-memory operand form: the no-swizzle K-major canonical layout (8-row x 16-byte core
+// matrices).  A pixel's 8 channels are one 16-byte row, 8 horizontally adjacent pixels form one
+// core matrix, so an M = 128 operand is a 16-row x 8-column pixel patch: SBO = window row pitch,
+// LBO = chunk plane pitch.  A filter tap (dy, dx) is then nothing but a different descriptor
+// start address into the SAME resident window -- the input is read from HBM/L2 once per unit and
+// reused by all S*S taps.
+//
+// CTA = 8 warps: w0 weight producer, w1 MMA issuer, w2 TMEM allocator, w3 input producer,
+// w4..7 epilogue (TMEM -> registers -> global).  Persistent over "units" (16 x 8*TILES_X pixels
+// of one frame); two TMEM accumulator sets so unit u's epilogue overlaps unit u+1's MMAs.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "sm100_ptx.cuh"
+
+namespace hgru {
+
+constexpr int kTileRows = 16;   // M tile = 16 rows x 8 cols of pixels
+
+template <int S, int KSTEPS, int CO_PAD, int TILES_X, int G, int WSTAGES>
+struct TcConvCfg {
+  static constexpr int kS = S;
+  static constexpr int kTaps = S * S;
+  static constexpr int kPad = (S - 1) / 2;
+  static constexpr int kRows = kTileRows + S - 1;           // window rows
+  static constexpr int kCols = 8 * TILES_X + S - 1;         // window cols
+  static constexpr int kRowPitch = kCols * 16;              // bytes (SBO of A)
+  static constexpr int kChunkPitch = kRows * kRowPitch;     // bytes (LBO of A)
+  static constexpr int kPartBytes = 2 * kChunkPitch;        // one kstep = 2 chunks
+  static constexpr int kInBytes = KSTEPS * kPartBytes;
+  static constexpr int kTapBytes = 2 * CO_PAD * 16;         // one (kstep, tap) weight block
+  static constexpr int kStageBytes = G * kTapBytes;
+  static constexpr int kStagesPerKstep = kTaps / G;
+  static constexpr int kAccCols = TILES_X * CO_PAD;         // TMEM columns per accumulator set
+  static constexpr int kNumBars = 2 * KSTEPS + 2 * WSTAGES + 4;
+  static constexpr int kSmemBytes = kInBytes + WSTAGES * kStageBytes + kNumBars * 8 + 16 + 1024;
+  static_assert(kTaps % G == 0, "taps per stage must divide S*S");
+  static_assert(2 * kAccCols <= 512, "two accumulator sets must fit TMEM");
+  static_assert(CO_PAD % 16 == 0 && CO_PAD >= 16 && CO_PAD <= 256, "UMMA N constraint (M=128)");
+  static_assert(kChunkPitch % 16 == 0 && (kChunkPitch >> 4) < 16384, "LBO range");
+};
+
+struct TcConvArgs {
+  int N, H, W;              // frames, image height / width
+  int k;                    // real channel count (<= CO_PAD); output row pitch
+  int units_x, units_y;     // units per frame
+  int num_units;
+  const __nv_bfloat16* wpk; // packed weights [KSTEPS][taps][2][CO_PAD][8]
+  const float* bias;        // [k] or nullptr
+  float* out;               // fp32 NHWC [N][H][W][k]
+};
+
+template <int S, int KSTEPS, int CO_PAD, int TILES_X, int G, int WSTAGES>
+__global__ void __launch_bounds__(256, 1)
+hconv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const TcConvArgs a) {
+  using namespace sm100;
+  using Cfg = TcConvCfg<S, KSTEPS, CO_PAD, TILES_X, G, WSTAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte aligned carve-up
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t in_buf = base;
+  const uint32_t w_buf = in_buf + Cfg::kInBytes;
+  const uint32_t bars = w_buf + WSTAGES * Cfg::kStageBytes;
+  const uint32_t bar_in_full = bars;                               // [KSTEPS]
+  const uint32_t bar_in_empty = bar_in_full + 8 * KSTEPS;          // [KSTEPS]
+  const uint32_t bar_w_full = bar_in_empty + 8 * KSTEPS;           // [WSTAGES]
+  const uint32_t bar_w_empty = bar_w_full + 8 * WSTAGES;           // [WSTAGES]
+  const uint32_t bar_acc_full = bar_w_empty + 8 * WSTAGES;         // [2]
+  const uint32_t bar_acc_empty = bar_acc_full + 16;                // [2]
+  const uint32_t tmem_slot = bar_acc_empty + 16;
+  uint32_t* tmem_slot_ptr =
+      reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < KSTEPS; ++i) {
+      mbar_init(bar_in_full + 8 * i, 1);
+      mbar_init(bar_in_empty + 8 * i, 1);
+    }
+    for (int i = 0; i < WSTAGES; ++i) {
+      mbar_init(bar_w_full + 8 * i, 1);
+      mbar_init(bar_w_empty + 8 * i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_acc_full + 8 * i, 1);
+      mbar_init(bar_acc_empty + 8 * i, 128);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&in_map);
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int units_per_frame = a.units_x * a.units_y;
+  const int first = blockIdx.x;
+  const int stride = gridDim.x;
+
+  if (warp == 0) {
+    // ---------------- weight producer: ring of WSTAGES stages, G taps each ----------------
+    if (lane == 0) {
+      uint32_t st = 0, ph = 0;
+      for (int u = first; u < a.num_units; u += stride) {
+        for (int q = 0; q < KSTEPS; ++q) {
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(a.wpk) +
+                               static_cast<size_t>(q) * Cfg::kTaps * Cfg::kTapBytes;
+          for (int sg = 0; sg < Cfg::kStagesPerKstep; ++sg) {
+            mbar_wait(bar_w_empty + 8 * st, ph ^ 1);
+            mbar_arrive_expect_tx(bar_w_full + 8 * st, Cfg::kStageBytes);
+            bulk_load(w_buf + st * Cfg::kStageBytes, src + static_cast<size_t>(sg) * Cfg::kStageBytes,
+                      Cfg::kStageBytes, bar_w_full + 8 * st);
+            if (++st == WSTAGES) { st = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ---------------- input producer: one TMA box per (unit, kstep) ----------------
+    if (lane == 0) {
+      int it = 0;
+      for (int u = first; u < a.num_units; u += stride, ++it) {
+        const int n = u / units_per_frame;
+        const int r = u - n * units_per_frame;
+        const int uy = r / a.units_x, ux = r - uy * a.units_x;
+        const int y0 = uy * kTileRows - Cfg::kPad;
+        const int x0 = ux * (8 * TILES_X) - Cfg::kPad;
+        for (int q = 0; q < KSTEPS; ++q) {
+          mbar_wait(bar_in_empty + 8 * q, (it & 1) ^ 1);
+          mbar_arrive_expect_tx(bar_in_full + 8 * q, Cfg::kPartBytes);
+          // tensor viewed as 8-byte elements: dim0 = 2*x, dim1 = y, dim2 = chunk, dim3 = frame
+          tma_load_4d(in_buf + q * Cfg::kPartBytes, &in_map, bar_in_full + 8 * q, 2 * x0, y0,
+                      2 * q, n);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer (single thread) ----------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(1 /*bf16*/, 128, CO_PAD);
+      uint32_t st = 0, ph = 0;
+      int it = 0;
+      for (int u = first; u < a.num_units; u += stride, ++it) {
+        const uint32_t s = it & 1;
+        const uint32_t acc = tmem_base + s * Cfg::kAccCols;
+        mbar_wait(bar_acc_empty + 8 * s, ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        for (int q = 0; q < KSTEPS; ++q) {
+          mbar_wait(bar_in_full + 8 * q, it & 1);
+          const uint32_t a_part = in_buf + q * Cfg::kPartBytes;
+          for (int sg = 0; sg < Cfg::kStagesPerKstep; ++sg) {
+            mbar_wait(bar_w_full + 8 * st, ph);
+            tc_fence_after();
+            const uint32_t w_st = w_buf + st * Cfg::kStageBytes;
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+              const int tap = sg * G + g;
+              const int dy = tap / S, dx = tap - dy * S;
+              const uint32_t a_tap = a_part + dy * Cfg::kRowPitch + dx * 16;
+              const uint64_t bdesc = make_smem_desc(w_st + g * Cfg::kTapBytes, CO_PAD * 16, 128);
+#pragma unroll
+              for (int t = 0; t < TILES_X; ++t) {
+                const uint64_t adesc =
+                    make_smem_desc(a_tap + t * 128, Cfg::kChunkPitch, Cfg::kRowPitch);
+                mma_bf16_ss(acc + t * CO_PAD, adesc, bdesc, idesc, (q | tap) != 0);
+              }
+            }
+            tc_commit(bar_w_empty + 8 * st);
+            if (++st == WSTAGES) { st = 0; ph ^= 1; }
+          }
+          tc_commit(bar_in_empty + 8 * q);
+        }
+        tc_commit(bar_acc_full + 8 * s);
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------- epilogue: TMEM -> registers -> fp32 NHWC ----------------
+    const int ew = warp & 3;                      // TMEM lane quarter this warp may access
+    const int m = ew * 32 + lane;                 // accumulator row = pixel within the M tile
+    const int prow = m >> 3, pcol = m & 7;
+    int it = 0;
+    for (int u = first; u < a.num_units; u += stride, ++it) {
+      const uint32_t s = it & 1;
+      const int n = u / units_per_frame;
+      const int r = u - n * units_per_frame;
+      const int uy = r / a.units_x, ux = r - uy * a.units_x;
+      const int y = uy * kTileRows + prow;
+      mbar_wait(bar_acc_full + 8 * s, (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int t = 0; t < TILES_X; ++t) {
+        const int x = ux * (8 * TILES_X) + t * 8 + pcol;
+        const bool ok = (y < a.H) && (x < a.W);
+        float* dst = a.out + (static_cast<size_t>(n) * a.H * a.W + static_cast<size_t>(y) * a.W + x) * a.k;
+        const uint32_t taddr =
+            tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + s * Cfg::kAccCols + t * CO_PAD;
+#pragma unroll
+        for (int c0 = 0; c0 < CO_PAD; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + c0, v);
+          tmem_ld_wait();
+          if (ok) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int c = c0 + j;
+              if (c < a.k) dst[c] = __uint_as_float(v[j]) + (a.bias ? a.bias[c] : 0.f);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_acc_empty + 8 * s);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace hgru
