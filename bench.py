@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""bench.py -- depth frames/sec of the hGRU-pose forward (8 timesteps, 15x15 horizontal kernels).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one forward pass of the whole hot path (stem -> 8-step hGRU -> readout) over one batch
+of synthetic 128x128 depth crops.  Workload at every N: BASELINE.json configs[1] per GPU (batch 256,
+25 hidden channels, 15x15, T = 8), i.e. weak scaling; frames are sharded over ranks with no
+data-path collective, predictions are all-gathered (NCCL) at the end of each step.
+
+Prints ONE JSON line on rank 0 (see the contract in the task statement): `value` is device-resident
+throughput, `e2e` the same metric through the public API with pinned host buffers (H2D + D2H inside
+the timed region), `roofline` the tensor-pipe fraction of the dominant kernel (the tcgen05
+horizontal conv) timed live with CUDA events, `cpu_baseline` the torch-CPU oracle on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "depth frames/sec (hGRU 8-step fwd)"
+UNIT = "frames/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="frames per GPU per step")
+    ap.add_argument("--channels", type=int, default=25)
+    ap.add_argument("--timesteps", type=int, default=8)
+    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-frames", type=int, default=64, help="frames in the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(a, n_gpus):
+    return {"workload": "hgru_pose forward, batch %d per GPU, 128x128 crops, 15x15 h-kernels, %d hidden "
+                        "channels, T=%d (BASELINE configs[1])" % (a.batch, a.channels, a.timesteps),
+            "global_batch": a.batch * n_gpus, "per_gpu_batch": a.batch, "channels": a.channels,
+            "timesteps": a.timesteps, "h_kernel": 15, "hconv_arithmetic": a.mode,
+            "parallelism": "batch-sharded x%d, no data-path collective" % n_gpus,
+            "cache": "per-step working set (%.0f MB of fp32 state per tensor) exceeds the 126 MB L2"
+                     % (a.batch * 64 * 64 * max(16, (a.channels + 15) // 16 * 16) * 4 / 1e6)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (torch-CPU stand-in for the reference's TF-CPU forward; TF is absent)
+# ------------------------------------------------------------------------------------------------
+def cpu_forward_fps(a, frames, reps):
+    import torch
+    from monkey_pose_b200 import initialization as init
+    from oracle import hgru_oracle_torch as otorch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    P = init.pose_params(channels=a.channels, S=15, T=a.timesteps, hw=64, fc_hidden=1024, out=69, seed=3)
+    P = {k: torch.as_tensor(v) for k, v in P.items()}
+    depth = init.synthetic_depth(frames, seed=1234)
+    h0 = init.hidden_init((frames, 64, 64, a.channels), seed=5)
+    otorch.pose_forward(depth[:2], P, h0[:2], timesteps=a.timesteps)      # warm-up
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        otorch.pose_forward(depth, P, h0, timesteps=a.timesteps)
+        ts.append(time.perf_counter() - t0)
+    ts.sort()
+    med = ts[len(ts) // 2]
+    return frames / med, med, cores
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, a.steps)
+    for _ in range(max(0, min(a.warmup, 1))):
+        pass
+    fps, med, cores = cpu_forward_fps(a, a.cpu_frames, steps)
+    sample = "%d frames per step (of the %d-frame batch), median of %d steps" % (a.cpu_frames, a.batch, steps)
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": a.gpus,
+            "steps": steps, "warmup": a.warmup, "ms_per_step": med * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(a, a.gpus),
+            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "note": "torch-CPU oracle: TensorFlow 1.x / Python 2 reference cannot run"},
+            "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------------
+class Clocks(object):
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append((time.perf_counter(), ln.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons, pw = [], None, set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, ln in self.rows:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                c, m = float(f[0]), float(f[1])
+            except ValueError:
+                continue
+            mx = m
+            if t0 <= ts <= t1 + 0.1:
+                sm.append(c)
+                try:
+                    pw.append(float(f[2]))
+                except ValueError:
+                    pass
+                for nme, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(pw) if pw else None}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    import monkey_pose_b200 as mp
+    from monkey_pose_b200 import initialization as init
+    from monkey_pose_b200.sharding import gather_predictions
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs CUDA devices (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n_gpus = world
+    lib = mp._lib.load()
+
+    B = a.batch
+    P = init.pose_params(channels=a.channels, S=15, T=a.timesteps, hw=64, fc_hidden=1024, out=69, seed=3)
+    depth_np = init.synthetic_depth(B, seed=1234 + rank)
+    h0 = torch.as_tensor(init.hidden_init((B, 64, 64, a.channels), seed=5 + rank)).cuda()
+    depth_dev = torch.as_tensor(depth_np).cuda()
+    depth_pin = torch.as_tensor(depth_np).pin_memory()
+
+    m = mp.model()
+    m.channels, m.timesteps, m.compute_mode, m.hidden_state = a.channels, a.timesteps, a.mode, h0
+    m.load_params(P)
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step_dev():
+        out = m.build(depth_dev, 69)
+        return gather_predictions(out, B * world) if world > 1 else out
+
+    def step_host():
+        out = m.build(depth_pin, 69)          # H2D of the crops + forward + D2H of the predictions
+        return out
+
+    def timed(fn, steps):
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        sync()
+        t1 = time.perf_counter()
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms], device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), t0, t1
+
+    for _ in range(max(3, a.warmup)):
+        step_dev()
+    clocks = Clocks(local) if rank == 0 else None
+    lib.hgru_enable_kernel_timing(1)
+    ms_dev, t0, t1 = timed(step_dev, a.steps)
+    k_ms, k_n = ctypes.c_float(0), ctypes.c_int(0)
+    lib.pose_plan_kernel_times(m._plan, ctypes.byref(k_ms), ctypes.byref(k_n))   # last step's hconv launches
+    lib.hgru_enable_kernel_timing(0)
+    clk = clocks.stop(t0, t1) if clocks else None
+    launches_per_step = m.gpu_launches
+    out_check = step_dev()
+    assert torch.isfinite(out_check).all()
+
+    for _ in range(2):
+        step_host()
+    ms_host, _, _ = timed(step_host, a.steps)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    frames = B * world * a.steps
+    value = frames / (ms_dev * 1e-3)
+    e2e = frames / (ms_host * 1e-3)
+    # roofline of the dominant kernel: algorithmic FLOPs of one horizontal conv over this rank's batch
+    k, S = a.channels, 15
+    flops_per_launch = 2.0 * B * 64 * 64 * S * S * k * k                 # 2*H*W*S^2*k^2 per frame
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("bf16_tflops_sustained") or 1400.0
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" \
+        if "bf16_tflops_sustained" in peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+    roof = None
+    if k_n.value > 0 and a.mode == "bf16":
+        avg_ms = k_ms.value / k_n.value
+        ach = flops_per_launch / (avg_ms * 1e-3) * 1e-12
+        roof = {"bound": "tensor", "kernel": "hconv_tc_kernel (15x15 implicit GEMM, tcgen05)", "achieved": ach,
+                "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "peak_source": peak_src, "peak_burst": peaks.get("bf16_tflops"),
+                "avg_launch_ms": avg_ms, "launches_per_step": k_n.value,
+                "share_of_step": k_ms.value / (ms_dev / a.steps),
+                "flops_per_launch": flops_per_launch}
+    cpu = None
+    if not a.no_cpu_baseline:
+        fps, med, cores = cpu_forward_fps(a, a.cpu_frames, 3)
+        cpu = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "%d of the %d frames, median of 3 forwards (%.1f s each), torch-CPU oracle "
+                         "(stand-in for TF-CPU: TensorFlow absent)" % (a.cpu_frames, B, med)}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps,
+            "warmup": max(3, a.warmup), "ms_per_step": ms_dev / a.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": a.mode if a.mode != "fp32" else "f32",
+            "data": "synthetic", "config": workload_config(a, n_gpus),
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(depth_pin.numel() * 4) * world,
+                    "d2h_bytes_per_step": int(B * 69 * 4) * world, "ms_per_step": ms_host / a.steps},
+            "gpu_launches": int(launches_per_step * a.steps), "clocks": clk, "roofline": roof,
+            "cpu_baseline": cpu,
+            "tensor_util_whole_step": (16 * flops_per_launch * world * a.steps / (ms_dev * 1e-3)) * 1e-12
+            / (peak * world)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,129 @@
+/* hgru_b200.h -- C ABI of the B200-native hGRU-pose forward (libhgru_b200.so).
+ *
+ * The reference (krg-nandu/monkey-pose) is pure Python/TensorFlow and has no FFI; this header is
+ * the drop-in boundary a maintainer binds (ctypes) in place of the TF graph
+ * nodes the two reference classes build.  Every entry point cites the reference interface it
+ * replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - all tensors are dense row-major float32; activations NHWC, conv weights HWIO (TF layout);
+ *   - `*_dev` pointers are CUDA device pointers, `*_host` pointers are host memory (pinned
+ *     recommended); nothing here takes torch / framework types;
+ *   - `stream` is a cudaStream_t passed as void* (0 = default stream); calls are asynchronous and
+ *     stream-ordered unless stated otherwise;
+ *   - every function returns 0 on success, non-zero on failure (HGRU_E_*); the message of the
+ *     last failure on the calling thread is available from hgru_last_error(); nothing aborts;
+ *   - one plan per GPU; a plan is not re-entrant (use it from one thread / stream at a time).
+ */
+#ifndef HGRU_B200_H_
+#define HGRU_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define HGRU_API __attribute__((visibility("default")))
+#else
+#define HGRU_API
+#endif
+
+#define HGRU_OK 0
+#define HGRU_E_INVALID 1      /* bad shape / argument                                  */
+#define HGRU_E_UNSUPPORTED 2  /* option the kernels do not implement                   */
+#define HGRU_E_CUDA 3         /* CUDA runtime / driver error (see hgru_last_error)     */
+#define HGRU_E_STATE 4        /* call order violation (e.g. forward before set_params) */
+
+/* arithmetic of the horizontal convolutions (everything else is fp32 in every mode) */
+#define HGRU_MODE_FP32 0 /* fp32 SIMT FFMA: the <= 1e-4 parity path                                */
+#define HGRU_MODE_BF16 1 /* tcgen05 tensor cores, bf16 operands, fp32 accumulate + fp32 state      */
+
+typedef struct hgru_plan_s* hgru_plan_t;
+typedef struct pose_plan_s* pose_plan_t;
+
+HGRU_API const char* hgru_last_error(void);
+HGRU_API int hgru_version(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Recurrent layer: replaces hgru_module.ContextualCircuit (hgru_module.py:54-959) on the path
+ * hgru_pose.py configures (aux dict hgru_pose.py:20-39: tanh, gru_gates, multiplicative_excitation,
+ * gamma, adapation; 'alternate' integration).
+ * ------------------------------------------------------------------------------------------ */
+
+/* ContextualCircuit.__init__ (hgru_module.py:61-128): static shape [N,H,W,k] of X (:74),
+ * S = SSF_ext = 2*floor(SSF/2)+1 (:94-97), T = timesteps.  Allocates all workspace. */
+HGRU_API int hgru_plan_create(int N, int H, int W, int k, int S, int T, int mode, hgru_plan_t* out);
+HGRU_API int hgru_plan_destroy(hgru_plan_t plan);
+
+/* prepare_tensors (hgru_module.py:172-503): the variables of scope `contextual_circuit`.
+ * p_r [S,S,k,k]; i_r, o_r [1,1,k,k]; i_b, o_b, beta, nu, gamma, kappa, omega, lateral_bias
+ * [1,1,1,k]; rho [T].  Device pointers; copied/packed into plan-owned storage. */
+HGRU_API int hgru_set_params(hgru_plan_t plan, const float* p_r_dev, const float* i_r_dev,
+                    const float* i_b_dev, const float* o_r_dev, const float* o_b_dev,
+                    const float* beta_dev, const float* nu_dev, const float* gamma_dev,
+                    const float* kappa_dev, const float* omega_dev, const float* rho_dev,
+                    const float* lateral_bias_dev, void* stream);
+
+/* build() (hgru_module.py:872-959): T iterations of `full` (:825-857).
+ * X, H2_init, H2_out: [N,H,W,k].  H2_init is the reference's O_0 (:884-887), explicit here.
+ * H1_trace / H2_trace: NULL or [T,N,H,W,k] buffers receiving I / O after every timestep. */
+HGRU_API int hgru_forward(hgru_plan_t plan, const float* X_dev, const float* H2_init_dev, float* H2_out_dev,
+                 float* H1_trace_dev, float* H2_trace_dev, void* stream);
+
+HGRU_API size_t hgru_plan_workspace_bytes(hgru_plan_t plan);
+/* number of kernels the last hgru_forward launched */
+HGRU_API int hgru_plan_launch_count(hgru_plan_t plan);
+
+/* ------------------------------------------------------------------------------------------
+ * Pose model: replaces hgru_pose.model.build (hgru_pose.py:47-105), inference-mode batch norm.
+ * ------------------------------------------------------------------------------------------ */
+
+/* Variables of hgru_pose.model by their reference names (hgru_pose.py:165-194, tf.layers BN
+ * scopes batch_normalization[_1.._4]); all device pointers. */
+typedef struct pose_params_s {
+  const float *conv_1_filters, *conv_1_biases; /* [3,3,1,C], [C]   hgru_pose.py:50  */
+  const float *conv_2_filters, *conv_2_biases; /* [3,3,C,C], [C]   hgru_pose.py:61  */
+  const float *conv_3_filters, *conv_3_biases; /* [3,3,C,C], [C]   hgru_pose.py:71  */
+  const float *fc_1_weights, *fc_1_biases;     /* [HW*C,F], [F]    hgru_pose.py:91  */
+  const float *fc_out_weights, *fc_out_biases; /* [F,O], [O]       hgru_pose.py:104 */
+  /* batch_normalization, _1, _2, _3 (C channels each), _4 (F): gamma, beta, moving_mean,
+   * moving_variance  (hgru_pose.py:52-60, 62-70, 72-80, 82-90, 95-103) */
+  const float* bn[5][4];
+  /* contextual_circuit/* (hgru_module.py:262-503), same order as hgru_set_params */
+  const float *p_r, *i_r, *i_b, *o_r, *o_b, *beta, *nu, *gamma, *kappa, *omega, *rho, *lateral_bias;
+} pose_params_t;
+
+/* model.__init__ (hgru_pose.py:8-39) + the static shapes of build(): N frames of
+ * [2*HW, 2*HW, 1] depth; C = stem / hidden channels (64 in the reference); S = SSF = 15;
+ * T = timesteps = 8; F = fc_1 width (1024); O = output_shape (69). */
+HGRU_API int pose_plan_create(int N, int HW, int C, int S, int T, int F, int O, int mode, pose_plan_t* out);
+HGRU_API int pose_plan_destroy(pose_plan_t plan);
+HGRU_API int pose_set_params(pose_plan_t plan, const pose_params_t* params, float bn_epsilon, void* stream);
+
+/* model.build -> self.out_put (hgru_pose.py:47-105).  depth [N,2HW,2HW,1], H2_init [N,HW,HW,C]
+ * (NULL = zeros, the reference's hidden_init='zeros'), out [N,O]. */
+HGRU_API int pose_forward(pose_plan_t plan, const float* depth_dev, const float* H2_init_dev, float* out_dev,
+                 void* stream);
+/* Same through host buffers: H2D copy of depth, forward, D2H copy of out, stream-synchronised
+ * on return.  H2_init stays a device pointer (it is state, not per-frame input). */
+HGRU_API int pose_forward_host(pose_plan_t plan, const float* depth_host, const float* H2_init_dev,
+                      float* out_host, void* stream);
+
+/* Intermediate activations of the last pose_forward, by the reference's attribute names
+ * ("pool1","conv2","conv3","hgru","fc1"; hgru_pose.py:50-105), copied into dst_dev in the
+ * reference's layout ([N,HW,HW,C] / [N,F]).  For parity tests. */
+HGRU_API int pose_get_activation(pose_plan_t plan, const char* name, float* dst_dev, void* stream);
+
+HGRU_API size_t pose_plan_workspace_bytes(pose_plan_t plan);
+HGRU_API int pose_plan_launch_count(pose_plan_t plan);
+/* average device time (ms) of the horizontal-conv kernels in the last pose_forward/hgru_forward
+ * when timing was enabled with hgru_enable_kernel_timing(plan-independent switch) */
+HGRU_API int hgru_enable_kernel_timing(int on);
+HGRU_API int pose_plan_kernel_times(pose_plan_t plan, float* hconv_ms_total, int* hconv_launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HGRU_B200_H_ */

@@ -1,3 +1,11 @@
+"""Public surface of the package: the two reference classes, re-implemented on sm_100a kernels."""
+from . import _lib  # noqa: F401
+from . import hgru_module  # noqa: F401
+from . import hgru_pose  # noqa: F401
 from . import initialization  # noqa: F401
+from . import sharding  # noqa: F401
+from .hgru_module import ContextualCircuit, auxilliary_variables  # noqa: F401
+from .hgru_pose import model  # noqa: F401
 
-__all__ = ["initialization"]
+__all__ = ["ContextualCircuit", "auxilliary_variables", "model", "initialization", "hgru_module",
+           "hgru_pose", "sharding", "_lib"]

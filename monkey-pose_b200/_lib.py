@@ -1,0 +1,89 @@
+"""ctypes binding of libhgru_b200.so (include/hgru_b200.h).  No torch types cross the boundary:
+tensors are passed as raw device / host pointers plus the CUDA stream handle.
+
+There is no CPU fallback: if the shared library is missing this module raises at import of the
+symbol table, and every compute call needs a CUDA device."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhgru_b200.so")
+
+MODE_FP32 = 0
+MODE_BF16 = 1
+MODES = {"fp32": MODE_FP32, "bf16": MODE_BF16}
+
+HGRU_PARAM_ORDER = ("p_r", "i_r", "i_b", "o_r", "o_b", "beta", "nu", "gamma", "kappa", "omega",
+                    "rho", "lateral_bias")
+
+_c_float_p = ctypes.c_void_p      # raw addresses (device or host)
+
+
+class PoseParams(ctypes.Structure):
+    """pose_params_t of include/hgru_b200.h (same field order)."""
+    _fields_ = ([(n, ctypes.c_void_p) for n in (
+        "conv_1_filters", "conv_1_biases", "conv_2_filters", "conv_2_biases",
+        "conv_3_filters", "conv_3_biases", "fc_1_weights", "fc_1_biases",
+        "fc_out_weights", "fc_out_biases")]
+        + [("bn", (ctypes.c_void_p * 4) * 5)]
+        + [(n, ctypes.c_void_p) for n in HGRU_PARAM_ORDER])
+
+
+# every symbol include/hgru_b200.h declares: name -> (restype, argtypes)
+_P = ctypes.c_void_p
+_I = ctypes.c_int
+SIGNATURES = {
+    "hgru_last_error": (ctypes.c_char_p, []),
+    "hgru_version": (_I, []),
+    "hgru_plan_create": (_I, [_I, _I, _I, _I, _I, _I, _I, ctypes.POINTER(_P)]),
+    "hgru_plan_destroy": (_I, [_P]),
+    "hgru_set_params": (_I, [_P] + [_P] * 12 + [_P]),
+    "hgru_forward": (_I, [_P, _P, _P, _P, _P, _P, _P]),
+    "hgru_plan_workspace_bytes": (ctypes.c_size_t, [_P]),
+    "hgru_plan_launch_count": (_I, [_P]),
+    "pose_plan_create": (_I, [_I, _I, _I, _I, _I, _I, _I, _I, ctypes.POINTER(_P)]),
+    "pose_plan_destroy": (_I, [_P]),
+    "pose_set_params": (_I, [_P, ctypes.POINTER(PoseParams), ctypes.c_float, _P]),
+    "pose_forward": (_I, [_P, _P, _P, _P, _P]),
+    "pose_forward_host": (_I, [_P, _P, _P, _P, _P]),
+    "pose_get_activation": (_I, [_P, ctypes.c_char_p, _P, _P]),
+    "pose_plan_workspace_bytes": (ctypes.c_size_t, [_P]),
+    "pose_plan_launch_count": (_I, [_P]),
+    "hgru_enable_kernel_timing": (_I, [_I]),
+    "pose_plan_kernel_times": (_I, [_P, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_I)]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once) and type its entry points.  Fails loudly when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "libhgru_b200.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C monkey-pose_b200/csrc` (needs nvcc, sm_100a). There is no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the export is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class HgruError(RuntimeError):
+    pass
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().hgru_last_error()
+        text = msg.decode() if msg else ""
+        if rc == 2:
+            raise NotImplementedError("%s: %s" % (what, text))
+        if rc == 1:
+            raise ValueError("%s: %s" % (what, text))
+        raise HgruError("%s failed (code %d): %s" % (what, rc, text))

@@ -101,12 +101,12 @@ int run_case(int N, int H, int W, int k, int grid_override, int iters) {
   if (rc) { printf("tensor map encode failed rc=%d\n", rc); return 1; }
 
   hgru::TcConvArgs a;
-  a.N = N; a.H = H; a.W = W; a.k = k;
+  a.N = N; a.H = H; a.W = W; a.KP = k; a.kreal = k; a.scale = nullptr; a.shift = nullptr; a.out_bf16 = nullptr;
   a.units_x = (W + 8 * TILES_X - 1) / (8 * TILES_X);
   a.units_y = (H + hgru::kTileRows - 1) / hgru::kTileRows;
   a.num_units = N * a.units_x * a.units_y;
   a.wpk = d_wpk; a.bias = d_bias; a.out = d_out;
-  auto kern = hgru::hconv_tc_kernel<S, KSTEPS, CO_PAD, TILES_X, G, WSTAGES>;
+  auto kern = hgru::hconv_tc_kernel<S, KSTEPS, CO_PAD, TILES_X, G, WSTAGES, hgru::EpiBias>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
   int sms = 0;
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));

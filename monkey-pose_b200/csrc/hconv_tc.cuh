@@ -58,15 +58,62 @@ struct TcConvCfg {
 
 struct TcConvArgs {
   int N, H, W;              // frames, image height / width
-  int k;                    // real channel count (<= CO_PAD); output row pitch
+  int KP;                   // padded channel count of the fp32 NHWC tensors (== CO_PAD)
+  int kreal;                // real channel count (pad channels are written as zero)
   int units_x, units_y;     // units per frame
   int num_units;
   const __nv_bfloat16* wpk; // packed weights [KSTEPS][taps][2][CO_PAD][8]
-  const float* bias;        // [k] or nullptr
-  float* out;               // fp32 NHWC [N][H][W][k]
+  const float* bias;        // [KP] lateral bias / conv bias (zero padded)
+  const float* scale;       // [KP] (EpiBiasReluAffine) batch-norm scale, zero padded
+  const float* shift;       // [KP]
+  float* out;               // fp32 NHWC [N][H][W][KP]
+  __nv_bfloat16* out_bf16;  // optional bf16 chunked copy [N][KP/8][H][W][8]
 };
 
-template <int S, int KSTEPS, int CO_PAD, int TILES_X, int G, int WSTAGES>
+// ---- epilogue functors: consume one pixel's CO_PAD accumulators --------------------------------
+// out = acc + bias                       (P = conv + lateral_bias, hgru_module.py:657)
+struct EpiBias {
+  template <int CO_PAD>
+  __device__ static __forceinline__ void apply(const TcConvArgs& a, int n, int y, int x,
+                                               float (&acc)[CO_PAD]) {
+    float* dst = a.out + ((static_cast<size_t>(n) * a.H + y) * a.W + x) * a.KP;
+#pragma unroll
+    for (int c = 0; c < CO_PAD; c += 4) {
+      const float4 b = *reinterpret_cast<const float4*>(a.bias + c);
+      *reinterpret_cast<float4*>(dst + c) =
+          make_float4(acc[c] + b.x, acc[c + 1] + b.y, acc[c + 2] + b.z, acc[c + 3] + b.w);
+    }
+  }
+};
+// out = relu(acc + bias) * scale + shift  (conv_layer + inference batch-norm, hgru_pose.py:61-80),
+// fp32 NHWC plus the bf16 chunked operand copy for the next tensor-core conv.
+struct EpiBiasReluAffine {
+  template <int CO_PAD>
+  __device__ static __forceinline__ void apply(const TcConvArgs& a, int n, int y, int x,
+                                               float (&acc)[CO_PAD]) {
+    const size_t pin = static_cast<size_t>(y) * a.W + x;
+    float* dst = a.out + (static_cast<size_t>(n) * a.H * a.W + pin) * a.KP;
+#pragma unroll
+    for (int c = 0; c < CO_PAD; c += 8) {
+      float r[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        r[j] = fmaxf(acc[c + j] + a.bias[c + j], 0.f) * a.scale[c + j] + a.shift[c + j];
+      *reinterpret_cast<float4*>(dst + c) = make_float4(r[0], r[1], r[2], r[3]);
+      *reinterpret_cast<float4*>(dst + c + 4) = make_float4(r[4], r[5], r[6], r[7]);
+      if (a.out_bf16) {
+        __nv_bfloat162 h[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(r[2 * j], r[2 * j + 1]);
+        __nv_bfloat16* o = a.out_bf16 +
+            ((static_cast<size_t>(n) * (a.KP >> 3) + (c >> 3)) * (a.H * a.W) + pin) * 8;
+        *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(h);
+      }
+    }
+  }
+};
+
+template <int S, int KSTEPS, int CO_PAD, int TILES_X, int G, int WSTAGES, class Epi>
 __global__ void __launch_bounds__(256, 1)
 hconv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const TcConvArgs a) {
   using namespace sm100;
@@ -210,22 +257,18 @@ hconv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const TcConvArgs a) 
       for (int t = 0; t < TILES_X; ++t) {
         const int x = ux * (8 * TILES_X) + t * 8 + pcol;
         const bool ok = (y < a.H) && (x < a.W);
-        float* dst = a.out + (static_cast<size_t>(n) * a.H * a.W + static_cast<size_t>(y) * a.W + x) * a.k;
         const uint32_t taddr =
             tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + s * Cfg::kAccCols + t * CO_PAD;
+        float acc[CO_PAD];
 #pragma unroll
         for (int c0 = 0; c0 < CO_PAD; c0 += 16) {
           uint32_t v[16];
           tmem_ld16(taddr + c0, v);
           tmem_ld_wait();
-          if (ok) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int c = c0 + j;
-              if (c < a.k) dst[c] = __uint_as_float(v[j]) + (a.bias ? a.bias[c] : 0.f);
-            }
-          }
+          for (int j = 0; j < 16; ++j) acc[c0 + j] = __uint_as_float(v[j]);
         }
+        if (ok) Epi::template apply<CO_PAD>(a, n, y, x, acc);
       }
       tc_fence_before();
       mbar_arrive(bar_acc_empty + 8 * s);

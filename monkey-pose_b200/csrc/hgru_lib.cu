@@ -1,0 +1,653 @@
+// libhgru_b200.so -- plans, parameter packing, kernel orchestration and the C ABI declared in
+// include/hgru_b200.h.  Pure CUDA runtime; no framework types cross this boundary.
+#include "../../include/hgru_b200.h"
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "hconv_tc.cuh"
+#include "simt_kernels.cuh"
+#include "tc_host.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+int g_timing = 0;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                        \
+  do {                                                                                        \
+    cudaError_t e_ = (expr);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(HGRU_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));           \
+  } while (0)
+
+inline unsigned nblk(size_t n, int b = 256) { return static_cast<unsigned>((n + b - 1) / b); }
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int alloc(size_t b) {
+    bytes = b;
+    cudaError_t e = cudaMalloc(&p, b ? b : 16);
+    if (e != cudaSuccess) return fail(HGRU_E_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+  }
+  template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+// ---------------------------------------------------------------- tensor-core conv dispatch
+template <int S, int KSTEPS, int CO_PAD, int TILES_X, int G, class Epi>
+int launch_tc(const CUtensorMap& map, hgru::TcConvArgs a, cudaStream_t st) {
+  using Cfg = hgru::TcConvCfg<S, KSTEPS, CO_PAD, TILES_X, G, 4>;
+  auto kern = hgru::hconv_tc_kernel<S, KSTEPS, CO_PAD, TILES_X, G, 4, Epi>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  a.units_x = (a.W + 8 * TILES_X - 1) / (8 * TILES_X);
+  a.units_y = (a.H + hgru::kTileRows - 1) / hgru::kTileRows;
+  a.num_units = a.N * a.units_x * a.units_y;
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int grid = a.num_units < sms ? a.num_units : sms;
+  kern<<<grid, 256, Cfg::kSmemBytes, st>>>(map, a);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+struct TcGeom { int tiles_x, box_cols, box_rows; };
+// geometry of the window box for a given (S, KP): must match the template instances below
+bool tc_geometry(int S, int KP, TcGeom* g) {
+  if (!(S == 1 || S == 3 || S == 5 || S == 7 || S == 15)) return false;
+  if (!(KP == 16 || KP == 32 || KP == 64)) return false;
+  g->tiles_x = (KP == 64) ? 4 : 8;
+  g->box_cols = 8 * g->tiles_x + S - 1;
+  g->box_rows = hgru::kTileRows + S - 1;
+  return true;
+}
+
+template <class Epi>
+int dispatch_tc(int S, int KP, const CUtensorMap& map, const hgru::TcConvArgs& a, cudaStream_t st) {
+#define TC_CASE(S_, KP_, KS_, TX_, G_) \
+  if (S == S_ && KP == KP_) return launch_tc<S_, KS_, KP_, TX_, G_, Epi>(map, a, st);
+  TC_CASE(15, 64, 4, 4, 5)
+  TC_CASE(15, 32, 2, 8, 15)
+  TC_CASE(15, 16, 1, 8, 15)
+  TC_CASE(7, 64, 4, 4, 7)
+  TC_CASE(7, 32, 2, 8, 7)
+  TC_CASE(7, 16, 1, 8, 7)
+  TC_CASE(5, 64, 4, 4, 5)
+  TC_CASE(5, 32, 2, 8, 5)
+  TC_CASE(5, 16, 1, 8, 5)
+  TC_CASE(3, 64, 4, 4, 9)
+  TC_CASE(3, 32, 2, 8, 9)
+  TC_CASE(3, 16, 1, 8, 9)
+  TC_CASE(1, 64, 4, 4, 1)
+  TC_CASE(1, 32, 2, 8, 1)
+  TC_CASE(1, 16, 1, 8, 1)
+#undef TC_CASE
+  return fail(HGRU_E_UNSUPPORTED, "tensor-core conv: unsupported (S, padded channels)");
+}
+
+template <int S>
+int launch_simt_conv(const float* in, const float* w, const float* bias, const float* scale,
+                     const float* shift, float* out, int N, int H, int W, int Ci, int Co, int relu,
+                     cudaStream_t st) {
+  using Cfg = hgru::ConvSimtCfg<S>;
+  auto kern = hgru::conv_simt_kernel<S>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  dim3 grid(((W + 15) / 16) * ((H + 15) / 16), (Co + 63) / 64, N);
+  kern<<<grid, 256, Cfg::kSmemBytes, st>>>(in, w, bias, scale, shift, out, N, H, W, Ci, Co, relu);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int dispatch_simt_conv(int S, const float* in, const float* w, const float* bias, const float* scale,
+                       const float* shift, float* out, int N, int H, int W, int Ci, int Co, int relu,
+                       cudaStream_t st) {
+  switch (S) {
+    case 1: return launch_simt_conv<1>(in, w, bias, scale, shift, out, N, H, W, Ci, Co, relu, st);
+    case 3: return launch_simt_conv<3>(in, w, bias, scale, shift, out, N, H, W, Ci, Co, relu, st);
+    case 5: return launch_simt_conv<5>(in, w, bias, scale, shift, out, N, H, W, Ci, Co, relu, st);
+    case 7: return launch_simt_conv<7>(in, w, bias, scale, shift, out, N, H, W, Ci, Co, relu, st);
+    case 9: return launch_simt_conv<9>(in, w, bias, scale, shift, out, N, H, W, Ci, Co, relu, st);
+    case 11: return launch_simt_conv<11>(in, w, bias, scale, shift, out, N, H, W, Ci, Co, relu, st);
+    case 13: return launch_simt_conv<13>(in, w, bias, scale, shift, out, N, H, W, Ci, Co, relu, st);
+    case 15: return launch_simt_conv<15>(in, w, bias, scale, shift, out, N, H, W, Ci, Co, relu, st);
+    default: return fail(HGRU_E_UNSUPPORTED, "conv: filter size must be odd and <= 15");
+  }
+}
+
+// copies a [rows][k] (or [k]) fp32 device array into a zero-padded [rows][KP] one
+__global__ void pad_matrix_kernel(const float* in, float* out, int rows, int k, int KP, int rows_pad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows_pad * KP) return;
+  const int c = i % KP, r = i / KP;
+  out[i] = (r < rows && c < k) ? in[static_cast<size_t>(r) * k + c] : 0.f;
+}
+// HWIO [taps][k][k] -> [taps][KP][KP] zero padded
+__global__ void pad_hwio_kernel(const float* in, float* out, int taps, int k, int KP) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= static_cast<size_t>(taps) * KP * KP) return;
+  const int co = i % KP;
+  const int ci = (i / KP) % KP;
+  const int t = i / (static_cast<size_t>(KP) * KP);
+  out[i] = (ci < k && co < k) ? in[(static_cast<size_t>(t) * k + ci) * k + co] : 0.f;
+}
+
+struct KernelTimer {
+  std::vector<cudaEvent_t> ev;
+  int used = 0;
+  void begin(cudaStream_t st) {
+    if (!g_timing) return;
+    while (static_cast<int>(ev.size()) < used + 2) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      ev.push_back(e);
+    }
+    cudaEventRecord(ev[used], st);
+  }
+  void end(cudaStream_t st) {
+    if (!g_timing) return;
+    cudaEventRecord(ev[used + 1], st);
+    used += 2;
+  }
+  void reset() { used = 0; }
+  int collect(float* total_ms) {
+    float t = 0.f;
+    for (int i = 0; i + 1 < used; i += 2) {
+      cudaEventSynchronize(ev[i + 1]);
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+      t += ms;
+    }
+    *total_ms = t;
+    return used / 2;
+  }
+  ~KernelTimer() {
+    for (auto e : ev) cudaEventDestroy(e);
+  }
+};
+
+}  // namespace
+
+// =================================================================================================
+// hGRU plan
+// =================================================================================================
+struct hgru_plan_s {
+  int N, H, W, k, KP, CG, S, T, mode;
+  size_t npix, nelem;        // pixels, padded elements
+  bool params_set = false;
+  int launches = 0;
+  // parameters (zero padded to KP)
+  DevBuf p_r, i_r, o_r, vecs, rho, wpk;   // vecs: 8 x [KP]: i_b o_b beta nu gamma kappa omega lateral_bias
+  // activations, fp32 [N,H,W,KP]
+  DevBuf Xp, H2, H1, C, G, A;
+  // bf16 chunked operand copies (tensor-core mode)
+  DevBuf actA, actH1;
+  CUtensorMap mapA, mapH1;
+  KernelTimer timer;
+  float* vec(int i) const { return vecs.as<float>() + static_cast<size_t>(i) * KP; }
+  size_t workspace() const {
+    return p_r.bytes + i_r.bytes + o_r.bytes + vecs.bytes + rho.bytes + wpk.bytes + Xp.bytes +
+           H2.bytes + H1.bytes + C.bytes + G.bytes + A.bytes + actA.bytes + actH1.bytes;
+  }
+};
+
+enum { V_IB = 0, V_OB, V_BETA, V_NU, V_GAMMA, V_KAPPA, V_OMEGA, V_LBIAS };
+
+static int hgru_plan_init(hgru_plan_s* p, int N, int H, int W, int k, int S, int T, int mode) {
+  if (N < 1 || H < 1 || W < 1 || k < 1 || T < 1) return fail(HGRU_E_INVALID, "hgru_plan_create: non-positive shape");
+  if (S < 1 || (S % 2) == 0 || S > 15) return fail(HGRU_E_UNSUPPORTED, "hgru_plan_create: S must be odd and <= 15");
+  if (mode != HGRU_MODE_FP32 && mode != HGRU_MODE_BF16) return fail(HGRU_E_UNSUPPORTED, "hgru_plan_create: unknown mode");
+  p->N = N; p->H = H; p->W = W; p->k = k; p->S = S; p->T = T; p->mode = mode;
+  p->KP = round_up(k, 16);
+  p->CG = p->KP / 8;
+  p->npix = static_cast<size_t>(N) * H * W;
+  p->nelem = p->npix * p->KP;
+  int rc = 0;
+  const size_t act = p->nelem * sizeof(float);
+  if ((rc = p->Xp.alloc(act)) || (rc = p->H2.alloc(act)) || (rc = p->H1.alloc(act)) ||
+      (rc = p->C.alloc(act)) || (rc = p->G.alloc(act)))
+    return rc;
+  if ((rc = p->i_r.alloc(sizeof(float) * p->KP * p->KP)) || (rc = p->o_r.alloc(sizeof(float) * p->KP * p->KP)) ||
+      (rc = p->vecs.alloc(sizeof(float) * 8 * p->KP)) || (rc = p->rho.alloc(sizeof(float) * T)))
+    return rc;
+  if (mode == HGRU_MODE_FP32) {
+    if ((rc = p->A.alloc(act)) || (rc = p->p_r.alloc(sizeof(float) * S * S * p->KP * p->KP))) return rc;
+  } else {
+    TcGeom g;
+    if (!tc_geometry(S, p->KP, &g))
+      return fail(HGRU_E_UNSUPPORTED, "hgru_plan_create: bf16 mode supports S in {1,3,5,7,15} and k <= 64");
+    const size_t ab = p->nelem * sizeof(__nv_bfloat16);
+    if ((rc = p->actA.alloc(ab)) || (rc = p->actH1.alloc(ab))) return rc;
+    const int ksteps = p->KP / 16;
+    if ((rc = p->wpk.alloc(sizeof(__nv_bfloat16) * ksteps * S * S * 2 * p->KP * 8))) return rc;
+    if (hgru::make_act_tensor_map(&p->mapA, p->actA.p, N, p->CG, H, W, g.box_cols, g.box_rows) ||
+        hgru::make_act_tensor_map(&p->mapH1, p->actH1.p, N, p->CG, H, W, g.box_cols, g.box_rows))
+      return fail(HGRU_E_CUDA, "cuTensorMapEncodeTiled failed");
+  }
+  return 0;
+}
+
+static void hgru_plan_free(hgru_plan_s* p) {
+  DevBuf* all[] = {&p->p_r, &p->i_r, &p->o_r, &p->vecs, &p->rho, &p->wpk, &p->Xp, &p->H2,
+                   &p->H1, &p->C, &p->G, &p->A, &p->actA, &p->actH1};
+  for (auto b : all) b->release();
+}
+
+static int hgru_set_params_impl(hgru_plan_s* p, const float* p_r, const float* i_r, const float* i_b,
+                                const float* o_r, const float* o_b, const float* beta, const float* nu,
+                                const float* gamma, const float* kappa, const float* omega,
+                                const float* rho, const float* lateral_bias, cudaStream_t st) {
+  const float* ptrs[] = {p_r, i_r, i_b, o_r, o_b, beta, nu, gamma, kappa, omega, rho, lateral_bias};
+  for (auto q : ptrs)
+    if (!q) return fail(HGRU_E_INVALID, "hgru_set_params: null parameter pointer");
+  const int k = p->k, KP = p->KP;
+  pad_matrix_kernel<<<nblk(KP * KP), 256, 0, st>>>(i_r, p->i_r.as<float>(), k, k, KP, KP);
+  pad_matrix_kernel<<<nblk(KP * KP), 256, 0, st>>>(o_r, p->o_r.as<float>(), k, k, KP, KP);
+  const float* v[8] = {i_b, o_b, beta, nu, gamma, kappa, omega, lateral_bias};
+  for (int i = 0; i < 8; ++i) pad_matrix_kernel<<<1, 256, 0, st>>>(v[i], p->vec(i), 1, k, KP, 1);
+  CUDA_TRY(cudaMemcpyAsync(p->rho.p, rho, sizeof(float) * p->T, cudaMemcpyDeviceToDevice, st));
+  const int taps = p->S * p->S;
+  if (p->mode == HGRU_MODE_FP32) {
+    pad_hwio_kernel<<<nblk(static_cast<size_t>(taps) * KP * KP), 256, 0, st>>>(p_r, p->p_r.as<float>(), taps, k, KP);
+  } else {
+    const int ksteps = KP / 16;
+    const size_t total = static_cast<size_t>(ksteps) * taps * 2 * KP * 8;
+    hgru::pack_weights_kernel<<<nblk(total), 256, 0, st>>>(p_r, p->wpk.as<__nv_bfloat16>(), taps, k, ksteps, KP);
+  }
+  CUDA_TRY(cudaGetLastError());
+  p->params_set = true;
+  return 0;
+}
+
+// one hconv: C = conv_SxS(src) + lateral_bias   (hgru_module.py:615-624, 657)
+static int hgru_hconv(hgru_plan_s* p, const float* src_fp32, const CUtensorMap* src_map, cudaStream_t st) {
+  p->timer.begin(st);
+  int rc;
+  if (p->mode == HGRU_MODE_FP32) {
+    rc = dispatch_simt_conv(p->S, src_fp32, p->p_r.as<float>(), p->vec(V_LBIAS), nullptr, nullptr,
+                            p->C.as<float>(), p->N, p->H, p->W, p->KP, p->KP, 0, st);
+  } else {
+    hgru::TcConvArgs a{};
+    a.N = p->N; a.H = p->H; a.W = p->W; a.KP = p->KP; a.kreal = p->k;
+    a.wpk = p->wpk.as<__nv_bfloat16>();
+    a.bias = p->vec(V_LBIAS);
+    a.out = p->C.as<float>();
+    rc = dispatch_tc<hgru::EpiBias>(p->S, p->KP, *src_map, a, st);
+  }
+  p->timer.end(st);
+  ++p->launches;
+  return rc;
+}
+
+// The recurrence on padded buffers: X = p->Xp, state in p->H2 (in/out).
+static int hgru_run_padded(hgru_plan_s* p, const float* Xp, float* H1_trace, float* H2_trace, cudaStream_t st) {
+  if (!p->params_set) return fail(HGRU_E_STATE, "hgru_forward before hgru_set_params");
+  const int KP = p->KP, HW = p->H * p->W;
+  const size_t nchunks = p->nelem / 8;
+  const size_t gate_smem = sizeof(float) * (KP * KP + 64 * (KP + 1));
+  const bool tc = p->mode == HGRU_MODE_BF16;
+  p->launches = 0;
+  p->timer.reset();
+  static bool gate_attr = false;
+  if (!gate_attr) {
+    CUDA_TRY(cudaFuncSetAttribute(hgru::gate1x1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    gate_attr = true;
+  }
+  int rc;
+  for (int t = 0; t < p->T; ++t) {
+    // circuit_input (hgru_module.py:692-724): G1, gated copy, C1
+    hgru::gate1x1_kernel<<<nblk(p->npix, 64), 256, gate_smem, st>>>(
+        p->H2.as<float>(), p->i_r.as<float>(), p->vec(V_IB), nullptr, tc ? nullptr : p->A.as<float>(),
+        tc ? p->actA.as<__nv_bfloat16>() : nullptr, p->npix, KP, p->k, HW);
+    ++p->launches;
+    if ((rc = hgru_hconv(p, p->A.as<float>(), &p->mapA, st))) return rc;
+    // input_integration (:795-804)
+    hgru::h1_kernel<<<nblk(nchunks), 256, 0, st>>>(Xp, p->H2.as<float>(), p->C.as<float>(), p->vec(V_BETA),
+                                                  p->vec(V_NU), p->H1.as<float>(),
+                                                  tc ? p->actH1.as<__nv_bfloat16>() : nullptr, nchunks, KP,
+                                                  p->k, HW);
+    ++p->launches;
+    // circuit_output (:726-756): G2, C2
+    hgru::gate1x1_kernel<<<nblk(p->npix, 64), 256, gate_smem, st>>>(
+        p->H1.as<float>(), p->o_r.as<float>(), p->vec(V_OB), p->G.as<float>(), nullptr, nullptr, p->npix, KP,
+        p->k, HW);
+    ++p->launches;
+    if ((rc = hgru_hconv(p, p->H1.as<float>(), &p->mapH1, st))) return rc;
+    // output_integration + rho (:806-823, 847-849)
+    hgru::h2_kernel<<<nblk(nchunks), 256, 0, st>>>(p->H1.as<float>(), p->C.as<float>(), p->G.as<float>(),
+                                                  p->vec(V_GAMMA), p->vec(V_KAPPA), p->vec(V_OMEGA),
+                                                  p->rho.as<float>(), t, p->H2.as<float>(), nchunks, KP, p->k);
+    ++p->launches;
+    if (H1_trace) {
+      hgru::unpad_channels_kernel<<<nblk(p->npix * p->k), 256, 0, st>>>(
+          p->H1.as<float>(), H1_trace + static_cast<size_t>(t) * p->npix * p->k, p->npix, p->k, KP);
+      ++p->launches;
+    }
+    if (H2_trace) {
+      hgru::unpad_channels_kernel<<<nblk(p->npix * p->k), 256, 0, st>>>(
+          p->H2.as<float>(), H2_trace + static_cast<size_t>(t) * p->npix * p->k, p->npix, p->k, KP);
+      ++p->launches;
+    }
+  }
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// =================================================================================================
+// pose plan
+// =================================================================================================
+struct pose_plan_s {
+  int N, HW, C, KP, S, T, F, O, mode;
+  bool params_set = false;
+  int launches = 0;
+  int nsplit = 16;
+  hgru_plan_s hg;
+  DevBuf depth, pool1, conv2, w1, b1, w2, b2, w3, b3, fc1_w, fc1_b, fc2_w, fc2_b, bn, part, fc1, out;
+  DevBuf act_pool1, act_conv2, wpk2, wpk3;         // tensor-core stem
+  CUtensorMap map_pool1, map_conv2;
+  float* bn_scale(int i) const { return bn.as<float>() + static_cast<size_t>(i) * 2 * bnw; }
+  float* bn_shift(int i) const { return bn_scale(i) + bnw; }
+  int bnw = 0;
+  size_t workspace() const {
+    return hg.workspace() + depth.bytes + pool1.bytes + conv2.bytes + w1.bytes + b1.bytes + w2.bytes +
+           b2.bytes + w3.bytes + b3.bytes + fc1_w.bytes + fc1_b.bytes + fc2_w.bytes + fc2_b.bytes +
+           bn.bytes + part.bytes + fc1.bytes + out.bytes + act_pool1.bytes + act_conv2.bytes +
+           wpk2.bytes + wpk3.bytes;
+  }
+};
+
+static void pose_plan_free(pose_plan_s* p) {
+  hgru_plan_free(&p->hg);
+  DevBuf* all[] = {&p->depth, &p->pool1, &p->conv2, &p->w1, &p->b1, &p->w2, &p->b2, &p->w3, &p->b3,
+                   &p->fc1_w, &p->fc1_b, &p->fc2_w, &p->fc2_b, &p->bn, &p->part, &p->fc1, &p->out,
+                   &p->act_pool1, &p->act_conv2, &p->wpk2, &p->wpk3};
+  for (auto b : all) b->release();
+}
+
+static int pose_forward_impl(pose_plan_s* p, const float* depth, const float* H2_init, float* out, cudaStream_t st) {
+  if (!p->params_set) return fail(HGRU_E_STATE, "pose_forward before pose_set_params");
+  if (!depth || !out) return fail(HGRU_E_INVALID, "pose_forward: null pointer");
+  hgru_plan_s* h = &p->hg;
+  const int N = p->N, HW = p->HW, KP = p->KP, C = p->C;
+  const size_t npix = static_cast<size_t>(N) * HW * HW;
+  const bool tc = p->mode == HGRU_MODE_BF16;
+  int rc;
+  p->launches = 0;
+  // conv_1 + relu + pool_1 + BN (hgru_pose.py:50-60)
+  hgru::stem_conv1_pool_bn_kernel<<<nblk(npix * KP), 256, 0, st>>>(
+      depth, p->w1.as<float>(), p->b1.as<float>(), p->bn_scale(0), p->bn_shift(0), p->pool1.as<float>(),
+      tc ? p->act_pool1.as<__nv_bfloat16>() : nullptr, N, HW, HW, C, KP);
+  ++p->launches;
+  // conv_2 + relu + BN (:61-70), conv_3 + relu + BN (:71-80); conv3 output is X of the hGRU
+  if (tc) {
+    hgru::TcConvArgs a{};
+    a.N = N; a.H = HW; a.W = HW; a.KP = KP; a.kreal = C;
+    a.wpk = p->wpk2.as<__nv_bfloat16>(); a.bias = p->b2.as<float>();
+    a.scale = p->bn_scale(1); a.shift = p->bn_shift(1);
+    a.out = p->conv2.as<float>(); a.out_bf16 = p->act_conv2.as<__nv_bfloat16>();
+    if ((rc = dispatch_tc<hgru::EpiBiasReluAffine>(3, KP, p->map_pool1, a, st))) return rc;
+    a.wpk = p->wpk3.as<__nv_bfloat16>(); a.bias = p->b3.as<float>();
+    a.scale = p->bn_scale(2); a.shift = p->bn_shift(2);
+    a.out = h->Xp.as<float>(); a.out_bf16 = nullptr;
+    if ((rc = dispatch_tc<hgru::EpiBiasReluAffine>(3, KP, p->map_conv2, a, st))) return rc;
+  } else {
+    if ((rc = dispatch_simt_conv(3, p->pool1.as<float>(), p->w2.as<float>(), p->b2.as<float>(), p->bn_scale(1),
+                                 p->bn_shift(1), p->conv2.as<float>(), N, HW, HW, KP, KP, 1, st)))
+      return rc;
+    if ((rc = dispatch_simt_conv(3, p->conv2.as<float>(), p->w3.as<float>(), p->b3.as<float>(), p->bn_scale(2),
+                                 p->bn_shift(2), h->Xp.as<float>(), N, HW, HW, KP, KP, 1, st)))
+      return rc;
+  }
+  p->launches += 2;
+  // hGRU (:81, R-D4)
+  if (H2_init) {
+    hgru::pad_channels_kernel<<<nblk(h->nelem), 256, 0, st>>>(H2_init, h->H2.as<float>(), npix, C, KP);
+    ++p->launches;
+  } else {
+    CUDA_TRY(cudaMemsetAsync(h->H2.p, 0, h->H2.bytes, st));
+  }
+  if ((rc = hgru_run_padded(h, h->Xp.as<float>(), nullptr, nullptr, st))) return rc;
+  p->launches += h->launches;
+  // BN (:82-90) folded into the A-operand load of fc_1 (:91); split-K partial sums
+  const int K = HW * HW * C;
+  const int kslice = round_up((K + p->nsplit - 1) / p->nsplit, 16);
+  dim3 g1((p->F + 63) / 64, (N + 63) / 64, p->nsplit);
+  hgru::fc1_splitk_kernel<<<g1, 256, 0, st>>>(h->H2.as<float>(), p->fc1_w.as<float>(), p->bn_scale(3),
+                                              p->bn_shift(3), p->part.as<float>(), N, K, p->F, C, KP, kslice);
+  // + bias, relu (:92), BN (:95-103), fc_out (:104)
+  hgru::fc_tail_kernel<<<N, 256, sizeof(float) * p->F, st>>>(
+      p->part.as<float>(), p->nsplit, p->fc1_b.as<float>(), p->bn_scale(4), p->bn_shift(4),
+      p->fc2_w.as<float>(), p->fc2_b.as<float>(), p->fc1.as<float>(), out, N, p->F, p->O);
+  p->launches += 2;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+const char* hgru_last_error(void) { return g_err.c_str(); }
+int hgru_version(void) { return 100; }
+int hgru_enable_kernel_timing(int on) {
+  g_timing = on ? 1 : 0;
+  return 0;
+}
+
+int hgru_plan_create(int N, int H, int W, int k, int S, int T, int mode, hgru_plan_t* out) {
+  if (!out) return fail(HGRU_E_INVALID, "hgru_plan_create: out is null");
+  *out = nullptr;
+  hgru_plan_s* p = new hgru_plan_s();
+  int rc = hgru_plan_init(p, N, H, W, k, S, T, mode);
+  if (rc) {
+    hgru_plan_free(p);
+    delete p;
+    return rc;
+  }
+  *out = p;
+  return 0;
+}
+
+int hgru_plan_destroy(hgru_plan_t plan) {
+  if (!plan) return 0;
+  hgru_plan_free(plan);
+  delete plan;
+  return 0;
+}
+
+int hgru_set_params(hgru_plan_t plan, const float* p_r, const float* i_r, const float* i_b,
+                    const float* o_r, const float* o_b, const float* beta, const float* nu,
+                    const float* gamma, const float* kappa, const float* omega, const float* rho,
+                    const float* lateral_bias, void* stream) {
+  if (!plan) return fail(HGRU_E_INVALID, "hgru_set_params: null plan");
+  return hgru_set_params_impl(plan, p_r, i_r, i_b, o_r, o_b, beta, nu, gamma, kappa, omega, rho,
+                              lateral_bias, static_cast<cudaStream_t>(stream));
+}
+
+int hgru_forward(hgru_plan_t p, const float* X, const float* H2_init, float* H2_out, float* H1_trace,
+                 float* H2_trace, void* stream) {
+  if (!p) return fail(HGRU_E_INVALID, "hgru_forward: null plan");
+  if (!X || !H2_out) return fail(HGRU_E_INVALID, "hgru_forward: null tensor pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  hgru::pad_channels_kernel<<<nblk(p->nelem), 256, 0, st>>>(X, p->Xp.as<float>(), p->npix, p->k, p->KP);
+  if (H2_init)
+    hgru::pad_channels_kernel<<<nblk(p->nelem), 256, 0, st>>>(H2_init, p->H2.as<float>(), p->npix, p->k, p->KP);
+  else
+    CUDA_TRY(cudaMemsetAsync(p->H2.p, 0, p->H2.bytes, st));
+  int rc = hgru_run_padded(p, p->Xp.as<float>(), H1_trace, H2_trace, st);
+  if (rc) return rc;
+  hgru::unpad_channels_kernel<<<nblk(p->npix * p->k), 256, 0, st>>>(p->H2.as<float>(), H2_out, p->npix, p->k, p->KP);
+  p->launches += 3;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+size_t hgru_plan_workspace_bytes(hgru_plan_t plan) { return plan ? plan->workspace() : 0; }
+int hgru_plan_launch_count(hgru_plan_t plan) { return plan ? plan->launches : 0; }
+
+int pose_plan_create(int N, int HW, int C, int S, int T, int F, int O, int mode, pose_plan_t* out) {
+  if (!out) return fail(HGRU_E_INVALID, "pose_plan_create: out is null");
+  *out = nullptr;
+  if (N < 1 || HW < 1 || C < 1 || F < 1 || O < 1) return fail(HGRU_E_INVALID, "pose_plan_create: non-positive shape");
+  pose_plan_s* p = new pose_plan_s();
+  p->N = N; p->HW = HW; p->C = C; p->S = S; p->T = T; p->F = F; p->O = O; p->mode = mode;
+  int rc = hgru_plan_init(&p->hg, N, HW, HW, C, S, T, mode);
+  const int KP = p->hg.KP;
+  p->KP = KP;
+  p->bnw = F > KP ? F : KP;
+  const size_t act = static_cast<size_t>(N) * HW * HW * KP * sizeof(float);
+  const size_t K = static_cast<size_t>(HW) * HW * C;
+  auto A = [&](DevBuf& b, size_t bytes) { if (!rc) rc = b.alloc(bytes); };
+  A(p->depth, static_cast<size_t>(N) * 4 * HW * HW * sizeof(float));
+  A(p->pool1, act); A(p->conv2, act);
+  A(p->w1, sizeof(float) * 9 * C); A(p->b1, sizeof(float) * KP);
+  A(p->b2, sizeof(float) * KP); A(p->b3, sizeof(float) * KP);
+  A(p->fc1_w, sizeof(float) * K * F); A(p->fc1_b, sizeof(float) * F);
+  A(p->fc2_w, sizeof(float) * F * O); A(p->fc2_b, sizeof(float) * O);
+  A(p->bn, sizeof(float) * 5 * 2 * p->bnw);
+  A(p->part, sizeof(float) * p->nsplit * N * F); A(p->fc1, sizeof(float) * N * F); A(p->out, sizeof(float) * N * O);
+  if (mode == HGRU_MODE_FP32) {
+    A(p->w2, sizeof(float) * 9 * KP * KP); A(p->w3, sizeof(float) * 9 * KP * KP);
+  } else if (!rc) {
+    const size_t ab = static_cast<size_t>(N) * HW * HW * KP * sizeof(__nv_bfloat16);
+    A(p->act_pool1, ab); A(p->act_conv2, ab);
+    const size_t wb = sizeof(__nv_bfloat16) * (KP / 16) * 9 * 2 * KP * 8;
+    A(p->wpk2, wb); A(p->wpk3, wb);
+    TcGeom g;
+    if (!rc && !tc_geometry(3, KP, &g)) rc = fail(HGRU_E_UNSUPPORTED, "pose_plan_create: unsupported channel count for bf16 mode");
+    if (!rc && (hgru::make_act_tensor_map(&p->map_pool1, p->act_pool1.p, N, KP / 8, HW, HW, g.box_cols, g.box_rows) ||
+                hgru::make_act_tensor_map(&p->map_conv2, p->act_conv2.p, N, KP / 8, HW, HW, g.box_cols, g.box_rows)))
+      rc = fail(HGRU_E_CUDA, "cuTensorMapEncodeTiled failed");
+  }
+  if (rc) {
+    pose_plan_free(p);
+    delete p;
+    return rc;
+  }
+  *out = p;
+  return 0;
+}
+
+int pose_plan_destroy(pose_plan_t plan) {
+  if (!plan) return 0;
+  pose_plan_free(plan);
+  delete plan;
+  return 0;
+}
+
+int pose_set_params(pose_plan_t p, const pose_params_t* q, float eps, void* stream) {
+  if (!p || !q) return fail(HGRU_E_INVALID, "pose_set_params: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int C = p->C, KP = p->KP, F = p->F, O = p->O;
+  const float* req[] = {q->conv_1_filters, q->conv_1_biases, q->conv_2_filters, q->conv_2_biases,
+                        q->conv_3_filters, q->conv_3_biases, q->fc_1_weights, q->fc_1_biases,
+                        q->fc_out_weights, q->fc_out_biases};
+  for (auto r : req)
+    if (!r) return fail(HGRU_E_INVALID, "pose_set_params: null parameter pointer");
+  for (int i = 0; i < 5; ++i)
+    for (int j = 0; j < 4; ++j)
+      if (!q->bn[i][j]) return fail(HGRU_E_INVALID, "pose_set_params: null batch-norm pointer");
+  CUDA_TRY(cudaMemcpyAsync(p->w1.p, q->conv_1_filters, sizeof(float) * 9 * C, cudaMemcpyDeviceToDevice, st));
+  pad_matrix_kernel<<<1, 256, 0, st>>>(q->conv_1_biases, p->b1.as<float>(), 1, C, KP, 1);
+  pad_matrix_kernel<<<1, 256, 0, st>>>(q->conv_2_biases, p->b2.as<float>(), 1, C, KP, 1);
+  pad_matrix_kernel<<<1, 256, 0, st>>>(q->conv_3_biases, p->b3.as<float>(), 1, C, KP, 1);
+  if (p->mode == HGRU_MODE_FP32) {
+    pad_hwio_kernel<<<nblk(static_cast<size_t>(9) * KP * KP), 256, 0, st>>>(q->conv_2_filters, p->w2.as<float>(), 9, C, KP);
+    pad_hwio_kernel<<<nblk(static_cast<size_t>(9) * KP * KP), 256, 0, st>>>(q->conv_3_filters, p->w3.as<float>(), 9, C, KP);
+  } else {
+    const size_t total = static_cast<size_t>(KP / 16) * 9 * 2 * KP * 8;
+    hgru::pack_weights_kernel<<<nblk(total), 256, 0, st>>>(q->conv_2_filters, p->wpk2.as<__nv_bfloat16>(), 9, C, KP / 16, KP);
+    hgru::pack_weights_kernel<<<nblk(total), 256, 0, st>>>(q->conv_3_filters, p->wpk3.as<__nv_bfloat16>(), 9, C, KP / 16, KP);
+  }
+  const size_t K = static_cast<size_t>(p->HW) * p->HW * C;
+  CUDA_TRY(cudaMemcpyAsync(p->fc1_w.p, q->fc_1_weights, sizeof(float) * K * F, cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(p->fc1_b.p, q->fc_1_biases, sizeof(float) * F, cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(p->fc2_w.p, q->fc_out_weights, sizeof(float) * F * O, cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(p->fc2_b.p, q->fc_out_biases, sizeof(float) * O, cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(cudaMemsetAsync(p->bn.p, 0, p->bn.bytes, st));
+  for (int i = 0; i < 5; ++i) {
+    const int c = (i == 4) ? F : C;
+    hgru::bn_fold_kernel<<<nblk(c), 256, 0, st>>>(q->bn[i][0], q->bn[i][1], q->bn[i][2], q->bn[i][3], eps,
+                                                  p->bn_scale(i), p->bn_shift(i), c);
+  }
+  CUDA_TRY(cudaGetLastError());
+  int rc = hgru_set_params_impl(&p->hg, q->p_r, q->i_r, q->i_b, q->o_r, q->o_b, q->beta, q->nu, q->gamma,
+                                q->kappa, q->omega, q->rho, q->lateral_bias, st);
+  if (rc) return rc;
+  p->params_set = true;
+  return 0;
+}
+
+int pose_forward(pose_plan_t p, const float* depth, const float* H2_init, float* out, void* stream) {
+  if (!p) return fail(HGRU_E_INVALID, "pose_forward: null plan");
+  return pose_forward_impl(p, depth, H2_init, out, static_cast<cudaStream_t>(stream));
+}
+
+int pose_forward_host(pose_plan_t p, const float* depth_host, const float* H2_init, float* out_host, void* stream) {
+  if (!p) return fail(HGRU_E_INVALID, "pose_forward_host: null plan");
+  if (!depth_host || !out_host) return fail(HGRU_E_INVALID, "pose_forward_host: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(cudaMemcpyAsync(p->depth.p, depth_host, p->depth.bytes, cudaMemcpyHostToDevice, st));
+  int rc = pose_forward_impl(p, p->depth.as<float>(), H2_init, p->out.as<float>(), st);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(out_host, p->out.p, p->out.bytes, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int pose_get_activation(pose_plan_t p, const char* name, float* dst, void* stream) {
+  if (!p || !name || !dst) return fail(HGRU_E_INVALID, "pose_get_activation: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t npix = static_cast<size_t>(p->N) * p->HW * p->HW;
+  const float* src = nullptr;
+  if (!strcmp(name, "pool1")) src = p->pool1.as<float>();
+  else if (!strcmp(name, "conv2")) src = p->conv2.as<float>();
+  else if (!strcmp(name, "conv3")) src = p->hg.Xp.as<float>();
+  else if (!strcmp(name, "hgru")) src = p->hg.H2.as<float>();
+  else if (!strcmp(name, "fc1")) {
+    CUDA_TRY(cudaMemcpyAsync(dst, p->fc1.p, p->fc1.bytes, cudaMemcpyDeviceToDevice, st));
+    return 0;
+  } else return fail(HGRU_E_INVALID, std::string("pose_get_activation: unknown name ") + name);
+  hgru::unpad_channels_kernel<<<nblk(npix * p->C), 256, 0, st>>>(src, dst, npix, p->C, p->KP);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+size_t pose_plan_workspace_bytes(pose_plan_t plan) { return plan ? plan->workspace() : 0; }
+int pose_plan_launch_count(pose_plan_t plan) { return plan ? plan->launches : 0; }
+
+int pose_plan_kernel_times(pose_plan_t plan, float* hconv_ms_total, int* hconv_launches) {
+  if (!plan || !hconv_ms_total || !hconv_launches) return fail(HGRU_E_INVALID, "pose_plan_kernel_times: null argument");
+  *hconv_launches = plan->hg.timer.collect(hconv_ms_total);
+  return 0;
+}
+
+}  // extern "C"

@@ -13,11 +13,6 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf
 // tanh with ~1e-7 relative error (tanhf from libdevice; NOT tanh.approx, the 1e-4 path needs it)
 __device__ __forceinline__ float tanhf_(float x) { return tanhf(x); }
 
-// Writes one bf16 value into the "chunked NHWC" operand copy [n][cg][y][x][8] (see hconv_tc.cuh).
-__device__ __forceinline__ size_t chunked_index(size_t pix_in_frame, int n, int c, int HW, int CG) {
-  return ((static_cast<size_t>(n) * CG + (c >> 3)) * HW + pix_in_frame) * 8 + (c & 7);
-}
-
 // ------------------------------------------------------------------------------------------------
 // Generic direct convolution, stride 1, SAME zero padding, fp32 (tf.nn.conv2d: hgru_module.py:531-548,
 // hgru_pose.py:146), with the epilogue  y = act(conv + bias) * scale + shift  (bias_add + relu of
@@ -141,81 +136,127 @@ __global__ void __launch_bounds__(256)
 stem_conv1_pool_bn_kernel(const float* __restrict__ depth, const float* __restrict__ w /*[3][3][1][C]*/,
                           const float* __restrict__ bias, const float* __restrict__ scale,
                           const float* __restrict__ shift, float* __restrict__ out,
-                          __nv_bfloat16* __restrict__ out_bf16, int N, int H, int W, int C, int CG) {
+                          __nv_bfloat16* __restrict__ out_bf16, int N, int H, int W, int C, int KP) {
   const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-  const size_t total = static_cast<size_t>(N) * H * W * C;
+  const size_t total = static_cast<size_t>(N) * H * W * KP;
   if (idx >= total) return;
-  const int c = idx % C;
-  const size_t p = idx / C;
+  const int c = idx % KP;
+  const size_t p = idx / KP;
   const int x = p % W;
   const int y = (p / W) % H;
   const int n = p / (static_cast<size_t>(W) * H);
   const int IH = 2 * H, IW = 2 * W;
-  float wv[9];
+  float r = 0.f;
+  if (c < C) {
+    float wv[9];
 #pragma unroll
-  for (int t = 0; t < 9; ++t) wv[t] = w[t * C + c];
-  // 4x4 input neighbourhood of the 2x2 pooling window
-  float v[4][4];
+    for (int t = 0; t < 9; ++t) wv[t] = w[t * C + c];
+    // 4x4 input neighbourhood of the 2x2 pooling window
+    float v[4][4];
 #pragma unroll
-  for (int r = 0; r < 4; ++r)
+    for (int rr = 0; rr < 4; ++rr)
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int yy = 2 * y - 1 + r, xx = 2 * x - 1 + q;
-      v[r][q] = (yy >= 0 && yy < IH && xx >= 0 && xx < IW)
-                    ? depth[(static_cast<size_t>(n) * IH + yy) * IW + xx] : 0.f;
-    }
-  const float b = bias[c];
-  float m = -INFINITY;
+      for (int q = 0; q < 4; ++q) {
+        const int yy = 2 * y - 1 + rr, xx = 2 * x - 1 + q;
+        v[rr][q] = (yy >= 0 && yy < IH && xx >= 0 && xx < IW)
+                       ? depth[(static_cast<size_t>(n) * IH + yy) * IW + xx] : 0.f;
+      }
+    const float b = bias[c];
+    float m = -INFINITY;
 #pragma unroll
-  for (int py = 0; py < 2; ++py)
+    for (int py = 0; py < 2; ++py)
 #pragma unroll
-    for (int px = 0; px < 2; ++px) {
-      float a = 0.f;
+      for (int px = 0; px < 2; ++px) {
+        float a = 0.f;
 #pragma unroll
-      for (int dy = 0; dy < 3; ++dy)
+        for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-        for (int dx = 0; dx < 3; ++dx) a = fmaf(v[py + dy][px + dx], wv[dy * 3 + dx], a);
-      m = fmaxf(m, fmaxf(a + b, 0.f));
-    }
-  const float r = m * scale[c] + shift[c];
+          for (int dx = 0; dx < 3; ++dx) a = fmaf(v[py + dy][px + dx], wv[dy * 3 + dx], a);
+        m = fmaxf(m, fmaxf(a + b, 0.f));
+      }
+    r = m * scale[c] + shift[c];
+  }
   out[idx] = r;
-  if (out_bf16) out_bf16[chunked_index(static_cast<size_t>(y) * W + x, n, c, H * W, CG)] = __float2bfloat16(r);
+  if (out_bf16)
+    out_bf16[((static_cast<size_t>(n) * (KP >> 3) + (c >> 3)) * (H * W) + static_cast<size_t>(y) * W + x) * 8 + (c & 7)] =
+        __float2bfloat16(r);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Internal activation layout: fp32 NHWC with the channel dimension padded to KP (a multiple of 16,
+// pad channels are zero) so every pixel-chunk of 8 channels is 32 B (fp32) / 16 B (bf16) aligned.
+// Elementwise kernels below: one thread = one pixel-chunk (8 channels).
+// ------------------------------------------------------------------------------------------------
+struct F8 { float v[8]; };
+__device__ __forceinline__ F8 ld8(const float* p) {
+  const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+  return F8{{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w}};
+}
+__device__ __forceinline__ void st8(float* p, const F8& f) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(f.v[0], f.v[1], f.v[2], f.v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(f.v[4], f.v[5], f.v[6], f.v[7]);
+}
+__device__ __forceinline__ void st8_bf16(__nv_bfloat16* p, const F8& f) {
+  __nv_bfloat162 h[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f.v[2 * i], f.v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(h);
+}
+// bf16 chunked operand copy [n][cg][pix][8]: address of chunk cg of pixel `pin` of frame n
+__device__ __forceinline__ __nv_bfloat16* chunk_ptr(__nv_bfloat16* base, int n, int cg, size_t pin,
+                                                    int HW, int CG) {
+  return base + ((static_cast<size_t>(n) * CG + cg) * HW + pin) * 8;
 }
 
 // ------------------------------------------------------------------------------------------------
 // 1x1 gate convolution + sigmoid (hgru_module.py:696-707 and :729-740):
 //   G = sigmoid(in *1x1 wg + bg);  optional gated copy  out_mul = in . G  (:709-711).
-// Block = 64 pixels x k channels; wg [k][k] in shared memory; one thread = one pixel x 8 outputs.
+// Block = 64 pixels; wg [KP][KP] and the pixel tile in shared memory; thread = pixel x 8 outputs.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-gate1x1_kernel(const float* __restrict__ in, const float* __restrict__ wg /*[ci][co]*/,
+gate1x1_kernel(const float* __restrict__ in, const float* __restrict__ wg /*[ci][co] KPxKP*/,
                const float* __restrict__ bg, float* __restrict__ out_g, float* __restrict__ out_mul,
-               __nv_bfloat16* __restrict__ out_mul_bf16, size_t npix, int k, int HW, int CG) {
+               __nv_bfloat16* __restrict__ out_mul_bf16, size_t npix, int KP, int kreal, int HW) {
   extern __shared__ float smem_f[];
-  float* wsm = smem_f;                 // [k][k]
-  float* xin = smem_f + k * k;         // [64][k+1]
+  float* wsm = smem_f;                 // [KP][KP]
+  float* xin = smem_f + KP * KP;       // [64][KP+1]
   const int tid = threadIdx.x;
+  const int CG = KP >> 3;
   const size_t p0 = blockIdx.x * static_cast<size_t>(64);
-  for (int e = tid; e < k * k; e += 256) wsm[e] = wg[e];
-  for (int e = tid; e < 64 * k; e += 256) {
-    const int pp = e / k, c = e - pp * k;
-    xin[pp * (k + 1) + c] = (p0 + pp < npix) ? in[(p0 + pp) * k + c] : 0.f;
+  for (int e = tid; e < KP * KP; e += 256) wsm[e] = wg[e];
+  for (int e = tid; e < 64 * KP; e += 256) {
+    const int pp = e / KP, c = e - pp * KP;
+    xin[pp * (KP + 1) + c] = (p0 + pp < npix) ? in[(p0 + pp) * KP + c] : 0.f;
   }
   __syncthreads();
-  const int pp = tid & 63;             // pixel within block
-  const int og = tid >> 6;             // 0..3: output channels og, og+4, ...
+  const int pp = tid & 63;
   const size_t p = p0 + pp;
   if (p >= npix) return;
   const int n = p / HW;
   const size_t pin = p - static_cast<size_t>(n) * HW;
-  for (int co = og; co < k; co += 4) {
-    float a = 0.f;
-    for (int ci = 0; ci < k; ++ci) a = fmaf(xin[pp * (k + 1) + ci], wsm[ci * k + co], a);
-    const float g = sigmoidf_(a + bg[co]);
-    if (out_g) out_g[p * k + co] = g;
-    const float mv = xin[pp * (k + 1) + co] * g;
-    if (out_mul) out_mul[p * k + co] = mv;
-    if (out_mul_bf16) out_mul_bf16[chunked_index(pin, n, co, HW, CG)] = __float2bfloat16(mv);
+  for (int cg = tid >> 6; cg < CG; cg += 4) {
+    F8 a;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a.v[j] = 0.f;
+    for (int ci = 0; ci < KP; ++ci) {
+      const float xv = xin[pp * (KP + 1) + ci];
+      const float4 w0 = *reinterpret_cast<const float4*>(wsm + ci * KP + cg * 8);
+      const float4 w1 = *reinterpret_cast<const float4*>(wsm + ci * KP + cg * 8 + 4);
+      a.v[0] = fmaf(xv, w0.x, a.v[0]); a.v[1] = fmaf(xv, w0.y, a.v[1]);
+      a.v[2] = fmaf(xv, w0.z, a.v[2]); a.v[3] = fmaf(xv, w0.w, a.v[3]);
+      a.v[4] = fmaf(xv, w1.x, a.v[4]); a.v[5] = fmaf(xv, w1.y, a.v[5]);
+      a.v[6] = fmaf(xv, w1.z, a.v[6]); a.v[7] = fmaf(xv, w1.w, a.v[7]);
+    }
+    F8 g, mv;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = cg * 8 + j;
+      g.v[j] = (c < kreal) ? sigmoidf_(a.v[j] + bg[c]) : 0.f;
+      mv.v[j] = xin[pp * (KP + 1) + c] * g.v[j];
+    }
+    if (out_g) st8(out_g + p * KP + cg * 8, g);
+    if (out_mul) st8(out_mul + p * KP + cg * 8, mv);
+    if (out_mul_bf16) st8_bf16(chunk_ptr(out_mul_bf16, n, cg, pin, HW, CG), mv);
   }
 }
 
@@ -226,67 +267,92 @@ gate1x1_kernel(const float* __restrict__ in, const float* __restrict__ wg /*[ci]
 __global__ void __launch_bounds__(256)
 h1_kernel(const float* __restrict__ X, const float* __restrict__ H2, const float* __restrict__ C1,
           const float* __restrict__ beta, const float* __restrict__ nu, float* __restrict__ H1,
-          __nv_bfloat16* __restrict__ H1_bf16, size_t total, int k, int HW, int CG) {
+          __nv_bfloat16* __restrict__ H1_bf16, size_t nchunks, int KP, int kreal, int HW) {
   const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-  if (i >= total) return;
-  const int c = i % k;
-  const float h1 = tanhf_(X[i] - (beta[c] * H2[i] + nu[c]) * C1[i]);
-  H1[i] = h1;
+  if (i >= nchunks) return;
+  const int CG = KP >> 3;
+  const int cg = i % CG;
+  const size_t p = i / CG;
+  const F8 x = ld8(X + i * 8), h2 = ld8(H2 + i * 8), c1 = ld8(C1 + i * 8);
+  const F8 b = ld8(beta + cg * 8), nv = ld8(nu + cg * 8);
+  F8 h1;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    h1.v[j] = (cg * 8 + j < kreal) ? tanhf_(x.v[j] - (b.v[j] * h2.v[j] + nv.v[j]) * c1.v[j]) : 0.f;
+  st8(H1 + i * 8, h1);
   if (H1_bf16) {
-    const size_t p = i / k;
     const int n = p / HW;
-    H1_bf16[chunked_index(p - static_cast<size_t>(n) * HW, n, c, HW, CG)] = __float2bfloat16(h1);
+    st8_bf16(chunk_ptr(H1_bf16, n, cg, p - static_cast<size_t>(n) * HW, HW, CG), h1);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // output_integration + adaptation (hgru_module.py:806-823, 847-849):
 //   e = gamma*C2; Ht = tanh(kappa*(H1+e) + omega*(H1*e)); H2 = (G2*H2 + (1-G2)*Ht) * rho_t
-// In place on H2; optional trace copies; optional bf16 chunked copy of the new H2.
+// In place on H2; optional trace copies are taken by the caller afterwards.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 h2_kernel(const float* __restrict__ H1, const float* __restrict__ C2, const float* __restrict__ G2,
           const float* __restrict__ gamma, const float* __restrict__ kappa,
           const float* __restrict__ omega, const float* __restrict__ rho, int t,
-          float* __restrict__ H2, __nv_bfloat16* __restrict__ H2_bf16, size_t total, int k, int HW,
-          int CG) {
+          float* __restrict__ H2, size_t nchunks, int KP, int kreal) {
   const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-  if (i >= total) return;
-  const int c = i % k;
-  const float h1 = H1[i];
-  const float e = gamma[c] * C2[i];
-  const float ht = tanhf_(kappa[c] * (h1 + e) + omega[c] * (h1 * e));
-  const float g = G2[i];
-  const float h2 = (g * H2[i] + (1.f - g) * ht) * rho[t];
-  H2[i] = h2;
-  if (H2_bf16) {
-    const size_t p = i / k;
-    const int n = p / HW;
-    H2_bf16[chunked_index(p - static_cast<size_t>(n) * HW, n, c, HW, CG)] = __float2bfloat16(h2);
+  if (i >= nchunks) return;
+  const int CG = KP >> 3;
+  const int cg = i % CG;
+  const F8 h1 = ld8(H1 + i * 8), c2 = ld8(C2 + i * 8), g = ld8(G2 + i * 8), h2 = ld8(H2 + i * 8);
+  const F8 ga = ld8(gamma + cg * 8), ka = ld8(kappa + cg * 8), om = ld8(omega + cg * 8);
+  const float r = rho[t];
+  F8 o;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float e = ga.v[j] * c2.v[j];
+    const float ht = tanhf_(ka.v[j] * (h1.v[j] + e) + om.v[j] * (h1.v[j] * e));
+    o.v[j] = (cg * 8 + j < kreal) ? (g.v[j] * h2.v[j] + (1.f - g.v[j]) * ht) * r : 0.f;
   }
+  st8(H2 + i * 8, o);
 }
 
-// fp32 NHWC -> bf16 chunked operand copy, with optional per-channel affine
+// NHWC [.., k] -> NHWC [.., KP] (zero pad channels) and back; optional per-channel affine on unpad.
 __global__ void __launch_bounds__(256)
-to_chunked_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t total,
-                       int k, int HW, int CG) {
+pad_channels_kernel(const float* __restrict__ in, float* __restrict__ out, size_t npix, int k, int KP) {
   const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-  if (i >= total) return;
+  if (i >= npix * KP) return;
+  const int c = i % KP;
+  const size_t p = i / KP;
+  out[i] = (c < k) ? in[p * k + c] : 0.f;
+}
+__global__ void __launch_bounds__(256)
+unpad_channels_kernel(const float* __restrict__ in, float* __restrict__ out, size_t npix, int k, int KP) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= npix * k) return;
   const int c = i % k;
   const size_t p = i / k;
+  out[i] = in[p * KP + c];
+}
+// fp32 padded NHWC -> bf16 chunked operand copy
+__global__ void __launch_bounds__(256)
+to_chunked_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t nchunks,
+                       int KP, int HW) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= nchunks) return;
+  const int CG = KP >> 3;
+  const int cg = i % CG;
+  const size_t p = i / CG;
   const int n = p / HW;
-  out[chunked_index(p - static_cast<size_t>(n) * HW, n, c, HW, CG)] = __float2bfloat16(in[i]);
+  st8_bf16(chunk_ptr(out, n, cg, p - static_cast<size_t>(n) * HW, HW, CG), ld8(in + i * 8));
 }
 
 // ------------------------------------------------------------------------------------------------
 // Readout FC1 (hgru_pose.py:91,156-163): part[z][m][j] = sum_{kk in slice z} (a[m][kk]*sc[kk%k]+sh[kk%k]) * Wt[kk][j]
+// (a is read from the channel-padded activation buffer; kk enumerates (h, w, c) like tf.reshape)
 // The per-channel affine on A is the inference batch-norm of the hGRU output (:82-90).
 // Split-K SGEMM: block tile 64(m) x 64(j), 256 threads, 4x4 per thread, K step 16.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 fc1_splitk_kernel(const float* __restrict__ A, const float* __restrict__ Wt,
                   const float* __restrict__ sc, const float* __restrict__ sh,
-                  float* __restrict__ part, int M, int K, int Nout, int kch, int kslice) {
+                  float* __restrict__ part, int M, int K, int Nout, int kch, int KP, int kslice) {
   __shared__ float As[16][64 + 4];
   __shared__ float Bs[16][64 + 4];
   const int tid = threadIdx.x;
@@ -304,8 +370,9 @@ fc1_splitk_kernel(const float* __restrict__ A, const float* __restrict__ Wt,
         const int kidx = k0 + kk + q;
         float v = 0.f;
         if (m < M && kidx < ke) {
-          const int c = kidx % kch;
-          v = A[static_cast<size_t>(m) * K + kidx] * sc[c] + sh[c];
+          // A is the channel-padded activation [M][K/kch pixels][KP]; kidx runs over (pixel, real channel)
+          const int pix = kidx / kch, c = kidx - pix * kch;
+          v = A[(static_cast<size_t>(m) * (K / kch) + pix) * KP + c] * sc[c] + sh[c];
         }
         As[kk + q][r] = v;
       }

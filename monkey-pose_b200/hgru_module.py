@@ -1,0 +1,321 @@
+"""B200-native drop-in for the reference's `hgru_module.ContextualCircuit` (hgru_module.py:54-959).
+
+Same constructor keywords, same `build()` return convention, same variable names; tensors are
+torch CUDA tensors (NHWC float32) instead of tf.Tensors and the arithmetic runs in the sm_100a
+kernels of libhgru_b200.so.  Only the path hgru_pose.py configures is implemented; every other
+option the reference declares is accepted as a key and raises NotImplementedError when selected
+(SURVEY.md section 8a, row a19).
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import initialization as init
+
+
+def auxilliary_variables():
+    """Defaults of the reference's auxilliary_variables() (hgru_module.py:9-51).  TensorFlow
+    callables are named by strings here ('tanh', 'sigmoid')."""
+    return {
+        'lesions': [None],
+        'lesion_beta': False,
+        'lesion_nu': False,
+        'lesion_omega': False,
+        'lesion_kappa': False,
+        'dtype': 'float32',
+        'return_weights': True,
+        'hidden_init': 'random',
+        'gate_bias_init': 'chronos',
+        'association_field': True,
+        'tuning_nl': 'tanh',
+        'store_states': False,
+        'train': True,
+        'dropout': None,
+        'recurrent_nl': 'tanh',
+        'gate_nl': 'sigmoid',
+        'ecrf_nl': 'tanh',
+        'normal_initializer': True,
+        'symmetric_weights': True,
+        'symmetric_gate_weights': False,
+        'gru_gates': False,
+        'output_gru_gates': False,
+        'post_tuning_nl': 'tanh',
+        'gate_filter': 1,
+        'zeta': False,
+        'gamma': True,
+        'xi': False,
+        'beta': True,
+        'nu': True,
+        'batch_norm': False,
+        'adapation': False,
+        'integration_type': 'alternate',
+        'dense_connections': False,
+        'atrous_convolutions': False,
+        'multiplicative_excitation': True,
+        'rectify_weights': None,
+    }
+
+
+_PLAN_CACHE = {}
+
+
+def _get_plan(N, H, W, k, S, T, mode):
+    key = (torch.cuda.current_device(), N, H, W, k, S, T, mode)
+    plan = _PLAN_CACHE.get(key)
+    if plan is None:
+        import ctypes
+        lib = _lib.load()
+        h = ctypes.c_void_p()
+        _lib.check(lib.hgru_plan_create(N, H, W, k, S, T, mode, ctypes.byref(h)), "hgru_plan_create")
+        plan = h
+        _PLAN_CACHE[key] = plan
+    return plan
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _as_dev(x, shape=None):
+    t = torch.as_tensor(x, dtype=torch.float32)
+    if not t.is_cuda:
+        t = t.cuda()
+    t = t.contiguous()
+    if shape is not None:
+        t = t.reshape(shape)
+    return t
+
+
+class ContextualCircuit(object):
+    def __getitem__(self, name):
+        return getattr(self, name)
+
+    def __contains__(self, name):
+        return hasattr(self, name)
+
+    def __init__(
+            self,
+            X,
+            timesteps=1,
+            SRF=1,
+            SSN=9,
+            SSF=29,
+            strides=[1, 1, 1, 1],
+            padding='SAME',
+            aux=None,
+            train=True,
+            params=None,
+            hidden_state=None,
+            compute_mode='bf16',
+            seed=42):
+        """Global initializations and settings (hgru_module.py:61-128).
+
+        X: torch CUDA tensor [n,h,w,k] float32 (static batch, hgru_module.py:74).
+        Non-reference keywords: `params` (dict of the `contextual_circuit/*` variables, by their
+        reference names), `hidden_state` (O_0, [n,h,w,k]), `compute_mode` ('fp32' | 'bf16'), `seed`.
+        """
+        if not (torch.is_tensor(X) and X.dim() == 4):
+            raise ValueError("X must be a 4-D torch tensor [n,h,w,k] (CUDA for build())")
+        self.X = X.to(torch.float32).contiguous()
+        self.n, self.h, self.w, self.k = [int(x) for x in X.shape]
+        self.timesteps = timesteps
+        self.strides = strides
+        self.padding = padding
+        self.train = train
+
+        aux_vars = auxilliary_variables()
+        if aux is not None and isinstance(aux, dict):
+            for k, v in aux.items():
+                aux_vars[k] = v
+        self.update_params(aux_vars)
+
+        self.SRF, self.SSN, self.SSF = SRF, SSN, SSF
+        if isinstance(SSF, list):
+            raise NotImplementedError('hierarchical_convolutions (list-valued SSF) are not on the hot path')
+        self.SSF_ext = 2 * int(math.floor(SSF / 2.0)) + 1            # hgru_module.py:94-97
+        if self.SSN is None:
+            self.SSN = self.SRF * 3
+        if self.SSF is None:
+            self.SSF = self.SRF * 5
+
+        self.q_shape = [self.SRF, self.SRF, self.k, self.k]
+        self.u_shape = [self.SRF, self.SRF, self.k, 1]
+        self.p_shape = [self.SSF_ext, self.SSF_ext, self.k, self.k]
+        self.i_shape = [self.gate_filter, self.gate_filter, self.k, self.k]
+        self.o_shape = [self.gate_filter, self.gate_filter, self.k, self.k]
+        self.bias_shape = [1, 1, 1, self.k]
+        self.tuning_params = ['Q', 'P']
+        self.tuning_shape = [1, 1, self.k, self.k]
+
+        if isinstance(self.recurrent_nl, str):
+            self.recurrent_nl = self.interpret_nl(self.recurrent_nl)
+        self.ii, self.oi = self.interpret_integration(self.integration_type)
+
+        if compute_mode not in _lib.MODES:
+            raise ValueError("compute_mode must be one of %s" % sorted(_lib.MODES))
+        self.compute_mode = compute_mode
+        self._injected = params
+        self._hidden_state = hidden_state
+        self._seed = seed
+        self._check_supported()
+
+    # -- option handling ---------------------------------------------------------------------
+    def interpret_nl(self, nl_type):
+        """hgru_module.py:130-143 -- only tanh runs in the kernels."""
+        if nl_type == 'tanh':
+            return 'tanh'
+        elif nl_type in ('relu', 'selu', 'leaky_relu', 'hard_tanh'):
+            raise NotImplementedError('recurrent_nl=%s: only tanh is on the hot path' % nl_type)
+        else:
+            raise NotImplementedError(nl_type)
+
+    def interpret_integration(self, integration_type):
+        """hgru_module.py:145-157."""
+        if integration_type == 'alternate':
+            return 'input_integration', 'output_integration'
+        elif integration_type in ('mely', 'control'):
+            raise NotImplementedError(
+                'Requested integration %s is declared by the reference but not on the hot path'
+                % integration_type)
+        else:
+            raise NotImplementedError('Requested integration %s' % integration_type)
+
+    def update_params(self, kwargs):
+        if kwargs is not None:
+            for k, v in kwargs.items():
+                setattr(self, k, v)
+
+    def _check_supported(self):
+        def need(cond, what):
+            if not cond:
+                raise NotImplementedError(what + ' (not on the path hgru_pose.py configures)')
+        need(list(self.strides) == [1, 1, 1, 1], 'strides != [1,1,1,1]')
+        need(self.padding == 'SAME', "padding != 'SAME'")
+        need(self.gate_filter == 1, 'gate_filter != 1')
+        need(self.gru_gates is True, 'gru_gates=False')
+        need(not self.output_gru_gates, 'output_gru_gates=True')
+        need(self.multiplicative_excitation is True, 'multiplicative_excitation=False')
+        need(self.association_field is True, 'association_field=False')
+        need(self.rectify_weights is None, 'rectify_weights')
+        need(not self.atrous_convolutions, 'atrous_convolutions')
+        need(not self.batch_norm, 'batch_norm inside the circuit')
+        need(self.gamma is True or torch.is_tensor(self.gamma), 'gamma=False')
+        need(self.beta is True or torch.is_tensor(self.beta), 'beta=False')
+        need(self.nu is True or torch.is_tensor(self.nu), 'nu=False')
+        need(not self.zeta or torch.is_tensor(self.zeta), 'zeta=True')
+        need(not self.xi or torch.is_tensor(self.xi), 'xi=True')
+        need(self.lesions in ([None], None, []), 'lesions')
+        need(not (self.lesion_beta or self.lesion_nu or self.lesion_omega or self.lesion_kappa), 'lesion_*')
+        need(not self.store_states, 'store_states (use build(trace=True))')
+        need(self.gate_nl in ('sigmoid',), 'gate_nl != sigmoid')
+        if self.train and self.dropout is not None:
+            raise NotImplementedError                                   # hgru_module.py:702-703
+        need(self.dtype in ('float32', torch.float32), 'dtype != float32')
+
+    # -- parameters --------------------------------------------------------------------------
+    def prepare_tensors(self):
+        """Variables of scope `contextual_circuit` (hgru_module.py:172-503) as torch CUDA tensors,
+        registered as attributes under the reference's names."""
+        self.weight_dict = {
+            'P': {'r': {'weight': 'p_r', 'activity': 'P_r', 'tuning': 'p_t'}},
+            'I': {'r': {'weight': 'i_r', 'bias': 'i_b', 'activity': 'I_r'}},
+            'O': {'r': {'weight': 'o_r', 'bias': 'o_b', 'activity': 'O_r'}},
+            'xi': {'r': {'weight': 'xi'}}, 'beta': {'r': {'weight': 'beta'}},
+            'nu': {'r': {'weight': 'nu'}}, 'zeta': {'r': {'weight': 'zeta'}},
+            'gamma': {'r': {'weight': 'gamma'}}, 'phi': {'r': {'weight': 'phi'}},
+            'kappa': {'r': {'weight': 'kappa'}}, 'rho': {'r': {'weight': 'rho'}},
+        }
+        k, S, T = self.k, self.SSF_ext, self.timesteps
+        shapes = {'p_r': (S, S, k, k), 'i_r': (1, 1, k, k), 'o_r': (1, 1, k, k), 'rho': (T,)}
+        for n in ('i_b', 'o_b', 'beta', 'nu', 'gamma', 'kappa', 'omega', 'lateral_bias'):
+            shapes[n] = (1, 1, 1, k)
+        if self._injected is not None:
+            src = {}
+            for n in _lib.HGRU_PARAM_ORDER:
+                v = self._injected.get(n, self._injected.get('contextual_circuit/' + n))
+                if v is None:
+                    raise KeyError('params is missing %r' % n)
+                src[n] = v
+        else:
+            if self.gate_bias_init != 'chronos':
+                raise NotImplementedError("gate_bias_init != 'chronos'")
+            src = init.hgru_params(k, S, T, seed=self._seed)
+        for n in _lib.HGRU_PARAM_ORDER:
+            t = _as_dev(src[n])
+            if tuple(t.shape) != shapes[n]:
+                if t.numel() != int(np.prod(shapes[n])):
+                    raise RuntimeError('%s has shape %s, expected %s' % (n, tuple(t.shape), shapes[n]))
+                t = t.reshape(shapes[n])
+            setattr(self, n, t)
+        dev = self.X.device
+        self.zeta = torch.ones((), device=dev)          # tf.constant(1.) hgru_module.py:437-438
+        self.xi = torch.ones((), device=dev)            # hgru_module.py:463-464
+
+    def gather_tensors(self, wak='weight'):
+        weights = {}
+        for k, v in self.weight_dict.items():
+            for wk, wv in v.items():
+                if wak in wv.keys() and hasattr(self, wv[wak]):
+                    weights['%s_%s' % (k, wk)] = self[wv[wak]]
+        return weights
+
+    # -- forward -----------------------------------------------------------------------------
+    def _initial_state(self):
+        if self._hidden_state is not None:
+            O = _as_dev(self._hidden_state)
+            if tuple(O.shape) != tuple(self.X.shape):
+                raise RuntimeError('hidden_state shape %s != X shape %s' % (tuple(O.shape), tuple(self.X.shape)))
+            return O
+        if self.hidden_init == 'identity':
+            return self.X.clone()
+        elif self.hidden_init == 'random':
+            # xavier-uniform over the activation shape (hgru_module.py:879-887), seeded
+            g = torch.Generator(device='cpu').manual_seed(self._seed + 1)
+            rf = self.n * self.h
+            lim = math.sqrt(6.0 / (self.w * rf + self.k * rf))
+            O = (torch.rand(tuple(self.X.shape), generator=g) * 2.0 - 1.0) * lim
+            return O.to(self.X.device)
+        elif self.hidden_init == 'zeros':
+            return torch.zeros_like(self.X)
+        else:
+            raise RuntimeError                                          # hgru_module.py:891-892
+
+    def build(self, trace=False):
+        """Run the circuit (hgru_module.py:872-959): `timesteps` iterations of `full` (:825-857).
+
+        Returns O, or (O, weights, activities) when return_weights (the reference default).
+        trace=True (non-reference) additionally stores per-timestep `self.I_steps`/`self.O_steps`
+        [T,n,h,w,k]."""
+        if not self.X.is_cuda:
+            raise RuntimeError("ContextualCircuit.build() needs X on a CUDA device (no CPU fallback)")
+        lib = _lib.load()
+        self.prepare_tensors()
+        plan = _get_plan(self.n, self.h, self.w, self.k, self.SSF_ext, self.timesteps,
+                         _lib.MODES[self.compute_mode])
+        self._plan = plan
+        st = _stream()
+        ptrs = [getattr(self, n).data_ptr() for n in _lib.HGRU_PARAM_ORDER]
+        _lib.check(lib.hgru_set_params(plan, *ptrs, st), "hgru_set_params")
+        O0 = self._initial_state()
+        O = torch.empty_like(self.X)
+        I_tr = O_tr = None
+        if trace:
+            I_tr = torch.empty((self.timesteps,) + tuple(self.X.shape), device=self.X.device)
+            O_tr = torch.empty_like(I_tr)
+        _lib.check(lib.hgru_forward(plan, self.X.data_ptr(), O0.data_ptr(), O.data_ptr(),
+                                    I_tr.data_ptr() if trace else None,
+                                    O_tr.data_ptr() if trace else None, st), "hgru_forward")
+        self.I_steps, self.O_steps = I_tr, O_tr
+        self.gpu_launches = lib.hgru_plan_launch_count(plan)
+        if self.return_weights:
+            weights = self.gather_tensors(wak='weight')
+            tuning = self.gather_tensors(wak='tuning')
+            weights = dict(weights, **{})
+            del tuning
+            activities = self.gather_tensors(wak='activity')
+            if self.association_field:
+                weights['p_t'] = self.p_r
+            return O, weights, activities
+        return O

@@ -1,0 +1,55 @@
+"""CPU: the C-ABI shared library loads and exports every symbol include/hgru_b200.h declares
+(no compute calls -- there is no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "hgru_b200.h")
+
+
+def _declared():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"HGRU_API\s+[\w\s\*]+?\b(\w+)\s*\(", src)))
+
+
+def test_header_declares_the_expected_entry_points():
+    names = _declared()
+    for must in ("hgru_plan_create", "hgru_set_params", "hgru_forward", "hgru_plan_destroy",
+                 "pose_plan_create", "pose_set_params", "pose_forward", "pose_forward_host",
+                 "pose_plan_destroy", "hgru_last_error"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol():
+    from monkey_pose_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        pytest.fail("libhgru_b200.so missing: run __graft_entry__.build()")
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in _declared():
+        assert hasattr(lib, name), name
+    assert set(_declared()) == set(_lib.SIGNATURES), "ctypes table out of sync with the header"
+
+
+def test_typed_load_and_pure_host_calls():
+    from monkey_pose_b200 import _lib
+    lib = _lib.load()
+    assert lib.hgru_version() >= 100
+    assert lib.hgru_plan_destroy(None) == 0          # destroying NULL is a no-op
+    assert lib.hgru_plan_workspace_bytes(None) == 0
+    # argument validation happens before any CUDA call
+    assert lib.hgru_plan_create(1, 8, 8, 8, 15, 1, 0, None) == 1
+    assert b"out is null" in lib.hgru_last_error()
+    h = ctypes.c_void_p()
+    assert lib.hgru_plan_create(1, 8, 8, 8, 4, 1, 0, ctypes.byref(h)) == 2     # even filter size
+    assert lib.hgru_plan_create(0, 8, 8, 8, 15, 1, 0, ctypes.byref(h)) == 1    # empty batch
+    assert lib.hgru_plan_create(1, 8, 8, 8, 15, 1, 7, ctypes.byref(h)) == 2    # unknown mode
+
+
+def test_pose_params_struct_matches_header_layout():
+    from monkey_pose_b200 import _lib
+    # 10 stem/fc pointers + 5x4 batch-norm pointers + 12 hGRU pointers
+    assert ctypes.sizeof(_lib.PoseParams) == (10 + 20 + 12) * ctypes.sizeof(ctypes.c_void_p)

@@ -1,0 +1,169 @@
+"""GPU (B200): the CUDA path, called through the C-ABI by the reference-shaped Python classes,
+against the oracle -- golden fixtures produced by the reference source, seeded random cases, edge
+shapes, and size-independent properties at BASELINE sizes.
+
+Tolerances (BASELINE.json north_star): fp32 path <= 1e-4 relative on hidden states and outputs;
+bf16 tensor-core path <= 1e-2 relative and <= 0.5 mm mean per-joint deviation."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import monkey_pose_b200 as mp
+from monkey_pose_b200 import initialization as init
+from oracle import hgru_oracle_np as onp
+from oracle import hgru_oracle_torch as otorch
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+HGRU_FILES = sorted(glob.glob(os.path.join(GOLDEN, "hgru_ref_*.npz")))
+POSE_AUX = mp.model().aux
+TOL = {"fp32": 1e-4, "bf16": 1e-2}
+
+
+def _run_cc(X, O0, params, T, S, mode, trace=True):
+    cc = mp.ContextualCircuit(X=torch.as_tensor(X).cuda(), timesteps=T, SRF=1, SSN=S, SSF=S, aux=POSE_AUX,
+                              params=params, hidden_state=O0, compute_mode=mode)
+    O, weights, acts = cc.build(trace=trace)
+    torch.cuda.synchronize()
+    return cc, O, weights
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("path", HGRU_FILES, ids=[os.path.basename(p) for p in HGRU_FILES])
+def test_hgru_matches_reference_golden_every_timestep(path, mode):
+    z = np.load(path)
+    T, S = int(z["T"]), int(z["S"])
+    params = {n: z["var:contextual_circuit/" + n] for n in onp.HGRU_PARAM_NAMES}
+    cc, O, weights = _run_cc(z["X"], z["O0"], params, T, S, mode)
+    for t in range(T):
+        e1 = onp.rel_err(cc.I_steps[t].cpu().numpy(), z["I_steps"][:, t])[0]
+        e2 = onp.rel_err(cc.O_steps[t].cpu().numpy(), z["O_steps"][:, t])[0]
+        assert e1 < TOL[mode] and e2 < TOL[mode], (t, e1, e2)
+    assert onp.rel_err(O.cpu().numpy(), z["O_final"])[0] < TOL[mode]
+    assert set(weights.keys()) == set(z["weights_keys"].tolist())
+    assert cc.gpu_launches > 0
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("shape", [(1, 64, 64, 64, 15, 2), (2, 64, 64, 25, 15, 2), (1, 20, 36, 32, 15, 2),
+                                   (3, 16, 16, 16, 5, 3), (1, 7, 9, 3, 3, 2)])
+def test_hgru_seeded_cases_vs_oracle(shape, mode):
+    """k = 64 (reference), 25 and 32 (BASELINE sweep), ragged H/W, tiny shapes; stress weights so
+    tanh leaves its linear region."""
+    n, h, w, k, S, T = shape
+    rng = np.random.default_rng(5)
+    X = rng.uniform(-1, 1, size=(n, h, w, k)).astype(np.float32)
+    O0 = init.hidden_init((n, h, w, k), seed=3, limit=0.5)
+    params = init.hgru_params(k, S, T, seed=9, stress=6.0)
+    cc, O, _ = _run_cc(X, O0, params, T, S, mode)
+    ref, H1s, H2s = otorch.hgru_forward(X, O0, params, T, dtype=torch.float64, trace=True)
+    for t in range(T):
+        assert onp.rel_err(cc.I_steps[t].cpu().numpy(), H1s[t].numpy())[0] < TOL[mode]
+        assert onp.rel_err(cc.O_steps[t].cpu().numpy(), H2s[t].numpy())[0] < TOL[mode]
+    assert np.abs(ref.numpy()).max() > 0.05
+    assert onp.rel_err(O.cpu().numpy(), ref.numpy())[0] < TOL[mode]
+
+
+def test_hgru_hidden_init_variants_and_return_convention():
+    X = torch.rand(1, 16, 16, 16, device="cuda")
+    aux = dict(POSE_AUX, hidden_init="zeros", return_weights=False)
+    O = mp.ContextualCircuit(X=X, timesteps=2, SSN=5, SSF=5, aux=aux, compute_mode="fp32").build()
+    assert torch.is_tensor(O) and O.shape == X.shape
+    params = init.hgru_params(16, 5, 2, seed=42)
+    ref = otorch.hgru_forward(X.cpu().numpy(), np.zeros((1, 16, 16, 16), np.float32), params, 2, dtype=torch.float64)
+    assert onp.rel_err(O.cpu().numpy(), ref.numpy())[0] < 1e-4
+    aux["hidden_init"] = "identity"
+    O2 = mp.ContextualCircuit(X=X, timesteps=2, SSN=5, SSF=5, aux=aux, compute_mode="fp32").build()
+    ref2 = otorch.hgru_forward(X.cpu().numpy(), X.cpu().numpy(), params, 2, dtype=torch.float64)
+    assert onp.rel_err(O2.cpu().numpy(), ref2.numpy())[0] < 1e-4
+    aux["hidden_init"] = "bogus"
+    with pytest.raises(RuntimeError):
+        mp.ContextualCircuit(X=X, timesteps=2, SSN=5, SSF=5, aux=aux).build()
+
+
+def _pose(mode, N, channels, hw, T, S, fc_hidden, seed=3, stress=4.0, host=False):
+    P = init.pose_params(channels=channels, S=S, T=T, hw=hw, fc_hidden=fc_hidden, out=69, seed=seed,
+                         stress=stress, random_bn=True)
+    depth = init.synthetic_depth(N, seed=0, size=2 * hw)
+    h0 = init.hidden_init((N, hw, hw, channels), seed=5)
+    m = mp.model()
+    m.channels, m.timesteps, m.SSF, m.SSN, m.fc_hidden, m.compute_mode = channels, T, S, S, fc_hidden, mode
+    m.hidden_state = h0
+    m.load_params(P)
+    d = torch.as_tensor(depth)
+    out = m.build(d.pin_memory() if host else d.cuda(), 69)
+    torch.cuda.synchronize()
+    return m, out, P, depth, h0
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("cfg", [(2, 8, 8, 3, 5, 32), (2, 25, 16, 2, 15, 64), (1, 64, 64, 2, 15, 128)])
+def test_pose_model_vs_oracle(cfg, mode):
+    N, ch, hw, T, S, F = cfg
+    m, out, P, depth, h0 = _pose(mode, N, ch, hw, T, S, F)
+    ref, acts = otorch.pose_forward(depth, P, h0, timesteps=T, dtype=torch.float64, trace=True)
+    tol = TOL[mode]
+    assert onp.rel_err(m.activation("conv3").cpu().numpy(), acts["conv3"].numpy())[0] < tol
+    assert onp.rel_err(m.activation("hgru").cpu().numpy(), acts["hgru"].numpy())[0] < tol
+    assert onp.rel_err(m.activation("fc1").cpu().numpy(), acts["fc1"].numpy())[0] < tol
+    assert onp.rel_err(out.cpu().numpy(), ref.numpy())[0] < tol
+    assert onp.mean_joint_error_mm(out.cpu().numpy(), ref.numpy()) < 0.5
+    assert out.shape == (N, 69) and m.out_put is out and m.gpu_launches > 0
+    assert ("conv_1", 0) in m.var_dict and ("fc_out", 1) in m.var_dict
+
+
+def test_pose_model_matches_reference_layer_golden():
+    """conv_layer / max_pool through the fused stem, against the reference's own layer outputs."""
+    z = np.load(os.path.join(GOLDEN, "pose_layers_ref.npz"))
+    # stem head only: conv_1 (1->6) + relu + pool, identity batch-norm => compare with pool1
+    m = mp.model()
+    m.channels, m.timesteps, m.SSF, m.fc_hidden, m.compute_mode = 6, 1, 3, 10, "fp32"
+    P = init.pose_params(channels=6, S=3, T=1, hw=6, fc_hidden=10, out=5, seed=1)
+    for n in ("conv_1/conv_1_filters", "conv_1/conv_1_biases", "conv_2/conv_2_filters", "conv_2/conv_2_biases"):
+        P[n] = z["var:" + n]
+    m.load_params(P)
+    m.build(torch.as_tensor(z["x"]).cuda(), 5)
+    eps_scale = 1.0 / np.sqrt(1.0 + 1e-5)
+    assert onp.rel_err(m.activation("pool1").cpu().numpy(), z["pool1"] * eps_scale)[0] < 1e-5
+    assert onp.rel_err(m.activation("conv2").cpu().numpy(),
+                       onp.conv_layer(z["pool1"] * eps_scale, z["var:conv_2/conv_2_filters"],
+                                      z["var:conv_2/conv_2_biases"]) * eps_scale)[0] < 1e-5
+
+
+def test_pose_host_entry_point_equals_device_entry_point():
+    m1, out_dev, *_ = _pose("bf16", 2, 16, 16, 2, 15, 64, host=False)
+    m2, out_host, *_ = _pose("bf16", 2, 16, 16, 2, 15, 64, host=True)
+    assert not out_host.is_cuda
+    assert torch.equal(out_dev.cpu(), out_host)
+
+
+def test_properties_at_baseline_size_bf16():
+    """N = 256, k = 25, T = 8, 15x15 (BASELINE configs[1]): (i) frames are independent -- a frame's
+    output does not depend on its batch neighbours (the sharding premise); (ii) determinism;
+    (iii) the fp32 and bf16 paths agree within the bf16 budget on a sub-batch."""
+    N, ch, hw, T, S, F = 256, 25, 64, 8, 15, 1024
+    P = init.pose_params(channels=ch, S=S, T=T, hw=hw, fc_hidden=F, out=69, seed=3)
+    depth = init.synthetic_depth(N, seed=1234, size=128)
+    h0 = init.hidden_init((N, hw, hw, ch), seed=5)
+
+    def run(mode, sl):
+        m = mp.model()
+        m.channels, m.compute_mode, m.hidden_state = ch, mode, h0[sl]
+        m.load_params(P)
+        o = m.build(torch.as_tensor(depth[sl]).cuda(), 69)
+        torch.cuda.synchronize()
+        return o.cpu().numpy()
+
+    full = run("bf16", slice(0, N))
+    again = run("bf16", slice(0, N))
+    assert np.array_equal(full, again)
+    part = run("bf16", slice(100, 104))
+    assert np.array_equal(full[100:104], part)
+    exact = run("fp32", slice(100, 104))
+    assert onp.rel_err(part, exact)[0] < 1e-2
+    assert onp.mean_joint_error_mm(part, exact) < 0.5
+    assert np.isfinite(full).all() and np.abs(full).max() > 0

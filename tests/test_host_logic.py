@@ -1,0 +1,94 @@
+"""CPU: host-side mirror of the reference interface -- option handling, error behaviour, parameter
+shapes, sharding arithmetic.  (No kernels run here.)"""
+import numpy as np
+import pytest
+import torch
+
+import monkey_pose_b200 as mp
+from monkey_pose_b200 import initialization as init
+from monkey_pose_b200.sharding import shard_bounds
+
+POSE_AUX = mp.model().aux
+
+
+def _cc(**kw):
+    aux = dict(POSE_AUX)
+    aux.update(kw.pop("aux", {}))
+    return mp.ContextualCircuit(X=torch.zeros(2, 8, 8, 8), timesteps=3, SRF=1, SSN=15, SSF=15, aux=aux, **kw)
+
+
+def test_constructor_mirrors_reference_attributes():
+    cc = _cc()
+    assert (cc.n, cc.h, cc.w, cc.k) == (2, 8, 8, 8)
+    assert cc.SSF_ext == 15 and cc.p_shape == [15, 15, 8, 8]
+    assert cc.i_shape == [1, 1, 8, 8] and cc.bias_shape == [1, 1, 1, 8]
+    assert cc["timesteps"] == 3 and "gru_gates" in cc            # __getitem__ / __contains__ sugar
+    assert cc.gru_gates is True and cc.return_weights is True     # aux merged over the defaults
+    assert mp.ContextualCircuit(X=torch.zeros(1, 4, 4, 4), SSF=28, aux=POSE_AUX).SSF_ext == 29
+
+
+def test_aux_defaults_match_reference_keys():
+    d = mp.auxilliary_variables()
+    for k in ("lesions", "return_weights", "hidden_init", "gate_bias_init", "gru_gates", "integration_type",
+              "multiplicative_excitation", "adapation", "rectify_weights", "store_states"):
+        assert k in d
+    assert d["gru_gates"] is False and d["integration_type"] == "alternate" and d["hidden_init"] == "random"
+
+
+@pytest.mark.parametrize("aux", [
+    {"integration_type": "mely"}, {"integration_type": "control"}, {"integration_type": "bogus"},
+    {"recurrent_nl": "relu"}, {"recurrent_nl": "bogus"}, {"gru_gates": False}, {"output_gru_gates": True},
+    {"multiplicative_excitation": False}, {"rectify_weights": True}, {"atrous_convolutions": 2},
+    {"gate_filter": 3}, {"lesions": ["P"]}, {"store_states": True}, {"dropout": 0.5},
+])
+def test_off_path_options_raise_not_implemented(aux):
+    with pytest.raises(NotImplementedError):
+        _cc(aux=aux)
+
+
+def test_list_ssf_and_strides_raise():
+    with pytest.raises(NotImplementedError):
+        mp.ContextualCircuit(X=torch.zeros(1, 4, 4, 4), SSF=[3, 5], aux=POSE_AUX)
+    with pytest.raises(NotImplementedError):
+        mp.ContextualCircuit(X=torch.zeros(1, 4, 4, 4), SSF=5, strides=[1, 2, 2, 1], aux=POSE_AUX)
+
+
+def test_build_without_cuda_fails_loudly():
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    with pytest.raises(RuntimeError):
+        _cc().build()
+
+
+def test_model_defaults_are_the_references():
+    m = mp.model()
+    assert (m.SRF, m.SSN, m.SSF, m.timesteps, m.padding) == (1, 15, 15, 8, 'SAME')
+    assert m._BATCH_NORM_DECAY == 0.997 and m._BATCH_NORM_EPSILON == 1e-5
+    assert m.aux["gru_gates"] and m.aux["adapation"] and m.aux["recurrent_nl"] == "tanh"
+    assert m["timesteps"] == 8 and "aux" in m
+    with pytest.raises(NotImplementedError):
+        m.build(torch.zeros(1, 128, 128, 1), 69, train_mode=True)
+    with pytest.raises(ValueError):
+        m.build(torch.zeros(1, 128, 64, 1), 69)
+
+
+def test_param_generators_shapes_and_statistics():
+    p = init.hgru_params(64, 15, 8, seed=1)
+    assert p["p_r"].shape == (15, 15, 64, 64) and p["rho"].shape == (8,)
+    lim = np.sqrt(6.0 / (225 * 64 + 225 * 64))
+    assert abs(np.abs(p["p_r"]).max() - lim) < 1e-3 * lim + 1e-6        # xavier-uniform limit 0.01443
+    assert np.all(p["i_b"] <= 0) and np.allclose(p["o_b"], -p["i_b"])   # chronos: -log U(1, T-1)
+    assert np.all(p["rho"] == 1)
+    P = init.pose_params(channels=8, hw=8, fc_hidden=16, out=6)
+    assert P["fc_1/fc_1_weights"].shape == (8 * 8 * 8, 16)
+    assert P["batch_normalization_4/gamma"].shape == (16,)
+    d = init.synthetic_depth(3, seed=0)
+    assert d.shape == (3, 128, 128, 1) and d.min() >= 0 and d.max() <= 1 and (d == 1.0).mean() > 0.2
+
+
+def test_shard_bounds_partition_the_batch():
+    for n, w in ((4096, 8), (256, 1), (10, 4), (3, 8)):
+        spans = [shard_bounds(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
