@@ -56,11 +56,11 @@ int run_case(int N, int H, int W, int k, int grid_override, int iters) {
   printf("case S=%d k=%d (KSTEPS=%d CO_PAD=%d TILES_X=%d G=%d) N=%d H=%d W=%d smem=%d\n", S, k,
          KSTEPS, CO_PAD, TILES_X, G, N, H, W, Cfg::kSmemBytes);
   size_t npix = (size_t)N * H * W;
-  std::vector<float> in(npix * k), w((size_t)S * S * k * k), bias(k);
+  std::vector<float> in(npix * k), w((size_t)S * S * k * k), bias(CO_PAD, 0.f);
   srand(123);
   for (auto& v : in) v = bf16r((rand() / (float)RAND_MAX) * 2.f - 1.f);
   for (auto& v : w) v = bf16r(((rand() / (float)RAND_MAX) * 2.f - 1.f) * 0.05f);
-  for (auto& v : bias) v = (rand() / (float)RAND_MAX) - 0.5f;
+  for (int c = 0; c < k; ++c) bias[c] = (rand() / (float)RAND_MAX) - 0.5f;
   // operand copies
   std::vector<__nv_bfloat16> act((size_t)N * CG * H * W * 8, __float2bfloat16(0.f));
   for (int n = 0; n < N; ++n)
@@ -84,24 +84,24 @@ int run_case(int N, int H, int W, int k, int grid_override, int iters) {
   __nv_bfloat16 *d_act, *d_wpk;
   CK(cudaMalloc(&d_in, in.size() * 4));
   CK(cudaMalloc(&d_w, w.size() * 4));
-  CK(cudaMalloc(&d_bias, k * 4));
+  CK(cudaMalloc(&d_bias, CO_PAD * 4));
   CK(cudaMalloc(&d_ref, npix * k * 4));
-  CK(cudaMalloc(&d_out, npix * k * 4));
+  CK(cudaMalloc(&d_out, npix * CO_PAD * 4));
   CK(cudaMalloc(&d_act, act.size() * 2));
   CK(cudaMalloc(&d_wpk, wpk.size() * 2));
   CK(cudaMemcpy(d_in, in.data(), in.size() * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_w, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(d_bias, bias.data(), k * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_bias, bias.data(), CO_PAD * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_act, act.data(), act.size() * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_wpk, wpk.data(), wpk.size() * 2, cudaMemcpyHostToDevice));
-  CK(cudaMemset(d_out, 0xFF, npix * k * 4));
+  CK(cudaMemset(d_out, 0xFF, npix * CO_PAD * 4));
 
   CUtensorMap map;
   int rc = hgru::make_act_tensor_map(&map, d_act, N, CG, H, W, Cfg::kCols, Cfg::kRows);
   if (rc) { printf("tensor map encode failed rc=%d\n", rc); return 1; }
 
   hgru::TcConvArgs a;
-  a.N = N; a.H = H; a.W = W; a.KP = k; a.kreal = k; a.scale = nullptr; a.shift = nullptr; a.out_bf16 = nullptr;
+  a.N = N; a.H = H; a.W = W; a.KP = CO_PAD; a.kreal = k; a.scale = nullptr; a.shift = nullptr; a.out_bf16 = nullptr;
   a.units_x = (W + 8 * TILES_X - 1) / (8 * TILES_X);
   a.units_y = (H + hgru::kTileRows - 1) / hgru::kTileRows;
   a.num_units = N * a.units_x * a.units_y;
@@ -118,8 +118,10 @@ int run_case(int N, int H, int W, int k, int grid_override, int iters) {
   size_t total = npix * k;
   naive_conv<<<(unsigned)((total + 255) / 256), 256>>>(d_in, d_w, d_bias, d_ref, N, H, W, k, S);
   CK(cudaDeviceSynchronize());
-  std::vector<float> out(total), ref(total);
-  CK(cudaMemcpy(out.data(), d_out, total * 4, cudaMemcpyDeviceToHost));
+  std::vector<float> out(total), ref(total), outp(npix * CO_PAD);
+  CK(cudaMemcpy(outp.data(), d_out, npix * CO_PAD * 4, cudaMemcpyDeviceToHost));
+  for (size_t p = 0; p < npix; ++p)
+    for (int c = 0; c < k; ++c) out[p * k + c] = outp[p * CO_PAD + c];
   CK(cudaMemcpy(ref.data(), d_ref, total * 4, cudaMemcpyDeviceToHost));
   double maxerr = 0, maxref = 0;
   size_t bad = 0, nan = 0, worst = 0;

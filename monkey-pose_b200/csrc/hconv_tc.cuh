@@ -201,44 +201,52 @@ hconv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const TcConvArgs a) 
       }
     }
   } else if (warp == 1) {
-    // ---------------- MMA issuer (single thread) ----------------
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(1 /*bf16*/, 128, CO_PAD);
-      uint32_t st = 0, ph = 0;
-      int it = 0;
-      for (int u = first; u < a.num_units; u += stride, ++it) {
-        const uint32_t s = it & 1;
-        const uint32_t acc = tmem_base + s * Cfg::kAccCols;
-        mbar_wait(bar_acc_empty + 8 * s, ((it >> 1) & 1) ^ 1);
-        tc_fence_after();
-        for (int q = 0; q < KSTEPS; ++q) {
-          mbar_wait(bar_in_full + 8 * q, it & 1);
-          const uint32_t a_part = in_buf + q * Cfg::kPartBytes;
-          for (int sg = 0; sg < Cfg::kStagesPerKstep; ++sg) {
-            mbar_wait(bar_w_full + 8 * st, ph);
-            tc_fence_after();
-            const uint32_t w_st = w_buf + st * Cfg::kStageBytes;
+    // ---------------- MMA issuer ----------------
+    // The whole warp runs this loop convergently so every address / descriptor stays in uniform
+    // registers; one elected lane issues the tcgen05 instructions (the same lane every time, so
+    // its commits track all of its MMAs).
+    const bool leader = elect_one();
+    constexpr uint32_t idesc = make_idesc(1 /*bf16*/, 128, CO_PAD);
+    // descriptor templates: only the 14-bit start-address field changes per instruction
+    const uint64_t adesc0 = make_smem_desc(in_buf, Cfg::kChunkPitch, Cfg::kRowPitch);
+    const uint64_t bdesc0 = make_smem_desc(w_buf, CO_PAD * 16, 128);
+    uint32_t st = 0, ph = 0;
+    int it = 0;
+    for (int u = first; u < a.num_units; u += stride, ++it) {
+      const uint32_t s = it & 1;
+      const uint32_t acc = tmem_base + s * Cfg::kAccCols;
+      mbar_wait(bar_acc_empty + 8 * s, ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      for (int q = 0; q < KSTEPS; ++q) {
+        mbar_wait(bar_in_full + 8 * q, it & 1);
+        const uint64_t adesc_q = adesc0 + static_cast<uint64_t>((q * Cfg::kPartBytes) >> 4);
+        uint32_t tap_off = 0;            // (dy * kRowPitch + dx * 16) >> 4, advanced incrementally
+        uint32_t dx = 0;
+        for (int sg = 0; sg < Cfg::kStagesPerKstep; ++sg) {
+          mbar_wait(bar_w_full + 8 * st, ph);
+          tc_fence_after();
+          const uint64_t bdesc_st = bdesc0 + static_cast<uint64_t>((st * Cfg::kStageBytes) >> 4);
 #pragma unroll
-            for (int g = 0; g < G; ++g) {
-              const int tap = sg * G + g;
-              const int dy = tap / S, dx = tap - dy * S;
-              const uint32_t a_tap = a_part + dy * Cfg::kRowPitch + dx * 16;
-              const uint64_t bdesc = make_smem_desc(w_st + g * Cfg::kTapBytes, CO_PAD * 16, 128);
+          for (int g = 0; g < G; ++g) {
+            const uint64_t bdesc = bdesc_st + static_cast<uint64_t>((g * Cfg::kTapBytes) >> 4);
+            const uint64_t adesc_tap = adesc_q + tap_off;
+            const uint32_t accum = (q | sg | g) != 0;
 #pragma unroll
-              for (int t = 0; t < TILES_X; ++t) {
-                const uint64_t adesc =
-                    make_smem_desc(a_tap + t * 128, Cfg::kChunkPitch, Cfg::kRowPitch);
-                mma_bf16_ss(acc + t * CO_PAD, adesc, bdesc, idesc, (q | tap) != 0);
-              }
+            for (int t = 0; t < TILES_X; ++t) {
+              if (leader) mma_bf16_ss(acc + t * CO_PAD, adesc_tap + static_cast<uint64_t>(t * 8), bdesc, idesc, accum);
             }
-            tc_commit(bar_w_empty + 8 * st);
-            if (++st == WSTAGES) { st = 0; ph ^= 1; }
+            // next tap: dx+1, wrapping to the next filter row
+            if (++dx == S) { dx = 0; tap_off += (Cfg::kRowPitch - (S - 1) * 16) >> 4; }
+            else tap_off += 1;
           }
-          tc_commit(bar_in_empty + 8 * q);
+          if (leader) tc_commit(bar_w_empty + 8 * st);
+          if (++st == WSTAGES) { st = 0; ph ^= 1; }
         }
-        tc_commit(bar_acc_full + 8 * s);
+        if (leader) tc_commit(bar_in_empty + 8 * q);
       }
+      if (leader) tc_commit(bar_acc_full + 8 * s);
     }
+    __syncwarp();
   } else if (warp >= 4) {
     // ---------------- epilogue: TMEM -> registers -> fp32 NHWC ----------------
     const int ew = warp & 3;                      // TMEM lane quarter this warp may access
