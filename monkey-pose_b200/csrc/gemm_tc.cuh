@@ -1,0 +1,181 @@
+// Split-K GEMM on tcgen05 for the readout's first dense layer (reference: hgru_pose.py:91,156-163,
+// `tf.matmul(reshape(x,[-1,in]), weights)`):   part[z][m][n] = sum_{k in slice z} A[m][k] * B[n][k]
+//   A [M][K]  bf16, K-major  = batch-norm'ed hGRU output, flattened (h, w, c)
+//   B [Nn][K] bf16, K-major  = fc_1 weights, transposed once at set_params
+// The layer is weight-streaming bound at these batch sizes (K = 262 144, M <= 512): the grid is
+// (N tiles) x (M tiles) x (K splits) ~ one CTA per SM so every SM streams a disjoint slice of B
+// exactly once; partial sums are reduced by the readout tail kernel.
+//
+// CTA tile 128 x 256 x 64; operands land in shared memory through 2-D TMA boxes with the 128-byte
+// swizzle (box = 64 bf16 = 128 B per row), the canonical K-major SW128 UMMA layout; 4-stage ring;
+// one accumulator (256 TMEM columns); warps: w0 TMA, w1 MMA, w2 TMEM alloc, w4..7 epilogue.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "sm100_ptx.cuh"
+
+namespace hgru {
+
+constexpr int kGemmBM = 128, kGemmBN = 256, kGemmBK = 64, kGemmStages = 4;
+constexpr int kGemmABytes = kGemmBM * kGemmBK * 2;    // 16 KB
+constexpr int kGemmBBytes = kGemmBN * kGemmBK * 2;    // 32 KB
+constexpr int kGemmStageBytes = kGemmABytes + kGemmBBytes;
+constexpr int kGemmSmemBytes = kGemmStages * kGemmStageBytes + 256 + 1024;
+
+struct GemmArgs {
+  int M, Nn, K;          // problem size
+  int kblocks_per_split; // K blocks (of 64) handled by one z slice
+  float* part;           // [splits][M][Nn] fp32
+};
+
+// K-major operand tile written by TMA with CU_TENSOR_MAP_SWIZZLE_128B: rows of 128 B, 8-row groups
+// of 1024 B (SBO), 16-byte chunks XOR-swizzled inside each 1024-B atom.  Tile base 1024-B aligned.
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>(1) << 16;                 // LBO (ignored for swizzled K-major)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;         // SBO: 8 rows x 128 B
+  d |= static_cast<uint64_t>(1) << 46;                 // descriptor version (sm_100)
+  d |= static_cast<uint64_t>(2) << 61;                 // SWIZZLE_128B
+  return d;
+}
+
+__global__ void __launch_bounds__(256, 1)
+gemm_tc_splitk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                      const GemmArgs g) {
+  using namespace sm100;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + kGemmStages * kGemmStageBytes;
+  const uint32_t bar_full = bars, bar_empty = bars + 8 * kGemmStages, bar_acc = bar_empty + 8 * kGemmStages;
+  const uint32_t tmem_slot = bar_acc + 8;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kGemmStages; ++i) {
+      mbar_init(bar_full + 8 * i, 1);
+      mbar_init(bar_empty + 8 * i, 1);
+    }
+    mbar_init(bar_acc, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 2) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int n0 = blockIdx.x * kGemmBN, m0 = blockIdx.y * kGemmBM, z = blockIdx.z;
+  const int total_kb = (g.K + kGemmBK - 1) / kGemmBK;
+  const int kb0 = z * g.kblocks_per_split;
+  int nkb = total_kb - kb0;
+  if (nkb > g.kblocks_per_split) nkb = g.kblocks_per_split;
+  if (nkb < 0) nkb = 0;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t st = 0, ph = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(bar_empty + 8 * st, ph ^ 1);
+        mbar_arrive_expect_tx(bar_full + 8 * st, kGemmStageBytes);
+        const uint32_t sa = base + st * kGemmStageBytes;
+        tma_load_2d(sa, &map_a, bar_full + 8 * st, (kb0 + kb) * kGemmBK, m0);
+        tma_load_2d(sa + kGemmABytes, &map_b, bar_full + 8 * st, (kb0 + kb) * kGemmBK, n0);
+        if (++st == kGemmStages) { st = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    const bool leader = elect_one();
+    constexpr uint32_t idesc = make_idesc(1, kGemmBM, kGemmBN);
+    const uint64_t a0 = make_smem_desc_sw128(base);
+    const uint64_t b0 = make_smem_desc_sw128(base + kGemmABytes);
+    uint32_t st = 0, ph = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+      mbar_wait(bar_full + 8 * st, ph);
+      tc_fence_after();
+      const uint64_t so = static_cast<uint64_t>((st * kGemmStageBytes) >> 4);
+#pragma unroll
+      for (int ks = 0; ks < kGemmBK / 16; ++ks) {
+        // advance 16 K-elements = 32 bytes inside the 128-byte swizzle row
+        if (leader) mma_bf16_ss(tmem_base, a0 + so + ks * 2, b0 + so + ks * 2, idesc, (kb | ks) != 0);
+      }
+      if (leader) tc_commit(bar_empty + 8 * st);
+      if (++st == kGemmStages) { st = 0; ph ^= 1; }
+    }
+    if (leader) tc_commit(bar_acc);
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int ew = warp & 3;
+    const int m = m0 + ew * 32 + lane;
+    float* dst = g.part + (static_cast<size_t>(z) * g.M + m) * g.Nn + n0;
+    if (nkb > 0) {
+      mbar_wait(bar_acc, 0);
+      tc_fence_after();
+    }
+#pragma unroll 1
+    for (int c0 = 0; c0 < kGemmBN; c0 += 16) {
+      uint32_t v[16];
+      if (nkb > 0) {
+        tmem_ld16(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + c0, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0u;
+      }
+      if (m < g.M) {
+        if (n0 + c0 + 16 <= g.Nn && (g.Nn & 3) == 0) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(dst + c0 + j) =
+                make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                            __uint_as_float(v[j + 3]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (n0 + c0 + j < g.Nn) dst[c0 + j] = __uint_as_float(v[j]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<256>(tmem_base);
+  }
+}
+
+// A operand of fc_1: bf16 [M][HW*k] = (H2[m][pix][c] * scale[c] + shift[c]) over real channels
+// (the inference batch-norm of the hGRU output, hgru_pose.py:82-90, applied while flattening).
+__global__ void __launch_bounds__(256)
+fc1_pack_a_kernel(const float* __restrict__ h2, const float* __restrict__ sc, const float* __restrict__ sh,
+                  __nv_bfloat16* __restrict__ a, size_t npix, int k, int KP) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= npix * k) return;
+  const int c = i % k;
+  const size_t p = i / k;
+  a[i] = __float2bfloat16(h2[p * KP + c] * sc[c] + sh[c]);
+}
+
+// fc_1 weights [K][F] fp32 -> bf16 [F][K] (K-major B operand); 32x32 tiles through shared memory.
+__global__ void __launch_bounds__(256)
+transpose_to_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wt, int K, int F) {
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const int kk = k0 + r, f = f0 + tx;
+    tile[r][tx] = (kk < K && f < F) ? w[static_cast<size_t>(kk) * F + f] : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int f = f0 + r, kk = k0 + tx;
+    if (f < F && kk < K) wt[static_cast<size_t>(f) * K + kk] = __float2bfloat16(tile[tx][r]);
+  }
+}
+
+}  // namespace hgru

@@ -68,7 +68,32 @@ struct TcConvArgs {
   const float* shift;       // [KP]
   float* out;               // fp32 NHWC [N][H][W][KP]
   __nv_bfloat16* out_bf16;  // optional bf16 chunked copy [N][KP/8][H][W][8]
+  // fused hGRU epilogues (all fp32 NHWC [N][H][W][KP] unless noted)
+  const float* X;           // feed-forward drive
+  const float* H1;          // EpiH2: inhibited state of this timestep
+  const float* G;           // EpiH2: mix gate G2
+  float* H2;                // EpiH1/EpiGate1: read; EpiH2: read + written in place
+  const float* v0;          // per-channel vectors [KP], meaning depends on the epilogue
+  const float* v1;
+  const float* v2;
+  const float* rho_t;       // device pointer to the adaptation scale rho[t] of this timestep
 };
+
+__device__ __forceinline__ float fast_sigmoid(float x) { return 1.f / (1.f + __expf(-x)); }
+// tanh via one exp: (1 - e^-2x) / (1 + e^-2x); |err| ~ 1e-7 abs, far inside the bf16-path budget
+__device__ __forceinline__ float fast_tanh(float x) {
+  const float e = __expf(-2.f * fabsf(x));
+  const float t = __fdividef(1.f - e, 1.f + e);
+  return copysignf(t, x);
+}
+__device__ __forceinline__ void store_chunk_bf16(__nv_bfloat16* base, int KP, int HWp, int n, int cg,
+                                                 size_t pin, const float* r) {
+  __nv_bfloat162 h[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(r[2 * j], r[2 * j + 1]);
+  __nv_bfloat16* o = base + ((static_cast<size_t>(n) * (KP >> 3) + cg) * HWp + pin) * 8;
+  *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(h);
+}
 
 // ---- epilogue functors: consume one pixel's CO_PAD accumulators --------------------------------
 // out = acc + bias                       (P = conv + lateral_bias, hgru_module.py:657)
@@ -109,6 +134,129 @@ struct EpiBiasReluAffine {
             ((static_cast<size_t>(n) * (a.KP >> 3) + (c >> 3)) * (a.H * a.W) + pin) * 8;
         *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(h);
       }
+    }
+  }
+};
+
+// input_integration fused into the C1 conv (hgru_module.py:657, 795-804):
+//   C1 = acc + lateral_bias;  H1 = tanh(X - (beta*H2 + nu) * C1)
+// writes H1 fp32 and its bf16 chunked operand copy.  bias = lateral_bias, v0 = beta, v1 = nu.
+struct EpiH1 {
+  template <int CO_PAD>
+  __device__ static __forceinline__ void apply(const TcConvArgs& a, int n, int y, int x,
+                                               float (&acc)[CO_PAD]) {
+    const size_t pin = static_cast<size_t>(y) * a.W + x;
+    const size_t off = (static_cast<size_t>(n) * a.H * a.W + pin) * a.KP;
+#pragma unroll
+    for (int c = 0; c < CO_PAD; c += 8) {
+      float r[8];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float4 xv = *reinterpret_cast<const float4*>(a.X + off + c + 4 * h);
+        const float4 hv = *reinterpret_cast<const float4*>(a.H2 + off + c + 4 * h);
+        const float4 lb = __ldg(reinterpret_cast<const float4*>(a.bias + c + 4 * h));
+        const float4 be = __ldg(reinterpret_cast<const float4*>(a.v0 + c + 4 * h));
+        const float4 nu = __ldg(reinterpret_cast<const float4*>(a.v1 + c + 4 * h));
+        r[4 * h + 0] = fast_tanh(xv.x - (be.x * hv.x + nu.x) * (acc[c + 4 * h + 0] + lb.x));
+        r[4 * h + 1] = fast_tanh(xv.y - (be.y * hv.y + nu.y) * (acc[c + 4 * h + 1] + lb.y));
+        r[4 * h + 2] = fast_tanh(xv.z - (be.z * hv.z + nu.z) * (acc[c + 4 * h + 2] + lb.z));
+        r[4 * h + 3] = fast_tanh(xv.w - (be.w * hv.w + nu.w) * (acc[c + 4 * h + 3] + lb.w));
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (c + j >= a.kreal) r[j] = 0.f;
+      float* dst = a.out + off + c;
+      *reinterpret_cast<float4*>(dst) = make_float4(r[0], r[1], r[2], r[3]);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(r[4], r[5], r[6], r[7]);
+      store_chunk_bf16(a.out_bf16, a.KP, a.H * a.W, n, c >> 3, pin, r);
+    }
+  }
+};
+// output_integration + adaptation fused into the C2 conv (hgru_module.py:657, 806-823, 847-849):
+//   C2 = acc + lateral_bias; e = gamma*C2; Ht = tanh(kappa*(H1+e) + omega*(H1*e));
+//   H2 = (G2*H2 + (1-G2)*Ht) * rho_t      (in place) + bf16 chunked copy of the new H2.
+// bias = lateral_bias, v0 = gamma, v1 = kappa, v2 = omega.
+struct EpiH2 {
+  template <int CO_PAD>
+  __device__ static __forceinline__ void apply(const TcConvArgs& a, int n, int y, int x,
+                                               float (&acc)[CO_PAD]) {
+    const size_t pin = static_cast<size_t>(y) * a.W + x;
+    const size_t off = (static_cast<size_t>(n) * a.H * a.W + pin) * a.KP;
+    const float rho = __ldg(a.rho_t);
+#pragma unroll
+    for (int c = 0; c < CO_PAD; c += 8) {
+      float r[8];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int cc = c + 4 * h;
+        const float4 h1 = *reinterpret_cast<const float4*>(a.H1 + off + cc);
+        const float4 g = *reinterpret_cast<const float4*>(a.G + off + cc);
+        const float4 h2 = *reinterpret_cast<const float4*>(a.H2 + off + cc);
+        const float4 lb = __ldg(reinterpret_cast<const float4*>(a.bias + cc));
+        const float4 ga = __ldg(reinterpret_cast<const float4*>(a.v0 + cc));
+        const float4 ka = __ldg(reinterpret_cast<const float4*>(a.v1 + cc));
+        const float4 om = __ldg(reinterpret_cast<const float4*>(a.v2 + cc));
+        const float h1v[4] = {h1.x, h1.y, h1.z, h1.w}, gv[4] = {g.x, g.y, g.z, g.w};
+        const float h2v[4] = {h2.x, h2.y, h2.z, h2.w}, lbv[4] = {lb.x, lb.y, lb.z, lb.w};
+        const float gav[4] = {ga.x, ga.y, ga.z, ga.w}, kav[4] = {ka.x, ka.y, ka.z, ka.w};
+        const float omv[4] = {om.x, om.y, om.z, om.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float e = gav[j] * (acc[cc + j] + lbv[j]);
+          const float ht = fast_tanh(kav[j] * (h1v[j] + e) + omv[j] * (h1v[j] * e));
+          r[4 * h + j] = (gv[j] * h2v[j] + (1.f - gv[j]) * ht) * rho;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (c + j >= a.kreal) r[j] = 0.f;
+      float* dst = a.H2 + off + c;
+      *reinterpret_cast<float4*>(dst) = make_float4(r[0], r[1], r[2], r[3]);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(r[4], r[5], r[6], r[7]);
+      store_chunk_bf16(a.out_bf16, a.KP, a.H * a.W, n, c >> 3, pin, r);
+    }
+  }
+};
+// mix gate as a 1x1 tensor-core conv (hgru_module.py:729-740): G2 = sigmoid(acc + o_b) -> fp32.
+struct EpiGateOut {
+  template <int CO_PAD>
+  __device__ static __forceinline__ void apply(const TcConvArgs& a, int n, int y, int x,
+                                               float (&acc)[CO_PAD]) {
+    float* dst = a.out + ((static_cast<size_t>(n) * a.H + y) * a.W + x) * a.KP;
+#pragma unroll
+    for (int c = 0; c < CO_PAD; c += 4) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + c));
+      float4 g = make_float4(fast_sigmoid(acc[c] + b.x), fast_sigmoid(acc[c + 1] + b.y),
+                             fast_sigmoid(acc[c + 2] + b.z), fast_sigmoid(acc[c + 3] + b.w));
+      if (c + 0 >= a.kreal) g.x = 0.f;
+      if (c + 1 >= a.kreal) g.y = 0.f;
+      if (c + 2 >= a.kreal) g.z = 0.f;
+      if (c + 3 >= a.kreal) g.w = 0.f;
+      *reinterpret_cast<float4*>(dst + c) = g;
+    }
+  }
+};
+// input gate as a 1x1 tensor-core conv + gated operand (hgru_module.py:696-711):
+//   G1 = sigmoid(acc + i_b);  operand = bf16(G1 . H2)   (chunked copy consumed by the C1 conv).
+struct EpiGateIn {
+  template <int CO_PAD>
+  __device__ static __forceinline__ void apply(const TcConvArgs& a, int n, int y, int x,
+                                               float (&acc)[CO_PAD]) {
+    const size_t pin = static_cast<size_t>(y) * a.W + x;
+    const size_t off = (static_cast<size_t>(n) * a.H * a.W + pin) * a.KP;
+#pragma unroll
+    for (int c = 0; c < CO_PAD; c += 8) {
+      float r[8];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + c + 4 * h));
+        const float4 hv = *reinterpret_cast<const float4*>(a.H2 + off + c + 4 * h);
+        r[4 * h + 0] = fast_sigmoid(acc[c + 4 * h + 0] + b.x) * hv.x;
+        r[4 * h + 1] = fast_sigmoid(acc[c + 4 * h + 1] + b.y) * hv.y;
+        r[4 * h + 2] = fast_sigmoid(acc[c + 4 * h + 2] + b.z) * hv.z;
+        r[4 * h + 3] = fast_sigmoid(acc[c + 4 * h + 3] + b.w) * hv.w;
+      }
+      store_chunk_bf16(a.out_bf16, a.KP, a.H * a.W, n, c >> 3, pin, r);   // pad channels: H2 pad is 0
     }
   }
 };

@@ -86,28 +86,39 @@ bool tc_geometry(int S, int KP, TcGeom* g) {
   return true;
 }
 
+// (S, KP) instances.  KP -> (KSTEPS, TILES_X): 64 -> (4,4), 32 -> (2,8), 16 -> (1,8); G taps per stage.
+#define TC_CASE(Epi_, S_, KP_, KS_, TX_, G_) \
+  if (S == S_ && KP == KP_) return launch_tc<S_, KS_, KP_, TX_, G_, Epi_>(map, a, st);
+#define TC_CASES_S(Epi_, S_, G64_, G32_)  \
+  TC_CASE(Epi_, S_, 64, 4, 4, G64_)       \
+  TC_CASE(Epi_, S_, 32, 2, 8, G32_)       \
+  TC_CASE(Epi_, S_, 16, 1, 8, G32_)
+
+// the horizontal convs with the fused integration epilogues
 template <class Epi>
-int dispatch_tc(int S, int KP, const CUtensorMap& map, const hgru::TcConvArgs& a, cudaStream_t st) {
-#define TC_CASE(S_, KP_, KS_, TX_, G_) \
-  if (S == S_ && KP == KP_) return launch_tc<S_, KS_, KP_, TX_, G_, Epi>(map, a, st);
-  TC_CASE(15, 64, 4, 4, 5)
-  TC_CASE(15, 32, 2, 8, 15)
-  TC_CASE(15, 16, 1, 8, 15)
-  TC_CASE(7, 64, 4, 4, 7)
-  TC_CASE(7, 32, 2, 8, 7)
-  TC_CASE(7, 16, 1, 8, 7)
-  TC_CASE(5, 64, 4, 4, 5)
-  TC_CASE(5, 32, 2, 8, 5)
-  TC_CASE(5, 16, 1, 8, 5)
-  TC_CASE(3, 64, 4, 4, 9)
-  TC_CASE(3, 32, 2, 8, 9)
-  TC_CASE(3, 16, 1, 8, 9)
-  TC_CASE(1, 64, 4, 4, 1)
-  TC_CASE(1, 32, 2, 8, 1)
-  TC_CASE(1, 16, 1, 8, 1)
-#undef TC_CASE
+int dispatch_tc_hconv(int S, int KP, const CUtensorMap& map, const hgru::TcConvArgs& a, cudaStream_t st) {
+  TC_CASES_S(Epi, 15, 5, 15)
+  TC_CASES_S(Epi, 7, 7, 7)
+  TC_CASES_S(Epi, 5, 5, 5)
+  TC_CASES_S(Epi, 3, 9, 9)
+  TC_CASES_S(Epi, 1, 1, 1)
   return fail(HGRU_E_UNSUPPORTED, "tensor-core conv: unsupported (S, padded channels)");
 }
+// 1x1 gate convs
+template <class Epi>
+int dispatch_tc_gate(int KP, const CUtensorMap& map, const hgru::TcConvArgs& a, cudaStream_t st) {
+  const int S = 1;
+  TC_CASES_S(Epi, 1, 1, 1)
+  return fail(HGRU_E_UNSUPPORTED, "tensor-core gate: unsupported padded channel count");
+}
+// 3x3 stem convs
+int dispatch_tc_stem(int KP, const CUtensorMap& map, const hgru::TcConvArgs& a, cudaStream_t st) {
+  const int S = 3;
+  TC_CASES_S(hgru::EpiBiasReluAffine, 3, 9, 9)
+  return fail(HGRU_E_UNSUPPORTED, "tensor-core stem conv: unsupported padded channel count");
+}
+#undef TC_CASES_S
+#undef TC_CASE
 
 template <int S>
 int launch_simt_conv(const float* in, const float* w, const float* bias, const float* scale,
@@ -204,17 +215,19 @@ struct hgru_plan_s {
   bool params_set = false;
   int launches = 0;
   // parameters (zero padded to KP)
-  DevBuf p_r, i_r, o_r, vecs, rho, wpk;   // vecs: 8 x [KP]: i_b o_b beta nu gamma kappa omega lateral_bias
+  DevBuf p_r, i_r, o_r, vecs, rho, wpk, wpk_i, wpk_o;   // vecs: 8 x [KP]: i_b o_b beta nu gamma kappa omega lateral_bias
   // activations, fp32 [N,H,W,KP]
   DevBuf Xp, H2, H1, C, G, A;
   // bf16 chunked operand copies (tensor-core mode)
-  DevBuf actA, actH1;
-  CUtensorMap mapA, mapH1;
+  DevBuf actA, actH1, actH2;
+  CUtensorMap mapA, mapH1;          // SxS halo-window boxes (horizontal convs)
+  CUtensorMap mapH1_g, mapH2_g;     // 1x1 boxes (gate convs)
   KernelTimer timer;
   float* vec(int i) const { return vecs.as<float>() + static_cast<size_t>(i) * KP; }
   size_t workspace() const {
-    return p_r.bytes + i_r.bytes + o_r.bytes + vecs.bytes + rho.bytes + wpk.bytes + Xp.bytes +
-           H2.bytes + H1.bytes + C.bytes + G.bytes + A.bytes + actA.bytes + actH1.bytes;
+    return p_r.bytes + i_r.bytes + o_r.bytes + vecs.bytes + rho.bytes + wpk.bytes + wpk_i.bytes +
+           wpk_o.bytes + Xp.bytes + H2.bytes + H1.bytes + C.bytes + G.bytes + A.bytes + actA.bytes +
+           actH1.bytes + actH2.bytes;
   }
 };
 
@@ -232,31 +245,38 @@ static int hgru_plan_init(hgru_plan_s* p, int N, int H, int W, int k, int S, int
   int rc = 0;
   const size_t act = p->nelem * sizeof(float);
   if ((rc = p->Xp.alloc(act)) || (rc = p->H2.alloc(act)) || (rc = p->H1.alloc(act)) ||
-      (rc = p->C.alloc(act)) || (rc = p->G.alloc(act)))
+      (rc = p->G.alloc(act)))
     return rc;
   if ((rc = p->i_r.alloc(sizeof(float) * p->KP * p->KP)) || (rc = p->o_r.alloc(sizeof(float) * p->KP * p->KP)) ||
       (rc = p->vecs.alloc(sizeof(float) * 8 * p->KP)) || (rc = p->rho.alloc(sizeof(float) * T)))
     return rc;
   if (mode == HGRU_MODE_FP32) {
-    if ((rc = p->A.alloc(act)) || (rc = p->p_r.alloc(sizeof(float) * S * S * p->KP * p->KP))) return rc;
+    if ((rc = p->A.alloc(act)) || (rc = p->C.alloc(act)) ||
+        (rc = p->p_r.alloc(sizeof(float) * S * S * p->KP * p->KP)))
+      return rc;
   } else {
     TcGeom g;
     if (!tc_geometry(S, p->KP, &g))
       return fail(HGRU_E_UNSUPPORTED, "hgru_plan_create: bf16 mode supports S in {1,3,5,7,15} and k <= 64");
     const size_t ab = p->nelem * sizeof(__nv_bfloat16);
-    if ((rc = p->actA.alloc(ab)) || (rc = p->actH1.alloc(ab))) return rc;
+    if ((rc = p->actA.alloc(ab)) || (rc = p->actH1.alloc(ab)) || (rc = p->actH2.alloc(ab))) return rc;
     const int ksteps = p->KP / 16;
-    if ((rc = p->wpk.alloc(sizeof(__nv_bfloat16) * ksteps * S * S * 2 * p->KP * 8))) return rc;
+    const size_t tapb = sizeof(__nv_bfloat16) * ksteps * 2 * p->KP * 8;
+    if ((rc = p->wpk.alloc(tapb * S * S)) || (rc = p->wpk_i.alloc(tapb)) || (rc = p->wpk_o.alloc(tapb))) return rc;
+    TcGeom g1;
+    tc_geometry(1, p->KP, &g1);
     if (hgru::make_act_tensor_map(&p->mapA, p->actA.p, N, p->CG, H, W, g.box_cols, g.box_rows) ||
-        hgru::make_act_tensor_map(&p->mapH1, p->actH1.p, N, p->CG, H, W, g.box_cols, g.box_rows))
+        hgru::make_act_tensor_map(&p->mapH1, p->actH1.p, N, p->CG, H, W, g.box_cols, g.box_rows) ||
+        hgru::make_act_tensor_map(&p->mapH1_g, p->actH1.p, N, p->CG, H, W, g1.box_cols, g1.box_rows) ||
+        hgru::make_act_tensor_map(&p->mapH2_g, p->actH2.p, N, p->CG, H, W, g1.box_cols, g1.box_rows))
       return fail(HGRU_E_CUDA, "cuTensorMapEncodeTiled failed");
   }
   return 0;
 }
 
 static void hgru_plan_free(hgru_plan_s* p) {
-  DevBuf* all[] = {&p->p_r, &p->i_r, &p->o_r, &p->vecs, &p->rho, &p->wpk, &p->Xp, &p->H2,
-                   &p->H1, &p->C, &p->G, &p->A, &p->actA, &p->actH1};
+  DevBuf* all[] = {&p->p_r, &p->i_r, &p->o_r, &p->vecs, &p->rho, &p->wpk, &p->wpk_i, &p->wpk_o, &p->Xp,
+                   &p->H2, &p->H1, &p->C, &p->G, &p->A, &p->actA, &p->actH1, &p->actH2};
   for (auto b : all) b->release();
 }
 
@@ -280,41 +300,20 @@ static int hgru_set_params_impl(hgru_plan_s* p, const float* p_r, const float* i
     const int ksteps = KP / 16;
     const size_t total = static_cast<size_t>(ksteps) * taps * 2 * KP * 8;
     hgru::pack_weights_kernel<<<nblk(total), 256, 0, st>>>(p_r, p->wpk.as<__nv_bfloat16>(), taps, k, ksteps, KP);
+    const size_t t1 = static_cast<size_t>(ksteps) * 2 * KP * 8;
+    hgru::pack_weights_kernel<<<nblk(t1), 256, 0, st>>>(i_r, p->wpk_i.as<__nv_bfloat16>(), 1, k, ksteps, KP);
+    hgru::pack_weights_kernel<<<nblk(t1), 256, 0, st>>>(o_r, p->wpk_o.as<__nv_bfloat16>(), 1, k, ksteps, KP);
   }
   CUDA_TRY(cudaGetLastError());
   p->params_set = true;
   return 0;
 }
 
-// one hconv: C = conv_SxS(src) + lateral_bias   (hgru_module.py:615-624, 657)
-static int hgru_hconv(hgru_plan_s* p, const float* src_fp32, const CUtensorMap* src_map, cudaStream_t st) {
-  p->timer.begin(st);
-  int rc;
-  if (p->mode == HGRU_MODE_FP32) {
-    rc = dispatch_simt_conv(p->S, src_fp32, p->p_r.as<float>(), p->vec(V_LBIAS), nullptr, nullptr,
-                            p->C.as<float>(), p->N, p->H, p->W, p->KP, p->KP, 0, st);
-  } else {
-    hgru::TcConvArgs a{};
-    a.N = p->N; a.H = p->H; a.W = p->W; a.KP = p->KP; a.kreal = p->k;
-    a.wpk = p->wpk.as<__nv_bfloat16>();
-    a.bias = p->vec(V_LBIAS);
-    a.out = p->C.as<float>();
-    rc = dispatch_tc<hgru::EpiBias>(p->S, p->KP, *src_map, a, st);
-  }
-  p->timer.end(st);
-  ++p->launches;
-  return rc;
-}
-
-// The recurrence on padded buffers: X = p->Xp, state in p->H2 (in/out).
-static int hgru_run_padded(hgru_plan_s* p, const float* Xp, float* H1_trace, float* H2_trace, cudaStream_t st) {
-  if (!p->params_set) return fail(HGRU_E_STATE, "hgru_forward before hgru_set_params");
+// ---- fp32 path: SIMT kernels, unfused (the <= 1e-4 anchor) --------------------------------------
+static int hgru_run_fp32(hgru_plan_s* p, const float* Xp, float* H1_trace, float* H2_trace, cudaStream_t st) {
   const int KP = p->KP, HW = p->H * p->W;
   const size_t nchunks = p->nelem / 8;
   const size_t gate_smem = sizeof(float) * (KP * KP + 64 * (KP + 1));
-  const bool tc = p->mode == HGRU_MODE_BF16;
-  p->launches = 0;
-  p->timer.reset();
   static bool gate_attr = false;
   if (!gate_attr) {
     CUDA_TRY(cudaFuncSetAttribute(hgru::gate1x1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
@@ -322,29 +321,32 @@ static int hgru_run_padded(hgru_plan_s* p, const float* Xp, float* H1_trace, flo
   }
   int rc;
   for (int t = 0; t < p->T; ++t) {
-    // circuit_input (hgru_module.py:692-724): G1, gated copy, C1
+    // circuit_input (hgru_module.py:692-724): G1, gated copy, C1 = conv + lateral_bias (:657)
     hgru::gate1x1_kernel<<<nblk(p->npix, 64), 256, gate_smem, st>>>(
-        p->H2.as<float>(), p->i_r.as<float>(), p->vec(V_IB), nullptr, tc ? nullptr : p->A.as<float>(),
-        tc ? p->actA.as<__nv_bfloat16>() : nullptr, p->npix, KP, p->k, HW);
-    ++p->launches;
-    if ((rc = hgru_hconv(p, p->A.as<float>(), &p->mapA, st))) return rc;
+        p->H2.as<float>(), p->i_r.as<float>(), p->vec(V_IB), nullptr, p->A.as<float>(), nullptr, p->npix, KP,
+        p->k, HW);
+    p->timer.begin(st);
+    if ((rc = dispatch_simt_conv(p->S, p->A.as<float>(), p->p_r.as<float>(), p->vec(V_LBIAS), nullptr, nullptr,
+                                 p->C.as<float>(), p->N, p->H, p->W, KP, KP, 0, st)))
+      return rc;
+    p->timer.end(st);
     // input_integration (:795-804)
     hgru::h1_kernel<<<nblk(nchunks), 256, 0, st>>>(Xp, p->H2.as<float>(), p->C.as<float>(), p->vec(V_BETA),
-                                                  p->vec(V_NU), p->H1.as<float>(),
-                                                  tc ? p->actH1.as<__nv_bfloat16>() : nullptr, nchunks, KP,
-                                                  p->k, HW);
-    ++p->launches;
+                                                  p->vec(V_NU), p->H1.as<float>(), nullptr, nchunks, KP, p->k, HW);
     // circuit_output (:726-756): G2, C2
     hgru::gate1x1_kernel<<<nblk(p->npix, 64), 256, gate_smem, st>>>(
         p->H1.as<float>(), p->o_r.as<float>(), p->vec(V_OB), p->G.as<float>(), nullptr, nullptr, p->npix, KP,
         p->k, HW);
-    ++p->launches;
-    if ((rc = hgru_hconv(p, p->H1.as<float>(), &p->mapH1, st))) return rc;
+    p->timer.begin(st);
+    if ((rc = dispatch_simt_conv(p->S, p->H1.as<float>(), p->p_r.as<float>(), p->vec(V_LBIAS), nullptr, nullptr,
+                                 p->C.as<float>(), p->N, p->H, p->W, KP, KP, 0, st)))
+      return rc;
+    p->timer.end(st);
     // output_integration + rho (:806-823, 847-849)
     hgru::h2_kernel<<<nblk(nchunks), 256, 0, st>>>(p->H1.as<float>(), p->C.as<float>(), p->G.as<float>(),
                                                   p->vec(V_GAMMA), p->vec(V_KAPPA), p->vec(V_OMEGA),
                                                   p->rho.as<float>(), t, p->H2.as<float>(), nchunks, KP, p->k);
-    ++p->launches;
+    p->launches += 6;
     if (H1_trace) {
       hgru::unpad_channels_kernel<<<nblk(p->npix * p->k), 256, 0, st>>>(
           p->H1.as<float>(), H1_trace + static_cast<size_t>(t) * p->npix * p->k, p->npix, p->k, KP);
@@ -356,6 +358,70 @@ static int hgru_run_padded(hgru_plan_s* p, const float* Xp, float* H1_trace, flo
       ++p->launches;
     }
   }
+  return 0;
+}
+
+// ---- bf16 path: four tcgen05 launches per timestep, all integration math in the epilogues ----
+static int hgru_run_bf16(hgru_plan_s* p, const float* Xp, float* H1_trace, float* H2_trace, cudaStream_t st) {
+  const int KP = p->KP, HW = p->H * p->W;
+  int rc;
+  hgru::TcConvArgs base{};
+  base.N = p->N; base.H = p->H; base.W = p->W; base.KP = KP; base.kreal = p->k;
+  // operand copy of the initial state
+  hgru::to_chunked_bf16_kernel<<<nblk(p->nelem / 8), 256, 0, st>>>(p->H2.as<float>(), p->actH2.as<__nv_bfloat16>(),
+                                                                  p->nelem / 8, KP, HW);
+  ++p->launches;
+  for (int t = 0; t < p->T; ++t) {
+    // circuit_input gate (hgru_module.py:696-711): operand A = bf16(sigmoid(H2 *1x1 i_r + i_b) . H2)
+    hgru::TcConvArgs a = base;
+    a.wpk = p->wpk_i.as<__nv_bfloat16>(); a.bias = p->vec(V_IB); a.H2 = p->H2.as<float>();
+    a.out_bf16 = p->actA.as<__nv_bfloat16>();
+    if ((rc = dispatch_tc_gate<hgru::EpiGateIn>(KP, p->mapH2_g, a, st))) return rc;
+    // C1 conv (:714-718, 657) + input_integration (:795-804) -> H1 (fp32 + bf16 operand copy)
+    a = base;
+    a.wpk = p->wpk.as<__nv_bfloat16>(); a.bias = p->vec(V_LBIAS); a.X = Xp; a.H2 = p->H2.as<float>();
+    a.v0 = p->vec(V_BETA); a.v1 = p->vec(V_NU);
+    a.out = p->H1.as<float>(); a.out_bf16 = p->actH1.as<__nv_bfloat16>();
+    p->timer.begin(st);
+    if ((rc = dispatch_tc_hconv<hgru::EpiH1>(p->S, KP, p->mapA, a, st))) return rc;
+    p->timer.end(st);
+    // circuit_output gate (:729-740): G2 = sigmoid(H1 *1x1 o_r + o_b)
+    a = base;
+    a.wpk = p->wpk_o.as<__nv_bfloat16>(); a.bias = p->vec(V_OB); a.out = p->G.as<float>();
+    if ((rc = dispatch_tc_gate<hgru::EpiGateOut>(KP, p->mapH1_g, a, st))) return rc;
+    // C2 conv (:746-750, 657) + output_integration + rho (:806-823, 847-849) -> H2 in place
+    a = base;
+    a.wpk = p->wpk.as<__nv_bfloat16>(); a.bias = p->vec(V_LBIAS); a.H1 = p->H1.as<float>();
+    a.G = p->G.as<float>(); a.H2 = p->H2.as<float>();
+    a.v0 = p->vec(V_GAMMA); a.v1 = p->vec(V_KAPPA); a.v2 = p->vec(V_OMEGA);
+    a.rho_t = p->rho.as<float>() + t;
+    a.out_bf16 = p->actH2.as<__nv_bfloat16>();
+    p->timer.begin(st);
+    if ((rc = dispatch_tc_hconv<hgru::EpiH2>(p->S, KP, p->mapH1, a, st))) return rc;
+    p->timer.end(st);
+    p->launches += 4;
+    if (H1_trace) {
+      hgru::unpad_channels_kernel<<<nblk(p->npix * p->k), 256, 0, st>>>(
+          p->H1.as<float>(), H1_trace + static_cast<size_t>(t) * p->npix * p->k, p->npix, p->k, KP);
+      ++p->launches;
+    }
+    if (H2_trace) {
+      hgru::unpad_channels_kernel<<<nblk(p->npix * p->k), 256, 0, st>>>(
+          p->H2.as<float>(), H2_trace + static_cast<size_t>(t) * p->npix * p->k, p->npix, p->k, KP);
+      ++p->launches;
+    }
+  }
+  return 0;
+}
+
+// The recurrence on padded buffers: X = Xp, state in p->H2 (in/out).
+static int hgru_run_padded(hgru_plan_s* p, const float* Xp, float* H1_trace, float* H2_trace, cudaStream_t st) {
+  if (!p->params_set) return fail(HGRU_E_STATE, "hgru_forward before hgru_set_params");
+  p->launches = 0;
+  p->timer.reset();
+  int rc = (p->mode == HGRU_MODE_BF16) ? hgru_run_bf16(p, Xp, H1_trace, H2_trace, st)
+                                       : hgru_run_fp32(p, Xp, H1_trace, H2_trace, st);
+  if (rc) return rc;
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -412,11 +478,11 @@ static int pose_forward_impl(pose_plan_s* p, const float* depth, const float* H2
     a.wpk = p->wpk2.as<__nv_bfloat16>(); a.bias = p->b2.as<float>();
     a.scale = p->bn_scale(1); a.shift = p->bn_shift(1);
     a.out = p->conv2.as<float>(); a.out_bf16 = p->act_conv2.as<__nv_bfloat16>();
-    if ((rc = dispatch_tc<hgru::EpiBiasReluAffine>(3, KP, p->map_pool1, a, st))) return rc;
+    if ((rc = dispatch_tc_stem(KP, p->map_pool1, a, st))) return rc;
     a.wpk = p->wpk3.as<__nv_bfloat16>(); a.bias = p->b3.as<float>();
     a.scale = p->bn_scale(2); a.shift = p->bn_shift(2);
     a.out = h->Xp.as<float>(); a.out_bf16 = nullptr;
-    if ((rc = dispatch_tc<hgru::EpiBiasReluAffine>(3, KP, p->map_conv2, a, st))) return rc;
+    if ((rc = dispatch_tc_stem(KP, p->map_conv2, a, st))) return rc;
   } else {
     if ((rc = dispatch_simt_conv(3, p->pool1.as<float>(), p->w2.as<float>(), p->b2.as<float>(), p->bn_scale(1),
                                  p->bn_shift(1), p->conv2.as<float>(), N, HW, HW, KP, KP, 1, st)))
