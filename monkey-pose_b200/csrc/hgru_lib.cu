@@ -10,6 +10,7 @@
 #include <string>
 #include <vector>
 
+#include "gemm_tc.cuh"
 #include "hconv_tc.cuh"
 #include "simt_kernels.cuh"
 #include "tc_host.cuh"
@@ -438,6 +439,10 @@ struct pose_plan_s {
   DevBuf depth, pool1, conv2, w1, b1, w2, b2, w3, b3, fc1_w, fc1_b, fc2_w, fc2_b, bn, part, fc1, out;
   DevBuf act_pool1, act_conv2, wpk2, wpk3;         // tensor-core stem
   CUtensorMap map_pool1, map_conv2;
+  DevBuf fc1_wt, fc1_a;                            // tensor-core fc_1: bf16 [F][K] weights, bf16 [N][K] input
+  CUtensorMap map_fc_a, map_fc_b;
+  bool fc1_tc = false;
+  int fc_splits = 1, fc_kbps = 1;
   float* bn_scale(int i) const { return bn.as<float>() + static_cast<size_t>(i) * 2 * bnw; }
   float* bn_shift(int i) const { return bn_scale(i) + bnw; }
   int bnw = 0;
@@ -445,7 +450,7 @@ struct pose_plan_s {
     return hg.workspace() + depth.bytes + pool1.bytes + conv2.bytes + w1.bytes + b1.bytes + w2.bytes +
            b2.bytes + w3.bytes + b3.bytes + fc1_w.bytes + fc1_b.bytes + fc2_w.bytes + fc2_b.bytes +
            bn.bytes + part.bytes + fc1.bytes + out.bytes + act_pool1.bytes + act_conv2.bytes +
-           wpk2.bytes + wpk3.bytes;
+           wpk2.bytes + wpk3.bytes + fc1_wt.bytes + fc1_a.bytes;
   }
 };
 
@@ -453,7 +458,7 @@ static void pose_plan_free(pose_plan_s* p) {
   hgru_plan_free(&p->hg);
   DevBuf* all[] = {&p->depth, &p->pool1, &p->conv2, &p->w1, &p->b1, &p->w2, &p->b2, &p->w3, &p->b3,
                    &p->fc1_w, &p->fc1_b, &p->fc2_w, &p->fc2_b, &p->bn, &p->part, &p->fc1, &p->out,
-                   &p->act_pool1, &p->act_conv2, &p->wpk2, &p->wpk3};
+                   &p->act_pool1, &p->act_conv2, &p->wpk2, &p->wpk3, &p->fc1_wt, &p->fc1_a};
   for (auto b : all) b->release();
 }
 
@@ -467,7 +472,7 @@ static int pose_forward_impl(pose_plan_s* p, const float* depth, const float* H2
   int rc;
   p->launches = 0;
   // conv_1 + relu + pool_1 + BN (hgru_pose.py:50-60)
-  hgru::stem_conv1_pool_bn_kernel<<<nblk(npix * KP), 256, 0, st>>>(
+  hgru::stem_conv1_pool_bn_kernel<<<nblk(npix * (KP / 8)), 256, sizeof(float) * 12 * KP, st>>>(
       depth, p->w1.as<float>(), p->b1.as<float>(), p->bn_scale(0), p->bn_shift(0), p->pool1.as<float>(),
       tc ? p->act_pool1.as<__nv_bfloat16>() : nullptr, N, HW, HW, C, KP);
   ++p->launches;
@@ -501,15 +506,26 @@ static int pose_forward_impl(pose_plan_s* p, const float* depth, const float* H2
   }
   if ((rc = hgru_run_padded(h, h->Xp.as<float>(), nullptr, nullptr, st))) return rc;
   p->launches += h->launches;
-  // BN (:82-90) folded into the A-operand load of fc_1 (:91); split-K partial sums
+  // BN (:82-90) folded into the A-operand of fc_1 (:91); split-K partial sums
   const int K = HW * HW * C;
-  const int kslice = round_up((K + p->nsplit - 1) / p->nsplit, 16);
-  dim3 g1((p->F + 63) / 64, (N + 63) / 64, p->nsplit);
-  hgru::fc1_splitk_kernel<<<g1, 256, 0, st>>>(h->H2.as<float>(), p->fc1_w.as<float>(), p->bn_scale(3),
-                                              p->bn_shift(3), p->part.as<float>(), N, K, p->F, C, KP, kslice);
+  int nsplit = p->nsplit;
+  if (p->fc1_tc) {
+    hgru::fc1_pack_a_kernel<<<nblk(npix * C), 256, 0, st>>>(h->H2.as<float>(), p->bn_scale(3), p->bn_shift(3),
+                                                           p->fc1_a.as<__nv_bfloat16>(), npix, C, KP);
+    hgru::GemmArgs g{N, p->F, K, p->fc_kbps, p->part.as<float>()};
+    dim3 grid((p->F + hgru::kGemmBN - 1) / hgru::kGemmBN, (N + hgru::kGemmBM - 1) / hgru::kGemmBM, p->fc_splits);
+    hgru::gemm_tc_splitk_kernel<<<grid, 256, hgru::kGemmSmemBytes, st>>>(p->map_fc_a, p->map_fc_b, g);
+    nsplit = p->fc_splits;
+    ++p->launches;
+  } else {
+    const int kslice = round_up((K + p->nsplit - 1) / p->nsplit, 16);
+    dim3 g1((p->F + 63) / 64, (N + 63) / 64, p->nsplit);
+    hgru::fc1_splitk_kernel<<<g1, 256, 0, st>>>(h->H2.as<float>(), p->fc1_w.as<float>(), p->bn_scale(3),
+                                                p->bn_shift(3), p->part.as<float>(), N, K, p->F, C, KP, kslice);
+  }
   // + bias, relu (:92), BN (:95-103), fc_out (:104)
   hgru::fc_tail_kernel<<<N, 256, sizeof(float) * p->F, st>>>(
-      p->part.as<float>(), p->nsplit, p->fc1_b.as<float>(), p->bn_scale(4), p->bn_shift(4),
+      p->part.as<float>(), nsplit, p->fc1_b.as<float>(), p->bn_scale(4), p->bn_shift(4),
       p->fc2_w.as<float>(), p->fc2_b.as<float>(), p->fc1.as<float>(), out, N, p->F, p->O);
   p->launches += 2;
   CUDA_TRY(cudaGetLastError());
@@ -596,10 +612,36 @@ int pose_plan_create(int N, int HW, int C, int S, int T, int F, int O, int mode,
   A(p->pool1, act); A(p->conv2, act);
   A(p->w1, sizeof(float) * 9 * C); A(p->b1, sizeof(float) * KP);
   A(p->b2, sizeof(float) * KP); A(p->b3, sizeof(float) * KP);
-  A(p->fc1_w, sizeof(float) * K * F); A(p->fc1_b, sizeof(float) * F);
+  // fc_1 on tensor cores needs a 16-byte aligned K-major row pitch (K % 8 == 0)
+  p->fc1_tc = (mode == HGRU_MODE_BF16) && (K % 8 == 0);
+  if (p->fc1_tc) {
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int total_kb = static_cast<int>((K + hgru::kGemmBK - 1) / hgru::kGemmBK);
+    // The K split depends on K and F only (not on the batch), so a frame's result is bitwise
+    // independent of its batch neighbours: ~2 M-tiles x N-tiles x splits CTAs fill the SMs.
+    const int ntiles_n = (F + hgru::kGemmBN - 1) / hgru::kGemmBN;
+    int splits = sms / (2 * ntiles_n);
+    if (splits < 1) splits = 1;
+    if (splits > total_kb) splits = total_kb;
+    p->fc_kbps = (total_kb + splits - 1) / splits;
+    p->fc_splits = (total_kb + p->fc_kbps - 1) / p->fc_kbps;
+    A(p->fc1_wt, sizeof(__nv_bfloat16) * K * F);
+    A(p->fc1_a, sizeof(__nv_bfloat16) * K * N);
+    if (!rc && (hgru::make_kmajor_bf16_map(&p->map_fc_a, p->fc1_a.p, N, K, hgru::kGemmBM) ||
+                hgru::make_kmajor_bf16_map(&p->map_fc_b, p->fc1_wt.p, F, K, hgru::kGemmBN)))
+      rc = fail(HGRU_E_CUDA, "cuTensorMapEncodeTiled (fc_1) failed");
+    if (!rc && cudaFuncSetAttribute(hgru::gemm_tc_splitk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    hgru::kGemmSmemBytes) != cudaSuccess)
+      rc = fail(HGRU_E_CUDA, "cudaFuncSetAttribute(gemm_tc_splitk_kernel) failed");
+  } else {
+    A(p->fc1_w, sizeof(float) * K * F);
+  }
+  A(p->fc1_b, sizeof(float) * F);
   A(p->fc2_w, sizeof(float) * F * O); A(p->fc2_b, sizeof(float) * O);
   A(p->bn, sizeof(float) * 5 * 2 * p->bnw);
-  A(p->part, sizeof(float) * p->nsplit * N * F); A(p->fc1, sizeof(float) * N * F); A(p->out, sizeof(float) * N * O);
+  A(p->part, sizeof(float) * (p->fc1_tc ? p->fc_splits : p->nsplit) * N * F); A(p->fc1, sizeof(float) * N * F); A(p->out, sizeof(float) * N * O);
   if (mode == HGRU_MODE_FP32) {
     A(p->w2, sizeof(float) * 9 * KP * KP); A(p->w3, sizeof(float) * 9 * KP * KP);
   } else if (!rc) {
@@ -654,7 +696,13 @@ int pose_set_params(pose_plan_t p, const pose_params_t* q, float eps, void* stre
     hgru::pack_weights_kernel<<<nblk(total), 256, 0, st>>>(q->conv_3_filters, p->wpk3.as<__nv_bfloat16>(), 9, C, KP / 16, KP);
   }
   const size_t K = static_cast<size_t>(p->HW) * p->HW * C;
-  CUDA_TRY(cudaMemcpyAsync(p->fc1_w.p, q->fc_1_weights, sizeof(float) * K * F, cudaMemcpyDeviceToDevice, st));
+  if (p->fc1_tc) {
+    dim3 tg(static_cast<unsigned>((K + 31) / 32), (F + 31) / 32);
+    hgru::transpose_to_bf16_kernel<<<tg, 256, 0, st>>>(q->fc_1_weights, p->fc1_wt.as<__nv_bfloat16>(),
+                                                     static_cast<int>(K), F);
+  } else {
+    CUDA_TRY(cudaMemcpyAsync(p->fc1_w.p, q->fc_1_weights, sizeof(float) * K * F, cudaMemcpyDeviceToDevice, st));
+  }
   CUDA_TRY(cudaMemcpyAsync(p->fc1_b.p, q->fc_1_biases, sizeof(float) * F, cudaMemcpyDeviceToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(p->fc2_w.p, q->fc_out_weights, sizeof(float) * F * O, cudaMemcpyDeviceToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(p->fc2_b.p, q->fc_out_biases, sizeof(float) * O, cudaMemcpyDeviceToDevice, st));

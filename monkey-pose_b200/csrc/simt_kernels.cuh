@@ -128,61 +128,6 @@ conv_simt_kernel(const float* __restrict__ in, const float* __restrict__ w,
 }
 
 // ------------------------------------------------------------------------------------------------
-// Stem head: conv 3x3 (1 -> C) + bias + ReLU (hgru_pose.py:50,146-148), 2x2/2 max-pool (:51,134-137)
-// and the inference batch-norm affine (:52-60), fused: [N,2H,2W,1] -> [N,H,W,C].  Bandwidth-bound
-// stencil; one thread per (pooled pixel, channel); optionally also emits the bf16 chunked copy.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-stem_conv1_pool_bn_kernel(const float* __restrict__ depth, const float* __restrict__ w /*[3][3][1][C]*/,
-                          const float* __restrict__ bias, const float* __restrict__ scale,
-                          const float* __restrict__ shift, float* __restrict__ out,
-                          __nv_bfloat16* __restrict__ out_bf16, int N, int H, int W, int C, int KP) {
-  const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-  const size_t total = static_cast<size_t>(N) * H * W * KP;
-  if (idx >= total) return;
-  const int c = idx % KP;
-  const size_t p = idx / KP;
-  const int x = p % W;
-  const int y = (p / W) % H;
-  const int n = p / (static_cast<size_t>(W) * H);
-  const int IH = 2 * H, IW = 2 * W;
-  float r = 0.f;
-  if (c < C) {
-    float wv[9];
-#pragma unroll
-    for (int t = 0; t < 9; ++t) wv[t] = w[t * C + c];
-    // 4x4 input neighbourhood of the 2x2 pooling window
-    float v[4][4];
-#pragma unroll
-    for (int rr = 0; rr < 4; ++rr)
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int yy = 2 * y - 1 + rr, xx = 2 * x - 1 + q;
-        v[rr][q] = (yy >= 0 && yy < IH && xx >= 0 && xx < IW)
-                       ? depth[(static_cast<size_t>(n) * IH + yy) * IW + xx] : 0.f;
-      }
-    const float b = bias[c];
-    float m = -INFINITY;
-#pragma unroll
-    for (int py = 0; py < 2; ++py)
-#pragma unroll
-      for (int px = 0; px < 2; ++px) {
-        float a = 0.f;
-#pragma unroll
-        for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-          for (int dx = 0; dx < 3; ++dx) a = fmaf(v[py + dy][px + dx], wv[dy * 3 + dx], a);
-        m = fmaxf(m, fmaxf(a + b, 0.f));
-      }
-    r = m * scale[c] + shift[c];
-  }
-  out[idx] = r;
-  if (out_bf16)
-    out_bf16[((static_cast<size_t>(n) * (KP >> 3) + (c >> 3)) * (H * W) + static_cast<size_t>(y) * W + x) * 8 + (c & 7)] =
-        __float2bfloat16(r);
-}
-
-// ------------------------------------------------------------------------------------------------
 // Internal activation layout: fp32 NHWC with the channel dimension padded to KP (a multiple of 16,
 // pad channels are zero) so every pixel-chunk of 8 channels is 32 B (fp32) / 16 B (bf16) aligned.
 // Elementwise kernels below: one thread = one pixel-chunk (8 channels).
@@ -206,6 +151,72 @@ __device__ __forceinline__ void st8_bf16(__nv_bfloat16* p, const F8& f) {
 __device__ __forceinline__ __nv_bfloat16* chunk_ptr(__nv_bfloat16* base, int n, int cg, size_t pin,
                                                     int HW, int CG) {
   return base + ((static_cast<size_t>(n) * CG + cg) * HW + pin) * 8;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stem head: conv 3x3 (1 -> C) + bias + ReLU (hgru_pose.py:50,146-148), 2x2/2 max-pool (:51,134-137)
+// and the inference batch-norm affine (:52-60), fused: [N,2H,2W,1] -> [N,H,W,KP] (+ bf16 chunked copy).
+// Bandwidth-bound stencil.  One thread = one pooled pixel x one chunk of 8 channels, so a warp writes
+// 32/CG whole pixels = 1 KB of contiguous fp32; filter taps / bias / affine live in shared memory.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+stem_conv1_pool_bn_kernel(const float* __restrict__ depth, const float* __restrict__ w /*[3][3][1][C]*/,
+                          const float* __restrict__ bias, const float* __restrict__ scale,
+                          const float* __restrict__ shift, float* __restrict__ out,
+                          __nv_bfloat16* __restrict__ out_bf16, int N, int H, int W, int C, int KP) {
+  extern __shared__ float smem_f[];
+  float* wsm = smem_f;             // [9][KP]
+  float* bsm = wsm + 9 * KP;       // bias, scale, shift: [3][KP]
+  for (int e = threadIdx.x; e < 9 * KP; e += blockDim.x) {
+    const int t = e / KP, c = e - t * KP;
+    wsm[e] = (c < C) ? w[t * C + c] : 0.f;
+  }
+  for (int e = threadIdx.x; e < KP; e += blockDim.x) {
+    bsm[e] = (e < C) ? bias[e] : 0.f;
+    bsm[KP + e] = (e < C) ? scale[e] : 0.f;
+    bsm[2 * KP + e] = (e < C) ? shift[e] : 0.f;
+  }
+  __syncthreads();
+  const int CG = KP >> 3;
+  const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  const size_t npix = static_cast<size_t>(N) * H * W;
+  if (idx >= npix * CG) return;
+  const int cg = idx % CG;
+  const size_t p = idx / CG;
+  const int x = p % W;
+  const int y = (p / W) % H;
+  const int n = p / (static_cast<size_t>(W) * H);
+  const int IH = 2 * H, IW = 2 * W;
+  float v[4][4];                    // 4x4 input neighbourhood of the 2x2 pooling window
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int yy = 2 * y - 1 + rr, xx = 2 * x - 1 + q;
+      v[rr][q] = (yy >= 0 && yy < IH && xx >= 0 && xx < IW)
+                     ? __ldg(depth + (static_cast<size_t>(n) * IH + yy) * IW + xx) : 0.f;
+    }
+  F8 r;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cg * 8 + j;
+    float m = -INFINITY;
+#pragma unroll
+    for (int py = 0; py < 2; ++py)
+#pragma unroll
+      for (int px = 0; px < 2; ++px) {
+        float a = 0.f;
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) a = fmaf(v[py + dy][px + dx], wsm[(dy * 3 + dx) * KP + c], a);
+        m = fmaxf(m, a);
+      }
+    // relu and max commute; pad channels have zero scale/shift -> 0
+    r.v[j] = fmaxf(m + bsm[c], 0.f) * bsm[KP + c] + bsm[2 * KP + c];
+  }
+  st8(out + p * KP + cg * 8, r);
+  if (out_bf16) st8_bf16(chunk_ptr(out_bf16, n, cg, static_cast<size_t>(y) * W + x, H * W, CG), r);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -46,4 +46,19 @@ inline int make_act_tensor_map(CUtensorMap* map, const void* base, int N, int CG
   return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
 }
 
+// Tensor map over a K-major bf16 matrix [rows][K] (row pitch K*2 bytes, K % 8 == 0) with boxes of
+// (64 K-elements = 128 bytes) x box_rows and the 128-byte swizzle: the canonical SW128 UMMA tile.
+inline int make_kmajor_bf16_map(CUtensorMap* map, const void* base, size_t rows, size_t K, int box_rows) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return -1;
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(K) * 2};
+  cuuint32_t box[2] = {64, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
+}
+
 }  // namespace hgru
