@@ -1,0 +1,118 @@
+// Development harness (GPU box only): tap-stacked tcgen05 conv vs a naive fp32 conv.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "../hconv_stack.cuh"
+#include "../tc_host.cuh"
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e_), __LINE__); exit(2);} } while (0)
+
+__global__ void naive_conv(const float* in, const float* w, const float* bias, float* out, int N, int H, int W, int k, int S) {
+  size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t total = (size_t)N * H * W * k;
+  if (idx >= total) return;
+  int co = idx % k; size_t p = idx / k; int x = p % W; int y = (p / W) % H; int n = p / ((size_t)W * H);
+  int pad = (S - 1) / 2; float acc = 0.f;
+  for (int dy = 0; dy < S; ++dy) { int yy = y + dy - pad; if (yy < 0 || yy >= H) continue;
+    for (int dx = 0; dx < S; ++dx) { int xx = x + dx - pad; if (xx < 0 || xx >= W) continue;
+      const float* ip = in + ((size_t)(n * H + yy) * W + xx) * k; const float* wp = w + ((size_t)(dy * S + dx) * k) * k + co;
+      for (int ci = 0; ci < k; ++ci) acc += ip[ci] * wp[(size_t)ci * k]; } }
+  out[idx] = acc + bias[co];
+}
+static float bf16r(float v) { return __bfloat162float(__float2bfloat16(v)); }
+
+template <int KP, int T, int KC, int CS>
+int run_case(int N, int H, int W, int k, int grid_override, int iters) {
+  using Cfg = hgru::StackCfg<KP, T, KC, CS>;
+  const int S = 15, CG = KP / 8;
+  printf("stack case KP=%d T=%d KC=%d CS=%d k=%d N=%d H=%d W=%d smem=%d cols=%d\n", KP, T, KC, CS, k, N, H, W, Cfg::SMEM_BYTES, Cfg::COLS);
+  size_t npix = (size_t)N * H * W;
+  std::vector<float> in(npix * k), w((size_t)S * S * k * k), bias(KP, 0.f);
+  srand(123);
+  for (auto& v : in) v = bf16r((rand() / (float)RAND_MAX) * 2.f - 1.f);
+  for (auto& v : w) v = bf16r(((rand() / (float)RAND_MAX) * 2.f - 1.f) * 0.05f);
+  for (int c = 0; c < k; ++c) bias[c] = (rand() / (float)RAND_MAX) - 0.5f;
+  std::vector<__nv_bfloat16> act((size_t)N * CG * H * W * 8, __float2bfloat16(0.f));
+  for (int n = 0; n < N; ++n) for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) for (int c = 0; c < k; ++c)
+    act[((((size_t)n * CG + c / 8) * H + y) * W + x) * 8 + (c % 8)] = __float2bfloat16(in[(((size_t)n * H + y) * W + x) * k + c]);
+  float *d_in, *d_w, *d_bias, *d_ref, *d_out; __nv_bfloat16 *d_act, *d_wpk;
+  size_t wpk_elems = (size_t)15 * Cfg::KSTEPS * Cfg::NG * 2 * 128 * 8;
+  CK(cudaMalloc(&d_in, in.size() * 4)); CK(cudaMalloc(&d_w, w.size() * 4)); CK(cudaMalloc(&d_bias, KP * 4));
+  CK(cudaMalloc(&d_ref, npix * k * 4)); CK(cudaMalloc(&d_out, npix * KP * 4));
+  CK(cudaMalloc(&d_act, act.size() * 2)); CK(cudaMalloc(&d_wpk, wpk_elems * 2));
+  CK(cudaMemcpy(d_in, in.data(), in.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_w, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_bias, bias.data(), KP * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_act, act.data(), act.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemset(d_out, 0xFF, npix * KP * 4));
+  hgru::pack_weights_stack_kernel<<<(unsigned)((wpk_elems + 255) / 256), 256>>>(d_w, d_wpk, k, Cfg::KSTEPS, T, KC, Cfg::NG);
+  CK(cudaDeviceSynchronize());
+  CUtensorMap map;
+  if (hgru::make_act_tensor_map(&map, d_act, N, CG, H, W, Cfg::COLS, Cfg::ROWS, CG)) { printf("map fail\n"); return 1; }
+  hgru::TcConvArgs a{};
+  a.N = N; a.H = H; a.W = W; a.KP = KP; a.kreal = k;
+  a.units_x = (W + 63) / 64; a.units_y = (H + 15) / 16; a.num_units = N * a.units_x * a.units_y;
+  a.wpk = d_wpk; a.bias = d_bias; a.out = d_out;
+  auto kern = hgru::hconv_stack_kernel<KP, T, KC, CS, hgru::EpiBias>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  int sms = 0; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+  int grid = grid_override > 0 ? grid_override : (a.num_units < sms ? a.num_units : sms);
+  grid = (grid + CS - 1) / CS * CS;
+  cudaLaunchConfig_t cfg{}; cfg.gridDim = dim3(grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  CK(cudaLaunchKernelEx(&cfg, kern, map, a));
+  CK(cudaDeviceSynchronize());
+  size_t total = npix * k;
+  naive_conv<<<(unsigned)((total + 255) / 256), 256>>>(d_in, d_w, d_bias, d_ref, N, H, W, k, S);
+  CK(cudaDeviceSynchronize());
+  std::vector<float> outp(npix * KP), ref(total);
+  CK(cudaMemcpy(outp.data(), d_out, npix * KP * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(ref.data(), d_ref, total * 4, cudaMemcpyDeviceToHost));
+  double maxerr = 0, maxref = 0; size_t bad = 0, nan = 0;
+  for (size_t p = 0; p < npix; ++p) for (int c = 0; c < k; ++c) {
+    float o = outp[p * KP + c], r = ref[p * k + c];
+    if (!(o == o)) { ++nan; continue; }
+    double e = fabs((double)o - r); if (e > maxerr) maxerr = e; if (fabs(r) > maxref) maxref = fabs(r);
+    if (e > 1e-3 * (1.0 + fabs(r))) ++bad; }
+  printf("  grid=%d units=%d maxerr=%.3e maxref=%.3e bad=%zu nan=%zu\n", grid, a.num_units, maxerr, maxref, bad, nan);
+  if (bad || nan) {
+    for (int y = 0; y < (H < 32 ? H : 32); ++y) { for (int x = 0; x < (W < 64 ? W : 64); ++x) {
+      float o = outp[(((size_t)0 * H + y) * W + x) * KP], r = ref[(((size_t)0 * H + y) * W + x) * k];
+      putchar(!(o == o) ? 'N' : (fabs(o - r) > 1e-3 * (1 + fabs(r)) ? 'x' : '.')); } putchar('\n'); }
+  }
+  if (iters > 0 && !bad && !nan) {
+    long long* d_prof; CK(cudaMalloc(&d_prof, grid * 8 * sizeof(long long))); CK(cudaMemset(d_prof, 0, grid * 8 * sizeof(long long)));
+    hgru::TcConvArgs ap = a; ap.prof = d_prof;
+    CK(cudaLaunchKernelEx(&cfg, kern, map, ap)); CK(cudaDeviceSynchronize());
+    std::vector<long long> pr(grid * 8); CK(cudaMemcpy(pr.data(), d_prof, grid * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+    double av[6] = {0, 0, 0, 0, 0, 0}; for (int b = 0; b < grid; ++b) for (int i = 0; i < 6; ++i) av[i] += pr[b * 8 + i] / (double)grid;
+    printf("  prof (avg cycles/CTA): mma_total=%.0f wait_win=%.0f wait_acc_empty=%.0f wait_w_full=%.0f | epi_total=%.0f epi_wait_acc_full=%.0f\n", av[0], av[1], av[2], av[3], av[4], av[5]);
+    cudaFree(d_prof);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int i = 0; i < 2; ++i) cudaLaunchKernelEx(&cfg, kern, map, a);
+    cudaEventRecord(e0);
+    for (int i = 0; i < iters; ++i) cudaLaunchKernelEx(&cfg, kern, map, a);
+    cudaEventRecord(e1); CK(cudaDeviceSynchronize());
+    float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= iters;
+    printf("  time %.3f ms -> %.1f TFLOP/s algorithmic\n", ms, 2.0 * npix * 225.0 * k * k / ms * 1e-9);
+  }
+  cudaFree(d_in); cudaFree(d_w); cudaFree(d_bias); cudaFree(d_ref); cudaFree(d_out); cudaFree(d_act); cudaFree(d_wpk);
+  return (bad || nan) ? 1 : 0;
+}
+int main(int argc, char** argv) {
+  int which = argc > 1 ? atoi(argv[1]) : 0, f = 0;
+  if (which == 0 || which == 1) f += run_case<32, 5, 25, 1>(2, 64, 64, 25, 0, 0);
+  if (which == 0 || which == 2) f += run_case<32, 5, 25, 1>(3, 64, 64, 25, 5, 0);      // several units per CTA, idle tail
+  if (which == 0 || which == 3) f += run_case<32, 5, 25, 1>(2, 40, 24, 20, 0, 0);      // ragged, k < KC
+  if (which == 0 || which == 4) f += run_case<32, 4, 32, 1>(2, 64, 64, 32, 0, 0);
+  if (which == 0 || which == 5) f += run_case<16, 8, 16, 1>(2, 32, 48, 16, 0, 0);
+  if (which == 0 || which == 6) f += run_case<32, 5, 25, 2>(3, 64, 64, 25, 6, 0);      // cluster of 2, multicast
+  if (which == 0 || which == 7) f += run_case<32, 5, 25, 1>(256, 64, 64, 25, 0, 5);
+  if (which == 0 || which == 8) f += run_case<32, 5, 25, 2>(256, 64, 64, 25, 0, 5);
+  if (which == 0 || which == 9) f += run_case<32, 4, 32, 2>(256, 64, 64, 32, 0, 5);
+  printf(f ? "FAILED %d\n" : "ALL OK\n", f);
+  return f;
+}

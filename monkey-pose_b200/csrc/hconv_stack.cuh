@@ -1,0 +1,381 @@
+// Tap-stacked implicit-GEMM 15x15 convolution for narrow layers (k <= 32) on tcgen05.
+//
+// Why: an M=128 UMMA reads 4 KB of A from shared memory whatever N is, and shared memory delivers
+// 128 B/clk (profiles/r01_mma_shape_microbench.log): N = 32 runs at 35 % of the tensor issue rate,
+// N >= 128 at 100 %.  With k = 25 output channels the N dimension is filled by stacking T
+// horizontally adjacent filter taps into one B operand:
+//     B[(s, c)][ci] = W[dy][T*g + T-1-s][ci][c]          (s = 0..T-1,  N = T*KC <= 128)
+// One MMA with the pixel window at tap (dy, T*g + T-1) then yields, for every window position
+// `pos`, the T partial products  D[pos][s] = in[pos + T*g + T-1 - PAD] * W[dy][T*g+T-1-s],
+// and the convolution is  out[x] = sum_s D[x - s][s].  The shift by s is undone in the epilogue:
+// a pixel row of a tile lives in 8 consecutive TMEM lanes of one warp, so a rotate-by-s shuffle
+// delivers D[x-s][s] from the same tile when x%8 >= s and otherwise produces exactly the value
+// lane x%8 of the NEXT tile needs -- kept in registers as a carry while the CTA walks the tiles
+// of a 16-row block from left to right (one extra leading tile per block supplies the first carry).
+//
+// Unit = 16 rows x 64 columns of one frame = 1 carry tile + 8 output tiles, whole halo window
+// (30 x ~82 pixels x KP channels) resident in shared memory.  TMEM holds four 128-column
+// accumulators: tiles are processed in pairs, two accumulating while two drain, so the epilogue
+// (shuffles + fused gate/integration math + global I/O) hides behind the MMAs.  The stacked
+// weights (360 KB at k = 25) stream through a 4-stage ring once per tile pair; with CS = 2 the two
+// CTAs of a cluster each fetch half of every stage and multicast it, halving L2 traffic.
+//
+// Warps: w0 weight producer, w1 MMA issuer, w2 TMEM alloc, w3 window producer, w4..7 epilogue.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "hconv_tc.cuh"
+#include "sm100_ptx.cuh"
+
+namespace hgru {
+
+template <int KP_, int T_, int KC_, int CS_>
+struct StackCfg {
+  static constexpr int KP = KP_, T = T_, KC = KC_, CS = CS_;
+  static constexpr int S = 15, PAD = 7;
+  static constexpr int KSTEPS = KP / 16;
+  static constexpr int CG = KP / 8;
+  static constexpr int NG = (S + T - 1) / T;             // tap groups per filter row
+  static constexpr int NPAD = 128;                        // UMMA N
+  static constexpr int MAXNTO = 8;                        // output tiles per unit (64 columns)
+  static constexpr int ROWS = kTileRows + S - 1;          // 30
+  static constexpr int COLS = 8 * MAXNTO + T * (NG - 1) + 8;
+  static constexpr int ROW_PITCH = COLS * 16;
+  static constexpr int CHUNK_PITCH = ROWS * ROW_PITCH;
+  static constexpr int WIN_BYTES = CG * CHUNK_PITCH;
+  static constexpr int MIN_COL = T - 16;                  // image column of window column 0, minus x0
+  static constexpr int BLK_BYTES = 2 * NPAD * 16;         // one (dy, q, g) weight block (4 KB)
+  static constexpr int STAGE_BYTES = NG * BLK_BYTES;      // all tap groups of one (dy, q)
+  static constexpr int PASS_STAGES = S * KSTEPS;          // stages per tile pair
+  static constexpr int WSTAGES = 4;
+  static constexpr int NUM_BARS = 2 + 2 * WSTAGES + 8;
+  static constexpr int SMEM_BYTES = WIN_BYTES + WSTAGES * STAGE_BYTES + NUM_BARS * 8 + 16 + 1024;
+  static_assert(T * KC <= NPAD, "stacked taps must fit N = 128");
+  static_assert(KC <= KP && KP % 16 == 0, "channel padding");
+  static_assert((CHUNK_PITCH >> 4) < 16384, "LBO range");
+  static_assert(STAGE_BYTES % (16 * CS) == 0, "stage must split evenly over the cluster");
+  static_assert(2 * COLS <= 256, "TMA box limit");
+};
+
+// Stacked weight packing: HWIO fp32 [15][15][k][k] -> bf16 [dy][q][g][2 chunks][128 n][8 ci],
+// n = s*KC + c  <->  tap dx = T*g + T-1-s, output channel c (zero where dx >= 15 or c, ci >= k).
+__global__ void pack_weights_stack_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wpk,
+                                          int k, int ksteps, int T, int KC, int NG) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  const size_t total = static_cast<size_t>(15) * ksteps * NG * 2 * 128 * 8;
+  if (i >= total) return;
+  const int j = i & 7;
+  size_t r = i >> 3;
+  const int n = r & 127; r >>= 7;
+  const int ch = r & 1; r >>= 1;
+  const int g = r % NG; r /= NG;
+  const int q = r % ksteps;
+  const int dy = r / ksteps;
+  const int s = n / KC, c = n - s * KC;
+  const int dx = T * g + T - 1 - s;
+  const int ci = q * 16 + ch * 8 + j;
+  float v = 0.f;
+  if (s < T && dx >= 0 && dx < 15 && c < k && ci < k) v = w[((static_cast<size_t>(dy) * 15 + dx) * k + ci) * k + c];
+  wpk[i] = __float2bfloat16(v);
+}
+
+namespace detail {
+template <int N>
+__device__ __forceinline__ void tmem_ld_f(uint32_t taddr, float* v);
+template <>
+__device__ __forceinline__ void tmem_ld_f<16>(uint32_t taddr, float* v) {
+  uint32_t u[16];
+  sm100::tmem_ld16(taddr, u);
+  sm100::tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(u[i]);
+}
+template <>
+__device__ __forceinline__ void tmem_ld_f<8>(uint32_t taddr, float* v) {
+  uint32_t u[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+               : "r"(taddr));
+  sm100::tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(u[i]);
+}
+template <>
+__device__ __forceinline__ void tmem_ld_f<1>(uint32_t taddr, float* v) {
+  uint32_t u;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(u) : "r"(taddr));
+  sm100::tmem_ld_wait();
+  v[0] = __uint_as_float(u);
+}
+// KC consecutive fp32 columns of this thread's TMEM lane
+template <int KC>
+__device__ __forceinline__ void tmem_ld_block(uint32_t taddr, float (&v)[KC]) {
+  static_assert(KC == 16 || KC == 25 || KC == 32, "supported stacked channel strides");
+  if constexpr (KC == 16) {
+    tmem_ld_f<16>(taddr, v);
+  } else if constexpr (KC == 32) {
+    tmem_ld_f<16>(taddr, v);
+    tmem_ld_f<16>(taddr + 16, v + 16);
+  } else {
+    tmem_ld_f<16>(taddr, v);
+    tmem_ld_f<8>(taddr + 16, v + 16);
+    tmem_ld_f<1>(taddr + 24, v + 24);
+  }
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// multicast 1-D bulk copy: lands at the same shared-memory offset in every CTA of `mask` and
+// completes bytes on the mbarrier at the same offset in each of them
+__device__ __forceinline__ void bulk_load_multicast(uint32_t dst, const void* src, uint32_t bytes,
+                                                    uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1], %2, [%3], %4;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_multicast(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"(mask) : "memory");
+}
+}  // namespace detail
+
+template <int KP, int T, int KC, int CS, class Epi>
+__global__ void __launch_bounds__(256, 1)
+hconv_stack_kernel(const __grid_constant__ CUtensorMap in_map, const TcConvArgs a) {
+  using namespace sm100;
+  using Cfg = StackCfg<KP, T, KC, CS>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t win = base;
+  const uint32_t w_buf = win + Cfg::WIN_BYTES;
+  const uint32_t bars = w_buf + Cfg::WSTAGES * Cfg::STAGE_BYTES;
+  const uint32_t bar_win_full = bars, bar_win_empty = bars + 8;
+  const uint32_t bar_w_full = bars + 16;                             // [WSTAGES]
+  const uint32_t bar_w_empty = bar_w_full + 8 * Cfg::WSTAGES;        // [WSTAGES]
+  const uint32_t bar_acc_full = bar_w_empty + 8 * Cfg::WSTAGES;      // [4]
+  const uint32_t bar_acc_empty = bar_acc_full + 32;                  // [4]
+  const uint32_t tmem_slot = bar_acc_empty + 32;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t crank = (CS > 1) ? detail::cluster_ctarank() : 0u;
+  constexpr uint16_t kMask = static_cast<uint16_t>((1u << CS) - 1u);
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_win_full, 1);
+    mbar_init(bar_win_empty, 1);
+    for (int i = 0; i < Cfg::WSTAGES; ++i) {
+      mbar_init(bar_w_full + 8 * i, 1);
+      mbar_init(bar_w_empty + 8 * i, CS);      // every CTA of the cluster releases the stage
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(bar_acc_full + 8 * i, 1);
+      mbar_init(bar_acc_empty + 8 * i, 128);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&in_map);
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  if constexpr (CS > 1) detail::cluster_sync_all();     // peers' barriers exist before any remote arrive
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  // every CTA runs the same number of iterations (cluster members share the weight stream)
+  const int iters = (a.num_units + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int units_per_frame = a.units_x * a.units_y;
+  const int wseg = a.W < 64 ? a.W : 64;
+  const int NT = 1 + (wseg + 7) / 8;               // carry tile + output tiles, uniform over units
+  const int npairs = (NT + 1) / 2;
+
+  if (warp == 0) {
+    // ---------------- weight producer ----------------
+    if (lane == 0) {
+      uint32_t st = 0, ph = 0;
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wpk);
+      constexpr uint32_t kShare = Cfg::STAGE_BYTES / CS;
+      for (int it = 0; it < iters; ++it)
+        for (int pr = 0; pr < npairs; ++pr)
+          for (int sg = 0; sg < Cfg::PASS_STAGES; ++sg) {
+            mbar_wait(bar_w_empty + 8 * st, ph ^ 1);
+            mbar_arrive_expect_tx(bar_w_full + 8 * st, Cfg::STAGE_BYTES);
+            const uint32_t dst = w_buf + st * Cfg::STAGE_BYTES + crank * kShare;
+            const uint8_t* src = wsrc + static_cast<size_t>(sg) * Cfg::STAGE_BYTES + crank * kShare;
+            if constexpr (CS > 1) detail::bulk_load_multicast(dst, src, kShare, bar_w_full + 8 * st, kMask);
+            else bulk_load(dst, src, kShare, bar_w_full + 8 * st);
+            if (++st == Cfg::WSTAGES) { st = 0; ph ^= 1; }
+          }
+    }
+  } else if (warp == 3) {
+    // ---------------- window producer: one TMA box per unit ----------------
+    if (lane == 0) {
+      int vit = 0;
+      for (int it = 0; it < iters; ++it) {
+        const int u = it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);
+        if (u >= a.num_units) continue;
+        const int n = u / units_per_frame;
+        const int r = u - n * units_per_frame;
+        const int uy = r / a.units_x, ux = r - uy * a.units_x;
+        mbar_wait(bar_win_empty, (vit & 1) ^ 1);
+        mbar_arrive_expect_tx(bar_win_full, Cfg::WIN_BYTES);
+        tma_load_4d(win, &in_map, bar_win_full, 2 * (ux * 64 + Cfg::MIN_COL), uy * kTileRows - Cfg::PAD, 0, n);
+        ++vit;
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer (convergent warp, one elected lane issues) ----------------
+    const bool leader = elect_one();
+    constexpr uint32_t idesc = make_idesc(1 /*bf16*/, 128, Cfg::NPAD);
+    const uint64_t adesc0 = make_smem_desc(win, Cfg::CHUNK_PITCH, Cfg::ROW_PITCH);
+    const uint64_t bdesc0 = make_smem_desc(w_buf, Cfg::NPAD * 16, 128);
+    uint32_t st = 0, ph = 0;
+    uint32_t tc = 0;            // running tile counter: TMEM slot = tc & 3, use count = tc >> 2
+    int vit = 0;
+    long long t_win = 0, t_acc = 0, t_w = 0, t_begin = clock64(), t0;
+    for (int it = 0; it < iters; ++it) {
+      const int u = it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);
+      const bool valid = u < a.num_units;
+      if (valid) {
+        t0 = clock64();
+        mbar_wait(bar_win_full, vit & 1);
+        t_win += clock64() - t0;
+        tc_fence_after();
+      }
+      for (int pr = 0; pr < npairs; ++pr) {
+        const int j0 = 2 * pr;
+        const bool two = (j0 + 1) < NT;
+        const uint32_t s0 = tc & 3, s1 = (tc + 1) & 3;
+        t0 = clock64();
+        mbar_wait(bar_acc_empty + 8 * s0, ((tc >> 2) & 1) ^ 1);
+        if (two) mbar_wait(bar_acc_empty + 8 * s1, (((tc + 1) >> 2) & 1) ^ 1);
+        t_acc += clock64() - t0;
+        tc_fence_after();
+        const uint32_t acc0 = tmem_base + s0 * Cfg::NPAD, acc1 = tmem_base + s1 * Cfg::NPAD;
+        const uint64_t a_tile0 = adesc0 + static_cast<uint64_t>(8 * j0);      // 8 pixels = 8 x 16 B
+        uint32_t stage_off = 0;      // (q * 2*CHUNK_PITCH + dy * ROW_PITCH) >> 4, advanced per stage
+        int q = 0;
+        for (int sg = 0; sg < Cfg::PASS_STAGES; ++sg) {
+          t0 = clock64();
+          mbar_wait(bar_w_full + 8 * st, ph);
+          t_w += clock64() - t0;
+          tc_fence_after();
+          const uint64_t bdesc_st = bdesc0 + static_cast<uint64_t>((st * Cfg::STAGE_BYTES) >> 4);
+#pragma unroll
+          for (int g = 0; g < Cfg::NG; ++g) {
+            const uint64_t bdesc = bdesc_st + static_cast<uint64_t>((g * Cfg::BLK_BYTES) >> 4);
+            const uint64_t adesc = a_tile0 + stage_off + static_cast<uint64_t>(T * g);
+            const uint32_t accum = (sg | g) != 0;
+            if (leader) {
+              mma_bf16_ss(acc0, adesc, bdesc, idesc, accum);
+              if (two) mma_bf16_ss(acc1, adesc + 8, bdesc, idesc, accum);
+            }
+          }
+          if (leader) {
+            if constexpr (CS > 1) detail::tc_commit_multicast(bar_w_empty + 8 * st, kMask);
+            else tc_commit(bar_w_empty + 8 * st);
+          }
+          if (++st == Cfg::WSTAGES) { st = 0; ph ^= 1; }
+          // stage order: dy-major, then k-step q
+          if (++q == Cfg::KSTEPS) {
+            q = 0;     // next filter row, back to k-step 0 (the delta may be negative: exact signed division)
+            stage_off += static_cast<uint32_t>((Cfg::ROW_PITCH - (Cfg::KSTEPS - 1) * 2 * Cfg::CHUNK_PITCH) / 16);
+          }
+          else stage_off += (2 * Cfg::CHUNK_PITCH) >> 4;
+        }
+        if (leader) {
+          tc_commit(bar_acc_full + 8 * s0);
+          if (two) tc_commit(bar_acc_full + 8 * s1);
+        }
+        tc += two ? 2 : 1;
+      }
+      if (valid) {
+        if (leader) tc_commit(bar_win_empty);
+        ++vit;
+      }
+    }
+    if (a.prof && leader) {
+      long long* o = a.prof + static_cast<size_t>(blockIdx.x) * 8;
+      o[0] = clock64() - t_begin; o[1] = t_win; o[2] = t_acc; o[3] = t_w;
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ---------------- epilogue: un-stack (rotate + carry), fused math, stores ----------------
+    const int ew = warp & 3;
+    const int m = ew * 32 + lane;
+    const int prow = m >> 3, pcol = m & 7;
+    uint32_t tc = 0;
+    long long e_wait = 0, e_begin = clock64(), e0;
+    for (int it = 0; it < iters; ++it) {
+      const int u = it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);
+      const bool valid = u < a.num_units;
+      const int n = u / units_per_frame;
+      const int r = u - n * units_per_frame;
+      const int uy = r / a.units_x, ux = r - uy * a.units_x;
+      const int y = uy * kTileRows + prow;
+      float carry[KC];
+#pragma unroll
+      for (int c = 0; c < KC; ++c) carry[c] = 0.f;
+#pragma unroll 1
+      for (int j = 0; j < NT; ++j, ++tc) {
+        const uint32_t slot = tc & 3;
+        e0 = clock64();
+        mbar_wait(bar_acc_full + 8 * slot, (tc >> 2) & 1);
+        e_wait += clock64() - e0;
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + slot * Cfg::NPAD;
+        float out[KC], nxt[KC];
+        detail::tmem_ld_block<KC>(taddr, out);
+#pragma unroll
+        for (int c = 0; c < KC; ++c) { out[c] += carry[c]; nxt[c] = 0.f; }
+#pragma unroll
+        for (int s = 1; s < T; ++s) {
+          float blk[KC];
+          detail::tmem_ld_block<KC>(taddr + s * KC, blk);
+          const int src = (lane & ~7) | ((pcol - s) & 7);
+          const bool own = pcol >= s;
+#pragma unroll
+          for (int c = 0; c < KC; ++c) {
+            const float v = __shfl_sync(0xffffffffu, blk[c], src);
+            if (own) out[c] += v; else nxt[c] += v;
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(bar_acc_empty + 8 * slot);          // accumulator drained: MMAs may reuse it
+#pragma unroll
+        for (int c = 0; c < KC; ++c) carry[c] = nxt[c];
+        const int x = ux * 64 + 8 * (j - 1) + pcol;
+        if (valid && j >= 1 && y < a.H && x < a.W) {
+          float acc[KP];
+#pragma unroll
+          for (int c = 0; c < KP; ++c) acc[c] = (c < KC) ? out[c < KC ? c : 0] : 0.f;
+          Epi::template apply<KP>(a, n, y, x, acc);
+        }
+      }
+    }
+    if (a.prof && threadIdx.x == 128) {
+      long long* o = a.prof + static_cast<size_t>(blockIdx.x) * 8;
+      o[4] = clock64() - e_begin; o[5] = e_wait;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if constexpr (CS > 1) detail::cluster_sync_all();     // no CTA exits while a peer may still signal it
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace hgru

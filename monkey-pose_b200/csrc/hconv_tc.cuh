@@ -77,6 +77,7 @@ struct TcConvArgs {
   const float* v1;
   const float* v2;
   const float* rho_t;       // device pointer to the adaptation scale rho[t] of this timestep
+  long long* prof;          // optional per-CTA cycle counters (development; nullptr in production)
 };
 
 __device__ __forceinline__ float fast_sigmoid(float x) { return 1.f / (1.f + __expf(-x)); }

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "gemm_tc.cuh"
+#include "hconv_stack.cuh"
 #include "hconv_tc.cuh"
 #include "simt_kernels.cuh"
 #include "tc_host.cuh"
@@ -121,6 +122,53 @@ int dispatch_tc_stem(int KP, const CUtensorMap& map, const hgru::TcConvArgs& a, 
 #undef TC_CASES_S
 #undef TC_CASE
 
+// ---------------------------------------------------------------- tap-stacked conv (k <= 32, S = 15)
+struct StackGeom { int T, KC, NG, ksteps, box_cols, box_rows; };
+bool stack_geometry(int S, int KP, int k, StackGeom* g) {
+  if (S != 15) return false;
+  if (KP == 32 && k <= 25) { g->T = 5; g->KC = 25; }
+  else if (KP == 32) { g->T = 4; g->KC = 32; }
+  else if (KP == 16) { g->T = 8; g->KC = 16; }
+  else return false;
+  g->NG = (15 + g->T - 1) / g->T;
+  g->ksteps = KP / 16;
+  g->box_cols = 64 + g->T * (g->NG - 1) + 8;
+  g->box_rows = hgru::kTileRows + 14;
+  return true;
+}
+
+template <int KP, int T, int KC, class Epi>
+int launch_stack(const CUtensorMap& map, hgru::TcConvArgs a, cudaStream_t st) {
+  using Cfg = hgru::StackCfg<KP, T, KC, 1>;
+  auto kern = hgru::hconv_stack_kernel<KP, T, KC, 1, Epi>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_done = true;
+  }
+  a.units_x = (a.W + 63) / 64;
+  a.units_y = (a.H + hgru::kTileRows - 1) / hgru::kTileRows;
+  a.num_units = a.N * a.units_x * a.units_y;
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int grid = a.num_units < sms ? a.num_units : sms;
+  kern<<<grid, 256, Cfg::SMEM_BYTES, st>>>(map, a);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+template <class Epi>
+int dispatch_stack(int KP, int T, const CUtensorMap& map, const hgru::TcConvArgs& a, cudaStream_t st) {
+  if (KP == 32 && T == 5) return launch_stack<32, 5, 25, Epi>(map, a, st);
+  if (KP == 32 && T == 4) return launch_stack<32, 4, 32, Epi>(map, a, st);
+  if (KP == 16 && T == 8) return launch_stack<16, 8, 16, Epi>(map, a, st);
+  return fail(HGRU_E_UNSUPPORTED, "stacked conv: unsupported configuration");
+}
+
 template <int S>
 int launch_simt_conv(const float* in, const float* w, const float* bias, const float* scale,
                      const float* shift, float* out, int N, int H, int W, int Ci, int Co, int relu,
@@ -223,6 +271,8 @@ struct hgru_plan_s {
   DevBuf actA, actH1, actH2;
   CUtensorMap mapA, mapH1;          // SxS halo-window boxes (horizontal convs)
   CUtensorMap mapH1_g, mapH2_g;     // 1x1 boxes (gate convs)
+  bool stacked = false;             // narrow layers: tap-stacked kernel (hconv_stack.cuh)
+  int stack_T = 0;
   KernelTimer timer;
   float* vec(int i) const { return vecs.as<float>() + static_cast<size_t>(i) * KP; }
   size_t workspace() const {
@@ -263,11 +313,20 @@ static int hgru_plan_init(hgru_plan_s* p, int N, int H, int W, int k, int S, int
     if ((rc = p->actA.alloc(ab)) || (rc = p->actH1.alloc(ab)) || (rc = p->actH2.alloc(ab))) return rc;
     const int ksteps = p->KP / 16;
     const size_t tapb = sizeof(__nv_bfloat16) * ksteps * 2 * p->KP * 8;
-    if ((rc = p->wpk.alloc(tapb * S * S)) || (rc = p->wpk_i.alloc(tapb)) || (rc = p->wpk_o.alloc(tapb))) return rc;
+    StackGeom sg;
+    p->stacked = stack_geometry(S, p->KP, k, &sg);
+    int box_cols = g.box_cols, box_rows = g.box_rows, box_chunks = 2;
+    size_t wbytes = tapb * S * S;
+    if (p->stacked) {
+      p->stack_T = sg.T;
+      box_cols = sg.box_cols; box_rows = sg.box_rows; box_chunks = p->CG;
+      wbytes = sizeof(__nv_bfloat16) * 15 * sg.ksteps * sg.NG * 2 * 128 * 8;
+    }
+    if ((rc = p->wpk.alloc(wbytes)) || (rc = p->wpk_i.alloc(tapb)) || (rc = p->wpk_o.alloc(tapb))) return rc;
     TcGeom g1;
     tc_geometry(1, p->KP, &g1);
-    if (hgru::make_act_tensor_map(&p->mapA, p->actA.p, N, p->CG, H, W, g.box_cols, g.box_rows) ||
-        hgru::make_act_tensor_map(&p->mapH1, p->actH1.p, N, p->CG, H, W, g.box_cols, g.box_rows) ||
+    if (hgru::make_act_tensor_map(&p->mapA, p->actA.p, N, p->CG, H, W, box_cols, box_rows, box_chunks) ||
+        hgru::make_act_tensor_map(&p->mapH1, p->actH1.p, N, p->CG, H, W, box_cols, box_rows, box_chunks) ||
         hgru::make_act_tensor_map(&p->mapH1_g, p->actH1.p, N, p->CG, H, W, g1.box_cols, g1.box_rows) ||
         hgru::make_act_tensor_map(&p->mapH2_g, p->actH2.p, N, p->CG, H, W, g1.box_cols, g1.box_rows))
       return fail(HGRU_E_CUDA, "cuTensorMapEncodeTiled failed");
@@ -300,7 +359,14 @@ static int hgru_set_params_impl(hgru_plan_s* p, const float* p_r, const float* i
   } else {
     const int ksteps = KP / 16;
     const size_t total = static_cast<size_t>(ksteps) * taps * 2 * KP * 8;
-    hgru::pack_weights_kernel<<<nblk(total), 256, 0, st>>>(p_r, p->wpk.as<__nv_bfloat16>(), taps, k, ksteps, KP);
+    StackGeom sg;
+    if (p->stacked && stack_geometry(p->S, KP, k, &sg)) {
+      const size_t ts = static_cast<size_t>(15) * sg.ksteps * sg.NG * 2 * 128 * 8;
+      hgru::pack_weights_stack_kernel<<<nblk(ts), 256, 0, st>>>(p_r, p->wpk.as<__nv_bfloat16>(), k, sg.ksteps,
+                                                               sg.T, sg.KC, sg.NG);
+    } else {
+      hgru::pack_weights_kernel<<<nblk(total), 256, 0, st>>>(p_r, p->wpk.as<__nv_bfloat16>(), taps, k, ksteps, KP);
+    }
     const size_t t1 = static_cast<size_t>(ksteps) * 2 * KP * 8;
     hgru::pack_weights_kernel<<<nblk(t1), 256, 0, st>>>(i_r, p->wpk_i.as<__nv_bfloat16>(), 1, k, ksteps, KP);
     hgru::pack_weights_kernel<<<nblk(t1), 256, 0, st>>>(o_r, p->wpk_o.as<__nv_bfloat16>(), 1, k, ksteps, KP);
@@ -384,7 +450,9 @@ static int hgru_run_bf16(hgru_plan_s* p, const float* Xp, float* H1_trace, float
     a.v0 = p->vec(V_BETA); a.v1 = p->vec(V_NU);
     a.out = p->H1.as<float>(); a.out_bf16 = p->actH1.as<__nv_bfloat16>();
     p->timer.begin(st);
-    if ((rc = dispatch_tc_hconv<hgru::EpiH1>(p->S, KP, p->mapA, a, st))) return rc;
+    if ((rc = p->stacked ? dispatch_stack<hgru::EpiH1>(KP, p->stack_T, p->mapA, a, st)
+                        : dispatch_tc_hconv<hgru::EpiH1>(p->S, KP, p->mapA, a, st)))
+      return rc;
     p->timer.end(st);
     // circuit_output gate (:729-740): G2 = sigmoid(H1 *1x1 o_r + o_b)
     a = base;
@@ -398,7 +466,9 @@ static int hgru_run_bf16(hgru_plan_s* p, const float* Xp, float* H1_trace, float
     a.rho_t = p->rho.as<float>() + t;
     a.out_bf16 = p->actH2.as<__nv_bfloat16>();
     p->timer.begin(st);
-    if ((rc = dispatch_tc_hconv<hgru::EpiH2>(p->S, KP, p->mapH1, a, st))) return rc;
+    if ((rc = p->stacked ? dispatch_stack<hgru::EpiH2>(KP, p->stack_T, p->mapH1, a, st)
+                        : dispatch_tc_hconv<hgru::EpiH2>(p->S, KP, p->mapH1, a, st)))
+      return rc;
     p->timer.end(st);
     p->launches += 4;
     if (H1_trace) {

@@ -31,14 +31,15 @@ inline EncodeTiledFn get_encode_tiled() {
 // (dim0 = 2*W so one pixel-chunk of 16 B is two elements); box = (2*cols, rows, 2 chunks, 1).
 // Out-of-bounds box elements are zero-filled: that implements the conv's SAME padding.
 inline int make_act_tensor_map(CUtensorMap* map, const void* base, int N, int CG, int H, int W,
-                               int box_cols, int box_rows) {
+                               int box_cols, int box_rows, int box_chunks = 2) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return -1;
   cuuint64_t gdim[4] = {static_cast<cuuint64_t>(2 * W), static_cast<cuuint64_t>(H),
                         static_cast<cuuint64_t>(CG), static_cast<cuuint64_t>(N)};
   cuuint64_t gstr[3] = {static_cast<cuuint64_t>(W) * 16, static_cast<cuuint64_t>(H) * W * 16,
                         static_cast<cuuint64_t>(CG) * H * W * 16};
-  cuuint32_t box[4] = {static_cast<cuuint32_t>(2 * box_cols), static_cast<cuuint32_t>(box_rows), 2, 1};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(2 * box_cols), static_cast<cuuint32_t>(box_rows),
+                       static_cast<cuuint32_t>(box_chunks), 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void*>(base), gdim, gstr, box,
                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
