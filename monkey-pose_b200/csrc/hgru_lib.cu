@@ -10,6 +10,7 @@
 #include <string>
 #include <vector>
 
+#include "gate_tc.cuh"
 #include "gemm_tc.cuh"
 #include "hconv_stack.cuh"
 #include "hconv_tc.cuh"
@@ -106,13 +107,6 @@ int dispatch_tc_hconv(int S, int KP, const CUtensorMap& map, const hgru::TcConvA
   TC_CASES_S(Epi, 1, 1, 1)
   return fail(HGRU_E_UNSUPPORTED, "tensor-core conv: unsupported (S, padded channels)");
 }
-// 1x1 gate convs
-template <class Epi>
-int dispatch_tc_gate(int KP, const CUtensorMap& map, const hgru::TcConvArgs& a, cudaStream_t st) {
-  const int S = 1;
-  TC_CASES_S(Epi, 1, 1, 1)
-  return fail(HGRU_E_UNSUPPORTED, "tensor-core gate: unsupported padded channel count");
-}
 // 3x3 stem convs
 int dispatch_tc_stem(int KP, const CUtensorMap& map, const hgru::TcConvArgs& a, cudaStream_t st) {
   const int S = 3;
@@ -167,6 +161,23 @@ int dispatch_stack(int KP, int T, const CUtensorMap& map, const hgru::TcConvArgs
   if (KP == 32 && T == 4) return launch_stack<32, 4, 32, Epi>(map, a, st);
   if (KP == 16 && T == 8) return launch_stack<16, 8, 16, Epi>(map, a, st);
   return fail(HGRU_E_UNSUPPORTED, "stacked conv: unsupported configuration");
+}
+
+// ---------------------------------------------------------------- 1x1 gate convs (light kernel)
+template <int KP, class Epi>
+int launch_gate(const __nv_bfloat16* act, const hgru::TcConvArgs& a, cudaStream_t st) {
+  using Cfg = hgru::GateCfg<KP>;
+  const int tiles_per_frame = (a.H * a.W + 127) / 128;
+  hgru::gate_tc_kernel<KP, Epi><<<a.N * tiles_per_frame, 128, Cfg::SMEM_BYTES, st>>>(act, a);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+template <class Epi>
+int dispatch_gate(int KP, const __nv_bfloat16* act, const hgru::TcConvArgs& a, cudaStream_t st) {
+  if (KP == 64) return launch_gate<64, Epi>(act, a, st);
+  if (KP == 32) return launch_gate<32, Epi>(act, a, st);
+  if (KP == 16) return launch_gate<16, Epi>(act, a, st);
+  return fail(HGRU_E_UNSUPPORTED, "tensor-core gate: unsupported padded channel count");
 }
 
 template <int S>
@@ -443,7 +454,7 @@ static int hgru_run_bf16(hgru_plan_s* p, const float* Xp, float* H1_trace, float
     hgru::TcConvArgs a = base;
     a.wpk = p->wpk_i.as<__nv_bfloat16>(); a.bias = p->vec(V_IB); a.H2 = p->H2.as<float>();
     a.out_bf16 = p->actA.as<__nv_bfloat16>();
-    if ((rc = dispatch_tc_gate<hgru::EpiGateIn>(KP, p->mapH2_g, a, st))) return rc;
+    if ((rc = dispatch_gate<hgru::EpiGateIn>(KP, p->actH2.as<__nv_bfloat16>(), a, st))) return rc;
     // C1 conv (:714-718, 657) + input_integration (:795-804) -> H1 (fp32 + bf16 operand copy)
     a = base;
     a.wpk = p->wpk.as<__nv_bfloat16>(); a.bias = p->vec(V_LBIAS); a.X = Xp; a.H2 = p->H2.as<float>();
@@ -457,7 +468,7 @@ static int hgru_run_bf16(hgru_plan_s* p, const float* Xp, float* H1_trace, float
     // circuit_output gate (:729-740): G2 = sigmoid(H1 *1x1 o_r + o_b)
     a = base;
     a.wpk = p->wpk_o.as<__nv_bfloat16>(); a.bias = p->vec(V_OB); a.out = p->G.as<float>();
-    if ((rc = dispatch_tc_gate<hgru::EpiGateOut>(KP, p->mapH1_g, a, st))) return rc;
+    if ((rc = dispatch_gate<hgru::EpiGateOut>(KP, p->actH1.as<__nv_bfloat16>(), a, st))) return rc;
     // C2 conv (:746-750, 657) + output_integration + rho (:806-823, 847-849) -> H2 in place
     a = base;
     a.wpk = p->wpk.as<__nv_bfloat16>(); a.bias = p->vec(V_LBIAS); a.H1 = p->H1.as<float>();
