@@ -111,7 +111,7 @@ class Clocks(object):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -126,7 +126,7 @@ class Clocks(object):
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        sm, mx, reasons, pw = [], None, set(), []
+        sm, mx, reasons, pw, allrows = [], None, set(), [], []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ts, ln in self.rows:
             f = [x.strip() for x in ln.split(",")]
@@ -137,7 +137,8 @@ class Clocks(object):
             except ValueError:
                 continue
             mx = m
-            if t0 <= ts <= t1 + 0.1:
+            allrows.append((ts, c))
+            if t0 <= ts <= t1 + 0.02:
                 sm.append(c)
                 try:
                     pw.append(float(f[2]))
@@ -146,6 +147,9 @@ class Clocks(object):
                 for nme, v in zip(names, f[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(nme)
+        if not sm and allrows:      # timed region shorter than the sampling period: nearest sample
+            mid = 0.5 * (t0 + t1)
+            sm = [min(allrows, key=lambda r: abs(r[0] - mid))[1]]
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
                 "samples": len(sm), "power_w_max": max(pw) if pw else None}

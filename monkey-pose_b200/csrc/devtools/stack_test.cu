@@ -47,10 +47,12 @@ int run_case(int N, int H, int W, int k, int grid_override, int iters) {
   CK(cudaMemcpy(d_bias, bias.data(), KP * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_act, act.data(), act.size() * 2, cudaMemcpyHostToDevice));
   CK(cudaMemset(d_out, 0xFF, npix * KP * 4));
-  hgru::pack_weights_stack_kernel<<<(unsigned)((wpk_elems + 255) / 256), 256>>>(d_w, d_wpk, k, Cfg::KSTEPS, T, KC, Cfg::NG);
+  hgru::pack_weights_stack_kernel<<<(unsigned)((wpk_elems + 255) / 256), 256>>>(d_w, d_wpk, k, Cfg::KSTEPS, T, KC, Cfg::NG, CS);
   CK(cudaDeviceSynchronize());
   CUtensorMap map;
   if (hgru::make_act_tensor_map(&map, d_act, N, CG, H, W, Cfg::COLS, Cfg::ROWS, CG)) { printf("map fail\n"); return 1; }
+  CUtensorMap wmap;
+  if (hgru::make_rows256_map(&wmap, d_wpk, wpk_elems * 2, Cfg::STAGE_ROWS)) { printf("wmap fail\n"); return 1; }
   hgru::TcConvArgs a{};
   a.N = N; a.H = H; a.W = W; a.KP = KP; a.kreal = k;
   a.units_x = (W + 63) / 64; a.units_y = (H + 15) / 16; a.num_units = N * a.units_x * a.units_y;
@@ -60,10 +62,10 @@ int run_case(int N, int H, int W, int k, int grid_override, int iters) {
   int sms = 0; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
   int grid = grid_override > 0 ? grid_override : (a.num_units < sms ? a.num_units : sms);
   grid = (grid + CS - 1) / CS * CS;
-  cudaLaunchConfig_t cfg{}; cfg.gridDim = dim3(grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cudaLaunchConfig_t cfg{}; cfg.gridDim = dim3(grid); cfg.blockDim = dim3(384); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  CK(cudaLaunchKernelEx(&cfg, kern, map, a));
+  CK(cudaLaunchKernelEx(&cfg, kern, map, wmap, a));
   CK(cudaDeviceSynchronize());
   size_t total = npix * k;
   naive_conv<<<(unsigned)((total + 255) / 256), 256>>>(d_in, d_w, d_bias, d_ref, N, H, W, k, S);
@@ -73,28 +75,29 @@ int run_case(int N, int H, int W, int k, int grid_override, int iters) {
   CK(cudaMemcpy(ref.data(), d_ref, total * 4, cudaMemcpyDeviceToHost));
   double maxerr = 0, maxref = 0; size_t bad = 0, nan = 0;
   for (size_t p = 0; p < npix; ++p) for (int c = 0; c < k; ++c) {
-    float o = outp[p * KP + c], r = ref[p * k + c];
+    size_t nn = p / ((size_t)H * W), pin = p % ((size_t)H * W);
+    float o = outp[((nn * (KP / 4) + c / 4) * (size_t)H * W + pin) * 4 + (c % 4)], r = ref[p * k + c];
     if (!(o == o)) { ++nan; continue; }
     double e = fabs((double)o - r); if (e > maxerr) maxerr = e; if (fabs(r) > maxref) maxref = fabs(r);
     if (e > 1e-3 * (1.0 + fabs(r))) ++bad; }
   printf("  grid=%d units=%d maxerr=%.3e maxref=%.3e bad=%zu nan=%zu\n", grid, a.num_units, maxerr, maxref, bad, nan);
   if (bad || nan) {
     for (int y = 0; y < (H < 32 ? H : 32); ++y) { for (int x = 0; x < (W < 64 ? W : 64); ++x) {
-      float o = outp[(((size_t)0 * H + y) * W + x) * KP], r = ref[(((size_t)0 * H + y) * W + x) * k];
+      float o = outp[((size_t)y * W + x) * 4], r = ref[(((size_t)0 * H + y) * W + x) * k];
       putchar(!(o == o) ? 'N' : (fabs(o - r) > 1e-3 * (1 + fabs(r)) ? 'x' : '.')); } putchar('\n'); }
   }
   if (iters > 0 && !bad && !nan) {
     long long* d_prof; CK(cudaMalloc(&d_prof, grid * 8 * sizeof(long long))); CK(cudaMemset(d_prof, 0, grid * 8 * sizeof(long long)));
     hgru::TcConvArgs ap = a; ap.prof = d_prof;
-    CK(cudaLaunchKernelEx(&cfg, kern, map, ap)); CK(cudaDeviceSynchronize());
+    CK(cudaLaunchKernelEx(&cfg, kern, map, wmap, ap)); CK(cudaDeviceSynchronize());
     std::vector<long long> pr(grid * 8); CK(cudaMemcpy(pr.data(), d_prof, grid * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
     double av[6] = {0, 0, 0, 0, 0, 0}; for (int b = 0; b < grid; ++b) for (int i = 0; i < 6; ++i) av[i] += pr[b * 8 + i] / (double)grid;
     printf("  prof (avg cycles/CTA): mma_total=%.0f wait_win=%.0f wait_acc_empty=%.0f wait_w_full=%.0f | epi_total=%.0f epi_wait_acc_full=%.0f\n", av[0], av[1], av[2], av[3], av[4], av[5]);
     cudaFree(d_prof);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    for (int i = 0; i < 2; ++i) cudaLaunchKernelEx(&cfg, kern, map, a);
+    for (int i = 0; i < 2; ++i) cudaLaunchKernelEx(&cfg, kern, map, wmap, a);
     cudaEventRecord(e0);
-    for (int i = 0; i < iters; ++i) cudaLaunchKernelEx(&cfg, kern, map, a);
+    for (int i = 0; i < iters; ++i) cudaLaunchKernelEx(&cfg, kern, map, wmap, a);
     cudaEventRecord(e1); CK(cudaDeviceSynchronize());
     float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= iters;
     printf("  time %.3f ms -> %.1f TFLOP/s algorithmic\n", ms, 2.0 * npix * 225.0 * k * k / ms * 1e-9);
@@ -102,6 +105,47 @@ int run_case(int N, int H, int W, int k, int grid_override, int iters) {
   cudaFree(d_in); cudaFree(d_w); cudaFree(d_bias); cudaFree(d_ref); cudaFree(d_out); cudaFree(d_act); cudaFree(d_wpk);
   return (bad || nan) ? 1 : 0;
 }
+template <int KP, int T, int KC, int CS, class Epi>
+void time_real_epilogue(const char* name, int N, int H, int W, int k) {
+  using Cfg = hgru::StackCfg<KP, T, KC, CS>;
+  const int CG = KP / 8;
+  size_t npix = (size_t)N * H * W;
+  float *X, *H1, *G, *H2, *vec; __nv_bfloat16 *act, *actout, *wpk;
+  size_t wpk_elems = (size_t)15 * Cfg::KSTEPS * Cfg::NG * 2 * 128 * 8;
+  CK(cudaMalloc(&X, npix * KP * 4)); CK(cudaMalloc(&H1, npix * KP * 4)); CK(cudaMalloc(&G, npix * KP * 4)); CK(cudaMalloc(&H2, npix * KP * 4));
+  CK(cudaMalloc(&vec, 8 * KP * 4)); CK(cudaMalloc(&act, npix * KP * 2)); CK(cudaMalloc(&actout, npix * KP * 2)); CK(cudaMalloc(&wpk, wpk_elems * 2));
+  CK(cudaMemset(X, 0, npix * KP * 4)); CK(cudaMemset(H1, 0, npix * KP * 4)); CK(cudaMemset(G, 0, npix * KP * 4)); CK(cudaMemset(H2, 0, npix * KP * 4));
+  CK(cudaMemset(vec, 0, 8 * KP * 4)); CK(cudaMemset(act, 0, npix * KP * 2)); CK(cudaMemset(wpk, 0, wpk_elems * 2));
+  CUtensorMap map, wmap;
+  hgru::make_act_tensor_map(&map, act, N, CG, H, W, Cfg::COLS, Cfg::ROWS, CG);
+  hgru::make_rows256_map(&wmap, wpk, wpk_elems * 2, Cfg::STAGE_ROWS);
+  hgru::TcConvArgs a{};
+  a.N = N; a.H = H; a.W = W; a.KP = KP; a.kreal = k;
+  a.units_x = (W + 63) / 64; a.units_y = (H + 15) / 16; a.num_units = N * a.units_x * a.units_y;
+  a.wpk = wpk; a.bias = vec; a.v0 = vec + KP; a.v1 = vec + 2 * KP; a.v2 = vec + 3 * KP; a.rho_t = vec + 4 * KP;
+  a.X = X; a.H1 = H1; a.G = G; a.H2 = H2; a.out = H1; a.out_bf16 = actout;
+  auto kern = hgru::hconv_stack_kernel<KP, T, KC, CS, Epi>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  int grid = 148;
+  cudaLaunchConfig_t cfg{}; cfg.gridDim = dim3(grid); cfg.blockDim = dim3(384); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  long long* d_prof; CK(cudaMalloc(&d_prof, grid * 8 * sizeof(long long))); CK(cudaMemset(d_prof, 0, grid * 8 * sizeof(long long)));
+  hgru::TcConvArgs ap = a; ap.prof = d_prof;
+  CK(cudaLaunchKernelEx(&cfg, kern, map, wmap, ap)); CK(cudaDeviceSynchronize());
+  std::vector<long long> pr(grid * 8); CK(cudaMemcpy(pr.data(), d_prof, grid * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+  double av[6] = {0, 0, 0, 0, 0, 0}; int nl = 0;
+  for (int b = 0; b < grid; ++b) { if (pr[b * 8]) ++nl; for (int i = 0; i < 6; ++i) av[i] += pr[b * 8 + i]; }
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0);
+  for (int i = 0; i < 5; ++i) cudaLaunchKernelEx(&cfg, kern, map, wmap, a);
+  cudaEventRecord(e1); CK(cudaDeviceSynchronize());
+  float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 5;
+  printf("%s CS=%d: %.3f ms | leader avg cycles: mma_total=%.0f wait_win=%.0f wait_acc_empty=%.0f wait_w=%.0f | epi_total=%.0f epi_wait=%.0f\n", name, CS, ms,
+         av[0] / nl, av[1] / nl, av[2] / nl, av[3] / nl, av[4] / grid, av[5] / grid);
+  cudaFree(X); cudaFree(H1); cudaFree(G); cudaFree(H2); cudaFree(vec); cudaFree(act); cudaFree(actout); cudaFree(wpk); cudaFree(d_prof);
+}
+
 int main(int argc, char** argv) {
   int which = argc > 1 ? atoi(argv[1]) : 0, f = 0;
   if (which == 0 || which == 1) f += run_case<32, 5, 25, 1>(2, 64, 64, 25, 0, 0);
@@ -113,6 +157,14 @@ int main(int argc, char** argv) {
   if (which == 0 || which == 7) f += run_case<32, 5, 25, 1>(256, 64, 64, 25, 0, 5);
   if (which == 0 || which == 8) f += run_case<32, 5, 25, 2>(256, 64, 64, 25, 0, 5);
   if (which == 0 || which == 9) f += run_case<32, 4, 32, 2>(256, 64, 64, 32, 0, 5);
+  if (which == 20) {
+    time_real_epilogue<32, 5, 25, 1, hgru::EpiBias>("EpiBias", 256, 64, 64, 25);
+    time_real_epilogue<32, 5, 25, 1, hgru::EpiH1>("EpiH1", 256, 64, 64, 25);
+    time_real_epilogue<32, 5, 25, 1, hgru::EpiH2>("EpiH2", 256, 64, 64, 25);
+    time_real_epilogue<32, 5, 25, 2, hgru::EpiBias>("EpiBias", 256, 64, 64, 25);
+    time_real_epilogue<32, 5, 25, 2, hgru::EpiH1>("EpiH1", 256, 64, 64, 25);
+    time_real_epilogue<32, 5, 25, 2, hgru::EpiH2>("EpiH2", 256, 64, 64, 25);
+  }
   printf(f ? "FAILED %d\n" : "ALL OK\n", f);
   return f;
 }

@@ -121,7 +121,10 @@ int run_case(int N, int H, int W, int k, int grid_override, int iters) {
   std::vector<float> out(total), ref(total), outp(npix * CO_PAD);
   CK(cudaMemcpy(outp.data(), d_out, npix * CO_PAD * 4, cudaMemcpyDeviceToHost));
   for (size_t p = 0; p < npix; ++p)
-    for (int c = 0; c < k; ++c) out[p * k + c] = outp[p * CO_PAD + c];
+    for (int c = 0; c < k; ++c) {
+      size_t nn = p / ((size_t)H * W), pin = p % ((size_t)H * W);
+      out[p * k + c] = outp[((nn * (CO_PAD / 4) + c / 4) * (size_t)H * W + pin) * 4 + (c % 4)];
+    }
   CK(cudaMemcpy(ref.data(), d_ref, total * 4, cudaMemcpyDeviceToHost));
   double maxerr = 0, maxref = 0;
   size_t bad = 0, nan = 0, worst = 0;

@@ -150,15 +150,17 @@ gemm_tc_splitk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 }
 
 // A operand of fc_1: bf16 [M][HW*k] = (H2[m][pix][c] * scale[c] + shift[c]) over real channels
-// (the inference batch-norm of the hGRU output, hgru_pose.py:82-90, applied while flattening).
+// (the inference batch-norm of the hGRU output, hgru_pose.py:82-90, applied while flattening);
+// H2 is read from the quad-chunked state layout [n][c/4][pix][4].
 __global__ void __launch_bounds__(256)
 fc1_pack_a_kernel(const float* __restrict__ h2, const float* __restrict__ sc, const float* __restrict__ sh,
-                  __nv_bfloat16* __restrict__ a, size_t npix, int k, int KP) {
+                  __nv_bfloat16* __restrict__ a, size_t npix, int k, int KP, int HW) {
   const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   if (i >= npix * k) return;
   const int c = i % k;
   const size_t p = i / k;
-  a[i] = __float2bfloat16(h2[p * KP + c] * sc[c] + sh[c]);
+  const size_t n = p / HW, pin = p - n * HW;
+  a[i] = __float2bfloat16(h2[((n * (KP >> 2) + (c >> 2)) * HW + pin) * 4 + (c & 3)] * sc[c] + sh[c]);
 }
 
 // fc_1 weights [K][F] fp32 -> bf16 [F][K] (K-major B operand); 32x32 tiles through shared memory.

@@ -17,8 +17,16 @@
 // (30 x ~82 pixels x KP channels) resident in shared memory.  TMEM holds four 128-column
 // accumulators: tiles are processed in pairs, two accumulating while two drain, so the epilogue
 // (shuffles + fused gate/integration math + global I/O) hides behind the MMAs.  The stacked
-// weights (360 KB at k = 25) stream through a 4-stage ring once per tile pair; with CS = 2 the two
-// CTAs of a cluster each fetch half of every stage and multicast it, halving L2 traffic.
+// weights (360 KB at k = 25) stream through a 4-stage ring once per tile pair.
+//
+// CS = 2 ("pair mode", cta_group::2): two CTAs on one TPC run in lockstep on two units; the leader
+// issues M = 256 MMAs whose A rows come half from each CTA's own window and whose B rows come half
+// from each CTA's weight ring, so every CTA stores, streams and reads only half of the weights.
+// That matters because this kernel is bound by the 128 B/clk shared-memory/L1 datapath (UMMA
+// operand reads + TMA writes + epilogue traffic), not by the tensor pipe.  All pair synchronisation
+// converges on the leader's barriers: both CTAs' TMA loads complete their bytes there
+// (cp.async.bulk.tensor ... cta_group::2), the peer's epilogue threads arrive there remotely, and
+// the leader's commits are multicast back to both CTAs.
 //
 // Warps: w0 weight producer, w1 MMA issuer, w2 TMEM alloc, w3 window producer, w4..7 epilogue.
 #pragma once
@@ -45,33 +53,42 @@ struct StackCfg {
   static constexpr int CHUNK_PITCH = ROWS * ROW_PITCH;
   static constexpr int WIN_BYTES = CG * CHUNK_PITCH;
   static constexpr int MIN_COL = T - 16;                  // image column of window column 0, minus x0
-  static constexpr int BLK_BYTES = 2 * NPAD * 16;         // one (dy, q, g) weight block (4 KB)
-  static constexpr int STAGE_BYTES = NG * BLK_BYTES;      // all tap groups of one (dy, q)
+  static constexpr int CSPLIT = KP / 2;                   // channels [0,CSPLIT) -> epilogue group A, rest -> group B
+  static constexpr int NTHREADS = 384;                    // 4 service warps + 2 x 4 epilogue warps
+  static constexpr int NLOC = NPAD / CS;                  // B rows held by one CTA
+  static constexpr int BLK_BYTES = 2 * NLOC * 16;         // one CTA's part of a (dy, q, g) weight block
+  static constexpr int STAGE_BYTES = NG * BLK_BYTES;      // all tap groups of one (dy, q), per CTA
   static constexpr int PASS_STAGES = S * KSTEPS;          // stages per tile pair
-  static constexpr int WSTAGES = 4;
+  static constexpr int WSTAGES = (CS == 2) ? 8 : 4;        // pair mode: half-size stages, deeper ring
   static constexpr int NUM_BARS = 2 + 2 * WSTAGES + 8;
+  static constexpr int STAGE_ROWS = STAGE_BYTES / 256;    // rows of the 256-byte weight view per stage
   static constexpr int SMEM_BYTES = WIN_BYTES + WSTAGES * STAGE_BYTES + NUM_BARS * 8 + 16 + 1024;
   static_assert(T * KC <= NPAD, "stacked taps must fit N = 128");
   static_assert(KC <= KP && KP % 16 == 0, "channel padding");
   static_assert((CHUNK_PITCH >> 4) < 16384, "LBO range");
-  static_assert(STAGE_BYTES % (16 * CS) == 0, "stage must split evenly over the cluster");
+  static_assert(CS == 1 || CS == 2, "single CTA or CTA pair");
+  static_assert(STAGE_BYTES % 256 == 0, "stage must be whole 256-byte rows");
   static_assert(2 * COLS <= 256, "TMA box limit");
 };
 
-// Stacked weight packing: HWIO fp32 [15][15][k][k] -> bf16 [dy][q][g][2 chunks][128 n][8 ci],
-// n = s*KC + c  <->  tap dx = T*g + T-1-s, output channel c (zero where dx >= 15 or c, ci >= k).
+// Stacked weight packing: HWIO fp32 [15][15][k][k] -> bf16 [dy][q][rank][g][2 chunks][128/CS n'][8 ci],
+// n = rank*(128/CS) + n' = s*KC + c  <->  tap dx = T*g + T-1-s, output channel c
+// (zero where dx >= 15 or c, ci >= k).  `rank` = which CTA of a pair holds that half of B.
 __global__ void pack_weights_stack_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wpk,
-                                          int k, int ksteps, int T, int KC, int NG) {
+                                          int k, int ksteps, int T, int KC, int NG, int CS) {
   const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   const size_t total = static_cast<size_t>(15) * ksteps * NG * 2 * 128 * 8;
   if (i >= total) return;
+  const int nloc = 128 / CS;
   const int j = i & 7;
   size_t r = i >> 3;
-  const int n = r & 127; r >>= 7;
+  const int np = r % nloc; r /= nloc;
   const int ch = r & 1; r >>= 1;
   const int g = r % NG; r /= NG;
+  const int rank = r % CS; r /= CS;
   const int q = r % ksteps;
   const int dy = r / ksteps;
+  const int n = rank * nloc + np;
   const int s = n / KC, c = n - s * KC;
   const int dx = T * g + T - 1 - s;
   const int ci = q * 16 + ch * 8 + j;
@@ -123,34 +140,102 @@ __device__ __forceinline__ void tmem_ld_block(uint32_t taddr, float (&v)[KC]) {
     tmem_ld_f<1>(taddr + 24, v + 24);
   }
 }
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// multicast 1-D bulk copy: lands at the same shared-memory offset in every CTA of `mask` and
-// completes bytes on the mbarrier at the same offset in each of them
-__device__ __forceinline__ void bulk_load_multicast(uint32_t dst, const void* src, uint32_t bytes,
-                                                    uint32_t bar, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1], %2, [%3], %4;"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar), "h"(mask)
-      : "memory");
-}
-__device__ __forceinline__ void tc_commit_multicast(uint32_t bar, uint16_t mask) {
-  asm volatile(
-      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-      ::"r"(bar), "h"(mask) : "memory");
+// CN consecutive fp32 columns (CN in {8, 9, 16}) of this thread's TMEM lane
+template <int CN>
+__device__ __forceinline__ void tmem_ld_range(uint32_t taddr, float (&v)[CN]) {
+  static_assert(CN == 8 || CN == 9 || CN == 16, "supported channel-range widths");
+  if constexpr (CN == 16) {
+    tmem_ld_f<16>(taddr, v);
+  } else if constexpr (CN == 8) {
+    tmem_ld_f<8>(taddr, v);
+  } else {
+    tmem_ld_f<8>(taddr, v);
+    tmem_ld_f<1>(taddr + 8, v + 8);
+  }
 }
 }  // namespace detail
 
+// Epilogue of one warpgroup for the channel range [C0, C0+CN) of every tile: un-stack (rotate +
+// carry), fused math, stores.  Two warpgroups split the channels so that each SM sub-partition has
+// two epilogue warps to overlap TMEM / global-memory latencies; they never need to talk to each
+// other (un-stacking and the integration math are per channel).
+template <class Cfg, class Epi, int C0, int CN>
+__device__ __forceinline__ void stack_epilogue(const TcConvArgs& a, uint32_t tmem_base, uint32_t bar_acc_full,
+                                               uint32_t bar_acc_empty, uint32_t crank, int iters, int NT,
+                                               int units_per_frame, int warp, int lane, bool profile) {
+  using namespace sm100;
+  constexpr int KC = Cfg::KC, T = Cfg::T, CS = Cfg::CS;
+  constexpr int NCH = (CN + 7) / 8 * 8;            // channels handed to the fused epilogue (8-aligned)
+  const int ew = warp & 3;
+  const int m = ew * 32 + lane;
+  const int prow = m >> 3, pcol = m & 7;
+  uint32_t tc = 0;
+  const uint32_t lead_acc_empty = (CS > 1) ? mapa_cluster(bar_acc_empty, 0) : 0u;
+  long long e_wait = 0, e_begin = clock64(), e0;
+  for (int it = 0; it < iters; ++it) {
+    const int u = it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);
+    const bool valid = u < a.num_units;
+    const int n = u / units_per_frame;
+    const int r = u - n * units_per_frame;
+    const int uy = r / a.units_x, ux = r - uy * a.units_x;
+    const int y = uy * kTileRows + prow;
+    float carry[CN];
+#pragma unroll
+    for (int c = 0; c < CN; ++c) carry[c] = 0.f;
+#pragma unroll 1
+    for (int j = 0; j < NT; ++j, ++tc) {
+      const uint32_t slot = tc & 3;
+      // this thread's output pixel; its global inputs are fetched while the MMAs still run
+      const int x = ux * 64 + 8 * (j - 1) + pcol;
+      const bool store = valid && j >= 1 && y < a.H && x < a.W;
+      const size_t pin = static_cast<size_t>(y) * a.W + x;
+      typename Epi::template Pre<NCH> pre;
+      if (store) Epi::template load<NCH>(a, n, pin, C0, pre);
+      e0 = clock64();
+      mbar_wait(bar_acc_full + 8 * slot, (tc >> 2) & 1);
+      e_wait += clock64() - e0;
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + slot * Cfg::NPAD + C0;
+      float out[NCH], nxt[CN];
+      {
+        float blk[CN];
+        detail::tmem_ld_range<CN>(taddr, blk);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) out[c] = (c < CN) ? blk[c < CN ? c : 0] + carry[c < CN ? c : 0] : 0.f;
+      }
+#pragma unroll
+      for (int c = 0; c < CN; ++c) nxt[c] = 0.f;
+#pragma unroll
+      for (int s = 1; s < T; ++s) {
+        float blk[CN];
+        detail::tmem_ld_range<CN>(taddr + s * KC, blk);
+        const int src = (lane & ~7) | ((pcol - s) & 7);
+        const bool own = pcol >= s;
+#pragma unroll
+        for (int c = 0; c < CN; ++c) {
+          const float v = __shfl_sync(0xffffffffu, blk[c], src);
+          if (own) out[c] += v; else nxt[c] += v;
+        }
+      }
+      tc_fence_before();
+      // accumulator drained: MMAs may reuse it (pair mode: the leader's barrier counts both CTAs)
+      if (CS > 1 && crank != 0) mbar_arrive_cluster(lead_acc_empty + 8 * slot);
+      else mbar_arrive(bar_acc_empty + 8 * slot);
+#pragma unroll
+      for (int c = 0; c < CN; ++c) carry[c] = nxt[c];
+      if (store) Epi::template finish<NCH>(a, n, pin, C0, out, pre);
+    }
+  }
+  if (profile && a.prof && (threadIdx.x & 127) == 0) {
+    long long* o = a.prof + static_cast<size_t>(blockIdx.x) * 8;
+    o[4] = clock64() - e_begin; o[5] = e_wait;
+  }
+}
+
 template <int KP, int T, int KC, int CS, class Epi>
-__global__ void __launch_bounds__(256, 1)
-hconv_stack_kernel(const __grid_constant__ CUtensorMap in_map, const TcConvArgs a) {
+__global__ void __launch_bounds__(384, 1)
+hconv_stack_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap w_map,
+                   const TcConvArgs a) {
   using namespace sm100;
   using Cfg = StackCfg<KP, T, KC, CS>;
   extern __shared__ uint8_t smem_raw[];
@@ -168,7 +253,7 @@ hconv_stack_kernel(const __grid_constant__ CUtensorMap in_map, const TcConvArgs 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t crank = (CS > 1) ? detail::cluster_ctarank() : 0u;
+  const uint32_t crank = (CS > 1) ? cluster_ctarank() : 0u;
   constexpr uint16_t kMask = static_cast<uint16_t>((1u << CS) - 1u);
 
   if (threadIdx.x == 0) {
@@ -176,19 +261,23 @@ hconv_stack_kernel(const __grid_constant__ CUtensorMap in_map, const TcConvArgs 
     mbar_init(bar_win_empty, 1);
     for (int i = 0; i < Cfg::WSTAGES; ++i) {
       mbar_init(bar_w_full + 8 * i, 1);
-      mbar_init(bar_w_empty + 8 * i, CS);      // every CTA of the cluster releases the stage
+      mbar_init(bar_w_empty + 8 * i, 1);
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(bar_acc_full + 8 * i, 1);
-      mbar_init(bar_acc_empty + 8 * i, 128);
+      mbar_init(bar_acc_empty + 8 * i, 256 * CS);     // 2 epilogue groups (pair mode: of both CTAs, at the leader)
     }
+    tma_prefetch_desc(&w_map);
     fence_barrier_init();
     tma_prefetch_desc(&in_map);
   }
-  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  if (warp == 2) {
+    if constexpr (CS > 1) tmem_alloc_2cta<512>(tmem_slot);
+    else tmem_alloc<512>(tmem_slot);
+  }
   tc_fence_before();
   __syncthreads();
-  if constexpr (CS > 1) detail::cluster_sync_all();     // peers' barriers exist before any remote arrive
+  if constexpr (CS > 1) cluster_sync_all();     // peers' barriers exist before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -200,20 +289,25 @@ hconv_stack_kernel(const __grid_constant__ CUtensorMap in_map, const TcConvArgs 
   const int npairs = (NT + 1) / 2;
 
   if (warp == 0) {
-    // ---------------- weight producer ----------------
+    // ---------------- weight producer: this CTA's share of every stage ----------------
     if (lane == 0) {
       uint32_t st = 0, ph = 0;
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wpk);
-      constexpr uint32_t kShare = Cfg::STAGE_BYTES / CS;
+      const uint32_t lead_w_full = (CS > 1) ? mapa_cluster(bar_w_full, 0) : 0u;
       for (int it = 0; it < iters; ++it)
         for (int pr = 0; pr < npairs; ++pr)
           for (int sg = 0; sg < Cfg::PASS_STAGES; ++sg) {
             mbar_wait(bar_w_empty + 8 * st, ph ^ 1);
-            mbar_arrive_expect_tx(bar_w_full + 8 * st, Cfg::STAGE_BYTES);
-            const uint32_t dst = w_buf + st * Cfg::STAGE_BYTES + crank * kShare;
-            const uint8_t* src = wsrc + static_cast<size_t>(sg) * Cfg::STAGE_BYTES + crank * kShare;
-            if constexpr (CS > 1) detail::bulk_load_multicast(dst, src, kShare, bar_w_full + 8 * st, kMask);
-            else bulk_load(dst, src, kShare, bar_w_full + 8 * st);
+            if constexpr (CS > 1) {
+              // both halves complete their bytes on the leader's barrier
+              if (crank == 0) mbar_arrive_expect_tx(bar_w_full + 8 * st, 2 * Cfg::STAGE_BYTES);
+              tma_load_2d_2cta(w_buf + st * Cfg::STAGE_BYTES, &w_map, lead_w_full + 8 * st, 0,
+                               (sg * CS + static_cast<int>(crank)) * Cfg::STAGE_ROWS);
+            } else {
+              mbar_arrive_expect_tx(bar_w_full + 8 * st, Cfg::STAGE_BYTES);
+              bulk_load(w_buf + st * Cfg::STAGE_BYTES, wsrc + static_cast<size_t>(sg) * Cfg::STAGE_BYTES,
+                        Cfg::STAGE_BYTES, bar_w_full + 8 * st);
+            }
             if (++st == Cfg::WSTAGES) { st = 0; ph ^= 1; }
           }
     }
@@ -221,6 +315,7 @@ hconv_stack_kernel(const __grid_constant__ CUtensorMap in_map, const TcConvArgs 
     // ---------------- window producer: one TMA box per unit ----------------
     if (lane == 0) {
       int vit = 0;
+      const uint32_t lead_win_full = (CS > 1) ? mapa_cluster(bar_win_full, 0) : 0u;
       for (int it = 0; it < iters; ++it) {
         const int u = it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);
         if (u >= a.num_units) continue;
@@ -228,17 +323,27 @@ hconv_stack_kernel(const __grid_constant__ CUtensorMap in_map, const TcConvArgs 
         const int r = u - n * units_per_frame;
         const int uy = r / a.units_x, ux = r - uy * a.units_x;
         mbar_wait(bar_win_empty, (vit & 1) ^ 1);
-        mbar_arrive_expect_tx(bar_win_full, Cfg::WIN_BYTES);
-        tma_load_4d(win, &in_map, bar_win_full, 2 * (ux * 64 + Cfg::MIN_COL), uy * kTileRows - Cfg::PAD, 0, n);
+        if constexpr (CS > 1) {
+          // the leader's barrier collects the bytes of both windows (the peer's unit is u + 1)
+          if (crank == 0)
+            mbar_arrive_expect_tx(bar_win_full, Cfg::WIN_BYTES * ((u + 1 < a.num_units) ? 2 : 1));
+          tma_load_4d_2cta(win, &in_map, lead_win_full, 2 * (ux * 64 + Cfg::MIN_COL),
+                           uy * kTileRows - Cfg::PAD, 0, n);
+        } else {
+          mbar_arrive_expect_tx(bar_win_full, Cfg::WIN_BYTES);
+          tma_load_4d(win, &in_map, bar_win_full, 2 * (ux * 64 + Cfg::MIN_COL), uy * kTileRows - Cfg::PAD, 0, n);
+        }
         ++vit;
       }
     }
+  } else if (warp == 1 && crank != 0) {
+    // peer CTA of a pair: its MMAs are issued by the leader
   } else if (warp == 1) {
     // ---------------- MMA issuer (convergent warp, one elected lane issues) ----------------
     const bool leader = elect_one();
-    constexpr uint32_t idesc = make_idesc(1 /*bf16*/, 128, Cfg::NPAD);
+    constexpr uint32_t idesc = make_idesc(1 /*bf16*/, 128 * CS, Cfg::NPAD);
     const uint64_t adesc0 = make_smem_desc(win, Cfg::CHUNK_PITCH, Cfg::ROW_PITCH);
-    const uint64_t bdesc0 = make_smem_desc(w_buf, Cfg::NPAD * 16, 128);
+    const uint64_t bdesc0 = make_smem_desc(w_buf, Cfg::NLOC * 16, 128);
     uint32_t st = 0, ph = 0;
     uint32_t tc = 0;            // running tile counter: TMEM slot = tc & 3, use count = tc >> 2
     int vit = 0;
@@ -246,12 +351,10 @@ hconv_stack_kernel(const __grid_constant__ CUtensorMap in_map, const TcConvArgs 
     for (int it = 0; it < iters; ++it) {
       const int u = it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);
       const bool valid = u < a.num_units;
-      if (valid) {
-        t0 = clock64();
-        mbar_wait(bar_win_full, vit & 1);
-        t_win += clock64() - t0;
-        tc_fence_after();
-      }
+      t0 = clock64();
+      if (valid) mbar_wait(bar_win_full, vit & 1);
+      t_win += clock64() - t0;
+      tc_fence_after();
       for (int pr = 0; pr < npairs; ++pr) {
         const int j0 = 2 * pr;
         const bool two = (j0 + 1) < NT;
@@ -277,12 +380,17 @@ hconv_stack_kernel(const __grid_constant__ CUtensorMap in_map, const TcConvArgs 
             const uint64_t adesc = a_tile0 + stage_off + static_cast<uint64_t>(T * g);
             const uint32_t accum = (sg | g) != 0;
             if (leader) {
-              mma_bf16_ss(acc0, adesc, bdesc, idesc, accum);
-              if (two) mma_bf16_ss(acc1, adesc + 8, bdesc, idesc, accum);
+              if constexpr (CS > 1) {
+                mma_bf16_ss_2cta(acc0, adesc, bdesc, idesc, accum);
+                if (two) mma_bf16_ss_2cta(acc1, adesc + 8, bdesc, idesc, accum);
+              } else {
+                mma_bf16_ss(acc0, adesc, bdesc, idesc, accum);
+                if (two) mma_bf16_ss(acc1, adesc + 8, bdesc, idesc, accum);
+              }
             }
           }
           if (leader) {
-            if constexpr (CS > 1) detail::tc_commit_multicast(bar_w_empty + 8 * st, kMask);
+            if constexpr (CS > 1) tc_commit_2cta(bar_w_empty + 8 * st, kMask);
             else tc_commit(bar_w_empty + 8 * st);
           }
           if (++st == Cfg::WSTAGES) { st = 0; ph ^= 1; }
@@ -294,15 +402,22 @@ hconv_stack_kernel(const __grid_constant__ CUtensorMap in_map, const TcConvArgs 
           else stage_off += (2 * Cfg::CHUNK_PITCH) >> 4;
         }
         if (leader) {
-          tc_commit(bar_acc_full + 8 * s0);
-          if (two) tc_commit(bar_acc_full + 8 * s1);
+          if constexpr (CS > 1) {
+            tc_commit_2cta(bar_acc_full + 8 * s0, kMask);
+            if (two) tc_commit_2cta(bar_acc_full + 8 * s1, kMask);
+          } else {
+            tc_commit(bar_acc_full + 8 * s0);
+            if (two) tc_commit(bar_acc_full + 8 * s1);
+          }
         }
         tc += two ? 2 : 1;
       }
-      if (valid) {
-        if (leader) tc_commit(bar_win_empty);
-        ++vit;
+      // release the windows: in pair mode both CTAs' windows were read by these MMAs
+      if (leader && valid) {
+        if constexpr (CS > 1) tc_commit_2cta(bar_win_empty, kMask);
+        else tc_commit(bar_win_empty);
       }
+      if (valid) ++vit;
     }
     if (a.prof && leader) {
       long long* o = a.prof + static_cast<size_t>(blockIdx.x) * 8;
@@ -310,71 +425,22 @@ hconv_stack_kernel(const __grid_constant__ CUtensorMap in_map, const TcConvArgs 
     }
     __syncwarp();
   } else if (warp >= 4) {
-    // ---------------- epilogue: un-stack (rotate + carry), fused math, stores ----------------
-    const int ew = warp & 3;
-    const int m = ew * 32 + lane;
-    const int prow = m >> 3, pcol = m & 7;
-    uint32_t tc = 0;
-    long long e_wait = 0, e_begin = clock64(), e0;
-    for (int it = 0; it < iters; ++it) {
-      const int u = it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);
-      const bool valid = u < a.num_units;
-      const int n = u / units_per_frame;
-      const int r = u - n * units_per_frame;
-      const int uy = r / a.units_x, ux = r - uy * a.units_x;
-      const int y = uy * kTileRows + prow;
-      float carry[KC];
-#pragma unroll
-      for (int c = 0; c < KC; ++c) carry[c] = 0.f;
-#pragma unroll 1
-      for (int j = 0; j < NT; ++j, ++tc) {
-        const uint32_t slot = tc & 3;
-        e0 = clock64();
-        mbar_wait(bar_acc_full + 8 * slot, (tc >> 2) & 1);
-        e_wait += clock64() - e0;
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + slot * Cfg::NPAD;
-        float out[KC], nxt[KC];
-        detail::tmem_ld_block<KC>(taddr, out);
-#pragma unroll
-        for (int c = 0; c < KC; ++c) { out[c] += carry[c]; nxt[c] = 0.f; }
-#pragma unroll
-        for (int s = 1; s < T; ++s) {
-          float blk[KC];
-          detail::tmem_ld_block<KC>(taddr + s * KC, blk);
-          const int src = (lane & ~7) | ((pcol - s) & 7);
-          const bool own = pcol >= s;
-#pragma unroll
-          for (int c = 0; c < KC; ++c) {
-            const float v = __shfl_sync(0xffffffffu, blk[c], src);
-            if (own) out[c] += v; else nxt[c] += v;
-          }
-        }
-        tc_fence_before();
-        mbar_arrive(bar_acc_empty + 8 * slot);          // accumulator drained: MMAs may reuse it
-#pragma unroll
-        for (int c = 0; c < KC; ++c) carry[c] = nxt[c];
-        const int x = ux * 64 + 8 * (j - 1) + pcol;
-        if (valid && j >= 1 && y < a.H && x < a.W) {
-          float acc[KP];
-#pragma unroll
-          for (int c = 0; c < KP; ++c) acc[c] = (c < KC) ? out[c < KC ? c : 0] : 0.f;
-          Epi::template apply<KP>(a, n, y, x, acc);
-        }
-      }
-    }
-    if (a.prof && threadIdx.x == 128) {
-      long long* o = a.prof + static_cast<size_t>(blockIdx.x) * 8;
-      o[4] = clock64() - e_begin; o[5] = e_wait;
-    }
+    // ---------------- epilogue: two warpgroups, channels split at Cfg::CSPLIT ----------------
+    if (warp < 8)
+      stack_epilogue<Cfg, Epi, 0, Cfg::CSPLIT>(a, tmem_base, bar_acc_full, bar_acc_empty, crank, iters, NT,
+                                               units_per_frame, warp, lane, true);
+    else
+      stack_epilogue<Cfg, Epi, Cfg::CSPLIT, KC - Cfg::CSPLIT>(a, tmem_base, bar_acc_full, bar_acc_empty, crank,
+                                                              iters, NT, units_per_frame, warp, lane, false);
   }
 
   tc_fence_before();
   __syncthreads();
-  if constexpr (CS > 1) detail::cluster_sync_all();     // no CTA exits while a peer may still signal it
+  if constexpr (CS > 1) cluster_sync_all();     // no CTA exits while a peer may still signal it
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    if constexpr (CS > 1) tmem_dealloc_2cta<512>(tmem_base);
+    else tmem_dealloc<512>(tmem_base);
   }
 }
 

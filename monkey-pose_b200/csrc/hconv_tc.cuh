@@ -66,9 +66,9 @@ struct TcConvArgs {
   const float* bias;        // [KP] lateral bias / conv bias (zero padded)
   const float* scale;       // [KP] (EpiBiasReluAffine) batch-norm scale, zero padded
   const float* shift;       // [KP]
-  float* out;               // fp32 NHWC [N][H][W][KP]
+  float* out;               // fp32 quad-chunked [N][KP/4][H][W][4]
   __nv_bfloat16* out_bf16;  // optional bf16 chunked copy [N][KP/8][H][W][8]
-  // fused hGRU epilogues (all fp32 NHWC [N][H][W][KP] unless noted)
+  // fused hGRU epilogues (all fp32 quad-chunked [N][KP/4][H][W][4] unless noted)
   const float* X;           // feed-forward drive
   const float* H1;          // EpiH2: inhibited state of this timestep
   const float* G;           // EpiH2: mix gate G2
@@ -79,6 +79,13 @@ struct TcConvArgs {
   const float* rho_t;       // device pointer to the adaptation scale rho[t] of this timestep
   long long* prof;          // optional per-CTA cycle counters (development; nullptr in production)
 };
+
+// fp32 state tensors of the tensor-core path are "quad-chunked": [n][c/4][y][x][4].  A thread owns
+// one pixel (its TMEM lane) and a warp covers 8 horizontally adjacent pixels x 4 rows, so one 16-byte
+// access per thread makes each warp request 4 fully used 128-byte lines (NHWC would touch 32 lines).
+__device__ __forceinline__ size_t quad_off(const TcConvArgs& a, int n, int quad, size_t pin) {
+  return ((static_cast<size_t>(n) * (a.KP >> 2) + quad) * (static_cast<size_t>(a.H) * a.W) + pin) * 4;
+}
 
 __device__ __forceinline__ float fast_sigmoid(float x) { return 1.f / (1.f + __expf(-x)); }
 // tanh via one exp: (1 - e^-2x) / (1 + e^-2x); |err| ~ 1e-7 abs, far inside the bf16-path budget
@@ -99,16 +106,24 @@ __device__ __forceinline__ void store_chunk_bf16(__nv_bfloat16* base, int KP, in
 // ---- epilogue functors: consume one pixel's CO_PAD accumulators --------------------------------
 // out = acc + bias                       (P = conv + lateral_bias, hgru_module.py:657)
 struct EpiBias {
+  template <int NCH> struct Pre {};
+  template <int NCH>
+  __device__ static __forceinline__ void load(const TcConvArgs&, int, size_t, int, Pre<NCH>&) {}
+  template <int NCH>
+  __device__ static __forceinline__ void finish(const TcConvArgs& a, int n, size_t pin, int c0,
+                                                const float* acc, const Pre<NCH>&) {
+#pragma unroll
+    for (int c = 0; c < NCH; c += 4) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + c0 + c));
+      *reinterpret_cast<float4*>(a.out + quad_off(a, n, (c0 + c) >> 2, pin)) =
+          make_float4(acc[c] + b.x, acc[c + 1] + b.y, acc[c + 2] + b.z, acc[c + 3] + b.w);
+    }
+  }
   template <int CO_PAD>
   __device__ static __forceinline__ void apply(const TcConvArgs& a, int n, int y, int x,
                                                float (&acc)[CO_PAD]) {
-    float* dst = a.out + ((static_cast<size_t>(n) * a.H + y) * a.W + x) * a.KP;
-#pragma unroll
-    for (int c = 0; c < CO_PAD; c += 4) {
-      const float4 b = *reinterpret_cast<const float4*>(a.bias + c);
-      *reinterpret_cast<float4*>(dst + c) =
-          make_float4(acc[c] + b.x, acc[c + 1] + b.y, acc[c + 2] + b.z, acc[c + 3] + b.w);
-    }
+    Pre<CO_PAD> p;
+    finish<CO_PAD>(a, n, static_cast<size_t>(y) * a.W + x, 0, acc, p);
   }
 };
 // out = relu(acc + bias) * scale + shift  (conv_layer + inference batch-norm, hgru_pose.py:61-80),
@@ -118,46 +133,53 @@ struct EpiBiasReluAffine {
   __device__ static __forceinline__ void apply(const TcConvArgs& a, int n, int y, int x,
                                                float (&acc)[CO_PAD]) {
     const size_t pin = static_cast<size_t>(y) * a.W + x;
-    float* dst = a.out + (static_cast<size_t>(n) * a.H * a.W + pin) * a.KP;
 #pragma unroll
     for (int c = 0; c < CO_PAD; c += 8) {
       float r[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        r[j] = fmaxf(acc[c + j] + a.bias[c + j], 0.f) * a.scale[c + j] + a.shift[c + j];
-      *reinterpret_cast<float4*>(dst + c) = make_float4(r[0], r[1], r[2], r[3]);
-      *reinterpret_cast<float4*>(dst + c + 4) = make_float4(r[4], r[5], r[6], r[7]);
-      if (a.out_bf16) {
-        __nv_bfloat162 h[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(r[2 * j], r[2 * j + 1]);
-        __nv_bfloat16* o = a.out_bf16 +
-            ((static_cast<size_t>(n) * (a.KP >> 3) + (c >> 3)) * (a.H * a.W) + pin) * 8;
-        *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(h);
-      }
+        r[j] = fmaxf(acc[c + j] + __ldg(a.bias + c + j), 0.f) * __ldg(a.scale + c + j) + __ldg(a.shift + c + j);
+      *reinterpret_cast<float4*>(a.out + quad_off(a, n, c >> 2, pin)) = make_float4(r[0], r[1], r[2], r[3]);
+      *reinterpret_cast<float4*>(a.out + quad_off(a, n, (c >> 2) + 1, pin)) = make_float4(r[4], r[5], r[6], r[7]);
+      if (a.out_bf16) store_chunk_bf16(a.out_bf16, a.KP, a.H * a.W, n, c >> 3, pin, r);
     }
   }
 };
 
+// ---- fused integration epilogues -----------------------------------------------------------------
+// Both are split into `load` (every global read of a pixel's NCH channels, issued back to back so
+// their latencies overlap, and callable BEFORE the accumulator is ready) and `finish` (math + stores).
+// The split matters: H2 is updated in place, so without it the compiler must order each chunk's
+// loads after the previous chunk's stores and the epilogue becomes a chain of DRAM round trips.
+//
 // input_integration fused into the C1 conv (hgru_module.py:657, 795-804):
 //   C1 = acc + lateral_bias;  H1 = tanh(X - (beta*H2 + nu) * C1)
 // writes H1 fp32 and its bf16 chunked operand copy.  bias = lateral_bias, v0 = beta, v1 = nu.
 struct EpiH1 {
-  template <int CO_PAD>
-  __device__ static __forceinline__ void apply(const TcConvArgs& a, int n, int y, int x,
-                                               float (&acc)[CO_PAD]) {
-    const size_t pin = static_cast<size_t>(y) * a.W + x;
-    const size_t off = (static_cast<size_t>(n) * a.H * a.W + pin) * a.KP;
+  template <int NCH>
+  struct Pre { float4 x[NCH / 4], h[NCH / 4]; };
+  template <int NCH>
+  __device__ static __forceinline__ void load(const TcConvArgs& a, int n, size_t pin, int c0, Pre<NCH>& p) {
 #pragma unroll
-    for (int c = 0; c < CO_PAD; c += 8) {
+    for (int i = 0; i < NCH / 4; ++i) {
+      const size_t o = quad_off(a, n, (c0 >> 2) + i, pin);
+      p.x[i] = *reinterpret_cast<const float4*>(a.X + o);
+      p.h[i] = *reinterpret_cast<const float4*>(a.H2 + o);
+    }
+  }
+  template <int NCH>
+  __device__ static __forceinline__ void finish(const TcConvArgs& a, int n, size_t pin, int c0,
+                                                const float* acc, const Pre<NCH>& p) {
+#pragma unroll
+    for (int c = 0; c < NCH; c += 8) {
       float r[8];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        const float4 xv = *reinterpret_cast<const float4*>(a.X + off + c + 4 * h);
-        const float4 hv = *reinterpret_cast<const float4*>(a.H2 + off + c + 4 * h);
-        const float4 lb = __ldg(reinterpret_cast<const float4*>(a.bias + c + 4 * h));
-        const float4 be = __ldg(reinterpret_cast<const float4*>(a.v0 + c + 4 * h));
-        const float4 nu = __ldg(reinterpret_cast<const float4*>(a.v1 + c + 4 * h));
+        const int i = (c >> 2) + h;
+        const float4 xv = p.x[i], hv = p.h[i];
+        const float4 lb = __ldg(reinterpret_cast<const float4*>(a.bias + c0 + c + 4 * h));
+        const float4 be = __ldg(reinterpret_cast<const float4*>(a.v0 + c0 + c + 4 * h));
+        const float4 nu = __ldg(reinterpret_cast<const float4*>(a.v1 + c0 + c + 4 * h));
         r[4 * h + 0] = fast_tanh(xv.x - (be.x * hv.x + nu.x) * (acc[c + 4 * h + 0] + lb.x));
         r[4 * h + 1] = fast_tanh(xv.y - (be.y * hv.y + nu.y) * (acc[c + 4 * h + 1] + lb.y));
         r[4 * h + 2] = fast_tanh(xv.z - (be.z * hv.z + nu.z) * (acc[c + 4 * h + 2] + lb.z));
@@ -165,11 +187,22 @@ struct EpiH1 {
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        if (c + j >= a.kreal) r[j] = 0.f;
-      float* dst = a.out + off + c;
-      *reinterpret_cast<float4*>(dst) = make_float4(r[0], r[1], r[2], r[3]);
-      *reinterpret_cast<float4*>(dst + 4) = make_float4(r[4], r[5], r[6], r[7]);
-      store_chunk_bf16(a.out_bf16, a.KP, a.H * a.W, n, c >> 3, pin, r);
+        if (c0 + c + j >= a.kreal) r[j] = 0.f;
+      *reinterpret_cast<float4*>(a.out + quad_off(a, n, (c0 + c) >> 2, pin)) = make_float4(r[0], r[1], r[2], r[3]);
+      *reinterpret_cast<float4*>(a.out + quad_off(a, n, ((c0 + c) >> 2) + 1, pin)) = make_float4(r[4], r[5], r[6], r[7]);
+      store_chunk_bf16(a.out_bf16, a.KP, a.H * a.W, n, (c0 + c) >> 3, pin, r);
+    }
+  }
+  template <int CO_PAD>
+  __device__ static __forceinline__ void apply(const TcConvArgs& a, int n, int y, int x,
+                                               float (&acc)[CO_PAD]) {
+    constexpr int NCH = CO_PAD < 32 ? CO_PAD : 32;
+    const size_t pin = static_cast<size_t>(y) * a.W + x;
+#pragma unroll
+    for (int c0 = 0; c0 < CO_PAD; c0 += NCH) {
+      Pre<NCH> p;
+      load<NCH>(a, n, pin, c0, p);
+      finish<NCH>(a, n, pin, c0, acc + c0, p);
     }
   }
 };
@@ -178,21 +211,29 @@ struct EpiH1 {
 //   H2 = (G2*H2 + (1-G2)*Ht) * rho_t      (in place) + bf16 chunked copy of the new H2.
 // bias = lateral_bias, v0 = gamma, v1 = kappa, v2 = omega.
 struct EpiH2 {
-  template <int CO_PAD>
-  __device__ static __forceinline__ void apply(const TcConvArgs& a, int n, int y, int x,
-                                               float (&acc)[CO_PAD]) {
-    const size_t pin = static_cast<size_t>(y) * a.W + x;
-    const size_t off = (static_cast<size_t>(n) * a.H * a.W + pin) * a.KP;
+  template <int NCH>
+  struct Pre { float4 h1[NCH / 4], g[NCH / 4], h2[NCH / 4]; };
+  template <int NCH>
+  __device__ static __forceinline__ void load(const TcConvArgs& a, int n, size_t pin, int c0, Pre<NCH>& p) {
+#pragma unroll
+    for (int i = 0; i < NCH / 4; ++i) {
+      const size_t o = quad_off(a, n, (c0 >> 2) + i, pin);
+      p.h1[i] = *reinterpret_cast<const float4*>(a.H1 + o);
+      p.g[i] = *reinterpret_cast<const float4*>(a.G + o);
+      p.h2[i] = *reinterpret_cast<const float4*>(a.H2 + o);
+    }
+  }
+  template <int NCH>
+  __device__ static __forceinline__ void finish(const TcConvArgs& a, int n, size_t pin, int c0,
+                                                const float* acc, const Pre<NCH>& p) {
     const float rho = __ldg(a.rho_t);
 #pragma unroll
-    for (int c = 0; c < CO_PAD; c += 8) {
+    for (int c = 0; c < NCH; c += 8) {
       float r[8];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        const int cc = c + 4 * h;
-        const float4 h1 = *reinterpret_cast<const float4*>(a.H1 + off + cc);
-        const float4 g = *reinterpret_cast<const float4*>(a.G + off + cc);
-        const float4 h2 = *reinterpret_cast<const float4*>(a.H2 + off + cc);
+        const int i = (c >> 2) + h, cc = c0 + c + 4 * h;
+        const float4 h1 = p.h1[i], g = p.g[i], h2 = p.h2[i];
         const float4 lb = __ldg(reinterpret_cast<const float4*>(a.bias + cc));
         const float4 ga = __ldg(reinterpret_cast<const float4*>(a.v0 + cc));
         const float4 ka = __ldg(reinterpret_cast<const float4*>(a.v1 + cc));
@@ -203,18 +244,29 @@ struct EpiH2 {
         const float omv[4] = {om.x, om.y, om.z, om.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float e = gav[j] * (acc[cc + j] + lbv[j]);
+          const float e = gav[j] * (acc[c + 4 * h + j] + lbv[j]);
           const float ht = fast_tanh(kav[j] * (h1v[j] + e) + omv[j] * (h1v[j] * e));
           r[4 * h + j] = (gv[j] * h2v[j] + (1.f - gv[j]) * ht) * rho;
         }
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        if (c + j >= a.kreal) r[j] = 0.f;
-      float* dst = a.H2 + off + c;
-      *reinterpret_cast<float4*>(dst) = make_float4(r[0], r[1], r[2], r[3]);
-      *reinterpret_cast<float4*>(dst + 4) = make_float4(r[4], r[5], r[6], r[7]);
-      store_chunk_bf16(a.out_bf16, a.KP, a.H * a.W, n, c >> 3, pin, r);
+        if (c0 + c + j >= a.kreal) r[j] = 0.f;
+      *reinterpret_cast<float4*>(a.H2 + quad_off(a, n, (c0 + c) >> 2, pin)) = make_float4(r[0], r[1], r[2], r[3]);
+      *reinterpret_cast<float4*>(a.H2 + quad_off(a, n, ((c0 + c) >> 2) + 1, pin)) = make_float4(r[4], r[5], r[6], r[7]);
+      store_chunk_bf16(a.out_bf16, a.KP, a.H * a.W, n, (c0 + c) >> 3, pin, r);
+    }
+  }
+  template <int CO_PAD>
+  __device__ static __forceinline__ void apply(const TcConvArgs& a, int n, int y, int x,
+                                               float (&acc)[CO_PAD]) {
+    constexpr int NCH = CO_PAD < 32 ? CO_PAD : 32;
+    const size_t pin = static_cast<size_t>(y) * a.W + x;
+#pragma unroll
+    for (int c0 = 0; c0 < CO_PAD; c0 += NCH) {
+      Pre<NCH> p;
+      load<NCH>(a, n, pin, c0, p);
+      finish<NCH>(a, n, pin, c0, acc + c0, p);
     }
   }
 };
@@ -223,7 +275,7 @@ struct EpiGateOut {
   template <int CO_PAD>
   __device__ static __forceinline__ void apply(const TcConvArgs& a, int n, int y, int x,
                                                float (&acc)[CO_PAD]) {
-    float* dst = a.out + ((static_cast<size_t>(n) * a.H + y) * a.W + x) * a.KP;
+    const size_t pin = static_cast<size_t>(y) * a.W + x;
 #pragma unroll
     for (int c = 0; c < CO_PAD; c += 4) {
       const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + c));
@@ -233,7 +285,7 @@ struct EpiGateOut {
       if (c + 1 >= a.kreal) g.y = 0.f;
       if (c + 2 >= a.kreal) g.z = 0.f;
       if (c + 3 >= a.kreal) g.w = 0.f;
-      *reinterpret_cast<float4*>(dst + c) = g;
+      *reinterpret_cast<float4*>(a.out + quad_off(a, n, c >> 2, pin)) = g;
     }
   }
 };
@@ -244,18 +296,20 @@ struct EpiGateIn {
   __device__ static __forceinline__ void apply(const TcConvArgs& a, int n, int y, int x,
                                                float (&acc)[CO_PAD]) {
     const size_t pin = static_cast<size_t>(y) * a.W + x;
-    const size_t off = (static_cast<size_t>(n) * a.H * a.W + pin) * a.KP;
+    float4 hv[CO_PAD / 4];
+#pragma unroll
+    for (int i = 0; i < CO_PAD / 4; ++i) hv[i] = *reinterpret_cast<const float4*>(a.H2 + quad_off(a, n, i, pin));
 #pragma unroll
     for (int c = 0; c < CO_PAD; c += 8) {
       float r[8];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + c + 4 * h));
-        const float4 hv = *reinterpret_cast<const float4*>(a.H2 + off + c + 4 * h);
-        r[4 * h + 0] = fast_sigmoid(acc[c + 4 * h + 0] + b.x) * hv.x;
-        r[4 * h + 1] = fast_sigmoid(acc[c + 4 * h + 1] + b.y) * hv.y;
-        r[4 * h + 2] = fast_sigmoid(acc[c + 4 * h + 2] + b.z) * hv.z;
-        r[4 * h + 3] = fast_sigmoid(acc[c + 4 * h + 3] + b.w) * hv.w;
+        const float4 v = hv[(c >> 2) + h];
+        r[4 * h + 0] = fast_sigmoid(acc[c + 4 * h + 0] + b.x) * v.x;
+        r[4 * h + 1] = fast_sigmoid(acc[c + 4 * h + 1] + b.y) * v.y;
+        r[4 * h + 2] = fast_sigmoid(acc[c + 4 * h + 2] + b.z) * v.z;
+        r[4 * h + 3] = fast_sigmoid(acc[c + 4 * h + 3] + b.w) * v.w;
       }
       store_chunk_bf16(a.out_bf16, a.KP, a.H * a.W, n, c >> 3, pin, r);   // pad channels: H2 pad is 0
     }

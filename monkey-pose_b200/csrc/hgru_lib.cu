@@ -150,7 +150,7 @@ int launch_stack(const CUtensorMap& map, hgru::TcConvArgs a, cudaStream_t st) {
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int grid = a.num_units < sms ? a.num_units : sms;
-  kern<<<grid, 256, Cfg::SMEM_BYTES, st>>>(map, a);
+  kern<<<grid, Cfg::NTHREADS, Cfg::SMEM_BYTES, st>>>(map, map, a);   // (w_map is only read in pair mode)
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
@@ -374,7 +374,7 @@ static int hgru_set_params_impl(hgru_plan_s* p, const float* p_r, const float* i
     if (p->stacked && stack_geometry(p->S, KP, k, &sg)) {
       const size_t ts = static_cast<size_t>(15) * sg.ksteps * sg.NG * 2 * 128 * 8;
       hgru::pack_weights_stack_kernel<<<nblk(ts), 256, 0, st>>>(p_r, p->wpk.as<__nv_bfloat16>(), k, sg.ksteps,
-                                                               sg.T, sg.KC, sg.NG);
+                                                               sg.T, sg.KC, sg.NG, 1);
     } else {
       hgru::pack_weights_kernel<<<nblk(total), 256, 0, st>>>(p_r, p->wpk.as<__nv_bfloat16>(), taps, k, ksteps, KP);
     }
@@ -446,8 +446,8 @@ static int hgru_run_bf16(hgru_plan_s* p, const float* Xp, float* H1_trace, float
   hgru::TcConvArgs base{};
   base.N = p->N; base.H = p->H; base.W = p->W; base.KP = KP; base.kreal = p->k;
   // operand copy of the initial state
-  hgru::to_chunked_bf16_kernel<<<nblk(p->nelem / 8), 256, 0, st>>>(p->H2.as<float>(), p->actH2.as<__nv_bfloat16>(),
-                                                                  p->nelem / 8, KP, HW);
+  hgru::quad_to_chunked_bf16_kernel<<<nblk(p->nelem / 8), 256, 0, st>>>(
+      p->H2.as<float>(), p->actH2.as<__nv_bfloat16>(), p->npix, KP, HW);
   ++p->launches;
   for (int t = 0; t < p->T; ++t) {
     // circuit_input gate (hgru_module.py:696-711): operand A = bf16(sigmoid(H2 *1x1 i_r + i_b) . H2)
@@ -483,17 +483,31 @@ static int hgru_run_bf16(hgru_plan_s* p, const float* Xp, float* H1_trace, float
     p->timer.end(st);
     p->launches += 4;
     if (H1_trace) {
-      hgru::unpad_channels_kernel<<<nblk(p->npix * p->k), 256, 0, st>>>(
-          p->H1.as<float>(), H1_trace + static_cast<size_t>(t) * p->npix * p->k, p->npix, p->k, KP);
+      hgru::quad_to_nhwc_kernel<<<nblk(p->npix * p->k), 256, 0, st>>>(
+          p->H1.as<float>(), H1_trace + static_cast<size_t>(t) * p->npix * p->k, p->npix, p->k, KP, HW);
       ++p->launches;
     }
     if (H2_trace) {
-      hgru::unpad_channels_kernel<<<nblk(p->npix * p->k), 256, 0, st>>>(
-          p->H2.as<float>(), H2_trace + static_cast<size_t>(t) * p->npix * p->k, p->npix, p->k, KP);
+      hgru::quad_to_nhwc_kernel<<<nblk(p->npix * p->k), 256, 0, st>>>(
+          p->H2.as<float>(), H2_trace + static_cast<size_t>(t) * p->npix * p->k, p->npix, p->k, KP, HW);
       ++p->launches;
     }
   }
   return 0;
+}
+
+// API boundary <-> internal state layout (fp32 mode: channel-padded NHWC; bf16 mode: quad-chunked)
+static void state_from_nhwc(const hgru_plan_s* p, const float* in, float* out, cudaStream_t st) {
+  if (p->mode == HGRU_MODE_BF16)
+    hgru::nhwc_to_quad_kernel<<<nblk(p->nelem / 4), 256, 0, st>>>(in, out, p->npix, p->k, p->KP, p->H * p->W);
+  else
+    hgru::pad_channels_kernel<<<nblk(p->nelem), 256, 0, st>>>(in, out, p->npix, p->k, p->KP);
+}
+static void state_to_nhwc(const hgru_plan_s* p, const float* in, float* out, cudaStream_t st) {
+  if (p->mode == HGRU_MODE_BF16)
+    hgru::quad_to_nhwc_kernel<<<nblk(p->npix * p->k), 256, 0, st>>>(in, out, p->npix, p->k, p->KP, p->H * p->W);
+  else
+    hgru::unpad_channels_kernel<<<nblk(p->npix * p->k), 256, 0, st>>>(in, out, p->npix, p->k, p->KP);
 }
 
 // The recurrence on padded buffers: X = Xp, state in p->H2 (in/out).
@@ -555,7 +569,7 @@ static int pose_forward_impl(pose_plan_s* p, const float* depth, const float* H2
   // conv_1 + relu + pool_1 + BN (hgru_pose.py:50-60)
   hgru::stem_conv1_pool_bn_kernel<<<nblk(npix * (KP / 8)), 256, sizeof(float) * 12 * KP, st>>>(
       depth, p->w1.as<float>(), p->b1.as<float>(), p->bn_scale(0), p->bn_shift(0), p->pool1.as<float>(),
-      tc ? p->act_pool1.as<__nv_bfloat16>() : nullptr, N, HW, HW, C, KP);
+      tc ? p->act_pool1.as<__nv_bfloat16>() : nullptr, N, HW, HW, C, KP, tc ? 1 : 0);
   ++p->launches;
   // conv_2 + relu + BN (:61-70), conv_3 + relu + BN (:71-80); conv3 output is X of the hGRU
   if (tc) {
@@ -580,7 +594,7 @@ static int pose_forward_impl(pose_plan_s* p, const float* depth, const float* H2
   p->launches += 2;
   // hGRU (:81, R-D4)
   if (H2_init) {
-    hgru::pad_channels_kernel<<<nblk(h->nelem), 256, 0, st>>>(H2_init, h->H2.as<float>(), npix, C, KP);
+    state_from_nhwc(h, H2_init, h->H2.as<float>(), st);
     ++p->launches;
   } else {
     CUDA_TRY(cudaMemsetAsync(h->H2.p, 0, h->H2.bytes, st));
@@ -592,7 +606,7 @@ static int pose_forward_impl(pose_plan_s* p, const float* depth, const float* H2
   int nsplit = p->nsplit;
   if (p->fc1_tc) {
     hgru::fc1_pack_a_kernel<<<nblk(npix * C), 256, 0, st>>>(h->H2.as<float>(), p->bn_scale(3), p->bn_shift(3),
-                                                           p->fc1_a.as<__nv_bfloat16>(), npix, C, KP);
+                                                           p->fc1_a.as<__nv_bfloat16>(), npix, C, KP, HW * HW);
     hgru::GemmArgs g{N, p->F, K, p->fc_kbps, p->part.as<float>()};
     dim3 grid((p->F + hgru::kGemmBN - 1) / hgru::kGemmBN, (N + hgru::kGemmBM - 1) / hgru::kGemmBM, p->fc_splits);
     hgru::gemm_tc_splitk_kernel<<<grid, 256, hgru::kGemmSmemBytes, st>>>(p->map_fc_a, p->map_fc_b, g);
@@ -660,14 +674,14 @@ int hgru_forward(hgru_plan_t p, const float* X, const float* H2_init, float* H2_
   if (!p) return fail(HGRU_E_INVALID, "hgru_forward: null plan");
   if (!X || !H2_out) return fail(HGRU_E_INVALID, "hgru_forward: null tensor pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  hgru::pad_channels_kernel<<<nblk(p->nelem), 256, 0, st>>>(X, p->Xp.as<float>(), p->npix, p->k, p->KP);
+  state_from_nhwc(p, X, p->Xp.as<float>(), st);
   if (H2_init)
-    hgru::pad_channels_kernel<<<nblk(p->nelem), 256, 0, st>>>(H2_init, p->H2.as<float>(), p->npix, p->k, p->KP);
+    state_from_nhwc(p, H2_init, p->H2.as<float>(), st);
   else
     CUDA_TRY(cudaMemsetAsync(p->H2.p, 0, p->H2.bytes, st));
   int rc = hgru_run_padded(p, p->Xp.as<float>(), H1_trace, H2_trace, st);
   if (rc) return rc;
-  hgru::unpad_channels_kernel<<<nblk(p->npix * p->k), 256, 0, st>>>(p->H2.as<float>(), H2_out, p->npix, p->k, p->KP);
+  state_to_nhwc(p, p->H2.as<float>(), H2_out, st);
   p->launches += 3;
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -831,7 +845,7 @@ int pose_get_activation(pose_plan_t p, const char* name, float* dst, void* strea
     CUDA_TRY(cudaMemcpyAsync(dst, p->fc1.p, p->fc1.bytes, cudaMemcpyDeviceToDevice, st));
     return 0;
   } else return fail(HGRU_E_INVALID, std::string("pose_get_activation: unknown name ") + name);
-  hgru::unpad_channels_kernel<<<nblk(npix * p->C), 256, 0, st>>>(src, dst, npix, p->C, p->KP);
+  state_to_nhwc(&p->hg, src, dst, st);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

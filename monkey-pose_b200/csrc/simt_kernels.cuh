@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(256)
 stem_conv1_pool_bn_kernel(const float* __restrict__ depth, const float* __restrict__ w /*[3][3][1][C]*/,
                           const float* __restrict__ bias, const float* __restrict__ scale,
                           const float* __restrict__ shift, float* __restrict__ out,
-                          __nv_bfloat16* __restrict__ out_bf16, int N, int H, int W, int C, int KP) {
+                          __nv_bfloat16* __restrict__ out_bf16, int N, int H, int W, int C, int KP, int quad) {
   extern __shared__ float smem_f[];
   float* wsm = smem_f;             // [9][KP]
   float* bsm = wsm + 9 * KP;       // bias, scale, shift: [3][KP]
@@ -215,8 +215,16 @@ stem_conv1_pool_bn_kernel(const float* __restrict__ depth, const float* __restri
     // relu and max commute; pad channels have zero scale/shift -> 0
     r.v[j] = fmaxf(m + bsm[c], 0.f) * bsm[KP + c] + bsm[2 * KP + c];
   }
-  st8(out + p * KP + cg * 8, r);
-  if (out_bf16) st8_bf16(chunk_ptr(out_bf16, n, cg, static_cast<size_t>(y) * W + x, H * W, CG), r);
+  const size_t pin = static_cast<size_t>(y) * W + x;
+  if (quad) {   // quad-chunked fp32 [n][c/4][pix][4] (tensor-core path)
+    const size_t HW = static_cast<size_t>(H) * W;
+    float* o = out + ((static_cast<size_t>(n) * (KP >> 2) + 2 * cg) * HW + pin) * 4;
+    *reinterpret_cast<float4*>(o) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    *reinterpret_cast<float4*>(o + HW * 4) = make_float4(r.v[4], r.v[5], r.v[6], r.v[7]);
+  } else {
+    st8(out + p * KP + cg * 8, r);
+  }
+  if (out_bf16) st8_bf16(chunk_ptr(out_bf16, n, cg, pin, H * W, CG), r);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -352,6 +360,50 @@ to_chunked_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__
   const size_t p = i / CG;
   const int n = p / HW;
   st8_bf16(chunk_ptr(out, n, cg, p - static_cast<size_t>(n) * HW, HW, CG), ld8(in + i * 8));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Layout conversions at the boundary of the tensor-core path, whose fp32 state tensors are
+// quad-chunked [n][c/4][pix][4] (see hconv_tc.cuh).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+nhwc_to_quad_kernel(const float* __restrict__ in, float* __restrict__ out, size_t npix, int k, int KP, int HW) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;   // over [n][quad][pin]
+  const int Q = KP >> 2;
+  if (i >= npix * Q) return;
+  const size_t pin = i % HW;
+  const int q = (i / HW) % Q;
+  const size_t n = i / (static_cast<size_t>(HW) * Q);
+  const float* src = in + (n * HW + pin) * k + 4 * q;
+  float4 v;
+  v.x = (4 * q + 0 < k) ? src[0] : 0.f;
+  v.y = (4 * q + 1 < k) ? src[1] : 0.f;
+  v.z = (4 * q + 2 < k) ? src[2] : 0.f;
+  v.w = (4 * q + 3 < k) ? src[3] : 0.f;
+  reinterpret_cast<float4*>(out)[i] = v;
+}
+__global__ void __launch_bounds__(256)
+quad_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, size_t npix, int k, int KP, int HW) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;   // over [npix][k]
+  if (i >= npix * k) return;
+  const int c = i % k;
+  const size_t p = i / k;
+  const size_t n = p / HW, pin = p - n * HW;
+  out[i] = in[((n * (KP >> 2) + (c >> 2)) * HW + pin) * 4 + (c & 3)];
+}
+__global__ void __launch_bounds__(256)
+quad_to_chunked_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t npix, int KP,
+                            int HW) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;   // over [n][cg][pin]
+  const int CG = KP >> 3;
+  if (i >= npix * CG) return;
+  const size_t pin = i % HW;
+  const int cg = (i / HW) % CG;
+  const size_t n = i / (static_cast<size_t>(HW) * CG);
+  const float4 a = *reinterpret_cast<const float4*>(in + ((n * (KP >> 2) + 2 * cg) * HW + pin) * 4);
+  const float4 b = *reinterpret_cast<const float4*>(in + ((n * (KP >> 2) + 2 * cg + 1) * HW + pin) * 4);
+  const F8 f{{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w}};
+  st8_bf16(out + i * 8, f);
 }
 
 // ------------------------------------------------------------------------------------------------
