@@ -59,10 +59,14 @@ struct StackCfg {
   static constexpr int BLK_BYTES = 2 * NLOC * 16;         // one CTA's part of a (dy, q, g) weight block
   static constexpr int STAGE_BYTES = NG * BLK_BYTES;      // all tap groups of one (dy, q), per CTA
   static constexpr int PASS_STAGES = S * KSTEPS;          // stages per tile pair
-  static constexpr int WSTAGES = (CS == 2) ? 8 : 4;        // pair mode: half-size stages, deeper ring
-  static constexpr int NUM_BARS = 2 + 2 * WSTAGES + 8;
+  static constexpr int GATE_A_BYTES = CG * 128 * 16;      // staging tile of the new state (bf16, K-major)
+  static constexpr int GATE_W_BYTES = KSTEPS * 2 * KP * 16;
+  static constexpr int GATE_BYTES = GATE_A_BYTES + GATE_W_BYTES;
+  // ring depth: as deep as the 227 KB allow (pair mode: half-size stages)
+  static constexpr int WSTAGES = (CS == 2) ? 8 : ((WIN_BYTES + GATE_BYTES + 4 * NG * 2 * NPAD * 16 + 2048 <= 232448) ? 4 : 3);
+  static constexpr int NUM_BARS = 2 + 2 * WSTAGES + 8 + 1;
   static constexpr int STAGE_ROWS = STAGE_BYTES / 256;    // rows of the 256-byte weight view per stage
-  static constexpr int SMEM_BYTES = WIN_BYTES + WSTAGES * STAGE_BYTES + NUM_BARS * 8 + 16 + 1024;
+  static constexpr int SMEM_BYTES = WIN_BYTES + WSTAGES * STAGE_BYTES + GATE_BYTES + NUM_BARS * 8 + 16 + 1024;
   static_assert(T * KC <= NPAD, "stacked taps must fit N = 128");
   static_assert(KC <= KP && KP % 16 == 0, "channel padding");
   static_assert((CHUNK_PITCH >> 4) < 16384, "LBO range");
@@ -162,9 +166,13 @@ __device__ __forceinline__ void tmem_ld_range(uint32_t taddr, float (&v)[CN]) {
 template <class Cfg, class Epi, int C0, int CN>
 __device__ __forceinline__ void stack_epilogue(const TcConvArgs& a, uint32_t tmem_base, uint32_t bar_acc_full,
                                                uint32_t bar_acc_empty, uint32_t crank, int iters, int NT,
-                                               int units_per_frame, int warp, int lane, bool profile) {
+                                               int units_per_frame, int warp, int lane, bool profile,
+                                               uint8_t* smem_raw, uint32_t gate_a, uint32_t gate_w,
+                                               uint32_t bar_gate) {
   using namespace sm100;
-  constexpr int KC = Cfg::KC, T = Cfg::T, CS = Cfg::CS;
+  constexpr int KC = Cfg::KC, T = Cfg::T, CS = Cfg::CS, KP = Cfg::KP;
+  const bool gated = Epi::kGate && a.do_gate;
+  uint32_t gate_uses = 0;
   constexpr int NCH = (CN + 7) / 8 * 8;            // channels handed to the fused epilogue (8-aligned)
   const int ew = warp & 3;
   const int m = ew * 32 + lane;
@@ -217,13 +225,60 @@ __device__ __forceinline__ void stack_epilogue(const TcConvArgs& a, uint32_t tme
           if (own) out[c] += v; else nxt[c] += v;
         }
       }
-      tc_fence_before();
-      // accumulator drained: MMAs may reuse it (pair mode: the leader's barrier counts both CTAs)
-      if (CS > 1 && crank != 0) mbar_arrive_cluster(lead_acc_empty + 8 * slot);
-      else mbar_arrive(bar_acc_empty + 8 * slot);
 #pragma unroll
       for (int c = 0; c < CN; ++c) carry[c] = nxt[c];
-      if (store) Epi::template finish<NCH>(a, n, pin, C0, out, pre);
+      if (!(gated && j >= 1)) {
+        tc_fence_before();
+        // accumulator drained: MMAs may reuse it (pair mode: the leader's barrier counts both CTAs)
+        if (CS > 1 && crank != 0) mbar_arrive_cluster(lead_acc_empty + 8 * slot);
+        else mbar_arrive(bar_acc_empty + 8 * slot);
+        if (store) Epi::template finish<NCH>(a, n, pin, C0, out, pre);
+      } else {
+        // ---- fused gate: new state -> bf16 staging tile -> 1x1 conv on the tensor core -> sigmoid ----
+        float hv[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) hv[c] = 0.f;
+        if (store) Epi::template finish<NCH>(a, n, pin, C0, out, pre, hv);
+        {
+          uint8_t* stg = smem_raw + (gate_a - smem_u32(smem_raw));
+#pragma unroll
+          for (int i = 0; i < NCH / 8; ++i) {
+            __nv_bfloat162 h[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(hv[8 * i + 2 * q], hv[8 * i + 2 * q + 1]);
+            *reinterpret_cast<uint4*>(stg + ((C0 >> 3) + i) * 2048 + m * 16) = *reinterpret_cast<const uint4*>(h);
+          }
+        }
+        fence_proxy_async();          // staging writes -> visible to the async (tensor core) proxy
+        tc_fence_before();            // our tcgen05.ld of this accumulator precede the barrier
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (warp == 4) {
+          // the tile's own accumulator columns [0, KP) are free now: gate pre-activations land there
+          const bool leader = elect_one();
+          tc_fence_after();
+          if (leader) {
+            constexpr uint32_t gdesc = make_idesc(1, 128, KP);
+            const uint64_t ad = make_smem_desc(gate_a, 2048, 128);
+            const uint64_t bd = make_smem_desc(gate_w, KP * 16, 128);
+#pragma unroll
+            for (int q = 0; q < Cfg::KSTEPS; ++q)
+              mma_bf16_ss(tmem_base + slot * Cfg::NPAD, ad + static_cast<uint64_t>((q * 2 * 2048) >> 4),
+                          bd + static_cast<uint64_t>((q * 2 * KP * 16) >> 4), gdesc, q != 0);
+            tc_commit(bar_gate);
+          }
+          __syncwarp();
+        }
+        mbar_wait(bar_gate, gate_uses & 1);
+        ++gate_uses;
+        tc_fence_after();
+        float gacc[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; c += 8) detail::tmem_ld_f<8>(taddr + c, gacc + c);   // columns C0 + c of the slot
+        tc_fence_before();
+        if (CS > 1 && crank != 0) mbar_arrive_cluster(lead_acc_empty + 8 * slot);
+        else mbar_arrive(bar_acc_empty + 8 * slot);
+        if (store) Epi::template gate<NCH>(a, n, pin, C0, gacc, hv);
+      }
     }
   }
   if (profile && a.prof && (threadIdx.x & 127) == 0) {
@@ -242,13 +297,16 @@ hconv_stack_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t win = base;
   const uint32_t w_buf = win + Cfg::WIN_BYTES;
-  const uint32_t bars = w_buf + Cfg::WSTAGES * Cfg::STAGE_BYTES;
+  const uint32_t gate_a = w_buf + Cfg::WSTAGES * Cfg::STAGE_BYTES;   // staging tile [CG][128 px][16 B]
+  const uint32_t gate_w = gate_a + Cfg::GATE_A_BYTES;                // 1x1 gate weights
+  const uint32_t bars = gate_w + Cfg::GATE_W_BYTES;
   const uint32_t bar_win_full = bars, bar_win_empty = bars + 8;
   const uint32_t bar_w_full = bars + 16;                             // [WSTAGES]
   const uint32_t bar_w_empty = bar_w_full + 8 * Cfg::WSTAGES;        // [WSTAGES]
   const uint32_t bar_acc_full = bar_w_empty + 8 * Cfg::WSTAGES;      // [4]
   const uint32_t bar_acc_empty = bar_acc_full + 32;                  // [4]
-  const uint32_t tmem_slot = bar_acc_empty + 32;
+  const uint32_t bar_gate = bar_acc_empty + 32;
+  const uint32_t tmem_slot = bar_gate + 8;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5;
@@ -267,6 +325,7 @@ hconv_stack_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
       mbar_init(bar_acc_full + 8 * i, 1);
       mbar_init(bar_acc_empty + 8 * i, 256 * CS);     // 2 epilogue groups (pair mode: of both CTAs, at the leader)
     }
+    mbar_init(bar_gate, 1);
     tma_prefetch_desc(&w_map);
     fence_barrier_init();
     tma_prefetch_desc(&in_map);
@@ -274,6 +333,14 @@ hconv_stack_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
   if (warp == 2) {
     if constexpr (CS > 1) tmem_alloc_2cta<512>(tmem_slot);
     else tmem_alloc<512>(tmem_slot);
+  }
+  if (Epi::kGate && a.do_gate && warp >= 4) {
+    // 1x1 gate weights -> shared memory (generic-proxy writes, made visible to the tensor core)
+    const uint4* src = reinterpret_cast<const uint4*>(a.gate_wpk);
+    uint8_t* dst = smem_raw + (gate_w - smem_u32(smem_raw));
+    for (int i = threadIdx.x - 128; i < Cfg::GATE_W_BYTES / 16; i += 256)
+      reinterpret_cast<uint4*>(dst)[i] = __ldg(src + i);
+    fence_proxy_async();
   }
   tc_fence_before();
   __syncthreads();
@@ -428,10 +495,12 @@ hconv_stack_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
     // ---------------- epilogue: two warpgroups, channels split at Cfg::CSPLIT ----------------
     if (warp < 8)
       stack_epilogue<Cfg, Epi, 0, Cfg::CSPLIT>(a, tmem_base, bar_acc_full, bar_acc_empty, crank, iters, NT,
-                                               units_per_frame, warp, lane, true);
+                                               units_per_frame, warp, lane, true, smem_raw, gate_a, gate_w,
+                                               bar_gate);
     else
       stack_epilogue<Cfg, Epi, Cfg::CSPLIT, KC - Cfg::CSPLIT>(a, tmem_base, bar_acc_full, bar_acc_empty, crank,
-                                                              iters, NT, units_per_frame, warp, lane, false);
+                                                              iters, NT, units_per_frame, warp, lane, false,
+                                                              smem_raw, gate_a, gate_w, bar_gate);
   }
 
   tc_fence_before();

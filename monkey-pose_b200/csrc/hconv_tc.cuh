@@ -77,6 +77,12 @@ struct TcConvArgs {
   const float* v1;
   const float* v2;
   const float* rho_t;       // device pointer to the adaptation scale rho[t] of this timestep
+  // gate fused behind the integration (stacked kernel): 1x1 conv of the new state on tensor cores
+  const __nv_bfloat16* gate_wpk;   // packed 1x1 weights [KSTEPS][2][KP][8] (o_r after H1, i_r after H2)
+  const float* gate_bias;          // [KP] (o_b / i_b)
+  float* gate_out;                 // EpiH1: G2 fp32 quad-chunked
+  __nv_bfloat16* gate_act_out;     // EpiH2: next step's gated operand bf16(G1 . H2), chunked
+  int do_gate;                     // 0: skip (last timestep's H2, or the unfused pipeline)
   long long* prof;          // optional per-CTA cycle counters (development; nullptr in production)
 };
 
@@ -106,12 +112,15 @@ __device__ __forceinline__ void store_chunk_bf16(__nv_bfloat16* base, int KP, in
 // ---- epilogue functors: consume one pixel's CO_PAD accumulators --------------------------------
 // out = acc + bias                       (P = conv + lateral_bias, hgru_module.py:657)
 struct EpiBias {
+  static constexpr bool kGate = false;
   template <int NCH> struct Pre {};
   template <int NCH>
   __device__ static __forceinline__ void load(const TcConvArgs&, int, size_t, int, Pre<NCH>&) {}
   template <int NCH>
+  __device__ static __forceinline__ void gate(const TcConvArgs&, int, size_t, int, const float*, const float*) {}
+  template <int NCH>
   __device__ static __forceinline__ void finish(const TcConvArgs& a, int n, size_t pin, int c0,
-                                                const float* acc, const Pre<NCH>&) {
+                                                const float* acc, const Pre<NCH>&, float* = nullptr) {
 #pragma unroll
     for (int c = 0; c < NCH; c += 4) {
       const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + c0 + c));
@@ -156,6 +165,7 @@ struct EpiBiasReluAffine {
 //   C1 = acc + lateral_bias;  H1 = tanh(X - (beta*H2 + nu) * C1)
 // writes H1 fp32 and its bf16 chunked operand copy.  bias = lateral_bias, v0 = beta, v1 = nu.
 struct EpiH1 {
+  static constexpr bool kGate = true;
   template <int NCH>
   struct Pre { float4 x[NCH / 4], h[NCH / 4]; };
   template <int NCH>
@@ -167,9 +177,25 @@ struct EpiH1 {
       p.h[i] = *reinterpret_cast<const float4*>(a.H2 + o);
     }
   }
+  // mix gate on the tensor-core result of H1 *1x1 o_r (hgru_module.py:729-740): G2 = sigmoid(. + o_b)
+  template <int NCH>
+  __device__ static __forceinline__ void gate(const TcConvArgs& a, int n, size_t pin, int c0, const float* gacc,
+                                              const float*) {
+#pragma unroll
+    for (int c = 0; c < NCH; c += 4) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(a.gate_bias + c0 + c));
+      float4 g = make_float4(fast_sigmoid(gacc[c] + b.x), fast_sigmoid(gacc[c + 1] + b.y),
+                             fast_sigmoid(gacc[c + 2] + b.z), fast_sigmoid(gacc[c + 3] + b.w));
+      if (c0 + c + 0 >= a.kreal) g.x = 0.f;
+      if (c0 + c + 1 >= a.kreal) g.y = 0.f;
+      if (c0 + c + 2 >= a.kreal) g.z = 0.f;
+      if (c0 + c + 3 >= a.kreal) g.w = 0.f;
+      *reinterpret_cast<float4*>(a.gate_out + quad_off(a, n, (c0 + c) >> 2, pin)) = g;
+    }
+  }
   template <int NCH>
   __device__ static __forceinline__ void finish(const TcConvArgs& a, int n, size_t pin, int c0,
-                                                const float* acc, const Pre<NCH>& p) {
+                                                const float* acc, const Pre<NCH>& p, float* hout = nullptr) {
 #pragma unroll
     for (int c = 0; c < NCH; c += 8) {
       float r[8];
@@ -191,6 +217,10 @@ struct EpiH1 {
       *reinterpret_cast<float4*>(a.out + quad_off(a, n, (c0 + c) >> 2, pin)) = make_float4(r[0], r[1], r[2], r[3]);
       *reinterpret_cast<float4*>(a.out + quad_off(a, n, ((c0 + c) >> 2) + 1, pin)) = make_float4(r[4], r[5], r[6], r[7]);
       store_chunk_bf16(a.out_bf16, a.KP, a.H * a.W, n, (c0 + c) >> 3, pin, r);
+      if (hout) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) hout[c + j] = r[j];
+      }
     }
   }
   template <int CO_PAD>
@@ -211,6 +241,7 @@ struct EpiH1 {
 //   H2 = (G2*H2 + (1-G2)*Ht) * rho_t      (in place) + bf16 chunked copy of the new H2.
 // bias = lateral_bias, v0 = gamma, v1 = kappa, v2 = omega.
 struct EpiH2 {
+  static constexpr bool kGate = true;
   template <int NCH>
   struct Pre { float4 h1[NCH / 4], g[NCH / 4], h2[NCH / 4]; };
   template <int NCH>
@@ -223,9 +254,23 @@ struct EpiH2 {
       p.h2[i] = *reinterpret_cast<const float4*>(a.H2 + o);
     }
   }
+  // input gate of the NEXT timestep on the tensor-core result of H2 *1x1 i_r (hgru_module.py:696-711):
+  // G1 = sigmoid(. + i_b); gated operand = bf16(G1 . H2) for the next C1 conv.
+  template <int NCH>
+  __device__ static __forceinline__ void gate(const TcConvArgs& a, int n, size_t pin, int c0, const float* gacc,
+                                              const float* hv) {
+#pragma unroll
+    for (int c = 0; c < NCH; c += 8) {
+      float r[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        r[j] = fast_sigmoid(gacc[c + j] + __ldg(a.gate_bias + c0 + c + j)) * hv[c + j];   // pad channels: hv = 0
+      store_chunk_bf16(a.gate_act_out, a.KP, a.H * a.W, n, (c0 + c) >> 3, pin, r);
+    }
+  }
   template <int NCH>
   __device__ static __forceinline__ void finish(const TcConvArgs& a, int n, size_t pin, int c0,
-                                                const float* acc, const Pre<NCH>& p) {
+                                                const float* acc, const Pre<NCH>& p, float* hout = nullptr) {
     const float rho = __ldg(a.rho_t);
 #pragma unroll
     for (int c = 0; c < NCH; c += 8) {
@@ -254,7 +299,11 @@ struct EpiH2 {
         if (c0 + c + j >= a.kreal) r[j] = 0.f;
       *reinterpret_cast<float4*>(a.H2 + quad_off(a, n, (c0 + c) >> 2, pin)) = make_float4(r[0], r[1], r[2], r[3]);
       *reinterpret_cast<float4*>(a.H2 + quad_off(a, n, ((c0 + c) >> 2) + 1, pin)) = make_float4(r[4], r[5], r[6], r[7]);
-      store_chunk_bf16(a.out_bf16, a.KP, a.H * a.W, n, (c0 + c) >> 3, pin, r);
+      if (a.out_bf16) store_chunk_bf16(a.out_bf16, a.KP, a.H * a.W, n, (c0 + c) >> 3, pin, r);
+      if (hout) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) hout[c + j] = r[j];
+      }
     }
   }
   template <int CO_PAD>

@@ -439,7 +439,10 @@ static int hgru_run_fp32(hgru_plan_s* p, const float* Xp, float* H1_trace, float
   return 0;
 }
 
-// ---- bf16 path: four tcgen05 launches per timestep, all integration math in the epilogues ----
+// ---- bf16 path ------------------------------------------------------------------------------------
+// Narrow layers (stacked kernel): two tcgen05 launches per timestep, the 1x1 gate convs run as
+// epilogue-issued MMAs inside them.  Wide layers (k = 64): four launches (gate-in, C1+H1, gate-out,
+// C2+H2).  All integration math happens on TMEM accumulators.
 static int hgru_run_bf16(hgru_plan_s* p, const float* Xp, float* H1_trace, float* H2_trace, cudaStream_t st) {
   const int KP = p->KP, HW = p->H * p->W;
   int rc;
@@ -449,39 +452,55 @@ static int hgru_run_bf16(hgru_plan_s* p, const float* Xp, float* H1_trace, float
   hgru::quad_to_chunked_bf16_kernel<<<nblk(p->nelem / 8), 256, 0, st>>>(
       p->H2.as<float>(), p->actH2.as<__nv_bfloat16>(), p->npix, KP, HW);
   ++p->launches;
+  const bool fused = p->stacked;
   for (int t = 0; t < p->T; ++t) {
-    // circuit_input gate (hgru_module.py:696-711): operand A = bf16(sigmoid(H2 *1x1 i_r + i_b) . H2)
-    hgru::TcConvArgs a = base;
-    a.wpk = p->wpk_i.as<__nv_bfloat16>(); a.bias = p->vec(V_IB); a.H2 = p->H2.as<float>();
-    a.out_bf16 = p->actA.as<__nv_bfloat16>();
-    if ((rc = dispatch_gate<hgru::EpiGateIn>(KP, p->actH2.as<__nv_bfloat16>(), a, st))) return rc;
+    hgru::TcConvArgs a;
+    if (!fused || t == 0) {
+      // circuit_input gate (hgru_module.py:696-711): operand A = bf16(sigmoid(H2 *1x1 i_r + i_b) . H2)
+      a = base;
+      a.wpk = p->wpk_i.as<__nv_bfloat16>(); a.bias = p->vec(V_IB); a.H2 = p->H2.as<float>();
+      a.out_bf16 = p->actA.as<__nv_bfloat16>();
+      if ((rc = dispatch_gate<hgru::EpiGateIn>(KP, p->actH2.as<__nv_bfloat16>(), a, st))) return rc;
+      ++p->launches;
+    }
     // C1 conv (:714-718, 657) + input_integration (:795-804) -> H1 (fp32 + bf16 operand copy)
+    // [fused: + circuit_output gate (:729-740) -> G2]
     a = base;
     a.wpk = p->wpk.as<__nv_bfloat16>(); a.bias = p->vec(V_LBIAS); a.X = Xp; a.H2 = p->H2.as<float>();
     a.v0 = p->vec(V_BETA); a.v1 = p->vec(V_NU);
     a.out = p->H1.as<float>(); a.out_bf16 = p->actH1.as<__nv_bfloat16>();
+    a.gate_wpk = p->wpk_o.as<__nv_bfloat16>(); a.gate_bias = p->vec(V_OB); a.gate_out = p->G.as<float>();
+    a.do_gate = fused ? 1 : 0;
     p->timer.begin(st);
     if ((rc = p->stacked ? dispatch_stack<hgru::EpiH1>(KP, p->stack_T, p->mapA, a, st)
                         : dispatch_tc_hconv<hgru::EpiH1>(p->S, KP, p->mapA, a, st)))
       return rc;
     p->timer.end(st);
-    // circuit_output gate (:729-740): G2 = sigmoid(H1 *1x1 o_r + o_b)
-    a = base;
-    a.wpk = p->wpk_o.as<__nv_bfloat16>(); a.bias = p->vec(V_OB); a.out = p->G.as<float>();
-    if ((rc = dispatch_gate<hgru::EpiGateOut>(KP, p->actH1.as<__nv_bfloat16>(), a, st))) return rc;
+    ++p->launches;
+    if (!fused) {
+      // circuit_output gate (:729-740): G2 = sigmoid(H1 *1x1 o_r + o_b)
+      a = base;
+      a.wpk = p->wpk_o.as<__nv_bfloat16>(); a.bias = p->vec(V_OB); a.out = p->G.as<float>();
+      if ((rc = dispatch_gate<hgru::EpiGateOut>(KP, p->actH1.as<__nv_bfloat16>(), a, st))) return rc;
+      ++p->launches;
+    }
     // C2 conv (:746-750, 657) + output_integration + rho (:806-823, 847-849) -> H2 in place
+    // [fused: + the next timestep's circuit_input gate -> operand A]
     a = base;
     a.wpk = p->wpk.as<__nv_bfloat16>(); a.bias = p->vec(V_LBIAS); a.H1 = p->H1.as<float>();
     a.G = p->G.as<float>(); a.H2 = p->H2.as<float>();
     a.v0 = p->vec(V_GAMMA); a.v1 = p->vec(V_KAPPA); a.v2 = p->vec(V_OMEGA);
     a.rho_t = p->rho.as<float>() + t;
-    a.out_bf16 = p->actH2.as<__nv_bfloat16>();
+    a.out_bf16 = fused ? nullptr : p->actH2.as<__nv_bfloat16>();
+    a.gate_wpk = p->wpk_i.as<__nv_bfloat16>(); a.gate_bias = p->vec(V_IB);
+    a.gate_act_out = p->actA.as<__nv_bfloat16>();
+    a.do_gate = (fused && t + 1 < p->T) ? 1 : 0;
     p->timer.begin(st);
     if ((rc = p->stacked ? dispatch_stack<hgru::EpiH2>(KP, p->stack_T, p->mapH1, a, st)
                         : dispatch_tc_hconv<hgru::EpiH2>(p->S, KP, p->mapH1, a, st)))
       return rc;
     p->timer.end(st);
-    p->launches += 4;
+    ++p->launches;
     if (H1_trace) {
       hgru::quad_to_nhwc_kernel<<<nblk(p->npix * p->k), 256, 0, st>>>(
           p->H1.as<float>(), H1_trace + static_cast<size_t>(t) * p->npix * p->k, p->npix, p->k, KP, HW);
