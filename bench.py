@@ -255,11 +255,19 @@ def run_ours(a):
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" \
         if "bf16_tflops_sustained" in peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
     roof = None
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json"))).get(str(k))
+        if tj and tj.get("batch") == B:
+            traffic = tj["bytes_per_launch"]
+    except Exception:
+        pass
     if k_n.value > 0 and a.mode == "bf16":
         avg_ms = k_ms.value / k_n.value
         ach = flops_per_launch / (avg_ms * 1e-3) * 1e-12
-        roof = {"bound": "tensor", "kernel": "hconv_tc_kernel (15x15 implicit GEMM, tcgen05)", "achieved": ach,
-                "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+        roof = {"bound": "tensor", "kernel": "hconv_stack_kernel (15x15 tap-stacked implicit GEMM + fused gates, tcgen05)" if k <= 32 else "hconv_tc_kernel (15x15 implicit GEMM, tcgen05)", "achieved": ach,
+                "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
+                "traffic_source": "ncu --set full capture, profiles/r01_ncu_traffic.json (bytes per launch)",
                 "peak_source": peak_src, "peak_burst": peaks.get("bf16_tflops"),
                 "avg_launch_ms": avg_ms, "launches_per_step": k_n.value,
                 "share_of_step": k_ms.value / (ms_dev / a.steps),

@@ -106,7 +106,7 @@ int run_case(int N, int H, int W, int k, int grid_override, int iters) {
   return (bad || nan) ? 1 : 0;
 }
 template <int KP, int T, int KC, int CS, class Epi>
-void time_real_epilogue(const char* name, int N, int H, int W, int k) {
+void time_real_epilogue(const char* name, int N, int H, int W, int k, int gate = 1) {
   using Cfg = hgru::StackCfg<KP, T, KC, CS>;
   const int CG = KP / 8;
   size_t npix = (size_t)N * H * W;
@@ -124,6 +124,7 @@ void time_real_epilogue(const char* name, int N, int H, int W, int k) {
   a.units_x = (W + 63) / 64; a.units_y = (H + 15) / 16; a.num_units = N * a.units_x * a.units_y;
   a.wpk = wpk; a.bias = vec; a.v0 = vec + KP; a.v1 = vec + 2 * KP; a.v2 = vec + 3 * KP; a.rho_t = vec + 4 * KP;
   a.X = X; a.H1 = H1; a.G = G; a.H2 = H2; a.out = H1; a.out_bf16 = actout;
+  a.gate_wpk = wpk; a.gate_bias = vec; a.gate_out = G; a.gate_act_out = actout; a.do_gate = gate;
   auto kern = hgru::hconv_stack_kernel<KP, T, KC, CS, Epi>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   int grid = 148;
@@ -141,7 +142,7 @@ void time_real_epilogue(const char* name, int N, int H, int W, int k) {
   for (int i = 0; i < 5; ++i) cudaLaunchKernelEx(&cfg, kern, map, wmap, a);
   cudaEventRecord(e1); CK(cudaDeviceSynchronize());
   float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 5;
-  printf("%s CS=%d: %.3f ms | leader avg cycles: mma_total=%.0f wait_win=%.0f wait_acc_empty=%.0f wait_w=%.0f | epi_total=%.0f epi_wait=%.0f\n", name, CS, ms,
+  printf("%s gate=%d CS=%d: %.3f ms | leader avg cycles: mma_total=%.0f wait_win=%.0f wait_acc_empty=%.0f wait_w=%.0f | epi_total=%.0f epi_wait=%.0f\n", name, gate, CS, ms,
          av[0] / nl, av[1] / nl, av[2] / nl, av[3] / nl, av[4] / grid, av[5] / grid);
   cudaFree(X); cudaFree(H1); cudaFree(G); cudaFree(H2); cudaFree(vec); cudaFree(act); cudaFree(actout); cudaFree(wpk); cudaFree(d_prof);
 }
@@ -158,12 +159,13 @@ int main(int argc, char** argv) {
   if (which == 0 || which == 8) f += run_case<32, 5, 25, 2>(256, 64, 64, 25, 0, 5);
   if (which == 0 || which == 9) f += run_case<32, 4, 32, 2>(256, 64, 64, 32, 0, 5);
   if (which == 20) {
-    time_real_epilogue<32, 5, 25, 1, hgru::EpiBias>("EpiBias", 256, 64, 64, 25);
-    time_real_epilogue<32, 5, 25, 1, hgru::EpiH1>("EpiH1", 256, 64, 64, 25);
-    time_real_epilogue<32, 5, 25, 1, hgru::EpiH2>("EpiH2", 256, 64, 64, 25);
-    time_real_epilogue<32, 5, 25, 2, hgru::EpiBias>("EpiBias", 256, 64, 64, 25);
-    time_real_epilogue<32, 5, 25, 2, hgru::EpiH1>("EpiH1", 256, 64, 64, 25);
-    time_real_epilogue<32, 5, 25, 2, hgru::EpiH2>("EpiH2", 256, 64, 64, 25);
+    time_real_epilogue<32, 5, 25, 1, hgru::EpiBias>("EpiBias", 256, 64, 64, 25, 0);
+    time_real_epilogue<32, 5, 25, 1, hgru::EpiH1>("EpiH1", 256, 64, 64, 25, 0);
+    time_real_epilogue<32, 5, 25, 1, hgru::EpiH1>("EpiH1", 256, 64, 64, 25, 1);
+    time_real_epilogue<32, 5, 25, 1, hgru::EpiH2>("EpiH2", 256, 64, 64, 25, 0);
+    time_real_epilogue<32, 5, 25, 1, hgru::EpiH2>("EpiH2", 256, 64, 64, 25, 1);
+    time_real_epilogue<32, 5, 25, 2, hgru::EpiH1>("EpiH1", 256, 64, 64, 25, 1);
+    time_real_epilogue<32, 5, 25, 2, hgru::EpiH2>("EpiH2", 256, 64, 64, 25, 1);
   }
   printf(f ? "FAILED %d\n" : "ALL OK\n", f);
   return f;
