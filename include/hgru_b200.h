@@ -123,6 +123,20 @@ HGRU_API int pose_plan_launch_count(pose_plan_t plan);
 HGRU_API int hgru_enable_kernel_timing(int on);
 HGRU_API int pose_plan_kernel_times(pose_plan_t plan, float* hconv_ms_total, int* hconv_launches);
 
+/* ------------------------------------------------------------------------------------------
+ * Crop stage (the step right before the pose network): replaces the per-frame host loop
+ * prepare_data_test -> tfMonkeyDetector.cropArea3D (train_cnn_networks_hgru.py:61-74,
+ * tf_monkeydetector.py:208-263, 292-365).  The window arithmetic (comToBounds, :193-206) stays on
+ * the host and arrives as per-frame integers; the gather / z clamp / nearest resize / paste /
+ * normalise runs on the device, bit-exact with the reference + OpenCV.
+ *   frames [N,H,W] (device), multiplied by frame_scale (image_max_depth) as the caller does;
+ *   iparams [N][8] = xstart, ystart, wb, hb, sz_w, sz_h, xs, ys;  zparams [N][2] = zstart, zend (fp32);
+ *   out [N,dh,dw] = value / out_divisor, `background` where the resized crop does not reach.
+ * ------------------------------------------------------------------------------------------ */
+HGRU_API int crop_area3d_forward(const float* frames_dev, int N, int H, int W, float frame_scale,
+                                 const int* iparams_dev, const float* zparams_dev, float background,
+                                 double out_divisor, float* out_dev, int dh, int dw, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,6 +51,8 @@ SIGNATURES = {
     "pose_plan_launch_count": (_I, [_P]),
     "hgru_enable_kernel_timing": (_I, [_I]),
     "pose_plan_kernel_times": (_I, [_P, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_I)]),
+    "crop_area3d_forward": (_I, [_P, _I, _I, _I, ctypes.c_float, _P, _P, ctypes.c_float, ctypes.c_double, _P,
+                                 _I, _I, _P]),
 }
 
 _lib = None

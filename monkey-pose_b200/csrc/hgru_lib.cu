@@ -10,6 +10,7 @@
 #include <string>
 #include <vector>
 
+#include "crop.cuh"
 #include "gate_tc.cuh"
 #include "gemm_tc.cuh"
 #include "hconv_stack.cuh"
@@ -875,6 +876,19 @@ int pose_plan_launch_count(pose_plan_t plan) { return plan ? plan->launches : 0;
 int pose_plan_kernel_times(pose_plan_t plan, float* hconv_ms_total, int* hconv_launches) {
   if (!plan || !hconv_ms_total || !hconv_launches) return fail(HGRU_E_INVALID, "pose_plan_kernel_times: null argument");
   *hconv_launches = plan->hg.timer.collect(hconv_ms_total);
+  return 0;
+}
+
+int crop_area3d_forward(const float* frames, int N, int H, int W, float frame_scale, const int* ip,
+                        const float* zp, float background, double out_divisor, float* out, int dh, int dw,
+                        void* stream) {
+  if (!frames || !ip || !zp || !out) return fail(HGRU_E_INVALID, "crop_area3d_forward: null pointer");
+  if (N < 1 || H < 1 || W < 1 || dh < 1 || dw < 1) return fail(HGRU_E_INVALID, "crop_area3d_forward: non-positive shape");
+  if (!(out_divisor > 0.0)) return fail(HGRU_E_INVALID, "crop_area3d_forward: out_divisor must be positive");
+  const size_t total = static_cast<size_t>(N) * dh * dw;
+  hgru::crop_area3d_kernel<<<nblk(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      frames, frame_scale, ip, zp, background, out_divisor, out, N, H, W, dh, dw);
+  CUDA_TRY(cudaGetLastError());
   return 0;
 }
 

@@ -1,0 +1,153 @@
+"""B200-native drop-in for the crop stage of the reference (`tf_monkeydetector.tfMonkeyDetector`,
+tf_monkeydetector.py:21-391, as used by `prepare_data_test`, train_cnn_networks_hgru.py:61-74).
+
+Same constructor and method names.  The camera / window arithmetic (a handful of scalars per frame)
+stays in numpy float64 exactly as the reference writes it; the per-pixel work -- slice, zero pad,
+z clamp, cv2 nearest-neighbour resize, paste, normalise -- runs in one CUDA kernel over the whole batch
+(`crop_area3d_forward`), bit-exact with the reference + OpenCV.  No CPU fallback.
+"""
+import numpy
+
+import torch
+
+from . import _lib
+from .hgru_module import _stream
+
+
+class tfMonkeyDetector(object):
+    RESIZE_BILINEAR = 0
+    RESIZE_CV2_NN = 1
+    RESIZE_CV2_LINEAR = 2
+
+    def __init__(self, fx, fy, ux, uy, cube, d1, d2, importer=None):
+        """tf_monkeydetector.py:30-64."""
+        self.maxDepth = d2
+        self.minDepth = d1
+        self.fx, self.fy, self.ux, self.uy = fx, fy, ux, uy
+        if len(cube) != 3:
+            raise ValueError("Volume must be 3D")
+        self.cube = cube
+        self.resizeMethod = self.RESIZE_CV2_NN
+
+    # ---- camera model (host, numpy; tf_monkeydetector.py:116-160, 193-206, 367-391) -------------------
+    def xyztouvd(self, jnts_xyz):
+        j = numpy.asarray(jnts_xyz)
+        single = j.ndim == 1
+        j = numpy.atleast_2d(j)
+        out = numpy.zeros((j.shape[0], 3), numpy.float32)
+        z = j[:, 2]
+        nz = z != 0.
+        out[~nz, 0], out[~nz, 1] = self.ux, self.uy
+        out[nz, 0] = self.ux - j[nz, 0] / z[nz] * self.fx
+        out[nz, 1] = j[nz, 1] / z[nz] * self.fy + self.uy
+        out[nz, 2] = -z[nz]
+        return out[0] if single else out
+
+    def uvdtoxyz(self, jnts_uvd):
+        j = numpy.asarray(jnts_uvd)
+        single = j.ndim == 1
+        j = numpy.atleast_2d(j)
+        out = numpy.zeros((j.shape[0], 3), numpy.float32)
+        out[:, 0] = (self.ux - j[:, 0]) * j[:, 2] / (-self.fx)
+        out[:, 1] = (j[:, 1] - self.uy) * j[:, 2] / (-self.fy)
+        out[:, 2] = -j[:, 2]
+        return out[0] if single else out
+
+    def comToBounds(self, com, size):
+        zstart = com[2] - size[2] / 2.
+        zend = com[2] + size[2] / 2.
+        xstart = int(numpy.floor((com[0] * com[2] / self.fx - size[0] / 2.) / com[2] * self.fx))
+        xend = int(numpy.floor((com[0] * com[2] / self.fx + size[0] / 2.) / com[2] * self.fx))
+        ystart = int(numpy.floor((com[1] * com[2] / self.fy - size[1] / 2.) / com[2] * self.fy))
+        yend = int(numpy.floor((com[1] * com[2] / self.fy + size[1] / 2.) / com[2] * self.fy))
+        return xstart, xend, ystart, yend, zstart, zend
+
+    def transformPoint2D(self, pt, M):
+        pt2 = numpy.asarray(M, numpy.float64).reshape(3, 3) @ numpy.array([pt[0], pt[1], 1.0])
+        return numpy.array([pt2[0] / pt2[2], pt2[1] / pt2[2]])
+
+    def getRelativeCoordinates(self, jnts_xyz, jnts_uvd, com_uvd, M):
+        com_xyz = self.uvdtoxyz(com_uvd)
+        rel_jnts_xyz = jnts_xyz - com_xyz
+        rel_jnts_uvd = numpy.zeros((jnts_uvd.shape[0], 3), numpy.float32)
+        for joint in range(jnts_uvd.shape[0]):
+            t = self.transformPoint2D(jnts_uvd[joint], M)
+            rel_jnts_uvd[joint, 0], rel_jnts_uvd[joint, 1] = t[0], t[1]
+            rel_jnts_uvd[joint, 2] = jnts_uvd[joint, 2]
+        return rel_jnts_xyz, rel_jnts_uvd
+
+    def getAbsoluteCoordinates(self, rel_jnts_xyz, com_uvd):
+        com_xyz = self.uvdtoxyz(com_uvd)
+        jnts_xyz = rel_jnts_xyz + com_xyz
+        return jnts_xyz, self.xyztouvd(jnts_xyz)
+
+    # ---- crop (device) ----------------------------------------------------------------------------------
+    def _window(self, com, H, W, dsize):
+        """Host-side integers of one frame's crop (tf_monkeydetector.py:309-362): window, resized size,
+        paste offset, the 3x3 transform.  Mirrors the reference line by line (Python-2 integer division)."""
+        xstart, xend, ystart, yend, zstart, zend = self.comToBounds(com, self.cube)
+        if xend <= 0 or yend <= 0 or xstart >= W or ystart >= H or xend <= xstart or yend <= ystart:
+            raise ValueError("crop window does not intersect the frame")
+        wb, hb = xend - xstart, yend - ystart
+        if wb > hb:
+            sz = (dsize[0], hb * dsize[0] // wb)
+        else:
+            sz = (wb * dsize[1] // hb, dsize[1])
+        trans = numpy.eye(3, dtype=float)
+        trans[0, 2], trans[1, 2] = -xstart, -ystart
+        if hb > wb:
+            scale = numpy.eye(3, dtype=float) * sz[1] / float(hb)
+        else:
+            scale = numpy.eye(3, dtype=float) * sz[0] / float(wb)
+        scale[2, 2] = 1
+        xs = int(numpy.floor(dsize[0] / 2. - sz[0] / 2.))
+        ys = int(numpy.floor(dsize[1] / 2. - sz[1] / 2.))
+        off = numpy.eye(3, dtype=float)
+        off[0, 2], off[1, 2] = xs, ys
+        return (xstart, ystart, wb, hb, sz[0], sz[1], xs, ys), (zstart, zend), off @ scale @ trans
+
+    def cropArea3D_batch(self, frames, coms, dsize=(128, 128), frame_scale=1.0, out_divisor=1.0):
+        """Batched cropArea3D: frames [N,H,W] torch CUDA float32 (times frame_scale = mm), coms [N,3]
+        (u, v, d mm).  Returns (patches [N,dsize[1],dsize[0]] CUDA = mm / out_divisor, Ms, coms)."""
+        if len(dsize) != 2:
+            raise ValueError("dsize must be a 2D bounding box")
+        if not (torch.is_tensor(frames) and frames.is_cuda and frames.dim() == 3):
+            raise RuntimeError("frames must be a [N,H,W] torch CUDA tensor (no CPU fallback)")
+        frames = frames.to(torch.float32).contiguous()
+        N, H, W = [int(v) for v in frames.shape]
+        ip = numpy.zeros((N, 8), numpy.int32)
+        zp = numpy.zeros((N, 2), numpy.float32)
+        Ms = []
+        for i in range(N):
+            ints, zz, M = self._window(numpy.asarray(coms[i], numpy.float64), H, W, dsize)
+            ip[i], zp[i] = ints, zz
+            Ms.append(M)
+        ip_d = torch.as_tensor(ip).cuda()
+        zp_d = torch.as_tensor(zp).cuda()
+        out = torch.empty((N, dsize[1], dsize[0]), device=frames.device, dtype=torch.float32)
+        _lib.check(_lib.load().crop_area3d_forward(
+            frames.data_ptr(), N, H, W, float(frame_scale), ip_d.data_ptr(), zp_d.data_ptr(), float(self.maxDepth),
+            float(out_divisor), out.data_ptr(), int(dsize[1]), int(dsize[0]), _stream()), "crop_area3d_forward")
+        return out, Ms, [numpy.asarray(c) for c in coms]
+
+    def cropArea3D(self, dpt, com=None, dsize=(128, 128), docom=False):
+        """tf_monkeydetector.py:292-365 for one frame [H,W] (mm): (patch, M, com)."""
+        if com is None or docom:
+            raise NotImplementedError("CoM estimation / refinement (calculateCoM) is not on the hot path: pass com")
+        out, Ms, coms = self.cropArea3D_batch(dpt[None], [com], dsize=dsize)
+        return out[0], Ms[0], coms[0]
+
+
+def prepare_data_test(image_np, tr_res, md, config):
+    """train_cnn_networks_hgru.py:61-74 on the device: frames in [0,1] ([N,H,W] or [N,H,W,1], torch CUDA)
+    and attention outputs tr_res [N,3] -> (patches [N,128,128,1] CUDA, coms, Ms)."""
+    if image_np.dim() == 4:
+        image_np = image_np[..., 0]
+    tr = numpy.asarray(tr_res, numpy.float64)
+    scale = numpy.array([config.image_orig_size[0], config.image_orig_size[1], config.image_max_depth], numpy.float64)
+    coms = [tr[i] * scale for i in range(tr.shape[0])]
+    ts = config.image_target_size
+    patches, Ms, coms = md.cropArea3D_batch(image_np, coms, dsize=(ts[1], ts[0]),
+                                            frame_scale=config.image_max_depth,
+                                            out_divisor=config.image_max_depth)
+    return patches[..., None], coms, Ms

@@ -167,3 +167,49 @@ def test_properties_at_baseline_size_bf16():
     assert onp.rel_err(part, exact)[0] < 1e-2
     assert onp.mean_joint_error_mm(part, exact) < 0.5
     assert np.isfinite(full).all() and np.abs(full).max() > 0
+
+
+# ---- crop stage ------------------------------------------------------------------
+class _Cfg(object):
+    image_orig_size = [424, 512, 1]
+    image_target_size = [128, 128, 1]
+    image_max_depth = 10000.
+
+
+def test_crop_stage_bit_exact_against_reference_golden():
+    from monkey_pose_b200 import tf_monkeydetector as tmd
+    z = np.load(os.path.join(GOLDEN, "crop_ref.npz"))
+    md = tmd.tfMonkeyDetector(365.456, 365.456, 256, 212, [800, 800, 1200], 200, 10000)
+    patches, coms, Ms = tmd.prepare_data_test(torch.as_tensor(z["frames"]).cuda(), z["coms_norm"], md, _Cfg())
+    torch.cuda.synchronize()
+    assert patches.shape == (5, 128, 128, 1)
+    assert np.array_equal(patches.cpu().numpy(), z["patches"])           # bit-exact (index + byte work)
+    for i in range(5):
+        np.testing.assert_allclose(np.asarray(Ms[i]), z["M"][i], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(coms[i], z["coms_out"][i], rtol=0, atol=0)
+    with pytest.raises(NotImplementedError):
+        md.cropArea3D(torch.zeros(424, 512, device="cuda"), com=None)
+    with pytest.raises(ValueError):
+        md.cropArea3D_batch(torch.zeros(1, 424, 512, device="cuda"), [np.array([-900.0, 100.0, 1500.0])])
+
+
+def test_crop_stage_vs_oracle_at_batch_size_and_feeds_the_model():
+    """256 random frames: the kernel equals the oracle bit for bit, and its output drives model.build."""
+    from monkey_pose_b200 import tf_monkeydetector as tmd
+    from oracle import crop_oracle_np as crop
+    rng = np.random.default_rng(5)
+    n, h, w = 256, 424, 512
+    base = np.round(rng.uniform(600, 4000, size=(8, h, w)) / 8) * 8
+    base[rng.uniform(size=base.shape) < 0.05] = 0
+    frames = (base[rng.integers(0, 8, n)] / 10000.0).astype(np.float32)
+    # attention outputs: the caller rescales by (height, width, max depth), component 0 is read as x
+    coms_norm = np.stack([rng.uniform(0.1, 1.1, n), rng.uniform(0.1, 0.75, n), rng.uniform(0.08, 0.35, n)], 1)
+    md = tmd.tfMonkeyDetector(365.456, 365.456, 256, 212, [800, 800, 1200], 200, 10000)
+    patches, coms, Ms = tmd.prepare_data_test(torch.as_tensor(frames).cuda(), coms_norm, md, _Cfg())
+    ref, _, refM = crop.prepare_data_test(frames, coms_norm, (365.456, 365.456, 256, 212), [800, 800, 1200])
+    assert np.array_equal(patches.cpu().numpy(), ref.astype(np.float32))
+    np.testing.assert_allclose(np.asarray(Ms[17]), refM[17], rtol=0, atol=1e-12)
+    m = mp.model()
+    m.channels, m.timesteps, m.fc_hidden = 16, 1, 32
+    out = m.build(patches[:4].contiguous(), 69)
+    assert out.shape == (4, 69) and torch.isfinite(out).all()
