@@ -93,6 +93,29 @@ __device__ __forceinline__ size_t quad_off(const TcConvArgs& a, int n, int quad,
   return ((static_cast<size_t>(n) * (a.KP >> 2) + quad) * (static_cast<size_t>(a.H) * a.W) + pin) * 4;
 }
 
+// streaming accesses of the epilogues: every state byte is touched once per launch, so keep it out of
+// L1 (whose SRAM and datapath the UMMA operand fetch needs)
+__device__ __forceinline__ float4 ld_stream(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float4 ld_stream_rw(const float* p) {   // data also written by this kernel (H2)
+  float4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ void st_stream(float* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};"
+               ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_stream(void* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1, %2, %3, %4};"
+               ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 __device__ __forceinline__ float fast_sigmoid(float x) { return 1.f / (1.f + __expf(-x)); }
 // tanh via one exp: (1 - e^-2x) / (1 + e^-2x); |err| ~ 1e-7 abs, far inside the bf16-path budget
 __device__ __forceinline__ float fast_tanh(float x) {
@@ -106,7 +129,7 @@ __device__ __forceinline__ void store_chunk_bf16(__nv_bfloat16* base, int KP, in
 #pragma unroll
   for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(r[2 * j], r[2 * j + 1]);
   __nv_bfloat16* o = base + ((static_cast<size_t>(n) * (KP >> 3) + cg) * HWp + pin) * 8;
-  *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(h);
+  st_stream(o, *reinterpret_cast<const uint4*>(h));
 }
 
 // ---- epilogue functors: consume one pixel's CO_PAD accumulators --------------------------------
@@ -173,8 +196,8 @@ struct EpiH1 {
 #pragma unroll
     for (int i = 0; i < NCH / 4; ++i) {
       const size_t o = quad_off(a, n, (c0 >> 2) + i, pin);
-      p.x[i] = *reinterpret_cast<const float4*>(a.X + o);
-      p.h[i] = *reinterpret_cast<const float4*>(a.H2 + o);
+      p.x[i] = ld_stream(a.X + o);
+      p.h[i] = ld_stream(a.H2 + o);
     }
   }
   // mix gate on the tensor-core result of H1 *1x1 o_r (hgru_module.py:729-740): G2 = sigmoid(. + o_b)
@@ -190,7 +213,7 @@ struct EpiH1 {
       if (c0 + c + 1 >= a.kreal) g.y = 0.f;
       if (c0 + c + 2 >= a.kreal) g.z = 0.f;
       if (c0 + c + 3 >= a.kreal) g.w = 0.f;
-      *reinterpret_cast<float4*>(a.gate_out + quad_off(a, n, (c0 + c) >> 2, pin)) = g;
+      st_stream(a.gate_out + quad_off(a, n, (c0 + c) >> 2, pin), g);
     }
   }
   template <int NCH>
@@ -214,8 +237,8 @@ struct EpiH1 {
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         if (c0 + c + j >= a.kreal) r[j] = 0.f;
-      *reinterpret_cast<float4*>(a.out + quad_off(a, n, (c0 + c) >> 2, pin)) = make_float4(r[0], r[1], r[2], r[3]);
-      *reinterpret_cast<float4*>(a.out + quad_off(a, n, ((c0 + c) >> 2) + 1, pin)) = make_float4(r[4], r[5], r[6], r[7]);
+      st_stream(a.out + quad_off(a, n, (c0 + c) >> 2, pin), make_float4(r[0], r[1], r[2], r[3]));
+      st_stream(a.out + quad_off(a, n, ((c0 + c) >> 2) + 1, pin), make_float4(r[4], r[5], r[6], r[7]));
       store_chunk_bf16(a.out_bf16, a.KP, a.H * a.W, n, (c0 + c) >> 3, pin, r);
       if (hout) {
 #pragma unroll
@@ -249,9 +272,9 @@ struct EpiH2 {
 #pragma unroll
     for (int i = 0; i < NCH / 4; ++i) {
       const size_t o = quad_off(a, n, (c0 >> 2) + i, pin);
-      p.h1[i] = *reinterpret_cast<const float4*>(a.H1 + o);
-      p.g[i] = *reinterpret_cast<const float4*>(a.G + o);
-      p.h2[i] = *reinterpret_cast<const float4*>(a.H2 + o);
+      p.h1[i] = ld_stream(a.H1 + o);
+      p.g[i] = ld_stream(a.G + o);
+      p.h2[i] = ld_stream_rw(a.H2 + o);
     }
   }
   // input gate of the NEXT timestep on the tensor-core result of H2 *1x1 i_r (hgru_module.py:696-711):
@@ -297,8 +320,8 @@ struct EpiH2 {
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         if (c0 + c + j >= a.kreal) r[j] = 0.f;
-      *reinterpret_cast<float4*>(a.H2 + quad_off(a, n, (c0 + c) >> 2, pin)) = make_float4(r[0], r[1], r[2], r[3]);
-      *reinterpret_cast<float4*>(a.H2 + quad_off(a, n, ((c0 + c) >> 2) + 1, pin)) = make_float4(r[4], r[5], r[6], r[7]);
+      st_stream(a.H2 + quad_off(a, n, (c0 + c) >> 2, pin), make_float4(r[0], r[1], r[2], r[3]));
+      st_stream(a.H2 + quad_off(a, n, ((c0 + c) >> 2) + 1, pin), make_float4(r[4], r[5], r[6], r[7]));
       if (a.out_bf16) store_chunk_bf16(a.out_bf16, a.KP, a.H * a.W, n, (c0 + c) >> 3, pin, r);
       if (hout) {
 #pragma unroll
