@@ -137,6 +137,21 @@ HGRU_API int crop_area3d_forward(const float* frames_dev, int N, int H, int W, f
                                  const int* iparams_dev, const float* zparams_dev, float background,
                                  double out_divisor, float* out_dev, int dh, int dw, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Post-processing (the step right after the pose network).
+ * pose_postprocess_forward: out_put [N,3J] (normalised) -> xyz [N,J,3] = out*scale + uvdtoxyz(com),
+ *   uvd [N,J,3] = xyztouvd(xyz): train_cnn_networks_hgru.py:293-296 + tfMonkeyDetector
+ *   .getAbsoluteCoordinates (tf_monkeydetector.py:387-391).  com_uvd [N,3] float64 (u, v, d mm).
+ * joint_error_forward: labels / results [N,J,3] (mm) -> result[0] = getMeanError_np,
+ *   result[1] = getMaxError_np (pose_evaluation.py:10-23); workspace: N doubles + N floats.
+ * ------------------------------------------------------------------------------------------ */
+HGRU_API int pose_postprocess_forward(const float* out_put_dev, const double* com_uvd_dev, int N, int J,
+                                      double fx, double fy, double ux, double uy, float scale,
+                                      float* xyz_dev, float* uvd_dev, void* stream);
+HGRU_API int joint_error_forward(const float* labels_dev, const float* results_dev, int N, int J,
+                                 double* frame_mean_ws_dev, float* frame_max_ws_dev, double* result_dev,
+                                 void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -3,10 +3,11 @@ from . import _lib  # noqa: F401
 from . import hgru_module  # noqa: F401
 from . import hgru_pose  # noqa: F401
 from . import initialization  # noqa: F401
+from . import pose_evaluation  # noqa: F401
 from . import sharding  # noqa: F401
 from . import tf_monkeydetector  # noqa: F401
 from .hgru_module import ContextualCircuit, auxilliary_variables  # noqa: F401
 from .hgru_pose import model  # noqa: F401
 
 __all__ = ["ContextualCircuit", "auxilliary_variables", "model", "initialization", "hgru_module",
-           "hgru_pose", "sharding", "tf_monkeydetector", "_lib"]
+           "hgru_pose", "pose_evaluation", "sharding", "tf_monkeydetector", "_lib"]

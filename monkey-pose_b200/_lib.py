@@ -53,6 +53,9 @@ SIGNATURES = {
     "pose_plan_kernel_times": (_I, [_P, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_I)]),
     "crop_area3d_forward": (_I, [_P, _I, _I, _I, ctypes.c_float, _P, _P, ctypes.c_float, ctypes.c_double, _P,
                                  _I, _I, _P]),
+    "pose_postprocess_forward": (_I, [_P, _P, _I, _I, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                      ctypes.c_double, ctypes.c_float, _P, _P, _P]),
+    "joint_error_forward": (_I, [_P, _P, _I, _I, _P, _P, _P, _P]),
 }
 
 _lib = None

@@ -17,14 +17,20 @@
 
 namespace hgru {
 
-constexpr int kGemmBM = 128, kGemmBN = 256, kGemmBK = 64, kGemmStages = 4;
+// Precision: both operands are stored as bf16 hi + lo halves (hi = bf16(x), lo = bf16(x - hi)), the hi parts in
+// columns [0, Kpad) and the lo parts in [Kpad, 2*Kpad) of A and B.  Each k-block is accumulated as three
+// products  A_hi*B_hi + A_lo*B_hi + A_hi*B_lo  (fp32-class accuracy: K = 262 144 bf16 products would
+// otherwise contribute ~2.5e-3 relative error, the largest single error of the bf16 path).  A stage holds
+// the four tiles so B_hi is fetched once for two products; 2 stages x 96 KB.
+constexpr int kGemmBM = 128, kGemmBN = 256, kGemmBK = 64, kGemmStages = 2;
 constexpr int kGemmABytes = kGemmBM * kGemmBK * 2;    // 16 KB
 constexpr int kGemmBBytes = kGemmBN * kGemmBK * 2;    // 32 KB
-constexpr int kGemmStageBytes = kGemmABytes + kGemmBBytes;
+constexpr int kGemmStageBytes = 2 * kGemmABytes + 2 * kGemmBBytes;   // A_hi, A_lo, B_hi, B_lo
 constexpr int kGemmSmemBytes = kGemmStages * kGemmStageBytes + 256 + 1024;
 
 struct GemmArgs {
   int M, Nn, K;          // problem size
+  int Kpad;              // column where the lo halves start (K rounded up to the k-block)
   int kblocks_per_split; // K blocks (of 64) handled by one z slice
   float* part;           // [splits][M][Nn] fp32
 };
@@ -83,16 +89,21 @@ gemm_tc_splitk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         mbar_wait(bar_empty + 8 * st, ph ^ 1);
         mbar_arrive_expect_tx(bar_full + 8 * st, kGemmStageBytes);
         const uint32_t sa = base + st * kGemmStageBytes;
-        tma_load_2d(sa, &map_a, bar_full + 8 * st, (kb0 + kb) * kGemmBK, m0);
-        tma_load_2d(sa + kGemmABytes, &map_b, bar_full + 8 * st, (kb0 + kb) * kGemmBK, n0);
+        const int kc = (kb0 + kb) * kGemmBK;
+        tma_load_2d(sa, &map_a, bar_full + 8 * st, kc, m0);                                     // A_hi
+        tma_load_2d(sa + kGemmABytes, &map_a, bar_full + 8 * st, g.Kpad + kc, m0);              // A_lo
+        tma_load_2d(sa + 2 * kGemmABytes, &map_b, bar_full + 8 * st, kc, n0);                   // B_hi
+        tma_load_2d(sa + 2 * kGemmABytes + kGemmBBytes, &map_b, bar_full + 8 * st, g.Kpad + kc, n0);   // B_lo
         if (++st == kGemmStages) { st = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
     const bool leader = elect_one();
     constexpr uint32_t idesc = make_idesc(1, kGemmBM, kGemmBN);
-    const uint64_t a0 = make_smem_desc_sw128(base);
-    const uint64_t b0 = make_smem_desc_sw128(base + kGemmABytes);
+    const uint64_t a_hi = make_smem_desc_sw128(base);
+    const uint64_t a_lo = make_smem_desc_sw128(base + kGemmABytes);
+    const uint64_t b_hi = make_smem_desc_sw128(base + 2 * kGemmABytes);
+    const uint64_t b_lo = make_smem_desc_sw128(base + 2 * kGemmABytes + kGemmBBytes);
     uint32_t st = 0, ph = 0;
     for (int kb = 0; kb < nkb; ++kb) {
       mbar_wait(bar_full + 8 * st, ph);
@@ -101,7 +112,11 @@ gemm_tc_splitk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 #pragma unroll
       for (int ks = 0; ks < kGemmBK / 16; ++ks) {
         // advance 16 K-elements = 32 bytes inside the 128-byte swizzle row
-        if (leader) mma_bf16_ss(tmem_base, a0 + so + ks * 2, b0 + so + ks * 2, idesc, (kb | ks) != 0);
+        if (leader) {
+          mma_bf16_ss(tmem_base, a_hi + so + ks * 2, b_hi + so + ks * 2, idesc, (kb | ks) != 0);
+          mma_bf16_ss(tmem_base, a_lo + so + ks * 2, b_hi + so + ks * 2, idesc, 1);
+          mma_bf16_ss(tmem_base, a_hi + so + ks * 2, b_lo + so + ks * 2, idesc, 1);
+        }
       }
       if (leader) tc_commit(bar_empty + 8 * st);
       if (++st == kGemmStages) { st = 0; ph ^= 1; }
@@ -152,20 +167,29 @@ gemm_tc_splitk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 // A operand of fc_1: bf16 [M][HW*k] = (H2[m][pix][c] * scale[c] + shift[c]) over real channels
 // (the inference batch-norm of the hGRU output, hgru_pose.py:82-90, applied while flattening);
 // H2 is read from the quad-chunked state layout [n][c/4][pix][4].
+// Output row m: [hi(0..K) | pad | lo(0..K) | pad], row pitch 2*Kpad (pad columns are zero-initialised once).
 __global__ void __launch_bounds__(256)
 fc1_pack_a_kernel(const float* __restrict__ h2, const float* __restrict__ sc, const float* __restrict__ sh,
-                  __nv_bfloat16* __restrict__ a, size_t npix, int k, int KP, int HW) {
+                  __nv_bfloat16* __restrict__ a, size_t npix, int k, int KP, int HW, int Kpad) {
   const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   if (i >= npix * k) return;
   const int c = i % k;
   const size_t p = i / k;
   const size_t n = p / HW, pin = p - n * HW;
-  a[i] = __float2bfloat16(h2[((n * (KP >> 2) + (c >> 2)) * HW + pin) * 4 + (c & 3)] * sc[c] + sh[c]);
+  const float v = h2[((n * (KP >> 2) + (c >> 2)) * HW + pin) * 4 + (c & 3)] * sc[c] + sh[c];
+  const __nv_bfloat16 hi = __float2bfloat16(v);
+  const size_t col = static_cast<size_t>(c) * HW + pin;     // channel-major K order (see transpose_to_bf16_kernel)
+  __nv_bfloat16* row = a + n * (2 * static_cast<size_t>(Kpad));
+  row[col] = hi;
+  row[Kpad + col] = __float2bfloat16(v - __bfloat162float(hi));
 }
 
-// fc_1 weights [K][F] fp32 -> bf16 [F][K] (K-major B operand); 32x32 tiles through shared memory.
+// fc_1 weights [K][F] fp32 -> bf16 [F][hi(0..K) | pad | lo(0..K) | pad] (K-major B operand, row pitch
+// 2*Kpad); 32x32 tiles through shared memory.  The reference's K index (pin*k + c, tf.reshape of NHWC) is
+// permuted to channel-major (c*HW + pin), the order in which the H2 epilogue emits the A operand.
 __global__ void __launch_bounds__(256)
-transpose_to_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wt, int K, int F) {
+transpose_to_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wt, int K, int F, int Kpad,
+                         int kch) {
   __shared__ float tile[32][33];
   const int k0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
@@ -176,7 +200,15 @@ transpose_to_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict_
   __syncthreads();
   for (int r = ty; r < 32; r += 8) {
     const int f = f0 + r, kk = k0 + tx;
-    if (f < F && kk < K) wt[static_cast<size_t>(f) * K + kk] = __float2bfloat16(tile[tx][r]);
+    if (f < F && kk < K) {
+      const float v = tile[tx][r];
+      const int pin_ = kk / kch, c_ = kk - pin_ * kch;
+      const int kd = c_ * (K / kch) + pin_;
+      const __nv_bfloat16 hi = __float2bfloat16(v);
+      __nv_bfloat16* row = wt + static_cast<size_t>(f) * (2 * static_cast<size_t>(Kpad));
+      row[kd] = hi;
+      row[Kpad + kd] = __float2bfloat16(v - __bfloat162float(hi));
+    }
   }
 }
 

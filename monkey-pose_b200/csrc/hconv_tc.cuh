@@ -33,8 +33,14 @@ namespace hgru {
 
 constexpr int kTileRows = 16;   // M tile = 16 rows x 8 cols of pixels
 
-template <int S, int KSTEPS, int CO_PAD, int TILES_X, int G, int WSTAGES>
+// SPLIT3: operands carry bf16 hi and lo halves (window parts [0,KSTEPS) = hi, [KSTEPS,2*KSTEPS) = lo) and
+// every 16-channel k-step is accumulated as three products  a_hi*w_hi + a_hi*w_lo + a_lo*w_hi
+// (fp32-class accuracy from bf16 tensor cores; used for the stem, whose smooth inputs make plain bf16
+// rounding errors add up coherently).
+template <int S, int KSTEPS, int CO_PAD, int TILES_X, int G, int WSTAGES, bool SPLIT3 = false>
 struct TcConvCfg {
+  static constexpr int kParts = SPLIT3 ? 2 * KSTEPS : KSTEPS;      // window parts (TMA boxes / barriers)
+  static constexpr int kWSteps = SPLIT3 ? 3 * KSTEPS : KSTEPS;     // weight k-steps
   static constexpr int kS = S;
   static constexpr int kTaps = S * S;
   static constexpr int kPad = (S - 1) / 2;
@@ -43,12 +49,12 @@ struct TcConvCfg {
   static constexpr int kRowPitch = kCols * 16;              // bytes (SBO of A)
   static constexpr int kChunkPitch = kRows * kRowPitch;     // bytes (LBO of A)
   static constexpr int kPartBytes = 2 * kChunkPitch;        // one kstep = 2 chunks
-  static constexpr int kInBytes = KSTEPS * kPartBytes;
+  static constexpr int kInBytes = kParts * kPartBytes;
   static constexpr int kTapBytes = 2 * CO_PAD * 16;         // one (kstep, tap) weight block
   static constexpr int kStageBytes = G * kTapBytes;
   static constexpr int kStagesPerKstep = kTaps / G;
   static constexpr int kAccCols = TILES_X * CO_PAD;         // TMEM columns per accumulator set
-  static constexpr int kNumBars = 2 * KSTEPS + 2 * WSTAGES + 4;
+  static constexpr int kNumBars = 2 * kParts + 2 * WSTAGES + 4;
   static constexpr int kSmemBytes = kInBytes + WSTAGES * kStageBytes + kNumBars * 8 + 16 + 1024;
   static_assert(kTaps % G == 0, "taps per stage must divide S*S");
   static_assert(2 * kAccCols <= 512, "two accumulator sets must fit TMEM");
@@ -83,6 +89,12 @@ struct TcConvArgs {
   float* gate_out;                 // EpiH1: G2 fp32 quad-chunked
   __nv_bfloat16* gate_act_out;     // EpiH2: next step's gated operand bf16(G1 . H2), chunked
   int do_gate;                     // 0: skip (last timestep's H2, or the unfused pipeline)
+  // readout operand fused behind the last H2 update: bf16 hi + lo halves of batch_norm(H2) in the fc_1
+  // GEMM's A layout, row n = [hi: c*HW + pin | ... | lo at +fc_kpad], row pitch 2*fc_kpad (nullptr: skip)
+  __nv_bfloat16* fc_a;
+  const float* fc_scale;           // [KP] folded inference batch-norm of the hGRU output (hgru_pose.py:82-90)
+  const float* fc_shift;
+  int fc_kpad;
   long long* prof;          // optional per-CTA cycle counters (development; nullptr in production)
 };
 
@@ -173,7 +185,17 @@ struct EpiBiasReluAffine {
         r[j] = fmaxf(acc[c + j] + __ldg(a.bias + c + j), 0.f) * __ldg(a.scale + c + j) + __ldg(a.shift + c + j);
       *reinterpret_cast<float4*>(a.out + quad_off(a, n, c >> 2, pin)) = make_float4(r[0], r[1], r[2], r[3]);
       *reinterpret_cast<float4*>(a.out + quad_off(a, n, (c >> 2) + 1, pin)) = make_float4(r[4], r[5], r[6], r[7]);
-      if (a.out_bf16) store_chunk_bf16(a.out_bf16, a.KP, a.H * a.W, n, c >> 3, pin, r);
+      if (a.out_bf16) {
+        // hi + lo bf16 split of the operand copy (see stem_conv1_pool_bn_kernel): planes [0,CG), [CG,2CG)
+        float hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          hi[j] = __bfloat162float(__float2bfloat16(r[j]));
+          lo[j] = r[j] - hi[j];
+        }
+        store_chunk_bf16(a.out_bf16, 2 * a.KP, a.H * a.W, n, c >> 3, pin, hi);
+        store_chunk_bf16(a.out_bf16, 2 * a.KP, a.H * a.W, n, (a.KP >> 3) + (c >> 3), pin, lo);
+      }
     }
   }
 };
@@ -323,6 +345,21 @@ struct EpiH2 {
       st_stream(a.H2 + quad_off(a, n, (c0 + c) >> 2, pin), make_float4(r[0], r[1], r[2], r[3]));
       st_stream(a.H2 + quad_off(a, n, ((c0 + c) >> 2) + 1, pin), make_float4(r[4], r[5], r[6], r[7]));
       if (a.out_bf16) store_chunk_bf16(a.out_bf16, a.KP, a.H * a.W, n, (c0 + c) >> 3, pin, r);
+      if (a.fc_a) {
+        // last timestep: emit the fc_1 operand (channel-major K order c*HW + pin, bf16 hi/lo split)
+        const size_t HWp = static_cast<size_t>(a.H) * a.W;
+        __nv_bfloat16* row = a.fc_a + static_cast<size_t>(n) * (2 * static_cast<size_t>(a.fc_kpad));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int ch = c0 + c + j;
+          if (ch < a.kreal) {
+            const float v = r[j] * __ldg(a.fc_scale + ch) + __ldg(a.fc_shift + ch);
+            const __nv_bfloat16 hi = __float2bfloat16(v);
+            row[ch * HWp + pin] = hi;
+            row[a.fc_kpad + ch * HWp + pin] = __float2bfloat16(v - __bfloat162float(hi));
+          }
+        }
+      }
       if (hout) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) hout[c + j] = r[j];
@@ -388,20 +425,21 @@ struct EpiGateIn {
   }
 };
 
-template <int S, int KSTEPS, int CO_PAD, int TILES_X, int G, int WSTAGES, class Epi>
+template <int S, int KSTEPS, int CO_PAD, int TILES_X, int G, int WSTAGES, class Epi, bool SPLIT3 = false>
 __global__ void __launch_bounds__(256, 1)
 hconv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const TcConvArgs a) {
   using namespace sm100;
-  using Cfg = TcConvCfg<S, KSTEPS, CO_PAD, TILES_X, G, WSTAGES>;
+  using Cfg = TcConvCfg<S, KSTEPS, CO_PAD, TILES_X, G, WSTAGES, SPLIT3>;
+  constexpr int NP = Cfg::kParts, NW = Cfg::kWSteps;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte aligned carve-up
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t in_buf = base;
   const uint32_t w_buf = in_buf + Cfg::kInBytes;
   const uint32_t bars = w_buf + WSTAGES * Cfg::kStageBytes;
-  const uint32_t bar_in_full = bars;                               // [KSTEPS]
-  const uint32_t bar_in_empty = bar_in_full + 8 * KSTEPS;          // [KSTEPS]
-  const uint32_t bar_w_full = bar_in_empty + 8 * KSTEPS;           // [WSTAGES]
+  const uint32_t bar_in_full = bars;                               // [NP]
+  const uint32_t bar_in_empty = bar_in_full + 8 * NP;              // [NP]
+  const uint32_t bar_w_full = bar_in_empty + 8 * NP;               // [WSTAGES]
   const uint32_t bar_w_empty = bar_w_full + 8 * WSTAGES;           // [WSTAGES]
   const uint32_t bar_acc_full = bar_w_empty + 8 * WSTAGES;         // [2]
   const uint32_t bar_acc_empty = bar_acc_full + 16;                // [2]
@@ -413,7 +451,7 @@ hconv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const TcConvArgs a) 
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < KSTEPS; ++i) {
+    for (int i = 0; i < NP; ++i) {
       mbar_init(bar_in_full + 8 * i, 1);
       mbar_init(bar_in_empty + 8 * i, 1);
     }
@@ -443,7 +481,7 @@ hconv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const TcConvArgs a) 
     if (lane == 0) {
       uint32_t st = 0, ph = 0;
       for (int u = first; u < a.num_units; u += stride) {
-        for (int q = 0; q < KSTEPS; ++q) {
+        for (int q = 0; q < NW; ++q) {
           const uint8_t* src = reinterpret_cast<const uint8_t*>(a.wpk) +
                                static_cast<size_t>(q) * Cfg::kTaps * Cfg::kTapBytes;
           for (int sg = 0; sg < Cfg::kStagesPerKstep; ++sg) {
@@ -466,7 +504,7 @@ hconv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const TcConvArgs a) 
         const int uy = r / a.units_x, ux = r - uy * a.units_x;
         const int y0 = uy * kTileRows - Cfg::kPad;
         const int x0 = ux * (8 * TILES_X) - Cfg::kPad;
-        for (int q = 0; q < KSTEPS; ++q) {
+        for (int q = 0; q < NP; ++q) {
           mbar_wait(bar_in_empty + 8 * q, (it & 1) ^ 1);
           mbar_arrive_expect_tx(bar_in_full + 8 * q, Cfg::kPartBytes);
           // tensor viewed as 8-byte elements: dim0 = 2*x, dim1 = y, dim2 = chunk, dim3 = frame
@@ -492,8 +530,12 @@ hconv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const TcConvArgs a) 
       const uint32_t acc = tmem_base + s * Cfg::kAccCols;
       mbar_wait(bar_acc_empty + 8 * s, ((it >> 1) & 1) ^ 1);
       tc_fence_after();
-      for (int q = 0; q < KSTEPS; ++q) {
-        mbar_wait(bar_in_full + 8 * q, it & 1);
+      for (int wq = 0; wq < NW; ++wq) {
+        // window part used by weight k-step wq; SPLIT3 order per 16-channel group: (hi,w_hi) (hi,w_lo) (lo,w_hi)
+        const int q = SPLIT3 ? ((wq % 3) < 2 ? wq / 3 : KSTEPS + wq / 3) : wq;
+        const bool first_use = !SPLIT3 || (wq % 3) != 1;
+        const bool last_use = !SPLIT3 || (wq % 3) != 0;
+        if (first_use) mbar_wait(bar_in_full + 8 * q, it & 1);
         const uint64_t adesc_q = adesc0 + static_cast<uint64_t>((q * Cfg::kPartBytes) >> 4);
         uint32_t tap_off = 0;            // (dy * kRowPitch + dx * 16) >> 4, advanced incrementally
         uint32_t dx = 0;
@@ -505,7 +547,7 @@ hconv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const TcConvArgs a) 
           for (int g = 0; g < G; ++g) {
             const uint64_t bdesc = bdesc_st + static_cast<uint64_t>((g * Cfg::kTapBytes) >> 4);
             const uint64_t adesc_tap = adesc_q + tap_off;
-            const uint32_t accum = (q | sg | g) != 0;
+            const uint32_t accum = (wq | sg | g) != 0;
 #pragma unroll
             for (int t = 0; t < TILES_X; ++t) {
               if (leader) mma_bf16_ss(acc + t * CO_PAD, adesc_tap + static_cast<uint64_t>(t * 8), bdesc, idesc, accum);
@@ -517,7 +559,7 @@ hconv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const TcConvArgs a) 
           if (leader) tc_commit(bar_w_empty + 8 * st);
           if (++st == WSTAGES) { st = 0; ph ^= 1; }
         }
-        if (leader) tc_commit(bar_in_empty + 8 * q);
+        if (leader && last_use) tc_commit(bar_in_empty + 8 * q);
       }
       if (leader) tc_commit(bar_acc_full + 8 * s);
     }

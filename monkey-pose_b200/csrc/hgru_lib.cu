@@ -14,6 +14,7 @@
 #include "gate_tc.cuh"
 #include "gemm_tc.cuh"
 #include "hconv_stack.cuh"
+#include "post.cuh"
 #include "hconv_tc.cuh"
 #include "simt_kernels.cuh"
 #include "tc_host.cuh"
@@ -55,10 +56,10 @@ struct DevBuf {
 };
 
 // ---------------------------------------------------------------- tensor-core conv dispatch
-template <int S, int KSTEPS, int CO_PAD, int TILES_X, int G, class Epi>
+template <int S, int KSTEPS, int CO_PAD, int TILES_X, int G, class Epi, bool SPLIT3 = false>
 int launch_tc(const CUtensorMap& map, hgru::TcConvArgs a, cudaStream_t st) {
-  using Cfg = hgru::TcConvCfg<S, KSTEPS, CO_PAD, TILES_X, G, 4>;
-  auto kern = hgru::hconv_tc_kernel<S, KSTEPS, CO_PAD, TILES_X, G, 4, Epi>;
+  using Cfg = hgru::TcConvCfg<S, KSTEPS, CO_PAD, TILES_X, G, 4, SPLIT3>;
+  auto kern = hgru::hconv_tc_kernel<S, KSTEPS, CO_PAD, TILES_X, G, 4, Epi, SPLIT3>;
   static bool attr_done = false;
   if (!attr_done) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -108,10 +109,11 @@ int dispatch_tc_hconv(int S, int KP, const CUtensorMap& map, const hgru::TcConvA
   TC_CASES_S(Epi, 1, 1, 1)
   return fail(HGRU_E_UNSUPPORTED, "tensor-core conv: unsupported (S, padded channels)");
 }
-// 3x3 stem convs
+// 3x3 stem convs: bf16 hi + lo operand halves, three products per k-step (SPLIT3): fp32-class accuracy
 int dispatch_tc_stem(int KP, const CUtensorMap& map, const hgru::TcConvArgs& a, cudaStream_t st) {
-  const int S = 3;
-  TC_CASES_S(hgru::EpiBiasReluAffine, 3, 9, 9)
+  if (KP == 64) return launch_tc<3, 4, 64, 4, 3, hgru::EpiBiasReluAffine, true>(map, a, st);
+  if (KP == 32) return launch_tc<3, 2, 32, 8, 9, hgru::EpiBiasReluAffine, true>(map, a, st);
+  if (KP == 16) return launch_tc<3, 1, 16, 8, 9, hgru::EpiBiasReluAffine, true>(map, a, st);
   return fail(HGRU_E_UNSUPPORTED, "tensor-core stem conv: unsupported padded channel count");
 }
 #undef TC_CASES_S
@@ -283,6 +285,11 @@ struct hgru_plan_s {
   DevBuf actA, actH1, actH2;
   CUtensorMap mapA, mapH1;          // SxS halo-window boxes (horizontal convs)
   CUtensorMap mapH1_g, mapH2_g;     // 1x1 boxes (gate convs)
+  // readout operand emitted by the last H2 epilogue (set by the pose plan; nullptr for the bare layer)
+  __nv_bfloat16* fc_a = nullptr;
+  const float* fc_scale = nullptr;
+  const float* fc_shift = nullptr;
+  int fc_kpad = 0;
   bool stacked = false;             // narrow layers: tap-stacked kernel (hconv_stack.cuh)
   int stack_T = 0;
   KernelTimer timer;
@@ -444,19 +451,29 @@ static int hgru_run_fp32(hgru_plan_s* p, const float* Xp, float* H1_trace, float
 // Narrow layers (stacked kernel): two tcgen05 launches per timestep, the 1x1 gate convs run as
 // epilogue-issued MMAs inside them.  Wide layers (k = 64): four launches (gate-in, C1+H1, gate-out,
 // C2+H2).  All integration math happens on TMEM accumulators.
-static int hgru_run_bf16(hgru_plan_s* p, const float* Xp, float* H1_trace, float* H2_trace, cudaStream_t st) {
+static int hgru_run_bf16(hgru_plan_s* p, const float* Xp, const float* H2_init_nhwc, float* H1_trace,
+                         float* H2_trace, cudaStream_t st) {
   const int KP = p->KP, HW = p->H * p->W;
   int rc;
   hgru::TcConvArgs base{};
   base.N = p->N; base.H = p->H; base.W = p->W; base.KP = KP; base.kreal = p->k;
-  // operand copy of the initial state
-  hgru::quad_to_chunked_bf16_kernel<<<nblk(p->nelem / 8), 256, 0, st>>>(
-      p->H2.as<float>(), p->actH2.as<__nv_bfloat16>(), p->npix, KP, HW);
-  ++p->launches;
+  // initial state O_0 (NHWC or zeros) -> H2 (quad-chunked fp32) + the first gated operand, one pass
+  {
+    static bool attr = false;
+    if (!attr) {
+      CUDA_TRY(cudaFuncSetAttribute(hgru::init_state_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      attr = true;
+    }
+    const size_t smem = sizeof(float) * (KP * KP + 64 * (KP + 1));
+    hgru::init_state_gate_kernel<<<nblk(p->npix, 64), 256, smem, st>>>(
+        H2_init_nhwc, p->i_r.as<float>(), p->vec(V_IB), p->H2.as<float>(), p->actA.as<__nv_bfloat16>(), p->npix,
+        p->k, KP, HW);
+    ++p->launches;
+  }
   const bool fused = p->stacked;
   for (int t = 0; t < p->T; ++t) {
     hgru::TcConvArgs a;
-    if (!fused || t == 0) {
+    if (!fused && t > 0) {
       // circuit_input gate (hgru_module.py:696-711): operand A = bf16(sigmoid(H2 *1x1 i_r + i_b) . H2)
       a = base;
       a.wpk = p->wpk_i.as<__nv_bfloat16>(); a.bias = p->vec(V_IB); a.H2 = p->H2.as<float>();
@@ -496,6 +513,9 @@ static int hgru_run_bf16(hgru_plan_s* p, const float* Xp, float* H1_trace, float
     a.gate_wpk = p->wpk_i.as<__nv_bfloat16>(); a.gate_bias = p->vec(V_IB);
     a.gate_act_out = p->actA.as<__nv_bfloat16>();
     a.do_gate = (fused && t + 1 < p->T) ? 1 : 0;
+    if (t + 1 == p->T && p->fc_a) {     // last update also emits the readout's bf16 hi/lo operand
+      a.fc_a = p->fc_a; a.fc_scale = p->fc_scale; a.fc_shift = p->fc_shift; a.fc_kpad = p->fc_kpad;
+    }
     p->timer.begin(st);
     if ((rc = p->stacked ? dispatch_stack<hgru::EpiH2>(KP, p->stack_T, p->mapH1, a, st)
                         : dispatch_tc_hconv<hgru::EpiH2>(p->S, KP, p->mapH1, a, st)))
@@ -531,12 +551,19 @@ static void state_to_nhwc(const hgru_plan_s* p, const float* in, float* out, cud
 }
 
 // The recurrence on padded buffers: X = Xp, state in p->H2 (in/out).
-static int hgru_run_padded(hgru_plan_s* p, const float* Xp, float* H1_trace, float* H2_trace, cudaStream_t st) {
+static int hgru_run_padded(hgru_plan_s* p, const float* Xp, const float* H2_init_nhwc, float* H1_trace,
+                           float* H2_trace, cudaStream_t st) {
   if (!p->params_set) return fail(HGRU_E_STATE, "hgru_forward before hgru_set_params");
   p->launches = 0;
   p->timer.reset();
-  int rc = (p->mode == HGRU_MODE_BF16) ? hgru_run_bf16(p, Xp, H1_trace, H2_trace, st)
-                                       : hgru_run_fp32(p, Xp, H1_trace, H2_trace, st);
+  int rc;
+  if (p->mode == HGRU_MODE_BF16) {
+    rc = hgru_run_bf16(p, Xp, H2_init_nhwc, H1_trace, H2_trace, st);
+  } else {
+    if (H2_init_nhwc) state_from_nhwc(p, H2_init_nhwc, p->H2.as<float>(), st);
+    else CUDA_TRY(cudaMemsetAsync(p->H2.p, 0, p->H2.bytes, st));
+    rc = hgru_run_fp32(p, Xp, H1_trace, H2_trace, st);
+  }
   if (rc) return rc;
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -557,7 +584,7 @@ struct pose_plan_s {
   DevBuf fc1_wt, fc1_a;                            // tensor-core fc_1: bf16 [F][K] weights, bf16 [N][K] input
   CUtensorMap map_fc_a, map_fc_b;
   bool fc1_tc = false;
-  int fc_splits = 1, fc_kbps = 1;
+  int fc_splits = 1, fc_kbps = 1, fc_kpad = 0;
   float* bn_scale(int i) const { return bn.as<float>() + static_cast<size_t>(i) * 2 * bnw; }
   float* bn_shift(int i) const { return bn_scale(i) + bnw; }
   int bnw = 0;
@@ -613,21 +640,17 @@ static int pose_forward_impl(pose_plan_s* p, const float* depth, const float* H2
   }
   p->launches += 2;
   // hGRU (:81, R-D4)
-  if (H2_init) {
-    state_from_nhwc(h, H2_init, h->H2.as<float>(), st);
-    ++p->launches;
-  } else {
-    CUDA_TRY(cudaMemsetAsync(h->H2.p, 0, h->H2.bytes, st));
+  if (p->fc1_tc) {   // the last H2 epilogue writes the fc_1 operand directly
+    h->fc_a = p->fc1_a.as<__nv_bfloat16>(); h->fc_scale = p->bn_scale(3); h->fc_shift = p->bn_shift(3);
+    h->fc_kpad = p->fc_kpad;
   }
-  if ((rc = hgru_run_padded(h, h->Xp.as<float>(), nullptr, nullptr, st))) return rc;
+  if ((rc = hgru_run_padded(h, h->Xp.as<float>(), H2_init, nullptr, nullptr, st))) return rc;
   p->launches += h->launches;
   // BN (:82-90) folded into the A-operand of fc_1 (:91); split-K partial sums
   const int K = HW * HW * C;
   int nsplit = p->nsplit;
   if (p->fc1_tc) {
-    hgru::fc1_pack_a_kernel<<<nblk(npix * C), 256, 0, st>>>(h->H2.as<float>(), p->bn_scale(3), p->bn_shift(3),
-                                                           p->fc1_a.as<__nv_bfloat16>(), npix, C, KP, HW * HW);
-    hgru::GemmArgs g{N, p->F, K, p->fc_kbps, p->part.as<float>()};
+    hgru::GemmArgs g{N, p->F, K, p->fc_kpad, p->fc_kbps, p->part.as<float>()};
     dim3 grid((p->F + hgru::kGemmBN - 1) / hgru::kGemmBN, (N + hgru::kGemmBM - 1) / hgru::kGemmBM, p->fc_splits);
     hgru::gemm_tc_splitk_kernel<<<grid, 256, hgru::kGemmSmemBytes, st>>>(p->map_fc_a, p->map_fc_b, g);
     nsplit = p->fc_splits;
@@ -695,11 +718,7 @@ int hgru_forward(hgru_plan_t p, const float* X, const float* H2_init, float* H2_
   if (!X || !H2_out) return fail(HGRU_E_INVALID, "hgru_forward: null tensor pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   state_from_nhwc(p, X, p->Xp.as<float>(), st);
-  if (H2_init)
-    state_from_nhwc(p, H2_init, p->H2.as<float>(), st);
-  else
-    CUDA_TRY(cudaMemsetAsync(p->H2.p, 0, p->H2.bytes, st));
-  int rc = hgru_run_padded(p, p->Xp.as<float>(), H1_trace, H2_trace, st);
+  int rc = hgru_run_padded(p, p->Xp.as<float>(), H2_init, H1_trace, H2_trace, st);
   if (rc) return rc;
   state_to_nhwc(p, p->H2.as<float>(), H2_out, st);
   p->launches += 3;
@@ -727,8 +746,8 @@ int pose_plan_create(int N, int HW, int C, int S, int T, int F, int O, int mode,
   A(p->pool1, act); A(p->conv2, act);
   A(p->w1, sizeof(float) * 9 * C); A(p->b1, sizeof(float) * KP);
   A(p->b2, sizeof(float) * KP); A(p->b3, sizeof(float) * KP);
-  // fc_1 on tensor cores needs a 16-byte aligned K-major row pitch (K % 8 == 0)
-  p->fc1_tc = (mode == HGRU_MODE_BF16) && (K % 8 == 0);
+  // fc_1 on tensor cores (operand rows are padded to whole k-blocks, so any K works)
+  p->fc1_tc = (mode == HGRU_MODE_BF16);
   if (p->fc1_tc) {
     int sms = 148, dev = 0;
     cudaGetDevice(&dev);
@@ -742,10 +761,16 @@ int pose_plan_create(int N, int HW, int C, int S, int T, int F, int O, int mode,
     if (splits > total_kb) splits = total_kb;
     p->fc_kbps = (total_kb + splits - 1) / splits;
     p->fc_splits = (total_kb + p->fc_kbps - 1) / p->fc_kbps;
-    A(p->fc1_wt, sizeof(__nv_bfloat16) * K * F);
-    A(p->fc1_a, sizeof(__nv_bfloat16) * K * N);
-    if (!rc && (hgru::make_kmajor_bf16_map(&p->map_fc_a, p->fc1_a.p, N, K, hgru::kGemmBM) ||
-                hgru::make_kmajor_bf16_map(&p->map_fc_b, p->fc1_wt.p, F, K, hgru::kGemmBN)))
+    p->fc_kpad = total_kb * hgru::kGemmBK;                       // lo halves start here; row pitch 2*Kpad
+    const size_t pitch = 2 * static_cast<size_t>(p->fc_kpad);
+    A(p->fc1_wt, sizeof(__nv_bfloat16) * pitch * F);
+    A(p->fc1_a, sizeof(__nv_bfloat16) * pitch * N);
+    if (!rc) {
+      cudaMemset(p->fc1_wt.p, 0, p->fc1_wt.bytes);               // pad columns stay zero
+      cudaMemset(p->fc1_a.p, 0, p->fc1_a.bytes);
+    }
+    if (!rc && (hgru::make_kmajor_bf16_map(&p->map_fc_a, p->fc1_a.p, N, pitch, hgru::kGemmBM) ||
+                hgru::make_kmajor_bf16_map(&p->map_fc_b, p->fc1_wt.p, F, pitch, hgru::kGemmBN)))
       rc = fail(HGRU_E_CUDA, "cuTensorMapEncodeTiled (fc_1) failed");
     if (!rc && cudaFuncSetAttribute(hgru::gemm_tc_splitk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     hgru::kGemmSmemBytes) != cudaSuccess)
@@ -760,14 +785,14 @@ int pose_plan_create(int N, int HW, int C, int S, int T, int F, int O, int mode,
   if (mode == HGRU_MODE_FP32) {
     A(p->w2, sizeof(float) * 9 * KP * KP); A(p->w3, sizeof(float) * 9 * KP * KP);
   } else if (!rc) {
-    const size_t ab = static_cast<size_t>(N) * HW * HW * KP * sizeof(__nv_bfloat16);
+    const size_t ab = 2 * static_cast<size_t>(N) * HW * HW * KP * sizeof(__nv_bfloat16);   // hi + lo halves
     A(p->act_pool1, ab); A(p->act_conv2, ab);
-    const size_t wb = sizeof(__nv_bfloat16) * (KP / 16) * 9 * 2 * KP * 8;
+    const size_t wb = sizeof(__nv_bfloat16) * (3 * KP / 16) * 9 * 2 * KP * 8;        // [w_hi, w_lo, w_hi] per k-step
     A(p->wpk2, wb); A(p->wpk3, wb);
     TcGeom g;
     if (!rc && !tc_geometry(3, KP, &g)) rc = fail(HGRU_E_UNSUPPORTED, "pose_plan_create: unsupported channel count for bf16 mode");
-    if (!rc && (hgru::make_act_tensor_map(&p->map_pool1, p->act_pool1.p, N, KP / 8, HW, HW, g.box_cols, g.box_rows) ||
-                hgru::make_act_tensor_map(&p->map_conv2, p->act_conv2.p, N, KP / 8, HW, HW, g.box_cols, g.box_rows)))
+    if (!rc && (hgru::make_act_tensor_map(&p->map_pool1, p->act_pool1.p, N, 2 * KP / 8, HW, HW, g.box_cols, g.box_rows) ||
+                hgru::make_act_tensor_map(&p->map_conv2, p->act_conv2.p, N, 2 * KP / 8, HW, HW, g.box_cols, g.box_rows)))
       rc = fail(HGRU_E_CUDA, "cuTensorMapEncodeTiled failed");
   }
   if (rc) {
@@ -806,15 +831,17 @@ int pose_set_params(pose_plan_t p, const pose_params_t* q, float eps, void* stre
     pad_hwio_kernel<<<nblk(static_cast<size_t>(9) * KP * KP), 256, 0, st>>>(q->conv_2_filters, p->w2.as<float>(), 9, C, KP);
     pad_hwio_kernel<<<nblk(static_cast<size_t>(9) * KP * KP), 256, 0, st>>>(q->conv_3_filters, p->w3.as<float>(), 9, C, KP);
   } else {
-    const size_t total = static_cast<size_t>(KP / 16) * 9 * 2 * KP * 8;
-    hgru::pack_weights_kernel<<<nblk(total), 256, 0, st>>>(q->conv_2_filters, p->wpk2.as<__nv_bfloat16>(), 9, C, KP / 16, KP);
-    hgru::pack_weights_kernel<<<nblk(total), 256, 0, st>>>(q->conv_3_filters, p->wpk3.as<__nv_bfloat16>(), 9, C, KP / 16, KP);
+    const size_t total = static_cast<size_t>(3 * KP / 16) * 9 * 2 * KP * 8;
+    hgru::pack_weights_split3_kernel<<<nblk(total), 256, 0, st>>>(q->conv_2_filters, p->wpk2.as<__nv_bfloat16>(), 9,
+                                                                 C, KP / 16, KP);
+    hgru::pack_weights_split3_kernel<<<nblk(total), 256, 0, st>>>(q->conv_3_filters, p->wpk3.as<__nv_bfloat16>(), 9,
+                                                                 C, KP / 16, KP);
   }
   const size_t K = static_cast<size_t>(p->HW) * p->HW * C;
   if (p->fc1_tc) {
     dim3 tg(static_cast<unsigned>((K + 31) / 32), (F + 31) / 32);
     hgru::transpose_to_bf16_kernel<<<tg, 256, 0, st>>>(q->fc_1_weights, p->fc1_wt.as<__nv_bfloat16>(),
-                                                     static_cast<int>(K), F);
+                                                     static_cast<int>(K), F, p->fc_kpad, C);
   } else {
     CUDA_TRY(cudaMemcpyAsync(p->fc1_w.p, q->fc_1_weights, sizeof(float) * K * F, cudaMemcpyDeviceToDevice, st));
   }
@@ -888,6 +915,28 @@ int crop_area3d_forward(const float* frames, int N, int H, int W, float frame_sc
   const size_t total = static_cast<size_t>(N) * dh * dw;
   hgru::crop_area3d_kernel<<<nblk(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       frames, frame_scale, ip, zp, background, out_divisor, out, N, H, W, dh, dw);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int pose_postprocess_forward(const float* out_put, const double* com_uvd, int N, int J, double fx, double fy,
+                             double ux, double uy, float scale, float* xyz, float* uvd, void* stream) {
+  if (!out_put || !com_uvd || !xyz || !uvd) return fail(HGRU_E_INVALID, "pose_postprocess_forward: null pointer");
+  if (N < 1 || J < 1) return fail(HGRU_E_INVALID, "pose_postprocess_forward: non-positive shape");
+  hgru::pose_postprocess_kernel<<<nblk(static_cast<size_t>(N) * J), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      out_put, com_uvd, N, J, fx, fy, ux, uy, scale, xyz, uvd);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int joint_error_forward(const float* labels, const float* results, int N, int J, double* frame_mean_ws,
+                        float* frame_max_ws, double* result, void* stream) {
+  if (!labels || !results || !frame_mean_ws || !frame_max_ws || !result)
+    return fail(HGRU_E_INVALID, "joint_error_forward: null pointer");
+  if (N < 1 || J < 1) return fail(HGRU_E_INVALID, "joint_error_forward: non-positive shape");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  hgru::joint_error_frame_kernel<<<N, 128, 0, st>>>(labels, results, J, frame_mean_ws, frame_max_ws);
+  hgru::joint_error_final_kernel<<<1, 32, 0, st>>>(frame_mean_ws, frame_max_ws, N, result);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

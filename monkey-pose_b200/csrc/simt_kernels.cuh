@@ -224,7 +224,18 @@ stem_conv1_pool_bn_kernel(const float* __restrict__ depth, const float* __restri
   } else {
     st8(out + p * KP + cg * 8, r);
   }
-  if (out_bf16) st8_bf16(chunk_ptr(out_bf16, n, cg, pin, H * W, CG), r);
+  if (out_bf16) {
+    // operand copy for the tensor-core conv_2, split into bf16 hi + lo parts (chunk planes [0,CG) and
+    // [CG,2CG)): the pooled depth map is smooth, so plain bf16 rounding errors add up coherently
+    F8 hi, lo;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      hi.v[j] = __bfloat162float(__float2bfloat16(r.v[j]));
+      lo.v[j] = r.v[j] - hi.v[j];
+    }
+    st8_bf16(chunk_ptr(out_bf16, n, cg, pin, H * W, 2 * CG), hi);
+    st8_bf16(chunk_ptr(out_bf16, n, CG + cg, pin, H * W, 2 * CG), lo);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -407,6 +418,60 @@ quad_to_chunked_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
+// Initial state of the tensor-core path in one pass: O_0 (NHWC, k channels; hgru_module.py:884-887)
+//   -> H2 fp32 quad-chunked (zero padded), and the first timestep's gated operand
+//   A = bf16(sigmoid(O_0 *1x1 i_r + i_b) . O_0)  (hgru_module.py:696-711) in the chunked layout.
+// Block = 64 pixels; i_r in shared memory; thread = one pixel x 8 output channels (like gate1x1_kernel).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+init_state_gate_kernel(const float* __restrict__ h0 /*[npix][k] or nullptr = zeros*/,
+                       const float* __restrict__ wg /*[KP][KP]*/, const float* __restrict__ bg,
+                       float* __restrict__ H2q, __nv_bfloat16* __restrict__ actA, size_t npix, int k, int KP,
+                       int HW) {
+  extern __shared__ float smem_f[];
+  float* wsm = smem_f;                 // [KP][KP]
+  float* xin = smem_f + KP * KP;       // [64][KP+1]
+  const int tid = threadIdx.x;
+  const int CG = KP >> 3;
+  const size_t p0 = blockIdx.x * static_cast<size_t>(64);
+  for (int e = tid; e < KP * KP; e += 256) wsm[e] = wg[e];
+  for (int e = tid; e < 64 * KP; e += 256) {
+    const int pp = e / KP, c = e - pp * KP;
+    xin[pp * (KP + 1) + c] = (h0 && p0 + pp < npix && c < k) ? h0[(p0 + pp) * k + c] : 0.f;
+  }
+  __syncthreads();
+  const int pp = tid & 63;
+  const size_t p = p0 + pp;
+  if (p >= npix) return;
+  const size_t n = p / HW, pin = p - n * HW;
+  for (int cg = tid >> 6; cg < CG; cg += 4) {
+    F8 a;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a.v[j] = 0.f;
+    for (int ci = 0; ci < KP; ++ci) {
+      const float xv = xin[pp * (KP + 1) + ci];
+      const float4 w0 = *reinterpret_cast<const float4*>(wsm + ci * KP + cg * 8);
+      const float4 w1 = *reinterpret_cast<const float4*>(wsm + ci * KP + cg * 8 + 4);
+      a.v[0] = fmaf(xv, w0.x, a.v[0]); a.v[1] = fmaf(xv, w0.y, a.v[1]);
+      a.v[2] = fmaf(xv, w0.z, a.v[2]); a.v[3] = fmaf(xv, w0.w, a.v[3]);
+      a.v[4] = fmaf(xv, w1.x, a.v[4]); a.v[5] = fmaf(xv, w1.y, a.v[5]);
+      a.v[6] = fmaf(xv, w1.z, a.v[6]); a.v[7] = fmaf(xv, w1.w, a.v[7]);
+    }
+    F8 hv, mv;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = cg * 8 + j;
+      hv.v[j] = xin[pp * (KP + 1) + c];
+      mv.v[j] = (c < k) ? sigmoidf_(a.v[j] + bg[c]) * hv.v[j] : 0.f;
+    }
+    float* o = H2q + ((n * (KP >> 2) + 2 * cg) * HW + pin) * 4;
+    *reinterpret_cast<float4*>(o) = make_float4(hv.v[0], hv.v[1], hv.v[2], hv.v[3]);
+    *reinterpret_cast<float4*>(o + static_cast<size_t>(HW) * 4) = make_float4(hv.v[4], hv.v[5], hv.v[6], hv.v[7]);
+    st8_bf16(chunk_ptr(actA, static_cast<int>(n), cg, pin, HW, CG), mv);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Readout FC1 (hgru_pose.py:91,156-163): part[z][m][j] = sum_{kk in slice z} (a[m][kk]*sc[kk%k]+sh[kk%k]) * Wt[kk][j]
 // (a is read from the channel-padded activation buffer; kk enumerates (h, w, c) like tf.reshape)
 // The per-channel affine on A is the inference batch-norm of the hGRU output (:82-90).
@@ -515,8 +580,10 @@ __global__ void bn_fold_kernel(const float* gamma, const float* beta, const floa
 }
 
 // Weight packing for the tcgen05 conv: HWIO fp32 [S][S][k][k] -> bf16 [KSTEPS][taps][2][CO_PAD][8 ci]
+// `ci_wrap` > 0: input channel index wraps at ci_wrap (the operand carries hi and lo bf16 halves of the
+// same channels in consecutive chunk planes, both multiplied by the same weights).
 __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wpk,
-                                    int taps, int k, int ksteps, int co_pad) {
+                                    int taps, int k, int ksteps, int co_pad, int ci_wrap = 0) {
   const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   const size_t total = static_cast<size_t>(ksteps) * taps * 2 * co_pad * 8;
   if (i >= total) return;
@@ -526,10 +593,32 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
   const int ch = r & 1; r >>= 1;
   const int tap = r % taps;
   const int q = r / taps;
-  const int ci = q * 16 + ch * 8 + j;
+  int ci = q * 16 + ch * 8 + j;
+  if (ci_wrap > 0 && ci >= ci_wrap) ci -= ci_wrap;
   float v = 0.f;
   if (ci < k && co < k) v = w[(static_cast<size_t>(tap) * k + ci) * k + co];
   wpk[i] = __float2bfloat16(v);
+}
+
+// Weight packing for the SPLIT3 tensor-core conv: per 16-channel group three blocks
+// [w_hi, w_lo, w_hi] (hi = bf16(w), lo = bf16(w - hi)); layout [3*ksteps][taps][2][co_pad][8 ci].
+__global__ void pack_weights_split3_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wpk,
+                                           int taps, int k, int ksteps, int co_pad) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  const size_t total = static_cast<size_t>(3 * ksteps) * taps * 2 * co_pad * 8;
+  if (i >= total) return;
+  const int j = i & 7;
+  size_t r = i >> 3;
+  const int co = r % co_pad; r /= co_pad;
+  const int ch = r & 1; r >>= 1;
+  const int tap = r % taps;
+  const int wq = r / taps;
+  const int q = wq / 3, part = wq % 3;
+  const int ci = q * 16 + ch * 8 + j;
+  float v = 0.f;
+  if (ci < k && co < k) v = w[(static_cast<size_t>(tap) * k + ci) * k + co];
+  const __nv_bfloat16 hi = __float2bfloat16(v);
+  wpk[i] = (part == 1) ? __float2bfloat16(v - __bfloat162float(hi)) : hi;
 }
 
 }  // namespace hgru

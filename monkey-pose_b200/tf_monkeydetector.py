@@ -81,6 +81,21 @@ class tfMonkeyDetector(object):
         jnts_xyz = rel_jnts_xyz + com_xyz
         return jnts_xyz, self.xyztouvd(jnts_xyz)
 
+    def getAbsoluteCoordinates_batch(self, out_put, coms, scale):
+        """Batched, on the device: network output [N,3J] (normalised) x scale (cube[2]/2,
+        train_cnn_networks_hgru.py:293-296) + getAbsoluteCoordinates per frame -> (xyz, uvd) [N,J,3]."""
+        if not (torch.is_tensor(out_put) and out_put.is_cuda and out_put.dim() == 2 and out_put.shape[1] % 3 == 0):
+            raise RuntimeError("out_put must be a [N,3J] torch CUDA tensor (no CPU fallback)")
+        out_put = out_put.to(torch.float32).contiguous()
+        N, J = int(out_put.shape[0]), int(out_put.shape[1]) // 3
+        com_d = torch.as_tensor(numpy.asarray(coms, numpy.float64).reshape(N, 3)).cuda()
+        xyz = torch.empty((N, J, 3), device=out_put.device, dtype=torch.float32)
+        uvd = torch.empty_like(xyz)
+        _lib.check(_lib.load().pose_postprocess_forward(
+            out_put.data_ptr(), com_d.data_ptr(), N, J, float(self.fx), float(self.fy), float(self.ux),
+            float(self.uy), float(scale), xyz.data_ptr(), uvd.data_ptr(), _stream()), "pose_postprocess_forward")
+        return xyz, uvd
+
     # ---- crop (device) ----------------------------------------------------------------------------------
     def _window(self, com, H, W, dsize):
         """Host-side integers of one frame's crop (tf_monkeydetector.py:309-362): window, resized size,

@@ -213,3 +213,24 @@ def test_crop_stage_vs_oracle_at_batch_size_and_feeds_the_model():
     m.channels, m.timesteps, m.fc_hidden = 16, 1, 32
     out = m.build(patches[:4].contiguous(), 69)
     assert out.shape == (4, 69) and torch.isfinite(out).all()
+
+
+# ---- post-processing -------------------------------------------------------------
+def test_postprocess_bit_exact_against_reference_golden():
+    from monkey_pose_b200 import pose_evaluation as pe
+    from monkey_pose_b200 import tf_monkeydetector as tmd
+    z = np.load(os.path.join(GOLDEN, "post_ref.npz"))
+    md = tmd.tfMonkeyDetector(365.456, 365.456, 256, 212, [800, 800, 1200], 200, 10000)
+    xyz, uvd = md.getAbsoluteCoordinates_batch(torch.as_tensor(z["out_put"]).cuda(), z["coms"], float(z["scale"]))
+    assert np.array_equal(xyz.cpu().numpy(), z["xyz"])
+    assert np.array_equal(uvd.cpu().numpy(), z["uvd"])
+    n = z["out_put"].shape[0]
+    res = torch.as_tensor(np.reshape(z["out_put"], (n, -1, 3)) * np.float32(z["scale"])).cuda()
+    lab = torch.as_tensor(np.reshape(z["labels"], (n, -1, 3)) * np.float32(z["scale"])).cuda()
+    assert abs(pe.getMeanError_np(lab, res) - float(z["mean_error_mm"])) <= 1e-5 * float(z["mean_error_mm"])
+    assert pe.getMaxError_np(lab, res) == float(z["max_error_mm"])
+    lab[0, 0, 0] = float("nan")                       # NaN joints are skipped like numpy.nanmean
+    assert np.isfinite(pe.getMeanError_np(lab, res))
+    # single-frame host methods mirror the reference API too
+    a, b = md.getAbsoluteCoordinates(z["xyz"][0] - md.uvdtoxyz(z["coms"][0]), z["coms"][0])
+    assert np.allclose(b, z["uvd"][0], rtol=1e-5, atol=1e-3)
