@@ -106,7 +106,7 @@ int run_case(int N, int H, int W, int k, int grid_override, int iters) {
   return (bad || nan) ? 1 : 0;
 }
 template <int KP, int T, int KC, int CS, class Epi>
-void time_real_epilogue(const char* name, int N, int H, int W, int k, int gate = 1) {
+void time_real_epilogue(const char* name, int N, int H, int W, int k, int gate = 1, int dbg = 0) {
   using Cfg = hgru::StackCfg<KP, T, KC, CS>;
   const int CG = KP / 8;
   size_t npix = (size_t)N * H * W;
@@ -124,16 +124,18 @@ void time_real_epilogue(const char* name, int N, int H, int W, int k, int gate =
   a.units_x = (W + 63) / 64; a.units_y = (H + 15) / 16; a.num_units = N * a.units_x * a.units_y;
   a.wpk = wpk; a.bias = vec; a.v0 = vec + KP; a.v1 = vec + 2 * KP; a.v2 = vec + 3 * KP; a.rho_t = vec + 4 * KP;
   a.X = X; a.H1 = H1; a.G = G; a.H2 = H2; a.out = H1; a.out_bf16 = actout;
-  a.gate_wpk = wpk; a.gate_bias = vec; a.gate_out = G; a.gate_act_out = actout; a.do_gate = gate;
-  auto kern = hgru::hconv_stack_kernel<KP, T, KC, CS, Epi>;
+  a.gate_wpk = wpk; a.gate_bias = vec; a.gate_out = G; a.gate_act_out = actout; a.do_gate = gate; a.dbg_flags = dbg;
+  auto kern = hgru::hconv_stack_kernel<KP, T, KC, CS, Epi, false>;
+  auto kern_prof = hgru::hconv_stack_kernel<KP, T, KC, CS, Epi, true>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  CK(cudaFuncSetAttribute(kern_prof, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   int grid = 148;
   cudaLaunchConfig_t cfg{}; cfg.gridDim = dim3(grid); cfg.blockDim = dim3(384); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   long long* d_prof; CK(cudaMalloc(&d_prof, grid * 8 * sizeof(long long))); CK(cudaMemset(d_prof, 0, grid * 8 * sizeof(long long)));
   hgru::TcConvArgs ap = a; ap.prof = d_prof;
-  CK(cudaLaunchKernelEx(&cfg, kern, map, wmap, ap)); CK(cudaDeviceSynchronize());
+  CK(cudaLaunchKernelEx(&cfg, kern_prof, map, wmap, ap)); CK(cudaDeviceSynchronize());
   std::vector<long long> pr(grid * 8); CK(cudaMemcpy(pr.data(), d_prof, grid * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
   double av[6] = {0, 0, 0, 0, 0, 0}; int nl = 0;
   for (int b = 0; b < grid; ++b) { if (pr[b * 8]) ++nl; for (int i = 0; i < 6; ++i) av[i] += pr[b * 8 + i]; }
@@ -158,6 +160,12 @@ int main(int argc, char** argv) {
   if (which == 0 || which == 7) f += run_case<32, 5, 25, 1>(256, 64, 64, 25, 0, 5);
   if (which == 0 || which == 8) f += run_case<32, 5, 25, 2>(256, 64, 64, 25, 0, 5);
   if (which == 0 || which == 9) f += run_case<32, 4, 32, 2>(256, 64, 64, 32, 0, 5);
+  if (which == 21) {
+    time_real_epilogue<32, 5, 25, 1, hgru::EpiBias>("EpiBias", 256, 64, 64, 25, 0, 0);
+    time_real_epilogue<32, 5, 25, 1, hgru::EpiBias>("EpiBias noWstream", 256, 64, 64, 25, 0, 1);
+    time_real_epilogue<32, 5, 25, 1, hgru::EpiH2>("EpiH2", 256, 64, 64, 25, 1, 0);
+    time_real_epilogue<32, 5, 25, 1, hgru::EpiH2>("EpiH2 noWstream", 256, 64, 64, 25, 1, 1);
+  }
   if (which == 20) {
     time_real_epilogue<32, 5, 25, 1, hgru::EpiBias>("EpiBias", 256, 64, 64, 25, 0);
     time_real_epilogue<32, 5, 25, 1, hgru::EpiH1>("EpiH1", 256, 64, 64, 25, 0);

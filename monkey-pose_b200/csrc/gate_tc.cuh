@@ -35,7 +35,8 @@ gate_tc_kernel(const __nv_bfloat16* __restrict__ act /*[N][CG][HW][8]*/, const T
   const uint32_t a_buf = base, w_buf = base + Cfg::A_BYTES;
   const uint32_t bar_ld = w_buf + Cfg::W_BYTES, bar_mma = bar_ld + 8, tmem_slot = bar_ld + 16;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);   // provably warp-uniform
+  const int lane = threadIdx.x & 31;
   const int HW = a.H * a.W;
   const int tiles_per_frame = (HW + 127) / 128;
   const int n = blockIdx.x / tiles_per_frame;
@@ -57,7 +58,7 @@ gate_tc_kernel(const __nv_bfloat16* __restrict__ act /*[N][CG][HW][8]*/, const T
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);
 
   if (warp == 0) {
     const bool leader = elect_one();

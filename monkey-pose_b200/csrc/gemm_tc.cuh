@@ -57,7 +57,8 @@ gemm_tc_splitk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   const uint32_t bar_full = bars, bar_empty = bars + 8 * kGemmStages, bar_acc = bar_empty + 8 * kGemmStages;
   const uint32_t tmem_slot = bar_acc + 8;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);   // provably warp-uniform
+  const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kGemmStages; ++i) {
@@ -73,7 +74,7 @@ gemm_tc_splitk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);
 
   const int n0 = blockIdx.x * kGemmBN, m0 = blockIdx.y * kGemmBM, z = blockIdx.z;
   const int total_kb = (g.K + kGemmBK - 1) / kGemmBK;
@@ -106,7 +107,7 @@ gemm_tc_splitk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     const uint64_t b_lo = make_smem_desc_sw128(base + 2 * kGemmABytes + kGemmBBytes);
     uint32_t st = 0, ph = 0;
     for (int kb = 0; kb < nkb; ++kb) {
-      mbar_wait(bar_full + 8 * st, ph);
+      mbar_wait_warp(bar_full + 8 * st, ph);
       tc_fence_after();
       const uint64_t so = static_cast<uint64_t>((st * kGemmStageBytes) >> 4);
 #pragma unroll

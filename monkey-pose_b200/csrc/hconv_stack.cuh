@@ -64,6 +64,9 @@ struct StackCfg {
   static constexpr int GATE_BYTES = GATE_A_BYTES + GATE_W_BYTES;
   // ring depth: as deep as the 227 KB allow (pair mode: half-size stages)
   static constexpr int WSTAGES = (CS == 2) ? 8 : ((WIN_BYTES + GATE_BYTES + 4 * NG * 2 * NPAD * 16 + 2048 <= 232448) ? 4 : 3);
+  // stages the MMA issuer awaits with one barrier round trip.  2 (a whole filter row) measured 2 % slower
+  // than 1 on B200 (the ring then runs out of slack), so every stage is awaited on its own.
+  static constexpr int WGROUP = 1;
   static constexpr int NUM_BARS = 2 + 2 * WSTAGES + 8 + 1;
   static constexpr int STAGE_ROWS = STAGE_BYTES / 256;    // rows of the 256-byte weight view per stage
   static constexpr int SMEM_BYTES = WIN_BYTES + WSTAGES * STAGE_BYTES + GATE_BYTES + NUM_BARS * 8 + 16 + 1024;
@@ -159,11 +162,119 @@ __device__ __forceinline__ void tmem_ld_range(uint32_t taddr, float (&v)[CN]) {
 }
 }  // namespace detail
 
+// MMA issue loop of the stacked kernel.  The whole warp runs it convergently (addresses and descriptors
+// stay warp-uniform); one elected lane issues the tcgen05 instructions.
+template <class Cfg, bool PROF>
+__device__ __forceinline__ void stack_mma_issuer(const TcConvArgs& a, uint32_t tmem_base, uint32_t win,
+                                                 uint32_t w_buf, uint32_t bar_win_full, uint32_t bar_win_empty,
+                                                 uint32_t bar_w_full, uint32_t bar_w_empty, uint32_t bar_acc_full,
+                                                 uint32_t bar_acc_empty, int iters, int NT, int npairs) {
+  using namespace sm100;
+  constexpr int CS = Cfg::CS, T = Cfg::T;
+  constexpr uint16_t kMask = static_cast<uint16_t>((1u << CS) - 1u);
+  (void)kMask;
+  const bool leader = elect_one();
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);      // read from shared memory: mark it warp-uniform
+  constexpr uint32_t idesc = make_idesc(1 /*bf16*/, 128 * CS, Cfg::NPAD);
+  const uint64_t adesc0 = make_smem_desc(win, Cfg::CHUNK_PITCH, Cfg::ROW_PITCH);
+  const uint64_t bdesc0 = make_smem_desc(w_buf, Cfg::NLOC * 16, 128);
+  uint32_t st = 0, ph = 0;
+  uint32_t tc = 0;            // running tile counter: TMEM slot = tc & 3, use count = tc >> 2
+  int vit = 0;
+  long long t_win = 0, t_acc = 0, t_w = 0, t_begin = 0, t0 = 0;
+  if constexpr (PROF) t_begin = clock64();
+  for (int it = 0; it < iters; ++it) {
+    const int u = it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);
+    const bool valid = u < a.num_units;
+    if constexpr (PROF) t0 = clock64();
+    if (valid) mbar_wait_warp(bar_win_full, vit & 1);
+    if constexpr (PROF) t_win += clock64() - t0;
+    tc_fence_after();
+    for (int pr = 0; pr < npairs; ++pr) {
+      const int j0 = 2 * pr;
+      const bool two = (j0 + 1) < NT;
+      const uint32_t s0 = tc & 3, s1 = (tc + 1) & 3;
+      if constexpr (PROF) t0 = clock64();
+      mbar_wait_warp(bar_acc_empty + 8 * s0, ((tc >> 2) & 1) ^ 1);
+      if (two) mbar_wait_warp(bar_acc_empty + 8 * s1, (((tc + 1) >> 2) & 1) ^ 1);
+      if constexpr (PROF) t_acc += clock64() - t0;
+      tc_fence_after();
+      const uint32_t acc0 = tmem_base + s0 * Cfg::NPAD, acc1 = tmem_base + s1 * Cfg::NPAD;
+      const uint64_t a_tile0 = adesc0 + static_cast<uint64_t>(8 * j0);      // 8 pixels = 8 x 16 B
+      // stage order: filter row dy, then k-step q
+      for (int dy = 0; dy < Cfg::S; ++dy) {
+        constexpr int GRP = Cfg::WGROUP;
+#pragma unroll
+        for (int q0 = 0; q0 < Cfg::KSTEPS; q0 += GRP) {
+          if constexpr (PROF) t0 = clock64();
+          if constexpr (GRP == 2) {
+            while (!__all_sync(0xffffffffu, mbar_try_wait(bar_w_full + 8 * st, ph) &
+                                                mbar_try_wait(bar_w_full + 8 * (st + 1), ph))) {
+            }
+          } else {
+            mbar_wait_warp(bar_w_full + 8 * st, ph);
+          }
+          if constexpr (PROF) t_w += clock64() - t0;
+          tc_fence_after();
+          if (leader) {
+#pragma unroll
+            for (int qq = 0; qq < GRP; ++qq) {
+              const int q = q0 + qq;
+              const uint64_t bdesc_st = bdesc0 + static_cast<uint64_t>(((st + qq) * Cfg::STAGE_BYTES) >> 4);
+              const uint64_t adesc_st =
+                  a_tile0 + static_cast<uint64_t>((dy * Cfg::ROW_PITCH + q * 2 * Cfg::CHUNK_PITCH) >> 4);
+#pragma unroll
+              for (int g = 0; g < Cfg::NG; ++g) {
+                const uint64_t bdesc = bdesc_st + static_cast<uint64_t>((g * Cfg::BLK_BYTES) >> 4);
+                const uint64_t adesc = adesc_st + static_cast<uint64_t>(T * g);
+                const uint32_t accum = (dy | q | g) != 0;
+                if constexpr (CS > 1) {
+                  mma_bf16_ss_2cta(acc0, adesc, bdesc, idesc, accum);
+                  if (two) mma_bf16_ss_2cta(acc1, adesc + 8, bdesc, idesc, accum);
+                } else {
+                  mma_bf16_ss(acc0, adesc, bdesc, idesc, accum);
+                  if (two) mma_bf16_ss(acc1, adesc + 8, bdesc, idesc, accum);
+                }
+              }
+              // release the weight stage when these MMAs have read it
+              if constexpr (CS > 1) tc_commit_2cta(bar_w_empty + 8 * (st + qq), kMask);
+              else tc_commit(bar_w_empty + 8 * (st + qq));
+            }
+          }
+          st += GRP;
+          if (st == Cfg::WSTAGES) { st = 0; ph ^= 1; }
+        }
+      }
+      if (leader) {
+        if constexpr (CS > 1) {
+          tc_commit_2cta(bar_acc_full + 8 * s0, kMask);
+          if (two) tc_commit_2cta(bar_acc_full + 8 * s1, kMask);
+        } else {
+          tc_commit(bar_acc_full + 8 * s0);
+          if (two) tc_commit(bar_acc_full + 8 * s1);
+        }
+      }
+      tc += two ? 2 : 1;
+    }
+    // release the windows: in pair mode both CTAs' windows were read by these MMAs
+    if (leader && valid) {
+      if constexpr (CS > 1) tc_commit_2cta(bar_win_empty, kMask);
+      else tc_commit(bar_win_empty);
+    }
+    if (valid) ++vit;
+  }
+  if (PROF && a.prof && leader) {
+    long long* o = a.prof + static_cast<size_t>(blockIdx.x) * 8;
+    o[0] = clock64() - t_begin; o[1] = t_win; o[2] = t_acc; o[3] = t_w;
+  }
+  __syncwarp();
+}
+
 // Epilogue of one warpgroup for the channel range [C0, C0+CN) of every tile: un-stack (rotate +
 // carry), fused math, stores.  Two warpgroups split the channels so that each SM sub-partition has
 // two epilogue warps to overlap TMEM / global-memory latencies; they never need to talk to each
 // other (un-stacking and the integration math are per channel).
-template <class Cfg, class Epi, int C0, int CN>
+template <class Cfg, class Epi, int C0, int CN, bool PROF>
 __device__ __forceinline__ void stack_epilogue(const TcConvArgs& a, uint32_t tmem_base, uint32_t bar_acc_full,
                                                uint32_t bar_acc_empty, uint32_t crank, int iters, int NT,
                                                int units_per_frame, int warp, int lane, bool profile,
@@ -179,7 +290,8 @@ __device__ __forceinline__ void stack_epilogue(const TcConvArgs& a, uint32_t tme
   const int prow = m >> 3, pcol = m & 7;
   uint32_t tc = 0;
   const uint32_t lead_acc_empty = (CS > 1) ? mapa_cluster(bar_acc_empty, 0) : 0u;
-  long long e_wait = 0, e_begin = clock64(), e0;
+  long long e_wait = 0, e_begin = 0, e0 = 0;
+  if constexpr (PROF) e_begin = clock64();
   for (int it = 0; it < iters; ++it) {
     const int u = it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);
     const bool valid = u < a.num_units;
@@ -199,9 +311,9 @@ __device__ __forceinline__ void stack_epilogue(const TcConvArgs& a, uint32_t tme
       const size_t pin = static_cast<size_t>(y) * a.W + x;
       typename Epi::template Pre<NCH> pre;
       if (store) Epi::template load<NCH>(a, n, pin, C0, pre);
-      e0 = clock64();
+      if constexpr (PROF) e0 = clock64();
       mbar_wait(bar_acc_full + 8 * slot, (tc >> 2) & 1);
-      e_wait += clock64() - e0;
+      if constexpr (PROF) e_wait += clock64() - e0;
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + slot * Cfg::NPAD + C0;
       float out[NCH], nxt[CN];
@@ -281,13 +393,13 @@ __device__ __forceinline__ void stack_epilogue(const TcConvArgs& a, uint32_t tme
       }
     }
   }
-  if (profile && a.prof && (threadIdx.x & 127) == 0) {
+  if (PROF && profile && a.prof && (threadIdx.x & 127) == 0) {
     long long* o = a.prof + static_cast<size_t>(blockIdx.x) * 8;
     o[4] = clock64() - e_begin; o[5] = e_wait;
   }
 }
 
-template <int KP, int T, int KC, int CS, class Epi>
+template <int KP, int T, int KC, int CS, class Epi, bool PROF = false>
 __global__ void __launch_bounds__(384, 1)
 hconv_stack_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap w_map,
                    const TcConvArgs a) {
@@ -309,10 +421,11 @@ hconv_stack_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
   const uint32_t tmem_slot = bar_gate + 8;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle: tells the compiler it is warp-uniform, so the role branches below are
+  // uniform branches and the MMA issuer's addresses can live in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const uint32_t crank = (CS > 1) ? cluster_ctarank() : 0u;
-  constexpr uint16_t kMask = static_cast<uint16_t>((1u << CS) - 1u);
 
   if (threadIdx.x == 0) {
     mbar_init(bar_win_full, 1);
@@ -370,6 +483,8 @@ hconv_stack_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
               if (crank == 0) mbar_arrive_expect_tx(bar_w_full + 8 * st, 2 * Cfg::STAGE_BYTES);
               tma_load_2d_2cta(w_buf + st * Cfg::STAGE_BYTES, &w_map, lead_w_full + 8 * st, 0,
                                (sg * CS + static_cast<int>(crank)) * Cfg::STAGE_ROWS);
+            } else if ((a.dbg_flags & 1) && (it | pr | (sg >= Cfg::WSTAGES))) {
+              mbar_arrive(bar_w_full + 8 * st);      // development: reuse the resident (stale) stage
             } else {
               mbar_arrive_expect_tx(bar_w_full + 8 * st, Cfg::STAGE_BYTES);
               bulk_load(w_buf + st * Cfg::STAGE_BYTES, wsrc + static_cast<size_t>(sg) * Cfg::STAGE_BYTES,
@@ -407,98 +522,16 @@ hconv_stack_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
     // peer CTA of a pair: its MMAs are issued by the leader
   } else if (warp == 1) {
     // ---------------- MMA issuer (convergent warp, one elected lane issues) ----------------
-    const bool leader = elect_one();
-    constexpr uint32_t idesc = make_idesc(1 /*bf16*/, 128 * CS, Cfg::NPAD);
-    const uint64_t adesc0 = make_smem_desc(win, Cfg::CHUNK_PITCH, Cfg::ROW_PITCH);
-    const uint64_t bdesc0 = make_smem_desc(w_buf, Cfg::NLOC * 16, 128);
-    uint32_t st = 0, ph = 0;
-    uint32_t tc = 0;            // running tile counter: TMEM slot = tc & 3, use count = tc >> 2
-    int vit = 0;
-    long long t_win = 0, t_acc = 0, t_w = 0, t_begin = clock64(), t0;
-    for (int it = 0; it < iters; ++it) {
-      const int u = it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);
-      const bool valid = u < a.num_units;
-      t0 = clock64();
-      if (valid) mbar_wait(bar_win_full, vit & 1);
-      t_win += clock64() - t0;
-      tc_fence_after();
-      for (int pr = 0; pr < npairs; ++pr) {
-        const int j0 = 2 * pr;
-        const bool two = (j0 + 1) < NT;
-        const uint32_t s0 = tc & 3, s1 = (tc + 1) & 3;
-        t0 = clock64();
-        mbar_wait(bar_acc_empty + 8 * s0, ((tc >> 2) & 1) ^ 1);
-        if (two) mbar_wait(bar_acc_empty + 8 * s1, (((tc + 1) >> 2) & 1) ^ 1);
-        t_acc += clock64() - t0;
-        tc_fence_after();
-        const uint32_t acc0 = tmem_base + s0 * Cfg::NPAD, acc1 = tmem_base + s1 * Cfg::NPAD;
-        const uint64_t a_tile0 = adesc0 + static_cast<uint64_t>(8 * j0);      // 8 pixels = 8 x 16 B
-        uint32_t stage_off = 0;      // (q * 2*CHUNK_PITCH + dy * ROW_PITCH) >> 4, advanced per stage
-        int q = 0;
-        for (int sg = 0; sg < Cfg::PASS_STAGES; ++sg) {
-          t0 = clock64();
-          mbar_wait(bar_w_full + 8 * st, ph);
-          t_w += clock64() - t0;
-          tc_fence_after();
-          const uint64_t bdesc_st = bdesc0 + static_cast<uint64_t>((st * Cfg::STAGE_BYTES) >> 4);
-#pragma unroll
-          for (int g = 0; g < Cfg::NG; ++g) {
-            const uint64_t bdesc = bdesc_st + static_cast<uint64_t>((g * Cfg::BLK_BYTES) >> 4);
-            const uint64_t adesc = a_tile0 + stage_off + static_cast<uint64_t>(T * g);
-            const uint32_t accum = (sg | g) != 0;
-            if (leader) {
-              if constexpr (CS > 1) {
-                mma_bf16_ss_2cta(acc0, adesc, bdesc, idesc, accum);
-                if (two) mma_bf16_ss_2cta(acc1, adesc + 8, bdesc, idesc, accum);
-              } else {
-                mma_bf16_ss(acc0, adesc, bdesc, idesc, accum);
-                if (two) mma_bf16_ss(acc1, adesc + 8, bdesc, idesc, accum);
-              }
-            }
-          }
-          if (leader) {
-            if constexpr (CS > 1) tc_commit_2cta(bar_w_empty + 8 * st, kMask);
-            else tc_commit(bar_w_empty + 8 * st);
-          }
-          if (++st == Cfg::WSTAGES) { st = 0; ph ^= 1; }
-          // stage order: dy-major, then k-step q
-          if (++q == Cfg::KSTEPS) {
-            q = 0;     // next filter row, back to k-step 0 (the delta may be negative: exact signed division)
-            stage_off += static_cast<uint32_t>((Cfg::ROW_PITCH - (Cfg::KSTEPS - 1) * 2 * Cfg::CHUNK_PITCH) / 16);
-          }
-          else stage_off += (2 * Cfg::CHUNK_PITCH) >> 4;
-        }
-        if (leader) {
-          if constexpr (CS > 1) {
-            tc_commit_2cta(bar_acc_full + 8 * s0, kMask);
-            if (two) tc_commit_2cta(bar_acc_full + 8 * s1, kMask);
-          } else {
-            tc_commit(bar_acc_full + 8 * s0);
-            if (two) tc_commit(bar_acc_full + 8 * s1);
-          }
-        }
-        tc += two ? 2 : 1;
-      }
-      // release the windows: in pair mode both CTAs' windows were read by these MMAs
-      if (leader && valid) {
-        if constexpr (CS > 1) tc_commit_2cta(bar_win_empty, kMask);
-        else tc_commit(bar_win_empty);
-      }
-      if (valid) ++vit;
-    }
-    if (a.prof && leader) {
-      long long* o = a.prof + static_cast<size_t>(blockIdx.x) * 8;
-      o[0] = clock64() - t_begin; o[1] = t_win; o[2] = t_acc; o[3] = t_w;
-    }
-    __syncwarp();
+    stack_mma_issuer<Cfg, PROF>(a, tmem_base, win, w_buf, bar_win_full, bar_win_empty, bar_w_full, bar_w_empty,
+                                bar_acc_full, bar_acc_empty, iters, NT, npairs);
   } else if (warp >= 4) {
     // ---------------- epilogue: two warpgroups, channels split at Cfg::CSPLIT ----------------
     if (warp < 8)
-      stack_epilogue<Cfg, Epi, 0, Cfg::CSPLIT>(a, tmem_base, bar_acc_full, bar_acc_empty, crank, iters, NT,
+      stack_epilogue<Cfg, Epi, 0, Cfg::CSPLIT, PROF>(a, tmem_base, bar_acc_full, bar_acc_empty, crank, iters, NT,
                                                units_per_frame, warp, lane, true, smem_raw, gate_a, gate_w,
                                                bar_gate);
     else
-      stack_epilogue<Cfg, Epi, Cfg::CSPLIT, KC - Cfg::CSPLIT>(a, tmem_base, bar_acc_full, bar_acc_empty, crank,
+      stack_epilogue<Cfg, Epi, Cfg::CSPLIT, KC - Cfg::CSPLIT, PROF>(a, tmem_base, bar_acc_full, bar_acc_empty, crank,
                                                               iters, NT, units_per_frame, warp, lane, false,
                                                               smem_raw, gate_a, gate_w, bar_gate);
   }

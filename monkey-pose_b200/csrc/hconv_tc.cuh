@@ -96,6 +96,7 @@ struct TcConvArgs {
   const float* fc_shift;
   int fc_kpad;
   long long* prof;          // optional per-CTA cycle counters (development; nullptr in production)
+  int dbg_flags;            // development only: bit 0 = do not re-stream weights after the first ring fill
 };
 
 // fp32 state tensors of the tensor-core path are "quad-chunked": [n][c/4][y][x][4].  A thread owns
@@ -447,7 +448,7 @@ hconv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const TcConvArgs a) 
   uint32_t* tmem_slot_ptr =
       reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);   // provably warp-uniform
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -470,7 +471,7 @@ hconv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const TcConvArgs a) 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);
 
   const int units_per_frame = a.units_x * a.units_y;
   const int first = blockIdx.x;
@@ -528,19 +529,19 @@ hconv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const TcConvArgs a) 
     for (int u = first; u < a.num_units; u += stride, ++it) {
       const uint32_t s = it & 1;
       const uint32_t acc = tmem_base + s * Cfg::kAccCols;
-      mbar_wait(bar_acc_empty + 8 * s, ((it >> 1) & 1) ^ 1);
+      mbar_wait_warp(bar_acc_empty + 8 * s, ((it >> 1) & 1) ^ 1);
       tc_fence_after();
       for (int wq = 0; wq < NW; ++wq) {
         // window part used by weight k-step wq; SPLIT3 order per 16-channel group: (hi,w_hi) (hi,w_lo) (lo,w_hi)
         const int q = SPLIT3 ? ((wq % 3) < 2 ? wq / 3 : KSTEPS + wq / 3) : wq;
         const bool first_use = !SPLIT3 || (wq % 3) != 1;
         const bool last_use = !SPLIT3 || (wq % 3) != 0;
-        if (first_use) mbar_wait(bar_in_full + 8 * q, it & 1);
+        if (first_use) mbar_wait_warp(bar_in_full + 8 * q, it & 1);
         const uint64_t adesc_q = adesc0 + static_cast<uint64_t>((q * Cfg::kPartBytes) >> 4);
         uint32_t tap_off = 0;            // (dy * kRowPitch + dx * 16) >> 4, advanced incrementally
         uint32_t dx = 0;
         for (int sg = 0; sg < Cfg::kStagesPerKstep; ++sg) {
-          mbar_wait(bar_w_full + 8 * st, ph);
+          mbar_wait_warp(bar_w_full + 8 * st, ph);
           tc_fence_after();
           const uint64_t bdesc_st = bdesc0 + static_cast<uint64_t>((st * Cfg::kStageBytes) >> 4);
 #pragma unroll

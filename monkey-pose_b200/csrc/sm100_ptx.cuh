@@ -51,8 +51,27 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking probe: has the phase with this parity completed?  Used to overlap a barrier's round trip
+// with independent work (the result is only consumed one pipeline step later).
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// Same, for a warp that waits convergently: the vote makes the loop condition warp-uniform, which lets
+// the compiler keep loop-carried state of the surrounding code in uniform registers.
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+  while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
   }
 }
 
