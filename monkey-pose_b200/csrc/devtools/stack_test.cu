@@ -34,11 +34,18 @@ int run_case(int N, int H, int W, int k, int grid_override, int iters) {
   for (auto& v : in) v = bf16r((rand() / (float)RAND_MAX) * 2.f - 1.f);
   for (auto& v : w) v = bf16r(((rand() / (float)RAND_MAX) * 2.f - 1.f) * 0.05f);
   for (int c = 0; c < k; ++c) bias[c] = (rand() / (float)RAND_MAX) - 0.5f;
-  std::vector<__nv_bfloat16> act((size_t)N * CG * H * W * 8, __float2bfloat16(0.f));
-  for (int n = 0; n < N; ++n) for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) for (int c = 0; c < k; ++c)
-    act[((((size_t)n * CG + c / 8) * H + y) * W + x) * 8 + (c % 8)] = __float2bfloat16(in[(((size_t)n * H + y) * W + x) * k + c]);
+  const int PADR = Cfg::ACT_PAD, HA = H + PADR;     // remainder-packed operand layout (StackCfg::REM)
+  std::vector<__nv_bfloat16> act((size_t)N * CG * HA * W * 8, __float2bfloat16(0.f));
+  for (int n = 0; n < N; ++n) for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) for (int c = 0; c < k; ++c) {
+    const __nv_bfloat16 v = __float2bfloat16(in[(((size_t)n * H + y) * W + x) * k + c]);
+    if (Cfg::REM && c / 8 == CG - 1) {
+      if (c % 8 == 0) for (int j = 0; j < 8; ++j) act[((((size_t)n * CG + CG - 1) * HA + (y + PADR - j)) * W + x) * 8 + j] = v;
+    } else {
+      act[((((size_t)n * CG + c / 8) * HA + y + PADR) * W + x) * 8 + (c % 8)] = v;
+    }
+  }
   float *d_in, *d_w, *d_bias, *d_ref, *d_out; __nv_bfloat16 *d_act, *d_wpk;
-  size_t wpk_elems = (size_t)15 * Cfg::KSTEPS * Cfg::NG * 2 * 128 * 8;
+  size_t wpk_elems = (size_t)Cfg::PASS_STAGES * Cfg::NG * 2 * 128 * 8;
   CK(cudaMalloc(&d_in, in.size() * 4)); CK(cudaMalloc(&d_w, w.size() * 4)); CK(cudaMalloc(&d_bias, KP * 4));
   CK(cudaMalloc(&d_ref, npix * k * 4)); CK(cudaMalloc(&d_out, npix * KP * 4));
   CK(cudaMalloc(&d_act, act.size() * 2)); CK(cudaMalloc(&d_wpk, wpk_elems * 2));
@@ -47,14 +54,15 @@ int run_case(int N, int H, int W, int k, int grid_override, int iters) {
   CK(cudaMemcpy(d_bias, bias.data(), KP * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_act, act.data(), act.size() * 2, cudaMemcpyHostToDevice));
   CK(cudaMemset(d_out, 0xFF, npix * KP * 4));
-  hgru::pack_weights_stack_kernel<<<(unsigned)((wpk_elems + 255) / 256), 256>>>(d_w, d_wpk, k, Cfg::KSTEPS, T, KC, Cfg::NG, CS);
+  if (Cfg::REM) hgru::pack_weights_stack_rem_kernel<<<(unsigned)((wpk_elems + 255) / 256), 256>>>(d_w, d_wpk, k, T, KC, Cfg::NG);
+  else hgru::pack_weights_stack_kernel<<<(unsigned)((wpk_elems + 255) / 256), 256>>>(d_w, d_wpk, k, Cfg::KSTEPS, T, KC, Cfg::NG, CS);
   CK(cudaDeviceSynchronize());
   CUtensorMap map;
-  if (hgru::make_act_tensor_map(&map, d_act, N, CG, H, W, Cfg::COLS, Cfg::ROWS, CG)) { printf("map fail\n"); return 1; }
+  if (hgru::make_act_tensor_map(&map, d_act, N, CG, HA, W, Cfg::COLS, Cfg::ROWS, CG)) { printf("map fail\n"); return 1; }
   CUtensorMap wmap;
   if (hgru::make_rows256_map(&wmap, d_wpk, wpk_elems * 2, Cfg::STAGE_ROWS)) { printf("wmap fail\n"); return 1; }
   hgru::TcConvArgs a{};
-  a.N = N; a.H = H; a.W = W; a.KP = KP; a.kreal = k;
+  a.N = N; a.H = H; a.W = W; a.KP = KP; a.kreal = k; a.act_pad = PADR;
   a.units_x = (W + 63) / 64; a.units_y = (H + 15) / 16; a.num_units = N * a.units_x * a.units_y;
   a.wpk = d_wpk; a.bias = d_bias; a.out = d_out;
   auto kern = hgru::hconv_stack_kernel<KP, T, KC, CS, hgru::EpiBias>;
@@ -62,7 +70,7 @@ int run_case(int N, int H, int W, int k, int grid_override, int iters) {
   int sms = 0; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
   int grid = grid_override > 0 ? grid_override : (a.num_units < sms ? a.num_units : sms);
   grid = (grid + CS - 1) / CS * CS;
-  cudaLaunchConfig_t cfg{}; cfg.gridDim = dim3(grid); cfg.blockDim = dim3(384); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cudaLaunchConfig_t cfg{}; cfg.gridDim = dim3(grid); cfg.blockDim = dim3(Cfg::NTHREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   CK(cudaLaunchKernelEx(&cfg, kern, map, wmap, a));
@@ -111,16 +119,17 @@ void time_real_epilogue(const char* name, int N, int H, int W, int k, int gate =
   const int CG = KP / 8;
   size_t npix = (size_t)N * H * W;
   float *X, *H1, *G, *H2, *vec; __nv_bfloat16 *act, *actout, *wpk;
-  size_t wpk_elems = (size_t)15 * Cfg::KSTEPS * Cfg::NG * 2 * 128 * 8;
+  size_t wpk_elems = (size_t)Cfg::PASS_STAGES * Cfg::NG * 2 * 128 * 8;
+  const int HA = H + Cfg::ACT_PAD; const size_t actb = (size_t)N * CG * HA * W * 8 * 2;
   CK(cudaMalloc(&X, npix * KP * 4)); CK(cudaMalloc(&H1, npix * KP * 4)); CK(cudaMalloc(&G, npix * KP * 4)); CK(cudaMalloc(&H2, npix * KP * 4));
-  CK(cudaMalloc(&vec, 8 * KP * 4)); CK(cudaMalloc(&act, npix * KP * 2)); CK(cudaMalloc(&actout, npix * KP * 2)); CK(cudaMalloc(&wpk, wpk_elems * 2));
+  CK(cudaMalloc(&vec, 8 * KP * 4)); CK(cudaMalloc(&act, actb)); CK(cudaMalloc(&actout, actb)); CK(cudaMalloc(&wpk, wpk_elems * 2));
   CK(cudaMemset(X, 0, npix * KP * 4)); CK(cudaMemset(H1, 0, npix * KP * 4)); CK(cudaMemset(G, 0, npix * KP * 4)); CK(cudaMemset(H2, 0, npix * KP * 4));
-  CK(cudaMemset(vec, 0, 8 * KP * 4)); CK(cudaMemset(act, 0, npix * KP * 2)); CK(cudaMemset(wpk, 0, wpk_elems * 2));
+  CK(cudaMemset(vec, 0, 8 * KP * 4)); CK(cudaMemset(act, 0, actb)); CK(cudaMemset(actout, 0, actb)); CK(cudaMemset(wpk, 0, wpk_elems * 2));
   CUtensorMap map, wmap;
-  hgru::make_act_tensor_map(&map, act, N, CG, H, W, Cfg::COLS, Cfg::ROWS, CG);
+  hgru::make_act_tensor_map(&map, act, N, CG, HA, W, Cfg::COLS, Cfg::ROWS, CG);
   hgru::make_rows256_map(&wmap, wpk, wpk_elems * 2, Cfg::STAGE_ROWS);
   hgru::TcConvArgs a{};
-  a.N = N; a.H = H; a.W = W; a.KP = KP; a.kreal = k;
+  a.N = N; a.H = H; a.W = W; a.KP = KP; a.kreal = k; a.act_pad = Cfg::ACT_PAD;
   a.units_x = (W + 63) / 64; a.units_y = (H + 15) / 16; a.num_units = N * a.units_x * a.units_y;
   a.wpk = wpk; a.bias = vec; a.v0 = vec + KP; a.v1 = vec + 2 * KP; a.v2 = vec + 3 * KP; a.rho_t = vec + 4 * KP;
   a.X = X; a.H1 = H1; a.G = G; a.H2 = H2; a.out = H1; a.out_bf16 = actout;
@@ -130,7 +139,7 @@ void time_real_epilogue(const char* name, int N, int H, int W, int k, int gate =
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   CK(cudaFuncSetAttribute(kern_prof, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   int grid = 148;
-  cudaLaunchConfig_t cfg{}; cfg.gridDim = dim3(grid); cfg.blockDim = dim3(384); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cudaLaunchConfig_t cfg{}; cfg.gridDim = dim3(grid); cfg.blockDim = dim3(Cfg::NTHREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   long long* d_prof; CK(cudaMalloc(&d_prof, grid * 8 * sizeof(long long))); CK(cudaMemset(d_prof, 0, grid * 8 * sizeof(long long)));

@@ -28,7 +28,7 @@
 // (cp.async.bulk.tensor ... cta_group::2), the peer's epilogue threads arrive there remotely, and
 // the leader's commits are multicast back to both CTAs.
 //
-// Warps: w0 weight producer, w1 MMA issuer, w2 TMEM alloc, w3 window producer, w4..7 epilogue.
+// Warps: w0 weight producer, w1 MMA issuer, w2 TMEM alloc, w3 window producer, w4.. epilogue warpgroups.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -53,20 +53,31 @@ struct StackCfg {
   static constexpr int CHUNK_PITCH = ROWS * ROW_PITCH;
   static constexpr int WIN_BYTES = CG * CHUNK_PITCH;
   static constexpr int MIN_COL = T - 16;                  // image column of window column 0, minus x0
-  static constexpr int CSPLIT = KP / 2;                   // channels [0,CSPLIT) -> epilogue group A, rest -> group B
-  static constexpr int NTHREADS = 384;                    // 4 service warps + 2 x 4 epilogue warps
+  // Epilogue warpgroups split each tile's channels in 8-channel chunks (the last group takes the rest): the
+  // epilogue is latency-bound per thread, so more, lighter warps per SM sub-partition is what speeds it up.
+  static constexpr int NGRP = (KC > 16) ? 3 : 2;
+  static constexpr int NEPI = 128 * NGRP;                 // epilogue threads
+  static constexpr int NTHREADS = 128 + NEPI;             // 4 service warps + NGRP x 4 epilogue warps
   static constexpr int NLOC = NPAD / CS;                  // B rows held by one CTA
   static constexpr int BLK_BYTES = 2 * NLOC * 16;         // one CTA's part of a (dy, q, g) weight block
   static constexpr int STAGE_BYTES = NG * BLK_BYTES;      // all tap groups of one (dy, q), per CTA
-  static constexpr int PASS_STAGES = S * KSTEPS;          // stages per tile pair
+  // Remainder packing (k = 25 = 3 full 8-channel chunks + ONE channel): instead of padding K to 32 for every
+  // filter row, the last channel is stored as a plane whose 8 "channels" are that channel at 8 consecutive
+  // rows, P[y][x][j] = in[y + j][x][c = 24] (written that way by the producing epilogues, 7 pad rows on top).
+  // One K = 16 step then covers all 15 filter rows of that channel, and chunk 2 pairs up across filter rows:
+  // 15 + 7 + 1 + 1 = 24 weight stages per tile pair instead of 30 -- a fifth fewer MMAs for the same result.
+#ifdef HGRU_STACK_NO_REM
+  static constexpr bool REM = false;      // development switch: A/B against the plain K schedule
+#else
+  static constexpr bool REM = (CS == 1) && (KC == 25) && (KP == 32);
+#endif
+  static constexpr int ACT_PAD = REM ? 7 : 0;             // zero rows on top of every operand chunk plane
+  static constexpr int PASS_STAGES = REM ? (S + S / 2 + 2) : S * KSTEPS;   // weight stages per tile pair
   static constexpr int GATE_A_BYTES = CG * 128 * 16;      // staging tile of the new state (bf16, K-major)
   static constexpr int GATE_W_BYTES = KSTEPS * 2 * KP * 16;
   static constexpr int GATE_BYTES = GATE_A_BYTES + GATE_W_BYTES;
   // ring depth: as deep as the 227 KB allow (pair mode: half-size stages)
   static constexpr int WSTAGES = (CS == 2) ? 8 : ((WIN_BYTES + GATE_BYTES + 4 * NG * 2 * NPAD * 16 + 2048 <= 232448) ? 4 : 3);
-  // stages the MMA issuer awaits with one barrier round trip.  2 (a whole filter row) measured 2 % slower
-  // than 1 on B200 (the ring then runs out of slack), so every stage is awaited on its own.
-  static constexpr int WGROUP = 1;
   static constexpr int NUM_BARS = 2 + 2 * WSTAGES + 8 + 1;
   static constexpr int STAGE_ROWS = STAGE_BYTES / 256;    // rows of the 256-byte weight view per stage
   static constexpr int SMEM_BYTES = WIN_BYTES + WSTAGES * STAGE_BYTES + GATE_BYTES + NUM_BARS * 8 + 16 + 1024;
@@ -104,6 +115,36 @@ __global__ void pack_weights_stack_kernel(const float* __restrict__ w, __nv_bflo
   wpk[i] = __float2bfloat16(v);
 }
 
+// Same for the remainder-packed schedule (StackCfg::REM, KC = 25): [stage 24][g][2 chunks][128 n'][8 j] with the
+// K elements of a stage drawn from
+//   stage dy        (0..14): chunk 0 = channels 0..7, chunk 1 = channels 8..15 of filter row dy
+//   stage 15 + i    (0..6) : chunks = channels 16..23 of filter rows 2i and 2i + 1
+//   stage 22               : chunk 0 = channels 16..23 of row 14, chunk 1 = channel 24 of rows 0..7
+//   stage 23               : chunk 0 = channel 24 of rows 8..14 (+ one zero), chunk 1 = zero
+__global__ void pack_weights_stack_rem_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wpk, int k,
+                                              int T, int KC, int NG) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  const size_t total = static_cast<size_t>(24) * NG * 2 * 128 * 8;
+  if (i >= total) return;
+  const int j = i & 7;
+  size_t r = i >> 3;
+  const int np = r % 128; r /= 128;
+  const int ch = r & 1; r >>= 1;
+  const int g = r % NG;
+  const int st = static_cast<int>(r / NG);
+  const int s = np / KC, c = np - s * KC;
+  const int dx = T * g + T - 1 - s;
+  int dy = -1, ci = -1;
+  if (st < 15) { dy = st; ci = ch * 8 + j; }
+  else if (st < 22) { dy = 2 * (st - 15) + ch; ci = 16 + j; }
+  else if (st == 22) { if (ch == 0) { dy = 14; ci = 16 + j; } else { dy = j; ci = 24; } }
+  else if (ch == 0 && 8 + j < 15) { dy = 8 + j; ci = 24; }
+  float v = 0.f;
+  if (dy >= 0 && s < T && dx >= 0 && dx < 15 && c < k && ci < k)
+    v = w[((static_cast<size_t>(dy) * 15 + dx) * k + ci) * k + c];
+  wpk[i] = __float2bfloat16(v);
+}
+
 namespace detail {
 template <int N>
 __device__ __forceinline__ void tmem_ld_f(uint32_t taddr, float* v);
@@ -131,6 +172,39 @@ __device__ __forceinline__ void tmem_ld_f<1>(uint32_t taddr, float* v) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(u) : "r"(taddr));
   sm100::tmem_ld_wait();
   v[0] = __uint_as_float(u);
+}
+// Issue-only variants (no tcgen05.wait::ld): the caller batches several loads behind one wait.
+template <int N>
+__device__ __forceinline__ void tmem_ld_issue(uint32_t taddr, uint32_t* u);
+template <>
+__device__ __forceinline__ void tmem_ld_issue<16>(uint32_t taddr, uint32_t* u) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+        "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+      : "r"(taddr));
+}
+template <>
+__device__ __forceinline__ void tmem_ld_issue<8>(uint32_t taddr, uint32_t* u) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+               : "r"(taddr));
+}
+template <>
+__device__ __forceinline__ void tmem_ld_issue<1>(uint32_t taddr, uint32_t* u) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(u[0]) : "r"(taddr));
+}
+template <int CN>
+__device__ __forceinline__ void tmem_ld_range_issue(uint32_t taddr, uint32_t (&u)[CN]) {
+  static_assert(CN == 8 || CN == 9 || CN == 16, "supported channel-range widths");
+  if constexpr (CN == 16) {
+    tmem_ld_issue<16>(taddr, u);
+  } else if constexpr (CN == 8) {
+    tmem_ld_issue<8>(taddr, u);
+  } else {
+    tmem_ld_issue<8>(taddr, u);
+    tmem_ld_issue<1>(taddr + 8, u + 8);
+  }
 }
 // KC consecutive fp32 columns of this thread's TMEM lane
 template <int KC>
@@ -201,48 +275,52 @@ __device__ __forceinline__ void stack_mma_issuer(const TcConvArgs& a, uint32_t t
       tc_fence_after();
       const uint32_t acc0 = tmem_base + s0 * Cfg::NPAD, acc1 = tmem_base + s1 * Cfg::NPAD;
       const uint64_t a_tile0 = adesc0 + static_cast<uint64_t>(8 * j0);      // 8 pixels = 8 x 16 B
-      // stage order: filter row dy, then k-step q
-      for (int dy = 0; dy < Cfg::S; ++dy) {
-        constexpr int GRP = Cfg::WGROUP;
+      // one weight stage: wait for it, NG tap groups x (1 or 2) tiles, release it
+      auto issue_stage = [&](uint64_t adesc_st, bool first) {
+        if constexpr (PROF) t0 = clock64();
+        mbar_wait_warp(bar_w_full + 8 * st, ph);
+        if constexpr (PROF) t_w += clock64() - t0;
+        tc_fence_after();
+        if (leader) {
+          const uint64_t bdesc_st = bdesc0 + static_cast<uint64_t>((st * Cfg::STAGE_BYTES) >> 4);
 #pragma unroll
-        for (int q0 = 0; q0 < Cfg::KSTEPS; q0 += GRP) {
-          if constexpr (PROF) t0 = clock64();
-          if constexpr (GRP == 2) {
-            while (!__all_sync(0xffffffffu, mbar_try_wait(bar_w_full + 8 * st, ph) &
-                                                mbar_try_wait(bar_w_full + 8 * (st + 1), ph))) {
-            }
-          } else {
-            mbar_wait_warp(bar_w_full + 8 * st, ph);
-          }
-          if constexpr (PROF) t_w += clock64() - t0;
-          tc_fence_after();
-          if (leader) {
-#pragma unroll
-            for (int qq = 0; qq < GRP; ++qq) {
-              const int q = q0 + qq;
-              const uint64_t bdesc_st = bdesc0 + static_cast<uint64_t>(((st + qq) * Cfg::STAGE_BYTES) >> 4);
-              const uint64_t adesc_st =
-                  a_tile0 + static_cast<uint64_t>((dy * Cfg::ROW_PITCH + q * 2 * Cfg::CHUNK_PITCH) >> 4);
-#pragma unroll
-              for (int g = 0; g < Cfg::NG; ++g) {
-                const uint64_t bdesc = bdesc_st + static_cast<uint64_t>((g * Cfg::BLK_BYTES) >> 4);
-                const uint64_t adesc = adesc_st + static_cast<uint64_t>(T * g);
-                const uint32_t accum = (dy | q | g) != 0;
-                if constexpr (CS > 1) {
-                  mma_bf16_ss_2cta(acc0, adesc, bdesc, idesc, accum);
-                  if (two) mma_bf16_ss_2cta(acc1, adesc + 8, bdesc, idesc, accum);
-                } else {
-                  mma_bf16_ss(acc0, adesc, bdesc, idesc, accum);
-                  if (two) mma_bf16_ss(acc1, adesc + 8, bdesc, idesc, accum);
-                }
-              }
-              // release the weight stage when these MMAs have read it
-              if constexpr (CS > 1) tc_commit_2cta(bar_w_empty + 8 * (st + qq), kMask);
-              else tc_commit(bar_w_empty + 8 * (st + qq));
+          for (int g = 0; g < Cfg::NG; ++g) {
+            const uint64_t bdesc = bdesc_st + static_cast<uint64_t>((g * Cfg::BLK_BYTES) >> 4);
+            const uint64_t adesc = adesc_st + static_cast<uint64_t>(T * g);
+            const uint32_t accum = (!first || g != 0) ? 1u : 0u;
+            if constexpr (CS > 1) {
+              mma_bf16_ss_2cta(acc0, adesc, bdesc, idesc, accum);
+              if (two) mma_bf16_ss_2cta(acc1, adesc + 8, bdesc, idesc, accum);
+            } else {
+              mma_bf16_ss(acc0, adesc, bdesc, idesc, accum);
+              if (two) mma_bf16_ss(acc1, adesc + 8, bdesc, idesc, accum);
             }
           }
-          st += GRP;
-          if (st == Cfg::WSTAGES) { st = 0; ph ^= 1; }
+          // release the weight stage when these MMAs have read it
+          if constexpr (CS > 1) tc_commit_2cta(bar_w_empty + 8 * st, kMask);
+          else tc_commit(bar_w_empty + 8 * st);
+        }
+        if (++st == Cfg::WSTAGES) { st = 0; ph ^= 1; }
+      };
+      if constexpr (Cfg::REM) {
+        // remainder-packed K schedule (see StackCfg::REM / pack_weights_stack_rem_kernel); the K = 16 chunk
+        // pair of a stage is (start address, LBO): any two 16-byte pixel columns of the resident window
+        constexpr uint32_t RP = Cfg::ROW_PITCH, CP = Cfg::CHUNK_PITCH;
+        const uint64_t tile_off = static_cast<uint64_t>(8 * j0);
+        const uint64_t dB = make_smem_desc(win + 2 * CP, RP, RP) + tile_off;                  // chunk 2 @ dy, dy+1
+        const uint64_t dC = make_smem_desc(win + 2 * CP + 14 * RP, CP - 14 * RP, RP) + tile_off;   // chunk 2 @ 14 | P @ 0
+        const uint64_t dD = make_smem_desc(win + 3 * CP + 8 * RP, RP, RP) + tile_off;         // P @ 8 | (zero weights)
+        for (int dy = 0; dy < Cfg::S; ++dy) issue_stage(a_tile0 + static_cast<uint64_t>((dy * RP) >> 4), dy == 0);
+        for (int i = 0; i < Cfg::S / 2; ++i) issue_stage(dB + static_cast<uint64_t>((2 * i * RP) >> 4), false);
+        issue_stage(dC, false);
+        issue_stage(dD, false);
+      } else {
+        // stage order: filter row dy, then k-step q
+        for (int dy = 0; dy < Cfg::S; ++dy) {
+#pragma unroll
+          for (int q = 0; q < Cfg::KSTEPS; ++q)
+            issue_stage(a_tile0 + static_cast<uint64_t>((dy * Cfg::ROW_PITCH + q * 2 * Cfg::CHUNK_PITCH) >> 4),
+                        (dy | q) == 0);
         }
       }
       if (leader) {
@@ -310,30 +388,29 @@ __device__ __forceinline__ void stack_epilogue(const TcConvArgs& a, uint32_t tme
       const bool store = valid && j >= 1 && y < a.H && x < a.W;
       const size_t pin = static_cast<size_t>(y) * a.W + x;
       typename Epi::template Pre<NCH> pre;
-      if (store) Epi::template load<NCH>(a, n, pin, C0, pre);
+      if (store) Epi::template load<NCH, CN>(a, n, pin, C0, pre);
       if constexpr (PROF) e0 = clock64();
       mbar_wait(bar_acc_full + 8 * slot, (tc >> 2) & 1);
       if constexpr (PROF) e_wait += clock64() - e0;
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + slot * Cfg::NPAD + C0;
       float out[NCH], nxt[CN];
-      {
-        float blk[CN];
-        detail::tmem_ld_range<CN>(taddr, blk);
+      // all T tap slots of this thread's channels: loads issued back to back behind ONE wait
+      uint32_t blk[T][CN];
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) out[c] = (c < CN) ? blk[c < CN ? c : 0] + carry[c < CN ? c : 0] : 0.f;
-      }
+      for (int s = 0; s < T; ++s) detail::tmem_ld_range_issue<CN>(taddr + s * KC, blk[s]);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) out[c] = (c < CN) ? __uint_as_float(blk[0][c < CN ? c : 0]) + carry[c < CN ? c : 0] : 0.f;
 #pragma unroll
       for (int c = 0; c < CN; ++c) nxt[c] = 0.f;
 #pragma unroll
       for (int s = 1; s < T; ++s) {
-        float blk[CN];
-        detail::tmem_ld_range<CN>(taddr + s * KC, blk);
         const int src = (lane & ~7) | ((pcol - s) & 7);
         const bool own = pcol >= s;
 #pragma unroll
         for (int c = 0; c < CN; ++c) {
-          const float v = __shfl_sync(0xffffffffu, blk[c], src);
+          const float v = __uint_as_float(__shfl_sync(0xffffffffu, blk[s][c], src));
           if (own) out[c] += v; else nxt[c] += v;
         }
       }
@@ -344,13 +421,13 @@ __device__ __forceinline__ void stack_epilogue(const TcConvArgs& a, uint32_t tme
         // accumulator drained: MMAs may reuse it (pair mode: the leader's barrier counts both CTAs)
         if (CS > 1 && crank != 0) mbar_arrive_cluster(lead_acc_empty + 8 * slot);
         else mbar_arrive(bar_acc_empty + 8 * slot);
-        if (store) Epi::template finish<NCH>(a, n, pin, C0, out, pre);
+        if (store) Epi::template finish<NCH, CN>(a, n, pin, C0, out, pre);
       } else {
         // ---- fused gate: new state -> bf16 staging tile -> 1x1 conv on the tensor core -> sigmoid ----
         float hv[NCH];
 #pragma unroll
         for (int c = 0; c < NCH; ++c) hv[c] = 0.f;
-        if (store) Epi::template finish<NCH>(a, n, pin, C0, out, pre, hv);
+        if (store) Epi::template finish<NCH, CN>(a, n, pin, C0, out, pre, hv);
         {
           uint8_t* stg = smem_raw + (gate_a - smem_u32(smem_raw));
 #pragma unroll
@@ -363,7 +440,7 @@ __device__ __forceinline__ void stack_epilogue(const TcConvArgs& a, uint32_t tme
         }
         fence_proxy_async();          // staging writes -> visible to the async (tensor core) proxy
         tc_fence_before();            // our tcgen05.ld of this accumulator precede the barrier
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(Cfg::NEPI) : "memory");
         if (warp == 4) {
           // the tile's own accumulator columns [0, KP) are free now: gate pre-activations land there
           const bool leader = elect_one();
@@ -389,7 +466,7 @@ __device__ __forceinline__ void stack_epilogue(const TcConvArgs& a, uint32_t tme
         tc_fence_before();
         if (CS > 1 && crank != 0) mbar_arrive_cluster(lead_acc_empty + 8 * slot);
         else mbar_arrive(bar_acc_empty + 8 * slot);
-        if (store) Epi::template gate<NCH>(a, n, pin, C0, gacc, hv);
+        if (store) Epi::template gate<NCH, CN>(a, n, pin, C0, gacc, hv);
       }
     }
   }
@@ -400,7 +477,7 @@ __device__ __forceinline__ void stack_epilogue(const TcConvArgs& a, uint32_t tme
 }
 
 template <int KP, int T, int KC, int CS, class Epi, bool PROF = false>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__((StackCfg<KP, T, KC, CS>::NTHREADS), 1)
 hconv_stack_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap w_map,
                    const TcConvArgs a) {
   using namespace sm100;
@@ -436,7 +513,7 @@ hconv_stack_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(bar_acc_full + 8 * i, 1);
-      mbar_init(bar_acc_empty + 8 * i, 256 * CS);     // 2 epilogue groups (pair mode: of both CTAs, at the leader)
+      mbar_init(bar_acc_empty + 8 * i, Cfg::NEPI * CS);     // all epilogue threads (pair mode: of both CTAs, at the leader)
     }
     mbar_init(bar_gate, 1);
     tma_prefetch_desc(&w_map);
@@ -451,7 +528,7 @@ hconv_stack_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
     // 1x1 gate weights -> shared memory (generic-proxy writes, made visible to the tensor core)
     const uint4* src = reinterpret_cast<const uint4*>(a.gate_wpk);
     uint8_t* dst = smem_raw + (gate_w - smem_u32(smem_raw));
-    for (int i = threadIdx.x - 128; i < Cfg::GATE_W_BYTES / 16; i += 256)
+    for (int i = threadIdx.x - 128; i < Cfg::GATE_W_BYTES / 16; i += Cfg::NEPI)
       reinterpret_cast<uint4*>(dst)[i] = __ldg(src + i);
     fence_proxy_async();
   }
@@ -510,10 +587,11 @@ hconv_stack_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
           if (crank == 0)
             mbar_arrive_expect_tx(bar_win_full, Cfg::WIN_BYTES * ((u + 1 < a.num_units) ? 2 : 1));
           tma_load_4d_2cta(win, &in_map, lead_win_full, 2 * (ux * 64 + Cfg::MIN_COL),
-                           uy * kTileRows - Cfg::PAD, 0, n);
+                           uy * kTileRows - Cfg::PAD + Cfg::ACT_PAD, 0, n);
         } else {
           mbar_arrive_expect_tx(bar_win_full, Cfg::WIN_BYTES);
-          tma_load_4d(win, &in_map, bar_win_full, 2 * (ux * 64 + Cfg::MIN_COL), uy * kTileRows - Cfg::PAD, 0, n);
+          tma_load_4d(win, &in_map, bar_win_full, 2 * (ux * 64 + Cfg::MIN_COL),
+                      uy * kTileRows - Cfg::PAD + Cfg::ACT_PAD, 0, n);
         }
         ++vit;
       }
@@ -525,15 +603,19 @@ hconv_stack_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
     stack_mma_issuer<Cfg, PROF>(a, tmem_base, win, w_buf, bar_win_full, bar_win_empty, bar_w_full, bar_w_empty,
                                 bar_acc_full, bar_acc_empty, iters, NT, npairs);
   } else if (warp >= 4) {
-    // ---------------- epilogue: two warpgroups, channels split at Cfg::CSPLIT ----------------
-    if (warp < 8)
-      stack_epilogue<Cfg, Epi, 0, Cfg::CSPLIT, PROF>(a, tmem_base, bar_acc_full, bar_acc_empty, crank, iters, NT,
-                                               units_per_frame, warp, lane, true, smem_raw, gate_a, gate_w,
-                                               bar_gate);
-    else
-      stack_epilogue<Cfg, Epi, Cfg::CSPLIT, KC - Cfg::CSPLIT, PROF>(a, tmem_base, bar_acc_full, bar_acc_empty, crank,
-                                                              iters, NT, units_per_frame, warp, lane, false,
-                                                              smem_raw, gate_a, gate_w, bar_gate);
+    // ---------------- epilogue: NGRP warpgroups, 8-channel chunks each, the last one takes the rest ----------
+#define HGRU_STACK_EPI(C0_, CN_, FIRST_)                                                                          \
+  stack_epilogue<Cfg, Epi, C0_, CN_, PROF>(a, tmem_base, bar_acc_full, bar_acc_empty, crank, iters, NT,           \
+                                           units_per_frame, warp, lane, FIRST_, smem_raw, gate_a, gate_w, bar_gate)
+    if constexpr (Cfg::NGRP == 3) {
+      if (warp < 8) HGRU_STACK_EPI(0, 8, true);
+      else if (warp < 12) HGRU_STACK_EPI(8, 8, false);
+      else HGRU_STACK_EPI(16, KC - 16, false);
+    } else {
+      if (warp < 8) HGRU_STACK_EPI(0, 8, true);
+      else HGRU_STACK_EPI(8, KC - 8, false);
+    }
+#undef HGRU_STACK_EPI
   }
 
   tc_fence_before();

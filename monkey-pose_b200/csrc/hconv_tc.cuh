@@ -97,6 +97,10 @@ struct TcConvArgs {
   int fc_kpad;
   long long* prof;          // optional per-CTA cycle counters (development; nullptr in production)
   int dbg_flags;            // development only: bit 0 = do not re-stream weights after the first ring fill
+  // bf16 operand tensors written by this launch (out_bf16 / gate_act_out) in the remainder-packed layout of
+  // the stacked kernel (StackCfg::REM): act_pad zero rows on top of every chunk plane, and the last chunk
+  // holds channel KP-8 at the 8 rows y..y+7.  0 = plain chunked layout.
+  int act_pad;
 };
 
 // fp32 state tensors of the tensor-core path are "quad-chunked": [n][c/4][y][x][4].  A thread owns
@@ -144,17 +148,37 @@ __device__ __forceinline__ void store_chunk_bf16(__nv_bfloat16* base, int KP, in
   __nv_bfloat16* o = base + ((static_cast<size_t>(n) * (KP >> 3) + cg) * HWp + pin) * 8;
   st_stream(o, *reinterpret_cast<const uint4*>(h));
 }
+// Operand store that honours TcConvArgs::act_pad (remainder-packed layout, see StackCfg::REM): chunk planes
+// have act_pad zero rows on top; the last chunk is the row-packed plane P[y][x][j] = v(y + j, x) of channel
+// KP - 8, so this pixel's value goes to the 8 planes rows y - j (j = 0..7), element j.
+__device__ __forceinline__ void store_act_chunk(const TcConvArgs& a, __nv_bfloat16* base, int n, int cg,
+                                                size_t pin, const float* r) {
+  if (a.act_pad == 0) {
+    store_chunk_bf16(base, a.KP, a.H * a.W, n, cg, pin, r);
+    return;
+  }
+  const size_t plane = static_cast<size_t>(a.H + a.act_pad) * a.W;
+  const size_t pp = pin + static_cast<size_t>(a.act_pad) * a.W;
+  if (cg != (a.KP >> 3) - 1) {
+    store_chunk_bf16(base, a.KP, static_cast<int>(plane), n, cg, pp, r);
+  } else {
+    __nv_bfloat16* o = base + ((static_cast<size_t>(n) * (a.KP >> 3) + cg) * plane + pp) * 8;
+    const __nv_bfloat16 v = __float2bfloat16(r[0]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j - static_cast<ptrdiff_t>(j) * a.W * 8] = v;
+  }
+}
 
 // ---- epilogue functors: consume one pixel's CO_PAD accumulators --------------------------------
 // out = acc + bias                       (P = conv + lateral_bias, hgru_module.py:657)
 struct EpiBias {
   static constexpr bool kGate = false;
   template <int NCH> struct Pre {};
-  template <int NCH>
+  template <int NCH, int NREAL = NCH>
   __device__ static __forceinline__ void load(const TcConvArgs&, int, size_t, int, Pre<NCH>&) {}
-  template <int NCH>
+  template <int NCH, int NREAL = NCH>
   __device__ static __forceinline__ void gate(const TcConvArgs&, int, size_t, int, const float*, const float*) {}
-  template <int NCH>
+  template <int NCH, int NREAL = NCH>
   __device__ static __forceinline__ void finish(const TcConvArgs& a, int n, size_t pin, int c0,
                                                 const float* acc, const Pre<NCH>&, float* = nullptr) {
 #pragma unroll
@@ -214,32 +238,38 @@ struct EpiH1 {
   static constexpr bool kGate = true;
   template <int NCH>
   struct Pre { float4 x[NCH / 4], h[NCH / 4]; };
-  template <int NCH>
+  // NREAL (compile time): channels [NREAL, NCH) of this range are layout padding -- never loaded, no math
+  template <int NCH, int NREAL = NCH>
   __device__ static __forceinline__ void load(const TcConvArgs& a, int n, size_t pin, int c0, Pre<NCH>& p) {
 #pragma unroll
     for (int i = 0; i < NCH / 4; ++i) {
-      const size_t o = quad_off(a, n, (c0 >> 2) + i, pin);
-      p.x[i] = ld_stream(a.X + o);
-      p.h[i] = ld_stream(a.H2 + o);
+      if (4 * i < NREAL) {
+        const size_t o = quad_off(a, n, (c0 >> 2) + i, pin);
+        p.x[i] = ld_stream(a.X + o);
+        p.h[i] = ld_stream(a.H2 + o);
+      } else {
+        p.x[i] = p.h[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
   }
   // mix gate on the tensor-core result of H1 *1x1 o_r (hgru_module.py:729-740): G2 = sigmoid(. + o_b)
-  template <int NCH>
+  template <int NCH, int NREAL = NCH>
   __device__ static __forceinline__ void gate(const TcConvArgs& a, int n, size_t pin, int c0, const float* gacc,
                                               const float*) {
 #pragma unroll
     for (int c = 0; c < NCH; c += 4) {
-      const float4 b = __ldg(reinterpret_cast<const float4*>(a.gate_bias + c0 + c));
-      float4 g = make_float4(fast_sigmoid(gacc[c] + b.x), fast_sigmoid(gacc[c + 1] + b.y),
-                             fast_sigmoid(gacc[c + 2] + b.z), fast_sigmoid(gacc[c + 3] + b.w));
-      if (c0 + c + 0 >= a.kreal) g.x = 0.f;
-      if (c0 + c + 1 >= a.kreal) g.y = 0.f;
-      if (c0 + c + 2 >= a.kreal) g.z = 0.f;
-      if (c0 + c + 3 >= a.kreal) g.w = 0.f;
-      st_stream(a.gate_out + quad_off(a, n, (c0 + c) >> 2, pin), g);
+      float g[4] = {0.f, 0.f, 0.f, 0.f};
+      if (c < NREAL) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(a.gate_bias + c0 + c));
+        const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (c + j < NREAL && c0 + c + j < a.kreal) g[j] = fast_sigmoid(gacc[c + j] + bv[j]);
+      }
+      st_stream(a.gate_out + quad_off(a, n, (c0 + c) >> 2, pin), make_float4(g[0], g[1], g[2], g[3]));
     }
   }
-  template <int NCH>
+  template <int NCH, int NREAL = NCH>
   __device__ static __forceinline__ void finish(const TcConvArgs& a, int n, size_t pin, int c0,
                                                 const float* acc, const Pre<NCH>& p, float* hout = nullptr) {
 #pragma unroll
@@ -247,22 +277,31 @@ struct EpiH1 {
       float r[8];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        const int i = (c >> 2) + h;
-        const float4 xv = p.x[i], hv = p.h[i];
-        const float4 lb = __ldg(reinterpret_cast<const float4*>(a.bias + c0 + c + 4 * h));
-        const float4 be = __ldg(reinterpret_cast<const float4*>(a.v0 + c0 + c + 4 * h));
-        const float4 nu = __ldg(reinterpret_cast<const float4*>(a.v1 + c0 + c + 4 * h));
-        r[4 * h + 0] = fast_tanh(xv.x - (be.x * hv.x + nu.x) * (acc[c + 4 * h + 0] + lb.x));
-        r[4 * h + 1] = fast_tanh(xv.y - (be.y * hv.y + nu.y) * (acc[c + 4 * h + 1] + lb.y));
-        r[4 * h + 2] = fast_tanh(xv.z - (be.z * hv.z + nu.z) * (acc[c + 4 * h + 2] + lb.z));
-        r[4 * h + 3] = fast_tanh(xv.w - (be.w * hv.w + nu.w) * (acc[c + 4 * h + 3] + lb.w));
+        const int i = (c >> 2) + h, cc = c0 + c + 4 * h;
+        const float xv[4] = {p.x[i].x, p.x[i].y, p.x[i].z, p.x[i].w};
+        const float hv[4] = {p.h[i].x, p.h[i].y, p.h[i].z, p.h[i].w};
+        float lbv[4] = {0.f, 0.f, 0.f, 0.f}, bev[4] = {0.f, 0.f, 0.f, 0.f}, nuv[4] = {0.f, 0.f, 0.f, 0.f};
+        if (c + 4 * h < NREAL) {     // per-channel parameters: one vector load per quad (zero padded)
+          const float4 lb = __ldg(reinterpret_cast<const float4*>(a.bias + cc));
+          const float4 be = __ldg(reinterpret_cast<const float4*>(a.v0 + cc));
+          const float4 nu = __ldg(reinterpret_cast<const float4*>(a.v1 + cc));
+          lbv[0] = lb.x; lbv[1] = lb.y; lbv[2] = lb.z; lbv[3] = lb.w;
+          bev[0] = be.x; bev[1] = be.y; bev[2] = be.z; bev[3] = be.w;
+          nuv[0] = nu.x; nuv[1] = nu.y; nuv[2] = nu.z; nuv[3] = nu.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          r[4 * h + j] = 0.f;
+          if (c + 4 * h + j < NREAL)
+            r[4 * h + j] = fast_tanh(xv[j] - (bev[j] * hv[j] + nuv[j]) * (acc[c + 4 * h + j] + lbv[j]));
+        }
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         if (c0 + c + j >= a.kreal) r[j] = 0.f;
       st_stream(a.out + quad_off(a, n, (c0 + c) >> 2, pin), make_float4(r[0], r[1], r[2], r[3]));
       st_stream(a.out + quad_off(a, n, ((c0 + c) >> 2) + 1, pin), make_float4(r[4], r[5], r[6], r[7]));
-      store_chunk_bf16(a.out_bf16, a.KP, a.H * a.W, n, (c0 + c) >> 3, pin, r);
+      store_act_chunk(a, a.out_bf16, n, (c0 + c) >> 3, pin, r);
       if (hout) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) hout[c + j] = r[j];
@@ -290,31 +329,43 @@ struct EpiH2 {
   static constexpr bool kGate = true;
   template <int NCH>
   struct Pre { float4 h1[NCH / 4], g[NCH / 4], h2[NCH / 4]; };
-  template <int NCH>
+  template <int NCH, int NREAL = NCH>
   __device__ static __forceinline__ void load(const TcConvArgs& a, int n, size_t pin, int c0, Pre<NCH>& p) {
 #pragma unroll
     for (int i = 0; i < NCH / 4; ++i) {
-      const size_t o = quad_off(a, n, (c0 >> 2) + i, pin);
-      p.h1[i] = ld_stream(a.H1 + o);
-      p.g[i] = ld_stream(a.G + o);
-      p.h2[i] = ld_stream_rw(a.H2 + o);
+      if (4 * i < NREAL) {
+        const size_t o = quad_off(a, n, (c0 >> 2) + i, pin);
+        p.h1[i] = ld_stream(a.H1 + o);
+        p.g[i] = ld_stream(a.G + o);
+        p.h2[i] = ld_stream_rw(a.H2 + o);
+      } else {
+        p.h1[i] = p.g[i] = p.h2[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
   }
   // input gate of the NEXT timestep on the tensor-core result of H2 *1x1 i_r (hgru_module.py:696-711):
   // G1 = sigmoid(. + i_b); gated operand = bf16(G1 . H2) for the next C1 conv.
-  template <int NCH>
+  template <int NCH, int NREAL = NCH>
   __device__ static __forceinline__ void gate(const TcConvArgs& a, int n, size_t pin, int c0, const float* gacc,
                                               const float* hv) {
 #pragma unroll
     for (int c = 0; c < NCH; c += 8) {
       float r[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        r[j] = fast_sigmoid(gacc[c + j] + __ldg(a.gate_bias + c0 + c + j)) * hv[c + j];   // pad channels: hv = 0
-      store_chunk_bf16(a.gate_act_out, a.KP, a.H * a.W, n, (c0 + c) >> 3, pin, r);
+      for (int h = 0; h < 2; ++h) {
+        float bv[4] = {0.f, 0.f, 0.f, 0.f};
+        if (c + 4 * h < NREAL) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(a.gate_bias + c0 + c + 4 * h));
+          bv[0] = b.x; bv[1] = b.y; bv[2] = b.z; bv[3] = b.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)   // pad channels: hv = 0
+          r[4 * h + j] = (c + 4 * h + j < NREAL) ? fast_sigmoid(gacc[c + 4 * h + j] + bv[j]) * hv[c + 4 * h + j] : 0.f;
+      }
+      store_act_chunk(a, a.gate_act_out, n, (c0 + c) >> 3, pin, r);
     }
   }
-  template <int NCH>
+  template <int NCH, int NREAL = NCH>
   __device__ static __forceinline__ void finish(const TcConvArgs& a, int n, size_t pin, int c0,
                                                 const float* acc, const Pre<NCH>& p, float* hout = nullptr) {
     const float rho = __ldg(a.rho_t);
@@ -325,19 +376,28 @@ struct EpiH2 {
       for (int h = 0; h < 2; ++h) {
         const int i = (c >> 2) + h, cc = c0 + c + 4 * h;
         const float4 h1 = p.h1[i], g = p.g[i], h2 = p.h2[i];
-        const float4 lb = __ldg(reinterpret_cast<const float4*>(a.bias + cc));
-        const float4 ga = __ldg(reinterpret_cast<const float4*>(a.v0 + cc));
-        const float4 ka = __ldg(reinterpret_cast<const float4*>(a.v1 + cc));
-        const float4 om = __ldg(reinterpret_cast<const float4*>(a.v2 + cc));
         const float h1v[4] = {h1.x, h1.y, h1.z, h1.w}, gv[4] = {g.x, g.y, g.z, g.w};
-        const float h2v[4] = {h2.x, h2.y, h2.z, h2.w}, lbv[4] = {lb.x, lb.y, lb.z, lb.w};
-        const float gav[4] = {ga.x, ga.y, ga.z, ga.w}, kav[4] = {ka.x, ka.y, ka.z, ka.w};
-        const float omv[4] = {om.x, om.y, om.z, om.w};
+        const float h2v[4] = {h2.x, h2.y, h2.z, h2.w};
+        float lbv[4] = {0.f, 0.f, 0.f, 0.f}, gav[4] = {0.f, 0.f, 0.f, 0.f}, kav[4] = {0.f, 0.f, 0.f, 0.f};
+        float omv[4] = {0.f, 0.f, 0.f, 0.f};
+        if (c + 4 * h < NREAL) {     // per-channel parameters: one vector load per quad (zero padded)
+          const float4 lb = __ldg(reinterpret_cast<const float4*>(a.bias + cc));
+          const float4 ga = __ldg(reinterpret_cast<const float4*>(a.v0 + cc));
+          const float4 ka = __ldg(reinterpret_cast<const float4*>(a.v1 + cc));
+          const float4 om = __ldg(reinterpret_cast<const float4*>(a.v2 + cc));
+          lbv[0] = lb.x; lbv[1] = lb.y; lbv[2] = lb.z; lbv[3] = lb.w;
+          gav[0] = ga.x; gav[1] = ga.y; gav[2] = ga.z; gav[3] = ga.w;
+          kav[0] = ka.x; kav[1] = ka.y; kav[2] = ka.z; kav[3] = ka.w;
+          omv[0] = om.x; omv[1] = om.y; omv[2] = om.z; omv[3] = om.w;
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float e = gav[j] * (acc[c + 4 * h + j] + lbv[j]);
-          const float ht = fast_tanh(kav[j] * (h1v[j] + e) + omv[j] * (h1v[j] * e));
-          r[4 * h + j] = (gv[j] * h2v[j] + (1.f - gv[j]) * ht) * rho;
+          r[4 * h + j] = 0.f;
+          if (c + 4 * h + j < NREAL) {
+            const float e = gav[j] * (acc[c + 4 * h + j] + lbv[j]);
+            const float ht = fast_tanh(kav[j] * (h1v[j] + e) + omv[j] * (h1v[j] * e));
+            r[4 * h + j] = (gv[j] * h2v[j] + (1.f - gv[j]) * ht) * rho;
+          }
         }
       }
 #pragma unroll

@@ -120,7 +120,7 @@ int dispatch_tc_stem(int KP, const CUtensorMap& map, const hgru::TcConvArgs& a, 
 #undef TC_CASE
 
 // ---------------------------------------------------------------- tap-stacked conv (k <= 32, S = 15)
-struct StackGeom { int T, KC, NG, ksteps, box_cols, box_rows; };
+struct StackGeom { int T, KC, NG, ksteps, box_cols, box_rows, stages, act_pad; };
 bool stack_geometry(int S, int KP, int k, StackGeom* g) {
   if (S != 15) return false;
   if (KP == 32 && k <= 25) { g->T = 5; g->KC = 25; }
@@ -131,6 +131,10 @@ bool stack_geometry(int S, int KP, int k, StackGeom* g) {
   g->ksteps = KP / 16;
   g->box_cols = 64 + g->T * (g->NG - 1) + 8;
   g->box_rows = hgru::kTileRows + 14;
+  // KC = 25: remainder-packed K schedule (hgru::StackCfg::REM) -- 24 weight stages, 7 pad rows per plane
+  const bool rem = hgru::StackCfg<32, 5, 25, 1>::REM && g->KC == 25;
+  g->stages = rem ? hgru::StackCfg<32, 5, 25, 1>::PASS_STAGES : 15 * g->ksteps;
+  g->act_pad = rem ? hgru::StackCfg<32, 5, 25, 1>::ACT_PAD : 0;
   return true;
 }
 
@@ -292,6 +296,7 @@ struct hgru_plan_s {
   int fc_kpad = 0;
   bool stacked = false;             // narrow layers: tap-stacked kernel (hconv_stack.cuh)
   int stack_T = 0;
+  int act_pad = 0;                  // pad rows of the bf16 operand planes (remainder-packed layout)
   KernelTimer timer;
   float* vec(int i) const { return vecs.as<float>() + static_cast<size_t>(i) * KP; }
   size_t workspace() const {
@@ -328,8 +333,6 @@ static int hgru_plan_init(hgru_plan_s* p, int N, int H, int W, int k, int S, int
     TcGeom g;
     if (!tc_geometry(S, p->KP, &g))
       return fail(HGRU_E_UNSUPPORTED, "hgru_plan_create: bf16 mode supports S in {1,3,5,7,15} and k <= 64");
-    const size_t ab = p->nelem * sizeof(__nv_bfloat16);
-    if ((rc = p->actA.alloc(ab)) || (rc = p->actH1.alloc(ab)) || (rc = p->actH2.alloc(ab))) return rc;
     const int ksteps = p->KP / 16;
     const size_t tapb = sizeof(__nv_bfloat16) * ksteps * 2 * p->KP * 8;
     StackGeom sg;
@@ -338,16 +341,24 @@ static int hgru_plan_init(hgru_plan_s* p, int N, int H, int W, int k, int S, int
     size_t wbytes = tapb * S * S;
     if (p->stacked) {
       p->stack_T = sg.T;
+      p->act_pad = sg.act_pad;
       box_cols = sg.box_cols; box_rows = sg.box_rows; box_chunks = p->CG;
-      wbytes = sizeof(__nv_bfloat16) * 15 * sg.ksteps * sg.NG * 2 * 128 * 8;
+      wbytes = sizeof(__nv_bfloat16) * sg.stages * sg.NG * 2 * 128 * 8;
     }
+    // operand planes carry act_pad zero rows on top in the remainder-packed layout; they (and the never
+    // written tail elements of the row-packed plane) must read as zero, so the buffers are cleared once
+    const int HA = H + p->act_pad;
+    const size_t ab = static_cast<size_t>(N) * p->CG * HA * W * 8 * sizeof(__nv_bfloat16);
+    if ((rc = p->actA.alloc(ab)) || (rc = p->actH1.alloc(ab)) || (rc = p->actH2.alloc(ab))) return rc;
+    CUDA_TRY(cudaMemset(p->actA.p, 0, ab));
+    CUDA_TRY(cudaMemset(p->actH1.p, 0, ab));
     if ((rc = p->wpk.alloc(wbytes)) || (rc = p->wpk_i.alloc(tapb)) || (rc = p->wpk_o.alloc(tapb))) return rc;
     TcGeom g1;
     tc_geometry(1, p->KP, &g1);
-    if (hgru::make_act_tensor_map(&p->mapA, p->actA.p, N, p->CG, H, W, box_cols, box_rows, box_chunks) ||
-        hgru::make_act_tensor_map(&p->mapH1, p->actH1.p, N, p->CG, H, W, box_cols, box_rows, box_chunks) ||
-        hgru::make_act_tensor_map(&p->mapH1_g, p->actH1.p, N, p->CG, H, W, g1.box_cols, g1.box_rows) ||
-        hgru::make_act_tensor_map(&p->mapH2_g, p->actH2.p, N, p->CG, H, W, g1.box_cols, g1.box_rows))
+    if (hgru::make_act_tensor_map(&p->mapA, p->actA.p, N, p->CG, HA, W, box_cols, box_rows, box_chunks) ||
+        hgru::make_act_tensor_map(&p->mapH1, p->actH1.p, N, p->CG, HA, W, box_cols, box_rows, box_chunks) ||
+        hgru::make_act_tensor_map(&p->mapH1_g, p->actH1.p, N, p->CG, HA, W, g1.box_cols, g1.box_rows) ||
+        hgru::make_act_tensor_map(&p->mapH2_g, p->actH2.p, N, p->CG, HA, W, g1.box_cols, g1.box_rows))
       return fail(HGRU_E_CUDA, "cuTensorMapEncodeTiled failed");
   }
   return 0;
@@ -380,9 +391,13 @@ static int hgru_set_params_impl(hgru_plan_s* p, const float* p_r, const float* i
     const size_t total = static_cast<size_t>(ksteps) * taps * 2 * KP * 8;
     StackGeom sg;
     if (p->stacked && stack_geometry(p->S, KP, k, &sg)) {
-      const size_t ts = static_cast<size_t>(15) * sg.ksteps * sg.NG * 2 * 128 * 8;
-      hgru::pack_weights_stack_kernel<<<nblk(ts), 256, 0, st>>>(p_r, p->wpk.as<__nv_bfloat16>(), k, sg.ksteps,
-                                                               sg.T, sg.KC, sg.NG, 1);
+      const size_t ts = static_cast<size_t>(sg.stages) * sg.NG * 2 * 128 * 8;
+      if (sg.act_pad)
+        hgru::pack_weights_stack_rem_kernel<<<nblk(ts), 256, 0, st>>>(p_r, p->wpk.as<__nv_bfloat16>(), k, sg.T,
+                                                                     sg.KC, sg.NG);
+      else
+        hgru::pack_weights_stack_kernel<<<nblk(ts), 256, 0, st>>>(p_r, p->wpk.as<__nv_bfloat16>(), k, sg.ksteps,
+                                                                 sg.T, sg.KC, sg.NG, 1);
     } else {
       hgru::pack_weights_kernel<<<nblk(total), 256, 0, st>>>(p_r, p->wpk.as<__nv_bfloat16>(), taps, k, ksteps, KP);
     }
@@ -457,6 +472,7 @@ static int hgru_run_bf16(hgru_plan_s* p, const float* Xp, const float* H2_init_n
   int rc;
   hgru::TcConvArgs base{};
   base.N = p->N; base.H = p->H; base.W = p->W; base.KP = KP; base.kreal = p->k;
+  base.act_pad = p->act_pad;
   // initial state O_0 (NHWC or zeros) -> H2 (quad-chunked fp32) + the first gated operand, one pass
   {
     static bool attr = false;
@@ -467,7 +483,7 @@ static int hgru_run_bf16(hgru_plan_s* p, const float* Xp, const float* H2_init_n
     const size_t smem = sizeof(float) * (KP * KP + 64 * (KP + 1));
     hgru::init_state_gate_kernel<<<nblk(p->npix, 64), 256, smem, st>>>(
         H2_init_nhwc, p->i_r.as<float>(), p->vec(V_IB), p->H2.as<float>(), p->actA.as<__nv_bfloat16>(), p->npix,
-        p->k, KP, HW);
+        p->k, KP, HW, p->W, p->act_pad);
     ++p->launches;
   }
   const bool fused = p->stacked;

@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(256)
 init_state_gate_kernel(const float* __restrict__ h0 /*[npix][k] or nullptr = zeros*/,
                        const float* __restrict__ wg /*[KP][KP]*/, const float* __restrict__ bg,
                        float* __restrict__ H2q, __nv_bfloat16* __restrict__ actA, size_t npix, int k, int KP,
-                       int HW) {
+                       int HW, int W, int act_pad /* remainder-packed operand layout, see StackCfg::REM */) {
   extern __shared__ float smem_f[];
   float* wsm = smem_f;                 // [KP][KP]
   float* xin = smem_f + KP * KP;       // [64][KP+1]
@@ -467,7 +467,21 @@ init_state_gate_kernel(const float* __restrict__ h0 /*[npix][k] or nullptr = zer
     float* o = H2q + ((n * (KP >> 2) + 2 * cg) * HW + pin) * 4;
     *reinterpret_cast<float4*>(o) = make_float4(hv.v[0], hv.v[1], hv.v[2], hv.v[3]);
     *reinterpret_cast<float4*>(o + static_cast<size_t>(HW) * 4) = make_float4(hv.v[4], hv.v[5], hv.v[6], hv.v[7]);
-    st8_bf16(chunk_ptr(actA, static_cast<int>(n), cg, pin, HW, CG), mv);
+    if (act_pad == 0) {
+      st8_bf16(chunk_ptr(actA, static_cast<int>(n), cg, pin, HW, CG), mv);
+    } else {
+      const int plane = HW + act_pad * W;
+      const size_t pp = pin + static_cast<size_t>(act_pad) * W;
+      if (cg != CG - 1) {
+        st8_bf16(chunk_ptr(actA, static_cast<int>(n), cg, pp, plane, CG), mv);
+      } else {
+        // last chunk = row-packed plane of channel KP - 8: element j of the pixel j rows above
+        __nv_bfloat16* o = chunk_ptr(actA, static_cast<int>(n), cg, pp, plane, CG);
+        const __nv_bfloat16 v = __float2bfloat16(mv.v[0]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j - static_cast<ptrdiff_t>(j) * W * 8] = v;
+      }
+    }
   }
 }
 
