@@ -21,6 +21,17 @@ __global__ void naive_conv(const float* in, const float* w, const float* bias, f
       for (int ci = 0; ci < k; ++ci) acc += ip[ci] * wp[(size_t)ci * k]; } }
   out[idx] = acc + bias[co];
 }
+__global__ void fill_f32(float* p, size_t n, float lo, float hi, unsigned seed) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
+  unsigned h = (unsigned)(i * 2654435761u) ^ seed; h ^= h << 13; h ^= h >> 17; h ^= h << 5;
+  p[i] = lo + (hi - lo) * (h & 0xFFFFFF) / 16777216.f;
+}
+__global__ void fill_bf16(__nv_bfloat16* p, size_t n, float lo, float hi, unsigned seed) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; if (i >= n) return;
+  unsigned h = (unsigned)(i * 2654435761u) ^ seed; h ^= h << 13; h ^= h >> 17; h ^= h << 5;
+  p[i] = __float2bfloat16(lo + (hi - lo) * (h & 0xFFFFFF) / 16777216.f);
+}
+static int g_random_data = 0;
 static float bf16r(float v) { return __bfloat162float(__float2bfloat16(v)); }
 
 template <int KP, int T, int KC, int CS>
@@ -95,7 +106,7 @@ int run_case(int N, int H, int W, int k, int grid_override, int iters) {
       putchar(!(o == o) ? 'N' : (fabs(o - r) > 1e-3 * (1 + fabs(r)) ? 'x' : '.')); } putchar('\n'); }
   }
   if (iters > 0 && !bad && !nan) {
-    long long* d_prof; CK(cudaMalloc(&d_prof, grid * 8 * sizeof(long long))); CK(cudaMemset(d_prof, 0, grid * 8 * sizeof(long long)));
+    long long* d_prof; CK(cudaMalloc(&d_prof, grid * 40 * sizeof(long long))); CK(cudaMemset(d_prof, 0, grid * 40 * sizeof(long long)));
     hgru::TcConvArgs ap = a; ap.prof = d_prof;
     CK(cudaLaunchKernelEx(&cfg, kern, map, wmap, ap)); CK(cudaDeviceSynchronize());
     std::vector<long long> pr(grid * 8); CK(cudaMemcpy(pr.data(), d_prof, grid * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
@@ -125,6 +136,15 @@ void time_real_epilogue(const char* name, int N, int H, int W, int k, int gate =
   CK(cudaMalloc(&vec, 8 * KP * 4)); CK(cudaMalloc(&act, actb)); CK(cudaMalloc(&actout, actb)); CK(cudaMalloc(&wpk, wpk_elems * 2));
   CK(cudaMemset(X, 0, npix * KP * 4)); CK(cudaMemset(H1, 0, npix * KP * 4)); CK(cudaMemset(G, 0, npix * KP * 4)); CK(cudaMemset(H2, 0, npix * KP * 4));
   CK(cudaMemset(vec, 0, 8 * KP * 4)); CK(cudaMemset(act, 0, actb)); CK(cudaMemset(actout, 0, actb)); CK(cudaMemset(wpk, 0, wpk_elems * 2));
+  if (g_random_data) {   // realistic operand / state values instead of zeros (switching power, real tanh inputs)
+    size_t ns = npix * KP;
+    fill_f32<<<(unsigned)((ns + 255) / 256), 256>>>(X, ns, -1.f, 1.f, 1u); fill_f32<<<(unsigned)((ns + 255) / 256), 256>>>(H1, ns, -1.f, 1.f, 2u);
+    fill_f32<<<(unsigned)((ns + 255) / 256), 256>>>(G, ns, 0.f, 1.f, 3u); fill_f32<<<(unsigned)((ns + 255) / 256), 256>>>(H2, ns, -1.f, 1.f, 4u);
+    fill_f32<<<(8 * KP + 255) / 256, 256>>>(vec, 8 * KP, 0.5f, 1.f, 5u);
+    fill_bf16<<<(unsigned)((actb / 2 + 255) / 256), 256>>>(act, actb / 2, -1.f, 1.f, 6u);
+    fill_bf16<<<(unsigned)((wpk_elems + 255) / 256), 256>>>(wpk, wpk_elems, -0.05f, 0.05f, 7u);
+    CK(cudaDeviceSynchronize());
+  }
   CUtensorMap map, wmap;
   hgru::make_act_tensor_map(&map, act, N, CG, HA, W, Cfg::COLS, Cfg::ROWS, CG);
   hgru::make_rows256_map(&wmap, wpk, wpk_elems * 2, Cfg::STAGE_ROWS);
@@ -142,19 +162,24 @@ void time_real_epilogue(const char* name, int N, int H, int W, int k, int gate =
   cudaLaunchConfig_t cfg{}; cfg.gridDim = dim3(grid); cfg.blockDim = dim3(Cfg::NTHREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  long long* d_prof; CK(cudaMalloc(&d_prof, grid * 8 * sizeof(long long))); CK(cudaMemset(d_prof, 0, grid * 8 * sizeof(long long)));
+  long long* d_prof; CK(cudaMalloc(&d_prof, grid * 40 * sizeof(long long))); CK(cudaMemset(d_prof, 0, grid * 40 * sizeof(long long)));
   hgru::TcConvArgs ap = a; ap.prof = d_prof;
   CK(cudaLaunchKernelEx(&cfg, kern_prof, map, wmap, ap)); CK(cudaDeviceSynchronize());
-  std::vector<long long> pr(grid * 8); CK(cudaMemcpy(pr.data(), d_prof, grid * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+  std::vector<long long> pr(grid * 40); CK(cudaMemcpy(pr.data(), d_prof, grid * 40 * sizeof(long long), cudaMemcpyDeviceToHost));
   double av[6] = {0, 0, 0, 0, 0, 0}; int nl = 0;
   for (int b = 0; b < grid; ++b) { if (pr[b * 8]) ++nl; for (int i = 0; i < 6; ++i) av[i] += pr[b * 8 + i]; }
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0);
-  for (int i = 0; i < 5; ++i) cudaLaunchKernelEx(&cfg, kern, map, wmap, a);
+  for (int i = 0; i < 20; ++i) cudaLaunchKernelEx(&cfg, kern, map, wmap, a);
   cudaEventRecord(e1); CK(cudaDeviceSynchronize());
-  float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 5;
+  float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 20;
   printf("%s gate=%d CS=%d: %.3f ms | leader avg cycles: mma_total=%.0f wait_win=%.0f wait_acc_empty=%.0f wait_w=%.0f | epi_total=%.0f epi_wait=%.0f\n", name, gate, CS, ms,
          av[0] / nl, av[1] / nl, av[2] / nl, av[3] / nl, av[4] / grid, av[5] / grid);
+  for (int g = 0; g < Cfg::NGRP; ++g) {
+    double ph[6] = {0, 0, 0, 0, 0, 0};
+    for (int b = 0; b < grid; ++b) for (int i = 0; i < 6; ++i) ph[i] += pr[grid * 8 + (b * Cfg::NGRP + g) * 8 + i] / (double)grid;
+    printf("    epilogue group %d: total=%.0f wait=%.0f tmem+unstack=%.0f finish=%.0f gate_wait=%.0f gate_math=%.0f\n", g, ph[0], ph[1], ph[2], ph[3], ph[4], ph[5]);
+  }
   cudaFree(X); cudaFree(H1); cudaFree(G); cudaFree(H2); cudaFree(vec); cudaFree(act); cudaFree(actout); cudaFree(wpk); cudaFree(d_prof);
 }
 
@@ -174,6 +199,14 @@ int main(int argc, char** argv) {
     time_real_epilogue<32, 5, 25, 1, hgru::EpiBias>("EpiBias noWstream", 256, 64, 64, 25, 0, 1);
     time_real_epilogue<32, 5, 25, 1, hgru::EpiH2>("EpiH2", 256, 64, 64, 25, 1, 0);
     time_real_epilogue<32, 5, 25, 1, hgru::EpiH2>("EpiH2 noWstream", 256, 64, 64, 25, 1, 1);
+  }
+  if (which == 22) {
+    for (g_random_data = 0; g_random_data < 2; ++g_random_data) {
+      printf("---- %s data\n", g_random_data ? "random" : "zero");
+      time_real_epilogue<32, 5, 25, 1, hgru::EpiBias>("EpiBias", 256, 64, 64, 25, 0);
+      time_real_epilogue<32, 5, 25, 1, hgru::EpiH1>("EpiH1", 256, 64, 64, 25, 1);
+      time_real_epilogue<32, 5, 25, 1, hgru::EpiH2>("EpiH2", 256, 64, 64, 25, 1);
+    }
   }
   if (which == 20) {
     time_real_epilogue<32, 5, 25, 1, hgru::EpiBias>("EpiBias", 256, 64, 64, 25, 0);

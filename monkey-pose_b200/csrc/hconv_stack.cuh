@@ -79,8 +79,10 @@ struct StackCfg {
   // ring depth: as deep as the 227 KB allow (pair mode: half-size stages)
   static constexpr int WSTAGES = (CS == 2) ? 8 : ((WIN_BYTES + GATE_BYTES + 4 * NG * 2 * NPAD * 16 + 2048 <= 232448) ? 4 : 3);
   static constexpr int NUM_BARS = 2 + 2 * WSTAGES + 8 + 1;
+  static constexpr int PAR_FLOATS = 5 * KP + 4;           // bias, v0, v1, v2, gate_bias (KP each) + rho_t
   static constexpr int STAGE_ROWS = STAGE_BYTES / 256;    // rows of the 256-byte weight view per stage
-  static constexpr int SMEM_BYTES = WIN_BYTES + WSTAGES * STAGE_BYTES + GATE_BYTES + NUM_BARS * 8 + 16 + 1024;
+  static constexpr int SMEM_BYTES =
+      WIN_BYTES + WSTAGES * STAGE_BYTES + GATE_BYTES + NUM_BARS * 8 + 32 + PAR_FLOATS * 4 + 1024;
   static_assert(T * KC <= NPAD, "stacked taps must fit N = 128");
   static_assert(KC <= KP && KP % 16 == 0, "channel padding");
   static_assert((CHUNK_PITCH >> 4) < 16384, "LBO range");
@@ -368,7 +370,7 @@ __device__ __forceinline__ void stack_epilogue(const TcConvArgs& a, uint32_t tme
   const int prow = m >> 3, pcol = m & 7;
   uint32_t tc = 0;
   const uint32_t lead_acc_empty = (CS > 1) ? mapa_cluster(bar_acc_empty, 0) : 0u;
-  long long e_wait = 0, e_begin = 0, e0 = 0;
+  long long e_wait = 0, e_begin = 0, e0 = 0, e_tm = 0, e_fin = 0, e_gw = 0, e_gm = 0;
   if constexpr (PROF) e_begin = clock64();
   for (int it = 0; it < iters; ++it) {
     const int u = it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);
@@ -391,7 +393,7 @@ __device__ __forceinline__ void stack_epilogue(const TcConvArgs& a, uint32_t tme
       if (store) Epi::template load<NCH, CN>(a, n, pin, C0, pre);
       if constexpr (PROF) e0 = clock64();
       mbar_wait(bar_acc_full + 8 * slot, (tc >> 2) & 1);
-      if constexpr (PROF) e_wait += clock64() - e0;
+      if constexpr (PROF) { const long long t = clock64(); e_wait += t - e0; e0 = t; }
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + slot * Cfg::NPAD + C0;
       float out[NCH], nxt[CN];
@@ -416,12 +418,14 @@ __device__ __forceinline__ void stack_epilogue(const TcConvArgs& a, uint32_t tme
       }
 #pragma unroll
       for (int c = 0; c < CN; ++c) carry[c] = nxt[c];
+      if constexpr (PROF) { const long long t = clock64(); e_tm += t - e0; e0 = t; }
       if (!(gated && j >= 1)) {
         tc_fence_before();
         // accumulator drained: MMAs may reuse it (pair mode: the leader's barrier counts both CTAs)
         if (CS > 1 && crank != 0) mbar_arrive_cluster(lead_acc_empty + 8 * slot);
         else mbar_arrive(bar_acc_empty + 8 * slot);
         if (store) Epi::template finish<NCH, CN>(a, n, pin, C0, out, pre);
+        if constexpr (PROF) { const long long t = clock64(); e_fin += t - e0; e0 = t; }
       } else {
         // ---- fused gate: new state -> bf16 staging tile -> 1x1 conv on the tensor core -> sigmoid ----
         float hv[NCH];
@@ -438,6 +442,7 @@ __device__ __forceinline__ void stack_epilogue(const TcConvArgs& a, uint32_t tme
             *reinterpret_cast<uint4*>(stg + ((C0 >> 3) + i) * 2048 + m * 16) = *reinterpret_cast<const uint4*>(h);
           }
         }
+        if constexpr (PROF) { const long long t = clock64(); e_fin += t - e0; e0 = t; }
         fence_proxy_async();          // staging writes -> visible to the async (tensor core) proxy
         tc_fence_before();            // our tcgen05.ld of this accumulator precede the barrier
         asm volatile("bar.sync 1, %0;" ::"n"(Cfg::NEPI) : "memory");
@@ -460,6 +465,7 @@ __device__ __forceinline__ void stack_epilogue(const TcConvArgs& a, uint32_t tme
         mbar_wait(bar_gate, gate_uses & 1);
         ++gate_uses;
         tc_fence_after();
+        if constexpr (PROF) { const long long t = clock64(); e_gw += t - e0; e0 = t; }
         float gacc[NCH];
 #pragma unroll
         for (int c = 0; c < NCH; c += 8) detail::tmem_ld_f<8>(taddr + c, gacc + c);   // columns C0 + c of the slot
@@ -467,12 +473,19 @@ __device__ __forceinline__ void stack_epilogue(const TcConvArgs& a, uint32_t tme
         if (CS > 1 && crank != 0) mbar_arrive_cluster(lead_acc_empty + 8 * slot);
         else mbar_arrive(bar_acc_empty + 8 * slot);
         if (store) Epi::template gate<NCH, CN>(a, n, pin, C0, gacc, hv);
+        if constexpr (PROF) { const long long t = clock64(); e_gm += t - e0; e0 = t; }
       }
     }
   }
-  if (PROF && profile && a.prof && (threadIdx.x & 127) == 0) {
-    long long* o = a.prof + static_cast<size_t>(blockIdx.x) * 8;
-    o[4] = clock64() - e_begin; o[5] = e_wait;
+  if (PROF && a.prof && (threadIdx.x & 127) == 0) {
+    if (profile) {
+      long long* o = a.prof + static_cast<size_t>(blockIdx.x) * 8;
+      o[4] = clock64() - e_begin; o[5] = e_wait;
+    }
+    // per-warpgroup phase split, after the per-CTA records: [total, wait, tmem+unstack, finish, gate wait, gate math]
+    long long* g = a.prof + static_cast<size_t>(gridDim.x) * 8 +
+                   (static_cast<size_t>(blockIdx.x) * Cfg::NGRP + ((warp - 4) >> 2)) * 8;
+    g[0] = clock64() - e_begin; g[1] = e_wait; g[2] = e_tm; g[3] = e_fin; g[4] = e_gw; g[5] = e_gm;
   }
 }
 
@@ -496,6 +509,8 @@ hconv_stack_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
   const uint32_t bar_acc_empty = bar_acc_full + 32;                  // [4]
   const uint32_t bar_gate = bar_acc_empty + 32;
   const uint32_t tmem_slot = bar_gate + 8;
+  const uint32_t par_off = (tmem_slot + 16 + 15u) & ~15u;            // per-channel parameter vectors (fp32)
+  float* par = reinterpret_cast<float*>(smem_raw + (par_off - smem_u32(smem_raw)));
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   // warp index through a shuffle: tells the compiler it is warp-uniform, so the role branches below are
@@ -523,6 +538,17 @@ hconv_stack_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
   if (warp == 2) {
     if constexpr (CS > 1) tmem_alloc_2cta<512>(tmem_slot);
     else tmem_alloc<512>(tmem_slot);
+  }
+  if (warp >= 4) {
+    // Per-channel parameter vectors -> shared memory.  With ~220 KB of the SM's SRAM carved out as shared
+    // memory the L1 is a few KB, so every per-tile __ldg of these vectors was an L2 round trip on the
+    // epilogue's critical path.
+    for (int i = threadIdx.x - 128; i < 5 * KP; i += Cfg::NEPI) {
+      const int v = i / KP;
+      const float* sp = v == 0 ? a.bias : v == 1 ? a.v0 : v == 2 ? a.v1 : v == 3 ? a.v2 : a.gate_bias;
+      par[i] = sp ? __ldg(sp + (i % KP)) : 0.f;
+    }
+    if (threadIdx.x == 128) par[5 * KP] = a.rho_t ? __ldg(a.rho_t) : 1.f;
   }
   if (Epi::kGate && a.do_gate && warp >= 4) {
     // 1x1 gate weights -> shared memory (generic-proxy writes, made visible to the tensor core)
@@ -603,9 +629,13 @@ hconv_stack_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
     stack_mma_issuer<Cfg, PROF>(a, tmem_base, win, w_buf, bar_win_full, bar_win_empty, bar_w_full, bar_w_empty,
                                 bar_acc_full, bar_acc_empty, iters, NT, npairs);
   } else if (warp >= 4) {
+    // the epilogue functors read the parameter vectors through the arguments: point them at the staged copies
+    TcConvArgs ae = a;
+    ae.bias = par; ae.v0 = par + KP; ae.v1 = par + 2 * KP; ae.v2 = par + 3 * KP; ae.gate_bias = par + 4 * KP;
+    ae.rho_t = par + 5 * KP;
     // ---------------- epilogue: NGRP warpgroups, 8-channel chunks each, the last one takes the rest ----------
 #define HGRU_STACK_EPI(C0_, CN_, FIRST_)                                                                          \
-  stack_epilogue<Cfg, Epi, C0_, CN_, PROF>(a, tmem_base, bar_acc_full, bar_acc_empty, crank, iters, NT,           \
+  stack_epilogue<Cfg, Epi, C0_, CN_, PROF>(ae, tmem_base, bar_acc_full, bar_acc_empty, crank, iters, NT,           \
                                            units_per_frame, warp, lane, FIRST_, smem_raw, gate_a, gate_w, bar_gate)
     if constexpr (Cfg::NGRP == 3) {
       if (warp < 8) HGRU_STACK_EPI(0, 8, true);

@@ -140,6 +140,8 @@ __device__ __forceinline__ float fast_tanh(float x) {
   const float t = __fdividef(1.f - e, 1.f + e);
   return copysignf(t, x);
 }
+// per-channel parameter quad; generic load: the stacked kernel stages these vectors in shared memory
+__device__ __forceinline__ float4 ld_par4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void store_chunk_bf16(__nv_bfloat16* base, int KP, int HWp, int n, int cg,
                                                  size_t pin, const float* r) {
   __nv_bfloat162 h[4];
@@ -183,7 +185,7 @@ struct EpiBias {
                                                 const float* acc, const Pre<NCH>&, float* = nullptr) {
 #pragma unroll
     for (int c = 0; c < NCH; c += 4) {
-      const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + c0 + c));
+      const float4 b = ld_par4(a.bias + c0 + c);
       *reinterpret_cast<float4*>(a.out + quad_off(a, n, (c0 + c) >> 2, pin)) =
           make_float4(acc[c] + b.x, acc[c + 1] + b.y, acc[c + 2] + b.z, acc[c + 3] + b.w);
     }
@@ -260,7 +262,7 @@ struct EpiH1 {
     for (int c = 0; c < NCH; c += 4) {
       float g[4] = {0.f, 0.f, 0.f, 0.f};
       if (c < NREAL) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(a.gate_bias + c0 + c));
+        const float4 b = ld_par4(a.gate_bias + c0 + c);
         const float bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j)
@@ -282,9 +284,9 @@ struct EpiH1 {
         const float hv[4] = {p.h[i].x, p.h[i].y, p.h[i].z, p.h[i].w};
         float lbv[4] = {0.f, 0.f, 0.f, 0.f}, bev[4] = {0.f, 0.f, 0.f, 0.f}, nuv[4] = {0.f, 0.f, 0.f, 0.f};
         if (c + 4 * h < NREAL) {     // per-channel parameters: one vector load per quad (zero padded)
-          const float4 lb = __ldg(reinterpret_cast<const float4*>(a.bias + cc));
-          const float4 be = __ldg(reinterpret_cast<const float4*>(a.v0 + cc));
-          const float4 nu = __ldg(reinterpret_cast<const float4*>(a.v1 + cc));
+          const float4 lb = ld_par4(a.bias + cc);
+          const float4 be = ld_par4(a.v0 + cc);
+          const float4 nu = ld_par4(a.v1 + cc);
           lbv[0] = lb.x; lbv[1] = lb.y; lbv[2] = lb.z; lbv[3] = lb.w;
           bev[0] = be.x; bev[1] = be.y; bev[2] = be.z; bev[3] = be.w;
           nuv[0] = nu.x; nuv[1] = nu.y; nuv[2] = nu.z; nuv[3] = nu.w;
@@ -355,7 +357,7 @@ struct EpiH2 {
       for (int h = 0; h < 2; ++h) {
         float bv[4] = {0.f, 0.f, 0.f, 0.f};
         if (c + 4 * h < NREAL) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(a.gate_bias + c0 + c + 4 * h));
+          const float4 b = ld_par4(a.gate_bias + c0 + c + 4 * h);
           bv[0] = b.x; bv[1] = b.y; bv[2] = b.z; bv[3] = b.w;
         }
 #pragma unroll
@@ -368,7 +370,7 @@ struct EpiH2 {
   template <int NCH, int NREAL = NCH>
   __device__ static __forceinline__ void finish(const TcConvArgs& a, int n, size_t pin, int c0,
                                                 const float* acc, const Pre<NCH>& p, float* hout = nullptr) {
-    const float rho = __ldg(a.rho_t);
+    const float rho = *a.rho_t;
 #pragma unroll
     for (int c = 0; c < NCH; c += 8) {
       float r[8];
@@ -381,10 +383,10 @@ struct EpiH2 {
         float lbv[4] = {0.f, 0.f, 0.f, 0.f}, gav[4] = {0.f, 0.f, 0.f, 0.f}, kav[4] = {0.f, 0.f, 0.f, 0.f};
         float omv[4] = {0.f, 0.f, 0.f, 0.f};
         if (c + 4 * h < NREAL) {     // per-channel parameters: one vector load per quad (zero padded)
-          const float4 lb = __ldg(reinterpret_cast<const float4*>(a.bias + cc));
-          const float4 ga = __ldg(reinterpret_cast<const float4*>(a.v0 + cc));
-          const float4 ka = __ldg(reinterpret_cast<const float4*>(a.v1 + cc));
-          const float4 om = __ldg(reinterpret_cast<const float4*>(a.v2 + cc));
+          const float4 lb = ld_par4(a.bias + cc);
+          const float4 ga = ld_par4(a.v0 + cc);
+          const float4 ka = ld_par4(a.v1 + cc);
+          const float4 om = ld_par4(a.v2 + cc);
           lbv[0] = lb.x; lbv[1] = lb.y; lbv[2] = lb.z; lbv[3] = lb.w;
           gav[0] = ga.x; gav[1] = ga.y; gav[2] = ga.z; gav[3] = ga.w;
           kav[0] = ka.x; kav[1] = ka.y; kav[2] = ka.z; kav[3] = ka.w;
@@ -448,7 +450,7 @@ struct EpiGateOut {
     const size_t pin = static_cast<size_t>(y) * a.W + x;
 #pragma unroll
     for (int c = 0; c < CO_PAD; c += 4) {
-      const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + c));
+      const float4 b = ld_par4(a.bias + c);
       float4 g = make_float4(fast_sigmoid(acc[c] + b.x), fast_sigmoid(acc[c + 1] + b.y),
                              fast_sigmoid(acc[c + 2] + b.z), fast_sigmoid(acc[c + 3] + b.w));
       if (c + 0 >= a.kreal) g.x = 0.f;
