@@ -50,7 +50,11 @@ def test_hgru_matches_reference_golden_every_timestep(path, mode):
 
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
 @pytest.mark.parametrize("shape", [(1, 64, 64, 64, 15, 2), (2, 64, 64, 25, 15, 2), (1, 20, 36, 32, 15, 2),
-                                   (3, 16, 16, 16, 5, 3), (1, 7, 9, 3, 3, 2)])
+                                   (3, 16, 16, 16, 5, 3), (1, 7, 9, 3, 3, 2),
+                                   # remainder-packed k <= 25 kernel: ragged H/W, two x-units per row (W > 64),
+                                   # k = 24 / 17 (the row-packed 25th-channel plane is all zero), T = 3
+                                   (2, 40, 24, 25, 15, 3), (1, 33, 70, 25, 15, 2), (1, 18, 66, 24, 15, 2),
+                                   (1, 64, 64, 17, 15, 2)])
 def test_hgru_seeded_cases_vs_oracle(shape, mode):
     """k = 64 (reference), 25 and 32 (BASELINE sweep), ragged H/W, tiny shapes; stress weights so
     tanh leaves its linear region."""
