@@ -255,6 +255,7 @@ __device__ __forceinline__ void stack_mma_issuer(const TcConvArgs& a, uint32_t t
   const uint64_t adesc0 = make_smem_desc(win, Cfg::CHUNK_PITCH, Cfg::ROW_PITCH);
   const uint64_t bdesc0 = make_smem_desc(w_buf, Cfg::NLOC * 16, 128);
   uint32_t st = 0, ph = 0;
+  bool w_ready = false;       // the current weight stage was already seen complete by the previous stage's probe
   uint32_t tc = 0;            // running tile counter: TMEM slot = tc & 3, use count = tc >> 2
   int vit = 0;
   long long t_win = 0, t_acc = 0, t_w = 0, t_begin = 0, t0 = 0;
@@ -280,9 +281,13 @@ __device__ __forceinline__ void stack_mma_issuer(const TcConvArgs& a, uint32_t t
       // one weight stage: wait for it, NG tap groups x (1 or 2) tiles, release it
       auto issue_stage = [&](uint64_t adesc_st, bool first) {
         if constexpr (PROF) t0 = clock64();
-        mbar_wait_warp(bar_w_full + 8 * st, ph);
+        if (!w_ready) mbar_wait_warp(bar_w_full + 8 * st, ph);
         if constexpr (PROF) t_w += clock64() - t0;
         tc_fence_after();
+        // Probe the NEXT stage's barrier now and read the answer only after this stage's MMAs are issued:
+        // the tensor queue is shallow (~2 MMAs), so a barrier round trip between stages otherwise drains it.
+        const uint32_t nst = (st + 1 == Cfg::WSTAGES) ? 0 : st + 1;
+        const bool probe = mbar_test(bar_w_full + 8 * nst, (st + 1 == Cfg::WSTAGES) ? ph ^ 1 : ph);
         if (leader) {
           const uint64_t bdesc_st = bdesc0 + static_cast<uint64_t>((st * Cfg::STAGE_BYTES) >> 4);
 #pragma unroll
@@ -302,6 +307,7 @@ __device__ __forceinline__ void stack_mma_issuer(const TcConvArgs& a, uint32_t t
           if constexpr (CS > 1) tc_commit_2cta(bar_w_empty + 8 * st, kMask);
           else tc_commit(bar_w_empty + 8 * st);
         }
+        w_ready = __all_sync(0xffffffffu, probe);
         if (++st == Cfg::WSTAGES) { st = 0; ph ^= 1; }
       };
       if constexpr (Cfg::REM) {
