@@ -477,11 +477,11 @@ static int hgru_run_bf16(hgru_plan_s* p, const float* Xp, const float* H2_init_n
   {
     static bool attr = false;
     if (!attr) {
-      CUDA_TRY(cudaFuncSetAttribute(hgru::init_state_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      CUDA_TRY(cudaFuncSetAttribute(hgru::init_state_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       attr = true;
     }
-    const size_t smem = sizeof(float) * (KP * KP + 64 * (KP + 1));
-    hgru::init_state_gate_kernel<<<nblk(p->npix, 64), 256, smem, st>>>(
+    const size_t smem = sizeof(float) * (KP * KP + hgru::kInitPix * (KP + 1));
+    hgru::init_state_gate_kernel<<<nblk(p->npix, hgru::kInitPix), 256, smem, st>>>(
         H2_init_nhwc, p->i_r.as<float>(), p->vec(V_IB), p->H2.as<float>(), p->actA.as<__nv_bfloat16>(), p->npix,
         p->k, KP, HW, p->W, p->act_pad);
     ++p->launches;

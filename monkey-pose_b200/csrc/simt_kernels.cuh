@@ -423,6 +423,7 @@ quad_to_chunked_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restr
 //   A = bf16(sigmoid(O_0 *1x1 i_r + i_b) . O_0)  (hgru_module.py:696-711) in the chunked layout.
 // Block = 64 pixels; i_r in shared memory; thread = one pixel x 8 output channels (like gate1x1_kernel).
 // ------------------------------------------------------------------------------------------------
+constexpr int kInitPix = 256;     // pixels per block of init_state_gate_kernel (4 per thread)
 __global__ void __launch_bounds__(256)
 init_state_gate_kernel(const float* __restrict__ h0 /*[npix][k] or nullptr = zeros*/,
                        const float* __restrict__ wg /*[KP][KP]*/, const float* __restrict__ bg,
@@ -430,56 +431,75 @@ init_state_gate_kernel(const float* __restrict__ h0 /*[npix][k] or nullptr = zer
                        int HW, int W, int act_pad /* remainder-packed operand layout, see StackCfg::REM */) {
   extern __shared__ float smem_f[];
   float* wsm = smem_f;                 // [KP][KP]
-  float* xin = smem_f + KP * KP;       // [64][KP+1]
+  float* xin = smem_f + KP * KP;       // [kInitPix][KP+1]
   const int tid = threadIdx.x;
   const int CG = KP >> 3;
-  const size_t p0 = blockIdx.x * static_cast<size_t>(64);
+  const size_t p0 = blockIdx.x * static_cast<size_t>(kInitPix);
   for (int e = tid; e < KP * KP; e += 256) wsm[e] = wg[e];
-  for (int e = tid; e < 64 * KP; e += 256) {
-    const int pp = e / KP, c = e - pp * KP;
-    xin[pp * (KP + 1) + c] = (h0 && p0 + pp < npix && c < k) ? h0[(p0 + pp) * k + c] : 0.f;
+  // the block's pixels are contiguous in h0 ([npix][k]): stream them in flat order, scatter into the padded rows
+  {
+    const size_t base = p0 * k;
+    const size_t lim = (p0 + kInitPix < npix ? static_cast<size_t>(kInitPix) : npix - p0) * k;
+    for (int e = tid; e < kInitPix * k; e += 256) {
+      const int pp = e / k, c = e - pp * k;
+      xin[pp * (KP + 1) + c] = (h0 && static_cast<size_t>(e) < lim) ? h0[base + e] : 0.f;
+    }
+    for (int e = tid; e < kInitPix * (KP - k); e += 256) {     // zero the pad channels
+      const int pp = e / (KP - k), c = k + e - pp * (KP - k);
+      xin[pp * (KP + 1) + c] = 0.f;
+    }
   }
   __syncthreads();
-  const int pp = tid & 63;
-  const size_t p = p0 + pp;
-  if (p >= npix) return;
-  const size_t n = p / HW, pin = p - n * HW;
+  // thread = 4 pixels (pq, pq+64, pq+128, pq+192) x one chunk of 8 output channels: every weight read from
+  // shared memory feeds 4 pixels
+  const int pq = tid & 63;
   for (int cg = tid >> 6; cg < CG; cg += 4) {
-    F8 a;
+    float acc[4][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) a.v[j] = 0.f;
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
     for (int ci = 0; ci < KP; ++ci) {
-      const float xv = xin[pp * (KP + 1) + ci];
       const float4 w0 = *reinterpret_cast<const float4*>(wsm + ci * KP + cg * 8);
       const float4 w1 = *reinterpret_cast<const float4*>(wsm + ci * KP + cg * 8 + 4);
-      a.v[0] = fmaf(xv, w0.x, a.v[0]); a.v[1] = fmaf(xv, w0.y, a.v[1]);
-      a.v[2] = fmaf(xv, w0.z, a.v[2]); a.v[3] = fmaf(xv, w0.w, a.v[3]);
-      a.v[4] = fmaf(xv, w1.x, a.v[4]); a.v[5] = fmaf(xv, w1.y, a.v[5]);
-      a.v[6] = fmaf(xv, w1.z, a.v[6]); a.v[7] = fmaf(xv, w1.w, a.v[7]);
-    }
-    F8 hv, mv;
+      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = cg * 8 + j;
-      hv.v[j] = xin[pp * (KP + 1) + c];
-      mv.v[j] = (c < k) ? sigmoidf_(a.v[j] + bg[c]) * hv.v[j] : 0.f;
+      for (int i = 0; i < 4; ++i) {
+        const float xv = xin[(pq + 64 * i) * (KP + 1) + ci];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(xv, wv[j], acc[i][j]);
+      }
     }
-    float* o = H2q + ((n * (KP >> 2) + 2 * cg) * HW + pin) * 4;
-    *reinterpret_cast<float4*>(o) = make_float4(hv.v[0], hv.v[1], hv.v[2], hv.v[3]);
-    *reinterpret_cast<float4*>(o + static_cast<size_t>(HW) * 4) = make_float4(hv.v[4], hv.v[5], hv.v[6], hv.v[7]);
-    if (act_pad == 0) {
-      st8_bf16(chunk_ptr(actA, static_cast<int>(n), cg, pin, HW, CG), mv);
-    } else {
-      const int plane = HW + act_pad * W;
-      const size_t pp = pin + static_cast<size_t>(act_pad) * W;
-      if (cg != CG - 1) {
-        st8_bf16(chunk_ptr(actA, static_cast<int>(n), cg, pp, plane, CG), mv);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int pp = pq + 64 * i;
+      const size_t p = p0 + pp;
+      if (p >= npix) continue;
+      const size_t n = p / HW, pin = p - n * HW;
+      F8 hv, mv;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = cg * 8 + j;
+        hv.v[j] = xin[pp * (KP + 1) + c];
+        mv.v[j] = (c < k) ? sigmoidf_(acc[i][j] + bg[c]) * hv.v[j] : 0.f;
+      }
+      float* o = H2q + ((n * (KP >> 2) + 2 * cg) * HW + pin) * 4;
+      *reinterpret_cast<float4*>(o) = make_float4(hv.v[0], hv.v[1], hv.v[2], hv.v[3]);
+      *reinterpret_cast<float4*>(o + static_cast<size_t>(HW) * 4) = make_float4(hv.v[4], hv.v[5], hv.v[6], hv.v[7]);
+      if (act_pad == 0) {
+        st8_bf16(chunk_ptr(actA, static_cast<int>(n), cg, pin, HW, CG), mv);
       } else {
-        // last chunk = row-packed plane of channel KP - 8: element j of the pixel j rows above
-        __nv_bfloat16* o = chunk_ptr(actA, static_cast<int>(n), cg, pp, plane, CG);
-        const __nv_bfloat16 v = __float2bfloat16(mv.v[0]);
+        const int plane = HW + act_pad * W;
+        const size_t pa = pin + static_cast<size_t>(act_pad) * W;
+        if (cg != CG - 1) {
+          st8_bf16(chunk_ptr(actA, static_cast<int>(n), cg, pa, plane, CG), mv);
+        } else {
+          // last chunk = row-packed plane of channel KP - 8: element j of the pixel j rows above
+          __nv_bfloat16* oa = chunk_ptr(actA, static_cast<int>(n), cg, pa, plane, CG);
+          const __nv_bfloat16 v = __float2bfloat16(mv.v[0]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j - static_cast<ptrdiff_t>(j) * W * 8] = v;
+          for (int j = 0; j < 8; ++j) oa[j - static_cast<ptrdiff_t>(j) * W * 8] = v;
+        }
       }
     }
   }
