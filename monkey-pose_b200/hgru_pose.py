@@ -102,6 +102,37 @@ class model:
         self.data_dict = dd
         self._dev_params = None
 
+    def load_checkpoint(self, prefix, scope="cnn"):
+        """Inject the variables of a TensorFlow V2 checkpoint written by the reference's
+        `tf.train.Saver` (train_cnn_networks_hgru.py:188, 248-250; restored at :312-313).  `prefix` is what
+        `tf.train.latest_checkpoint(config.model_output)` returns; a directory is resolved the same way.
+        The reference builds the model under `tf.variable_scope("cnn")` (:96), so names carry that
+        prefix; optimizer slots (`.../Adam`, `beta1_power`, ...) and `global_step` are ignored.
+        Read without TensorFlow by `monkey_pose_b200.tf_checkpoint`."""
+        from . import tf_checkpoint
+        import os
+        if os.path.isdir(prefix):
+            found = tf_checkpoint.latest_checkpoint(prefix)
+            if found is None:
+                raise FileNotFoundError("no `checkpoint` state file in %s" % prefix)
+            prefix = found
+        lead = scope + "/" if scope else ""
+        wanted = {}
+        for name, _, _ in tf_checkpoint.list_variables(prefix):
+            if not name.startswith(lead):
+                continue
+            short = name[len(lead):]
+            tail = short.rsplit("/", 1)[-1]
+            if tail.startswith("Adam") or tail in ("beta1_power", "beta2_power", "global_step"):
+                continue
+            wanted[name] = short
+        flat = {wanted[n]: v for n, v in tf_checkpoint.read_checkpoint(prefix, names=list(wanted)).items()}
+        try:
+            self.load_params(flat)
+        except KeyError as e:
+            raise KeyError("checkpoint %s lacks variable %s (scope %r)" % (prefix, e, scope))
+        return sorted(flat)
+
     def get_var(self, initial_value, name, idx, var_name, in_size=None, out_size=None):
         """hgru_pose.py:196-216: value from data_dict[name][idx] when present, else the initial
         value; registered in var_dict[(name, idx)]."""
