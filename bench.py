@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-frames", type=int, default=64, help="frames in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stages", action="store_true", help="skip the crop / post-processing stage timings")
     return ap.parse_args()
 
 
@@ -278,6 +279,12 @@ def run_ours(a):
         cpu = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "%d of the %d frames, median of 3 forwards (%.1f s each), torch-CPU oracle "
                          "(stand-in for TF-CPU: TensorFlow absent)" % (a.cpu_frames, B, med)}
+    stages = None
+    if not a.no_stages and world == 1 and a.mode == "bf16":
+        try:
+            stages = neighbour_stages(a, m, torch, mp)
+        except Exception as e:                      # never lose the headline line to an auxiliary measurement
+            stages = {"error": repr(e)}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps,
             "warmup": max(3, a.warmup), "ms_per_step": ms_dev / a.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": a.mode if a.mode != "fp32" else "f32",
@@ -285,12 +292,99 @@ def run_ours(a):
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(depth_pin.numel() * 4) * world,
                     "d2h_bytes_per_step": int(B * 69 * 4) * world, "ms_per_step": ms_host / a.steps},
             "gpu_launches": int(launches_per_step * a.steps), "clocks": clk, "roofline": roof,
-            "cpu_baseline": cpu,
+            "cpu_baseline": cpu, "neighbour_stages": stages,
             "tensor_util_whole_step": (16 * flops_per_launch * world * a.steps / (ms_dev * 1e-3)) * 1e-12
             / (peak * world)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def neighbour_stages(a, m, torch, mp):
+    """SURVEY 8(f) rows 1 + 2, measured at the same batch on rank 0: the GPU crop stage before the network
+    (prepare_data_test -> cropArea3D) and the post-processing after it (absolute coordinates + joint error), plus
+    the whole chain camera frames -> joints through the public API with host buffers.  HBM-bound byte work:
+    GB/s against MEASURED_PEAKS.json hbm_gbps."""
+    import numpy as np
+    from monkey_pose_b200 import tf_monkeydetector as tmd
+    from monkey_pose_b200 import pose_evaluation as pe
+
+    class Cfg(object):
+        image_orig_size = [424, 512, 1]
+        image_target_size = [128, 128, 1]
+        image_max_depth = 10000.
+
+    B, h, w = a.batch, 424, 512
+    rng = np.random.default_rng(99)
+    base = np.round(rng.uniform(600, 4000, size=(8, h, w)) / 8) * 8
+    base[rng.uniform(size=base.shape) < 0.05] = 0
+    frames_np = (base[rng.integers(0, 8, B)] / 10000.0).astype(np.float32)
+    coms_norm = np.stack([rng.uniform(0.3, 0.9, B), rng.uniform(0.25, 0.7, B), rng.uniform(0.1, 0.3, B)], 1)
+    md = tmd.tfMonkeyDetector(365.456, 365.456, 256, 212, [800, 800, 1200], 200, 10000)
+    frames_dev = torch.as_tensor(frames_np).cuda()
+    frames_pin = torch.as_tensor(frames_np).pin_memory()
+    labels = torch.rand(B, 23, 3, device="cuda") * 100.0
+
+    def ev_time(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(reps):
+            r = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps, (time.perf_counter() - t0) * 1e3 / reps, r
+
+    patches, coms, _ = tmd.prepare_data_test(frames_dev, coms_norm, md, Cfg())
+    # algorithmic bytes of the crop: every source pixel of each frame's window once + the 128x128 output
+    ints, _, _ = md._windows_batch(np.asarray(coms), h, w, (128, 128))
+    x0, y0, wb, hb = [ints[:, i].astype(np.int64) for i in range(4)]
+    win_px = int((np.clip(np.minimum(x0 + wb, w) - np.maximum(x0, 0), 0, None) *
+                  np.clip(np.minimum(y0 + hb, h) - np.maximum(y0, 0), 0, None)).sum())
+    crop_bytes = 4.0 * win_px + 4.0 * B * 128 * 128
+    crop_gpu_ms, crop_wall_ms, _ = ev_time(lambda: tmd.prepare_data_test(frames_dev, coms_norm, md, Cfg()))
+    # the kernel alone, through the C ABI, parameters already on the device
+    lib = mp._lib.load()
+    _, zf, _ = md._windows_batch(np.asarray(coms), h, w, (128, 128))
+    ip_d, zp_d = torch.as_tensor(ints).cuda(), torch.as_tensor(zf).cuda()
+    out_d = torch.empty((B, 128, 128), device="cuda", dtype=torch.float32)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def crop_kernel():
+        mp._lib.check(lib.crop_area3d_forward(frames_dev.data_ptr(), B, h, w, 10000.0, ip_d.data_ptr(),
+                                              zp_d.data_ptr(), float(md.maxDepth), 10000.0, out_d.data_ptr(),
+                                              128, 128, stream), "crop_area3d_forward")
+
+    crop_kernel_ms, _, _ = ev_time(crop_kernel, 20)
+    out = m.build(patches, 69)
+    post_gpu_ms, post_wall_ms, _ = ev_time(lambda: pe.getMeanError_np(
+        labels, md.getAbsoluteCoordinates_batch(out, coms, 600.0)[0]))
+
+    def chain():
+        p, cs, _ = tmd.prepare_data_test(frames_pin.cuda(non_blocking=True), coms_norm, md, Cfg())
+        xyz, _ = md.getAbsoluteCoordinates_batch(m.build(p, 69), cs, 600.0)
+        return xyz.cpu()
+
+    chain_gpu_ms, chain_wall_ms, _ = ev_time(chain, 3)
+    hbm = None
+    try:
+        hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs")
+    except Exception:
+        pass
+    crop_gbs = crop_bytes / (crop_kernel_ms * 1e-3) * 1e-9
+    return {"batch": B, "frame": [h, w],
+            "crop": {"kernel_ms": crop_kernel_ms, "algorithmic_bytes": crop_bytes, "GB/s": crop_gbs,
+                     "frac_of_hbm": (crop_gbs / hbm) if hbm else None,
+                     "api_ms": crop_gpu_ms, "api_wall_ms": crop_wall_ms,
+                     "note": "kernel_ms: crop_area3d_forward alone (C ABI, parameters on the device); api_ms: "
+                             "prepare_data_test = host window arithmetic (comToBounds) + parameter upload + "
+                             "kernel; frames resident in HBM"},
+            "post": {"gpu_ms": post_gpu_ms, "wall_ms": post_wall_ms,
+                     "note": "x600 + CoM, xyz->uvd, mean joint error; 23 joints per frame, latency-bound"},
+            "frames_to_joints_e2e": {"value": B / (chain_wall_ms * 1e-3), "unit": UNIT, "wall_ms": chain_wall_ms,
+                                     "h2d_bytes": int(frames_np.nbytes), "d2h_bytes": int(B * 69 * 4)}}
 
 
 def main():

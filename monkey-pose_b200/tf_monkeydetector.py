@@ -121,6 +121,36 @@ class tfMonkeyDetector(object):
         off[0, 2], off[1, 2] = xs, ys
         return (xstart, ystart, wb, hb, sz[0], sz[1], xs, ys), (zstart, zend), off @ scale @ trans
 
+    def _windows_batch(self, coms, H, W, dsize):
+        """`_window` for a whole batch in array form (same float64 operations element by element, so the
+        integers are identical): at 40K+ frames/s a per-frame Python loop costs more than the network.
+        Returns (ints [N,8] int32, z [N,2] float32, Ms [N,3,3] float64)."""
+        c = numpy.asarray(coms, numpy.float64).reshape(-1, 3)
+        sx, sy, sz = [float(v) for v in self.cube]
+        zstart, zend = c[:, 2] - sz / 2., c[:, 2] + sz / 2.
+        xstart = numpy.floor((c[:, 0] * c[:, 2] / self.fx - sx / 2.) / c[:, 2] * self.fx).astype(numpy.int64)
+        xend = numpy.floor((c[:, 0] * c[:, 2] / self.fx + sx / 2.) / c[:, 2] * self.fx).astype(numpy.int64)
+        ystart = numpy.floor((c[:, 1] * c[:, 2] / self.fy - sy / 2.) / c[:, 2] * self.fy).astype(numpy.int64)
+        yend = numpy.floor((c[:, 1] * c[:, 2] / self.fy + sy / 2.) / c[:, 2] * self.fy).astype(numpy.int64)
+        if numpy.any((xend <= 0) | (yend <= 0) | (xstart >= W) | (ystart >= H) | (xend <= xstart) | (yend <= ystart)):
+            raise ValueError("crop window does not intersect the frame")
+        wb, hb = xend - xstart, yend - ystart
+        wide = wb > hb
+        szx = numpy.where(wide, dsize[0], wb * dsize[1] // hb)
+        szy = numpy.where(wide, hb * dsize[0] // wb, dsize[1])
+        sc = numpy.where(hb > wb, szy / hb.astype(numpy.float64), szx / wb.astype(numpy.float64))
+        xs = numpy.floor(dsize[0] / 2. - szx / 2.).astype(numpy.int64)
+        ys = numpy.floor(dsize[1] / 2. - szy / 2.).astype(numpy.int64)
+        # M = off @ scale @ trans written out (the products only ever add exact zeros, so this is the same
+        # floating-point result; a stacked 3x3 matmul would cost one BLAS call per frame)
+        Ms = numpy.zeros((c.shape[0], 3, 3), numpy.float64)
+        Ms[:, 0, 0] = Ms[:, 1, 1] = sc
+        Ms[:, 0, 2] = sc * (-xstart) + xs
+        Ms[:, 1, 2] = sc * (-ystart) + ys
+        Ms[:, 2, 2] = 1.0
+        ints = numpy.stack([xstart, ystart, wb, hb, szx, szy, xs, ys], 1).astype(numpy.int32)
+        return ints, numpy.stack([zstart, zend], 1).astype(numpy.float32), Ms
+
     def cropArea3D_batch(self, frames, coms, dsize=(128, 128), frame_scale=1.0, out_divisor=1.0):
         """Batched cropArea3D: frames [N,H,W] torch CUDA float32 (times frame_scale = mm), coms [N,3]
         (u, v, d mm).  Returns (patches [N,dsize[1],dsize[0]] CUDA = mm / out_divisor, Ms, coms)."""
@@ -130,20 +160,15 @@ class tfMonkeyDetector(object):
             raise RuntimeError("frames must be a [N,H,W] torch CUDA tensor (no CPU fallback)")
         frames = frames.to(torch.float32).contiguous()
         N, H, W = [int(v) for v in frames.shape]
-        ip = numpy.zeros((N, 8), numpy.int32)
-        zp = numpy.zeros((N, 2), numpy.float32)
-        Ms = []
-        for i in range(N):
-            ints, zz, M = self._window(numpy.asarray(coms[i], numpy.float64), H, W, dsize)
-            ip[i], zp[i] = ints, zz
-            Ms.append(M)
+        coms = numpy.asarray(coms, numpy.float64).reshape(N, 3)
+        ip, zp, Ms = self._windows_batch(coms, H, W, dsize)
         ip_d = torch.as_tensor(ip).cuda()
         zp_d = torch.as_tensor(zp).cuda()
         out = torch.empty((N, dsize[1], dsize[0]), device=frames.device, dtype=torch.float32)
         _lib.check(_lib.load().crop_area3d_forward(
             frames.data_ptr(), N, H, W, float(frame_scale), ip_d.data_ptr(), zp_d.data_ptr(), float(self.maxDepth),
             float(out_divisor), out.data_ptr(), int(dsize[1]), int(dsize[0]), _stream()), "crop_area3d_forward")
-        return out, Ms, [numpy.asarray(c) for c in coms]
+        return out, list(Ms), list(coms)
 
     def cropArea3D(self, dpt, com=None, dsize=(128, 128), docom=False):
         """tf_monkeydetector.py:292-365 for one frame [H,W] (mm): (patch, M, com)."""
@@ -160,7 +185,7 @@ def prepare_data_test(image_np, tr_res, md, config):
         image_np = image_np[..., 0]
     tr = numpy.asarray(tr_res, numpy.float64)
     scale = numpy.array([config.image_orig_size[0], config.image_orig_size[1], config.image_max_depth], numpy.float64)
-    coms = [tr[i] * scale for i in range(tr.shape[0])]
+    coms = tr * scale
     ts = config.image_target_size
     patches, Ms, coms = md.cropArea3D_batch(image_np, coms, dsize=(ts[1], ts[0]),
                                             frame_scale=config.image_max_depth,

@@ -92,3 +92,21 @@ def test_shard_bounds_partition_the_batch():
         assert spans[0][0] == 0 and spans[-1][1] == n
         assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
         assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def test_crop_windows_batch_equals_per_frame_reference_arithmetic():
+    """tfMonkeyDetector._windows_batch (array form used at batch size) == the line-by-line mirror of
+    comToBounds / cropArea3D's window arithmetic (tf_monkeydetector.py:193-206, 309-362) for every frame."""
+    import numpy as np
+    from monkey_pose_b200 import tf_monkeydetector as tmd
+    md = tmd.tfMonkeyDetector(365.456, 365.456, 256, 212, [800, 800, 1200], 200, 10000)
+    rng = np.random.default_rng(0)
+    n = 500
+    coms = np.stack([rng.uniform(0.1, 1.1, n) * 424, rng.uniform(0.1, 0.75, n) * 512,
+                     rng.uniform(0.08, 0.35, n) * 10000], 1)
+    ints, z, Ms = md._windows_batch(coms, 424, 512, (128, 128))
+    for i in range(n):
+        a, b, M = md._window(coms[i], 424, 512, (128, 128))
+        assert tuple(int(v) for v in ints[i]) == tuple(int(v) for v in a)
+        assert np.array_equal(z[i], np.asarray(b, np.float32))
+        np.testing.assert_allclose(Ms[i], M, rtol=0, atol=1e-12)
