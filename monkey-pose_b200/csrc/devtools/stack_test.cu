@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 #include <vector>
 #include "../hconv_stack.cuh"
 #include "../tc_host.cuh"
@@ -31,7 +32,7 @@ __global__ void fill_bf16(__nv_bfloat16* p, size_t n, float lo, float hi, unsign
   unsigned h = (unsigned)(i * 2654435761u) ^ seed; h ^= h << 13; h ^= h >> 17; h ^= h << 5;
   p[i] = __float2bfloat16(lo + (hi - lo) * (h & 0xFFFFFF) / 16777216.f);
 }
-static int g_random_data = 0;
+static int g_random_data = 0, g_check_layout = 0, g_audit_fail = 0;
 static float bf16r(float v) { return __bfloat162float(__float2bfloat16(v)); }
 
 template <int KP, int T, int KC, int CS>
@@ -133,7 +134,9 @@ void time_real_epilogue(const char* name, int N, int H, int W, int k, int gate =
   size_t wpk_elems = (size_t)Cfg::PASS_STAGES * Cfg::NG * 2 * 128 * 8;
   const int HA = H + Cfg::ACT_PAD; const size_t actb = (size_t)N * CG * HA * W * 8 * 2;
   CK(cudaMalloc(&X, npix * KP * 4)); CK(cudaMalloc(&H1, npix * KP * 4)); CK(cudaMalloc(&G, npix * KP * 4)); CK(cudaMalloc(&H2, npix * KP * 4));
-  CK(cudaMalloc(&vec, 8 * KP * 4)); CK(cudaMalloc(&act, actb)); CK(cudaMalloc(&actout, actb)); CK(cudaMalloc(&wpk, wpk_elems * 2));
+  CK(cudaMalloc(&vec, 8 * KP * 4)); CK(cudaMalloc(&act, actb));
+  const size_t GUARD = 1 << 20; uint8_t* actout_raw; CK(cudaMalloc(&actout_raw, actb + 2 * GUARD)); CK(cudaMemset(actout_raw, 0xA5, actb + 2 * GUARD));
+  actout = reinterpret_cast<__nv_bfloat16*>(actout_raw + GUARD); CK(cudaMalloc(&wpk, wpk_elems * 2));
   CK(cudaMemset(X, 0, npix * KP * 4)); CK(cudaMemset(H1, 0, npix * KP * 4)); CK(cudaMemset(G, 0, npix * KP * 4)); CK(cudaMemset(H2, 0, npix * KP * 4));
   CK(cudaMemset(vec, 0, 8 * KP * 4)); CK(cudaMemset(act, 0, actb)); CK(cudaMemset(actout, 0, actb)); CK(cudaMemset(wpk, 0, wpk_elems * 2));
   if (g_random_data) {   // realistic operand / state values instead of zeros (switching power, real tanh inputs)
@@ -154,6 +157,7 @@ void time_real_epilogue(const char* name, int N, int H, int W, int k, int gate =
   a.wpk = wpk; a.bias = vec; a.v0 = vec + KP; a.v1 = vec + 2 * KP; a.v2 = vec + 3 * KP; a.rho_t = vec + 4 * KP;
   a.X = X; a.H1 = H1; a.G = G; a.H2 = H2; a.out = H1; a.out_bf16 = actout;
   a.gate_wpk = wpk; a.gate_bias = vec; a.gate_out = G; a.gate_act_out = actout; a.do_gate = gate; a.dbg_flags = dbg;
+  if (std::is_same<Epi, hgru::EpiH2>::value) a.out_bf16 = nullptr;   // fused pipeline: H2's operand copy comes from the gate
   auto kern = hgru::hconv_stack_kernel<KP, T, KC, CS, Epi, false>;
   auto kern_prof = hgru::hconv_stack_kernel<KP, T, KC, CS, Epi, true>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -175,12 +179,39 @@ void time_real_epilogue(const char* name, int N, int H, int W, int k, int gate =
   float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 20;
   printf("%s gate=%d CS=%d: %.3f ms | leader avg cycles: mma_total=%.0f wait_win=%.0f wait_acc_empty=%.0f wait_w=%.0f | epi_total=%.0f epi_wait=%.0f\n", name, gate, CS, ms,
          av[0] / nl, av[1] / nl, av[2] / nl, av[3] / nl, av[4] / grid, av[5] / grid);
+  if (g_check_layout) {
+    // Bounds / layout audit of the operand tensor the epilogue wrote (stands in for a memory checker):
+    // guard bands untouched; pad rows and never-written elements still zero; in the remainder-packed plane every
+    // value appears at its 8 (row - j, lane j) positions.
+    std::vector<uint8_t> hb(actb + 2 * GUARD);
+    CK(cudaMemcpy(hb.data(), actout_raw, hb.size(), cudaMemcpyDeviceToHost));
+    size_t guard_bad = 0, pad_bad = 0, pack_bad = 0, nonzero = 0;
+    for (size_t i = 0; i < GUARD; ++i) { if (hb[i] != 0xA5) ++guard_bad; if (hb[GUARD + actb + i] != 0xA5) ++guard_bad; }
+    const uint16_t* o = reinterpret_cast<const uint16_t*>(hb.data() + GUARD);
+    const int PADR = Cfg::ACT_PAD;
+    auto at = [&](int n, int cg, int r, int x, int j) { return o[((((size_t)n * CG + cg) * HA + r) * W + x) * 8 + j]; };
+    for (int n = 0; n < N; n += 37) for (int cg = 0; cg < CG; ++cg) for (int r = 0; r < HA; ++r) for (int x = 0; x < W; ++x) for (int j = 0; j < 8; ++j) {
+      const uint16_t v = at(n, cg, r, x, j);
+      if (v) ++nonzero;
+      const bool rem_plane = Cfg::REM && cg == CG - 1;
+      if (!rem_plane) {
+        if (r < PADR && v) ++pad_bad;                                       // top pad rows stay zero
+        if (cg * 8 + j >= k && v) ++pad_bad;                                // pad channels stay zero
+      } else {
+        const int y = r - PADR + j;                                         // source pixel row of this element
+        if ((y < 0 || y >= H) && v) ++pad_bad;                              // never written -> still zero
+        if (y >= 0 && y < H && v != at(n, cg, y + PADR, x, 0)) ++pack_bad;  // == the value stored at (y, lane 0)
+      }
+    }
+    printf("    layout audit: guard_bad=%zu pad_bad=%zu pack_bad=%zu (nonzero elements seen %zu)\n", guard_bad, pad_bad, pack_bad, nonzero);
+    if (guard_bad || pad_bad || pack_bad || !nonzero) g_audit_fail = 1;
+  }
   for (int g = 0; g < Cfg::NGRP; ++g) {
     double ph[6] = {0, 0, 0, 0, 0, 0};
     for (int b = 0; b < grid; ++b) for (int i = 0; i < 6; ++i) ph[i] += pr[grid * 8 + (b * Cfg::NGRP + g) * 8 + i] / (double)grid;
     printf("    epilogue group %d: total=%.0f wait=%.0f tmem+unstack=%.0f finish=%.0f gate_wait=%.0f gate_math=%.0f\n", g, ph[0], ph[1], ph[2], ph[3], ph[4], ph[5]);
   }
-  cudaFree(X); cudaFree(H1); cudaFree(G); cudaFree(H2); cudaFree(vec); cudaFree(act); cudaFree(actout); cudaFree(wpk); cudaFree(d_prof);
+  cudaFree(X); cudaFree(H1); cudaFree(G); cudaFree(H2); cudaFree(vec); cudaFree(act); cudaFree(actout_raw); cudaFree(wpk); cudaFree(d_prof);
 }
 
 int main(int argc, char** argv) {
@@ -199,6 +230,14 @@ int main(int argc, char** argv) {
     time_real_epilogue<32, 5, 25, 1, hgru::EpiBias>("EpiBias noWstream", 256, 64, 64, 25, 0, 1);
     time_real_epilogue<32, 5, 25, 1, hgru::EpiH2>("EpiH2", 256, 64, 64, 25, 1, 0);
     time_real_epilogue<32, 5, 25, 1, hgru::EpiH2>("EpiH2 noWstream", 256, 64, 64, 25, 1, 1);
+  }
+  if (which == 23) {   // epilogue-written operand tensors: guard bands, zero padding, remainder-plane consistency
+    g_random_data = 1; g_check_layout = 1;
+    time_real_epilogue<32, 5, 25, 1, hgru::EpiH1>("EpiH1", 256, 64, 64, 25, 1);
+    time_real_epilogue<32, 5, 25, 1, hgru::EpiH2>("EpiH2", 256, 64, 64, 25, 1);
+    time_real_epilogue<32, 5, 25, 1, hgru::EpiH2>("EpiH2 ragged", 37, 40, 24, 25, 1);
+    time_real_epilogue<32, 4, 32, 1, hgru::EpiH2>("EpiH2 k32", 64, 64, 64, 32, 1);
+    g_random_data = 0; g_check_layout = 0; f += g_audit_fail;
   }
   if (which == 22) {
     for (g_random_data = 0; g_random_data < 2; ++g_random_data) {
