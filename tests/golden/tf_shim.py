@@ -57,6 +57,8 @@ class _Registry(object):
         self.scope = []
         self.drawn = []          # (shape, array) returned by initialisers, in call order
         self.conv_calls = 0
+        self.bn_calls = 0        # tf.layers.batch_normalization scopes: batch_normalization, batch_normalization_1, ...
+        self.bn_preset = {}      # scope -> (gamma, beta, moving_mean, moving_variance) injected by the generator
 
 
 REG = _Registry(0)
@@ -223,7 +225,69 @@ nn = types.SimpleNamespace(
     conv2d=_conv2d,
     max_pool=_max_pool,
     bias_add=lambda x, b: _t(np.asarray(x) + np.asarray(b)),
+    dropout=None,        # train-mode only: never reached by the inference-mode golden runs
 )
+
+
+# ---- tf.layers.batch_normalization (inference: moving statistics) -----------------------------------
+def _batch_normalization(inputs, axis=-1, momentum=0.99, epsilon=1e-3, center=True, scale=True, training=False,
+                         fused=None, name=None):
+    """Inference-mode tf.layers.batch_normalization.  Variables live in scopes `batch_normalization`,
+    `batch_normalization_1`, ... in call order (TF's default naming); values come from REG.bn_preset or the TF
+    defaults (gamma 1, beta 0, mean 0, variance 1).  `axis` beyond the rank (the reference passes axis=3 for the
+    rank-2 fc tensor: defect D5) is resolved to the last axis (R-D5)."""
+    assert training in (False, None), "golden vectors are inference-mode (moving statistics)"
+    x = np.asarray(inputs, np.float64)
+    scope = "batch_normalization" if REG.bn_calls == 0 else "batch_normalization_%d" % REG.bn_calls
+    REG.bn_calls += 1
+    ax = axis if -x.ndim <= axis < x.ndim else x.ndim - 1
+    c = x.shape[ax]
+    g, b, m, v = REG.bn_preset.get(scope, (np.ones(c), np.zeros(c), np.zeros(c), np.ones(c)))
+    full = "/".join(REG.scope + [scope])
+    for nm, val in (("gamma", g), ("beta", b), ("moving_mean", m), ("moving_variance", v)):
+        REG.variables[full + "/" + nm] = np.asarray(val, np.float32)
+    shp = [1] * x.ndim
+    shp[ax] = c
+    g, b, m, v = [np.asarray(REG.variables[full + "/" + nm], np.float64).reshape(shp)
+                  for nm in ("gamma", "beta", "moving_mean", "moving_variance")]
+    return _t((x - m) / np.sqrt(v + epsilon) * g + b)
+
+
+layers = types.SimpleNamespace(batch_normalization=_batch_normalization)
+
+
+# ---- tf.image.resize_images (TF 1.x default: bilinear, align_corners=False, no half-pixel centres) ----
+def _resize_images(images, size, method=0, align_corners=False):
+    """ResizeBilinear as TF 1.x computes it (kernels/resize_bilinear_op.cc), in float32: scale = in / out,
+    src = dst * scale, lower = floor(src), upper = min(lower + 1, in - 1), lerp = src - lower;
+    top = tl + (tr - tl) * xl; bottom = bl + (br - bl) * xl; out = top + (bottom - top) * yl."""
+    assert method == 0 and not align_corners
+    x = np.asarray(images, np.float32)
+    n, h, w, c = x.shape
+    oh, ow = int(size[0]), int(size[1])
+    if (oh, ow) == (h, w):
+        return _t(x.astype(np.float64))
+
+    def weights(insz, outsz):
+        scale = np.float32(insz) / np.float32(outsz)
+        src = np.arange(outsz, dtype=np.float32) * scale
+        lo = np.floor(src).astype(np.int64)
+        hi = np.minimum(lo + 1, insz - 1)
+        return lo, hi, (src - lo.astype(np.float32)).astype(np.float32)
+
+    y0, y1, yl = weights(h, oh)
+    x0, x1, xl = weights(w, ow)
+    xl_ = xl.reshape(1, 1, ow, 1)
+    yl_ = yl.reshape(1, oh, 1, 1)
+    tl, tr = x[:, y0][:, :, x0], x[:, y0][:, :, x1]
+    bl, br = x[:, y1][:, :, x0], x[:, y1][:, :, x1]
+    top = (tl + (tr - tl) * xl_).astype(np.float32)
+    bot = (bl + (br - bl) * xl_).astype(np.float32)
+    out = (top + (bot - top) * yl_).astype(np.float32)
+    return _t(out.astype(np.float64))
+
+
+image = types.SimpleNamespace(resize_images=_resize_images)
 
 
 # ---- tf.contrib.layers.xavier_initializer* (hgru_pose.py:171,186) ----------------------------
