@@ -152,6 +152,37 @@ HGRU_API int joint_error_forward(const float* labels_dev, const float* results_d
                                  double* frame_mean_ws_dev, float* frame_max_ws_dev, double* result_dev,
                                  void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Attention (centre-of-mass) CNN: the network right before the crop stage, reference
+ * `attn_model_struct.build` (train_cnn_networks_hgru.py:422-525): bilinear resize to 128x128,
+ * 5 x [conv (3,3,3,3,5) + relu -> max-pool -> batch-norm], fc -> relu -> batch-norm -> fc (O = 3 outputs:
+ * u/height, v/width, d/max_depth of the centre of mass).  Inference mode (moving statistics).
+ * widths = output channels of the five convolutions (reference: 64,128,256,512,1024; multiples of 8),
+ * fc_hidden = 1024 in the reference.  Variables arrive under their TF names' meaning:
+ *   conv_filters[i] = aconv_<i+1>_filters HWIO, conv_biases[i]; fc_1 = afc_1 [16*widths[4]][fc_hidden];
+ *   fc_out = afc_out [fc_hidden][O]; bn[i] = batch_normalization[_i]/{gamma,beta,moving_mean,moving_variance},
+ *   i = 0..4 after the pools, 5 after relu(afc_1).  All device pointers, fp32.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct attn_plan_s* attn_plan_t;
+typedef struct {
+  const float* conv_filters[5];
+  const float* conv_biases[5];
+  const float* fc_1_weights;
+  const float* fc_1_biases;
+  const float* fc_out_weights;
+  const float* fc_out_biases;
+  const float* bn[6][4];
+} attn_params_t;
+HGRU_API int attn_plan_create(int N, int H, int W, const int* widths, int fc_hidden, int O, attn_plan_t* out);
+HGRU_API int attn_plan_destroy(attn_plan_t plan);
+HGRU_API int attn_set_params(attn_plan_t plan, const attn_params_t* params, float bn_epsilon, void* stream);
+/* frames [N,H,W] fp32 (depth / image_max_depth, as the caller feeds the reference graph) -> out [N,O] */
+HGRU_API int attn_forward(attn_plan_t plan, const float* frames_dev, float* out_dev, void* stream);
+/* name in {"resized","pool1",...,"pool5","fc1"}: dense fp32 NHWC copy of an intermediate tensor */
+HGRU_API int attn_get_activation(attn_plan_t plan, const char* name, float* dst_dev, void* stream);
+HGRU_API size_t attn_plan_workspace_bytes(attn_plan_t plan);
+HGRU_API int attn_plan_launch_count(attn_plan_t plan);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,6 +29,14 @@ class PoseParams(ctypes.Structure):
         + [(n, ctypes.c_void_p) for n in HGRU_PARAM_ORDER])
 
 
+class AttnParams(ctypes.Structure):
+    """attn_params_t of include/hgru_b200.h (same field order)."""
+    _fields_ = [("conv_filters", ctypes.c_void_p * 5), ("conv_biases", ctypes.c_void_p * 5),
+                ("fc_1_weights", ctypes.c_void_p), ("fc_1_biases", ctypes.c_void_p),
+                ("fc_out_weights", ctypes.c_void_p), ("fc_out_biases", ctypes.c_void_p),
+                ("bn", (ctypes.c_void_p * 4) * 6)]
+
+
 # every symbol include/hgru_b200.h declares: name -> (restype, argtypes)
 _P = ctypes.c_void_p
 _I = ctypes.c_int
@@ -56,6 +64,13 @@ SIGNATURES = {
     "pose_postprocess_forward": (_I, [_P, _P, _I, _I, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                       ctypes.c_double, ctypes.c_float, _P, _P, _P]),
     "joint_error_forward": (_I, [_P, _P, _I, _I, _P, _P, _P, _P]),
+    "attn_plan_create": (_I, [_I, _I, _I, ctypes.POINTER(_I), _I, _I, ctypes.POINTER(_P)]),
+    "attn_plan_destroy": (_I, [_P]),
+    "attn_set_params": (_I, [_P, ctypes.POINTER(AttnParams), ctypes.c_float, _P]),
+    "attn_forward": (_I, [_P, _P, _P, _P]),
+    "attn_get_activation": (_I, [_P, ctypes.c_char_p, _P, _P]),
+    "attn_plan_workspace_bytes": (ctypes.c_size_t, [_P]),
+    "attn_plan_launch_count": (_I, [_P]),
 }
 
 _lib = None

@@ -17,6 +17,9 @@
 #include "post.cuh"
 #include "hconv_tc.cuh"
 #include "simt_kernels.cuh"
+#include <algorithm>
+
+#include "attn.cuh"
 #include "tc_host.cuh"
 
 namespace {
@@ -686,6 +689,8 @@ static int pose_forward_impl(pose_plan_s* p, const float* depth, const float* H2
   return 0;
 }
 
+#include "attn_plan.inl"
+
 // =================================================================================================
 // C ABI
 // =================================================================================================
@@ -956,5 +961,61 @@ int joint_error_forward(const float* labels, const float* results, int N, int J,
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
+
+// ---- attention (centre-of-mass) CNN ----------------------------------------------------------------
+int attn_plan_create(int N, int H, int W, const int* widths, int fc_hidden, int O, attn_plan_t* out) {
+  if (!out || !widths) return fail(HGRU_E_INVALID, "attn_plan_create: null pointer");
+  *out = nullptr;
+  if (N < 1 || H < 1 || W < 1 || fc_hidden < 1 || O < 1)
+    return fail(HGRU_E_INVALID, "attn_plan_create: non-positive shape");
+  for (int i = 0; i < 5; ++i)
+    if (widths[i] < 8 || widths[i] % 8) return fail(HGRU_E_UNSUPPORTED, "attn_plan_create: widths must be multiples of 8");
+  attn_plan_s* p = new attn_plan_s();
+  p->N = N; p->H = H; p->W = W; p->F = fc_hidden; p->O = O;
+  for (int i = 0; i < 5; ++i) p->w[i] = widths[i];
+  const int rc = attn_plan_build(p);
+  if (rc) {
+    attn_plan_free(p);
+    delete p;
+    return rc;
+  }
+  *out = p;
+  return 0;
+}
+
+int attn_plan_destroy(attn_plan_t plan) {
+  if (!plan) return 0;
+  attn_plan_free(plan);
+  delete plan;
+  return 0;
+}
+
+int attn_set_params(attn_plan_t plan, const attn_params_t* params, float bn_epsilon, void* stream) {
+  if (!plan) return fail(HGRU_E_INVALID, "attn_set_params: null plan");
+  return attn_set_params_impl(plan, params, bn_epsilon, static_cast<cudaStream_t>(stream));
+}
+
+int attn_forward(attn_plan_t plan, const float* frames_dev, float* out_dev, void* stream) {
+  if (!plan) return fail(HGRU_E_INVALID, "attn_forward: null plan");
+  return attn_forward_impl(plan, frames_dev, out_dev, static_cast<cudaStream_t>(stream));
+}
+
+int attn_get_activation(attn_plan_t plan, const char* name, float* dst, void* stream) {
+  if (!plan || !name || !dst) return fail(HGRU_E_INVALID, "attn_get_activation: null pointer");
+  const std::string n(name);
+  const void* src = nullptr;
+  size_t bytes = 0;
+  if (n == "resized") { src = plan->resized.p; bytes = plan->resized.bytes; }
+  else if (n == "fc1") { src = plan->fc1.p; bytes = plan->fc1.bytes; }
+  else if (n.size() == 5 && n.compare(0, 4, "pool") == 0 && n[4] >= '1' && n[4] <= '5') {
+    src = plan->pool[n[4] - '1'].p; bytes = plan->pool[n[4] - '1'].bytes;
+  }
+  if (!src) return fail(HGRU_E_INVALID, "attn_get_activation: unknown tensor name '" + n + "'");
+  CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+size_t attn_plan_workspace_bytes(attn_plan_t plan) { return plan ? plan->workspace_bytes() : 0; }
+int attn_plan_launch_count(attn_plan_t plan) { return plan ? plan->launches : 0; }
 
 }  // extern "C"

@@ -140,3 +140,27 @@ def synthetic_depth(n, seed=1234, size=128, uniform=False):
         img = np.where(mask, d, 1.0).astype(np.float32)
         out[i, :, :, 0] = img
     return out
+
+
+ATTN_BN_SCOPES = BN_SCOPES[:5] + ("batch_normalization_5",)
+ATTN_CONV = (("aconv_1", 3), ("aconv_2", 3), ("aconv_3", 3), ("aconv_4", 3), ("aconv_5", 5))
+
+
+def attn_params(widths=(64, 128, 256, 512, 1024), fc_hidden=1024, out=3, seed=42, random_bn=False):
+    """All variables of attn_model_struct (train_cnn_networks_hgru.py:440-525) keyed by the reference's names:
+    xavier-normal filters / weights, truncated_normal(0, .001) biases (:566-592), batch-norm defaults."""
+    rng = np.random.default_rng(seed + 11)
+    P, cin = {}, 1
+    for (name, fs), co in zip(ATTN_CONV, widths):
+        P["%s/%s_filters" % (name, name)] = xavier_normal(rng, (fs, fs, cin, co))
+        P["%s/%s_biases" % (name, name)] = _truncated_normal(rng, (co,), 0.001)
+        cin = co
+    P["afc_1/afc_1_weights"] = xavier_normal(rng, (16 * widths[4], fc_hidden))
+    P["afc_1/afc_1_biases"] = _truncated_normal(rng, (fc_hidden,), 0.001)
+    P["afc_out/afc_out_weights"] = xavier_normal(rng, (fc_hidden, out))
+    P["afc_out/afc_out_biases"] = _truncated_normal(rng, (out,), 0.001)
+    for scope, c in zip(ATTN_BN_SCOPES, tuple(widths) + (fc_hidden,)):
+        bn = bn_random(rng, c) if random_bn else bn_identity(c)
+        for n, v in bn.items():
+            P["%s/%s" % (scope, n)] = v
+    return P

@@ -238,3 +238,51 @@ def test_postprocess_bit_exact_against_reference_golden():
     # single-frame host methods mirror the reference API too
     a, b = md.getAbsoluteCoordinates(z["xyz"][0] - md.uvdtoxyz(z["coms"][0]), z["coms"][0])
     assert np.allclose(b, z["uvd"][0], rtol=1e-5, atol=1e-3)
+
+
+# ---- attention (centre-of-mass) CNN ----------------------------------------------
+def _attn_golden():
+    z = np.load(os.path.join(GOLDEN, "attn_ref.npz"))
+    return z["frames"], {k[4:]: z[k] for k in z.files if k.startswith("var:")}, \
+        {k[4:]: z[k] for k in z.files if k.startswith("act:")}
+
+
+@pytest.mark.gpu
+def test_attn_model_matches_reference_golden_every_layer():
+    """attn_model_struct against the outputs of the reference's own class (tests/golden/make_golden_attn.py):
+    the resize bit for bit, every pooled feature map and the head within the split-bf16 budget."""
+    frames, P, A = _attn_golden()
+    m = mp.attn_model_struct()
+    m.load_params(P)
+    out = m.build(torch.as_tensor(frames).cuda(), 3, train_mode=False)
+    assert out.shape == (2, 3) and m.gpu_launches > 0
+    assert np.array_equal(m.activation("resized").cpu().numpy()[..., 0], A["resized"][..., 0])
+    for k in ("pool1", "pool2", "pool3", "pool4", "pool5"):
+        assert onp.rel_err(getattr(m, k).cpu().numpy(), A[k])[0] < 1e-4, k
+    assert onp.rel_err(m.fc1.cpu().numpy(), A["fc1"])[0] < 1e-4
+    assert onp.rel_err(out.cpu().numpy(), A["out_put"])[0] < 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", [(3, 424, 512, (64, 128, 256, 512, 1024), 1024), (5, 96, 80, (8, 24, 16, 40, 32), 64)])
+def test_attn_model_vs_oracle(cfg):
+    """Reference widths on Kinect-size frames (and an odd small configuration) against the fp64 torch oracle."""
+    from oracle import attn_oracle_torch as atorch
+    N, H, W, widths, F = cfg
+    P = init.attn_params(widths, F, 3, seed=5, random_bn=True)
+    rng = np.random.default_rng(3)
+    frames = rng.uniform(0.06, 0.4, size=(N, H, W, 1)).astype(np.float32)
+    frames[rng.uniform(size=frames.shape) < 0.05] = 0.0
+    m = mp.attn_model_struct()
+    m.load_params(P)
+    out = m.build(torch.as_tensor(frames).cuda(), 3)
+    ref, acts = atorch.attn_forward(frames, P, dtype=torch.float64, trace=True)
+    assert onp.rel_err(m.pool3.cpu().numpy(), acts["pool3"].numpy())[0] < 1e-4
+    assert onp.rel_err(m.pool5.cpu().numpy(), acts["pool5"].numpy())[0] < 1e-4
+    assert onp.rel_err(out.cpu().numpy(), ref.numpy())[0] < 1e-4
+    # determinism + the error convention of the mirror
+    assert torch.equal(out, m.build(torch.as_tensor(frames).cuda(), 3))
+    with pytest.raises(NotImplementedError):
+        m.build(torch.as_tensor(frames).cuda(), 3, train_mode=True)
+    with pytest.raises(RuntimeError):
+        m.build(torch.as_tensor(frames), 3)
