@@ -282,7 +282,7 @@ def run_ours(a):
     stages = None
     if not a.no_stages and world == 1 and a.mode == "bf16":
         try:
-            stages = neighbour_stages(a, m, torch, mp)
+            stages = neighbour_stages(a, m, torch, mp, init)
         except Exception as e:                      # never lose the headline line to an auxiliary measurement
             stages = {"error": repr(e)}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps,
@@ -300,7 +300,7 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
-def neighbour_stages(a, m, torch, mp):
+def neighbour_stages(a, m, torch, mp, init_mod):
     """SURVEY 8(f) rows 1 + 2, measured at the same batch on rank 0: the GPU crop stage before the network
     (prepare_data_test -> cropArea3D) and the post-processing after it (absolute coordinates + joint error), plus
     the whole chain camera frames -> joints through the public API with host buffers.  HBM-bound byte work:
@@ -362,8 +362,17 @@ def neighbour_stages(a, m, torch, mp):
     post_gpu_ms, post_wall_ms, _ = ev_time(lambda: pe.getMeanError_np(
         labels, md.getAbsoluteCoordinates_batch(out, coms, 600.0)[0]))
 
+    # attention (centre-of-mass) CNN at the reference's widths: the network that produces the crop centres
+    am = mp.attn_model_struct()
+    am.load_params(init_mod.attn_params(seed=8))
+    attn_gpu_ms, attn_wall_ms, attn_out = ev_time(lambda: am.build(frames_dev, 3), 3)
+    attn_flops = 2.0 * B * (128 * 128 * 9 * 64 + 64 * 64 * 9 * 64 * 128 + 32 * 32 * 9 * 128 * 256 +
+                            16 * 16 * 9 * 256 * 512 + 8 * 8 * 25 * 512 * 1024 + 16384 * 1024 + 1024 * 3)
+
     def chain():
-        p, cs, _ = tmd.prepare_data_test(frames_pin.cuda(non_blocking=True), coms_norm, md, Cfg())
+        f = frames_pin.cuda(non_blocking=True)
+        am.build(f, 3)                               # its output would drive the crop; fixed centres keep it valid
+        p, cs, _ = tmd.prepare_data_test(f, coms_norm, md, Cfg())
         xyz, _ = md.getAbsoluteCoordinates_batch(m.build(p, 69), cs, 600.0)
         return xyz.cpu()
 
@@ -383,7 +392,15 @@ def neighbour_stages(a, m, torch, mp):
                              "kernel; frames resident in HBM"},
             "post": {"gpu_ms": post_gpu_ms, "wall_ms": post_wall_ms,
                      "note": "x600 + CoM, xyz->uvd, mean joint error; 23 joints per frame, latency-bound"},
+            "attention_cnn": {"gpu_ms": attn_gpu_ms, "frames_per_s": B / (attn_gpu_ms * 1e-3),
+                              "algorithmic_TFLOP/s": attn_flops / (attn_gpu_ms * 1e-3) * 1e-12,
+                              "launches": am.gpu_launches,
+                              "note": "attn_model_struct.build at 64..1024 channels: resize + 5 x (conv, relu, "
+                                      "pool, batch-norm) + 2 fc; convs as tcgen05 GEMMs over im2col with bf16 "
+                                      "hi/lo splits (3 MMAs per k-step)"},
             "frames_to_joints_e2e": {"value": B / (chain_wall_ms * 1e-3), "unit": UNIT, "wall_ms": chain_wall_ms,
+                                     "stages": "H2D frames, attention CNN, crop, hGRU pose net, post-processing, "
+                                               "D2H joints",
                                      "h2d_bytes": int(frames_np.nbytes), "d2h_bytes": int(B * 69 * 4)}}
 
 
