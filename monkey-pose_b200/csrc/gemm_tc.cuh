@@ -165,26 +165,6 @@ gemm_tc_splitk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   }
 }
 
-// A operand of fc_1: bf16 [M][HW*k] = (H2[m][pix][c] * scale[c] + shift[c]) over real channels
-// (the inference batch-norm of the hGRU output, hgru_pose.py:82-90, applied while flattening);
-// H2 is read from the quad-chunked state layout [n][c/4][pix][4].
-// Output row m: [hi(0..K) | pad | lo(0..K) | pad], row pitch 2*Kpad (pad columns are zero-initialised once).
-__global__ void __launch_bounds__(256)
-fc1_pack_a_kernel(const float* __restrict__ h2, const float* __restrict__ sc, const float* __restrict__ sh,
-                  __nv_bfloat16* __restrict__ a, size_t npix, int k, int KP, int HW, int Kpad) {
-  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-  if (i >= npix * k) return;
-  const int c = i % k;
-  const size_t p = i / k;
-  const size_t n = p / HW, pin = p - n * HW;
-  const float v = h2[((n * (KP >> 2) + (c >> 2)) * HW + pin) * 4 + (c & 3)] * sc[c] + sh[c];
-  const __nv_bfloat16 hi = __float2bfloat16(v);
-  const size_t col = static_cast<size_t>(c) * HW + pin;     // channel-major K order (see transpose_to_bf16_kernel)
-  __nv_bfloat16* row = a + n * (2 * static_cast<size_t>(Kpad));
-  row[col] = hi;
-  row[Kpad + col] = __float2bfloat16(v - __bfloat162float(hi));
-}
-
 // fc_1 weights [K][F] fp32 -> bf16 [F][hi(0..K) | pad | lo(0..K) | pad] (K-major B operand, row pitch
 // 2*Kpad); 32x32 tiles through shared memory.  The reference's K index (pin*k + c, tf.reshape of NHWC) is
 // permuted to channel-major (c*HW + pin), the order in which the H2 epilogue emits the A operand.

@@ -903,7 +903,6 @@ int pose_forward_host(pose_plan_t p, const float* depth_host, const float* H2_in
 int pose_get_activation(pose_plan_t p, const char* name, float* dst, void* stream) {
   if (!p || !name || !dst) return fail(HGRU_E_INVALID, "pose_get_activation: null argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const size_t npix = static_cast<size_t>(p->N) * p->HW * p->HW;
   const float* src = nullptr;
   if (!strcmp(name, "pool1")) src = p->pool1.as<float>();
   else if (!strcmp(name, "conv2")) src = p->conv2.as<float>();

@@ -402,20 +402,6 @@ quad_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, size_
   const size_t n = p / HW, pin = p - n * HW;
   out[i] = in[((n * (KP >> 2) + (c >> 2)) * HW + pin) * 4 + (c & 3)];
 }
-__global__ void __launch_bounds__(256)
-quad_to_chunked_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t npix, int KP,
-                            int HW) {
-  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;   // over [n][cg][pin]
-  const int CG = KP >> 3;
-  if (i >= npix * CG) return;
-  const size_t pin = i % HW;
-  const int cg = (i / HW) % CG;
-  const size_t n = i / (static_cast<size_t>(HW) * CG);
-  const float4 a = *reinterpret_cast<const float4*>(in + ((n * (KP >> 2) + 2 * cg) * HW + pin) * 4);
-  const float4 b = *reinterpret_cast<const float4*>(in + ((n * (KP >> 2) + 2 * cg + 1) * HW + pin) * 4);
-  const F8 f{{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w}};
-  st8_bf16(out + i * 8, f);
-}
 
 // ------------------------------------------------------------------------------------------------
 // Initial state of the tensor-core path in one pass: O_0 (NHWC, k channels; hgru_module.py:884-887)
