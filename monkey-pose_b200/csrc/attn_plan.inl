@@ -20,6 +20,7 @@ struct attn_plan_s {
   int bnw = 0;
   // geometry of the GEMM layers (index 1..4 = conv 2..5, index 5 = fc_1)
   int gK[6] = {0}, gKpad[6] = {0}, gM[6] = {0}, gN[6] = {0}, gSplits[6] = {0}, gKbps[6] = {0};
+  int gBN[6] = {0};              // N tile of the layer's GEMM: 128 when the output has <= 128 columns, else 256
   CUtensorMap mapA[6], mapB[6];
   // workspace
   DevBuf resized, pool[5], a_op, part, fc1, out;
@@ -69,7 +70,8 @@ static int attn_plan_build(attn_plan_s* p) {
     p->gM[g] = fc ? N : N * hw * hw;
     p->gN[g] = fc ? p->F : p->w[g];
     const int total_kb = p->gKpad[g] / hgru::kGemmBK;
-    const int ntn = (p->gN[g] + hgru::kGemmBN - 1) / hgru::kGemmBN, ntm = (p->gM[g] + hgru::kGemmBM - 1) / hgru::kGemmBM;
+    p->gBN[g] = p->gN[g] <= 128 ? 128 : 256;
+    const int ntn = (p->gN[g] + p->gBN[g] - 1) / p->gBN[g], ntm = (p->gM[g] + hgru::kGemmBM - 1) / hgru::kGemmBM;
     int splits = sms / (2 * ntn * ntm);               // split K only when the tile grid leaves SMs idle
     if (splits < 1) splits = 1;
     if (splits > total_kb) splits = total_kb;
@@ -92,11 +94,13 @@ static int attn_plan_build(attn_plan_s* p) {
     const size_t pitch = 2 * static_cast<size_t>(p->gKpad[g]);
     DevBuf& wbuf = g == 5 ? p->fc1_wt : p->wt[g];
     if (hgru::make_kmajor_bf16_map(&p->mapA[g], p->a_op.p, p->gM[g], pitch, hgru::kGemmBM) ||
-        hgru::make_kmajor_bf16_map(&p->mapB[g], wbuf.p, p->gN[g], pitch, hgru::kGemmBN))
+        hgru::make_kmajor_bf16_map(&p->mapB[g], wbuf.p, p->gN[g], pitch, p->gBN[g]))
       return fail(HGRU_E_CUDA, "cuTensorMapEncodeTiled (attention CNN) failed");
   }
-  CUDA_TRY(cudaFuncSetAttribute(hgru::gemm_tc_splitk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                hgru::kGemmSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(hgru::gemm_tc_splitk_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                hgru::GemmCfg<256>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(hgru::gemm_tc_splitk_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                hgru::GemmCfg<128>::kSmemBytes));
   A(p->fc1_b, sizeof(float) * p->F);
   A(p->fc2_w, sizeof(float) * p->F * p->O); A(p->fc2_b, sizeof(float) * p->O);
   A(p->bn, sizeof(float) * 6 * 2 * p->bnw);
@@ -167,9 +171,12 @@ static int attn_forward_impl(attn_plan_s* p, const float* frames, float* out, cu
     hgru::im2col_split_kernel<<<nblk(threads), 256, 0, st>>>(p->pool[g - 1].as<float>(), p->a_op.as<__nv_bfloat16>(),
                                                             N, ih, ih, cin, S, p->gKpad[g]);
     hgru::GemmArgs ga{p->gM[g], p->gN[g], p->gK[g], p->gKpad[g], p->gKbps[g], p->part.as<float>()};
-    dim3 grid((p->gN[g] + hgru::kGemmBN - 1) / hgru::kGemmBN, (p->gM[g] + hgru::kGemmBM - 1) / hgru::kGemmBM,
+    dim3 grid((p->gN[g] + p->gBN[g] - 1) / p->gBN[g], (p->gM[g] + hgru::kGemmBM - 1) / hgru::kGemmBM,
               p->gSplits[g]);
-    hgru::gemm_tc_splitk_kernel<<<grid, 256, hgru::kGemmSmemBytes, st>>>(p->mapA[g], p->mapB[g], ga);
+    if (p->gBN[g] == 128)
+      hgru::gemm_tc_splitk_kernel<128><<<grid, 256, hgru::GemmCfg<128>::kSmemBytes, st>>>(p->mapA[g], p->mapB[g], ga);
+    else
+      hgru::gemm_tc_splitk_kernel<256><<<grid, 256, hgru::GemmCfg<256>::kSmemBytes, st>>>(p->mapA[g], p->mapB[g], ga);
     p->launches += 2;
     if (!fc) {
       // bias + relu (:553-554), max-pool (:540-543), batch-norm

@@ -22,11 +22,17 @@ namespace hgru {
 // products  A_hi*B_hi + A_lo*B_hi + A_hi*B_lo  (fp32-class accuracy: K = 262 144 bf16 products would
 // otherwise contribute ~2.5e-3 relative error, the largest single error of the bf16 path).  A stage holds
 // the four tiles so B_hi is fetched once for two products; 2 stages x 96 KB.
-constexpr int kGemmBM = 128, kGemmBN = 256, kGemmBK = 64, kGemmStages = 2;
+constexpr int kGemmBM = 128, kGemmBN = 256, kGemmBK = 64;
 constexpr int kGemmABytes = kGemmBM * kGemmBK * 2;    // 16 KB
-constexpr int kGemmBBytes = kGemmBN * kGemmBK * 2;    // 32 KB
-constexpr int kGemmStageBytes = 2 * kGemmABytes + 2 * kGemmBBytes;   // A_hi, A_lo, B_hi, B_lo
-constexpr int kGemmSmemBytes = kGemmStages * kGemmStageBytes + 256 + 1024;
+template <int BN>
+struct GemmCfg {
+  static_assert(BN == 128 || BN == 256, "N tile");
+  static constexpr int kStages = BN == 256 ? 2 : 3;
+  static constexpr int kBBytes = BN * kGemmBK * 2;                       // 32 / 16 KB
+  static constexpr int kStageBytes = 2 * kGemmABytes + 2 * kBBytes;      // A_hi, A_lo, B_hi, B_lo
+  static constexpr int kSmemBytes = kStages * kStageBytes + 256 + 1024;
+};
+constexpr int kGemmSmemBytes = GemmCfg<kGemmBN>::kSmemBytes;
 
 struct GemmArgs {
   int M, Nn, K;          // problem size
@@ -47,10 +53,15 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {
   return d;
 }
 
+// BN = 256 (2 stages x 96 KB) for wide outputs; BN = 128 (3 stages x 64 KB) where the output has <= 128 columns,
+// so that half of every MMA is not spent on zero-filled B rows.
+template <int BN>
 __global__ void __launch_bounds__(256, 1)
 gemm_tc_splitk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                       const GemmArgs g) {
   using namespace sm100;
+  constexpr int kGemmBN = BN, kGemmStages = GemmCfg<BN>::kStages, kGemmBBytes = GemmCfg<BN>::kBBytes;
+  constexpr int kGemmStageBytes = GemmCfg<BN>::kStageBytes;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = base + kGemmStages * kGemmStageBytes;
@@ -70,7 +81,7 @@ gemm_tc_splitk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
   }
-  if (warp == 2) tmem_alloc<256>(tmem_slot);
+  if (warp == 2) tmem_alloc<BN>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -161,7 +172,7 @@ gemm_tc_splitk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<256>(tmem_base);
+    tmem_dealloc<BN>(tmem_base);
   }
 }
 

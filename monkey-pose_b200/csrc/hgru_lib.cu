@@ -671,7 +671,7 @@ static int pose_forward_impl(pose_plan_s* p, const float* depth, const float* H2
   if (p->fc1_tc) {
     hgru::GemmArgs g{N, p->F, K, p->fc_kpad, p->fc_kbps, p->part.as<float>()};
     dim3 grid((p->F + hgru::kGemmBN - 1) / hgru::kGemmBN, (N + hgru::kGemmBM - 1) / hgru::kGemmBM, p->fc_splits);
-    hgru::gemm_tc_splitk_kernel<<<grid, 256, hgru::kGemmSmemBytes, st>>>(p->map_fc_a, p->map_fc_b, g);
+    hgru::gemm_tc_splitk_kernel<hgru::kGemmBN><<<grid, 256, hgru::kGemmSmemBytes, st>>>(p->map_fc_a, p->map_fc_b, g);
     nsplit = p->fc_splits;
     ++p->launches;
   } else {
@@ -793,7 +793,7 @@ int pose_plan_create(int N, int HW, int C, int S, int T, int F, int O, int mode,
     if (!rc && (hgru::make_kmajor_bf16_map(&p->map_fc_a, p->fc1_a.p, N, pitch, hgru::kGemmBM) ||
                 hgru::make_kmajor_bf16_map(&p->map_fc_b, p->fc1_wt.p, F, pitch, hgru::kGemmBN)))
       rc = fail(HGRU_E_CUDA, "cuTensorMapEncodeTiled (fc_1) failed");
-    if (!rc && cudaFuncSetAttribute(hgru::gemm_tc_splitk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (!rc && cudaFuncSetAttribute(hgru::gemm_tc_splitk_kernel<hgru::kGemmBN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     hgru::kGemmSmemBytes) != cudaSuccess)
       rc = fail(HGRU_E_CUDA, "cudaFuncSetAttribute(gemm_tc_splitk_kernel) failed");
   } else {
