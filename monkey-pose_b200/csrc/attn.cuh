@@ -87,6 +87,8 @@ im2col_split_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ a,
 __global__ void __launch_bounds__(256)
 bias_relu_pool_bn_kernel(const float* __restrict__ part, int nsplit, const float* __restrict__ bias,
                          const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ out,
+                         __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo /* optional bf16
+                         hi / lo copies (same NHWC layout): the next layer's implicit-GEMM operand */,
                          int N, int H, int W, int C) {
   const int c4n = C >> 2, PH = H >> 1, PW = W >> 1;
   const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
@@ -115,8 +117,38 @@ bias_relu_pool_bn_kernel(const float* __restrict__ part, int nsplit, const float
     }
   const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + c4);
   const float4 sf = __ldg(reinterpret_cast<const float4*>(shift) + c4);
-  reinterpret_cast<float4*>(out + p * C)[c4] =
-      make_float4(m.x * sc.x + sf.x, m.y * sc.y + sf.y, m.z * sc.z + sf.z, m.w * sc.w + sf.w);
+  const float r[4] = {m.x * sc.x + sf.x, m.y * sc.y + sf.y, m.z * sc.z + sf.z, m.w * sc.w + sf.w};
+  reinterpret_cast<float4*>(out + p * C)[c4] = make_float4(r[0], r[1], r[2], r[3]);
+  if (out_hi) {
+    __nv_bfloat162 hi[2], lo[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const __nv_bfloat16 h0 = __float2bfloat16(r[2 * j]), h1 = __float2bfloat16(r[2 * j + 1]);
+      hi[j] = __halves2bfloat162(h0, h1);
+      lo[j] = __floats2bfloat162_rn(r[2 * j] - __bfloat162float(h0), r[2 * j + 1] - __bfloat162float(h1));
+    }
+    reinterpret_cast<uint2*>(out_hi + p * C)[c4] = *reinterpret_cast<const uint2*>(hi);
+    reinterpret_cast<uint2*>(out_lo + p * C)[c4] = *reinterpret_cast<const uint2*>(lo);
+  }
+}
+
+// fp32 -> bf16 hi + lo (x ~ hi + lo to ~16 mantissa bits), 8 elements per thread; n % 8 == 0.
+__global__ void __launch_bounds__(256)
+split_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                  size_t n8) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= n8) return;
+  const float4 a = __ldg(reinterpret_cast<const float4*>(in) + 2 * i), b = __ldg(reinterpret_cast<const float4*>(in) + 2 * i + 1);
+  const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  __nv_bfloat162 h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __nv_bfloat16 h0 = __float2bfloat16(v[2 * j]), h1 = __float2bfloat16(v[2 * j + 1]);
+    h[j] = __halves2bfloat162(h0, h1);
+    l[j] = __floats2bfloat162_rn(v[2 * j] - __bfloat162float(h0), v[2 * j + 1] - __bfloat162float(h1));
+  }
+  reinterpret_cast<uint4*>(hi)[i] = *reinterpret_cast<const uint4*>(h);
+  reinterpret_cast<uint4*>(lo)[i] = *reinterpret_cast<const uint4*>(l);
 }
 
 }  // namespace hgru

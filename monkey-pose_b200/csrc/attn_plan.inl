@@ -22,6 +22,11 @@ struct attn_plan_s {
   int gK[6] = {0}, gKpad[6] = {0}, gM[6] = {0}, gN[6] = {0}, gSplits[6] = {0}, gKbps[6] = {0};
   int gBN[6] = {0};              // N tile of the layer's GEMM: 128 when the output has <= 128 columns, else 256
   CUtensorMap mapA[6], mapB[6];
+  // implicit-GEMM convolution (input channels % 64 == 0): 4-D TMA boxes over bf16 hi / lo NHWC activations
+  bool implicit_[6] = {false, false, false, false, false, false};
+  int gBY[6] = {0}, gNF[6] = {0};
+  CUtensorMap mapAhi[6], mapAlo[6];
+  DevBuf act_hi[4], act_lo[4];   // bf16 copies of pool[0..3]
   // workspace
   DevBuf resized, pool[5], a_op, part, fc1, out;
   float* bn_scale(int i) { return bn.as<float>() + static_cast<size_t>(2 * i) * bnw; }
@@ -30,6 +35,7 @@ struct attn_plan_s {
     size_t s = w1.bytes + b1.bytes + fc1_wt.bytes + fc1_b.bytes + fc2_w.bytes + fc2_b.bytes + bn.bytes +
                resized.bytes + a_op.bytes + part.bytes + fc1.bytes + out.bytes;
     for (int i = 0; i < 5; ++i) s += wt[i].bytes + cb[i].bytes + pool[i].bytes;
+    for (int i = 0; i < 4; ++i) s += act_hi[i].bytes + act_lo[i].bytes;
     return s;
   }
 };
@@ -42,6 +48,7 @@ static void attn_plan_free(attn_plan_s* p) {
                    &p->part, &p->fc1, &p->out};
   for (auto b : all) b->release();
   for (int i = 0; i < 5; ++i) { p->wt[i].release(); p->cb[i].release(); p->pool[i].release(); }
+  for (int i = 0; i < 4; ++i) { p->act_hi[i].release(); p->act_lo[i].release(); }
 }
 
 static int attn_plan_build(attn_plan_s* p) {
@@ -78,7 +85,18 @@ static int attn_plan_build(attn_plan_s* p) {
     p->gKbps[g] = (total_kb + splits - 1) / splits;
     p->gSplits[g] = (total_kb + p->gKbps[g] - 1) / p->gKbps[g];
     const size_t pitch = 2 * static_cast<size_t>(p->gKpad[g]);
-    a_max = std::max(a_max, sizeof(__nv_bfloat16) * pitch * p->gM[g]);
+    // implicit GEMM when a k-block never straddles a tap (Cin % 64 == 0) and 128-pixel tiles are whole image rows
+    const int ppf = hw * hw;
+    p->implicit_[g] = !fc && cin % hgru::kGemmBK == 0 && hw <= 64 && hgru::kGemmBM % hw == 0 &&
+                      (ppf % hgru::kGemmBM == 0 || hgru::kGemmBM % ppf == 0);
+    if (p->implicit_[g]) {
+      p->gBY[g] = ppf >= hgru::kGemmBM ? hgru::kGemmBM / hw : hw;
+      p->gNF[g] = ppf >= hgru::kGemmBM ? 1 : hgru::kGemmBM / ppf;
+      const size_t ab = sizeof(__nv_bfloat16) * static_cast<size_t>(N) * ppf * cin;
+      A(p->act_hi[g - 1], ab); A(p->act_lo[g - 1], ab);
+    } else {
+      a_max = std::max(a_max, sizeof(__nv_bfloat16) * pitch * p->gM[g]);
+    }
     part_max = std::max(part_max, sizeof(float) * p->gSplits[g] * static_cast<size_t>(p->gM[g]) * p->gN[g]);
     DevBuf& wbuf = fc ? p->fc1_wt : p->wt[g];
     A(wbuf, sizeof(__nv_bfloat16) * pitch * p->gN[g]);
@@ -93,13 +111,23 @@ static int attn_plan_build(attn_plan_s* p) {
   for (int g = 1; g <= 5; ++g) {
     const size_t pitch = 2 * static_cast<size_t>(p->gKpad[g]);
     DevBuf& wbuf = g == 5 ? p->fc1_wt : p->wt[g];
-    if (hgru::make_kmajor_bf16_map(&p->mapA[g], p->a_op.p, p->gM[g], pitch, hgru::kGemmBM) ||
-        hgru::make_kmajor_bf16_map(&p->mapB[g], wbuf.p, p->gN[g], pitch, p->gBN[g]))
-      return fail(HGRU_E_CUDA, "cuTensorMapEncodeTiled (attention CNN) failed");
+    int bad = hgru::make_kmajor_bf16_map(&p->mapB[g], wbuf.p, p->gN[g], pitch, p->gBN[g]);
+    if (p->implicit_[g]) {
+      const int ih = kAttnHW >> g, cin = p->w[g - 1];
+      bad |= hgru::make_nhwc_bf16_map(&p->mapAhi[g], p->act_hi[g - 1].p, N, ih, ih, cin, ih, p->gBY[g], p->gNF[g]);
+      bad |= hgru::make_nhwc_bf16_map(&p->mapAlo[g], p->act_lo[g - 1].p, N, ih, ih, cin, ih, p->gBY[g], p->gNF[g]);
+    } else {
+      bad |= hgru::make_kmajor_bf16_map(&p->mapA[g], p->a_op.p, p->gM[g], pitch, hgru::kGemmBM);
+    }
+    if (bad) return fail(HGRU_E_CUDA, "cuTensorMapEncodeTiled (attention CNN) failed");
   }
   CUDA_TRY(cudaFuncSetAttribute(hgru::gemm_tc_splitk_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 hgru::GemmCfg<256>::kSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(hgru::gemm_tc_splitk_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                hgru::GemmCfg<128>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(hgru::gemm_tc_splitk_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                hgru::GemmCfg<256>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(hgru::gemm_tc_splitk_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 hgru::GemmCfg<128>::kSmemBytes));
   A(p->fc1_b, sizeof(float) * p->F);
   A(p->fc2_w, sizeof(float) * p->F * p->O); A(p->fc2_b, sizeof(float) * p->O);
@@ -159,31 +187,51 @@ static int attn_forward_impl(attn_plan_s* p, const float* frames, float* out, cu
         p->pool[0].as<float>(), nullptr, N, HW, HW, C, C, 0);
   }
   p->launches += 2;
+  if (p->implicit_[1]) {
+    const size_t n8 = static_cast<size_t>(N) * (kAttnHW / 2) * (kAttnHW / 2) * p->w[0] / 8;
+    hgru::split_bf16_kernel<<<nblk(n8), 256, 0, st>>>(p->pool[0].as<float>(), p->act_hi[0].as<__nv_bfloat16>(),
+                                                     p->act_lo[0].as<__nv_bfloat16>(), n8);
+    ++p->launches;
+  }
   int hw = kAttnHW / 2;
   for (int g = 1; g <= 5; ++g) {
     const bool fc = g == 5;
     const int S = fc ? 1 : kAttnS[g];
     const int cin = fc ? 16 * p->w[4] : p->w[g - 1];
     const int ih = fc ? 1 : hw;
-    if (p->gKpad[g] != p->gK[g])     // the shared operand buffer's pad columns must read as zero for this pitch
-      CUDA_TRY(cudaMemsetAsync(p->a_op.p, 0, sizeof(__nv_bfloat16) * 2 * static_cast<size_t>(p->gKpad[g]) * p->gM[g], st));
-    const size_t threads = static_cast<size_t>(p->gM[g]) * S * S * (cin / 8);
-    hgru::im2col_split_kernel<<<nblk(threads), 256, 0, st>>>(p->pool[g - 1].as<float>(), p->a_op.as<__nv_bfloat16>(),
-                                                            N, ih, ih, cin, S, p->gKpad[g]);
-    hgru::GemmArgs ga{p->gM[g], p->gN[g], p->gK[g], p->gKpad[g], p->gKbps[g], p->part.as<float>()};
+    hgru::GemmArgs ga{p->gM[g], p->gN[g], p->gK[g], p->gKpad[g], p->gKbps[g], p->part.as<float>(),
+                      S, cin, ih, ih, p->gBY[g], p->gNF[g]};
     dim3 grid((p->gN[g] + p->gBN[g] - 1) / p->gBN[g], (p->gM[g] + hgru::kGemmBM - 1) / hgru::kGemmBM,
               p->gSplits[g]);
-    if (p->gBN[g] == 128)
-      hgru::gemm_tc_splitk_kernel<128><<<grid, 256, hgru::GemmCfg<128>::kSmemBytes, st>>>(p->mapA[g], p->mapB[g], ga);
-    else
-      hgru::gemm_tc_splitk_kernel<256><<<grid, 256, hgru::GemmCfg<256>::kSmemBytes, st>>>(p->mapA[g], p->mapB[g], ga);
-    p->launches += 2;
+    if (p->implicit_[g]) {
+      // conv as an implicit GEMM: the A tile of a k-block is one TMA box of the bf16 activation, shifted by the tap
+      if (p->gBN[g] == 128)
+        hgru::gemm_tc_splitk_kernel<128, true><<<grid, 256, hgru::GemmCfg<128>::kSmemBytes, st>>>(
+            p->mapAhi[g], p->mapAlo[g], p->mapB[g], ga);
+      else
+        hgru::gemm_tc_splitk_kernel<256, true><<<grid, 256, hgru::GemmCfg<256>::kSmemBytes, st>>>(
+            p->mapAhi[g], p->mapAlo[g], p->mapB[g], ga);
+      ++p->launches;
+    } else {
+      if (p->gKpad[g] != p->gK[g])   // the shared operand buffer's pad columns must read as zero for this pitch
+        CUDA_TRY(cudaMemsetAsync(p->a_op.p, 0, sizeof(__nv_bfloat16) * 2 * static_cast<size_t>(p->gKpad[g]) * p->gM[g], st));
+      const size_t threads = static_cast<size_t>(p->gM[g]) * S * S * (cin / 8);
+      hgru::im2col_split_kernel<<<nblk(threads), 256, 0, st>>>(p->pool[g - 1].as<float>(), p->a_op.as<__nv_bfloat16>(),
+                                                              N, ih, ih, cin, S, p->gKpad[g]);
+      if (p->gBN[g] == 128)
+        hgru::gemm_tc_splitk_kernel<128><<<grid, 256, hgru::GemmCfg<128>::kSmemBytes, st>>>(p->mapA[g], p->mapA[g], p->mapB[g], ga);
+      else
+        hgru::gemm_tc_splitk_kernel<256><<<grid, 256, hgru::GemmCfg<256>::kSmemBytes, st>>>(p->mapA[g], p->mapA[g], p->mapB[g], ga);
+      p->launches += 2;
+    }
     if (!fc) {
       // bias + relu (:553-554), max-pool (:540-543), batch-norm
       const size_t pt = static_cast<size_t>(N) * (hw / 2) * (hw / 2) * (p->w[g] / 4);
-      hgru::bias_relu_pool_bn_kernel<<<nblk(pt), 256, 0, st>>>(p->part.as<float>(), p->gSplits[g], p->cb[g].as<float>(),
-                                                              p->bn_scale(g), p->bn_shift(g), p->pool[g].as<float>(),
-                                                              N, hw, hw, p->w[g]);
+      const bool nxt = g < 4 && p->implicit_[g + 1];      // the next conv reads bf16 hi / lo copies
+      hgru::bias_relu_pool_bn_kernel<<<nblk(pt), 256, 0, st>>>(
+          p->part.as<float>(), p->gSplits[g], p->cb[g].as<float>(), p->bn_scale(g), p->bn_shift(g),
+          p->pool[g].as<float>(), nxt ? p->act_hi[g].as<__nv_bfloat16>() : nullptr,
+          nxt ? p->act_lo[g].as<__nv_bfloat16>() : nullptr, N, hw, hw, p->w[g]);
       ++p->launches;
       hw /= 2;
     }

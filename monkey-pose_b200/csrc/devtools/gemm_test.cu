@@ -56,7 +56,7 @@ int run(int M, int N, int K, int iters) {
   hgru::GemmArgs g{M, N, K, Kpad, kbps, dP};
   CK(cudaFuncSetAttribute(hgru::gemm_tc_splitk_kernel<hgru::kGemmBN>, cudaFuncAttributeMaxDynamicSharedMemorySize, hgru::kGemmSmemBytes));
   dim3 grid((N + 255) / 256, (M + 127) / 128, splits);
-  hgru::gemm_tc_splitk_kernel<hgru::kGemmBN><<<grid, 256, hgru::kGemmSmemBytes>>>(ma, mb, g);
+  hgru::gemm_tc_splitk_kernel<hgru::kGemmBN><<<grid, 256, hgru::kGemmSmemBytes>>>(ma, ma, mb, g);
   CK(cudaGetLastError()); CK(cudaDeviceSynchronize());
   reduce<<<(unsigned)(((size_t)M * N + 255) / 256), 256>>>(dP, dC, splits, (size_t)M * N);
   naive<<<dim3((N + 127) / 128, M), 128>>>(dAf, dBf, dR, M, N, K);
@@ -70,7 +70,7 @@ int run(int M, int N, int K, int iters) {
   if (!bad && iters) {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0);
-    for (int i = 0; i < iters; ++i) hgru::gemm_tc_splitk_kernel<hgru::kGemmBN><<<grid, 256, hgru::kGemmSmemBytes>>>(ma, mb, g);
+    for (int i = 0; i < iters; ++i) hgru::gemm_tc_splitk_kernel<hgru::kGemmBN><<<grid, 256, hgru::kGemmSmemBytes>>>(ma, ma, mb, g);
     cudaEventRecord(e1); CK(cudaDeviceSynchronize());
     float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= iters;
     printf("  %.3f ms  %.1f TFLOP/s  B-stream %.0f GB/s\n", ms, 2.0 * M * N * K / ms * 1e-9, (double)N * K * 4 / ms * 1e-6);

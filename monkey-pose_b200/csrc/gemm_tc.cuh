@@ -39,6 +39,9 @@ struct GemmArgs {
   int Kpad;              // column where the lo halves start (K rounded up to the k-block)
   int kblocks_per_split; // K blocks (of 64) handled by one z slice
   float* part;           // [splits][M][Nn] fp32
+  // implicit-GEMM convolution (CONV = true): A rows are the pixels (n, y, x) of a bf16 NHWC activation, K runs
+  // over (dy, dx, ci); a 128-row tile is `by` image rows of `nf` frames
+  int S, Cin, H, W, by, nf;
 };
 
 // K-major operand tile written by TMA with CU_TENSOR_MAP_SWIZZLE_128B: rows of 128 B, 8-row groups
@@ -55,10 +58,13 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {
 
 // BN = 256 (2 stages x 96 KB) for wide outputs; BN = 128 (3 stages x 64 KB) where the output has <= 128 columns,
 // so that half of every MMA is not spent on zero-filled B rows.
-template <int BN>
+// CONV = true: stride-1 SAME convolution as an implicit GEMM -- the A tile of k-block (tap, 64-channel block) is
+// one 4-D TMA box of the NHWC activation shifted by the tap (zero fill = padding); map_a / map_a_lo are the hi
+// and lo activation tensors.  CONV = false: plain GEMM, map_a_lo is ignored (lo halves sit at column Kpad).
+template <int BN, bool CONV = false>
 __global__ void __launch_bounds__(256, 1)
-gemm_tc_splitk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                      const GemmArgs g) {
+gemm_tc_splitk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a_lo,
+                      const __grid_constant__ CUtensorMap map_b, const GemmArgs g) {
   using namespace sm100;
   constexpr int kGemmBN = BN, kGemmStages = GemmCfg<BN>::kStages, kGemmBBytes = GemmCfg<BN>::kBBytes;
   constexpr int kGemmStageBytes = GemmCfg<BN>::kStageBytes;
@@ -79,6 +85,7 @@ gemm_tc_splitk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     mbar_init(bar_acc, 1);
     fence_barrier_init();
     tma_prefetch_desc(&map_a);
+    if constexpr (CONV) tma_prefetch_desc(&map_a_lo);
     tma_prefetch_desc(&map_b);
   }
   if (warp == 2) tmem_alloc<BN>(tmem_slot);
@@ -102,8 +109,20 @@ gemm_tc_splitk_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         mbar_arrive_expect_tx(bar_full + 8 * st, kGemmStageBytes);
         const uint32_t sa = base + st * kGemmStageBytes;
         const int kc = (kb0 + kb) * kGemmBK;
-        tma_load_2d(sa, &map_a, bar_full + 8 * st, kc, m0);                                     // A_hi
-        tma_load_2d(sa + kGemmABytes, &map_a, bar_full + 8 * st, g.Kpad + kc, m0);              // A_lo
+        if constexpr (CONV) {
+          const int cblks = g.Cin / kGemmBK, kbi = kb0 + kb;
+          const int tap = kbi / cblks, cb = kbi - tap * cblks, pad = (g.S - 1) / 2;
+          const int ppf = g.H * g.W;                      // pixels per frame
+          const int tile = blockIdx.y;
+          const int f0 = ppf >= kGemmBM ? tile / (ppf / kGemmBM) : tile * g.nf;
+          const int y0 = ppf >= kGemmBM ? (tile % (ppf / kGemmBM)) * g.by : 0;
+          const int cx = tap % g.S - pad, cy = y0 + tap / g.S - pad;
+          tma_load_4d(sa, &map_a, bar_full + 8 * st, cb * kGemmBK, cx, cy, f0);                  // A_hi
+          tma_load_4d(sa + kGemmABytes, &map_a_lo, bar_full + 8 * st, cb * kGemmBK, cx, cy, f0); // A_lo
+        } else {
+          tma_load_2d(sa, &map_a, bar_full + 8 * st, kc, m0);                                     // A_hi
+          tma_load_2d(sa + kGemmABytes, &map_a, bar_full + 8 * st, g.Kpad + kc, m0);              // A_lo
+        }
         tma_load_2d(sa + 2 * kGemmABytes, &map_b, bar_full + 8 * st, kc, n0);                   // B_hi
         tma_load_2d(sa + 2 * kGemmABytes + kGemmBBytes, &map_b, bar_full + 8 * st, g.Kpad + kc, n0);   // B_lo
         if (++st == kGemmStages) { st = 0; ph ^= 1; }

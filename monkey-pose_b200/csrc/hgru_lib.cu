@@ -669,9 +669,9 @@ static int pose_forward_impl(pose_plan_s* p, const float* depth, const float* H2
   const int K = HW * HW * C;
   int nsplit = p->nsplit;
   if (p->fc1_tc) {
-    hgru::GemmArgs g{N, p->F, K, p->fc_kpad, p->fc_kbps, p->part.as<float>()};
+    hgru::GemmArgs g{N, p->F, K, p->fc_kpad, p->fc_kbps, p->part.as<float>(), 0, 0, 0, 0, 0, 0};
     dim3 grid((p->F + hgru::kGemmBN - 1) / hgru::kGemmBN, (N + hgru::kGemmBM - 1) / hgru::kGemmBM, p->fc_splits);
-    hgru::gemm_tc_splitk_kernel<hgru::kGemmBN><<<grid, 256, hgru::kGemmSmemBytes, st>>>(p->map_fc_a, p->map_fc_b, g);
+    hgru::gemm_tc_splitk_kernel<hgru::kGemmBN><<<grid, 256, hgru::kGemmSmemBytes, st>>>(p->map_fc_a, p->map_fc_a, p->map_fc_b, g);
     nsplit = p->fc_splits;
     ++p->launches;
   } else {

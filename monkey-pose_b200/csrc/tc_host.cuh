@@ -77,4 +77,24 @@ inline int make_kmajor_bf16_map(CUtensorMap* map, const void* base, size_t rows,
   return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
 }
 
+// Tensor map over a bf16 NHWC activation [N][H][W][C] (C % 64 == 0) for implicit-GEMM convolutions: box =
+// (64 channels = 128 bytes) x box_w x box_h x box_n pixels with the 128-byte swizzle, so a box lands as box_w *
+// box_h * box_n rows of a K-major SW128 UMMA tile in pixel order; out-of-image pixels are zero-filled (= SAME).
+inline int make_nhwc_bf16_map(CUtensorMap* map, const void* base, int N, int H, int W, int C, int box_w, int box_h,
+                              int box_n) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return -1;
+  cuuint64_t gdim[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                        static_cast<cuuint64_t>(N)};
+  cuuint64_t gstr[3] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(W) * C * 2,
+                        static_cast<cuuint64_t>(H) * W * C * 2};
+  cuuint32_t box[4] = {64, static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h),
+                       static_cast<cuuint32_t>(box_n)};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
+}
+
 }  // namespace hgru
