@@ -102,7 +102,7 @@ class model:
         self.data_dict = dd
         self._dev_params = None
 
-    def load_checkpoint(self, prefix, scope="cnn"):
+    def load_checkpoint(self, prefix, scope="cnn", bn_offset=None):
         """Inject the variables of a TensorFlow V2 checkpoint written by the reference's
         `tf.train.Saver` (train_cnn_networks_hgru.py:188, 248-250; restored at :312-313).  `prefix` is what
         `tf.train.latest_checkpoint(config.model_output)` returns; a directory is resolved the same way.
@@ -127,6 +127,16 @@ class model:
                 continue
             wanted[name] = short
         flat = {wanted[n]: v for n, v in tf_checkpoint.read_checkpoint(prefix, names=list(wanted)).items()}
+        # The reference builds the attention CNN first in the same variable scope (:115-117), so its six
+        # tf.layers.batch_normalization calls take the names batch_normalization .. _5 and this model's five
+        # layers are batch_normalization_6 .. _10 in such checkpoints.
+        if bn_offset is None:
+            bn_offset = 6 if any(n.startswith("aconv_1/") for n in flat) else 0
+        if bn_offset:
+            for i, s in enumerate(BN_SCOPES):
+                src = "batch_normalization_%d" % (i + bn_offset)
+                for f in _BN_FIELDS:
+                    flat["%s/%s" % (s, f)] = flat["%s/%s" % (src, f)]
         try:
             self.load_params(flat)
         except KeyError as e:

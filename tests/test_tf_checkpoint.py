@@ -189,3 +189,29 @@ def test_model_load_checkpoint_maps_reference_names(tmp_path):
     os.remove(prefix + ".data-00000-of-00001")
     with pytest.raises(ck.CheckpointError, match="missing data shard"):
         mp.model().load_checkpoint(prefix)
+
+
+def test_model_load_checkpoint_from_the_combined_graph(tmp_path):
+    """Checkpoints of the reference's training graph hold BOTH networks under 'cnn/' (train_cnn_networks_hgru.py:
+    96-142): the attention CNN's batch-norm layers are batch_normalization .. _5, the pose model's _6 .. _10."""
+    import monkey_pose_b200 as mp
+    from monkey_pose_b200 import initialization as init
+    P = init.pose_params(channels=3, S=5, T=2, hw=8, fc_hidden=16, out=6, seed=4, random_bn=True)
+    A = init.attn_params(widths=(8, 8, 8, 8, 8), fc_hidden=16, out=3, seed=2, random_bn=True)
+    flat = {"cnn/" + k: np.asarray(v) for k, v in A.items()}
+    for k, v in P.items():
+        if k.startswith("batch_normalization"):
+            scope, field = k.split("/")
+            i = 0 if scope == "batch_normalization" else int(scope.rsplit("_", 1)[1])
+            k = "batch_normalization_%d/%s" % (i + 6, field)
+        flat["cnn/" + k] = np.asarray(v)
+    prefix = str(tmp_path / "both.ckpt-1")
+    ck.write_checkpoint(prefix, flat)
+    m = mp.model()
+    m.load_checkpoint(prefix)
+    np.testing.assert_array_equal(m.data_dict["batch_normalization_3"][2], P["batch_normalization_3/moving_mean"])
+    np.testing.assert_array_equal(m.data_dict["batch_normalization"][0], P["batch_normalization/gamma"])
+    am = mp.attn_model_struct()
+    am.load_checkpoint(prefix)
+    np.testing.assert_array_equal(am.data_dict["batch_normalization_5"][3], A["batch_normalization_5/moving_variance"])
+    np.testing.assert_array_equal(am.data_dict["aconv_5"][0], A["aconv_5/aconv_5_filters"])
