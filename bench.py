@@ -39,7 +39,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=256, help="frames per GPU per step")
     ap.add_argument("--channels", type=int, default=25)
     ap.add_argument("--timesteps", type=int, default=8)
-    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32", "bf16x3"],
+                    help="bf16: tcgen05, bf16 operands; bf16x3: tcgen05, bf16 hi/lo splits (fp32-class, k <= 32); "
+                         "fp32: exact SIMT")
     ap.add_argument("--cpu-frames", type=int, default=64, help="frames in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stages", action="store_true", help="skip the crop / post-processing stage timings")
@@ -263,10 +265,14 @@ def run_ours(a):
             traffic = tj["bytes_per_launch"]
     except Exception:
         pass
-    if k_n.value > 0 and a.mode == "bf16":
+    if k_n.value > 0 and a.mode in ("bf16", "bf16x3"):
         avg_ms = k_ms.value / k_n.value
         ach = flops_per_launch / (avg_ms * 1e-3) * 1e-12
-        roof = {"bound": "tensor", "kernel": "hconv_stack_kernel (15x15 tap-stacked implicit GEMM + fused gates, tcgen05)" if k <= 32 else "hconv_tc_kernel (15x15 implicit GEMM, tcgen05)", "achieved": ach,
+        kern = ("hconv_tc_kernel SPLIT3 (15x15 implicit GEMM, bf16 hi/lo operand splits = 3 MMAs per useful one, "
+                "tcgen05)" if a.mode == "bf16x3" else
+                "hconv_stack_kernel (15x15 tap-stacked implicit GEMM + fused gates, tcgen05)" if k <= 32 else
+                "hconv_tc_kernel (15x15 implicit GEMM, tcgen05)")
+        roof = {"bound": "tensor", "kernel": kern, "achieved": ach,
                 "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
                 "traffic_source": "ncu --set full capture, profiles/r01_ncu_traffic.json (bytes per launch)",
                 "peak_source": peak_src, "peak_burst": peaks.get("bf16_tflops"),

@@ -101,6 +101,9 @@ struct TcConvArgs {
   // the stacked kernel (StackCfg::REM): act_pad zero rows on top of every chunk plane, and the last chunk
   // holds channel KP-8 at the 8 rows y..y+7.  0 = plain chunked layout.
   int act_pad;
+  // operand tensors written by this launch carry bf16 hi AND lo halves (chunk planes [0,CG) and [CG,2CG)):
+  // the SPLIT3 kernels of the bf16x3 mode read both (mutually exclusive with act_pad)
+  int split_out;
 };
 
 // fp32 state tensors of the tensor-core path are "quad-chunked": [n][c/4][y][x][4].  A thread owns
@@ -155,6 +158,17 @@ __device__ __forceinline__ void store_chunk_bf16(__nv_bfloat16* base, int KP, in
 // KP - 8, so this pixel's value goes to the 8 planes rows y - j (j = 0..7), element j.
 __device__ __forceinline__ void store_act_chunk(const TcConvArgs& a, __nv_bfloat16* base, int n, int cg,
                                                 size_t pin, const float* r) {
+  if (a.split_out) {
+    float hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      hi[j] = __bfloat162float(__float2bfloat16(r[j]));
+      lo[j] = r[j] - hi[j];
+    }
+    store_chunk_bf16(base, 2 * a.KP, a.H * a.W, n, cg, pin, hi);
+    store_chunk_bf16(base, 2 * a.KP, a.H * a.W, n, (a.KP >> 3) + cg, pin, lo);
+    return;
+  }
   if (a.act_pad == 0) {
     store_chunk_bf16(base, a.KP, a.H * a.W, n, cg, pin, r);
     return;

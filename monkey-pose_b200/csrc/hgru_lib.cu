@@ -119,6 +119,21 @@ int dispatch_tc_stem(int KP, const CUtensorMap& map, const hgru::TcConvArgs& a, 
   if (KP == 16) return launch_tc<3, 1, 16, 8, 9, hgru::EpiBiasReluAffine, true>(map, a, st);
   return fail(HGRU_E_UNSUPPORTED, "tensor-core stem conv: unsupported padded channel count");
 }
+// bf16x3 mode: the 15x15 horizontal convs on hi/lo operand splits (window holds both halves, so the unit is
+// narrower for 32 channels); k <= 32 only -- 64 channels' doubled window does not fit shared memory.
+bool x3_geometry(int S, int KP, TcGeom* g) {
+  if (S != 15 || !(KP == 16 || KP == 32)) return false;
+  g->tiles_x = (KP == 32) ? 4 : 8;
+  g->box_cols = 8 * g->tiles_x + S - 1;
+  g->box_rows = hgru::kTileRows + S - 1;
+  return true;
+}
+template <class Epi>
+int dispatch_tc_hconv_x3(int S, int KP, const CUtensorMap& map, const hgru::TcConvArgs& a, cudaStream_t st) {
+  if (S == 15 && KP == 32) return launch_tc<15, 2, 32, 4, 5, Epi, true>(map, a, st);
+  if (S == 15 && KP == 16) return launch_tc<15, 1, 16, 8, 5, Epi, true>(map, a, st);
+  return fail(HGRU_E_UNSUPPORTED, "bf16x3 conv: unsupported (S, padded channels)");
+}
 #undef TC_CASES_S
 #undef TC_CASE
 
@@ -314,7 +329,8 @@ enum { V_IB = 0, V_OB, V_BETA, V_NU, V_GAMMA, V_KAPPA, V_OMEGA, V_LBIAS };
 static int hgru_plan_init(hgru_plan_s* p, int N, int H, int W, int k, int S, int T, int mode) {
   if (N < 1 || H < 1 || W < 1 || k < 1 || T < 1) return fail(HGRU_E_INVALID, "hgru_plan_create: non-positive shape");
   if (S < 1 || (S % 2) == 0 || S > 15) return fail(HGRU_E_UNSUPPORTED, "hgru_plan_create: S must be odd and <= 15");
-  if (mode != HGRU_MODE_FP32 && mode != HGRU_MODE_BF16) return fail(HGRU_E_UNSUPPORTED, "hgru_plan_create: unknown mode");
+  if (mode != HGRU_MODE_FP32 && mode != HGRU_MODE_BF16 && mode != HGRU_MODE_BF16X3)
+    return fail(HGRU_E_UNSUPPORTED, "hgru_plan_create: unknown mode");
   p->N = N; p->H = H; p->W = W; p->k = k; p->S = S; p->T = T; p->mode = mode;
   p->KP = round_up(k, 16);
   p->CG = p->KP / 8;
@@ -332,6 +348,18 @@ static int hgru_plan_init(hgru_plan_s* p, int N, int H, int W, int k, int S, int
     if ((rc = p->A.alloc(act)) || (rc = p->C.alloc(act)) ||
         (rc = p->p_r.alloc(sizeof(float) * S * S * p->KP * p->KP)))
       return rc;
+  } else if (mode == HGRU_MODE_BF16X3) {
+    TcGeom g;
+    if (!x3_geometry(S, p->KP, &g))
+      return fail(HGRU_E_UNSUPPORTED, "hgru_plan_create: bf16x3 mode supports S = 15 and k <= 32");
+    // operands carry hi and lo bf16 halves: 2*CG chunk planes per frame
+    const size_t ab = 2 * p->nelem * sizeof(__nv_bfloat16);
+    if ((rc = p->actA.alloc(ab)) || (rc = p->actH1.alloc(ab))) return rc;
+    const int ksteps = p->KP / 16;
+    if ((rc = p->wpk.alloc(sizeof(__nv_bfloat16) * 3 * ksteps * S * S * 2 * p->KP * 8))) return rc;
+    if (hgru::make_act_tensor_map(&p->mapA, p->actA.p, N, 2 * p->CG, H, W, g.box_cols, g.box_rows) ||
+        hgru::make_act_tensor_map(&p->mapH1, p->actH1.p, N, 2 * p->CG, H, W, g.box_cols, g.box_rows))
+      return fail(HGRU_E_CUDA, "cuTensorMapEncodeTiled failed");
   } else {
     TcGeom g;
     if (!tc_geometry(S, p->KP, &g))
@@ -389,6 +417,10 @@ static int hgru_set_params_impl(hgru_plan_s* p, const float* p_r, const float* i
   const int taps = p->S * p->S;
   if (p->mode == HGRU_MODE_FP32) {
     pad_hwio_kernel<<<nblk(static_cast<size_t>(taps) * KP * KP), 256, 0, st>>>(p_r, p->p_r.as<float>(), taps, k, KP);
+  } else if (p->mode == HGRU_MODE_BF16X3) {
+    const int ksteps = KP / 16;
+    const size_t total = static_cast<size_t>(3 * ksteps) * taps * 2 * KP * 8;
+    hgru::pack_weights_split3_kernel<<<nblk(total), 256, 0, st>>>(p_r, p->wpk.as<__nv_bfloat16>(), taps, k, ksteps, KP);
   } else {
     const int ksteps = KP / 16;
     const size_t total = static_cast<size_t>(ksteps) * taps * 2 * KP * 8;
@@ -555,15 +587,80 @@ static int hgru_run_bf16(hgru_plan_s* p, const float* Xp, const float* H2_init_n
   return 0;
 }
 
-// API boundary <-> internal state layout (fp32 mode: channel-padded NHWC; bf16 mode: quad-chunked)
+// ---- bf16x3 path: fp32-class accuracy on tensor cores (k <= 32) -----------------------------------------
+// Every conv operand is a bf16 hi + lo pair and each k-step is three products (hi*hi + hi*w_lo + lo*w_hi, the
+// SPLIT3 mode of hconv_tc.cuh); the 1x1 gates are exact fp32 (SIMT); state, accumulation and the integration
+// epilogues are the fp32 ones of the bf16 path.  Four launches per timestep.
+static int hgru_run_bf16x3(hgru_plan_s* p, const float* Xp, const float* H2_init_nhwc, float* H1_trace,
+                           float* H2_trace, cudaStream_t st) {
+  const int KP = p->KP, HW = p->H * p->W;
+  int rc;
+  static bool attr = false;
+  if (!attr) {
+    CUDA_TRY(cudaFuncSetAttribute(hgru::gate_quad_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr = true;
+  }
+  const size_t gsmem = sizeof(float) * (KP * KP + hgru::kInitPix * (KP + 1));
+  if (H2_init_nhwc)
+    hgru::nhwc_to_quad_kernel<<<nblk(p->nelem / 4), 256, 0, st>>>(H2_init_nhwc, p->H2.as<float>(), p->npix, p->k, KP, HW);
+  else
+    CUDA_TRY(cudaMemsetAsync(p->H2.p, 0, p->H2.bytes, st));
+  ++p->launches;
+  hgru::TcConvArgs base{};
+  base.N = p->N; base.H = p->H; base.W = p->W; base.KP = KP; base.kreal = p->k;
+  base.split_out = 1;
+  for (int t = 0; t < p->T; ++t) {
+    // circuit_input gate (hgru_module.py:696-711): operand A = split(sigmoid(H2 *1x1 i_r + i_b) . H2)
+    hgru::gate_quad_split_kernel<<<nblk(p->npix, hgru::kInitPix), 256, gsmem, st>>>(
+        p->H2.as<float>(), p->i_r.as<float>(), p->vec(V_IB), nullptr, p->actA.as<__nv_bfloat16>(), p->npix, p->k,
+        KP, HW);
+    // C1 conv (:714-718, 657) + input_integration (:795-804) -> H1 (fp32 + hi/lo operand)
+    hgru::TcConvArgs a = base;
+    a.wpk = p->wpk.as<__nv_bfloat16>(); a.bias = p->vec(V_LBIAS); a.X = Xp; a.H2 = p->H2.as<float>();
+    a.v0 = p->vec(V_BETA); a.v1 = p->vec(V_NU);
+    a.out = p->H1.as<float>(); a.out_bf16 = p->actH1.as<__nv_bfloat16>();
+    p->timer.begin(st);
+    if ((rc = dispatch_tc_hconv_x3<hgru::EpiH1>(p->S, KP, p->mapA, a, st))) return rc;
+    p->timer.end(st);
+    // circuit_output gate (:729-740): G2 = sigmoid(H1 *1x1 o_r + o_b), exact fp32
+    hgru::gate_quad_split_kernel<<<nblk(p->npix, hgru::kInitPix), 256, gsmem, st>>>(
+        p->H1.as<float>(), p->o_r.as<float>(), p->vec(V_OB), p->G.as<float>(), nullptr, p->npix, p->k, KP, HW);
+    // C2 conv (:746-750, 657) + output_integration + rho (:806-823, 847-849) -> H2 in place
+    a = base;
+    a.wpk = p->wpk.as<__nv_bfloat16>(); a.bias = p->vec(V_LBIAS); a.H1 = p->H1.as<float>();
+    a.G = p->G.as<float>(); a.H2 = p->H2.as<float>();
+    a.v0 = p->vec(V_GAMMA); a.v1 = p->vec(V_KAPPA); a.v2 = p->vec(V_OMEGA);
+    a.rho_t = p->rho.as<float>() + t;
+    if (t + 1 == p->T && p->fc_a) {
+      a.fc_a = p->fc_a; a.fc_scale = p->fc_scale; a.fc_shift = p->fc_shift; a.fc_kpad = p->fc_kpad;
+    }
+    p->timer.begin(st);
+    if ((rc = dispatch_tc_hconv_x3<hgru::EpiH2>(p->S, KP, p->mapH1, a, st))) return rc;
+    p->timer.end(st);
+    p->launches += 4;
+    if (H1_trace) {
+      hgru::quad_to_nhwc_kernel<<<nblk(p->npix * p->k), 256, 0, st>>>(
+          p->H1.as<float>(), H1_trace + static_cast<size_t>(t) * p->npix * p->k, p->npix, p->k, KP, HW);
+      ++p->launches;
+    }
+    if (H2_trace) {
+      hgru::quad_to_nhwc_kernel<<<nblk(p->npix * p->k), 256, 0, st>>>(
+          p->H2.as<float>(), H2_trace + static_cast<size_t>(t) * p->npix * p->k, p->npix, p->k, KP, HW);
+      ++p->launches;
+    }
+  }
+  return 0;
+}
+
+// API boundary <-> internal state layout (fp32 mode: channel-padded NHWC; bf16 modes: quad-chunked)
 static void state_from_nhwc(const hgru_plan_s* p, const float* in, float* out, cudaStream_t st) {
-  if (p->mode == HGRU_MODE_BF16)
+  if (p->mode != HGRU_MODE_FP32)
     hgru::nhwc_to_quad_kernel<<<nblk(p->nelem / 4), 256, 0, st>>>(in, out, p->npix, p->k, p->KP, p->H * p->W);
   else
     hgru::pad_channels_kernel<<<nblk(p->nelem), 256, 0, st>>>(in, out, p->npix, p->k, p->KP);
 }
 static void state_to_nhwc(const hgru_plan_s* p, const float* in, float* out, cudaStream_t st) {
-  if (p->mode == HGRU_MODE_BF16)
+  if (p->mode != HGRU_MODE_FP32)
     hgru::quad_to_nhwc_kernel<<<nblk(p->npix * p->k), 256, 0, st>>>(in, out, p->npix, p->k, p->KP, p->H * p->W);
   else
     hgru::unpad_channels_kernel<<<nblk(p->npix * p->k), 256, 0, st>>>(in, out, p->npix, p->k, p->KP);
@@ -578,6 +675,8 @@ static int hgru_run_padded(hgru_plan_s* p, const float* Xp, const float* H2_init
   int rc;
   if (p->mode == HGRU_MODE_BF16) {
     rc = hgru_run_bf16(p, Xp, H2_init_nhwc, H1_trace, H2_trace, st);
+  } else if (p->mode == HGRU_MODE_BF16X3) {
+    rc = hgru_run_bf16x3(p, Xp, H2_init_nhwc, H1_trace, H2_trace, st);
   } else {
     if (H2_init_nhwc) state_from_nhwc(p, H2_init_nhwc, p->H2.as<float>(), st);
     else CUDA_TRY(cudaMemsetAsync(p->H2.p, 0, p->H2.bytes, st));
@@ -629,7 +728,7 @@ static int pose_forward_impl(pose_plan_s* p, const float* depth, const float* H2
   hgru_plan_s* h = &p->hg;
   const int N = p->N, HW = p->HW, KP = p->KP, C = p->C;
   const size_t npix = static_cast<size_t>(N) * HW * HW;
-  const bool tc = p->mode == HGRU_MODE_BF16;
+  const bool tc = p->mode != HGRU_MODE_FP32;      // stem + fc_1 on tensor cores (hi/lo splits) in both bf16 modes
   int rc;
   p->launches = 0;
   // conv_1 + relu + pool_1 + BN (hgru_pose.py:50-60)
@@ -768,7 +867,7 @@ int pose_plan_create(int N, int HW, int C, int S, int T, int F, int O, int mode,
   A(p->w1, sizeof(float) * 9 * C); A(p->b1, sizeof(float) * KP);
   A(p->b2, sizeof(float) * KP); A(p->b3, sizeof(float) * KP);
   // fc_1 on tensor cores (operand rows are padded to whole k-blocks, so any K works)
-  p->fc1_tc = (mode == HGRU_MODE_BF16);
+  p->fc1_tc = (mode != HGRU_MODE_FP32);
   if (p->fc1_tc) {
     int sms = 148, dev = 0;
     cudaGetDevice(&dev);

@@ -492,6 +492,81 @@ init_state_gate_kernel(const float* __restrict__ h0 /*[npix][k] or nullptr = zer
 }
 
 // ------------------------------------------------------------------------------------------------
+// Exact fp32 1x1 gate on the quad-chunked state layout (bf16x3 mode; hgru_module.py:696-711, 729-740):
+//   g = sigmoid(in *1x1 wg + bg);  out_g (quad fp32) = g              when out_g  != nullptr   (G2)
+//                                  out_act = bf16 hi | lo of g . in   when out_act != nullptr  (gated operand)
+// Same tiling as init_state_gate_kernel: 256 pixels per block, thread = 4 pixels x 8 output channels.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gate_quad_split_kernel(const float* __restrict__ inq, const float* __restrict__ wg /*[KP][KP]*/,
+                       const float* __restrict__ bg, float* __restrict__ out_g, __nv_bfloat16* __restrict__ out_act,
+                       size_t npix, int k, int KP, int HW) {
+  extern __shared__ float smem_f[];
+  float* wsm = smem_f;                 // [KP][KP]
+  float* xin = smem_f + KP * KP;       // [kInitPix][KP+1]
+  const int tid = threadIdx.x;
+  const int CG = KP >> 3;
+  const size_t p0 = blockIdx.x * static_cast<size_t>(kInitPix);
+  for (int e = tid; e < KP * KP; e += 256) wsm[e] = wg[e];
+  for (int e = tid; e < kInitPix * (KP >> 2); e += 256) {        // one float4 = 4 channels of one pixel
+    const int pp = e % kInitPix, q = e / kInitPix;
+    const size_t p = p0 + pp;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p < npix) {
+      const size_t n = p / HW, pin = p - n * HW;
+      v = *reinterpret_cast<const float4*>(inq + ((n * (KP >> 2) + q) * HW + pin) * 4);
+    }
+    float* d = xin + pp * (KP + 1) + 4 * q;
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+  }
+  __syncthreads();
+  const int pq = tid & 63;
+  for (int cg = tid >> 6; cg < CG; cg += 4) {
+    float acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int ci = 0; ci < KP; ++ci) {
+      const float4 w0 = *reinterpret_cast<const float4*>(wsm + ci * KP + cg * 8);
+      const float4 w1 = *reinterpret_cast<const float4*>(wsm + ci * KP + cg * 8 + 4);
+      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float xv = xin[(pq + 64 * i) * (KP + 1) + ci];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(xv, wv[j], acc[i][j]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int pp = pq + 64 * i;
+      const size_t p = p0 + pp;
+      if (p >= npix) continue;
+      const size_t n = p / HW, pin = p - n * HW;
+      F8 g, hi, lo;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = cg * 8 + j;
+        g.v[j] = (c < k) ? sigmoidf_(acc[i][j] + bg[c]) : 0.f;
+        const float a = g.v[j] * xin[pp * (KP + 1) + c];
+        hi.v[j] = __bfloat162float(__float2bfloat16(a));
+        lo.v[j] = a - hi.v[j];
+      }
+      if (out_g) {
+        float* o = out_g + ((n * (KP >> 2) + 2 * cg) * HW + pin) * 4;
+        *reinterpret_cast<float4*>(o) = make_float4(g.v[0], g.v[1], g.v[2], g.v[3]);
+        *reinterpret_cast<float4*>(o + static_cast<size_t>(HW) * 4) = make_float4(g.v[4], g.v[5], g.v[6], g.v[7]);
+      }
+      if (out_act) {
+        st8_bf16(chunk_ptr(out_act, static_cast<int>(n), cg, pin, HW, 2 * CG), hi);
+        st8_bf16(chunk_ptr(out_act, static_cast<int>(n), CG + cg, pin, HW, 2 * CG), lo);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Readout FC1 (hgru_pose.py:91,156-163): part[z][m][j] = sum_{kk in slice z} (a[m][kk]*sc[kk%k]+sh[kk%k]) * Wt[kk][j]
 // (a is read from the channel-padded activation buffer; kk enumerates (h, w, c) like tf.reshape)
 // The per-channel affine on A is the inference batch-norm of the hGRU output (:82-90).

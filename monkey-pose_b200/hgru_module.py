@@ -114,7 +114,7 @@ class ContextualCircuit(object):
 
         X: torch CUDA tensor [n,h,w,k] float32 (static batch, hgru_module.py:74).
         Non-reference keywords: `params` (dict of the `contextual_circuit/*` variables, by their
-        reference names), `hidden_state` (O_0, [n,h,w,k]), `compute_mode` ('fp32' | 'bf16'), `seed`.
+        reference names), `hidden_state` (O_0, [n,h,w,k]), `compute_mode` ('fp32' | 'bf16' | 'bf16x3'), `seed`.
         """
         if not (torch.is_tensor(X) and X.dim() == 4):
             raise ValueError("X must be a 4-D torch tensor [n,h,w,k] (CUDA for build())")

@@ -21,7 +21,7 @@ pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 HGRU_FILES = sorted(glob.glob(os.path.join(GOLDEN, "hgru_ref_*.npz")))
 POSE_AUX = mp.model().aux
-TOL = {"fp32": 1e-4, "bf16": 1e-2}
+TOL = {"fp32": 1e-4, "bf16": 1e-2, "bf16x3": 1e-4}
 
 
 def _run_cc(X, O0, params, T, S, mode, trace=True):
@@ -286,3 +286,46 @@ def test_attn_model_vs_oracle(cfg):
         m.build(torch.as_tensor(frames).cuda(), 3, train_mode=True)
     with pytest.raises(RuntimeError):
         m.build(torch.as_tensor(frames), 3)
+
+
+# ---- bf16x3: fp32-class accuracy on tensor cores (hi/lo operand splits), k <= 32, S = 15 -------------------
+@pytest.mark.gpu
+def test_bf16x3_mode_matches_reference_golden_every_timestep():
+    z = np.load(os.path.join(GOLDEN, "hgru_ref_S15_k8.npz"))
+    T, S = int(z["T"]), int(z["S"])
+    params = {n: z["var:contextual_circuit/" + n] for n in onp.HGRU_PARAM_NAMES}
+    cc, O, _ = _run_cc(z["X"], z["O0"], params, T, S, "bf16x3")
+    for t in range(T):
+        assert onp.rel_err(cc.I_steps[t].cpu().numpy(), z["I_steps"][:, t])[0] < 1e-4, t
+        assert onp.rel_err(cc.O_steps[t].cpu().numpy(), z["O_steps"][:, t])[0] < 1e-4, t
+    assert onp.rel_err(O.cpu().numpy(), z["O_final"])[0] < 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(2, 64, 64, 25, 15, 2), (1, 20, 36, 32, 15, 3), (1, 33, 70, 16, 15, 2)])
+def test_bf16x3_mode_seeded_cases_vs_oracle(shape):
+    """Stress weights (tanh off its linear region): the split-bf16 tensor-core path stays inside the fp32 budget
+    that plain bf16 misses by two orders of magnitude."""
+    n, h, w, k, S, T = shape
+    rng = np.random.default_rng(5)
+    X = rng.uniform(-1, 1, size=(n, h, w, k)).astype(np.float32)
+    O0 = init.hidden_init((n, h, w, k), seed=3, limit=0.5)
+    params = init.hgru_params(k, S, T, seed=9, stress=6.0)
+    cc, O, _ = _run_cc(X, O0, params, T, S, "bf16x3")
+    ref, H1s, H2s = otorch.hgru_forward(X, O0, params, T, dtype=torch.float64, trace=True)
+    for t in range(T):
+        assert onp.rel_err(cc.I_steps[t].cpu().numpy(), H1s[t].numpy())[0] < 1e-4
+        assert onp.rel_err(cc.O_steps[t].cpu().numpy(), H2s[t].numpy())[0] < 1e-4
+    assert onp.rel_err(O.cpu().numpy(), ref.numpy())[0] < 1e-4
+
+
+@pytest.mark.gpu
+def test_bf16x3_pose_model_and_unsupported_shapes():
+    m, out, P, depth, h0 = _pose("bf16x3", 2, 25, 16, 2, 15, 64)
+    ref = otorch.pose_forward(depth, P, h0, timesteps=2, dtype=torch.float64)
+    assert onp.rel_err(out.cpu().numpy(), ref.numpy())[0] < 1e-4
+    assert onp.mean_joint_error_mm(out.cpu().numpy(), ref.numpy()) < 0.01
+    with pytest.raises(NotImplementedError):          # 64 channels: the doubled window does not fit shared memory
+        _pose("bf16x3", 1, 64, 16, 1, 15, 32)
+    with pytest.raises(NotImplementedError):          # only the 15x15 horizontal kernel is instantiated
+        _pose("bf16x3", 1, 16, 16, 1, 5, 32)
