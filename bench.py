@@ -114,11 +114,17 @@ class Clocks(object):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "10"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
             self.proc = None
+
+    def wait_ready(self, timeout=4.0):
+        """nvidia-smi needs ~0.1-1 s before its first row: do not enter a 50 ms timed region before it samples."""
+        t = time.perf_counter()
+        while self.proc is not None and not self.rows and time.perf_counter() - t < timeout:
+            time.sleep(0.01)
 
     def _read(self):
         for ln in self.proc.stdout:
@@ -224,6 +230,9 @@ def run_ours(a):
     for _ in range(max(3, a.warmup)):
         step_dev()
     clocks = Clocks(local) if rank == 0 else None
+    if clocks:
+        clocks.wait_ready()
+        step_dev()                      # the sampler start-up left the GPU idle: one more untimed step
     lib.hgru_enable_kernel_timing(1)
     ms_dev, t0, t1 = timed(step_dev, a.steps)
     k_ms, k_n = ctypes.c_float(0), ctypes.c_int(0)
