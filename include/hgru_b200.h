@@ -39,7 +39,7 @@ extern "C" {
 /* arithmetic of the horizontal convolutions (everything else is fp32 in every mode) */
 #define HGRU_MODE_FP32 0 /* fp32 SIMT FFMA: the <= 1e-4 parity path                                */
 #define HGRU_MODE_BF16 1 /* tcgen05 tensor cores, bf16 operands, fp32 accumulate + fp32 state      */
-#define HGRU_MODE_BF16X3 2 /* tcgen05, bf16 hi/lo operand splits (3 products): fp32-class accuracy, k <= 32 */
+#define HGRU_MODE_BF16X3 2 /* tcgen05, bf16 hi/lo operand splits (3 products): fp32-class accuracy, S = 15    */
 
 typedef struct hgru_plan_s* hgru_plan_t;
 typedef struct pose_plan_s* pose_plan_t;

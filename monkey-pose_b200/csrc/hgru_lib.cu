@@ -120,16 +120,17 @@ int dispatch_tc_stem(int KP, const CUtensorMap& map, const hgru::TcConvArgs& a, 
   return fail(HGRU_E_UNSUPPORTED, "tensor-core stem conv: unsupported padded channel count");
 }
 // bf16x3 mode: the 15x15 horizontal convs on hi/lo operand splits (window holds both halves, so the unit is
-// narrower for 32 channels); k <= 32 only -- 64 channels' doubled window does not fit shared memory.
+// narrower the more channels there are: 8 / 4 / 1 tiles of 8 columns for 16 / 32 / 64 channels).
 bool x3_geometry(int S, int KP, TcGeom* g) {
-  if (S != 15 || !(KP == 16 || KP == 32)) return false;
-  g->tiles_x = (KP == 32) ? 4 : 8;
+  if (S != 15 || !(KP == 16 || KP == 32 || KP == 64)) return false;
+  g->tiles_x = (KP == 64) ? 1 : (KP == 32) ? 4 : 8;     // 64 channels: hi + lo windows only fit one 8-column tile
   g->box_cols = 8 * g->tiles_x + S - 1;
   g->box_rows = hgru::kTileRows + S - 1;
   return true;
 }
 template <class Epi>
 int dispatch_tc_hconv_x3(int S, int KP, const CUtensorMap& map, const hgru::TcConvArgs& a, cudaStream_t st) {
+  if (S == 15 && KP == 64) return launch_tc<15, 4, 64, 1, 5, Epi, true>(map, a, st);
   if (S == 15 && KP == 32) return launch_tc<15, 2, 32, 4, 5, Epi, true>(map, a, st);
   if (S == 15 && KP == 16) return launch_tc<15, 1, 16, 8, 5, Epi, true>(map, a, st);
   return fail(HGRU_E_UNSUPPORTED, "bf16x3 conv: unsupported (S, padded channels)");
@@ -333,6 +334,7 @@ static int hgru_plan_init(hgru_plan_s* p, int N, int H, int W, int k, int S, int
     return fail(HGRU_E_UNSUPPORTED, "hgru_plan_create: unknown mode");
   p->N = N; p->H = H; p->W = W; p->k = k; p->S = S; p->T = T; p->mode = mode;
   p->KP = round_up(k, 16);
+  if (mode != HGRU_MODE_FP32 && p->KP == 48) p->KP = 64;      // tensor-core kernels exist for 16 / 32 / 64 padded channels
   p->CG = p->KP / 8;
   p->npix = static_cast<size_t>(N) * H * W;
   p->nelem = p->npix * p->KP;
@@ -351,7 +353,7 @@ static int hgru_plan_init(hgru_plan_s* p, int N, int H, int W, int k, int S, int
   } else if (mode == HGRU_MODE_BF16X3) {
     TcGeom g;
     if (!x3_geometry(S, p->KP, &g))
-      return fail(HGRU_E_UNSUPPORTED, "hgru_plan_create: bf16x3 mode supports S = 15 and k <= 32");
+      return fail(HGRU_E_UNSUPPORTED, "hgru_plan_create: bf16x3 mode supports S = 15 and k <= 64");
     // operands carry hi and lo bf16 halves: 2*CG chunk planes per frame
     const size_t ab = 2 * p->nelem * sizeof(__nv_bfloat16);
     if ((rc = p->actA.alloc(ab)) || (rc = p->actH1.alloc(ab))) return rc;
