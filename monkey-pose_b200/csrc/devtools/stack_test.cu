@@ -70,7 +70,7 @@ int run_case(int N, int H, int W, int k, int grid_override, int iters) {
   else hgru::pack_weights_stack_kernel<<<(unsigned)((wpk_elems + 255) / 256), 256>>>(d_w, d_wpk, k, Cfg::KSTEPS, T, KC, Cfg::NG, CS);
   CK(cudaDeviceSynchronize());
   CUtensorMap map;
-  if (hgru::make_act_tensor_map(&map, d_act, N, CG, HA, W, Cfg::COLS, Cfg::ROWS, CG)) { printf("map fail\n"); return 1; }
+  if (hgru::make_act_tensor_map(&map, d_act, N, CG, HA, W, Cfg::COLS, Cfg::ROWS, Cfg::PART_CHUNKS)) { printf("map fail\n"); return 1; }
   CUtensorMap wmap;
   if (hgru::make_rows256_map(&wmap, d_wpk, wpk_elems * 2, Cfg::STAGE_ROWS)) { printf("wmap fail\n"); return 1; }
   hgru::TcConvArgs a{};
@@ -149,7 +149,7 @@ void time_real_epilogue(const char* name, int N, int H, int W, int k, int gate =
     CK(cudaDeviceSynchronize());
   }
   CUtensorMap map, wmap;
-  hgru::make_act_tensor_map(&map, act, N, CG, HA, W, Cfg::COLS, Cfg::ROWS, CG);
+  hgru::make_act_tensor_map(&map, act, N, CG, HA, W, Cfg::COLS, Cfg::ROWS, Cfg::PART_CHUNKS);
   hgru::make_rows256_map(&wmap, wpk, wpk_elems * 2, Cfg::STAGE_ROWS);
   hgru::TcConvArgs a{};
   a.N = N; a.H = H; a.W = W; a.KP = KP; a.kreal = k; a.act_pad = Cfg::ACT_PAD;

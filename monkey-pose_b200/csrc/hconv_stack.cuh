@@ -78,7 +78,13 @@ struct StackCfg {
   static constexpr int GATE_BYTES = GATE_A_BYTES + GATE_W_BYTES;
   // ring depth: as deep as the 227 KB allow (pair mode: half-size stages)
   static constexpr int WSTAGES = (CS == 2) ? 8 : ((WIN_BYTES + GATE_BYTES + 4 * NG * 2 * NPAD * 16 + 2048 <= 232448) ? 4 : 3);
-  static constexpr int NUM_BARS = 2 + 2 * WSTAGES + 8 + 1;
+  // The window is loaded in WPARTS parts with their own barriers.  With the remainder-packed schedule the first
+  // 15 stages of a pass read chunk planes 0-1 only and the last 9 read planes 2-3 only, so the next unit's first
+  // half is loaded under the current unit's last 9 stages and its second half under the next unit's first 15.
+  static constexpr int WPARTS = REM ? 2 : 1;
+  static constexpr int PART_CHUNKS = CG / WPARTS;
+  static constexpr int PART_BYTES = WIN_BYTES / WPARTS;
+  static constexpr int NUM_BARS = 4 + 2 * WSTAGES + 8 + 1;
   static constexpr int PAR_FLOATS = 5 * KP + 4;           // bias, v0, v1, v2, gate_bias (KP each) + rho_t
   static constexpr int STAGE_ROWS = STAGE_BYTES / 256;    // rows of the 256-byte weight view per stage
   static constexpr int SMEM_BYTES =
@@ -267,9 +273,14 @@ __device__ __forceinline__ void stack_mma_issuer(const TcConvArgs& a, uint32_t t
     if (valid) mbar_wait_warp(bar_win_full, vit & 1);
     if constexpr (PROF) t_win += clock64() - t0;
     tc_fence_after();
+    bool part1_ready = Cfg::WPARTS == 1;
     for (int pr = 0; pr < npairs; ++pr) {
-      const int j0 = 2 * pr;
-      const bool two = (j0 + 1) < NT;
+      // tiles are accumulated in pairs; with an odd count the single tile goes FIRST, so the last pass of a unit
+      // is a full pair and the next unit's first window part has the longest possible time to land
+      const bool odd = (NT & 1) != 0;
+      const int j0 = odd ? (pr == 0 ? 0 : 2 * pr - 1) : 2 * pr;
+      const bool two = odd ? (pr != 0) : true;
+      const bool last_pass = pr + 1 == npairs;
       const uint32_t s0 = tc & 3, s1 = (tc + 1) & 3;
       if constexpr (PROF) t0 = clock64();
       mbar_wait_warp(bar_acc_empty + 8 * s0, ((tc >> 2) & 1) ^ 1);
@@ -319,9 +330,19 @@ __device__ __forceinline__ void stack_mma_issuer(const TcConvArgs& a, uint32_t t
         const uint64_t dC = make_smem_desc(win + 2 * CP + 14 * RP, CP - 14 * RP, RP) + tile_off;   // chunk 2 @ 14 | P @ 0
         const uint64_t dD = make_smem_desc(win + 3 * CP + 8 * RP, RP, RP) + tile_off;         // P @ 8 | (zero weights)
         for (int dy = 0; dy < Cfg::S; ++dy) issue_stage(a_tile0 + static_cast<uint64_t>((dy * RP) >> 4), dy == 0);
+        // chunk planes 0-1 are not read again by this unit: hand them to the window producer already
+        if (last_pass && leader && valid) tc_commit(bar_win_empty);
+        if (!part1_ready) {        // planes 2-3 of this unit were loading under the stages above
+          if constexpr (PROF) t0 = clock64();
+          if (valid) mbar_wait_warp(bar_win_full + 8, vit & 1);
+          if constexpr (PROF) t_win += clock64() - t0;
+          tc_fence_after();
+          part1_ready = true;
+        }
         for (int i = 0; i < Cfg::S / 2; ++i) issue_stage(dB + static_cast<uint64_t>((2 * i * RP) >> 4), false);
         issue_stage(dC, false);
         issue_stage(dD, false);
+        if (last_pass && leader && valid) tc_commit(bar_win_empty + 8);
       } else {
         // stage order: filter row dy, then k-step q
         for (int dy = 0; dy < Cfg::S; ++dy) {
@@ -342,10 +363,13 @@ __device__ __forceinline__ void stack_mma_issuer(const TcConvArgs& a, uint32_t t
       }
       tc += two ? 2 : 1;
     }
-    // release the windows: in pair mode both CTAs' windows were read by these MMAs
-    if (leader && valid) {
-      if constexpr (CS > 1) tc_commit_2cta(bar_win_empty, kMask);
-      else tc_commit(bar_win_empty);
+    // release the window (the two-part schedule released its parts inside the last pass): in pair mode both
+    // CTAs' windows were read by these MMAs
+    if constexpr (Cfg::WPARTS == 1) {
+      if (leader && valid) {
+        if constexpr (CS > 1) tc_commit_2cta(bar_win_empty, kMask);
+        else tc_commit(bar_win_empty);
+      }
     }
     if (valid) ++vit;
   }
@@ -508,8 +532,8 @@ hconv_stack_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
   const uint32_t gate_a = w_buf + Cfg::WSTAGES * Cfg::STAGE_BYTES;   // staging tile [CG][128 px][16 B]
   const uint32_t gate_w = gate_a + Cfg::GATE_A_BYTES;                // 1x1 gate weights
   const uint32_t bars = gate_w + Cfg::GATE_W_BYTES;
-  const uint32_t bar_win_full = bars, bar_win_empty = bars + 8;
-  const uint32_t bar_w_full = bars + 16;                             // [WSTAGES]
+  const uint32_t bar_win_full = bars, bar_win_empty = bars + 16;     // [2] each (one per window part)
+  const uint32_t bar_w_full = bars + 32;                             // [WSTAGES]
   const uint32_t bar_w_empty = bar_w_full + 8 * Cfg::WSTAGES;        // [WSTAGES]
   const uint32_t bar_acc_full = bar_w_empty + 8 * Cfg::WSTAGES;      // [4]
   const uint32_t bar_acc_empty = bar_acc_full + 32;                  // [4]
@@ -526,8 +550,10 @@ hconv_stack_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
   const uint32_t crank = (CS > 1) ? cluster_ctarank() : 0u;
 
   if (threadIdx.x == 0) {
-    mbar_init(bar_win_full, 1);
-    mbar_init(bar_win_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_win_full + 8 * i, 1);
+      mbar_init(bar_win_empty + 8 * i, 1);
+    }
     for (int i = 0; i < Cfg::WSTAGES; ++i) {
       mbar_init(bar_w_full + 8 * i, 1);
       mbar_init(bar_w_empty + 8 * i, 1);
@@ -621,9 +647,15 @@ hconv_stack_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
           tma_load_4d_2cta(win, &in_map, lead_win_full, 2 * (ux * 64 + Cfg::MIN_COL),
                            uy * kTileRows - Cfg::PAD + Cfg::ACT_PAD, 0, n);
         } else {
-          mbar_arrive_expect_tx(bar_win_full, Cfg::WIN_BYTES);
+          mbar_arrive_expect_tx(bar_win_full, Cfg::PART_BYTES);
           tma_load_4d(win, &in_map, bar_win_full, 2 * (ux * 64 + Cfg::MIN_COL),
                       uy * kTileRows - Cfg::PAD + Cfg::ACT_PAD, 0, n);
+          if constexpr (Cfg::WPARTS == 2) {
+            mbar_wait(bar_win_empty + 8, (vit & 1) ^ 1);
+            mbar_arrive_expect_tx(bar_win_full + 8, Cfg::PART_BYTES);
+            tma_load_4d(win + Cfg::PART_BYTES, &in_map, bar_win_full + 8, 2 * (ux * 64 + Cfg::MIN_COL),
+                        uy * kTileRows - Cfg::PAD + Cfg::ACT_PAD, Cfg::PART_CHUNKS, n);
+          }
         }
         ++vit;
       }

@@ -375,7 +375,8 @@ static int hgru_plan_init(hgru_plan_s* p, int N, int H, int W, int k, int S, int
     if (p->stacked) {
       p->stack_T = sg.T;
       p->act_pad = sg.act_pad;
-      box_cols = sg.box_cols; box_rows = sg.box_rows; box_chunks = p->CG;
+      box_cols = sg.box_cols; box_rows = sg.box_rows;
+      box_chunks = sg.act_pad ? p->CG / 2 : p->CG;      // remainder-packed kernel loads the window in two parts
       wbytes = sizeof(__nv_bfloat16) * sg.stages * sg.NG * 2 * 128 * 8;
     }
     // operand planes carry act_pad zero rows on top in the remainder-packed layout; they (and the never
