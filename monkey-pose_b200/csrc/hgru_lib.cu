@@ -316,6 +316,7 @@ struct hgru_plan_s {
   bool stacked = false;             // narrow layers: tap-stacked kernel (hconv_stack.cuh)
   int stack_T = 0;
   int act_pad = 0;                  // pad rows of the bf16 operand planes (remainder-packed layout)
+  bool state_ready = false;         // the caller already ran hgru_init_state_bf16 for the coming forward
   KernelTimer timer;
   float* vec(int i) const { return vecs.as<float>() + static_cast<size_t>(i) * KP; }
   size_t workspace() const {
@@ -504,6 +505,23 @@ static int hgru_run_fp32(hgru_plan_s* p, const float* Xp, float* H1_trace, float
 // Narrow layers (stacked kernel): two tcgen05 launches per timestep, the 1x1 gate convs run as
 // epilogue-issued MMAs inside them.  Wide layers (k = 64): four launches (gate-in, C1+H1, gate-out,
 // C2+H2).  All integration math happens on TMEM accumulators.
+// Initial state of the bf16 path: O_0 (NHWC, or zeros) -> H2 (quad-chunked fp32) + the first gated operand.
+// Touches only H2 / actA, so it can run before (and concurrently with the input copy of) the stem.
+static int hgru_init_state_bf16(hgru_plan_s* p, const float* H2_init_nhwc, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    CUDA_TRY(cudaFuncSetAttribute(hgru::init_state_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr = true;
+  }
+  const int KP = p->KP;
+  const size_t smem = sizeof(float) * (KP * KP + hgru::kInitPix * (KP + 1));
+  hgru::init_state_gate_kernel<<<nblk(p->npix, hgru::kInitPix), 256, smem, st>>>(
+      H2_init_nhwc, p->i_r.as<float>(), p->vec(V_IB), p->H2.as<float>(), p->actA.as<__nv_bfloat16>(), p->npix,
+      p->k, KP, p->H * p->W, p->W, p->act_pad);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 static int hgru_run_bf16(hgru_plan_s* p, const float* Xp, const float* H2_init_nhwc, float* H1_trace,
                          float* H2_trace, cudaStream_t st) {
   const int KP = p->KP, HW = p->H * p->W;
@@ -511,19 +529,11 @@ static int hgru_run_bf16(hgru_plan_s* p, const float* Xp, const float* H2_init_n
   hgru::TcConvArgs base{};
   base.N = p->N; base.H = p->H; base.W = p->W; base.KP = KP; base.kreal = p->k;
   base.act_pad = p->act_pad;
-  // initial state O_0 (NHWC or zeros) -> H2 (quad-chunked fp32) + the first gated operand, one pass
-  {
-    static bool attr = false;
-    if (!attr) {
-      CUDA_TRY(cudaFuncSetAttribute(hgru::init_state_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-      attr = true;
-    }
-    const size_t smem = sizeof(float) * (KP * KP + hgru::kInitPix * (KP + 1));
-    hgru::init_state_gate_kernel<<<nblk(p->npix, hgru::kInitPix), 256, smem, st>>>(
-        H2_init_nhwc, p->i_r.as<float>(), p->vec(V_IB), p->H2.as<float>(), p->actA.as<__nv_bfloat16>(), p->npix,
-        p->k, KP, HW, p->W, p->act_pad);
-    ++p->launches;
-  }
+  // initial state O_0 (NHWC or zeros) -> H2 (quad-chunked fp32) + the first gated operand, one pass (unless the
+  // caller already ran it: the pose plan overlaps it with the upload of the crops)
+  if (!p->state_ready && (rc = hgru_init_state_bf16(p, H2_init_nhwc, st))) return rc;
+  p->state_ready = false;
+  ++p->launches;
   const bool fused = p->stacked;
   for (int t = 0; t < p->T; ++t) {
     hgru::TcConvArgs a;
@@ -706,6 +716,8 @@ struct pose_plan_s {
   CUtensorMap map_fc_a, map_fc_b;
   bool fc1_tc = false;
   int fc_splits = 1, fc_kbps = 1, fc_kpad = 0;
+  cudaStream_t copy_st = nullptr;                  // pose_forward_host: upload of the crops overlaps the initial-state pass
+  cudaEvent_t ev_begin = nullptr, ev_copied = nullptr;
   float* bn_scale(int i) const { return bn.as<float>() + static_cast<size_t>(i) * 2 * bnw; }
   float* bn_shift(int i) const { return bn_scale(i) + bnw; }
   int bnw = 0;
@@ -719,13 +731,17 @@ struct pose_plan_s {
 
 static void pose_plan_free(pose_plan_s* p) {
   hgru_plan_free(&p->hg);
+  if (p->copy_st) cudaStreamDestroy(p->copy_st);
+  if (p->ev_begin) cudaEventDestroy(p->ev_begin);
+  if (p->ev_copied) cudaEventDestroy(p->ev_copied);
   DevBuf* all[] = {&p->depth, &p->pool1, &p->conv2, &p->w1, &p->b1, &p->w2, &p->b2, &p->w3, &p->b3,
                    &p->fc1_w, &p->fc1_b, &p->fc2_w, &p->fc2_b, &p->bn, &p->part, &p->fc1, &p->out,
                    &p->act_pool1, &p->act_conv2, &p->wpk2, &p->wpk3, &p->fc1_wt, &p->fc1_a};
   for (auto b : all) b->release();
 }
 
-static int pose_forward_impl(pose_plan_s* p, const float* depth, const float* H2_init, float* out, cudaStream_t st) {
+static int pose_forward_impl(pose_plan_s* p, const float* depth, const float* H2_init, float* out, cudaStream_t st,
+                             cudaEvent_t depth_ready = nullptr) {
   if (!p->params_set) return fail(HGRU_E_STATE, "pose_forward before pose_set_params");
   if (!depth || !out) return fail(HGRU_E_INVALID, "pose_forward: null pointer");
   hgru_plan_s* h = &p->hg;
@@ -734,6 +750,13 @@ static int pose_forward_impl(pose_plan_s* p, const float* depth, const float* H2
   const bool tc = p->mode != HGRU_MODE_FP32;      // stem + fc_1 on tensor cores (hi/lo splits) in both bf16 modes
   int rc;
   p->launches = 0;
+  if (p->mode == HGRU_MODE_BF16) {
+    // the hGRU's initial-state pass does not depend on the crops: run it first (under their upload, when the
+    // caller copies them on another stream)
+    if ((rc = hgru_init_state_bf16(h, H2_init, st))) return rc;
+    h->state_ready = true;
+  }
+  if (depth_ready) CUDA_TRY(cudaStreamWaitEvent(st, depth_ready, 0));
   // conv_1 + relu + pool_1 + BN (hgru_pose.py:50-60)
   hgru::stem_conv1_pool_bn_kernel<<<nblk(npix * (KP / 8)), 256, sizeof(float) * 12 * KP, st>>>(
       depth, p->w1.as<float>(), p->b1.as<float>(), p->bn_scale(0), p->bn_shift(0), p->pool1.as<float>(),
@@ -994,8 +1017,18 @@ int pose_forward_host(pose_plan_t p, const float* depth_host, const float* H2_in
   if (!p) return fail(HGRU_E_INVALID, "pose_forward_host: null plan");
   if (!depth_host || !out_host) return fail(HGRU_E_INVALID, "pose_forward_host: null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  CUDA_TRY(cudaMemcpyAsync(p->depth.p, depth_host, p->depth.bytes, cudaMemcpyHostToDevice, st));
-  int rc = pose_forward_impl(p, p->depth.as<float>(), H2_init, p->out.as<float>(), st);
+  // upload on the plan's copy stream (ordered after the work already queued on `st`), so that the copy engine
+  // runs under the initial-state kernel; the stem waits for the copy
+  if (!p->copy_st) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&p->copy_st, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&p->ev_begin, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&p->ev_copied, cudaEventDisableTiming));
+  }
+  CUDA_TRY(cudaEventRecord(p->ev_begin, st));
+  CUDA_TRY(cudaStreamWaitEvent(p->copy_st, p->ev_begin, 0));
+  CUDA_TRY(cudaMemcpyAsync(p->depth.p, depth_host, p->depth.bytes, cudaMemcpyHostToDevice, p->copy_st));
+  CUDA_TRY(cudaEventRecord(p->ev_copied, p->copy_st));
+  int rc = pose_forward_impl(p, p->depth.as<float>(), H2_init, p->out.as<float>(), st, p->ev_copied);
   if (rc) return rc;
   CUDA_TRY(cudaMemcpyAsync(out_host, p->out.p, p->out.bytes, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
