@@ -172,11 +172,20 @@ void time_real_epilogue(const char* name, int N, int H, int W, int k, int gate =
   std::vector<long long> pr(grid * 40); CK(cudaMemcpy(pr.data(), d_prof, grid * 40 * sizeof(long long), cudaMemcpyDeviceToHost));
   double av[6] = {0, 0, 0, 0, 0, 0}; int nl = 0;
   for (int b = 0; b < grid; ++b) { if (pr[b * 8]) ++nl; for (int i = 0; i < 6; ++i) av[i] += pr[b * 8 + i]; }
+  { long long mx = 0, mxe = 0; double ns = 0; for (int b = 0; b < grid; ++b) { if (pr[b * 8] > mx) mx = pr[b * 8]; if (pr[b * 8 + 4] > mxe) mxe = pr[b * 8 + 4]; ns += pr[b * 8 + 6]; }
+    printf("    max over CTAs: mma_total=%lld epi_total=%lld | mean CTA wall %.1f us -> SM clock %.3f GHz\n", mx, mxe, ns / nl * 1e-3, av[0] / ns); }
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0);
   for (int i = 0; i < 20; ++i) cudaLaunchKernelEx(&cfg, kern, map, wmap, a);
   cudaEventRecord(e1); CK(cudaDeviceSynchronize());
   float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 20;
+  { // the same PROF launch again, right behind 40 more back-to-back launches: clock under sustained load
+    for (int i = 0; i < 40; ++i) cudaLaunchKernelEx(&cfg, kern, map, wmap, a);
+    CK(cudaMemset(d_prof, 0, grid * 40 * sizeof(long long)));
+    CK(cudaLaunchKernelEx(&cfg, kern_prof, map, wmap, ap)); CK(cudaDeviceSynchronize());
+    std::vector<long long> p2(grid * 8); CK(cudaMemcpy(p2.data(), d_prof, grid * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+    double cyc = 0, ns = 0; long long mx = 0; for (int b = 0; b < grid; ++b) { cyc += p2[b * 8]; ns += p2[b * 8 + 6]; if (p2[b * 8] > mx) mx = p2[b * 8]; }
+    printf("    sustained: mma_total avg %.0f max %lld cycles, mean CTA wall %.1f us -> SM clock %.3f GHz\n", cyc / grid, mx, ns / grid * 1e-3, cyc / ns); }
   printf("%s gate=%d CS=%d: %.3f ms | leader avg cycles: mma_total=%.0f wait_win=%.0f wait_acc_empty=%.0f wait_w=%.0f | epi_total=%.0f epi_wait=%.0f\n", name, gate, CS, ms,
          av[0] / nl, av[1] / nl, av[2] / nl, av[3] / nl, av[4] / grid, av[5] / grid);
   if (g_check_layout) {

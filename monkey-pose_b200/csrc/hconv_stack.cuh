@@ -77,7 +77,15 @@ struct StackCfg {
   static constexpr int GATE_W_BYTES = KSTEPS * 2 * KP * 16;
   static constexpr int GATE_BYTES = GATE_A_BYTES + GATE_W_BYTES;
   // ring depth: as deep as the 227 KB allow (pair mode: half-size stages)
-  static constexpr int WSTAGES = (CS == 2) ? 8 : ((WIN_BYTES + GATE_BYTES + 4 * NG * 2 * NPAD * 16 + 2048 <= 232448) ? 4 : 3);
+#ifdef HGRU_STACK_WSTAGES
+  static constexpr int WSTAGES = HGRU_STACK_WSTAGES;      // development switch
+#else
+  // as many as fit next to the window (3..6).  The issuer's wait for a weight stage is the round trip
+  // MMA completion -> commit -> producer -> bulk copy, not bandwidth: it is the same with the refills disabled,
+  // and a fifth stage at k = 25 cut it from 50K to 37K cycles per launch (profiles/r01_stack_kernel_v19_*.log).
+  static constexpr int WFIT = (232448 - WIN_BYTES - GATE_BYTES - 2048) / STAGE_BYTES;
+  static constexpr int WSTAGES = (CS == 2) ? 8 : (WFIT > 6 ? 6 : (WFIT < 3 ? 3 : WFIT));
+#endif
   // The window is loaded in WPARTS parts with their own barriers.  With the remainder-packed schedule the first
   // 15 stages of a pass read chunk planes 0-1 only and the last 9 read planes 2-3 only, so the next unit's first
   // half is loaded under the current unit's last 9 stages and its second half under the next unit's first 15.
@@ -265,10 +273,18 @@ __device__ __forceinline__ void stack_mma_issuer(const TcConvArgs& a, uint32_t t
   uint32_t tc = 0;            // running tile counter: TMEM slot = tc & 3, use count = tc >> 2
   int vit = 0;
   long long t_win = 0, t_acc = 0, t_w = 0, t_begin = 0, t0 = 0;
-  if constexpr (PROF) t_begin = clock64();
+  unsigned long long g_begin = 0;
+  if constexpr (PROF) {
+    t_begin = clock64();
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g_begin));
+  }
   for (int it = 0; it < iters; ++it) {
     const int u = it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);
     const bool valid = u < a.num_units;
+    if (CS == 1 && !valid) break;      // idle tail (a CTA pair keeps going: its members share the weight stream)
+    // Left-most unit of an image row: tap group 0 of the carry tile reads window columns 0..7 = image columns
+    // T-16 .. T-9 < 0, all zero-filled by TMA, so those MMAs add nothing and are not issued.
+    const bool carry_zero = (u % a.units_x) == 0;
     if constexpr (PROF) t0 = clock64();
     if (valid) mbar_wait_warp(bar_win_full, vit & 1);
     if constexpr (PROF) t_win += clock64() - t0;
@@ -290,6 +306,7 @@ __device__ __forceinline__ void stack_mma_issuer(const TcConvArgs& a, uint32_t t
       const uint32_t acc0 = tmem_base + s0 * Cfg::NPAD, acc1 = tmem_base + s1 * Cfg::NPAD;
       const uint64_t a_tile0 = adesc0 + static_cast<uint64_t>(8 * j0);      // 8 pixels = 8 x 16 B
       // one weight stage: wait for it, NG tap groups x (1 or 2) tiles, release it
+      const bool skip0 = carry_zero && j0 == 0;      // tile j0 (accumulator 0) is the carry tile
       auto issue_stage = [&](uint64_t adesc_st, bool first) {
         if constexpr (PROF) t0 = clock64();
         if (!w_ready) mbar_wait_warp(bar_w_full + 8 * st, ph);
@@ -310,7 +327,8 @@ __device__ __forceinline__ void stack_mma_issuer(const TcConvArgs& a, uint32_t t
               mma_bf16_ss_2cta(acc0, adesc, bdesc, idesc, accum);
               if (two) mma_bf16_ss_2cta(acc1, adesc + 8, bdesc, idesc, accum);
             } else {
-              mma_bf16_ss(acc0, adesc, bdesc, idesc, accum);
+              // (with g = 0 skipped, g = 1 of the first stage is the MMA that overwrites the accumulator)
+              if (!(skip0 && g == 0)) mma_bf16_ss(acc0, adesc, bdesc, idesc, (!first || g > (skip0 ? 1 : 0)) ? 1u : 0u);
               if (two) mma_bf16_ss(acc1, adesc + 8, bdesc, idesc, accum);
             }
           }
@@ -376,6 +394,9 @@ __device__ __forceinline__ void stack_mma_issuer(const TcConvArgs& a, uint32_t t
   if (PROF && a.prof && leader) {
     long long* o = a.prof + static_cast<size_t>(blockIdx.x) * 8;
     o[0] = clock64() - t_begin; o[1] = t_win; o[2] = t_acc; o[3] = t_w;
+    unsigned long long g_end;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g_end));
+    o[6] = static_cast<long long>(g_end - g_begin);      // nanoseconds: o[0] / o[6] = the SM clock in GHz
   }
   __syncwarp();
 }
@@ -405,6 +426,7 @@ __device__ __forceinline__ void stack_epilogue(const TcConvArgs& a, uint32_t tme
   for (int it = 0; it < iters; ++it) {
     const int u = it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);
     const bool valid = u < a.num_units;
+    if (CS == 1 && !valid) break;      // idle tail: every role of a single CTA stops at the same iteration
     const int n = u / units_per_frame;
     const int r = u - n * units_per_frame;
     const int uy = r / a.units_x, ux = r - uy * a.units_x;
@@ -430,7 +452,16 @@ __device__ __forceinline__ void stack_epilogue(const TcConvArgs& a, uint32_t tme
       // all T tap slots of this thread's channels: loads issued back to back behind ONE wait
       uint32_t blk[T][CN];
 #pragma unroll
+#ifdef HGRU_DBG_ONE_TMEM_LD
+      detail::tmem_ld_range_issue<CN>(taddr, blk[0]);
+#pragma unroll
+      for (int s = 1; s < T; ++s)
+#pragma unroll
+        for (int c = 0; c < CN; ++c) blk[s][c] = blk[0][c] + s;
+#else
+#pragma unroll
       for (int s = 0; s < T; ++s) detail::tmem_ld_range_issue<CN>(taddr + s * KC, blk[s]);
+#endif
       tmem_ld_wait();
 #pragma unroll
       for (int c = 0; c < NCH; ++c) out[c] = (c < CN) ? __uint_as_float(blk[0][c < CN ? c : 0]) + carry[c < CN ? c : 0] : 0.f;
@@ -442,7 +473,11 @@ __device__ __forceinline__ void stack_epilogue(const TcConvArgs& a, uint32_t tme
         const bool own = pcol >= s;
 #pragma unroll
         for (int c = 0; c < CN; ++c) {
+#ifdef HGRU_DBG_NO_SHFL
+          const float v = __uint_as_float(blk[s][c] + src);
+#else
           const float v = __uint_as_float(__shfl_sync(0xffffffffu, blk[s][c], src));
+#endif
           if (own) out[c] += v; else nxt[c] += v;
         }
       }
@@ -609,7 +644,8 @@ hconv_stack_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
       uint32_t st = 0, ph = 0;
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wpk);
       const uint32_t lead_w_full = (CS > 1) ? mapa_cluster(bar_w_full, 0) : 0u;
-      for (int it = 0; it < iters; ++it)
+      for (int it = 0; it < iters; ++it) {
+        if (CS == 1 && it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x) >= a.num_units) break;
         for (int pr = 0; pr < npairs; ++pr)
           for (int sg = 0; sg < Cfg::PASS_STAGES; ++sg) {
             mbar_wait(bar_w_empty + 8 * st, ph ^ 1);
@@ -627,6 +663,7 @@ hconv_stack_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
             }
             if (++st == Cfg::WSTAGES) { st = 0; ph ^= 1; }
           }
+      }
     }
   } else if (warp == 3) {
     // ---------------- window producer: one TMA box per unit ----------------

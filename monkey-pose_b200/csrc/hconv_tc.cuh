@@ -117,21 +117,33 @@ __device__ __forceinline__ size_t quad_off(const TcConvArgs& a, int n, int quad,
 // L1 (whose SRAM and datapath the UMMA operand fetch needs)
 __device__ __forceinline__ float4 ld_stream(const float* p) {
   float4 r;
+#ifdef HGRU_DBG_NO_GLOBAL
+  return make_float4(0.f, 0.f, 0.f, 0.f);
+#endif
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
                : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
   return r;
 }
 __device__ __forceinline__ float4 ld_stream_rw(const float* p) {   // data also written by this kernel (H2)
   float4 r;
+#ifdef HGRU_DBG_NO_GLOBAL
+  return make_float4(0.f, 0.f, 0.f, 0.f);
+#endif
   asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
                : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
   return r;
 }
 __device__ __forceinline__ void st_stream(float* p, const float4& v) {
+#ifdef HGRU_DBG_NO_GLOBAL
+  if (v.x != 123.456f) return;
+#endif
   asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};"
                ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 __device__ __forceinline__ void st_stream(void* p, const uint4& v) {
+#ifdef HGRU_DBG_NO_GLOBAL
+  if (v.x != 0x12345678u) return;
+#endif
   asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1, %2, %3, %4};"
                ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -180,8 +192,12 @@ __device__ __forceinline__ void store_act_chunk(const TcConvArgs& a, __nv_bfloat
   } else {
     __nv_bfloat16* o = base + ((static_cast<size_t>(n) * (a.KP >> 3) + cg) * plane + pp) * 8;
     const __nv_bfloat16 v = __float2bfloat16(r[0]);
+#ifdef HGRU_DBG_REM_ONE_STORE
+    o[0] = v;      // development: upper bound of what a cheaper remainder-plane write could give (wrong results)
+#else
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j - static_cast<ptrdiff_t>(j) * a.W * 8] = v;
+#endif
   }
 }
 

@@ -425,15 +425,17 @@ init_state_gate_kernel(const float* __restrict__ h0 /*[npix][k] or nullptr = zer
   // the block's pixels are contiguous in h0 ([npix][k]): stream them in flat order, scatter into the padded rows
   {
     const size_t base = p0 * k;
-    const size_t lim = (p0 + kInitPix < npix ? static_cast<size_t>(kInitPix) : npix - p0) * k;
+    const int lim = static_cast<int>((p0 + kInitPix < npix ? static_cast<size_t>(kInitPix) : npix - p0) * k);
+    // e / k by multiplication (exact for e < 2^16, k <= 64): an integer division per element made this
+    // load loop a third of the kernel's instructions
+    const unsigned magic = 0xFFFFFFFFu / static_cast<unsigned>(k) + 1u;
     for (int e = tid; e < kInitPix * k; e += 256) {
-      const int pp = e / k, c = e - pp * k;
-      xin[pp * (KP + 1) + c] = (h0 && static_cast<size_t>(e) < lim) ? h0[base + e] : 0.f;
+      const int pp = static_cast<int>(__umulhi(static_cast<unsigned>(e), magic)), c = e - pp * k;
+      xin[pp * (KP + 1) + c] = (h0 && e < lim) ? __ldg(h0 + base + e) : 0.f;
     }
-    for (int e = tid; e < kInitPix * (KP - k); e += 256) {     // zero the pad channels
-      const int pp = e / (KP - k), c = k + e - pp * (KP - k);
-      xin[pp * (KP + 1) + c] = 0.f;
-    }
+    const int npad = KP - k;                                     // zero the pad channels
+    for (int pp = tid; pp < kInitPix; pp += 256)
+      for (int c = k; c < k + npad; ++c) xin[pp * (KP + 1) + c] = 0.f;
   }
   __syncthreads();
   // thread = 4 pixels (pq, pq+64, pq+128, pq+192) x one chunk of 8 output channels: every weight read from
@@ -445,7 +447,7 @@ init_state_gate_kernel(const float* __restrict__ h0 /*[npix][k] or nullptr = zer
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-    for (int ci = 0; ci < KP; ++ci) {
+    for (int ci = 0; ci < k; ++ci) {          // (the pad input channels are zero)
       const float4 w0 = *reinterpret_cast<const float4*>(wsm + ci * KP + cg * 8);
       const float4 w1 = *reinterpret_cast<const float4*>(wsm + ci * KP + cg * 8 + 4);
       const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
@@ -456,6 +458,9 @@ init_state_gate_kernel(const float* __restrict__ h0 /*[npix][k] or nullptr = zer
         for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(xv, wv[j], acc[i][j]);
       }
     }
+    float bgv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bgv[j] = (cg * 8 + j < k) ? __ldg(bg + cg * 8 + j) : 0.f;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int pp = pq + 64 * i;
@@ -467,7 +472,7 @@ init_state_gate_kernel(const float* __restrict__ h0 /*[npix][k] or nullptr = zer
       for (int j = 0; j < 8; ++j) {
         const int c = cg * 8 + j;
         hv.v[j] = xin[pp * (KP + 1) + c];
-        mv.v[j] = (c < k) ? sigmoidf_(acc[i][j] + bg[c]) * hv.v[j] : 0.f;
+        mv.v[j] = (c < k) ? sigmoidf_(acc[i][j] + bgv[j]) * hv.v[j] : 0.f;
       }
       float* o = H2q + ((n * (KP >> 2) + 2 * cg) * HW + pin) * 4;
       *reinterpret_cast<float4*>(o) = make_float4(hv.v[0], hv.v[1], hv.v[2], hv.v[3]);
