@@ -181,8 +181,8 @@ static int attn_forward_impl(attn_plan_s* p, const float* frames, float* out, cu
   // aconv_1 + relu + apool_1 + batch-norm (:443-454): fused SIMT stem kernel (1 input channel)
   {
     const int C = p->w[0], HW = kAttnHW / 2;
-    const size_t npix = static_cast<size_t>(N) * HW * HW;
-    hgru::stem_conv1_pool_bn_kernel<<<nblk(npix * (C / 8)), 256, sizeof(float) * 12 * C, st>>>(
+    hgru::stem_conv1_pool_bn_kernel<<<dim3(nblk(static_cast<size_t>(N) * HW * ((HW + hgru::kStemPix - 1) / hgru::kStemPix)), C / 8),
+                                      256, 0, st>>>(
         p->resized.as<float>(), p->w1.as<float>(), p->cb[0].as<float>(), p->bn_scale(0), p->bn_shift(0),
         p->pool[0].as<float>(), nullptr, N, HW, HW, C, C, 0);
   }

@@ -240,8 +240,10 @@ struct EpiBiasReluAffine {
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         r[j] = fmaxf(acc[c + j] + __ldg(a.bias + c + j), 0.f) * __ldg(a.scale + c + j) + __ldg(a.shift + c + j);
-      *reinterpret_cast<float4*>(a.out + quad_off(a, n, c >> 2, pin)) = make_float4(r[0], r[1], r[2], r[3]);
-      *reinterpret_cast<float4*>(a.out + quad_off(a, n, (c >> 2) + 1, pin)) = make_float4(r[4], r[5], r[6], r[7]);
+      if (a.out) {
+        *reinterpret_cast<float4*>(a.out + quad_off(a, n, c >> 2, pin)) = make_float4(r[0], r[1], r[2], r[3]);
+        *reinterpret_cast<float4*>(a.out + quad_off(a, n, (c >> 2) + 1, pin)) = make_float4(r[4], r[5], r[6], r[7]);
+      }
       if (a.out_bf16) {
         // hi + lo bf16 split of the operand copy (see stem_conv1_pool_bn_kernel): planes [0,CG), [CG,2CG)
         float hi[8], lo[8];

@@ -746,7 +746,6 @@ static int pose_forward_impl(pose_plan_s* p, const float* depth, const float* H2
   if (!depth || !out) return fail(HGRU_E_INVALID, "pose_forward: null pointer");
   hgru_plan_s* h = &p->hg;
   const int N = p->N, HW = p->HW, KP = p->KP, C = p->C;
-  const size_t npix = static_cast<size_t>(N) * HW * HW;
   const bool tc = p->mode != HGRU_MODE_FP32;      // stem + fc_1 on tensor cores (hi/lo splits) in both bf16 modes
   int rc;
   p->launches = 0;
@@ -758,9 +757,11 @@ static int pose_forward_impl(pose_plan_s* p, const float* depth, const float* H2
   }
   if (depth_ready) CUDA_TRY(cudaStreamWaitEvent(st, depth_ready, 0));
   // conv_1 + relu + pool_1 + BN (hgru_pose.py:50-60)
-  hgru::stem_conv1_pool_bn_kernel<<<nblk(npix * (KP / 8)), 256, sizeof(float) * 12 * KP, st>>>(
-      depth, p->w1.as<float>(), p->b1.as<float>(), p->bn_scale(0), p->bn_shift(0), p->pool1.as<float>(),
-      tc ? p->act_pool1.as<__nv_bfloat16>() : nullptr, N, HW, HW, C, KP, tc ? 1 : 0);
+  hgru::stem_conv1_pool_bn_kernel<<<dim3(nblk(static_cast<size_t>(N) * HW * ((HW + hgru::kStemPix - 1) / hgru::kStemPix)), KP / 8),
+                                    256, 0, st>>>(
+      depth, p->w1.as<float>(), p->b1.as<float>(), p->bn_scale(0), p->bn_shift(0),
+      tc ? nullptr : p->pool1.as<float>(), tc ? p->act_pool1.as<__nv_bfloat16>() : nullptr, N, HW, HW, C, KP,
+      tc ? 1 : 0);
   ++p->launches;
   // conv_2 + relu + BN (:61-70), conv_3 + relu + BN (:71-80); conv3 output is X of the hGRU
   if (tc) {
@@ -768,7 +769,7 @@ static int pose_forward_impl(pose_plan_s* p, const float* depth, const float* H2
     a.N = N; a.H = HW; a.W = HW; a.KP = KP; a.kreal = C;
     a.wpk = p->wpk2.as<__nv_bfloat16>(); a.bias = p->b2.as<float>();
     a.scale = p->bn_scale(1); a.shift = p->bn_shift(1);
-    a.out = p->conv2.as<float>(); a.out_bf16 = p->act_conv2.as<__nv_bfloat16>();
+    a.out = nullptr; a.out_bf16 = p->act_conv2.as<__nv_bfloat16>();      // (no fp32 copy: see pose_plan_create)
     if ((rc = dispatch_tc_stem(KP, p->map_pool1, a, st))) return rc;
     a.wpk = p->wpk3.as<__nv_bfloat16>(); a.bias = p->b3.as<float>();
     a.scale = p->bn_scale(2); a.shift = p->bn_shift(2);
@@ -889,7 +890,9 @@ int pose_plan_create(int N, int HW, int C, int S, int T, int F, int O, int mode,
   const size_t K = static_cast<size_t>(HW) * HW * C;
   auto A = [&](DevBuf& b, size_t bytes) { if (!rc) rc = b.alloc(bytes); };
   A(p->depth, static_cast<size_t>(N) * 4 * HW * HW * sizeof(float));
-  A(p->pool1, act); A(p->conv2, act);
+  // fp32 copies of pool1 / conv2 exist only on the exact path: the tensor-core stem consumes bf16 hi/lo operand
+  // copies, and pose_get_activation rebuilds the fp32 tensors from those (hi + lo, 16 mantissa bits)
+  if (mode == HGRU_MODE_FP32) { A(p->pool1, act); A(p->conv2, act); }
   A(p->w1, sizeof(float) * 9 * C); A(p->b1, sizeof(float) * KP);
   A(p->b2, sizeof(float) * KP); A(p->b3, sizeof(float) * KP);
   // fc_1 on tensor cores (operand rows are padded to whole k-blocks, so any K works)
@@ -1039,8 +1042,17 @@ int pose_get_activation(pose_plan_t p, const char* name, float* dst, void* strea
   if (!p || !name || !dst) return fail(HGRU_E_INVALID, "pose_get_activation: null argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const float* src = nullptr;
-  if (!strcmp(name, "pool1")) src = p->pool1.as<float>();
-  else if (!strcmp(name, "conv2")) src = p->conv2.as<float>();
+  const bool is_pool1 = !strcmp(name, "pool1"), is_conv2 = !strcmp(name, "conv2");
+  if ((is_pool1 || is_conv2) && p->mode != HGRU_MODE_FP32) {
+    // tensor-core stem: the activation lives as bf16 hi | lo chunk planes
+    const hgru_plan_s* h = &p->hg;
+    hgru::split_chunks_to_nhwc_kernel<<<nblk(h->npix * h->k), 256, 0, st>>>(
+        (is_pool1 ? p->act_pool1 : p->act_conv2).as<__nv_bfloat16>(), dst, h->npix, h->k, h->KP / 8, h->H * h->W);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+  }
+  if (is_pool1) src = p->pool1.as<float>();
+  else if (is_conv2) src = p->conv2.as<float>();
   else if (!strcmp(name, "conv3")) src = p->hg.Xp.as<float>();
   else if (!strcmp(name, "hgru")) src = p->hg.H2.as<float>();
   else if (!strcmp(name, "fc1")) {

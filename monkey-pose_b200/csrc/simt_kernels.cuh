@@ -155,86 +155,110 @@ __device__ __forceinline__ __nv_bfloat16* chunk_ptr(__nv_bfloat16* base, int n, 
 
 // ------------------------------------------------------------------------------------------------
 // Stem head: conv 3x3 (1 -> C) + bias + ReLU (hgru_pose.py:50,146-148), 2x2/2 max-pool (:51,134-137)
-// and the inference batch-norm affine (:52-60), fused: [N,2H,2W,1] -> [N,H,W,KP] (+ bf16 chunked copy).
-// Bandwidth-bound stencil.  One thread = one pooled pixel x one chunk of 8 channels, so a warp writes
-// 32/CG whole pixels = 1 KB of contiguous fp32; filter taps / bias / affine live in shared memory.
+// and the inference batch-norm affine (:52-60), fused: [N,2H,2W,1] -> [N,H,W,KP] (+ bf16 hi/lo chunked copy).
+// One thread = 4 horizontally adjacent pooled pixels x one chunk of 8 channels (blockIdx.y = the chunk, so a
+// chunk of layout padding costs nothing and a warp writes 128 consecutive pixels of one chunk plane).  Every
+// filter tap read from shared memory feeds 16 FMAs (4 pixels x the 2x2 pooling window); with one pixel per
+// thread the kernel was bound by those shared-memory reads (145 us per 256 frames, now HBM-bound).
+// `out` (fp32) may be null: the tensor-core path only consumes the bf16 hi/lo copy.
 // ------------------------------------------------------------------------------------------------
+constexpr int kStemPix = 4;      // pooled pixels per thread
 __global__ void __launch_bounds__(256)
 stem_conv1_pool_bn_kernel(const float* __restrict__ depth, const float* __restrict__ w /*[3][3][1][C]*/,
                           const float* __restrict__ bias, const float* __restrict__ scale,
                           const float* __restrict__ shift, float* __restrict__ out,
                           __nv_bfloat16* __restrict__ out_bf16, int N, int H, int W, int C, int KP, int quad) {
-  extern __shared__ float smem_f[];
-  float* wsm = smem_f;             // [9][KP]
-  float* bsm = wsm + 9 * KP;       // bias, scale, shift: [3][KP]
-  for (int e = threadIdx.x; e < 9 * KP; e += blockDim.x) {
-    const int t = e / KP, c = e - t * KP;
-    wsm[e] = (c < C) ? w[t * C + c] : 0.f;
-  }
-  for (int e = threadIdx.x; e < KP; e += blockDim.x) {
-    bsm[e] = (e < C) ? bias[e] : 0.f;
-    bsm[KP + e] = (e < C) ? scale[e] : 0.f;
-    bsm[2 * KP + e] = (e < C) ? shift[e] : 0.f;
+  __shared__ float wsm[9][8];      // this chunk's filter taps
+  __shared__ float bsm[3][8];      // bias, scale, shift
+  const int cg = blockIdx.y, CG = KP >> 3;
+  if (threadIdx.x < 72) {
+    const int t = threadIdx.x >> 3, c = cg * 8 + (threadIdx.x & 7);
+    wsm[t][threadIdx.x & 7] = (c < C) ? w[t * C + c] : 0.f;
+  } else if (threadIdx.x < 96) {
+    const int v = (threadIdx.x - 72) >> 3, c = cg * 8 + (threadIdx.x & 7);
+    const float* src = v == 0 ? bias : v == 1 ? scale : shift;
+    bsm[v][threadIdx.x & 7] = (c < C) ? src[c] : 0.f;
   }
   __syncthreads();
-  const int CG = KP >> 3;
-  const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-  const size_t npix = static_cast<size_t>(N) * H * W;
-  if (idx >= npix * CG) return;
-  const int cg = idx % CG;
-  const size_t p = idx / CG;
-  const int x = p % W;
-  const int y = (p / W) % H;
-  const int n = p / (static_cast<size_t>(W) * H);
+  const int WQ = (W + kStemPix - 1) / kStemPix;
+  const size_t g = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (g >= static_cast<size_t>(N) * H * WQ) return;
+  const int xq = g % WQ;
+  const int y = (g / WQ) % H;
+  const int n = g / (static_cast<size_t>(WQ) * H);
+  const int x0 = xq * kStemPix;
   const int IH = 2 * H, IW = 2 * W;
-  float v[4][4];                    // 4x4 input neighbourhood of the 2x2 pooling window
+  float v[4][2 * kStemPix + 2];     // input rows 2y-1 .. 2y+2, columns 2x0-1 .. 2x0+8
 #pragma unroll
-  for (int rr = 0; rr < 4; ++rr)
+  for (int rr = 0; rr < 4; ++rr) {
+    const int yy = 2 * y - 1 + rr;
+    const float* row = depth + (static_cast<size_t>(n) * IH + yy) * IW;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int yy = 2 * y - 1 + rr, xx = 2 * x - 1 + q;
-      v[rr][q] = (yy >= 0 && yy < IH && xx >= 0 && xx < IW)
-                     ? __ldg(depth + (static_cast<size_t>(n) * IH + yy) * IW + xx) : 0.f;
+    for (int q = 0; q < 2 * kStemPix + 2; ++q) {
+      const int xx = 2 * x0 - 1 + q;
+      v[rr][q] = (yy >= 0 && yy < IH && xx >= 0 && xx < IW) ? __ldg(row + xx) : 0.f;
     }
-  F8 r;
+  }
+  const int nreal = C - cg * 8;     // real channels of this chunk (uniform over the block)
+  float r[kStemPix][8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const int c = cg * 8 + j;
-    float m = -INFINITY;
+    if (j < nreal) {
+      float wt[9];
 #pragma unroll
-    for (int py = 0; py < 2; ++py)
+      for (int t = 0; t < 9; ++t) wt[t] = wsm[t][j];
+      const float bj = bsm[0][j], sj = bsm[1][j], hj = bsm[2][j];
 #pragma unroll
-      for (int px = 0; px < 2; ++px) {
-        float a = 0.f;
+      for (int px = 0; px < kStemPix; ++px) {
+        float m = -INFINITY;
 #pragma unroll
-        for (int dy = 0; dy < 3; ++dy)
+        for (int py = 0; py < 2; ++py)
 #pragma unroll
-          for (int dx = 0; dx < 3; ++dx) a = fmaf(v[py + dy][px + dx], wsm[(dy * 3 + dx) * KP + c], a);
-        m = fmaxf(m, a);
+          for (int qx = 0; qx < 2; ++qx) {
+            float a = 0.f;
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+              for (int dx = 0; dx < 3; ++dx) a = fmaf(v[py + dy][2 * px + qx + dx], wt[dy * 3 + dx], a);
+            m = fmaxf(m, a);
+          }
+        r[px][j] = fmaxf(m + bj, 0.f) * sj + hj;      // relu and max commute
       }
-    // relu and max commute; pad channels have zero scale/shift -> 0
-    r.v[j] = fmaxf(m + bsm[c], 0.f) * bsm[KP + c] + bsm[2 * KP + c];
-  }
-  const size_t pin = static_cast<size_t>(y) * W + x;
-  if (quad) {   // quad-chunked fp32 [n][c/4][pix][4] (tensor-core path)
-    const size_t HW = static_cast<size_t>(H) * W;
-    float* o = out + ((static_cast<size_t>(n) * (KP >> 2) + 2 * cg) * HW + pin) * 4;
-    *reinterpret_cast<float4*>(o) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
-    *reinterpret_cast<float4*>(o + HW * 4) = make_float4(r.v[4], r.v[5], r.v[6], r.v[7]);
-  } else {
-    st8(out + p * KP + cg * 8, r);
-  }
-  if (out_bf16) {
-    // operand copy for the tensor-core conv_2, split into bf16 hi + lo parts (chunk planes [0,CG) and
-    // [CG,2CG)): the pooled depth map is smooth, so plain bf16 rounding errors add up coherently
-    F8 hi, lo;
+    } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      hi.v[j] = __bfloat162float(__float2bfloat16(r.v[j]));
-      lo.v[j] = r.v[j] - hi.v[j];
+      for (int px = 0; px < kStemPix; ++px) r[px][j] = 0.f;     // layout padding
     }
-    st8_bf16(chunk_ptr(out_bf16, n, cg, pin, H * W, 2 * CG), hi);
-    st8_bf16(chunk_ptr(out_bf16, n, CG + cg, pin, H * W, 2 * CG), lo);
+  }
+  const size_t HW = static_cast<size_t>(H) * W;
+#pragma unroll
+  for (int px = 0; px < kStemPix; ++px) {
+    const int x = x0 + px;
+    if (x >= W) break;
+    const size_t pin = static_cast<size_t>(y) * W + x;
+    F8 rv;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) rv.v[j] = r[px][j];
+    if (out) {
+      if (quad) {   // quad-chunked fp32 [n][c/4][pix][4] (tensor-core path)
+        float* o = out + ((static_cast<size_t>(n) * (KP >> 2) + 2 * cg) * HW + pin) * 4;
+        *reinterpret_cast<float4*>(o) = make_float4(rv.v[0], rv.v[1], rv.v[2], rv.v[3]);
+        *reinterpret_cast<float4*>(o + HW * 4) = make_float4(rv.v[4], rv.v[5], rv.v[6], rv.v[7]);
+      } else {
+        st8(out + (static_cast<size_t>(n) * HW + pin) * KP + cg * 8, rv);
+      }
+    }
+    if (out_bf16) {
+      // operand copy for the tensor-core conv_2, split into bf16 hi + lo parts (chunk planes [0,CG) and
+      // [CG,2CG)): the pooled depth map is smooth, so plain bf16 rounding errors add up coherently
+      F8 hi, lo;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        hi.v[j] = __bfloat162float(__float2bfloat16(rv.v[j]));
+        lo.v[j] = rv.v[j] - hi.v[j];
+      }
+      st8_bf16(chunk_ptr(out_bf16, n, cg, pin, H * W, 2 * CG), hi);
+      st8_bf16(chunk_ptr(out_bf16, n, CG + cg, pin, H * W, 2 * CG), lo);
+    }
   }
 }
 
@@ -401,6 +425,20 @@ quad_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, size_
   const size_t p = i / k;
   const size_t n = p / HW, pin = p - n * HW;
   out[i] = in[((n * (KP >> 2) + (c >> 2)) * HW + pin) * 4 + (c & 3)];
+}
+
+// bf16 hi | lo chunk planes [n][2*CG][pix][8] (the operand copies of the tensor-core stem) -> fp32 NHWC
+__global__ void __launch_bounds__(256)
+split_chunks_to_nhwc_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, size_t npix, int k, int CG,
+                            int HW) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;   // over [npix][k]
+  if (i >= npix * k) return;
+  const int c = i % k;
+  const size_t p = i / k;
+  const size_t n = p / HW, pin = p - n * HW;
+  const size_t hi = ((n * 2 * CG + (c >> 3)) * HW + pin) * 8 + (c & 7);
+  const size_t lo = ((n * 2 * CG + CG + (c >> 3)) * HW + pin) * 8 + (c & 7);
+  out[i] = __bfloat162float(in[hi]) + __bfloat162float(in[lo]);
 }
 
 // ------------------------------------------------------------------------------------------------

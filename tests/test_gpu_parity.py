@@ -140,6 +140,22 @@ def test_pose_model_matches_reference_layer_golden():
                                       z["var:conv_2/conv_2_biases"]) * eps_scale)[0] < 1e-5
 
 
+def test_stem_activations_on_the_tensor_core_path():
+    """bf16 modes keep pool1 / conv2 only as bf16 hi | lo operand copies; `activation()` rebuilds the fp32 tensors
+    from them (16 mantissa bits).  Odd width and 25 channels: ragged 4-pixel groups and a padded chunk."""
+    outs = {}
+    for mode in ("fp32", "bf16"):
+        m = mp.model()
+        m.channels, m.timesteps, m.fc_hidden, m.compute_mode = 25, 1, 16, mode
+        P = init.pose_params(channels=25, S=15, T=1, hw=9, fc_hidden=16, out=5, seed=11, random_bn=True)
+        m.load_params(P)
+        m.build(torch.as_tensor(init.synthetic_depth(3, seed=4, size=18)).cuda(), 5)
+        outs[mode] = {k: m.activation(k).cpu().numpy() for k in ("pool1", "conv2", "conv3")}
+    assert onp.rel_err(outs["bf16"]["pool1"], outs["fp32"]["pool1"])[0] < 2e-5
+    assert onp.rel_err(outs["bf16"]["conv2"], outs["fp32"]["conv2"])[0] < 1e-4
+    assert onp.rel_err(outs["bf16"]["conv3"], outs["fp32"]["conv3"])[0] < 1e-4
+
+
 def test_pose_host_entry_point_equals_device_entry_point():
     m1, out_dev, *_ = _pose("bf16", 2, 16, 16, 2, 15, 64, host=False)
     m2, out_host, *_ = _pose("bf16", 2, 16, 16, 2, 15, 64, host=True)
