@@ -431,6 +431,12 @@ __device__ __forceinline__ void stack_epilogue(const TcConvArgs& a, uint32_t tme
     const int r = u - n * units_per_frame;
     const int uy = r / a.units_x, ux = r - uy * a.units_x;
     const int y = uy * kTileRows + prow;
+    if (a.wait_flags && valid) {
+      // chained launch: this frame's tensors are ready once all its units finished in the previous launch
+      if (lane == 0)
+        while (ld_acquire_gpu(a.wait_flags + n) < a.flag_target) {}
+      __syncwarp();
+    }
     float carry[CN];
 #pragma unroll
     for (int c = 0; c < CN; ++c) carry[c] = 0.f;
@@ -541,6 +547,14 @@ __device__ __forceinline__ void stack_epilogue(const TcConvArgs& a, uint32_t tme
         if constexpr (PROF) { const long long t = clock64(); e_gm += t - e0; e0 = t; }
       }
     }
+    if (a.done_flags && valid) {
+      // all epilogue stores of this unit are issued: publish them, then count the unit as done
+      asm volatile("bar.sync 2, %0;" ::"n"(Cfg::NEPI) : "memory");
+      if (threadIdx.x == 128) {
+        __threadfence();
+        atomicAdd(a.done_flags + n, 1);
+      }
+    }
   }
   if (PROF && a.prof && (threadIdx.x & 127) == 0) {
     if (profile) {
@@ -630,6 +644,7 @@ hconv_stack_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
   if constexpr (CS > 1) cluster_sync_all();     // peers' barriers exist before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  grid_launch_dependents();      // a chained next launch may take SMs as they free up (no effect otherwise)
 
   // every CTA runs the same number of iterations (cluster members share the weight stream)
   const int iters = (a.num_units + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
@@ -676,6 +691,10 @@ hconv_stack_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
         const int n = u / units_per_frame;
         const int r = u - n * units_per_frame;
         const int uy = r / a.units_x, ux = r - uy * a.units_x;
+        if (a.wait_flags) {
+          while (ld_acquire_gpu(a.wait_flags + n) < a.flag_target) {}
+          fence_proxy_async_global();
+        }
         mbar_wait(bar_win_empty, (vit & 1) ^ 1);
         if constexpr (CS > 1) {
           // the leader's barrier collects the bytes of both windows (the peer's unit is u + 1)

@@ -104,6 +104,12 @@ struct TcConvArgs {
   // operand tensors written by this launch carry bf16 hi AND lo halves (chunk planes [0,CG) and [CG,2CG)):
   // the SPLIT3 kernels of the bf16x3 mode read both (mutually exclusive with act_pad)
   int split_out;
+  // Launch chaining (stacked kernel): per-frame completion counters.  A unit of frame n may touch that frame's
+  // tensors once wait_flags[n] == flag_target (all units of the frame finished in the previous launch), and adds 1
+  // to done_flags[n] when its own stores are out.  nullptr = ordinary stream order.
+  const int* wait_flags;
+  int* done_flags;
+  int flag_target;
 };
 
 // fp32 state tensors of the tensor-core path are "quad-chunked": [n][c/4][y][x][4].  A thread owns
@@ -120,7 +126,8 @@ __device__ __forceinline__ float4 ld_stream(const float* p) {
 #ifdef HGRU_DBG_NO_GLOBAL
   return make_float4(0.f, 0.f, 0.f, 0.f);
 #endif
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+  // (not .nc: a chained launch reads tensors that the previous launch, possibly still running, wrote)
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
                : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
   return r;
 }

@@ -176,8 +176,16 @@ int launch_stack(const CUtensorMap& map, hgru::TcConvArgs a, cudaStream_t st) {
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int grid = a.num_units < sms ? a.num_units : sms;
-  kern<<<grid, Cfg::NTHREADS, Cfg::SMEM_BYTES, st>>>(map, map, a);   // (w_map is only read in pair mode)
-  CUDA_TRY(cudaGetLastError());
+  a.flag_target = a.units_x * a.units_y;
+  // A launch that waits on the previous launch's per-frame counters is chained to it (programmatic dependent
+  // launch): its CTAs take SMs as the previous launch's CTAs exit instead of waiting for the whole grid.
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(Cfg::NTHREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = a.wait_flags ? 1 : 0;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, map, map, a));     // (w_map is only read in pair mode)
   return 0;
 }
 
@@ -259,8 +267,11 @@ __global__ void pad_hwio_kernel(const float* in, float* out, int taps, int k, in
 struct KernelTimer {
   std::vector<cudaEvent_t> ev;
   int used = 0;
+  int kernels = 0;        // horizontal-conv launches inside the recorded intervals
+  bool open = false;
   void begin(cudaStream_t st) {
-    if (!g_timing) return;
+    if (!g_timing || open) return;
+    open = true;
     while (static_cast<int>(ev.size()) < used + 2) {
       cudaEvent_t e;
       cudaEventCreate(&e);
@@ -268,12 +279,14 @@ struct KernelTimer {
     }
     cudaEventRecord(ev[used], st);
   }
-  void end(cudaStream_t st) {
-    if (!g_timing) return;
+  void end(cudaStream_t st, int n = 1) {
+    if (!g_timing || !open) return;
     cudaEventRecord(ev[used + 1], st);
     used += 2;
+    kernels += n;
+    open = false;
   }
-  void reset() { used = 0; }
+  void reset() { used = 0; kernels = 0; open = false; }
   int collect(float* total_ms) {
     float t = 0.f;
     for (int i = 0; i + 1 < used; i += 2) {
@@ -283,7 +296,7 @@ struct KernelTimer {
       t += ms;
     }
     *total_ms = t;
-    return used / 2;
+    return used ? kernels : 0;
   }
   ~KernelTimer() {
     for (auto e : ev) cudaEventDestroy(e);
@@ -306,6 +319,8 @@ struct hgru_plan_s {
   DevBuf Xp, H2, H1, C, G, A;
   // bf16 chunked operand copies (tensor-core mode)
   DevBuf actA, actH1, actH2;
+  DevBuf flags;                     // launch chaining: [2T][N] per-frame completion counters (stacked kernel)
+  bool chain = false;
   CUtensorMap mapA, mapH1;          // SxS halo-window boxes (horizontal convs)
   CUtensorMap mapH1_g, mapH2_g;     // 1x1 boxes (gate convs)
   // readout operand emitted by the last H2 epilogue (set by the pose plan; nullptr for the bare layer)
@@ -322,7 +337,7 @@ struct hgru_plan_s {
   size_t workspace() const {
     return p_r.bytes + i_r.bytes + o_r.bytes + vecs.bytes + rho.bytes + wpk.bytes + wpk_i.bytes +
            wpk_o.bytes + Xp.bytes + H2.bytes + H1.bytes + C.bytes + G.bytes + A.bytes + actA.bytes +
-           actH1.bytes + actH2.bytes;
+           actH1.bytes + actH2.bytes + flags.bytes;
   }
 };
 
@@ -374,6 +389,10 @@ static int hgru_plan_init(hgru_plan_s* p, int N, int H, int W, int k, int S, int
     int box_cols = g.box_cols, box_rows = g.box_rows, box_chunks = 2;
     size_t wbytes = tapb * S * S;
     if (p->stacked) {
+      // consecutive conv launches are chained through per-frame counters (HGRU_NO_CHAIN=1: plain stream order)
+      const char* nc = getenv("HGRU_NO_CHAIN");
+      p->chain = !(nc && nc[0] == '1');
+      if (p->chain && (rc = p->flags.alloc(sizeof(int) * 2 * static_cast<size_t>(T) * N))) return rc;
       p->stack_T = sg.T;
       p->act_pad = sg.act_pad;
       box_cols = sg.box_cols; box_rows = sg.box_rows;
@@ -401,7 +420,7 @@ static int hgru_plan_init(hgru_plan_s* p, int N, int H, int W, int k, int S, int
 
 static void hgru_plan_free(hgru_plan_s* p) {
   DevBuf* all[] = {&p->p_r, &p->i_r, &p->o_r, &p->vecs, &p->rho, &p->wpk, &p->wpk_i, &p->wpk_o, &p->Xp,
-                   &p->H2, &p->H1, &p->C, &p->G, &p->A, &p->actA, &p->actH1, &p->actH2};
+                   &p->H2, &p->H1, &p->C, &p->G, &p->A, &p->actA, &p->actH1, &p->actH2, &p->flags};
   for (auto b : all) b->release();
 }
 
@@ -535,6 +554,17 @@ static int hgru_run_bf16(hgru_plan_s* p, const float* Xp, const float* H2_init_n
   p->state_ready = false;
   ++p->launches;
   const bool fused = p->stacked;
+  // Chained launches (see TcConvArgs::wait_flags): launch l waits per frame on launch l-1's counters instead of on
+  // the whole grid.  Not with traces (their copy kernels sit between the launches).
+  const bool chain = fused && p->chain && !H1_trace && !H2_trace;
+  int* flags = chain ? p->flags.as<int>() : nullptr;
+  if (chain) CUDA_TRY(cudaMemsetAsync(flags, 0, p->flags.bytes, st));
+  auto set_flags = [&](hgru::TcConvArgs& a, int l) {
+    if (!chain) return;
+    a.done_flags = flags + static_cast<size_t>(l) * p->N;
+    a.wait_flags = l > 0 ? flags + static_cast<size_t>(l - 1) * p->N : nullptr;
+  };
+  if (chain) p->timer.begin(st);
   for (int t = 0; t < p->T; ++t) {
     hgru::TcConvArgs a;
     if (!fused && t > 0) {
@@ -553,11 +583,12 @@ static int hgru_run_bf16(hgru_plan_s* p, const float* Xp, const float* H2_init_n
     a.out = p->H1.as<float>(); a.out_bf16 = p->actH1.as<__nv_bfloat16>();
     a.gate_wpk = p->wpk_o.as<__nv_bfloat16>(); a.gate_bias = p->vec(V_OB); a.gate_out = p->G.as<float>();
     a.do_gate = fused ? 1 : 0;
-    p->timer.begin(st);
+    set_flags(a, 2 * t);
+    if (!chain) p->timer.begin(st);
     if ((rc = p->stacked ? dispatch_stack<hgru::EpiH1>(KP, p->stack_T, p->mapA, a, st)
                         : dispatch_tc_hconv<hgru::EpiH1>(p->S, KP, p->mapA, a, st)))
       return rc;
-    p->timer.end(st);
+    if (!chain) p->timer.end(st);
     ++p->launches;
     if (!fused) {
       // circuit_output gate (:729-740): G2 = sigmoid(H1 *1x1 o_r + o_b)
@@ -580,11 +611,13 @@ static int hgru_run_bf16(hgru_plan_s* p, const float* Xp, const float* H2_init_n
     if (t + 1 == p->T && p->fc_a) {     // last update also emits the readout's bf16 hi/lo operand
       a.fc_a = p->fc_a; a.fc_scale = p->fc_scale; a.fc_shift = p->fc_shift; a.fc_kpad = p->fc_kpad;
     }
-    p->timer.begin(st);
+    set_flags(a, 2 * t + 1);
+    if (!chain) p->timer.begin(st);
     if ((rc = p->stacked ? dispatch_stack<hgru::EpiH2>(KP, p->stack_T, p->mapH1, a, st)
                         : dispatch_tc_hconv<hgru::EpiH2>(p->S, KP, p->mapH1, a, st)))
       return rc;
-    p->timer.end(st);
+    if (!chain) p->timer.end(st);
+    else if (t + 1 == p->T) p->timer.end(st, 2 * p->T);      // chained: one interval around all 2T launches
     ++p->launches;
     if (H1_trace) {
       hgru::quad_to_nhwc_kernel<<<nblk(p->npix * p->k), 256, 0, st>>>(

@@ -156,6 +156,35 @@ def test_stem_activations_on_the_tensor_core_path():
     assert onp.rel_err(outs["bf16"]["conv3"], outs["fp32"]["conv3"])[0] < 1e-4
 
 
+def test_chained_launches_equal_stream_ordered_launches(monkeypatch):
+    """The stacked conv launches of a forward are chained through per-frame counters (programmatic dependent launch:
+    launch l+1 starts while launch l is still running).  Same results, bit for bit, as plain stream order
+    (HGRU_NO_CHAIN=1), on every repetition; 150 frames = 600 units on 148 CTAs: several rounds, ragged tail."""
+    N, ch, hw, T, S, F = 150, 25, 64, 4, 15, 32
+    P = init.pose_params(channels=ch, S=S, T=T, hw=hw, fc_hidden=F, out=69, seed=3, stress=4.0, random_bn=True)
+    depth = torch.as_tensor(init.synthetic_depth(N, seed=0, size=2 * hw)).cuda()
+    h0 = init.hidden_init((N, hw, hw, ch), seed=5)
+    outs = {}
+    for chained in (False, True):
+        if chained:
+            monkeypatch.delenv("HGRU_NO_CHAIN", raising=False)
+        else:
+            monkeypatch.setenv("HGRU_NO_CHAIN", "1")      # read when the plan is created
+        m = mp.model()
+        m.channels, m.timesteps, m.fc_hidden, m.compute_mode, m.hidden_state = ch, T, F, "bf16", h0
+        m.load_params(P)
+        reps = []
+        for _ in range(12 if chained else 2):
+            reps.append(m.build(depth, 69).clone())
+        torch.cuda.synchronize()
+        hg = m.activation("hgru")
+        for r in reps[1:]:
+            assert torch.equal(r, reps[0])
+        outs[chained] = (reps[0], hg)
+    assert torch.equal(outs[True][0], outs[False][0])
+    assert torch.equal(outs[True][1], outs[False][1])
+
+
 def test_pose_host_entry_point_equals_device_entry_point():
     m1, out_dev, *_ = _pose("bf16", 2, 16, 16, 2, 15, 64, host=False)
     m2, out_host, *_ = _pose("bf16", 2, 16, 16, 2, 15, 64, host=True)
