@@ -237,7 +237,7 @@ static int attn_forward_impl(attn_plan_s* p, const float* frames, float* out, cu
     }
   }
   // afc_1 bias, relu, batch-norm (R-D5: last axis), afc_out (:501-525)
-  hgru::fc_tail_kernel<<<N, 256, sizeof(float) * p->F, st>>>(
+  hgru::fc_tail_kernel<<<N, 256, sizeof(float) * (p->F + hgru::kFcTailScratch), st>>>(
       p->part.as<float>(), p->gSplits[5], p->fc1_b.as<float>(), p->bn_scale(5), p->bn_shift(5),
       p->fc2_w.as<float>(), p->fc2_b.as<float>(), p->fc1.as<float>(), out, N, p->F, p->O);
   ++p->launches;

@@ -526,7 +526,33 @@ static int hgru_run_fp32(hgru_plan_s* p, const float* Xp, float* H1_trace, float
 // C2+H2).  All integration math happens on TMEM accumulators.
 // Initial state of the bf16 path: O_0 (NHWC, or zeros) -> H2 (quad-chunked fp32) + the first gated operand.
 // Touches only H2 / actA, so it can run before (and concurrently with the input copy of) the stem.
+template <int KP>
+static int launch_init_tc(const float* h0, const hgru::TcConvArgs& a, cudaStream_t st) {
+  using Cfg = hgru::InitCfg<KP>;
+  const int tiles_per_frame = (a.H * a.W + 127) / 128;
+  hgru::init_state_tc_kernel<KP><<<a.N * tiles_per_frame, 128, Cfg::SMEM_BYTES, st>>>(h0, a);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 static int hgru_init_state_bf16(hgru_plan_s* p, const float* H2_init_nhwc, cudaStream_t st) {
+  static const bool simt_init = [] { const char* e = getenv("HGRU_SIMT_INIT"); return e && e[0] == '1'; }();
+  if (!simt_init) {      // (development switch: HGRU_SIMT_INIT=1 runs the exact-fp32 SIMT gate below)
+    // tensor-core version: the 1x1 gate conv as one UMMA tile per 128 pixels (bf16 operands like every later gate)
+    hgru::TcConvArgs a{};
+    a.N = p->N; a.H = p->H; a.W = p->W; a.KP = p->KP; a.kreal = p->k; a.act_pad = p->act_pad;
+    a.wpk = p->wpk_i.as<__nv_bfloat16>(); a.bias = p->vec(V_IB); a.H2 = p->H2.as<float>();
+    a.out_bf16 = p->actA.as<__nv_bfloat16>();
+    static bool attr64 = false;
+    if (p->KP == 64 && !attr64) {
+      CUDA_TRY(cudaFuncSetAttribute(hgru::init_state_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    hgru::InitCfg<64>::SMEM_BYTES));
+      attr64 = true;
+    }
+    if (p->KP == 64) return launch_init_tc<64>(H2_init_nhwc, a, st);
+    if (p->KP == 32) return launch_init_tc<32>(H2_init_nhwc, a, st);
+    if (p->KP == 16) return launch_init_tc<16>(H2_init_nhwc, a, st);
+  }
   static bool attr = false;
   if (!attr) {
     CUDA_TRY(cudaFuncSetAttribute(hgru::init_state_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -840,7 +866,7 @@ static int pose_forward_impl(pose_plan_s* p, const float* depth, const float* H2
                                                 p->bn_shift(3), p->part.as<float>(), N, K, p->F, C, KP, kslice);
   }
   // + bias, relu (:92), BN (:95-103), fc_out (:104)
-  hgru::fc_tail_kernel<<<N, 256, sizeof(float) * p->F, st>>>(
+  hgru::fc_tail_kernel<<<N, 256, sizeof(float) * (p->F + hgru::kFcTailScratch), st>>>(
       p->part.as<float>(), nsplit, p->fc1_b.as<float>(), p->bn_scale(4), p->bn_shift(4),
       p->fc2_w.as<float>(), p->fc2_b.as<float>(), p->fc1.as<float>(), out, N, p->F, p->O);
   p->launches += 2;

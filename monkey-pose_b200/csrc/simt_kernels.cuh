@@ -189,14 +189,27 @@ stem_conv1_pool_bn_kernel(const float* __restrict__ depth, const float* __restri
   const int x0 = xq * kStemPix;
   const int IH = 2 * H, IW = 2 * W;
   float v[4][2 * kStemPix + 2];     // input rows 2y-1 .. 2y+2, columns 2x0-1 .. 2x0+8
+  // the 8 inner columns start at a multiple of 8 floats: two 16-byte loads when the row pitch allows it
+  const bool vec = (IW & 3) == 0 && 2 * x0 + 2 * kStemPix <= IW && (reinterpret_cast<uintptr_t>(depth) & 15) == 0;
 #pragma unroll
   for (int rr = 0; rr < 4; ++rr) {
     const int yy = 2 * y - 1 + rr;
+    const bool rowok = yy >= 0 && yy < IH;
     const float* row = depth + (static_cast<size_t>(n) * IH + yy) * IW;
+    if (vec) {
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 lo = rowok ? __ldg(reinterpret_cast<const float4*>(row + 2 * x0)) : z4;
+      const float4 hi = rowok ? __ldg(reinterpret_cast<const float4*>(row + 2 * x0 + 4)) : z4;
+      v[rr][0] = (rowok && x0 > 0) ? __ldg(row + 2 * x0 - 1) : 0.f;
+      v[rr][1] = lo.x; v[rr][2] = lo.y; v[rr][3] = lo.z; v[rr][4] = lo.w;
+      v[rr][5] = hi.x; v[rr][6] = hi.y; v[rr][7] = hi.z; v[rr][8] = hi.w;
+      v[rr][9] = (rowok && 2 * x0 + 8 < IW) ? __ldg(row + 2 * x0 + 8) : 0.f;
+    } else {
 #pragma unroll
-    for (int q = 0; q < 2 * kStemPix + 2; ++q) {
-      const int xx = 2 * x0 - 1 + q;
-      v[rr][q] = (yy >= 0 && yy < IH && xx >= 0 && xx < IW) ? __ldg(row + xx) : 0.f;
+      for (int q = 0; q < 2 * kStemPix + 2; ++q) {
+        const int xx = 2 * x0 - 1 + q;
+        v[rr][q] = (rowok && xx >= 0 && xx < IW) ? __ldg(row + xx) : 0.f;
+      }
     }
   }
   const int nreal = C - cg * 8;     // real channels of this chunk (uniform over the block)
@@ -682,28 +695,81 @@ fc1_splitk_kernel(const float* __restrict__ A, const float* __restrict__ Wt,
 // resolution R-D5); fc_out (:104, R-D6): out[m][o] = sum_j r[j] * W2[j][o] + b2[o].
 // One block per frame.
 // ------------------------------------------------------------------------------------------------
+constexpr int kFcTailScratch = 256;      // floats of shared memory behind r[Hid]
 __global__ void __launch_bounds__(256)
 fc_tail_kernel(const float* __restrict__ part, int nsplit, const float* __restrict__ b1,
                const float* __restrict__ sc, const float* __restrict__ sh,
                const float* __restrict__ W2, const float* __restrict__ b2, float* __restrict__ fc1_out,
                float* __restrict__ out, int M, int Hid, int Nout) {
-  extern __shared__ float r[];      // [Hid]
+  extern __shared__ float r[];      // [Hid] + [kFcTailScratch]
+  float* scratch = r + Hid;
   const int m = blockIdx.x;
-  for (int j = threadIdx.x; j < Hid; j += blockDim.x) {
-    float a = 0.f;
-    for (int z = 0; z < nsplit; ++z) a += part[(static_cast<size_t>(z) * M + m) * Hid + j];
-    a += b1[j];
-    if (fc1_out) fc1_out[static_cast<size_t>(m) * Hid + j] = a;
-    r[j] = fmaxf(a, 0.f) * sc[j] + sh[j];
+  // split-K partial sums, added in slice order.  Everything here is latency-bound (a few hundred KB per frame),
+  // so the loops are shaped to keep many independent loads in flight: 4 columns per thread as one 16-byte load,
+  // six slices per round.
+  const size_t zs = static_cast<size_t>(M) * Hid;
+  if ((Hid & 3) == 0) {
+    for (int j = 4 * threadIdx.x; j < Hid; j += 4 * blockDim.x) {
+      const float* pj = part + static_cast<size_t>(m) * Hid + j;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      int z = 0;
+      for (; z + 6 <= nsplit; z += 6) {
+        float4 v[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) v[q] = __ldg(reinterpret_cast<const float4*>(pj + (z + q) * zs));
+#pragma unroll
+        for (int q = 0; q < 6; ++q) { a.x += v[q].x; a.y += v[q].y; a.z += v[q].z; a.w += v[q].w; }
+      }
+      for (; z < nsplit; ++z) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(pj + z * zs));
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      }
+      const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float t = av[q] + b1[j + q];
+        if (fc1_out) fc1_out[static_cast<size_t>(m) * Hid + j + q] = t;
+        r[j + q] = fmaxf(t, 0.f) * sc[j + q] + sh[j + q];
+      }
+    }
+  } else {
+    for (int j = threadIdx.x; j < Hid; j += blockDim.x) {
+      const float* pj = part + static_cast<size_t>(m) * Hid + j;
+      float a = 0.f;
+      for (int z = 0; z < nsplit; ++z) a += pj[z * zs];
+      a += b1[j];
+      if (fc1_out) fc1_out[static_cast<size_t>(m) * Hid + j] = a;
+      r[j] = fmaxf(a, 0.f) * sc[j] + sh[j];
+    }
   }
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int o = warp; o < Nout; o += nw) {
-    float a = 0.f;
-    for (int j = lane; j < Hid; j += 32) a = fmaf(r[j], W2[static_cast<size_t>(j) * Nout + o], a);
+  // fc_out: thread = (group g, output o); a group walks the rows j = g, g + G, ... of W2 [Hid][Nout], so a warp
+  // reads consecutive outputs of one row (the old lane-per-row mapping touched 32 cache lines per load)
+  for (int o0 = 0; o0 < Nout; o0 += kFcTailScratch) {
+    const int no = min(Nout - o0, kFcTailScratch);
+    const int G = kFcTailScratch / no;
+    const int g = threadIdx.x / no, o = threadIdx.x - g * no;
+    if (g < G) {
+      const float* wcol = W2 + o0 + o;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      int j = g;
+      for (; j + 15 * G < Hid; j += 16 * G) {      // 16 independent loads per round
+        float w[16];
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s);
-    if (lane == 0) out[static_cast<size_t>(m) * Nout + o] = a + b2[o];
+        for (int q = 0; q < 16; ++q) w[q] = __ldg(wcol + static_cast<size_t>(j + q * G) * Nout);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) acc[q & 3] = fmaf(r[j + q * G], w[q], acc[q & 3]);
+      }
+      for (; j < Hid; j += G) acc[0] = fmaf(r[j], __ldg(wcol + static_cast<size_t>(j) * Nout), acc[0]);
+      scratch[g * no + o] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    }
+    __syncthreads();
+    if (threadIdx.x < no) {
+      float a = 0.f;
+      for (int gg = 0; gg < G; ++gg) a += scratch[gg * no + threadIdx.x];
+      out[static_cast<size_t>(m) * Nout + o0 + threadIdx.x] = a + b2[o0 + threadIdx.x];
+    }
+    __syncthreads();
   }
 }
 
