@@ -232,7 +232,7 @@ def run_ours(a):
     clocks = Clocks(local) if rank == 0 else None
     if clocks:
         clocks.wait_ready()
-        step_dev()                      # the sampler start-up left the GPU idle: one more untimed step
+    step_dev()      # the sampler start-up left rank 0's GPU idle: one more untimed step (every rank: it has a collective)
     lib.hgru_enable_kernel_timing(1)
     ms_dev, t0, t1 = timed(step_dev, a.steps)
     k_ms, k_n = ctypes.c_float(0), ctypes.c_int(0)
