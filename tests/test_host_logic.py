@@ -110,3 +110,25 @@ def test_crop_windows_batch_equals_per_frame_reference_arithmetic():
         assert tuple(int(v) for v in ints[i]) == tuple(int(v) for v in a)
         assert np.array_equal(z[i], np.asarray(b, np.float32))
         np.testing.assert_allclose(Ms[i], M, rtol=0, atol=1e-12)
+
+
+def test_bench_has_no_rank_conditional_steps():
+    """Every rank must run the same sequence of steps (each multi-GPU step ends in an all-gather): a forward
+    pass under `if clocks:` / `if rank == 0:` deadlocks torchrun runs.  Static check of bench.py."""
+    import ast
+    import os
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py")).read()
+    tree = ast.parse(src)
+    bad = []
+    for node in ast.walk(tree):
+        if not isinstance(node, ast.If):
+            continue
+        names = {n.id for n in ast.walk(node.test) if isinstance(n, ast.Name)}
+        if not names & {"rank", "clocks"}:
+            continue
+        for sub in node.body + node.orelse:
+            for call in ast.walk(sub):
+                if isinstance(call, ast.Call) and isinstance(call.func, ast.Name) and \
+                        call.func.id in ("step_dev", "step_host", "timed", "gather_predictions"):
+                    bad.append((node.lineno, call.func.id))
+    assert not bad, bad
