@@ -185,6 +185,26 @@ def test_chained_launches_equal_stream_ordered_launches(monkeypatch):
     assert torch.equal(outs[True][1], outs[False][1])
 
 
+@pytest.mark.parametrize("shape", [(5, 40, 24, 25, 15, 3), (3, 33, 70, 25, 15, 2), (40, 64, 64, 32, 15, 3),
+                                   (9, 18, 66, 16, 15, 2)])
+def test_chained_layer_equals_traced_layer_on_ragged_shapes(shape):
+    """`build(trace=True)` runs the launches in plain stream order (trace copies sit between them); without the
+    trace they are chained.  Ragged H / W, two x-units per row, k = 16 / 25 / 32, more units than CTAs: the final
+    state must be bitwise the same, and within tolerance of the oracle."""
+    n, h, w, k, S, T = shape
+    rng = np.random.default_rng(5)
+    X = rng.uniform(-1, 1, size=(n, h, w, k)).astype(np.float32)
+    O0 = init.hidden_init((n, h, w, k), seed=3, limit=0.5)
+    params = init.hgru_params(k, S, T, seed=9, stress=6.0)
+    _, O_traced, _ = _run_cc(X, O0, params, T, S, "bf16", trace=True)
+    for _ in range(3):
+        _, O_chained, _ = _run_cc(X, O0, params, T, S, "bf16", trace=False)
+        assert torch.equal(O_chained, O_traced)
+    ref = otorch.hgru_forward(X[:2], O0[:2], params, T, dtype=torch.float64)
+    ref = ref[0] if isinstance(ref, tuple) else ref
+    assert onp.rel_err(O_chained[:2].cpu().numpy(), ref.numpy())[0] < TOL["bf16"]
+
+
 def test_pose_host_entry_point_equals_device_entry_point():
     m1, out_dev, *_ = _pose("bf16", 2, 16, 16, 2, 15, 64, host=False)
     m2, out_host, *_ = _pose("bf16", 2, 16, 16, 2, 15, 64, host=True)
