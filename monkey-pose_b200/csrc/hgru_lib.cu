@@ -777,6 +777,8 @@ struct pose_plan_s {
   int fc_splits = 1, fc_kbps = 1, fc_kpad = 0;
   cudaStream_t copy_st = nullptr;                  // pose_forward_host: upload of the crops overlaps the initial-state pass
   cudaEvent_t ev_begin = nullptr, ev_copied = nullptr;
+  cudaStream_t side_st = nullptr;                  // the initial-state pass runs beside the stem (independent inputs)
+  cudaEvent_t ev_fork = nullptr, ev_init = nullptr;
   float* bn_scale(int i) const { return bn.as<float>() + static_cast<size_t>(i) * 2 * bnw; }
   float* bn_shift(int i) const { return bn_scale(i) + bnw; }
   int bnw = 0;
@@ -793,6 +795,9 @@ static void pose_plan_free(pose_plan_s* p) {
   if (p->copy_st) cudaStreamDestroy(p->copy_st);
   if (p->ev_begin) cudaEventDestroy(p->ev_begin);
   if (p->ev_copied) cudaEventDestroy(p->ev_copied);
+  if (p->side_st) cudaStreamDestroy(p->side_st);
+  if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+  if (p->ev_init) cudaEventDestroy(p->ev_init);
   DevBuf* all[] = {&p->depth, &p->pool1, &p->conv2, &p->w1, &p->b1, &p->w2, &p->b2, &p->w3, &p->b3,
                    &p->fc1_w, &p->fc1_b, &p->fc2_w, &p->fc2_b, &p->bn, &p->part, &p->fc1, &p->out,
                    &p->act_pool1, &p->act_conv2, &p->wpk2, &p->wpk3, &p->fc1_wt, &p->fc1_a};
@@ -811,7 +816,16 @@ static int pose_forward_impl(pose_plan_s* p, const float* depth, const float* H2
   if (p->mode == HGRU_MODE_BF16) {
     // the hGRU's initial-state pass does not depend on the crops: run it first (under their upload, when the
     // caller copies them on another stream)
-    if ((rc = hgru_init_state_bf16(h, H2_init, st))) return rc;
+    // ... and beside the stem: both are latency-bound passes of ~0.1 ms that leave most of the chip idle
+    if (!p->side_st) {
+      CUDA_TRY(cudaStreamCreateWithFlags(&p->side_st, cudaStreamNonBlocking));
+      CUDA_TRY(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&p->ev_init, cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaEventRecord(p->ev_fork, st));            // after everything earlier in `st` (the previous forward)
+    CUDA_TRY(cudaStreamWaitEvent(p->side_st, p->ev_fork, 0));
+    if ((rc = hgru_init_state_bf16(h, H2_init, p->side_st))) return rc;
+    CUDA_TRY(cudaEventRecord(p->ev_init, p->side_st));
     h->state_ready = true;
   }
   if (depth_ready) CUDA_TRY(cudaStreamWaitEvent(st, depth_ready, 0));
@@ -848,6 +862,7 @@ static int pose_forward_impl(pose_plan_s* p, const float* depth, const float* H2
     h->fc_a = p->fc1_a.as<__nv_bfloat16>(); h->fc_scale = p->bn_scale(3); h->fc_shift = p->bn_shift(3);
     h->fc_kpad = p->fc_kpad;
   }
+  if (p->mode == HGRU_MODE_BF16) CUDA_TRY(cudaStreamWaitEvent(st, p->ev_init, 0));      // join the initial-state pass
   if ((rc = hgru_run_padded(h, h->Xp.as<float>(), H2_init, nullptr, nullptr, st))) return rc;
   p->launches += h->launches;
   // BN (:82-90) folded into the A-operand of fc_1 (:91); split-K partial sums
