@@ -777,6 +777,8 @@ struct pose_plan_s {
   int fc_splits = 1, fc_kbps = 1, fc_kpad = 0;
   cudaStream_t copy_st = nullptr;                  // pose_forward_host: upload of the crops overlaps the initial-state pass
   cudaEvent_t ev_begin = nullptr, ev_copied = nullptr;
+  static constexpr int kUploadChunks = 4;          // the crops are uploaded in frame chunks; conv_1 follows chunk by chunk
+  cudaEvent_t ev_chunk[kUploadChunks] = {nullptr, nullptr, nullptr, nullptr};
   cudaStream_t side_st = nullptr;                  // the initial-state pass runs beside the stem (independent inputs)
   cudaEvent_t ev_fork = nullptr, ev_init = nullptr;
   float* bn_scale(int i) const { return bn.as<float>() + static_cast<size_t>(i) * 2 * bnw; }
@@ -795,6 +797,7 @@ static void pose_plan_free(pose_plan_s* p) {
   if (p->copy_st) cudaStreamDestroy(p->copy_st);
   if (p->ev_begin) cudaEventDestroy(p->ev_begin);
   if (p->ev_copied) cudaEventDestroy(p->ev_copied);
+  for (auto e : p->ev_chunk) if (e) cudaEventDestroy(e);
   if (p->side_st) cudaStreamDestroy(p->side_st);
   if (p->ev_fork) cudaEventDestroy(p->ev_fork);
   if (p->ev_init) cudaEventDestroy(p->ev_init);
@@ -805,7 +808,7 @@ static void pose_plan_free(pose_plan_s* p) {
 }
 
 static int pose_forward_impl(pose_plan_s* p, const float* depth, const float* H2_init, float* out, cudaStream_t st,
-                             cudaEvent_t depth_ready = nullptr) {
+                             const cudaEvent_t* chunk_ready = nullptr, int nchunks = 1) {
   if (!p->params_set) return fail(HGRU_E_STATE, "pose_forward before pose_set_params");
   if (!depth || !out) return fail(HGRU_E_INVALID, "pose_forward: null pointer");
   hgru_plan_s* h = &p->hg;
@@ -828,14 +831,22 @@ static int pose_forward_impl(pose_plan_s* p, const float* depth, const float* H2
     CUDA_TRY(cudaEventRecord(p->ev_init, p->side_st));
     h->state_ready = true;
   }
-  if (depth_ready) CUDA_TRY(cudaStreamWaitEvent(st, depth_ready, 0));
-  // conv_1 + relu + pool_1 + BN (hgru_pose.py:50-60)
-  hgru::stem_conv1_pool_bn_kernel<<<dim3(nblk(static_cast<size_t>(N) * HW * ((HW + hgru::kStemPix - 1) / hgru::kStemPix)), KP / 8),
-                                    256, 0, st>>>(
-      depth, p->w1.as<float>(), p->b1.as<float>(), p->bn_scale(0), p->bn_shift(0),
-      tc ? nullptr : p->pool1.as<float>(), tc ? p->act_pool1.as<__nv_bfloat16>() : nullptr, N, HW, HW, C, KP,
-      tc ? 1 : 0);
-  ++p->launches;
+  // conv_1 + relu + pool_1 + BN (hgru_pose.py:50-60); frames are independent, so with a chunked upload
+  // (pose_forward_host) each chunk is processed as soon as it has landed
+  for (int c = 0; c < nchunks; ++c) {
+    const int per = (N + nchunks - 1) / nchunks;
+    const int n0 = c * per, nn = (n0 + per <= N ? per : N - n0);
+    if (nn <= 0) break;
+    if (chunk_ready) CUDA_TRY(cudaStreamWaitEvent(st, chunk_ready[c], 0));
+    const size_t pix = static_cast<size_t>(HW) * HW;
+    float* o32 = tc ? nullptr : p->pool1.as<float>() + static_cast<size_t>(n0) * pix * KP;
+    __nv_bfloat16* o16 = tc ? p->act_pool1.as<__nv_bfloat16>() + static_cast<size_t>(n0) * 2 * KP * pix : nullptr;
+    hgru::stem_conv1_pool_bn_kernel<<<dim3(nblk(static_cast<size_t>(nn) * HW * ((HW + hgru::kStemPix - 1) / hgru::kStemPix)), KP / 8),
+                                      256, 0, st>>>(
+        depth + static_cast<size_t>(n0) * 4 * pix, p->w1.as<float>(), p->b1.as<float>(), p->bn_scale(0), p->bn_shift(0),
+        o32, o16, nn, HW, HW, C, KP, tc ? 1 : 0);
+    ++p->launches;
+  }
   // conv_2 + relu + BN (:61-70), conv_3 + relu + BN (:71-80); conv3 output is X of the hGRU
   if (tc) {
     hgru::TcConvArgs a{};
@@ -1100,12 +1111,24 @@ int pose_forward_host(pose_plan_t p, const float* depth_host, const float* H2_in
     CUDA_TRY(cudaStreamCreateWithFlags(&p->copy_st, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&p->ev_begin, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&p->ev_copied, cudaEventDisableTiming));
+    for (auto& e : p->ev_chunk) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
   CUDA_TRY(cudaEventRecord(p->ev_begin, st));
   CUDA_TRY(cudaStreamWaitEvent(p->copy_st, p->ev_begin, 0));
-  CUDA_TRY(cudaMemcpyAsync(p->depth.p, depth_host, p->depth.bytes, cudaMemcpyHostToDevice, p->copy_st));
-  CUDA_TRY(cudaEventRecord(p->ev_copied, p->copy_st));
-  int rc = pose_forward_impl(p, p->depth.as<float>(), H2_init, p->out.as<float>(), st, p->ev_copied);
+  // frame chunks, one event each: conv_1 of chunk c runs while chunk c+1 is still on the bus
+  const int nchunks = p->N >= 4 * pose_plan_s::kUploadChunks ? pose_plan_s::kUploadChunks : 1;
+  {
+    const int per = (p->N + nchunks - 1) / nchunks;
+    const size_t frame = static_cast<size_t>(4) * p->HW * p->HW;      // floats per 2HW x 2HW crop
+    for (int c = 0; c < nchunks; ++c) {
+      const int n0 = c * per, nn = (n0 + per <= p->N ? per : p->N - n0);
+      if (nn > 0)
+        CUDA_TRY(cudaMemcpyAsync(p->depth.as<float>() + n0 * frame, depth_host + n0 * frame, nn * frame * sizeof(float),
+                                 cudaMemcpyHostToDevice, p->copy_st));
+      CUDA_TRY(cudaEventRecord(p->ev_chunk[c], p->copy_st));
+    }
+  }
+  int rc = pose_forward_impl(p, p->depth.as<float>(), H2_init, p->out.as<float>(), st, p->ev_chunk, nchunks);
   if (rc) return rc;
   CUDA_TRY(cudaMemcpyAsync(out_host, p->out.p, p->out.bytes, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));

@@ -205,11 +205,15 @@ def test_chained_layer_equals_traced_layer_on_ragged_shapes(shape):
     assert onp.rel_err(O_chained[:2].cpu().numpy(), ref.numpy())[0] < TOL["bf16"]
 
 
-def test_pose_host_entry_point_equals_device_entry_point():
-    m1, out_dev, *_ = _pose("bf16", 2, 16, 16, 2, 15, 64, host=False)
-    m2, out_host, *_ = _pose("bf16", 2, 16, 16, 2, 15, 64, host=True)
+@pytest.mark.parametrize("N,mode", [(2, "bf16"), (19, "bf16"), (17, "fp32")])
+def test_pose_host_entry_point_equals_device_entry_point(N, mode):
+    """Host buffers in / out (N >= 16: the crops go up in four frame chunks, ragged here, conv_1 chunk by chunk)
+    against the device-tensor entry point."""
+    m1, out_dev, *_ = _pose(mode, N, 16, 16, 2, 15, 64, host=False)
+    m2, out_host, *_ = _pose(mode, N, 16, 16, 2, 15, 64, host=True)
     assert not out_host.is_cuda
     assert torch.equal(out_dev.cpu(), out_host)
+    assert torch.equal(m1.activation("conv3"), m2.activation("conv3"))
 
 
 def test_properties_at_baseline_size_bf16():
