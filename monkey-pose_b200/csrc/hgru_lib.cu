@@ -776,7 +776,7 @@ struct pose_plan_s {
   bool fc1_tc = false;
   int fc_splits = 1, fc_kbps = 1, fc_kpad = 0;
   cudaStream_t copy_st = nullptr;                  // pose_forward_host: upload of the crops overlaps the initial-state pass
-  cudaEvent_t ev_begin = nullptr, ev_copied = nullptr;
+  cudaEvent_t ev_begin = nullptr;
   static constexpr int kUploadChunks = 4;          // the crops are uploaded in frame chunks; conv_1 follows chunk by chunk
   cudaEvent_t ev_chunk[kUploadChunks] = {nullptr, nullptr, nullptr, nullptr};
   cudaStream_t side_st = nullptr;                  // the initial-state pass runs beside the stem (independent inputs)
@@ -796,7 +796,6 @@ static void pose_plan_free(pose_plan_s* p) {
   hgru_plan_free(&p->hg);
   if (p->copy_st) cudaStreamDestroy(p->copy_st);
   if (p->ev_begin) cudaEventDestroy(p->ev_begin);
-  if (p->ev_copied) cudaEventDestroy(p->ev_copied);
   for (auto e : p->ev_chunk) if (e) cudaEventDestroy(e);
   if (p->side_st) cudaStreamDestroy(p->side_st);
   if (p->ev_fork) cudaEventDestroy(p->ev_fork);
@@ -1110,7 +1109,6 @@ int pose_forward_host(pose_plan_t p, const float* depth_host, const float* H2_in
   if (!p->copy_st) {
     CUDA_TRY(cudaStreamCreateWithFlags(&p->copy_st, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&p->ev_begin, cudaEventDisableTiming));
-    CUDA_TRY(cudaEventCreateWithFlags(&p->ev_copied, cudaEventDisableTiming));
     for (auto& e : p->ev_chunk) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
   CUDA_TRY(cudaEventRecord(p->ev_begin, st));
