@@ -55,7 +55,14 @@ struct StackCfg {
   static constexpr int MIN_COL = T - 16;                  // image column of window column 0, minus x0
   // Epilogue warpgroups split each tile's channels in 8-channel chunks (the last group takes the rest): the
   // epilogue is latency-bound per thread, so more, lighter warps per SM sub-partition is what speeds it up.
+#ifdef HGRU_STACK_NGRP4
+  // development switch: at k = 25 give the 25th channel (the row-packed remainder plane with its 8 scattered operand
+  // stores) a warpgroup of its own.  It balances the groups (no more waiting at the gate barrier) but the fifth warp
+  // per SM sub-partition slows the MMA issuer: +8 % cycles, same time (profiles/r01_stack_kernel_v27_ngrp4_ab.log).
+  static constexpr int NGRP = (KC == 25) ? 4 : ((KC > 16) ? 3 : 2);
+#else
   static constexpr int NGRP = (KC > 16) ? 3 : 2;
+#endif
   static constexpr int NEPI = 128 * NGRP;                 // epilogue threads
   static constexpr int NTHREADS = 128 + NEPI;             // 4 service warps + NGRP x 4 epilogue warps
   static constexpr int NLOC = NPAD / CS;                  // B rows held by one CTA
@@ -212,8 +219,10 @@ __device__ __forceinline__ void tmem_ld_issue<1>(uint32_t taddr, uint32_t* u) {
 }
 template <int CN>
 __device__ __forceinline__ void tmem_ld_range_issue(uint32_t taddr, uint32_t (&u)[CN]) {
-  static_assert(CN == 8 || CN == 9 || CN == 16, "supported channel-range widths");
-  if constexpr (CN == 16) {
+  static_assert(CN == 1 || CN == 8 || CN == 9 || CN == 16, "supported channel-range widths");
+  if constexpr (CN == 1) {
+    tmem_ld_issue<1>(taddr, u);
+  } else if constexpr (CN == 16) {
     tmem_ld_issue<16>(taddr, u);
   } else if constexpr (CN == 8) {
     tmem_ld_issue<8>(taddr, u);
@@ -731,7 +740,12 @@ hconv_stack_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
 #define HGRU_STACK_EPI(C0_, CN_, FIRST_)                                                                          \
   stack_epilogue<Cfg, Epi, C0_, CN_, PROF>(ae, tmem_base, bar_acc_full, bar_acc_empty, crank, iters, NT,           \
                                            units_per_frame, warp, lane, FIRST_, smem_raw, gate_a, gate_w, bar_gate)
-    if constexpr (Cfg::NGRP == 3) {
+    if constexpr (Cfg::NGRP == 4) {
+      if (warp < 8) HGRU_STACK_EPI(0, 8, true);
+      else if (warp < 12) HGRU_STACK_EPI(8, 8, false);
+      else if (warp < 16) HGRU_STACK_EPI(16, 8, false);
+      else HGRU_STACK_EPI(24, KC - 24, false);
+    } else if constexpr (Cfg::NGRP == 3) {
       if (warp < 8) HGRU_STACK_EPI(0, 8, true);
       else if (warp < 12) HGRU_STACK_EPI(8, 8, false);
       else HGRU_STACK_EPI(16, KC - 16, false);
