@@ -234,11 +234,13 @@ int main(int argc, char** argv) {
   if (which == 0 || which == 7) f += run_case<32, 5, 25, 1>(256, 64, 64, 25, 0, 5);
   if (which == 0 || which == 8) f += run_case<32, 5, 25, 2>(256, 64, 64, 25, 0, 5);
   if (which == 0 || which == 9) f += run_case<32, 4, 32, 2>(256, 64, 64, 32, 0, 5);
-  if (which == 21) {
+  if (which == 21) {   // weight ring refills on / off (dbg bit 0), random operand data: what the L2 -> SM weight stream costs
+    g_random_data = 1;
     time_real_epilogue<32, 5, 25, 1, hgru::EpiBias>("EpiBias", 256, 64, 64, 25, 0, 0);
     time_real_epilogue<32, 5, 25, 1, hgru::EpiBias>("EpiBias noWstream", 256, 64, 64, 25, 0, 1);
     time_real_epilogue<32, 5, 25, 1, hgru::EpiH2>("EpiH2", 256, 64, 64, 25, 1, 0);
     time_real_epilogue<32, 5, 25, 1, hgru::EpiH2>("EpiH2 noWstream", 256, 64, 64, 25, 1, 1);
+    g_random_data = 0;
   }
   if (which == 23) {   // epilogue-written operand tensors: guard bands, zero padding, remainder-plane consistency
     g_random_data = 1; g_check_layout = 1;
