@@ -258,8 +258,10 @@ int main(int argc, char** argv) {
       time_real_epilogue<32, 5, 25, 1, hgru::EpiH2>("EpiH2", 256, 64, 64, 25, 1);
     }
   }
-  if (which == 20) {
+  if (which == 20) {   // single CTA (remainder-packed, 24 stages) vs cta_group::2 pair mode (plain schedule, 30 stages), random data
+    g_random_data = 1;
     time_real_epilogue<32, 5, 25, 1, hgru::EpiBias>("EpiBias", 256, 64, 64, 25, 0);
+    time_real_epilogue<32, 5, 25, 2, hgru::EpiBias>("EpiBias", 256, 64, 64, 25, 0);
     time_real_epilogue<32, 5, 25, 1, hgru::EpiH1>("EpiH1", 256, 64, 64, 25, 0);
     time_real_epilogue<32, 5, 25, 1, hgru::EpiH1>("EpiH1", 256, 64, 64, 25, 1);
     time_real_epilogue<32, 5, 25, 1, hgru::EpiH2>("EpiH2", 256, 64, 64, 25, 0);
