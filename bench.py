@@ -411,8 +411,8 @@ def neighbour_stages(a, m, torch, mp, init_mod):
                               "algorithmic_TFLOP/s": attn_flops / (attn_gpu_ms * 1e-3) * 1e-12,
                               "launches": am.gpu_launches,
                               "note": "attn_model_struct.build at 64..1024 channels: resize + 5 x (conv, relu, "
-                                      "pool, batch-norm) + 2 fc; convs as tcgen05 GEMMs over im2col with bf16 "
-                                      "hi/lo splits (3 MMAs per k-step)"},
+                                      "pool, batch-norm) + 2 fc; convs 2-5 as implicit tcgen05 GEMMs (4-D TMA boxes of the NHWC "
+                                      "activation per tap) with bf16 hi/lo splits (3 MMAs per k-step)"},
             "frames_to_joints_e2e": {"value": B / (chain_wall_ms * 1e-3), "unit": UNIT, "wall_ms": chain_wall_ms,
                                      "stages": "H2D frames, attention CNN, crop, hGRU pose net, post-processing, "
                                                "D2H joints",

@@ -17,13 +17,20 @@
 // (30 x ~82 pixels x KP channels) resident in shared memory.  TMEM holds four 128-column
 // accumulators: tiles are processed in pairs, two accumulating while two drain, so the epilogue
 // (shuffles + fused gate/integration math + global I/O) hides behind the MMAs.  The stacked
-// weights (360 KB at k = 25) stream through a 4-stage ring once per tile pair.
+// weights (288 KB at k = 25 with the remainder-packed schedule) stream through a ring (5 stages at k = 25) once per
+// tile pair.  Tap group 0 of a row's first carry tile only reads zero-filled window columns and is not issued.
+//
+// Launch chaining: the launches of one forward depend on each other only frame by frame (a unit needs the four
+// units of its frame from the previous launch), so instead of grid-wide stream order each unit's epilogue counts
+// itself done in a per-launch, per-frame counter (TcConvArgs::done_flags) and the next launch -- started early by
+// programmatic dependent launch, its CTAs taking SMs as this launch's CTAs exit -- waits per frame
+// (wait_flags) in its window producer and epilogue warps.
 //
 // CS = 2 ("pair mode", cta_group::2): two CTAs on one TPC run in lockstep on two units; the leader
 // issues M = 256 MMAs whose A rows come half from each CTA's own window and whose B rows come half
 // from each CTA's weight ring, so every CTA stores, streams and reads only half of the weights.
-// That matters because this kernel is bound by the 128 B/clk shared-memory/L1 datapath (UMMA
-// operand reads + TMA writes + epilogue traffic), not by the tensor pipe.  All pair synchronisation
+// (Measured: worth 0-3 % on equal schedules and not combined with the remainder-packed schedule, so CS = 1 is
+// what runs)  All pair synchronisation
 // converges on the leader's barriers: both CTAs' TMA loads complete their bytes there
 // (cp.async.bulk.tensor ... cta_group::2), the peer's epilogue threads arrive there remotely, and
 // the leader's commits are multicast back to both CTAs.

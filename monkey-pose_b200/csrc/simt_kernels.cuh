@@ -458,7 +458,8 @@ split_chunks_to_nhwc_kernel(const __nv_bfloat16* __restrict__ in, float* __restr
 // Initial state of the tensor-core path in one pass: O_0 (NHWC, k channels; hgru_module.py:884-887)
 //   -> H2 fp32 quad-chunked (zero padded), and the first timestep's gated operand
 //   A = bf16(sigmoid(O_0 *1x1 i_r + i_b) . O_0)  (hgru_module.py:696-711) in the chunked layout.
-// Block = 64 pixels; i_r in shared memory; thread = one pixel x 8 output channels (like gate1x1_kernel).
+// Exact-fp32 SIMT version (block = 256 pixels, i_r in shared memory, thread = 4 pixels x 8 output channels); the
+// production path runs init_state_tc_kernel (gate_tc.cuh) instead -- this one stays behind HGRU_SIMT_INIT=1.
 // ------------------------------------------------------------------------------------------------
 constexpr int kInitPix = 256;     // pixels per block of init_state_gate_kernel (4 per thread)
 __global__ void __launch_bounds__(256)
