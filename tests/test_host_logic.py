@@ -132,3 +132,20 @@ def test_bench_has_no_rank_conditional_steps():
                         call.func.id in ("step_dev", "step_host", "timed", "gather_predictions"):
                     bad.append((node.lineno, call.func.id))
     assert not bad, bad
+
+
+def test_product_build_defines_no_development_switch():
+    """The kernels carry compile-time development switches (HGRU_DBG_*, HGRU_STACK_*) for the devtools' A/B builds;
+    the library's Makefile must not define any of them, and every switch that exists is off by default (#ifdef)."""
+    import os
+    import re
+    csrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "monkey-pose_b200", "csrc")
+    mk = open(os.path.join(csrc, "Makefile")).read()
+    assert "-DHGRU_" not in mk
+    switches = set()
+    for fn in os.listdir(csrc):
+        if fn.endswith((".cuh", ".cu", ".inl")):
+            src = open(os.path.join(csrc, fn)).read()
+            switches |= set(re.findall(r"#\s*ifn?def\s+(HGRU_(?:DBG|STACK)_\w+)", src))
+            assert not re.search(r"#\s*define\s+HGRU_(?:DBG|STACK)_\w+", src), fn
+    assert {"HGRU_STACK_NO_REM", "HGRU_STACK_NGRP4", "HGRU_DBG_NO_GLOBAL"} <= switches
