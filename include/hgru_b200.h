@@ -92,7 +92,7 @@ typedef struct pose_params_s {
   /* batch_normalization, _1, _2, _3 (C channels each), _4 (F): gamma, beta, moving_mean,
    * moving_variance  (hgru_pose.py:52-60, 62-70, 72-80, 82-90, 95-103) */
   const float* bn[5][4];
-  /* contextual_circuit/* (hgru_module.py:262-503), same order as hgru_set_params */
+  /* scope contextual_circuit (hgru_module.py:262-503), same order as hgru_set_params */
   const float *p_r, *i_r, *i_b, *o_r, *o_b, *beta, *nu, *gamma, *kappa, *omega, *rho, *lateral_bias;
 } pose_params_t;
 

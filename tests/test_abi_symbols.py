@@ -53,3 +53,26 @@ def test_pose_params_struct_matches_header_layout():
     from monkey_pose_b200 import _lib
     # 10 stem/fc pointers + 5x4 batch-norm pointers + 12 hGRU pointers
     assert ctypes.sizeof(_lib.PoseParams) == (10 + 20 + 12) * ctypes.sizeof(ctypes.c_void_p)
+
+
+def test_header_is_plain_c():
+    """The drop-in boundary is a C ABI: include/hgru_b200.h must compile as C99 without warnings and a C program
+    must link against the library (no C++ or torch types in the signatures)."""
+    import os
+    import subprocess
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(root, "monkey-pose_b200", "libhgru_b200.so")
+    if not os.path.exists(lib):
+        import pytest
+        pytest.skip("library not built")
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "abi.c")
+        open(src, "w").write('#include "hgru_b200.h"\n#include <stdio.h>\n'
+                             'int main(void) { printf("%d\\n", hgru_version()); return 0; }\n')
+        exe = os.path.join(d, "abi")
+        r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"),
+                            src, "-o", exe, lib, "-Wl,-rpath," + os.path.dirname(lib)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        out = subprocess.run([exe], capture_output=True, text=True)
+        assert out.returncode == 0 and int(out.stdout.strip()) >= 100, (out.stdout, out.stderr)
