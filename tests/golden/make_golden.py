@@ -57,8 +57,9 @@ def pose_aux(hgru_pose_mod):
     return dict(hgru_pose_mod.model().aux)
 
 
-def gen_hgru(hm, aux, tag, n, h, w, k, S, T, seed):
+def gen_hgru(hm, aux, tag, n, h, w, k, S, T, seed, gains=None, f32_steps=False):
     reg = tf_shim.reset(seed)
+    reg.init_gain = dict(gains or {})
     X = tf_shim.Tensor(reg.rng.uniform(-1.0, 1.0, size=(n, h, w, k)).astype(np.float32))
     cc = hm.ContextualCircuit(X=X, timesteps=T, SRF=1, SSN=S, SSF=S, strides=[1, 1, 1, 1],
                               padding="SAME", aux=dict(aux))
@@ -84,11 +85,15 @@ def gen_hgru(hm, aux, tag, n, h, w, k, S, T, seed):
     out = {"X": np.asarray(X).astype(np.float32), "I0": act_draws[0], "O0": act_draws[1],
            "O_final": np.asarray(O_final), "O_steps": np.stack(steps_O, 1),
            "I_steps": np.stack(steps_I, 1),
+           "init_gain": np.array(sorted("%s:%g" % (shp, g) for shp, g in reg.init_gain.items())),
            "T": np.int64(T), "S": np.int64(S), "weights_keys": np.array(sorted(weights.keys()))}
     for name, val in reg.variables.items():
         out["var:" + name] = val
     assert np.array_equal(out["O_steps"][:, -1], out["O_final"])
     assert reg.conv_calls == 4 * T, reg.conv_calls
+    if f32_steps:      # BASELINE-width sets: float32 storage (6e-8 relative, far below the 1e-4 gate) keeps them small
+        for key in ("O_final", "O_steps", "I_steps"):
+            out[key] = out[key].astype(np.float32)
     path = os.path.join(HERE, "hgru_ref_%s.npz" % tag)
     np.savez_compressed(path, **out)
     print("wrote", path, "O_final absmax", np.abs(out["O_final"]).max())
@@ -130,6 +135,14 @@ def main():
     gen_hgru(hm, aux, "S15_k8", n=2, h=16, w=16, k=8, S=15, T=3, seed=11)
     gen_hgru(hm, aux, "S5_k8", n=2, h=16, w=16, k=8, S=5, T=3, seed=12)
     gen_hgru(hm, aux, "S7_k5", n=1, h=12, w=10, k=5, S=7, T=4, seed=13)
+    # BASELINE widths: 25 channels / T = 8 (the remainder-packed tap-stacked kernel), random-init and a
+    # "stress" set (15x15 kernel x5, initial state x10 so tanh leaves its linear region), and the deep variant
+    # 32 channels / T = 16
+    gen_hgru(hm, aux, "S15_k25_T8", n=1, h=32, w=32, k=25, S=15, T=8, seed=14, f32_steps=True)
+    gen_hgru(hm, aux, "S15_k25_T8_stress", n=1, h=32, w=32, k=25, S=15, T=8, seed=15, f32_steps=True,
+             gains={(15, 15, 25, 25): 5.0, (1, 32, 32, 25): 10.0})
+    gen_hgru(hm, aux, "S15_k32_T16_stress", n=1, h=20, w=24, k=32, S=15, T=16, seed=16, f32_steps=True,
+             gains={(15, 15, 32, 32): 4.0, (1, 20, 24, 32): 10.0})
     gen_pose_layers(pm, seed=21)
 
 

@@ -59,6 +59,9 @@ class _Registry(object):
         self.conv_calls = 0
         self.bn_calls = 0        # tf.layers.batch_normalization scopes: batch_normalization, batch_normalization_1, ...
         self.bn_preset = {}      # scope -> (gamma, beta, moving_mean, moving_variance) injected by the generator
+        self.init_gain = {}      # shape -> factor applied to ops.initialization draws of that shape ("stress" sets:
+        #                          a wider initial distribution for the 15x15 kernel / the initial state; the
+        #                          arithmetic that follows is still the reference's own statements)
 
 
 REG = _Registry(0)
@@ -318,7 +321,11 @@ py_utils = types.SimpleNamespace(ifloor=lambda x: int(np.floor(x)), iceil=lambda
 
 def _xavier_initializer(shape, uniform=True, mask=None):
     """ops.initialization.xavier_initializer: returns a *tensor* (call sites hgru_module.py:278...)."""
-    return _t(_xavier(uniform)(shape))
+    a = _xavier(uniform)(shape)
+    g = REG.init_gain.get(tuple(int(s) for s in shape))
+    if g is not None:
+        a *= np.float32(g)          # in place: REG.drawn holds this same array
+    return _t(a)
 
 
 initialization = types.SimpleNamespace(xavier_initializer=_xavier_initializer)

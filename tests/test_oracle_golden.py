@@ -17,8 +17,14 @@ def _params(z, scope="contextual_circuit/"):
     return {n: z["var:" + scope + n] for n in onp.HGRU_PARAM_NAMES}
 
 
+def _atol(z):
+    """The small sets store the reference's float64 outputs; the BASELINE-width sets (25 / 32 channels, T = 8 / 16)
+    store them rounded to float32 (half an ulp of values below 4: 2.4e-7)."""
+    return 1e-12 if z["O_steps"].dtype == np.float64 else 2.5e-7
+
+
 def test_golden_files_present():
-    assert len(HGRU_FILES) >= 3
+    assert len(HGRU_FILES) >= 6
     assert os.path.exists(os.path.join(GOLDEN, "pose_layers_ref.npz"))
 
 
@@ -28,9 +34,9 @@ def test_numpy_oracle_matches_reference_every_timestep(path):
     T = int(z["T"])
     out, H1s, H2s = onp.hgru_forward(z["X"], z["O0"], _params(z), T, trace=True)
     for t in range(T):
-        np.testing.assert_allclose(H1s[t], z["I_steps"][:, t], rtol=0, atol=1e-12)
-        np.testing.assert_allclose(H2s[t], z["O_steps"][:, t], rtol=0, atol=1e-12)
-    np.testing.assert_allclose(out, z["O_final"], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(H1s[t], z["I_steps"][:, t], rtol=0, atol=_atol(z))
+        np.testing.assert_allclose(H2s[t], z["O_steps"][:, t], rtol=0, atol=_atol(z))
+    np.testing.assert_allclose(out, z["O_final"], rtol=0, atol=_atol(z))
 
 
 @pytest.mark.parametrize("path", HGRU_FILES, ids=[os.path.basename(p) for p in HGRU_FILES])
@@ -38,7 +44,7 @@ def test_initial_I_is_dead_on_configured_path(path):
     """gru_gates=True: the reference's I_0 draw never reaches the output."""
     z = np.load(path)
     a = onp.hgru_forward(z["X"], z["O0"], _params(z), int(z["T"]))
-    np.testing.assert_allclose(a, z["O_final"], rtol=0, atol=1e-12)   # oracle takes no I_0 at all
+    np.testing.assert_allclose(a, z["O_final"], rtol=0, atol=_atol(z))   # oracle takes no I_0 at all
 
 
 @pytest.mark.parametrize("path", HGRU_FILES, ids=[os.path.basename(p) for p in HGRU_FILES])
