@@ -443,8 +443,9 @@ __device__ __forceinline__ void stack_epilogue(const TcConvArgs& a, uint32_t tme
     const int u = it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);
     const bool valid = u < a.num_units;
     if (CS == 1 && !valid) break;      // idle tail: every role of a single CTA stops at the same iteration
-    const int n = u / units_per_frame;
-    const int r = u - n * units_per_frame;
+    const int nl = u / units_per_frame;
+    const int r = u - nl * units_per_frame;
+    const int n = a.n0 + nl;
     const int uy = r / a.units_x, ux = r - uy * a.units_x;
     const int y = uy * kTileRows + prow;
     if (a.wait_flags && valid) {
@@ -704,8 +705,9 @@ hconv_stack_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
       for (int it = 0; it < iters; ++it) {
         const int u = it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);
         if (u >= a.num_units) continue;
-        const int n = u / units_per_frame;
-        const int r = u - n * units_per_frame;
+        const int nl = u / units_per_frame;
+        const int r = u - nl * units_per_frame;
+        const int n = a.n0 + nl;
         const int uy = r / a.units_x, ux = r - uy * a.units_x;
         if (a.wait_flags) {
           while (ld_acquire_gpu(a.wait_flags + n) < a.flag_target) {}

@@ -37,7 +37,11 @@ constexpr int kTileRows = 16;   // M tile = 16 rows x 8 cols of pixels
 // every 16-channel k-step is accumulated as three products  a_hi*w_hi + a_hi*w_lo + a_lo*w_hi
 // (fp32-class accuracy from bf16 tensor cores; used for the stem, whose smooth inputs make plain bf16
 // rounding errors add up coherently).
-template <int S, int KSTEPS, int CO_PAD, int TILES_X, int G, int WSTAGES, bool SPLIT3 = false>
+// FUSE: the 1x1 gate conv that follows the integration (G2 after H1, the next step's G1 after H2) is issued from
+// the epilogue as tcgen05.mma on a shared-memory staging tile of the new state (as in hconv_stack.cuh), and the
+// launches of a forward are chained through per-frame completion counters (TcConvArgs::wait_flags / done_flags):
+// two launches per timestep instead of four, no grid-wide stream order between them.
+template <int S, int KSTEPS, int CO_PAD, int TILES_X, int G, int WSTAGES, bool SPLIT3 = false, bool FUSE = false>
 struct TcConvCfg {
   static constexpr int kParts = SPLIT3 ? 2 * KSTEPS : KSTEPS;      // window parts (TMA boxes / barriers)
   static constexpr int kWSteps = SPLIT3 ? 3 * KSTEPS : KSTEPS;     // weight k-steps
@@ -54,8 +58,14 @@ struct TcConvCfg {
   static constexpr int kStageBytes = G * kTapBytes;
   static constexpr int kStagesPerKstep = kTaps / G;
   static constexpr int kAccCols = TILES_X * CO_PAD;         // TMEM columns per accumulator set
-  static constexpr int kNumBars = 2 * kParts + 2 * WSTAGES + 4;
-  static constexpr int kSmemBytes = kInBytes + WSTAGES * kStageBytes + kNumBars * 8 + 16 + 1024;
+  static constexpr int kGateABytes = FUSE ? (CO_PAD / 8) * 128 * 16 : 0;   // staging tile of the new state (bf16, K-major)
+  static constexpr int kGateWBytes = FUSE ? KSTEPS * 2 * CO_PAD * 16 : 0;   // packed 1x1 gate weights
+  static constexpr int kGateBytes = kGateABytes + kGateWBytes;
+  static constexpr int kNumBars = 2 * kParts + 2 * WSTAGES + 4 + (FUSE ? 1 : 0);
+  // (no-swizzle operands and TMA boxes need 128-byte alignment; the fused configuration has no kilobyte to spare)
+  static constexpr int kAlign = FUSE ? 128 : 1024;
+  static constexpr int kSmemBytes = kInBytes + WSTAGES * kStageBytes + kGateBytes + kNumBars * 8 + 16 + kAlign;
+  static_assert(kSmemBytes <= 232448, "shared memory per CTA");
   static_assert(kTaps % G == 0, "taps per stage must divide S*S");
   static_assert(2 * kAccCols <= 512, "two accumulator sets must fit TMEM");
   static_assert(CO_PAD % 16 == 0 && CO_PAD >= 16 && CO_PAD <= 256, "UMMA N constraint (M=128)");
@@ -110,6 +120,11 @@ struct TcConvArgs {
   const int* wait_flags;
   int* done_flags;
   int flag_target;
+  // Frame groups: a launch covers frames [n0, n0 + N) of the tensors (N = frames of this launch; tensor strides do
+  // not depend on it).  `pdl` asks for a programmatic dependent launch although there is nothing to wait for (the
+  // first launch of a frame group follows the last launch of the previous, independent, group).
+  int n0;
+  int pdl;
 };
 
 // fp32 state tensors of the tensor-core path are "quad-chunked": [n][c/4][y][x][4].  A thread owns
@@ -527,25 +542,30 @@ struct EpiGateIn {
   }
 };
 
-template <int S, int KSTEPS, int CO_PAD, int TILES_X, int G, int WSTAGES, class Epi, bool SPLIT3 = false>
+template <int S, int KSTEPS, int CO_PAD, int TILES_X, int G, int WSTAGES, class Epi, bool SPLIT3 = false,
+          bool FUSE = false>
 __global__ void __launch_bounds__(256, 1)
 hconv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const TcConvArgs a) {
   using namespace sm100;
-  using Cfg = TcConvCfg<S, KSTEPS, CO_PAD, TILES_X, G, WSTAGES, SPLIT3>;
+  using Cfg = TcConvCfg<S, KSTEPS, CO_PAD, TILES_X, G, WSTAGES, SPLIT3, FUSE>;
   constexpr int NP = Cfg::kParts, NW = Cfg::kWSteps;
+  static_assert(!FUSE || !SPLIT3, "the fused-gate epilogue serves the plain bf16 path");
   extern __shared__ uint8_t smem_raw[];
-  // 1024-byte aligned carve-up
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  // aligned carve-up
+  const uint32_t base = (smem_u32(smem_raw) + static_cast<uint32_t>(Cfg::kAlign - 1)) & ~static_cast<uint32_t>(Cfg::kAlign - 1);
   const uint32_t in_buf = base;
   const uint32_t w_buf = in_buf + Cfg::kInBytes;
-  const uint32_t bars = w_buf + WSTAGES * Cfg::kStageBytes;
+  const uint32_t gate_a = w_buf + WSTAGES * Cfg::kStageBytes;      // [CO_PAD/8][128 px][16 B]   (FUSE)
+  const uint32_t gate_w = gate_a + Cfg::kGateABytes;               // packed 1x1 weights          (FUSE)
+  const uint32_t bars = gate_w + Cfg::kGateWBytes;
   const uint32_t bar_in_full = bars;                               // [NP]
   const uint32_t bar_in_empty = bar_in_full + 8 * NP;              // [NP]
   const uint32_t bar_w_full = bar_in_empty + 8 * NP;               // [WSTAGES]
   const uint32_t bar_w_empty = bar_w_full + 8 * WSTAGES;           // [WSTAGES]
   const uint32_t bar_acc_full = bar_w_empty + 8 * WSTAGES;         // [2]
   const uint32_t bar_acc_empty = bar_acc_full + 16;                // [2]
-  const uint32_t tmem_slot = bar_acc_empty + 16;
+  const uint32_t bar_gate = bar_acc_empty + 16;                    // (FUSE)
+  const uint32_t tmem_slot = bar_gate + (FUSE ? 8 : 0);
   uint32_t* tmem_slot_ptr =
       reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -565,14 +585,26 @@ hconv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const TcConvArgs a) 
       mbar_init(bar_acc_full + 8 * i, 1);
       mbar_init(bar_acc_empty + 8 * i, 128);
     }
+    if constexpr (FUSE) mbar_init(bar_gate, 1);
     fence_barrier_init();
     tma_prefetch_desc(&in_map);
   }
   if (warp == 2) tmem_alloc<512>(tmem_slot);
+  if constexpr (FUSE) {
+    if (a.do_gate && warp >= 4) {
+      // 1x1 gate weights -> shared memory (generic-proxy writes, made visible to the tensor core)
+      const uint4* src = reinterpret_cast<const uint4*>(a.gate_wpk);
+      uint8_t* dst = smem_raw + (gate_w - smem_u32(smem_raw));
+      for (int i = threadIdx.x - 128; i < Cfg::kGateWBytes / 16; i += 128)
+        reinterpret_cast<uint4*>(dst)[i] = __ldg(src + i);
+      fence_proxy_async();
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);
+  if constexpr (FUSE) grid_launch_dependents();   // a chained next launch may take SMs as they free up
 
   const int units_per_frame = a.units_x * a.units_y;
   const int first = blockIdx.x;
@@ -601,11 +633,19 @@ hconv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const TcConvArgs a) 
     if (lane == 0) {
       int it = 0;
       for (int u = first; u < a.num_units; u += stride, ++it) {
-        const int n = u / units_per_frame;
-        const int r = u - n * units_per_frame;
+        const int nl = u / units_per_frame;
+        const int r = u - nl * units_per_frame;
+        const int n = a.n0 + nl;
         const int uy = r / a.units_x, ux = r - uy * a.units_x;
         const int y0 = uy * kTileRows - Cfg::kPad;
         const int x0 = ux * (8 * TILES_X) - Cfg::kPad;
+        if constexpr (FUSE) {
+          if (a.wait_flags) {
+            // chained launch: this frame's operand is complete once all its units finished in the previous launch
+            while (ld_acquire_gpu(a.wait_flags + n) < a.flag_target) {}
+            fence_proxy_async_global();
+          }
+        }
         for (int q = 0; q < NP; ++q) {
           mbar_wait(bar_in_empty + 8 * q, (it & 1) ^ 1);
           mbar_arrive_expect_tx(bar_in_full + 8 * q, Cfg::kPartBytes);
@@ -672,12 +712,23 @@ hconv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const TcConvArgs a) 
     const int m = ew * 32 + lane;                 // accumulator row = pixel within the M tile
     const int prow = m >> 3, pcol = m & 7;
     int it = 0;
+    uint32_t gate_uses = 0;
+    (void)gate_uses;
     for (int u = first; u < a.num_units; u += stride, ++it) {
       const uint32_t s = it & 1;
-      const int n = u / units_per_frame;
-      const int r = u - n * units_per_frame;
+      const int nl = u / units_per_frame;
+      const int r = u - nl * units_per_frame;
+      const int n = a.n0 + nl;
       const int uy = r / a.units_x, ux = r - uy * a.units_x;
       const int y = uy * kTileRows + prow;
+      if constexpr (FUSE) {
+        if (a.wait_flags) {
+          // chained launch: the state tensors of this frame are final once its units of the previous launch are done
+          if (lane == 0)
+            while (ld_acquire_gpu(a.wait_flags + n) < a.flag_target) {}
+          __syncwarp();
+        }
+      }
       mbar_wait(bar_acc_full + 8 * s, (it >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
@@ -686,6 +737,67 @@ hconv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const TcConvArgs a) 
         const bool ok = (y < a.H) && (x < a.W);
         const uint32_t taddr =
             tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + s * Cfg::kAccCols + t * CO_PAD;
+        if constexpr (FUSE) {
+          // integration in 16-channel pieces (accumulator columns, global inputs and parameters of one piece live
+          // at a time); the new state stays in registers for the gate that follows
+          const size_t pin = static_cast<size_t>(y) * a.W + x;
+          float hv[CO_PAD];
+#pragma unroll
+          for (int c0 = 0; c0 < CO_PAD; c0 += 16) {
+            typename Epi::template Pre<16> pre;
+            if (ok) Epi::template load<16>(a, n, pin, c0, pre);
+            uint32_t v[16];
+            tmem_ld16(taddr + c0, v);
+            tmem_ld_wait();
+            float acc[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { acc[j] = __uint_as_float(v[j]); hv[c0 + j] = 0.f; }
+            if (ok) Epi::template finish<16>(a, n, pin, c0, acc, pre, hv + c0);
+          }
+          if (a.do_gate) {
+            // ---- fused gate: new state -> bf16 staging tile -> 1x1 conv on the tensor core -> sigmoid ----
+            uint8_t* stg = smem_raw + (gate_a - smem_u32(smem_raw));
+#pragma unroll
+            for (int i = 0; i < CO_PAD / 8; ++i) {
+              __nv_bfloat162 h[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(hv[8 * i + 2 * q], hv[8 * i + 2 * q + 1]);
+              *reinterpret_cast<uint4*>(stg + i * 2048 + m * 16) = *reinterpret_cast<const uint4*>(h);
+            }
+            fence_proxy_async();          // staging writes -> visible to the async (tensor core) proxy
+            tc_fence_before();            // our tcgen05.ld of this tile's columns precede the barrier
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (warp == 4) {
+              // the tile's own accumulator columns are drained: the gate pre-activations land there
+              const bool leader = elect_one();
+              tc_fence_after();
+              if (leader) {
+                constexpr uint32_t gdesc = make_idesc(1, 128, CO_PAD);
+                const uint64_t ad = make_smem_desc(gate_a, 2048, 128);
+                const uint64_t bd = make_smem_desc(gate_w, CO_PAD * 16, 128);
+#pragma unroll
+                for (int q = 0; q < KSTEPS; ++q)
+                  mma_bf16_ss(tmem_base + s * Cfg::kAccCols + t * CO_PAD, ad + static_cast<uint64_t>((q * 2 * 2048) >> 4),
+                              bd + static_cast<uint64_t>((q * 2 * CO_PAD * 16) >> 4), gdesc, q != 0);
+                tc_commit(bar_gate);
+              }
+              __syncwarp();
+            }
+            mbar_wait(bar_gate, gate_uses & 1);
+            ++gate_uses;
+            tc_fence_after();
+#pragma unroll
+            for (int c0 = 0; c0 < CO_PAD; c0 += 16) {
+              uint32_t v[16];
+              tmem_ld16(taddr + c0, v);
+              tmem_ld_wait();
+              float gacc[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) gacc[j] = __uint_as_float(v[j]);
+              if (ok) Epi::template gate<16>(a, n, pin, c0, gacc, hv + c0);
+            }
+          }
+        } else {
         float acc[CO_PAD];
 #pragma unroll
         for (int c0 = 0; c0 < CO_PAD; c0 += 16) {
@@ -696,9 +808,20 @@ hconv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const TcConvArgs a) 
           for (int j = 0; j < 16; ++j) acc[c0 + j] = __uint_as_float(v[j]);
         }
         if (ok) Epi::template apply<CO_PAD>(a, n, y, x, acc);
+        }
       }
       tc_fence_before();
       mbar_arrive(bar_acc_empty + 8 * s);
+      if constexpr (FUSE) {
+        if (a.done_flags) {
+          // all epilogue stores of this unit are issued: publish them, then count the unit as done
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+          if (threadIdx.x == 128) {
+            __threadfence();
+            atomicAdd(a.done_flags + n, 1);
+          }
+        }
+      }
     }
   }
 

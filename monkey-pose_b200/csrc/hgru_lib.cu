@@ -5,7 +5,9 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -39,6 +41,38 @@ int fail(int code, const std::string& msg) {
       return fail(HGRU_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));           \
   } while (0)
 
+// Function attributes (the dynamic shared-memory opt-in) and the SM count belong to a DEVICE, and one process may
+// drive several: remember per device what was done / read, not per process.
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> mask{0};
+  bool seen(int dev) const { return dev >= 0 && dev < 64 && ((mask.load(std::memory_order_acquire) >> dev) & 1ull); }
+  void mark(int dev) { if (dev >= 0 && dev < 64) mask.fetch_or(1ull << dev, std::memory_order_release); }
+};
+#define SMEM_ATTR_ONCE(kern, bytes)                                                                       \
+  do {                                                                                                    \
+    static PerDeviceOnce once_;                                                                           \
+    int dev_ = 0;                                                                                         \
+    CUDA_TRY(cudaGetDevice(&dev_));                                                                       \
+    if (!once_.seen(dev_)) {      /* (idempotent: a race only sets the attribute twice) */                \
+      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));           \
+      once_.mark(dev_);                                                                                   \
+    }                                                                                                     \
+  } while (0)
+
+// multiprocessor count of the current device
+inline int sm_count(int* out) {
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  int v = (dev >= 0 && dev < 64) ? cache[dev].load(std::memory_order_relaxed) : 0;
+  if (!v) {
+    CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+    if (dev >= 0 && dev < 64) cache[dev].store(v, std::memory_order_relaxed);
+  }
+  *out = v;
+  return 0;
+}
+
 inline unsigned nblk(size_t n, int b = 256) { return static_cast<unsigned>((n + b - 1) / b); }
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
@@ -63,23 +97,40 @@ template <int S, int KSTEPS, int CO_PAD, int TILES_X, int G, class Epi, bool SPL
 int launch_tc(const CUtensorMap& map, hgru::TcConvArgs a, cudaStream_t st) {
   using Cfg = hgru::TcConvCfg<S, KSTEPS, CO_PAD, TILES_X, G, 4, SPLIT3>;
   auto kern = hgru::hconv_tc_kernel<S, KSTEPS, CO_PAD, TILES_X, G, 4, Epi, SPLIT3>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_done = true;
-  }
+  SMEM_ATTR_ONCE(kern, Cfg::kSmemBytes);
   a.units_x = (a.W + 8 * TILES_X - 1) / (8 * TILES_X);
   a.units_y = (a.H + hgru::kTileRows - 1) / hgru::kTileRows;
   a.num_units = a.N * a.units_x * a.units_y;
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    CUDA_TRY(cudaGetDevice(&dev));
-    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  int sms = 0, rc = sm_count(&sms);
+  if (rc) return rc;
   const int grid = a.num_units < sms ? a.num_units : sms;
   kern<<<grid, 256, Cfg::kSmemBytes, st>>>(map, a);
   CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// 64 channels, 15x15 (the reference's own width): the same kernel with the 1x1 gate convs issued from its epilogue
+// and the launches of a forward chained per frame (TcConvCfg FUSE) -- two launches per timestep.  Three weight
+// stages instead of four make room for the gate's staging tile and weights.
+template <class Epi, int G = 5, int WS = 3>
+int launch_tc_fused64(const CUtensorMap& map, hgru::TcConvArgs a, cudaStream_t st) {
+  using Cfg = hgru::TcConvCfg<15, 4, 64, 4, G, WS, false, true>;
+  auto kern = hgru::hconv_tc_kernel<15, 4, 64, 4, G, WS, Epi, false, true>;
+  SMEM_ATTR_ONCE(kern, Cfg::kSmemBytes);
+  a.units_x = (a.W + 31) / 32;
+  a.units_y = (a.H + hgru::kTileRows - 1) / hgru::kTileRows;
+  a.num_units = a.N * a.units_x * a.units_y;
+  a.flag_target = a.units_x * a.units_y;
+  int sms = 0, rc = sm_count(&sms);
+  if (rc) return rc;
+  const int grid = a.num_units < sms ? a.num_units : sms;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = Cfg::kSmemBytes; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = (a.wait_flags || a.pdl) ? 1 : 0;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, map, a));
   return 0;
 }
 
@@ -161,20 +212,12 @@ template <int KP, int T, int KC, class Epi>
 int launch_stack(const CUtensorMap& map, hgru::TcConvArgs a, cudaStream_t st) {
   using Cfg = hgru::StackCfg<KP, T, KC, 1>;
   auto kern = hgru::hconv_stack_kernel<KP, T, KC, 1, Epi>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_done = true;
-  }
+  SMEM_ATTR_ONCE(kern, Cfg::SMEM_BYTES);
   a.units_x = (a.W + 63) / 64;
   a.units_y = (a.H + hgru::kTileRows - 1) / hgru::kTileRows;
   a.num_units = a.N * a.units_x * a.units_y;
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    CUDA_TRY(cudaGetDevice(&dev));
-    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  int sms = 0, rc = sm_count(&sms);
+  if (rc) return rc;
   const int grid = a.num_units < sms ? a.num_units : sms;
   a.flag_target = a.units_x * a.units_y;
   // A launch that waits on the previous launch's per-frame counters is chained to it (programmatic dependent
@@ -184,7 +227,7 @@ int launch_stack(const CUtensorMap& map, hgru::TcConvArgs a, cudaStream_t st) {
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = a.wait_flags ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = (a.wait_flags || a.pdl) ? 1 : 0;
   CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, map, map, a));     // (w_map is only read in pair mode)
   return 0;
 }
@@ -220,11 +263,7 @@ int launch_simt_conv(const float* in, const float* w, const float* bias, const f
                      cudaStream_t st) {
   using Cfg = hgru::ConvSimtCfg<S>;
   auto kern = hgru::conv_simt_kernel<S>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_done = true;
-  }
+  SMEM_ATTR_ONCE(kern, Cfg::kSmemBytes);
   dim3 grid(((W + 15) / 16) * ((H + 15) / 16), (Co + 63) / 64, N);
   kern<<<grid, 256, Cfg::kSmemBytes, st>>>(in, w, bias, scale, shift, out, N, H, W, Ci, Co, relu);
   CUDA_TRY(cudaGetLastError());
@@ -321,6 +360,7 @@ struct hgru_plan_s {
   DevBuf actA, actH1, actH2;
   DevBuf flags;                     // launch chaining: [2T][N] per-frame completion counters (stacked kernel)
   bool chain = false;
+  int group_frames = 0;             // chained launches walk the batch in groups of this many frames (0 = whole batch)
   CUtensorMap mapA, mapH1;          // SxS halo-window boxes (horizontal convs)
   CUtensorMap mapH1_g, mapH2_g;     // 1x1 boxes (gate convs)
   // readout operand emitted by the last H2 epilogue (set by the pose plan; nullptr for the bare layer)
@@ -329,6 +369,7 @@ struct hgru_plan_s {
   const float* fc_shift = nullptr;
   int fc_kpad = 0;
   bool stacked = false;             // narrow layers: tap-stacked kernel (hconv_stack.cuh)
+  bool fused_tc = false;            // 64 channels, 15x15: hconv_tc_kernel with epilogue-issued gates, chained (FUSE)
   int stack_T = 0;
   int act_pad = 0;                  // pad rows of the bf16 operand planes (remainder-packed layout)
   bool state_ready = false;         // the caller already ran hgru_init_state_bf16 for the coming forward
@@ -351,6 +392,9 @@ static int hgru_plan_init(hgru_plan_s* p, int N, int H, int W, int k, int S, int
   p->N = N; p->H = H; p->W = W; p->k = k; p->S = S; p->T = T; p->mode = mode;
   p->KP = round_up(k, 16);
   if (mode != HGRU_MODE_FP32 && p->KP == 48) p->KP = 64;      // tensor-core kernels exist for 16 / 32 / 64 padded channels
+  // exact path: the 1x1 gate kernel keeps the k x k matrix and a 64-pixel tile in <= 64 KB of shared memory
+  if (mode == HGRU_MODE_FP32 && p->KP > 96)
+    return fail(HGRU_E_UNSUPPORTED, "hgru_plan_create: fp32 mode supports k <= 96 channels");
   p->CG = p->KP / 8;
   p->npix = static_cast<size_t>(N) * H * W;
   p->nelem = p->npix * p->KP;
@@ -388,11 +432,21 @@ static int hgru_plan_init(hgru_plan_s* p, int N, int H, int W, int k, int S, int
     p->stacked = stack_geometry(S, p->KP, k, &sg);
     int box_cols = g.box_cols, box_rows = g.box_rows, box_chunks = 2;
     size_t wbytes = tapb * S * S;
-    if (p->stacked) {
+    {
+      const char* nf = getenv("HGRU_NO_FUSE64");      // development switch: the unfused four-launch pipeline
+      p->fused_tc = !p->stacked && S == 15 && p->KP == 64 && !(nf && nf[0] == '1');
+    }
+    if (p->stacked || p->fused_tc) {
       // consecutive conv launches are chained through per-frame counters (HGRU_NO_CHAIN=1: plain stream order)
       const char* nc = getenv("HGRU_NO_CHAIN");
       p->chain = !(nc && nc[0] == '1');
       if (p->chain && (rc = p->flags.alloc(sizeof(int) * 2 * static_cast<size_t>(T) * N))) return rc;
+      // Group-major order (time-major inside a frame group): all 2T launches of one group of frames before the next
+      // group, so that a group's state (X, H1, H2, G2 and the two bf16 operands) can stay in L2 across timesteps.
+      const char* gf = getenv("HGRU_GROUP_FRAMES");
+      if (gf && p->chain) p->group_frames = atoi(gf);
+    }
+    if (p->stacked) {
       p->stack_T = sg.T;
       p->act_pad = sg.act_pad;
       box_cols = sg.box_cols; box_rows = sg.box_rows;
@@ -404,6 +458,8 @@ static int hgru_plan_init(hgru_plan_s* p, int N, int H, int W, int k, int S, int
     const int HA = H + p->act_pad;
     const size_t ab = static_cast<size_t>(N) * p->CG * HA * W * 8 * sizeof(__nv_bfloat16);
     if ((rc = p->actA.alloc(ab)) || (rc = p->actH1.alloc(ab)) || (rc = p->actH2.alloc(ab))) return rc;
+    // (cudaMemset on device memory is asynchronous and the kernels run on non-blocking streams: hgru_plan_init's
+    // caller synchronises the device once after all clears, see plan_clears_done)
     CUDA_TRY(cudaMemset(p->actA.p, 0, ab));
     CUDA_TRY(cudaMemset(p->actH1.p, 0, ab));
     if ((rc = p->wpk.alloc(wbytes)) || (rc = p->wpk_i.alloc(tapb)) || (rc = p->wpk_o.alloc(tapb))) return rc;
@@ -435,7 +491,7 @@ static int hgru_set_params_impl(hgru_plan_s* p, const float* p_r, const float* i
   pad_matrix_kernel<<<nblk(KP * KP), 256, 0, st>>>(i_r, p->i_r.as<float>(), k, k, KP, KP);
   pad_matrix_kernel<<<nblk(KP * KP), 256, 0, st>>>(o_r, p->o_r.as<float>(), k, k, KP, KP);
   const float* v[8] = {i_b, o_b, beta, nu, gamma, kappa, omega, lateral_bias};
-  for (int i = 0; i < 8; ++i) pad_matrix_kernel<<<1, 256, 0, st>>>(v[i], p->vec(i), 1, k, KP, 1);
+  for (int i = 0; i < 8; ++i) pad_matrix_kernel<<<nblk(KP), 256, 0, st>>>(v[i], p->vec(i), 1, k, KP, 1);
   CUDA_TRY(cudaMemcpyAsync(p->rho.p, rho, sizeof(float) * p->T, cudaMemcpyDeviceToDevice, st));
   const int taps = p->S * p->S;
   if (p->mode == HGRU_MODE_FP32) {
@@ -473,11 +529,7 @@ static int hgru_run_fp32(hgru_plan_s* p, const float* Xp, float* H1_trace, float
   const int KP = p->KP, HW = p->H * p->W;
   const size_t nchunks = p->nelem / 8;
   const size_t gate_smem = sizeof(float) * (KP * KP + 64 * (KP + 1));
-  static bool gate_attr = false;
-  if (!gate_attr) {
-    CUDA_TRY(cudaFuncSetAttribute(hgru::gate1x1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    gate_attr = true;
-  }
+  SMEM_ATTR_ONCE(hgru::gate1x1_kernel, 64 * 1024);
   int rc;
   for (int t = 0; t < p->T; ++t) {
     // circuit_input (hgru_module.py:692-724): G1, gated copy, C1 = conv + lateral_bias (:657)
@@ -543,21 +595,12 @@ static int hgru_init_state_bf16(hgru_plan_s* p, const float* H2_init_nhwc, cudaS
     a.N = p->N; a.H = p->H; a.W = p->W; a.KP = p->KP; a.kreal = p->k; a.act_pad = p->act_pad;
     a.wpk = p->wpk_i.as<__nv_bfloat16>(); a.bias = p->vec(V_IB); a.H2 = p->H2.as<float>();
     a.out_bf16 = p->actA.as<__nv_bfloat16>();
-    static bool attr64 = false;
-    if (p->KP == 64 && !attr64) {
-      CUDA_TRY(cudaFuncSetAttribute(hgru::init_state_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    hgru::InitCfg<64>::SMEM_BYTES));
-      attr64 = true;
-    }
+    if (p->KP == 64) SMEM_ATTR_ONCE(hgru::init_state_tc_kernel<64>, hgru::InitCfg<64>::SMEM_BYTES);
     if (p->KP == 64) return launch_init_tc<64>(H2_init_nhwc, a, st);
     if (p->KP == 32) return launch_init_tc<32>(H2_init_nhwc, a, st);
     if (p->KP == 16) return launch_init_tc<16>(H2_init_nhwc, a, st);
   }
-  static bool attr = false;
-  if (!attr) {
-    CUDA_TRY(cudaFuncSetAttribute(hgru::init_state_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    attr = true;
-  }
+  SMEM_ATTR_ONCE(hgru::init_state_gate_kernel, 100 * 1024);
   const int KP = p->KP;
   const size_t smem = sizeof(float) * (KP * KP + hgru::kInitPix * (KP + 1));
   hgru::init_state_gate_kernel<<<nblk(p->npix, hgru::kInitPix), 256, smem, st>>>(
@@ -579,7 +622,9 @@ static int hgru_run_bf16(hgru_plan_s* p, const float* Xp, const float* H2_init_n
   if (!p->state_ready && (rc = hgru_init_state_bf16(p, H2_init_nhwc, st))) return rc;
   p->state_ready = false;
   ++p->launches;
-  const bool fused = p->stacked;
+  const bool fused = p->stacked || p->fused_tc;
+  // (development switch: weight ring of 5 stages x 3 taps instead of 3 stages x 5 taps for the fused 64-channel kernel)
+  static const bool ring35 = [] { const char* e = getenv("HGRU_F64_RING35"); return e && e[0] == '1'; }();
   // Chained launches (see TcConvArgs::wait_flags): launch l waits per frame on launch l-1's counters instead of on
   // the whole grid.  Not with traces (their copy kernels sit between the launches).
   const bool chain = fused && p->chain && !H1_trace && !H2_trace;
@@ -591,6 +636,11 @@ static int hgru_run_bf16(hgru_plan_s* p, const float* Xp, const float* H2_init_n
     a.wait_flags = l > 0 ? flags + static_cast<size_t>(l - 1) * p->N : nullptr;
   };
   if (chain) p->timer.begin(st);
+  const int GF = (chain && p->group_frames > 0 && p->group_frames < p->N) ? p->group_frames : p->N;
+  for (int n0 = 0; n0 < p->N; n0 += GF) {
+  base.n0 = n0;
+  base.N = (n0 + GF <= p->N) ? GF : p->N - n0;
+  const bool last_group = n0 + GF >= p->N;
   for (int t = 0; t < p->T; ++t) {
     hgru::TcConvArgs a;
     if (!fused && t > 0) {
@@ -610,9 +660,12 @@ static int hgru_run_bf16(hgru_plan_s* p, const float* Xp, const float* H2_init_n
     a.gate_wpk = p->wpk_o.as<__nv_bfloat16>(); a.gate_bias = p->vec(V_OB); a.gate_out = p->G.as<float>();
     a.do_gate = fused ? 1 : 0;
     set_flags(a, 2 * t);
+    a.pdl = (chain && t == 0 && n0 > 0) ? 1 : 0;      // follows the previous group's last launch: nothing to wait for
     if (!chain) p->timer.begin(st);
-    if ((rc = p->stacked ? dispatch_stack<hgru::EpiH1>(KP, p->stack_T, p->mapA, a, st)
-                        : dispatch_tc_hconv<hgru::EpiH1>(p->S, KP, p->mapA, a, st)))
+    if ((rc = p->stacked    ? dispatch_stack<hgru::EpiH1>(KP, p->stack_T, p->mapA, a, st)
+              : p->fused_tc ? (ring35 ? launch_tc_fused64<hgru::EpiH1, 3, 5>(p->mapA, a, st)
+                                      : launch_tc_fused64<hgru::EpiH1>(p->mapA, a, st))
+                            : dispatch_tc_hconv<hgru::EpiH1>(p->S, KP, p->mapA, a, st)))
       return rc;
     if (!chain) p->timer.end(st);
     ++p->launches;
@@ -639,11 +692,14 @@ static int hgru_run_bf16(hgru_plan_s* p, const float* Xp, const float* H2_init_n
     }
     set_flags(a, 2 * t + 1);
     if (!chain) p->timer.begin(st);
-    if ((rc = p->stacked ? dispatch_stack<hgru::EpiH2>(KP, p->stack_T, p->mapH1, a, st)
-                        : dispatch_tc_hconv<hgru::EpiH2>(p->S, KP, p->mapH1, a, st)))
+    if ((rc = p->stacked    ? dispatch_stack<hgru::EpiH2>(KP, p->stack_T, p->mapH1, a, st)
+              : p->fused_tc ? (ring35 ? launch_tc_fused64<hgru::EpiH2, 3, 5>(p->mapH1, a, st)
+                                      : launch_tc_fused64<hgru::EpiH2>(p->mapH1, a, st))
+                            : dispatch_tc_hconv<hgru::EpiH2>(p->S, KP, p->mapH1, a, st)))
       return rc;
     if (!chain) p->timer.end(st);
-    else if (t + 1 == p->T) p->timer.end(st, 2 * p->T);      // chained: one interval around all 2T launches
+    else if (t + 1 == p->T && last_group) p->timer.end(st, 2 * p->T);   // chained: one interval around all launches,
+    //                                                                     counted as 2T passes over the whole batch
     ++p->launches;
     if (H1_trace) {
       hgru::quad_to_nhwc_kernel<<<nblk(p->npix * p->k), 256, 0, st>>>(
@@ -656,6 +712,7 @@ static int hgru_run_bf16(hgru_plan_s* p, const float* Xp, const float* H2_init_n
       ++p->launches;
     }
   }
+  }
   return 0;
 }
 
@@ -667,11 +724,7 @@ static int hgru_run_bf16x3(hgru_plan_s* p, const float* Xp, const float* H2_init
                            float* H2_trace, cudaStream_t st) {
   const int KP = p->KP, HW = p->H * p->W;
   int rc;
-  static bool attr = false;
-  if (!attr) {
-    CUDA_TRY(cudaFuncSetAttribute(hgru::gate_quad_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    attr = true;
-  }
+  SMEM_ATTR_ONCE(hgru::gate_quad_split_kernel, 100 * 1024);
   const size_t gsmem = sizeof(float) * (KP * KP + hgru::kInitPix * (KP + 1));
   if (H2_init_nhwc)
     hgru::nhwc_to_quad_kernel<<<nblk(p->nelem / 4), 256, 0, st>>>(H2_init_nhwc, p->H2.as<float>(), p->npix, p->k, KP, HW);
@@ -919,6 +972,8 @@ int hgru_plan_create(int N, int H, int W, int k, int S, int T, int mode, hgru_pl
   *out = nullptr;
   hgru_plan_s* p = new hgru_plan_s();
   int rc = hgru_plan_init(p, N, H, W, k, S, T, mode);
+  if (!rc && cudaDeviceSynchronize() != cudaSuccess)      // the workspace clears are done before any stream uses it
+    rc = fail(HGRU_E_CUDA, "hgru_plan_create: device synchronisation failed");
   if (rc) {
     hgru_plan_free(p);
     delete p;
@@ -1029,6 +1084,8 @@ int pose_plan_create(int N, int HW, int C, int S, int T, int F, int O, int mode,
                 hgru::make_act_tensor_map(&p->map_conv2, p->act_conv2.p, N, 2 * KP / 8, HW, HW, g.box_cols, g.box_rows)))
       rc = fail(HGRU_E_CUDA, "cuTensorMapEncodeTiled failed");
   }
+  if (!rc && cudaDeviceSynchronize() != cudaSuccess)      // the workspace clears are done before any stream uses it
+    rc = fail(HGRU_E_CUDA, "pose_plan_create: device synchronisation failed");
   if (rc) {
     pose_plan_free(p);
     delete p;
@@ -1058,9 +1115,9 @@ int pose_set_params(pose_plan_t p, const pose_params_t* q, float eps, void* stre
     for (int j = 0; j < 4; ++j)
       if (!q->bn[i][j]) return fail(HGRU_E_INVALID, "pose_set_params: null batch-norm pointer");
   CUDA_TRY(cudaMemcpyAsync(p->w1.p, q->conv_1_filters, sizeof(float) * 9 * C, cudaMemcpyDeviceToDevice, st));
-  pad_matrix_kernel<<<1, 256, 0, st>>>(q->conv_1_biases, p->b1.as<float>(), 1, C, KP, 1);
-  pad_matrix_kernel<<<1, 256, 0, st>>>(q->conv_2_biases, p->b2.as<float>(), 1, C, KP, 1);
-  pad_matrix_kernel<<<1, 256, 0, st>>>(q->conv_3_biases, p->b3.as<float>(), 1, C, KP, 1);
+  pad_matrix_kernel<<<nblk(KP), 256, 0, st>>>(q->conv_1_biases, p->b1.as<float>(), 1, C, KP, 1);
+  pad_matrix_kernel<<<nblk(KP), 256, 0, st>>>(q->conv_2_biases, p->b2.as<float>(), 1, C, KP, 1);
+  pad_matrix_kernel<<<nblk(KP), 256, 0, st>>>(q->conv_3_biases, p->b3.as<float>(), 1, C, KP, 1);
   if (p->mode == HGRU_MODE_FP32) {
     pad_hwio_kernel<<<nblk(static_cast<size_t>(9) * KP * KP), 256, 0, st>>>(q->conv_2_filters, p->w2.as<float>(), 9, C, KP);
     pad_hwio_kernel<<<nblk(static_cast<size_t>(9) * KP * KP), 256, 0, st>>>(q->conv_3_filters, p->w3.as<float>(), 9, C, KP);
