@@ -45,12 +45,26 @@ def parse():
     ap.add_argument("--cpu-frames", type=int, default=64, help="frames in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stages", action="store_true", help="skip the crop / post-processing stage timings")
+    ap.add_argument("--no-extra", action="store_true", help="skip the short runs of the other BASELINE configs")
     return ap.parse_args()
+
+
+def config_label(batch, channels, timesteps):
+    """Which BASELINE.json config (if any) a (per-GPU batch, channels, timesteps) triple is."""
+    if (channels, timesteps) == (25, 8):
+        return "BASELINE configs[1]" if batch == 256 else \
+            ("BASELINE configs[2] per-GPU shard" if batch == 512 else "BASELINE configs[4] sweep point")
+    if (channels, timesteps) == (32, 16):
+        return "BASELINE configs[3], the deep variant"
+    if (channels, timesteps) == (64, 8):
+        return "the reference's own width, hgru_pose.py:50-81"
+    return "non-BASELINE sweep point"
 
 
 def workload_config(a, n_gpus):
     return {"workload": "hgru_pose forward, batch %d per GPU, 128x128 crops, 15x15 h-kernels, %d hidden "
-                        "channels, T=%d (BASELINE configs[1])" % (a.batch, a.channels, a.timesteps),
+                        "channels, T=%d (%s)" % (a.batch, a.channels, a.timesteps,
+                                                 config_label(a.batch, a.channels, a.timesteps)),
             "global_batch": a.batch * n_gpus, "per_gpu_batch": a.batch, "channels": a.channels,
             "timesteps": a.timesteps, "h_kernel": 15, "hconv_arithmetic": a.mode,
             "parallelism": "batch-sharded x%d, no data-path collective" % n_gpus,
@@ -87,8 +101,8 @@ def run_reference(a):
     if rank != 0:
         return
     steps = max(1, a.steps)
-    for _ in range(max(0, min(a.warmup, 1))):
-        pass
+    # (cpu_forward_fps runs one untimed 2-frame forward first: thread pool and oneDNN primitives are warm; a full
+    # --warmup W of 64-frame CPU forwards would not fit the few-minutes budget of this arm)
     fps, med, cores = cpu_forward_fps(a, a.cpu_frames, steps)
     sample = "%d frames per step (of the %d-frame batch), median of %d steps" % (a.cpu_frames, a.batch, steps)
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": a.gpus,
@@ -185,31 +199,21 @@ def run_ours(a):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n_gpus = world
     lib = mp._lib.load()
-
-    B = a.batch
-    P = init.pose_params(channels=a.channels, S=15, T=a.timesteps, hw=64, fc_hidden=1024, out=69, seed=3)
-    depth_np = init.synthetic_depth(B, seed=1234 + rank)
-    h0 = torch.as_tensor(init.hidden_init((B, 64, 64, a.channels), seed=5 + rank)).cuda()
-    depth_dev = torch.as_tensor(depth_np).cuda()
-    depth_pin = torch.as_tensor(depth_np).pin_memory()
-
-    m = mp.model()
-    m.channels, m.timesteps, m.compute_mode, m.hidden_state = a.channels, a.timesteps, a.mode, h0
-    m.load_params(P)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("bf16_tflops_sustained") or 1400.0
+    peak_burst = peaks.get("bf16_tflops") or 1650.0
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" \
+        if "bf16_tflops_sustained" in peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
 
     def sync():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
-
-    def step_dev():
-        out = m.build(depth_dev, 69)
-        return gather_predictions(out, B * world) if world > 1 else out
-
-    def step_host():
-        out = m.build(depth_pin, 69)          # H2D of the crops + forward + D2H of the predictions
-        return out
 
     def timed(fn, steps):
         sync()
@@ -227,25 +231,86 @@ def run_ours(a):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), t0, t1
 
-    for _ in range(max(3, a.warmup)):
-        step_dev()
-    clocks = Clocks(local) if rank == 0 else None
-    if clocks:
-        clocks.wait_ready()
-    step_dev()      # the sampler start-up left rank 0's GPU idle: one more untimed step (every rank: it has a collective)
-    lib.hgru_enable_kernel_timing(1)
-    ms_dev, t0, t1 = timed(step_dev, a.steps)
-    k_ms, k_n = ctypes.c_float(0), ctypes.c_int(0)
-    lib.pose_plan_kernel_times(m._plan, ctypes.byref(k_ms), ctypes.byref(k_n))   # last step's hconv launches
-    lib.hgru_enable_kernel_timing(0)
-    clk = clocks.stop(t0, t1) if clocks else None
-    launches_per_step = m.gpu_launches
-    out_check = step_dev()
-    assert torch.isfinite(out_check).all()
+    def make_model(channels, timesteps, mode, B, seed_off):
+        P = init.pose_params(channels=channels, S=15, T=timesteps, hw=64, fc_hidden=1024, out=69, seed=3)
+        h0 = torch.as_tensor(init.hidden_init((B, 64, 64, channels), seed=5 + seed_off)).cuda()
+        m = mp.model()
+        m.channels, m.timesteps, m.compute_mode, m.hidden_state = channels, timesteps, mode, h0
+        m.load_params(P)
+        return m
 
-    for _ in range(2):
-        step_host()
-    ms_host, _, _ = timed(step_host, a.steps)
+    def measure(m, channels, timesteps, mode, B, depth_dev, depth_pin, steps, warmup, with_clocks, gather):
+        """W warm-up steps, then K timed steps of the device-resident forward (+ the all-gather of the predictions
+        when sharded), the conv kernels timed live; then the same through host buffers."""
+        def step_dev():
+            out = m.build(depth_dev, 69)
+            return gather_predictions(out, B * world) if (gather and world > 1) else out
+
+        def step_host():
+            return m.build(depth_pin, 69)          # H2D of the crops + forward + D2H of the predictions
+
+        for _ in range(max(3, warmup)):
+            step_dev()
+        clocks = Clocks(local) if (with_clocks and rank == 0) else None
+        if clocks:
+            clocks.wait_ready()
+        step_dev()  # the sampler start-up left rank 0's GPU idle: one more untimed step (every rank: it has a collective)
+        lib.hgru_enable_kernel_timing(1)
+        ms_dev, t0, t1 = timed(step_dev, steps)
+        k_ms, k_n = ctypes.c_float(0), ctypes.c_int(0)
+        lib.pose_plan_kernel_times(m._plan, ctypes.byref(k_ms), ctypes.byref(k_n))   # last step's hconv launches
+        g_mean, g_min = ctypes.c_float(0), ctypes.c_float(0)
+        lib.pose_plan_sm_clock_ghz(m._plan, ctypes.byref(g_mean), ctypes.byref(g_min))
+        lib.hgru_enable_kernel_timing(0)
+        clk = clocks.stop(t0, t1) if clocks else None
+        if clk is not None:
+            # nvidia-smi keeps reporting the nominal clock; this is what the conv kernel's own clock64 / %globaltimer saw
+            clk["sm_clock_in_kernel_ghz"] = round(float(g_mean.value), 4) if g_mean.value else None
+            clk["sm_clock_in_kernel_ghz_min_cta"] = round(float(g_min.value), 4) if g_min.value else None
+        launches = m.gpu_launches
+        out_check = step_dev()
+        assert torch.isfinite(out_check).all()
+        ms_host = None
+        if depth_pin is not None:
+            for _ in range(2):
+                step_host()
+            ms_host, _, _ = timed(step_host, steps)
+        flops_per_launch = 2.0 * B * 64 * 64 * 15 * 15 * channels * channels     # SURVEY 8(d): 2*H*W*S^2*k^2 per frame
+        res = {"ms_dev": ms_dev, "ms_host": ms_host, "launches_per_step": launches, "clk": clk,
+               "flops_per_launch": flops_per_launch, "roof": None, "out": out_check,
+               "sm_clock_in_kernel_ghz": round(float(g_mean.value), 4) if g_mean.value else None}
+        if k_n.value > 0 and mode in ("bf16", "bf16x3"):
+            avg_ms = k_ms.value / k_n.value
+            ach = flops_per_launch / (avg_ms * 1e-3) * 1e-12
+            kern = ("hconv_tc_kernel SPLIT3 (15x15 implicit GEMM, bf16 hi/lo operand splits = 3 MMAs per useful one, "
+                    "tcgen05)" if mode == "bf16x3" else
+                    "hconv_stack_kernel (15x15 tap-stacked implicit GEMM + fused gates, tcgen05)" if channels <= 32 else
+                    "hconv_tc_kernel FUSE (15x15 implicit GEMM + fused gates, tcgen05)")
+            res["roof"] = {"bound": "tensor", "kernel": kern, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                           "frac": ach / peak, "frac_of_burst": ach / peak_burst, "peak_burst": peak_burst,
+                           "peak_source": peak_src, "avg_launch_ms": avg_ms, "launches_per_step": k_n.value,
+                           "share_of_step": k_ms.value / (ms_dev / steps), "flops_per_launch": flops_per_launch,
+                           "flops_note": "algorithmic, un-padded: 2*N*H*W*S^2*k^2"}
+        return res
+
+    B = a.batch
+    depth_np = init.synthetic_depth(B, seed=1234 + rank)
+    depth_dev = torch.as_tensor(depth_np).cuda()
+    depth_pin = torch.as_tensor(depth_np).pin_memory()
+    m = make_model(a.channels, a.timesteps, a.mode, B, rank)
+    r = measure(m, a.channels, a.timesteps, a.mode, B, depth_dev, depth_pin, a.steps, a.warmup, True, True)
+
+    # sharded run: the gathered predictions are those of the unsharded forward (rank 0 recomputes the last rank's shard)
+    shard_check = None
+    if world > 1:
+        if rank == 0:
+            other = world - 1
+            d2 = torch.as_tensor(init.synthetic_depth(B, seed=1234 + other)).cuda()
+            m.hidden_state = torch.as_tensor(init.hidden_init((B, 64, 64, a.channels), seed=5 + other)).cuda()
+            mine = m.build(d2, 69)
+            shard_check = "ok" if torch.equal(mine, r["out"][other * B:(other + 1) * B]) else "MISMATCH"
+        sync()
+    ms_dev, ms_host = r["ms_dev"], r["ms_host"]
 
     if rank != 0:
         if world > 1:
@@ -255,39 +320,18 @@ def run_ours(a):
     frames = B * world * a.steps
     value = frames / (ms_dev * 1e-3)
     e2e = frames / (ms_host * 1e-3)
-    # roofline of the dominant kernel: algorithmic FLOPs of one horizontal conv over this rank's batch
-    k, S = a.channels, 15
-    flops_per_launch = 2.0 * B * 64 * 64 * S * S * k * k                 # 2*H*W*S^2*k^2 per frame
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = peaks.get("bf16_tflops_sustained") or 1400.0
-    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" \
-        if "bf16_tflops_sustained" in peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
-    roof = None
-    traffic = None
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json"))).get(str(k))
-        if tj and tj.get("batch") == B:
-            traffic = tj["bytes_per_launch"]
-    except Exception:
-        pass
-    if k_n.value > 0 and a.mode in ("bf16", "bf16x3"):
-        avg_ms = k_ms.value / k_n.value
-        ach = flops_per_launch / (avg_ms * 1e-3) * 1e-12
-        kern = ("hconv_tc_kernel SPLIT3 (15x15 implicit GEMM, bf16 hi/lo operand splits = 3 MMAs per useful one, "
-                "tcgen05)" if a.mode == "bf16x3" else
-                "hconv_stack_kernel (15x15 tap-stacked implicit GEMM + fused gates, tcgen05)" if k <= 32 else
-                "hconv_tc_kernel (15x15 implicit GEMM, tcgen05)")
-        roof = {"bound": "tensor", "kernel": kern, "achieved": ach,
-                "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
-                "traffic_source": "ncu --set full capture, profiles/r01_ncu_traffic.json (bytes per launch)",
-                "peak_source": peak_src, "peak_burst": peaks.get("bf16_tflops"),
-                "avg_launch_ms": avg_ms, "launches_per_step": k_n.value,
-                "share_of_step": k_ms.value / (ms_dev / a.steps),
-                "flops_per_launch": flops_per_launch}
+    k = a.channels
+    roof = r["roof"]
+    if roof is not None:
+        traffic, tsrc = None, None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json"))).get(str(k))
+            if tj and tj.get("batch") == B and tj.get("timesteps", 8) == a.timesteps:
+                traffic, tsrc = tj["bytes_per_launch"], tj.get("source")
+        except Exception:
+            pass
+        roof["traffic"] = traffic
+        roof["traffic_source"] = tsrc or "no ncu --set full capture for this configuration"
     cpu = None
     if not a.no_cpu_baseline:
         fps, med, cores = cpu_forward_fps(a, a.cpu_frames, 3)
@@ -300,15 +344,37 @@ def run_ours(a):
             stages = neighbour_stages(a, m, torch, mp, init)
         except Exception as e:                      # never lose the headline line to an auxiliary measurement
             stages = {"error": repr(e)}
+    # The other BASELINE configs on this GPU, short runs (N = 1, default workload only): the reference's own width
+    # (64 channels), the deep variant (32 channels, T = 16) and the fp32-class tensor-core arithmetic at 25 channels.
+    extra = None
+    default_workload = (a.channels, a.timesteps, a.mode, B) == (25, 8, "bf16", 256)
+    if world == 1 and default_workload and not a.no_extra:
+        extra = {}
+        del m
+        for key, (ch, T, mode) in (("k64_T8", (64, 8, "bf16")), ("deep_k32_T16", (32, 16, "bf16")),
+                                   ("k25_T8_bf16x3", (25, 8, "bf16x3"))):
+            try:
+                torch.cuda.empty_cache()
+                mx = make_model(ch, T, mode, B, 0)
+                rx = measure(mx, ch, T, mode, B, depth_dev, None, 3, 3, False, False)
+                flops_step = 2 * T * rx["flops_per_launch"]
+                extra[key] = {"workload": "batch %d, %d channels, T=%d, %s (%s)" % (B, ch, T, mode, config_label(B, ch, T)),
+                              "value": B * 3 / (rx["ms_dev"] * 1e-3), "unit": UNIT, "ms_per_step": rx["ms_dev"] / 3,
+                              "steps": 3, "gpu_launches_per_step": rx["launches_per_step"],
+                              "hconv_TFLOP/s_whole_step": flops_step / (rx["ms_dev"] / 3 * 1e-3) * 1e-12,
+                              "roofline": rx["roof"], "sm_clock_in_kernel_ghz": rx["sm_clock_in_kernel_ghz"]}
+                del mx, rx
+            except Exception as e:
+                extra[key] = {"error": repr(e)}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps,
             "warmup": max(3, a.warmup), "ms_per_step": ms_dev / a.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": a.mode if a.mode != "fp32" else "f32",
             "data": "synthetic", "config": workload_config(a, n_gpus),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(depth_pin.numel() * 4) * world,
                     "d2h_bytes_per_step": int(B * 69 * 4) * world, "ms_per_step": ms_host / a.steps},
-            "gpu_launches": int(launches_per_step * a.steps), "clocks": clk, "roofline": roof,
-            "cpu_baseline": cpu, "neighbour_stages": stages,
-            "tensor_util_whole_step": (16 * flops_per_launch * world * a.steps / (ms_dev * 1e-3)) * 1e-12
+            "gpu_launches": int(r["launches_per_step"] * a.steps), "clocks": r["clk"], "roofline": roof,
+            "cpu_baseline": cpu, "neighbour_stages": stages, "extra": extra, "shard_check": shard_check,
+            "tensor_util_whole_step": (2 * a.timesteps * r["flops_per_launch"] * world * a.steps / (ms_dev * 1e-3)) * 1e-12
             / (peak * world)}
     print(json.dumps(line))
     if world > 1:

@@ -123,6 +123,37 @@ HGRU_API int pose_plan_launch_count(pose_plan_t plan);
  * when timing was enabled with hgru_enable_kernel_timing(plan-independent switch) */
 HGRU_API int hgru_enable_kernel_timing(int on);
 HGRU_API int pose_plan_kernel_times(pose_plan_t plan, float* hconv_ms_total, int* hconv_launches);
+/* SM clock (GHz) the last horizontal-conv launch of the last timed forward actually ran at, measured inside the
+ * kernel (clock64 cycles / %globaltimer nanoseconds of every CTA's MMA loop): mean and minimum over its CTAs, 0 when
+ * timing was off.  nvidia-smi reports the nominal clock while these kernels run power-limited.  Synchronises. */
+HGRU_API int pose_plan_sm_clock_ghz(pose_plan_t plan, float* ghz_mean, float* ghz_min);
+
+/* ------------------------------------------------------------------------------------------
+ * Stand-alone layers: the reference model's layer METHODS, for callers that compose the graph themselves the way
+ * hgru_pose.model.build does (hgru_pose.py:47-105).  Exact fp32, unfused, any channel counts; pose_forward does not
+ * go through these (it runs the fused tensor-core pipeline).  Dense fp32 NHWC activations, HWIO filters.
+ *   layer_conv2d_forward      model.conv_layer (hgru_pose.py:139-154): relu?(conv2d(x, filters, stride 1, SAME) + biases)
+ *   layer_max_pool2x2_forward model.max_pool (:134-137): 2x2, stride 2, SAME -> [N, ceil(H/2), ceil(W/2), C]
+ *   layer_fc_forward          model.fc_layer (:156-163): x [M,K] @ weights [K,F] + biases
+ *   layer_batch_norm_forward  tf.layers.batch_normalization(axis = last, momentum, epsilon, training) (:52-103) over
+ *       x [rows, C].  training = 0: moving statistics.  training = 1: statistics of the batch (biased variance); when
+ *       new_moving_mean / new_moving_var are given they receive moving * momentum + batch * (1 - momentum) (unbiased
+ *       batch variance), the update the reference runs through UPDATE_OPS (train_cnn_networks_hgru.py:123-126);
+ *       sums_ws = 2*C doubles of device workspace.  relu_first applies tf.nn.relu to x first (:92); dropout_keep < 1
+ *       (training only) then applies tf.nn.dropout(x, keep) (:93-94) with a counter-based keep mask: element i is
+ *       kept iff (splitmix64(seed ^ i * 0xD1B54A32D192ED03) >> 40) / 2^24 < keep, kept values scaled by 1 / keep.
+ * ------------------------------------------------------------------------------------------ */
+HGRU_API int layer_conv2d_forward(const float* x_dev, int N, int H, int W, int Cin, const float* filters_dev, int S,
+                                  int Cout, const float* biases_dev, int relu, float* out_dev, void* stream);
+HGRU_API int layer_max_pool2x2_forward(const float* x_dev, int N, int H, int W, int C, float* out_dev, void* stream);
+HGRU_API int layer_fc_forward(const float* x_dev, int M, int K, const float* weights_dev, const float* biases_dev,
+                              int F, float* out_dev, void* stream);
+HGRU_API int layer_batch_norm_forward(const float* x_dev, size_t rows, int C, const float* gamma_dev,
+                                      const float* beta_dev, const float* moving_mean_dev,
+                                      const float* moving_var_dev, float epsilon, int training, int relu_first,
+                                      float dropout_keep, unsigned long long dropout_seed, float momentum,
+                                      float* new_moving_mean_dev, float* new_moving_var_dev, double* sums_ws_dev,
+                                      float* y_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Crop stage (the step right before the pose network): replaces the per-frame host loop

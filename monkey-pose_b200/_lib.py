@@ -60,6 +60,12 @@ SIGNATURES = {
     "pose_plan_launch_count": (_I, [_P]),
     "hgru_enable_kernel_timing": (_I, [_I]),
     "pose_plan_kernel_times": (_I, [_P, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_I)]),
+    "pose_plan_sm_clock_ghz": (_I, [_P, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
+    "layer_conv2d_forward": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _P, _I, _P, _P]),
+    "layer_max_pool2x2_forward": (_I, [_P, _I, _I, _I, _I, _P, _P]),
+    "layer_fc_forward": (_I, [_P, _I, _I, _P, _P, _I, _P, _P]),
+    "layer_batch_norm_forward": (_I, [_P, ctypes.c_size_t, _I, _P, _P, _P, _P, ctypes.c_float, _I, _I, ctypes.c_float,
+                                      ctypes.c_ulonglong, ctypes.c_float, _P, _P, _P, _P, _P]),
     "crop_area3d_forward": (_I, [_P, _I, _I, _I, ctypes.c_float, _P, _P, ctypes.c_float, ctypes.c_double, _P,
                                  _I, _I, _P]),
     "pose_postprocess_forward": (_I, [_P, _P, _I, _I, ctypes.c_double, ctypes.c_double, ctypes.c_double,

@@ -738,8 +738,14 @@ hconv_stack_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
     // peer CTA of a pair: its MMAs are issued by the leader
   } else if (warp == 1) {
     // ---------------- MMA issuer (convergent warp, one elected lane issues) ----------------
+    const long long clk0 = a.clk_out ? clock64() : 0;
+    const unsigned long long ns0 = a.clk_out ? global_timer_ns() : 0ull;
     stack_mma_issuer<Cfg, PROF>(a, tmem_base, win, w_buf, bar_win_full, bar_win_empty, bar_w_full, bar_w_empty,
                                 bar_acc_full, bar_acc_empty, iters, NT, npairs);
+    if (a.clk_out && lane == 0) {      // cycles / nanoseconds of this CTA's MMA loop = its SM clock in GHz
+      a.clk_out[2 * blockIdx.x] = static_cast<unsigned long long>(clock64() - clk0);
+      a.clk_out[2 * blockIdx.x + 1] = global_timer_ns() - ns0;
+    }
   } else if (warp >= 4) {
     // the epilogue functors read the parameter vectors through the arguments: point them at the staged copies
     TcConvArgs ae = a;

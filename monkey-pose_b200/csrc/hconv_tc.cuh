@@ -125,7 +125,17 @@ struct TcConvArgs {
   // first launch of a frame group follows the last launch of the previous, independent, group).
   int n0;
   int pdl;
+  // Optional in-kernel SM clock measurement (nvidia-smi keeps reporting the nominal clock while the kernel runs at
+  // its power-limited one): the MMA issuer of CTA b stores {clock64 cycles, %globaltimer nanoseconds} it spent in
+  // its loop at clk_out[2b], clk_out[2b + 1].  nullptr = off.
+  unsigned long long* clk_out;
 };
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 // fp32 state tensors of the tensor-core path are "quad-chunked": [n][c/4][y][x][4].  A thread owns
 // one pixel (its TMEM lane) and a warp covers 8 horizontally adjacent pixels x 4 rows, so one 16-byte
@@ -661,6 +671,8 @@ hconv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const TcConvArgs a) 
     // registers; one elected lane issues the tcgen05 instructions (the same lane every time, so
     // its commits track all of its MMAs).
     const bool leader = elect_one();
+    const long long clk0 = a.clk_out ? clock64() : 0;
+    const unsigned long long ns0 = a.clk_out ? global_timer_ns() : 0ull;
     constexpr uint32_t idesc = make_idesc(1 /*bf16*/, 128, CO_PAD);
     // descriptor templates: only the 14-bit start-address field changes per instruction
     const uint64_t adesc0 = make_smem_desc(in_buf, Cfg::kChunkPitch, Cfg::kRowPitch);
@@ -704,6 +716,10 @@ hconv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const TcConvArgs a) 
         if (leader && last_use) tc_commit(bar_in_empty + 8 * q);
       }
       if (leader) tc_commit(bar_acc_full + 8 * s);
+    }
+    if (a.clk_out && leader) {
+      a.clk_out[2 * blockIdx.x] = static_cast<unsigned long long>(clock64() - clk0);
+      a.clk_out[2 * blockIdx.x + 1] = global_timer_ns() - ns0;
     }
     __syncwarp();
   } else if (warp >= 4) {

@@ -18,6 +18,7 @@
 #include "hconv_stack.cuh"
 #include "post.cuh"
 #include "hconv_tc.cuh"
+#include "layers.cuh"
 #include "simt_kernels.cuh"
 #include <algorithm>
 
@@ -359,6 +360,7 @@ struct hgru_plan_s {
   // bf16 chunked operand copies (tensor-core mode)
   DevBuf actA, actH1, actH2;
   DevBuf flags;                     // launch chaining: [2T][N] per-frame completion counters (stacked kernel)
+  DevBuf clk;                       // in-kernel clock samples of the last conv launch: [CTA][2] (cycles, ns)
   bool chain = false;
   int group_frames = 0;             // chained launches walk the batch in groups of this many frames (0 = whole batch)
   CUtensorMap mapA, mapH1;          // SxS halo-window boxes (horizontal convs)
@@ -378,7 +380,7 @@ struct hgru_plan_s {
   size_t workspace() const {
     return p_r.bytes + i_r.bytes + o_r.bytes + vecs.bytes + rho.bytes + wpk.bytes + wpk_i.bytes +
            wpk_o.bytes + Xp.bytes + H2.bytes + H1.bytes + C.bytes + G.bytes + A.bytes + actA.bytes +
-           actH1.bytes + actH2.bytes + flags.bytes;
+           actH1.bytes + actH2.bytes + flags.bytes + clk.bytes;
   }
 };
 
@@ -463,6 +465,8 @@ static int hgru_plan_init(hgru_plan_s* p, int N, int H, int W, int k, int S, int
     CUDA_TRY(cudaMemset(p->actA.p, 0, ab));
     CUDA_TRY(cudaMemset(p->actH1.p, 0, ab));
     if ((rc = p->wpk.alloc(wbytes)) || (rc = p->wpk_i.alloc(tapb)) || (rc = p->wpk_o.alloc(tapb))) return rc;
+    if ((rc = p->clk.alloc(sizeof(unsigned long long) * 2 * 1024))) return rc;
+    CUDA_TRY(cudaMemset(p->clk.p, 0, p->clk.bytes));
     TcGeom g1;
     tc_geometry(1, p->KP, &g1);
     if (hgru::make_act_tensor_map(&p->mapA, p->actA.p, N, p->CG, HA, W, box_cols, box_rows, box_chunks) ||
@@ -476,7 +480,7 @@ static int hgru_plan_init(hgru_plan_s* p, int N, int H, int W, int k, int S, int
 
 static void hgru_plan_free(hgru_plan_s* p) {
   DevBuf* all[] = {&p->p_r, &p->i_r, &p->o_r, &p->vecs, &p->rho, &p->wpk, &p->wpk_i, &p->wpk_o, &p->Xp,
-                   &p->H2, &p->H1, &p->C, &p->G, &p->A, &p->actA, &p->actH1, &p->actH2, &p->flags};
+                   &p->H2, &p->H1, &p->C, &p->G, &p->A, &p->actA, &p->actH1, &p->actH2, &p->flags, &p->clk};
   for (auto b : all) b->release();
 }
 
@@ -687,6 +691,7 @@ static int hgru_run_bf16(hgru_plan_s* p, const float* Xp, const float* H2_init_n
     a.gate_wpk = p->wpk_i.as<__nv_bfloat16>(); a.gate_bias = p->vec(V_IB);
     a.gate_act_out = p->actA.as<__nv_bfloat16>();
     a.do_gate = (fused && t + 1 < p->T) ? 1 : 0;
+    if (g_timing && t + 1 == p->T && last_group) a.clk_out = p->clk.as<unsigned long long>();   // (grids are <= 1024 CTAs)
     if (t + 1 == p->T && p->fc_a) {     // last update also emits the readout's bf16 hi/lo operand
       a.fc_a = p->fc_a; a.fc_scale = p->fc_scale; a.fc_shift = p->fc_shift; a.fc_kpad = p->fc_kpad;
     }
@@ -1220,6 +1225,24 @@ int pose_get_activation(pose_plan_t p, const char* name, float* dst, void* strea
 size_t pose_plan_workspace_bytes(pose_plan_t plan) { return plan ? plan->workspace() : 0; }
 int pose_plan_launch_count(pose_plan_t plan) { return plan ? plan->launches : 0; }
 
+int pose_plan_sm_clock_ghz(pose_plan_t plan, float* ghz_mean, float* ghz_min) {
+  if (!plan || !ghz_mean || !ghz_min) return fail(HGRU_E_INVALID, "pose_plan_sm_clock_ghz: null argument");
+  *ghz_mean = *ghz_min = 0.f;
+  const hgru_plan_s* h = &plan->hg;
+  if (!h->clk.p) return 0;                       // (the exact fp32 path has no tensor-core launch to sample)
+  std::vector<unsigned long long> v(h->clk.bytes / sizeof(unsigned long long));
+  CUDA_TRY(cudaMemcpy(v.data(), h->clk.p, h->clk.bytes, cudaMemcpyDeviceToHost));   // (synchronises the device)
+  double sum = 0.0, mn = 1e30;
+  int n = 0;
+  for (size_t i = 0; i + 1 < v.size(); i += 2) {
+    if (!v[i + 1]) continue;
+    const double g = static_cast<double>(v[i]) / static_cast<double>(v[i + 1]);
+    sum += g; mn = g < mn ? g : mn; ++n;
+  }
+  if (n) { *ghz_mean = static_cast<float>(sum / n); *ghz_min = static_cast<float>(mn); }
+  return 0;
+}
+
 int pose_plan_kernel_times(pose_plan_t plan, float* hconv_ms_total, int* hconv_launches) {
   if (!plan || !hconv_ms_total || !hconv_launches) return fail(HGRU_E_INVALID, "pose_plan_kernel_times: null argument");
   *hconv_launches = plan->hg.timer.collect(hconv_ms_total);
@@ -1257,6 +1280,70 @@ int joint_error_forward(const float* labels, const float* results, int N, int J,
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   hgru::joint_error_frame_kernel<<<N, 128, 0, st>>>(labels, results, J, frame_mean_ws, frame_max_ws);
   hgru::joint_error_final_kernel<<<1, 32, 0, st>>>(frame_mean_ws, frame_max_ws, N, result);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// ---- stand-alone layers (the reference model's layer methods; exact fp32, unfused) -----------------------------
+int layer_conv2d_forward(const float* x, int N, int H, int W, int Cin, const float* filters, int S, int Cout,
+                         const float* biases, int relu, float* out, void* stream) {
+  if (!x || !filters || !biases || !out) return fail(HGRU_E_INVALID, "layer_conv2d_forward: null pointer");
+  if (N < 1 || H < 1 || W < 1 || Cin < 1 || Cout < 1) return fail(HGRU_E_INVALID, "layer_conv2d_forward: non-positive shape");
+  if (S < 1 || (S % 2) == 0) return fail(HGRU_E_UNSUPPORTED, "layer_conv2d_forward: filter size must be odd");
+  const size_t total = static_cast<size_t>(N) * H * W * Cout;
+  hgru::conv2d_direct_kernel<<<nblk(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, filters, biases, out, N, H,
+                                                                                       W, Cin, Cout, S, relu ? 1 : 0);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int layer_max_pool2x2_forward(const float* x, int N, int H, int W, int C, float* out, void* stream) {
+  if (!x || !out) return fail(HGRU_E_INVALID, "layer_max_pool2x2_forward: null pointer");
+  if (N < 1 || H < 1 || W < 1 || C < 1) return fail(HGRU_E_INVALID, "layer_max_pool2x2_forward: non-positive shape");
+  const size_t total = static_cast<size_t>(N) * ((H + 1) / 2) * ((W + 1) / 2) * C;
+  hgru::max_pool2x2_kernel<<<nblk(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, out, N, H, W, C);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int layer_fc_forward(const float* x, int M, int K, const float* weights, const float* biases, int F, float* out,
+                     void* stream) {
+  if (!x || !weights || !biases || !out) return fail(HGRU_E_INVALID, "layer_fc_forward: null pointer");
+  if (M < 1 || K < 1 || F < 1) return fail(HGRU_E_INVALID, "layer_fc_forward: non-positive shape");
+  hgru::fc_direct_kernel<<<nblk(static_cast<size_t>(M) * F), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, weights, biases, out, M, K, F);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int layer_batch_norm_forward(const float* x, size_t rows, int C, const float* gamma, const float* beta,
+                             const float* moving_mean, const float* moving_var, float eps, int training,
+                             int relu_first, float dropout_keep, unsigned long long dropout_seed, float momentum,
+                             float* new_moving_mean, float* new_moving_var, double* sums_ws, float* y, void* stream) {
+  if (!x || !gamma || !beta || !moving_mean || !moving_var || !y)
+    return fail(HGRU_E_INVALID, "layer_batch_norm_forward: null pointer");
+  if (rows < 1 || C < 1) return fail(HGRU_E_INVALID, "layer_batch_norm_forward: non-positive shape");
+  if (!(dropout_keep > 0.f)) return fail(HGRU_E_INVALID, "layer_batch_norm_forward: dropout_keep must be positive");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t total = rows * static_cast<size_t>(C);
+  if (!training) {
+    if (dropout_keep < 1.f) return fail(HGRU_E_INVALID, "layer_batch_norm_forward: dropout is a training-mode op");
+    hgru::bn_inference_kernel<<<nblk(total), 256, 0, st>>>(x, y, total, C, gamma, beta, moving_mean, moving_var, eps,
+                                                          relu_first ? 1 : 0);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+  }
+  if (!sums_ws) return fail(HGRU_E_INVALID, "layer_batch_norm_forward: training mode needs the 2*C doubles of workspace");
+  if ((new_moving_mean == nullptr) != (new_moving_var == nullptr))
+    return fail(HGRU_E_INVALID, "layer_batch_norm_forward: give both new moving statistics or neither");
+  CUDA_TRY(cudaMemsetAsync(sums_ws, 0, sizeof(double) * 2 * C, st));
+  size_t chunks = (rows + 2047) / 2048;
+  if (chunks > 2048) chunks = 2048;
+  hgru::bn_batch_sums_kernel<<<dim3((C + 31) / 32, static_cast<unsigned>(chunks)), 256, 0, st>>>(
+      x, rows, C, sums_ws, relu_first ? 1 : 0, dropout_keep, dropout_seed);
+  hgru::bn_apply_batch_kernel<<<nblk(total > static_cast<size_t>(C) ? total : C), 256, 0, st>>>(
+      x, y, rows, C, sums_ws, gamma, beta, eps, moving_mean, moving_var, momentum, new_moving_mean, new_moving_var,
+      relu_first ? 1 : 0, dropout_keep, dropout_seed);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

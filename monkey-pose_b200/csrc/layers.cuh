@@ -1,0 +1,178 @@
+// Stand-alone layer kernels behind the reference model's layer METHODS (hgru_pose.py:134-163: max_pool,
+// conv_layer, fc_layer) and the train-mode batch normalisation (tf.layers.batch_normalization(training=True),
+// hgru_pose.py:52-103).  model.build() does not go through these -- it runs the fused tensor-core pipeline; these
+// serve callers that compose the layers themselves, exactly (fp32, any channel counts), without the fusion.
+// All tensors dense fp32, activations NHWC, conv weights HWIO.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace hgru {
+
+// relu?(conv2d(x, w, stride 1, SAME) + b): one thread per (pixel, output channel); consecutive threads take
+// consecutive output channels, so weight reads are coalesced and the input value is a warp broadcast.
+__global__ void __launch_bounds__(256)
+conv2d_direct_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                     float* __restrict__ out, int N, int H, int W, int Ci, int Co, int S, int relu) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  const size_t total = static_cast<size_t>(N) * H * W * Co;
+  if (i >= total) return;
+  const int co = static_cast<int>(i % Co);
+  const size_t pix = i / Co;
+  const int xx = static_cast<int>(pix % W);
+  const int yy = static_cast<int>((pix / W) % H);
+  const int n = static_cast<int>(pix / (static_cast<size_t>(W) * H));
+  const int pad = (S - 1) / 2;          // TF SAME, stride 1, odd S
+  float acc = 0.f;
+  for (int dy = 0; dy < S; ++dy) {
+    const int y = yy + dy - pad;
+    if (y < 0 || y >= H) continue;
+    for (int dx = 0; dx < S; ++dx) {
+      const int xq = xx + dx - pad;
+      if (xq < 0 || xq >= W) continue;
+      const float* xp = x + ((static_cast<size_t>(n) * H + y) * W + xq) * Ci;
+      const float* wp = w + (static_cast<size_t>(dy) * S + dx) * Ci * Co + co;
+      for (int ci = 0; ci < Ci; ++ci) acc = fmaf(__ldg(xp + ci), __ldg(wp + static_cast<size_t>(ci) * Co), acc);
+    }
+  }
+  acc += __ldg(b + co);
+  out[i] = relu ? fmaxf(acc, 0.f) : acc;
+}
+
+// tf.nn.max_pool(ksize 2x2, stride 2, SAME): output ceil(H/2) x ceil(W/2); windows are clipped at the border
+__global__ void __launch_bounds__(256)
+max_pool2x2_kernel(const float* __restrict__ x, float* __restrict__ out, int N, int H, int W, int C) {
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  const size_t total = static_cast<size_t>(N) * Ho * Wo * C;
+  if (i >= total) return;
+  const int c = static_cast<int>(i % C);
+  const size_t pix = i / C;
+  const int xo = static_cast<int>(pix % Wo);
+  const int yo = static_cast<int>((pix / Wo) % Ho);
+  const int n = static_cast<int>(pix / (static_cast<size_t>(Wo) * Ho));
+  float m = -INFINITY;
+  for (int dy = 0; dy < 2; ++dy)
+    for (int dx = 0; dx < 2; ++dx) {
+      const int y = 2 * yo + dy, xq = 2 * xo + dx;
+      if (y < H && xq < W) m = fmaxf(m, __ldg(x + ((static_cast<size_t>(n) * H + y) * W + xq) * C + c));
+    }
+  out[i] = m;
+}
+
+// x [M][K] @ w [K][F] + b [F]: block = 64 outputs j of one row m... one thread per (m, j), K walked in chunks whose
+// fp32 partial sums are added in double (K is 262 144 for fc_1).
+__global__ void __launch_bounds__(256)
+fc_direct_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                 float* __restrict__ out, int M, int K, int F) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= static_cast<size_t>(M) * F) return;
+  const int j = static_cast<int>(i % F);
+  const int m = static_cast<int>(i / F);
+  const float* xr = x + static_cast<size_t>(m) * K;
+  double acc = 0.0;
+  for (int k0 = 0; k0 < K; k0 += 256) {
+    const int k1 = k0 + 256 < K ? k0 + 256 : K;
+    float part = 0.f;
+    for (int k = k0; k < k1; ++k) part = fmaf(__ldg(xr + k), __ldg(w + static_cast<size_t>(k) * F + j), part);
+    acc += static_cast<double>(part);
+  }
+  out[i] = static_cast<float>(acc + static_cast<double>(__ldg(b + j)));
+}
+
+// ---- train-mode batch normalisation ------------------------------------------------------------------------------
+// Element-wise prologue shared by the two passes: optional relu (hgru_pose.py:92) and optional inverted dropout
+// (tf.nn.dropout(x, keep_prob), :93-94: kept elements are scaled by 1 / keep_prob).  TensorFlow's random stream
+// cannot be reproduced, so the keep mask is a counter-based hash of (seed, element index): splitmix64, keep when the
+// top 24 bits / 2^24 < keep_prob.  keep >= 1 disables dropout.
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ float bn_pre_op(float v, size_t idx, int relu, float keep, unsigned long long seed) {
+  if (relu) v = fmaxf(v, 0.f);
+  if (keep < 1.f) {
+    const unsigned long long h = splitmix64(seed ^ (static_cast<unsigned long long>(idx) * 0xD1B54A32D192ED03ull));
+    const float u = static_cast<float>(h >> 40) * (1.0f / 16777216.0f);
+    v = (u < keep) ? v / keep : 0.f;
+  }
+  return v;
+}
+
+// Batch statistics over every axis but the last (tf.layers.batch_normalization(training=True, fused=True): mean and
+// BIASED variance of the batch).  x is [rows][C] (NHWC flattened).  Pass 1: per-channel sum and sum of squares in
+// double, blocks = (channel group of 32) x (row chunk), combined with double atomics into sums[c], sums[C + c]
+// (zeroed by the caller).  Double keeps the one-pass variance exact to ~1e-13 at these sizes.
+__global__ void __launch_bounds__(256)
+bn_batch_sums_kernel(const float* __restrict__ x, size_t rows, int C, double* __restrict__ sums, int relu,
+                     float keep, unsigned long long seed) {
+  __shared__ double sh[2][8][32];
+  const int lane = threadIdx.x & 31, rlane = threadIdx.x >> 5;          // 32 channels x 8 row lanes
+  const int c = blockIdx.x * 32 + lane;
+  const size_t per = (rows + gridDim.y - 1) / gridDim.y;
+  const size_t r0 = blockIdx.y * per, r1 = r0 + per < rows ? r0 + per : rows;
+  double s = 0.0, q = 0.0;
+  if (c < C)
+    for (size_t r = r0 + rlane; r < r1; r += 8) {
+      const double v = static_cast<double>(bn_pre_op(__ldg(x + r * C + c), r * C + c, relu, keep, seed));
+      s += v;
+      q += v * v;
+    }
+  sh[0][rlane][lane] = s;
+  sh[1][rlane][lane] = q;
+  __syncthreads();
+  if (rlane == 0 && c < C) {
+    for (int k = 1; k < 8; ++k) { s += sh[0][k][lane]; q += sh[1][k][lane]; }
+    atomicAdd(sums + c, s);
+    atomicAdd(sums + C + c, q);
+  }
+}
+
+// Pass 2: y = (x - mean) / sqrt(var + eps) * gamma + beta with mean = S / rows, var = Q / rows - mean^2; also the
+// moving-statistics update the reference's UPDATE_OPS perform (train_cnn_networks_hgru.py:123-126): moving = moving *
+// momentum + batch * (1 - momentum), with the UNBIASED batch variance as TF's fused kernel reports it -- written to
+// new_mean / new_var when non-null (threads i < C do it).  batch_mean / batch_var (biased) are exported when non-null.
+__global__ void __launch_bounds__(256)
+bn_apply_batch_kernel(const float* __restrict__ x, float* __restrict__ y, size_t rows, int C,
+                      const double* __restrict__ sums, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, float eps, const float* __restrict__ moving_mean,
+                      const float* __restrict__ moving_var, float momentum, float* __restrict__ new_mean,
+                      float* __restrict__ new_var, int relu, float keep, unsigned long long seed) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  const double inv_rows = 1.0 / static_cast<double>(rows);
+  if (i < static_cast<size_t>(C) && new_mean && new_var) {
+    const int c = static_cast<int>(i);
+    const double mean = sums[c] * inv_rows;
+    double var = sums[C + c] * inv_rows - mean * mean;
+    var = var > 0.0 ? var : 0.0;
+    const double unbiased = rows > 1 ? var * static_cast<double>(rows) / static_cast<double>(rows - 1) : var;
+    new_mean[c] = static_cast<float>(static_cast<double>(moving_mean[c]) * momentum + mean * (1.0 - momentum));
+    new_var[c] = static_cast<float>(static_cast<double>(moving_var[c]) * momentum + unbiased * (1.0 - momentum));
+  }
+  if (i >= rows * C) return;
+  const int c = static_cast<int>(i % C);
+  const double mean = sums[c] * inv_rows;
+  double var = sums[C + c] * inv_rows - mean * mean;
+  var = var > 0.0 ? var : 0.0;
+  const double v = static_cast<double>(bn_pre_op(x[i], i, relu, keep, seed));
+  y[i] = static_cast<float>((v - mean) / sqrt(var + static_cast<double>(eps)) * static_cast<double>(__ldg(gamma + c)) +
+                            static_cast<double>(__ldg(beta + c)));
+}
+
+
+// tf.layers.batch_normalization(training=False): y = (x - moving_mean) / sqrt(moving_var + eps) * gamma + beta
+__global__ void __launch_bounds__(256)
+bn_inference_kernel(const float* __restrict__ x, float* __restrict__ y, size_t total, int C,
+                    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
+                    const float* __restrict__ var, float eps, int relu) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int c = static_cast<int>(i % C);
+  float v = x[i];
+  if (relu) v = fmaxf(v, 0.f);
+  const float sc = __ldg(gamma + c) / sqrtf(__ldg(var + c) + eps);
+  y[i] = (v - __ldg(mean + c)) * sc + __ldg(beta + c);
+}
+
+}  // namespace hgru
