@@ -58,19 +58,34 @@ def auxilliary_variables():
     }
 
 
-_PLAN_CACHE = {}
+# Plans own their workspace (gigabytes at batch 256), so only the most recently used few shapes stay alive.
+_PLAN_CACHE = {}          # key -> plan handle, in least-recently-used order (dicts keep insertion order)
+PLAN_CACHE_SIZE = 4
+
+
+def clear_plan_cache():
+    """Destroy every cached layer plan and free its device workspace."""
+    lib = _lib.load()
+    torch.cuda.synchronize()
+    for plan in _PLAN_CACHE.values():
+        lib.hgru_plan_destroy(plan)
+    _PLAN_CACHE.clear()
 
 
 def _get_plan(N, H, W, k, S, T, mode):
     key = (torch.cuda.current_device(), N, H, W, k, S, T, mode)
-    plan = _PLAN_CACHE.get(key)
+    plan = _PLAN_CACHE.pop(key, None)
     if plan is None:
         import ctypes
         lib = _lib.load()
+        while len(_PLAN_CACHE) >= PLAN_CACHE_SIZE:          # evict the least recently used plan
+            old = next(iter(_PLAN_CACHE))
+            torch.cuda.synchronize()                        # (its last forward may still be running)
+            lib.hgru_plan_destroy(_PLAN_CACHE.pop(old))
         h = ctypes.c_void_p()
         _lib.check(lib.hgru_plan_create(N, H, W, k, S, T, mode, ctypes.byref(h)), "hgru_plan_create")
         plan = h
-        _PLAN_CACHE[key] = plan
+    _PLAN_CACHE[key] = plan          # (re)insert as most recently used
     return plan
 
 
@@ -231,9 +246,14 @@ class ContextualCircuit(object):
         shapes = {'p_r': (S, S, k, k), 'i_r': (1, 1, k, k), 'o_r': (1, 1, k, k), 'rho': (T,)}
         for n in ('i_b', 'o_b', 'beta', 'nu', 'gamma', 'kappa', 'omega', 'lateral_bias'):
             shapes[n] = (1, 1, 1, k)
+        # `rho` exists only with adapation=True (hgru_module.py:490-493); without it the state is not rescaled
+        # (:847-849) -- the kernels then multiply by a vector of ones that is not a variable of the layer.
+        adapt = bool(self.adapation)
         if self._injected is not None:
             src = {}
             for n in _lib.HGRU_PARAM_ORDER:
+                if n == 'rho' and not adapt:
+                    continue
                 v = self._injected.get(n, self._injected.get('contextual_circuit/' + n))
                 if v is None:
                     raise KeyError('params is missing %r' % n)
@@ -242,7 +262,13 @@ class ContextualCircuit(object):
             if self.gate_bias_init != 'chronos':
                 raise NotImplementedError("gate_bias_init != 'chronos'")
             src = init.hgru_params(k, S, T, seed=self._seed)
+        self._rho_ones = None
         for n in _lib.HGRU_PARAM_ORDER:
+            if n == 'rho' and not adapt:
+                self._rho_ones = torch.ones(T, device=self.X.device, dtype=torch.float32)
+                if hasattr(self, 'rho'):
+                    delattr(self, 'rho')
+                continue
             t = _as_dev(src[n])
             if tuple(t.shape) != shapes[n]:
                 if t.numel() != int(np.prod(shapes[n])):
@@ -296,7 +322,8 @@ class ContextualCircuit(object):
                          _lib.MODES[self.compute_mode])
         self._plan = plan
         st = _stream()
-        ptrs = [getattr(self, n).data_ptr() for n in _lib.HGRU_PARAM_ORDER]
+        ptrs = [(self._rho_ones if (n == 'rho' and self._rho_ones is not None) else getattr(self, n)).data_ptr()
+                for n in _lib.HGRU_PARAM_ORDER]
         _lib.check(lib.hgru_set_params(plan, *ptrs, st), "hgru_set_params")
         O0 = self._initial_state()
         O = torch.empty_like(self.X)

@@ -9,7 +9,15 @@ a (pinned) CPU tensor goes through the host entry point (H2D copy, forward, D2H 
 
 The reference graph cannot run as committed (defects D4-D6); this module
 implements the documented resolutions: hgru = build()[0] (R-D4), batch-norm over the last axis of
-the fc tensor (R-D5), fc_out consumes relu1 (R-D6).  Inference-mode batch norm only (R-D7).
+the fc tensor (R-D5), fc_out consumes relu1 (R-D6).
+
+Two execution paths behind `build()`:
+  * train_mode in (None, False): the fused tensor-core pipeline (`pose_forward`), inference-mode batch norm
+    (moving statistics) -- the hot path, the benchmark and the parity mode, the one that shards over GPUs;
+  * train_mode=True (what the reference's only live caller passes, train_cnn_networks_hgru.py:142): the graph
+    composed layer by layer from the model's own layer methods the way the reference composes it
+    (`conv_layer`, `max_pool`, `hgru_layer`, `fc_layer`, tf.layers.batch_normalization(training=True) with
+    batch statistics, dropout keep 0.7) -- forward only, single GPU (batch statistics couple the batch).
 """
 import ctypes
 
@@ -35,6 +43,9 @@ class _Lazy(object):
         _lib.check(_lib.load().pose_get_activation(self.owner._plan, self.name.encode(), out.data_ptr(),
                                                    _stream()), "pose_get_activation")
         return out
+
+
+_LAZY_NAMES = ("conv1", "pool1", "conv2", "conv3", "hgru", "fc1", "relu1")
 
 
 class model:
@@ -78,9 +89,24 @@ class model:
         #                               splits, <=1e-4, 15x15 kernels)
         self.hidden_state = None      # O_0 [N,64,64,k]; None -> seeded xavier-uniform draw
         self.seed = 42
+        self.dropout_seed = 1234      # train_mode=True: seed of the counter-based dropout mask
         self._plan = None
         self._plan_key = None
         self._dev_params = None
+        self._h0_cache = None         # (key, device tensor) of the seeded O_0 draw
+        self._lazy = {}
+
+    def __getattr__(self, name):
+        """The tensors the reference's build() leaves as attributes (hgru_pose.py:50-105: conv1, pool1, conv2,
+        conv3, hgru, fc1, relu1 -- batch-normalised where the reference re-assigns them).  The fused pipeline keeps
+        only what later kernels read, so these are materialised on first access after a build()."""
+        if name in _LAZY_NAMES:
+            lazy = self.__dict__.get("_lazy") or {}
+            if name in lazy:
+                val = lazy[name].get() if hasattr(lazy[name], "get") else lazy[name]()
+                self.__dict__[name] = val
+                return val
+        raise AttributeError(name)
 
     def __getitem__(self, name):
         return getattr(self, name)
@@ -151,17 +177,18 @@ class model:
             value = self.data_dict[name][idx]
         else:
             value = initial_value
+        src = self.__dict__.setdefault("_var_src", {})
+        if src.get((name, idx)) is value and (name, idx) in self.var_dict:
+            return self.var_dict[(name, idx)]          # same host array as last time: keep its device copy
         var = _as_dev(value)
         self.var_dict[(name, idx)] = var
+        src[(name, idx)] = value
         return var
 
     def _materialise(self, in_ch, hw, output_shape):
         """Create every variable of the graph (hgru_pose.py:165-194 + hgru_module.py:262-503)."""
         k, T, S = self.channels, self.timesteps, 2 * (self.SSF // 2) + 1
-        fresh = init.pose_params(channels=k, S=S, T=T, hw=hw, fc_hidden=self.fc_hidden, out=output_shape,
-                                 seed=self.seed) if self.data_dict is None or not all(
-            n in self.data_dict for n in ("conv_1", "conv_2", "conv_3", "fc_1", "fc_out",
-                                          "contextual_circuit") + BN_SCOPES) else None
+        fresh = self.__dict__.get("_defaults")      # None when data_dict supplies every variable
 
         def default(key):
             return fresh[key] if fresh is not None else None
@@ -190,21 +217,194 @@ class model:
                 raise ValueError("%s has shape %s, expected %s" % (n, tuple(P[n].shape), shp))
         return P
 
+    # -- layer methods (hgru_pose.py:107-194) -------------------------------------------------------
+    # Stand-alone, exact fp32, unfused: what a caller composing the graph by hand gets.  build() in inference mode
+    # does NOT go through them (it runs the fused tensor-core pipeline); build(train_mode=True) does.
+    def _rng(self, name):
+        import zlib
+        return np.random.default_rng([self.seed, zlib.crc32(name.encode())])
+
+    def _default(self, key, fallback):
+        """Initial value of variable `key` ('conv_2/conv_2_filters', 'batch_normalization_3/gamma', ...): inside
+        build() the seeded draw of the whole graph (the same one whichever path runs), else `fallback()`."""
+        d = self.__dict__.get("_defaults")
+        if d is not None and key in d:
+            return d[key]
+        return fallback()
+
+    def get_conv_var(self, filter_size, in_channels, out_channels, name, init_type='xavier'):
+        """hgru_pose.py:165-180: xavier-normal filters (or truncated_normal(0, .001)), truncated_normal(0, .001) biases,
+        unless `data_dict[name]` supplies them."""
+        rng = self._rng(name)
+        shape = (filter_size, filter_size, in_channels, out_channels)
+        w0 = self._default("%s/%s_filters" % (name, name), lambda: (
+            init.xavier_normal(rng, shape) if init_type == 'xavier' else init._truncated_normal(rng, shape, 0.001)))
+        b0 = self._default("%s/%s_biases" % (name, name), lambda: init._truncated_normal(rng, (out_channels,), 0.001))
+        filters = self.get_var(w0, name, 0, name + "_filters")
+        biases = self.get_var(b0, name, 1, name + "_biases")
+        return filters, biases
+
+    def get_fc_var(self, in_size, out_size, name, init_type='xavier'):
+        """hgru_pose.py:182-194."""
+        rng = self._rng(name)
+        w0 = self._default("%s/%s_weights" % (name, name), lambda: (
+            init.xavier_normal(rng, (in_size, out_size)) if init_type == 'xavier' else
+            init._truncated_normal(rng, (in_size, out_size), 0.001)))
+        b0 = self._default("%s/%s_biases" % (name, name), lambda: init._truncated_normal(rng, (out_size,), 0.001))
+        weights = self.get_var(w0, name, 0, name + "_weights")
+        biases = self.get_var(b0, name, 1, name + "_biases")
+        return weights, biases
+
+    @staticmethod
+    def _need_cuda(t, what):
+        if not (torch.is_tensor(t) and t.is_cuda):
+            raise RuntimeError("%s needs a CUDA tensor (no CPU fallback)" % what)
+        return t.to(torch.float32).contiguous()
+
+    def conv_layer(self, bottom, in_channels, out_channels, name, filter_size=3, batchnorm=None,
+                   stride=[1, 1, 1, 1]):
+        """hgru_pose.py:139-154: relu(conv2d(bottom, filters, SAME) + biases); variables `<name>/<name>_filters`,
+        `<name>/<name>_biases`."""
+        if list(stride) != [1, 1, 1, 1]:
+            raise NotImplementedError("conv_layer: stride != [1,1,1,1] is not on the path hgru_pose.py configures")
+        if batchnorm is not None and name in batchnorm:
+            raise NotImplementedError("conv_layer(batchnorm=...) (tf.nn.moments over the batch axis, hgru_pose.py:"
+                                      "120-122) is never selected by hgru_pose.build")
+        x = self._need_cuda(bottom, "conv_layer")
+        if x.dim() != 4 or int(x.shape[-1]) != int(in_channels):
+            raise ValueError("conv_layer: bottom must be [N,H,W,%d]" % in_channels)
+        filt, bias = self.get_conv_var(filter_size, in_channels, out_channels, name)
+        if tuple(filt.shape) != (filter_size, filter_size, in_channels, out_channels):
+            raise ValueError("%s_filters has shape %s" % (name, tuple(filt.shape)))
+        N, H, W = [int(v) for v in x.shape[:3]]
+        out = torch.empty((N, H, W, int(out_channels)), device=x.device, dtype=torch.float32)
+        _lib.check(_lib.load().layer_conv2d_forward(x.data_ptr(), N, H, W, int(in_channels), filt.data_ptr(),
+                                                    int(filter_size), int(out_channels), bias.data_ptr(), 1,
+                                                    out.data_ptr(), _stream()), "layer_conv2d_forward")
+        return out
+
+    def max_pool(self, bottom, name):
+        """hgru_pose.py:134-137: tf.nn.max_pool 2x2, stride 2, SAME."""
+        x = self._need_cuda(bottom, "max_pool")
+        N, H, W, C = [int(v) for v in x.shape]
+        out = torch.empty((N, (H + 1) // 2, (W + 1) // 2, C), device=x.device, dtype=torch.float32)
+        _lib.check(_lib.load().layer_max_pool2x2_forward(x.data_ptr(), N, H, W, C, out.data_ptr(), _stream()),
+                   "layer_max_pool2x2_forward")
+        return out
+
+    def fc_layer(self, bottom, in_size, out_size, name):
+        """hgru_pose.py:156-163: reshape(bottom, [-1, in_size]) @ weights + biases."""
+        x = self._need_cuda(bottom, "fc_layer").reshape(-1, int(in_size))
+        w, b = self.get_fc_var(int(in_size), int(out_size), name)
+        if tuple(w.shape) != (int(in_size), int(out_size)):
+            raise ValueError("%s_weights has shape %s" % (name, tuple(w.shape)))
+        out = torch.empty((int(x.shape[0]), int(out_size)), device=x.device, dtype=torch.float32)
+        _lib.check(_lib.load().layer_fc_forward(x.data_ptr(), int(x.shape[0]), int(in_size), w.data_ptr(),
+                                                b.data_ptr(), int(out_size), out.data_ptr(), _stream()),
+                   "layer_fc_forward")
+        return out
+
+    def hgru_layer(self, bottom):
+        """hgru_pose.py:107-118: ContextualCircuit(X=bottom, timesteps, SRF, SSN, SSF, strides, padding, aux).build().
+        As in the reference this is what build() of the circuit returns -- the tuple (O, weights, activities) under
+        the default return_weights=True (reference defect D4; callers take element 0)."""
+        from .hgru_module import ContextualCircuit
+        x = self._need_cuda(bottom, "hgru_layer")
+        cc = self.data_dict.get("contextual_circuit") if self.data_dict else None
+        d = self.__dict__.get("_defaults")
+        if cc is None and d is not None and "contextual_circuit/p_r" in d:
+            cc = {n: d["contextual_circuit/" + n] for n in _lib.HGRU_PARAM_ORDER}
+        layer = ContextualCircuit(X=x, timesteps=self.timesteps, SRF=self.SRF, SSN=self.SSN, SSF=self.SSF,
+                                  strides=self.strides, padding=self.padding, aux=self.aux, params=cc,
+                                  hidden_state=self.hidden_state, compute_mode=self.compute_mode, seed=self.seed)
+        return layer.build()
+
+    def batch_normalization(self, inputs, index, training, relu_first=False, dropout_keep=1.0):
+        """tf.layers.batch_normalization(inputs, axis=last, momentum=.997, epsilon=1e-5, center, scale, training,
+        fused=True) as hgru_pose.py:52-103 calls it; `index` 0..4 = scope batch_normalization, _1 .. _4.  In training
+        mode the batch statistics normalise and `self.updated_moving_stats[scope]` receives the moving statistics the
+        reference's UPDATE_OPS would assign (train_cnn_networks_hgru.py:123-126)."""
+        x = self._need_cuda(inputs, "batch_normalization")
+        C = int(x.shape[-1])
+        scope = BN_SCOPES[index]
+        bn = init.bn_identity(C)
+        g, b, mu, var = [self.get_var(self._default("%s/%s" % (scope, f), lambda f=f: bn[f]), scope, i, f)
+                         for i, f in enumerate(_BN_FIELDS)]
+        for t in (g, b, mu, var):
+            if t.numel() != C:
+                raise ValueError("%s variables must have %d elements" % (scope, C))
+        rows = x.numel() // C
+        y = torch.empty_like(x)
+        new_mu = new_var = ws = None
+        if training:
+            new_mu, new_var = torch.empty_like(mu), torch.empty_like(var)
+            ws = torch.empty(2 * C, device=x.device, dtype=torch.float64)
+        _lib.check(_lib.load().layer_batch_norm_forward(
+            x.data_ptr(), rows, C, g.data_ptr(), b.data_ptr(), mu.data_ptr(), var.data_ptr(),
+            float(self._BATCH_NORM_EPSILON), 1 if training else 0, 1 if relu_first else 0, float(dropout_keep),
+            int(self.dropout_seed), float(self._BATCH_NORM_DECAY),
+            new_mu.data_ptr() if training else None, new_var.data_ptr() if training else None,
+            ws.data_ptr() if training else None, y.data_ptr(), _stream()), "layer_batch_norm_forward")
+        if training:
+            self.updated_moving_stats[scope] = {"moving_mean": new_mu, "moving_variance": new_var}
+        return y
+
     # -- forward -----------------------------------------------------------------------------
+    def _build_layerwise(self, depth, output_shape, train_mode):
+        """hgru_pose.py:47-105 statement by statement on the layer methods (R-D4, R-D5, R-D6 applied)."""
+        C = self.channels
+        self.updated_moving_stats = {}
+        x = self._need_cuda(depth, "build(train_mode=True)")
+        self.conv1 = self.conv_layer(x, int(x.shape[-1]), C, "conv_1", filter_size=3)                # :50
+        self.pool1 = self.max_pool(self.conv1, 'pool_1')                                             # :51
+        self.pool1 = self.batch_normalization(self.pool1, 0, train_mode)                             # :52-60
+        self.conv2 = self.conv_layer(self.pool1, C, C, "conv_2", filter_size=3)                      # :61
+        self.conv2 = self.batch_normalization(self.conv2, 1, train_mode)                             # :62-70
+        self.conv3 = self.conv_layer(self.conv2, C, C, "conv_3", filter_size=3)                      # :71
+        self.conv3 = self.batch_normalization(self.conv3, 2, train_mode)                             # :72-80
+        hg = self.hgru_layer(self.conv3)                                                             # :81
+        self.hgru = hg[0] if isinstance(hg, tuple) else hg                                           # R-D4
+        self.hgru = self.batch_normalization(self.hgru, 3, train_mode)                               # :82-90
+        in_size = int(np.prod([int(v) for v in self.hgru.shape[1:]]))
+        self.fc1 = self.fc_layer(self.hgru, in_size, self.fc_hidden, "fc_1")                         # :91
+        # relu (:92), dropout keep 0.7 when train_mode == True (:93-94), batch norm over the last axis (:95-103, R-D5)
+        self.relu1 = self.batch_normalization(self.fc1, 4, train_mode, relu_first=True,
+                                              dropout_keep=0.7 if train_mode is True else 1.0)
+        self.fc4 = self.fc_layer(self.relu1, self.fc_hidden, int(output_shape), "fc_out")            # :104 (R-D6)
+        self.out_put = self.fc4                                                                      # :105
+        self.gpu_launches = 6 + 2 * 5 + 2 + 22      # (not counted by a plan: layer kernels + the circuit's own)
+        self._lazy = {}
+        return self.out_put
+
     def build(self, depth, output_shape, batch_norm=None, train_mode=None):
         """hgru_pose.py:47-105.  `batch_norm` is accepted and ignored exactly as in the reference."""
-        if train_mode:
-            raise NotImplementedError(
-                "train_mode=True (batch statistics + dropout) is outside the forward hot path; "
-                "inference-mode batch norm only (SURVEY.md R-D7)")
         if not torch.is_tensor(depth):
             depth = torch.as_tensor(np.asarray(depth, dtype=np.float32))
         if depth.dim() != 4 or depth.shape[-1] != 1 or depth.shape[1] != depth.shape[2] or depth.shape[1] % 2:
             raise ValueError("depth must be [N, 2*HW, 2*HW, 1]")
         depth = depth.to(torch.float32).contiguous()
-        lib = _lib.load()
+        for n in _LAZY_NAMES:
+            self.__dict__.pop(n, None)
+        if self.aux.get('hidden_init', 'random') == 'identity' and self.hidden_state is None:
+            raise NotImplementedError("aux['hidden_init']='identity' is not on the path hgru_pose.py configures "
+                                      "(pass model.hidden_state explicitly)")
+        if train_mode:
+            self._need_cuda(depth, "build(train_mode=True)")
         N, hw = int(depth.shape[0]), int(depth.shape[1]) // 2
         S = 2 * (self.SSF // 2) + 1
+        complete = self.data_dict is not None and all(
+            n in self.data_dict for n in ("conv_1", "conv_2", "conv_3", "fc_1", "fc_out", "contextual_circuit") + BN_SCOPES)
+        dkey = (self.channels, S, self.timesteps, hw, self.fc_hidden, int(output_shape), self.seed)
+        if complete:
+            self._defaults, self._defaults_key = None, None
+        elif self.__dict__.get("_defaults_key") != dkey:
+            # one seeded draw of the whole graph's variables, shared by the fused and the layer-wise path
+            self._defaults = init.pose_params(channels=self.channels, S=S, T=self.timesteps, hw=hw,
+                                              fc_hidden=self.fc_hidden, out=int(output_shape), seed=self.seed)
+            self._defaults_key = dkey
+        if train_mode:
+            return self._build_layerwise(depth, output_shape, train_mode)
+        lib = _lib.load()
         mode = _lib.MODES[self.compute_mode]
         key = (torch.cuda.current_device(), N, hw, self.channels, S, self.timesteps, self.fc_hidden,
                int(output_shape), mode)
@@ -236,7 +436,13 @@ class model:
             if tuple(h0.shape) != (N, hw, hw, self.channels):
                 raise ValueError("hidden_state must be [N,%d,%d,%d]" % (hw, hw, self.channels))
         elif self.aux.get('hidden_init', 'random') == 'random':
-            h0 = _as_dev(init.hidden_init((N, hw, hw, self.channels), seed=self.seed + 7))
+            # the seeded O_0 draw is made once per shape and kept on the device (268 MB at N = 256, 64 channels)
+            hkey = (torch.cuda.current_device(), N, hw, self.channels, self.seed)
+            if self._h0_cache is None or self._h0_cache[0] != hkey:
+                self._h0_cache = (hkey, _as_dev(init.hidden_init((N, hw, hw, self.channels), seed=self.seed + 7)))
+            h0 = self._h0_cache[1]
+        elif self.aux.get('hidden_init') != 'zeros':
+            raise RuntimeError("hidden_init must be 'random', 'zeros' or 'identity'")      # hgru_module.py:891-892
         self._h0 = h0
         h0_ptr = h0.data_ptr() if h0 is not None else None
         if depth.is_cuda:
@@ -248,18 +454,30 @@ class model:
                        "pose_forward_host")
         self.gpu_launches = lib.pose_plan_launch_count(self._plan)
         act = (N, hw, hw, self.channels)
-        self._lazy = {"pool1": _Lazy(self, "pool1", act), "conv2": _Lazy(self, "conv2", act),
-                      "conv3": _Lazy(self, "conv3", act), "hgru": _Lazy(self, "hgru", act),
-                      "fc1": _Lazy(self, "fc1", (N, self.fc_hidden))}
+        self._act = {"pool1": _Lazy(self, "pool1", act), "conv2": _Lazy(self, "conv2", act),
+                     "conv3": _Lazy(self, "conv3", act), "hgru": _Lazy(self, "hgru", act),
+                     "fc1": _Lazy(self, "fc1", (N, self.fc_hidden))}
+        # attribute surface of the reference (hgru_pose.py:50-105), materialised on first access (__getattr__)
+        C = self.channels
+        dev_depth = depth
+
+        def conv1():
+            d = dev_depth if dev_depth.is_cuda else dev_depth.cuda()
+            return self.conv_layer(d, int(d.shape[-1]), C, "conv_1", filter_size=3)
+
+        self._lazy = {"conv1": conv1, "pool1": self._act["pool1"], "conv2": self._act["conv2"],
+                      "conv3": self._act["conv3"], "fc1": self._act["fc1"],
+                      # the reference re-assigns self.hgru / self.relu1 to their batch-normalised tensors (:82, :95)
+                      "hgru": lambda: self.batch_normalization(self._act["hgru"].get(), 3, False),
+                      "relu1": lambda: self.batch_normalization(self._act["fc1"].get(), 4, False, relu_first=True)}
         self.fc4 = out
         self.out_put = out
         return out
 
     def activation(self, name):
-        """Intermediate tensor of the last build() by the reference's attribute name
-        (`pool1`, `conv2`, `conv3` [post batch-norm, as in the reference], `hgru` [pre batch-norm],
-        `fc1`)."""
-        return self._lazy[name].get()
+        """Intermediate tensor of the last build() straight from the plan (`pool1`, `conv2`, `conv3` [post
+        batch-norm, as in the reference], `hgru` [PRE batch-norm: the circuit's output], `fc1`)."""
+        return self._act[name].get()
 
     def __del__(self):
         try:

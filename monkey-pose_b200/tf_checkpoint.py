@@ -52,13 +52,94 @@ def _make_crc_table():
 _CRC_TABLE = _make_crc_table()
 
 
-def crc32c(data, crc=0):
-    """CRC-32C (Castagnoli), the checksum of leveldb tables and tensor bundles."""
+def _crc32c_scalar(data, crc=0):
     c = crc ^ 0xFFFFFFFF
     tab = _CRC_TABLE
     for b in bytes(data):
         c = tab[(c ^ b) & 0xFF] ^ (c >> 8)
     return c ^ 0xFFFFFFFF
+
+
+# -- vectorised CRC for large tensors (the fc_1 matrix is hundreds of megabytes; a byte loop in Python is not an option)
+_CRC_TABLE_NP = np.array(_CRC_TABLE, dtype=np.uint32)
+_SEG = 1024          # bytes per lane
+
+
+def _zero_operator(nbytes):
+    """32x32 GF(2) matrix (32 uint32 columns) that advances a CRC register over `nbytes` zero bytes."""
+    cols = [int(_CRC_TABLE[(1 << i) & 0xFF] ^ ((1 << i) >> 8)) for i in range(32)]      # one zero byte
+
+    def mul(a, b):          # a o b: apply b, then a
+        out = []
+        for v in b:
+            r, i = 0, 0
+            while v:
+                if v & 1:
+                    r ^= a[i]
+                v >>= 1
+                i += 1
+            out.append(r)
+        return out
+    result = [1 << i for i in range(32)]
+    n = int(nbytes)
+    while n:
+        if n & 1:
+            result = mul(cols, result)
+        cols = mul(cols, cols)
+        n >>= 1
+    return np.array(result, dtype=np.uint32)
+
+
+def _apply_operator(op, v):
+    """op (32 columns) applied to an array of registers."""
+    out = np.zeros_like(v)
+    for i in range(32):
+        out ^= np.where((v >> np.uint32(i)) & np.uint32(1), op[i], np.uint32(0)).astype(np.uint32)
+    return out
+
+
+def _crc32c_numpy(buf):
+    """CRC-32C of a uint8 array: the buffer is cut into lanes of _SEG bytes whose CRCs advance together (one table
+    lookup per byte position, vectorised over the lanes); lane CRCs are then folded pairwise with the zero-byte
+    operator, crc(A || B) = Z_len(B)(crc(A)) ^ crc(B) (the identity behind zlib's crc32_combine)."""
+    n = buf.size
+    lanes = n // _SEG
+    head = n - lanes * _SEG                       # a short leading piece keeps every lane the same length
+    c0 = _crc32c_scalar(buf[:head].tobytes()) if head else None
+    seg = buf[head:].reshape(lanes, _SEG)
+    c = np.full(lanes, 0xFFFFFFFF, dtype=np.uint32)
+    for j in range(_SEG):
+        c = _CRC_TABLE_NP[(c ^ seg[:, j]) & np.uint32(0xFF)] ^ (c >> np.uint32(8))
+    c ^= np.uint32(0xFFFFFFFF)
+    # fold: after each level a lane covers twice the bytes; an odd lane out is carried in front (it is the leftmost)
+    length = _SEG
+    carry, carry_len = None, 0                    # CRC of a leading part not yet merged, and the bytes AFTER it so far
+    while c.size > 1:
+        if c.size & 1:
+            first, c = int(c[0]), c[1:]
+            if carry is None:
+                carry, carry_len = first, 0
+            else:                                  # carry || first
+                carry = int(_apply_operator(_zero_operator(length), np.array([carry], np.uint32))[0]) ^ first
+            # bytes that follow the carry are exactly the lanes left in c
+        op = _zero_operator(length)
+        c = _apply_operator(op, c[0::2]) ^ c[1::2]
+        length *= 2
+    total = int(c[0])
+    if carry is not None:                          # carry || (everything folded so far)
+        total = int(_apply_operator(_zero_operator(length), np.array([carry], np.uint32))[0]) ^ total
+    if c0 is not None:
+        total = int(_apply_operator(_zero_operator(n - head), np.array([c0], np.uint32))[0]) ^ total
+    return total
+
+
+def crc32c(data, crc=0):
+    """CRC-32C (Castagnoli), the checksum of leveldb tables and tensor bundles."""
+    if crc == 0 and isinstance(data, np.ndarray) and data.dtype == np.uint8 and data.size >= (1 << 16):
+        return _crc32c_numpy(np.ascontiguousarray(data))
+    if crc == 0 and isinstance(data, (bytes, bytearray, memoryview)) and len(data) >= (1 << 16):
+        return _crc32c_numpy(np.frombuffer(data, dtype=np.uint8))
+    return _crc32c_scalar(data, crc)
 
 
 def mask_crc(c):
@@ -317,11 +398,11 @@ def read_checkpoint(prefix, names=None, verify=True):
         raw = shards[sid][e["offset"]:e["offset"] + e["size"]]
         if raw.size != e["size"]:
             raise CheckpointError("%s: data shard is truncated" % name)
-        if verify and e["crc32c"] is not None and e["size"] <= (1 << 22):
-            # (pure-Python CRC: only small tensors are verified; the 100+ MB fc_1 matrix is not)
-            if mask_crc(crc32c(raw.tobytes())) != e["crc32c"]:
+        buf = np.array(raw)          # the one copy out of the memory map (also the returned tensor's storage)
+        if verify and e["crc32c"] is not None:
+            if mask_crc(crc32c(buf)) != e["crc32c"]:
                 raise CheckpointError("%s: tensor checksum mismatch" % name)
-        out[name] = np.frombuffer(raw.tobytes(), dtype=dt).reshape(e["shape"]).copy()
+        out[name] = buf.view(dt).reshape(e["shape"])
     if wanted is not None and wanted - set(out):
         raise KeyError("not in checkpoint: %s" % sorted(wanted - set(out)))
     return out

@@ -132,12 +132,21 @@ class tfMonkeyDetector(object):
         xend = numpy.floor((c[:, 0] * c[:, 2] / self.fx + sx / 2.) / c[:, 2] * self.fx).astype(numpy.int64)
         ystart = numpy.floor((c[:, 1] * c[:, 2] / self.fy - sy / 2.) / c[:, 2] * self.fy).astype(numpy.int64)
         yend = numpy.floor((c[:, 1] * c[:, 2] / self.fy + sy / 2.) / c[:, 2] * self.fy).astype(numpy.int64)
-        if numpy.any((xend <= 0) | (yend <= 0) | (xstart >= W) | (ystart >= H) | (xend <= xstart) | (yend <= ystart)):
-            raise ValueError("crop window does not intersect the frame")
+        # A window that misses the frame (a wild centre-of-mass prediction) must not abort the other frames of the
+        # batch: that frame gets an all-background patch (resized size 0: nothing is pasted) and is reported in
+        # `self.last_invalid`; the single-frame `_window` / `cropArea3D` raise ValueError for it.
+        bad = (xend <= 0) | (yend <= 0) | (xstart >= W) | (ystart >= H) | (xend <= xstart) | (yend <= ystart) | \
+            ~numpy.isfinite(c).all(axis=1)
+        self.last_invalid = numpy.nonzero(bad)[0]
+        if bad.any():
+            xstart, ystart = numpy.where(bad, 0, xstart), numpy.where(bad, 0, ystart)
+            xend, yend = numpy.where(bad, 1, xend), numpy.where(bad, 1, yend)
         wb, hb = xend - xstart, yend - ystart
         wide = wb > hb
         szx = numpy.where(wide, dsize[0], wb * dsize[1] // hb)
         szy = numpy.where(wide, hb * dsize[0] // wb, dsize[1])
+        if bad.any():
+            szx, szy = numpy.where(bad, 0, szx), numpy.where(bad, 0, szy)
         sc = numpy.where(hb > wb, szy / hb.astype(numpy.float64), szx / wb.astype(numpy.float64))
         xs = numpy.floor(dsize[0] / 2. - szx / 2.).astype(numpy.int64)
         ys = numpy.floor(dsize[1] / 2. - szy / 2.).astype(numpy.int64)
@@ -175,6 +184,8 @@ class tfMonkeyDetector(object):
         if com is None or docom:
             raise NotImplementedError("CoM estimation / refinement (calculateCoM) is not on the hot path: pass com")
         out, Ms, coms = self.cropArea3D_batch(dpt[None], [com], dsize=dsize)
+        if len(self.last_invalid):
+            raise ValueError("crop window does not intersect the frame")
         return out[0], Ms[0], coms[0]
 
 

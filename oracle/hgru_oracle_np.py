@@ -73,6 +73,33 @@ def batch_norm_training(x, gamma, beta, eps=1e-5):
     return (x - mean) / np.sqrt(var + eps) * gamma + beta
 
 
+def dropout_keep_mask(n, keep, seed):
+    """Keep mask of the training-mode dropout (tf.nn.dropout(x, keep), hgru_pose.py:93-94).  TensorFlow's random stream
+    cannot be reproduced, so the C ABI documents its own counter-based mask (include/hgru_b200.h,
+    layer_batch_norm_forward): element i is kept iff (splitmix64(seed ^ i * 0xD1B54A32D192ED03) >> 40) / 2^24 < keep.
+    This is that definition in numpy (uint64 arithmetic wraps)."""
+    with np.errstate(over="ignore"):
+        i = np.arange(n, dtype=np.uint64)
+        z = np.uint64(seed) ^ (i * np.uint64(0xD1B54A32D192ED03))
+        z = z + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    u = (z >> np.uint64(40)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+    return u < np.float32(keep)
+
+
+def batch_norm_moving_update(x, moving_mean, moving_var, momentum=0.997):
+    """What the reference's UPDATE_OPS assign in training mode (train_cnn_networks_hgru.py:123-126): moving statistics
+    <- moving * momentum + batch * (1 - momentum), batch variance UNBIASED (TF's fused batch norm)."""
+    x = np.asarray(x, F64)
+    ax = tuple(range(x.ndim - 1))
+    n = x.size // x.shape[-1]
+    mean, var = x.mean(axis=ax), x.var(axis=ax) * (n / max(n - 1.0, 1.0))
+    return (np.asarray(moving_mean, F64) * momentum + mean * (1 - momentum),
+            np.asarray(moving_var, F64) * momentum + var * (1 - momentum))
+
+
 # ----------------------------------------------------------------------------------------------
 # hGRU recurrent layer  (hgru_module.py)
 # ----------------------------------------------------------------------------------------------
@@ -153,13 +180,15 @@ def fc_layer(x, w, b):
     return x.reshape(x.shape[0], -1) @ np.asarray(w, F64) + np.asarray(b, F64)
 
 
-def pose_forward(depth, params, H2_init, timesteps=8, train_mode=False, eps=1e-5, trace=False):
+def pose_forward(depth, params, H2_init, timesteps=8, train_mode=False, eps=1e-5, trace=False,
+                 dropout_keep=None, dropout_seed=0):
     """hgru_pose.model.build (hgru_pose.py:47-105).
 
     depth [N,128,128,1]; params: dict keyed by the reference's variable names
     (`conv_1/conv_1_filters`, ..., `contextual_circuit/p_r`, ..., `fc_out/fc_out_biases`,
     `batch_normalization[_i]/{gamma,beta,moving_mean,moving_variance}`).
-    Dropout (hgru_pose.py:93-94) is random and excluded.
+    Dropout (hgru_pose.py:93-94) is random: excluded unless `dropout_keep` is given, in which case the documented
+    counter-based mask (dropout_keep_mask) is applied to relu(fc1) before the batch norm, as the reference orders them.
     """
     P = params
     acts = {}
@@ -174,7 +203,11 @@ def pose_forward(depth, params, H2_init, timesteps=8, train_mode=False, eps=1e-5
     hgru = hgru_forward(conv3, H2_init, hp, timesteps)                                   # :81 (R-D4)
     hgru_bn = _bn(hgru, P, BN_SCOPES[3], train_mode, eps)                                # :82-90
     fc1 = fc_layer(hgru_bn, P["fc_1/fc_1_weights"], P["fc_1/fc_1_biases"])               # :91
-    relu1 = _bn(np.maximum(fc1, 0.0), P, BN_SCOPES[4], train_mode, eps)                  # :92-103 (R-D5)
+    r = np.maximum(fc1, 0.0)                                                             # :92
+    if dropout_keep is not None and dropout_keep < 1.0:                                  # :93-94
+        keep = dropout_keep_mask(r.size, dropout_keep, dropout_seed).reshape(r.shape)
+        r = np.where(keep, r / np.float64(np.float32(dropout_keep)), 0.0)
+    relu1 = _bn(r, P, BN_SCOPES[4], train_mode, eps)                                     # :95-103 (R-D5)
     out = fc_layer(relu1, P["fc_out/fc_out_weights"], P["fc_out/fc_out_biases"])         # :104 (R-D6)
     if trace:
         acts.update(conv1=conv1, pool1=pool1, conv2=conv2, conv3=conv3, hgru=hgru,

@@ -290,8 +290,17 @@ def test_crop_stage_bit_exact_against_reference_golden():
         np.testing.assert_allclose(coms[i], z["coms_out"][i], rtol=0, atol=0)
     with pytest.raises(NotImplementedError):
         md.cropArea3D(torch.zeros(424, 512, device="cuda"), com=None)
+    # a centre of mass whose window misses the frame: that frame becomes an all-background patch, its neighbours are
+    # untouched (one wild attention prediction must not abort the batch); the single-frame call raises
+    two = torch.as_tensor(z["frames"][:2]).cuda() * 10000.0
+    good = z["coms_out"][1]
+    out, _, _ = md.cropArea3D_batch(two, [np.array([-900.0, 100.0, 1500.0]), good])
+    assert list(md.last_invalid) == [0]
+    assert torch.all(out[0] == float(md.maxDepth))
+    ref1, _, _ = md.cropArea3D_batch(two[1:], [good])
+    assert torch.equal(out[1], ref1[0]) and len(md.last_invalid) == 0
     with pytest.raises(ValueError):
-        md.cropArea3D_batch(torch.zeros(1, 424, 512, device="cuda"), [np.array([-900.0, 100.0, 1500.0])])
+        md.cropArea3D(two[0], com=np.array([-900.0, 100.0, 1500.0]))
 
 
 def test_crop_stage_vs_oracle_at_batch_size_and_feeds_the_model():

@@ -66,10 +66,14 @@ def test_model_defaults_are_the_references():
     assert m._BATCH_NORM_DECAY == 0.997 and m._BATCH_NORM_EPSILON == 1e-5
     assert m.aux["gru_gates"] and m.aux["adapation"] and m.aux["recurrent_nl"] == "tanh"
     assert m["timesteps"] == 8 and "aux" in m
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="CUDA"):          # the layer-wise training-mode forward has no CPU fallback
         m.build(torch.zeros(1, 128, 128, 1), 69, train_mode=True)
     with pytest.raises(ValueError):
         m.build(torch.zeros(1, 128, 64, 1), 69)
+    for meth in ("conv_layer", "max_pool", "fc_layer", "hgru_layer", "get_conv_var", "get_fc_var", "get_var"):
+        assert callable(getattr(m, meth))                    # hgru_pose.py:107-216
+    with pytest.raises(AttributeError):
+        m.conv1                                              # set by build(), as in the reference
 
 
 def test_param_generators_shapes_and_statistics():
