@@ -36,7 +36,11 @@ constexpr int kTileRows = 16;   // M tile = 16 rows x 8 cols of pixels
 // SPLIT3: operands carry bf16 hi and lo halves (window parts [0,KSTEPS) = hi, [KSTEPS,2*KSTEPS) = lo) and
 // every 16-channel k-step is accumulated as three products  a_hi*w_hi + a_hi*w_lo + a_lo*w_hi
 // (fp32-class accuracy from bf16 tensor cores; used for the stem, whose smooth inputs make plain bf16
-// rounding errors add up coherently).
+// rounding errors add up coherently, and for the hGRU's own convs in the bf16x3 mode).  The three products are
+// TWO instructions: the weights of the a_hi pass are [w_hi | w_lo] stacked along N (accumulator columns [0, CO) and
+// [CO, 2 CO), summed in the epilogue), the a_lo pass adds a_lo*w_hi into columns [0, CO).  An M = 128 MMA costs the
+// same shared-memory operand fetch whatever its N, so one N = 2 CO instruction replaces two N = CO ones
+// (N = 32: 35 % of the issue rate, N = 64: 67 %; profiles/r01_mma_shape_microbench.log).
 // FUSE: the 1x1 gate conv that follows the integration (G2 after H1, the next step's G1 after H2) is issued from
 // the epilogue as tcgen05.mma on a shared-memory staging tile of the new state (as in hconv_stack.cuh), and the
 // launches of a forward are chained through per-frame completion counters (TcConvArgs::wait_flags / done_flags):
@@ -44,7 +48,7 @@ constexpr int kTileRows = 16;   // M tile = 16 rows x 8 cols of pixels
 template <int S, int KSTEPS, int CO_PAD, int TILES_X, int G, int WSTAGES, bool SPLIT3 = false, bool FUSE = false>
 struct TcConvCfg {
   static constexpr int kParts = SPLIT3 ? 2 * KSTEPS : KSTEPS;      // window parts (TMA boxes / barriers)
-  static constexpr int kWSteps = SPLIT3 ? 3 * KSTEPS : KSTEPS;     // weight k-steps
+  static constexpr int kWSteps = SPLIT3 ? 2 * KSTEPS : KSTEPS;     // weight k-steps (SPLIT3: wide a_hi pass, a_lo pass)
   static constexpr int kS = S;
   static constexpr int kTaps = S * S;
   static constexpr int kPad = (S - 1) / 2;
@@ -55,9 +59,12 @@ struct TcConvCfg {
   static constexpr int kPartBytes = 2 * kChunkPitch;        // one kstep = 2 chunks
   static constexpr int kInBytes = kParts * kPartBytes;
   static constexpr int kTapBytes = 2 * CO_PAD * 16;         // one (kstep, tap) weight block
-  static constexpr int kStageBytes = G * kTapBytes;
+  static constexpr int kTapBytesWide = SPLIT3 ? 2 * kTapBytes : kTapBytes;   // [w_hi | w_lo] stacked along N
+  static constexpr int kGroupBytes = kTaps * (kTapBytesWide + kTapBytes);     // SPLIT3: both passes of a 16-channel group
+  static constexpr int kStageBytes = G * kTapBytesWide;
   static constexpr int kStagesPerKstep = kTaps / G;
-  static constexpr int kAccCols = TILES_X * CO_PAD;         // TMEM columns per accumulator set
+  static constexpr int kAccN = SPLIT3 ? 2 * CO_PAD : CO_PAD; // accumulator columns per tile
+  static constexpr int kAccCols = TILES_X * kAccN;          // TMEM columns per accumulator set
   static constexpr int kGateABytes = FUSE ? (CO_PAD / 8) * 128 * 16 : 0;   // staging tile of the new state (bf16, K-major)
   static constexpr int kGateWBytes = FUSE ? KSTEPS * 2 * CO_PAD * 16 : 0;   // packed 1x1 gate weights
   static constexpr int kGateBytes = kGateABytes + kGateWBytes;
@@ -68,7 +75,7 @@ struct TcConvCfg {
   static_assert(kSmemBytes <= 232448, "shared memory per CTA");
   static_assert(kTaps % G == 0, "taps per stage must divide S*S");
   static_assert(2 * kAccCols <= 512, "two accumulator sets must fit TMEM");
-  static_assert(CO_PAD % 16 == 0 && CO_PAD >= 16 && CO_PAD <= 256, "UMMA N constraint (M=128)");
+  static_assert(CO_PAD % 16 == 0 && CO_PAD >= 16 && kAccN <= 256, "UMMA N constraint (M=128)");
   static_assert(kChunkPitch % 16 == 0 && (kChunkPitch >> 4) < 16384, "LBO range");
 };
 
@@ -626,13 +633,18 @@ hconv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const TcConvArgs a) 
       uint32_t st = 0, ph = 0;
       for (int u = first; u < a.num_units; u += stride) {
         for (int q = 0; q < NW; ++q) {
+          // SPLIT3 layout per 16-channel group: [taps] wide blocks ([w_hi | w_lo]) then [taps] w_hi blocks
+          const bool wide = SPLIT3 && !(q & 1);
+          const uint32_t sbytes = G * (wide ? Cfg::kTapBytesWide : Cfg::kTapBytes);
           const uint8_t* src = reinterpret_cast<const uint8_t*>(a.wpk) +
-                               static_cast<size_t>(q) * Cfg::kTaps * Cfg::kTapBytes;
+                               (SPLIT3 ? static_cast<size_t>(q >> 1) * Cfg::kGroupBytes +
+                                             ((q & 1) ? static_cast<size_t>(Cfg::kTaps) * Cfg::kTapBytesWide : 0)
+                                       : static_cast<size_t>(q) * Cfg::kTaps * Cfg::kTapBytes);
           for (int sg = 0; sg < Cfg::kStagesPerKstep; ++sg) {
             mbar_wait(bar_w_empty + 8 * st, ph ^ 1);
-            mbar_arrive_expect_tx(bar_w_full + 8 * st, Cfg::kStageBytes);
-            bulk_load(w_buf + st * Cfg::kStageBytes, src + static_cast<size_t>(sg) * Cfg::kStageBytes,
-                      Cfg::kStageBytes, bar_w_full + 8 * st);
+            mbar_arrive_expect_tx(bar_w_full + 8 * st, sbytes);
+            bulk_load(w_buf + st * Cfg::kStageBytes, src + static_cast<size_t>(sg) * sbytes, sbytes,
+                      bar_w_full + 8 * st);
             if (++st == WSTAGES) { st = 0; ph ^= 1; }
           }
         }
@@ -673,10 +685,12 @@ hconv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const TcConvArgs a) 
     const bool leader = elect_one();
     const long long clk0 = a.clk_out ? clock64() : 0;
     const unsigned long long ns0 = a.clk_out ? global_timer_ns() : 0ull;
-    constexpr uint32_t idesc = make_idesc(1 /*bf16*/, 128, CO_PAD);
+    constexpr uint32_t idesc_n = make_idesc(1 /*bf16*/, 128, CO_PAD);
+    constexpr uint32_t idesc_w = make_idesc(1 /*bf16*/, 128, Cfg::kAccN);      // SPLIT3: the wide a_hi pass
     // descriptor templates: only the 14-bit start-address field changes per instruction
     const uint64_t adesc0 = make_smem_desc(in_buf, Cfg::kChunkPitch, Cfg::kRowPitch);
-    const uint64_t bdesc0 = make_smem_desc(w_buf, CO_PAD * 16, 128);
+    const uint64_t bdesc0_n = make_smem_desc(w_buf, CO_PAD * 16, 128);
+    const uint64_t bdesc0_w = make_smem_desc(w_buf, Cfg::kAccN * 16, 128);
     uint32_t st = 0, ph = 0;
     int it = 0;
     for (int u = first; u < a.num_units; u += stride, ++it) {
@@ -685,11 +699,13 @@ hconv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const TcConvArgs a) 
       mbar_wait_warp(bar_acc_empty + 8 * s, ((it >> 1) & 1) ^ 1);
       tc_fence_after();
       for (int wq = 0; wq < NW; ++wq) {
-        // window part used by weight k-step wq; SPLIT3 order per 16-channel group: (hi,w_hi) (hi,w_lo) (lo,w_hi)
-        const int q = SPLIT3 ? ((wq % 3) < 2 ? wq / 3 : KSTEPS + wq / 3) : wq;
-        const bool first_use = !SPLIT3 || (wq % 3) != 1;
-        const bool last_use = !SPLIT3 || (wq % 3) != 0;
-        if (first_use) mbar_wait_warp(bar_in_full + 8 * q, it & 1);
+        // window part used by weight k-step wq; SPLIT3 order per 16-channel group: (a_hi, [w_hi | w_lo]), (a_lo, w_hi)
+        const int q = SPLIT3 ? ((wq & 1) ? KSTEPS + (wq >> 1) : (wq >> 1)) : wq;
+        const bool wide = SPLIT3 && !(wq & 1);
+        const uint32_t idesc = wide ? idesc_w : idesc_n;
+        const uint64_t bdesc0 = wide ? bdesc0_w : bdesc0_n;
+        const uint32_t tapb = wide ? Cfg::kTapBytesWide : Cfg::kTapBytes;
+        mbar_wait_warp(bar_in_full + 8 * q, it & 1);
         const uint64_t adesc_q = adesc0 + static_cast<uint64_t>((q * Cfg::kPartBytes) >> 4);
         uint32_t tap_off = 0;            // (dy * kRowPitch + dx * 16) >> 4, advanced incrementally
         uint32_t dx = 0;
@@ -699,12 +715,12 @@ hconv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const TcConvArgs a) 
           const uint64_t bdesc_st = bdesc0 + static_cast<uint64_t>((st * Cfg::kStageBytes) >> 4);
 #pragma unroll
           for (int g = 0; g < G; ++g) {
-            const uint64_t bdesc = bdesc_st + static_cast<uint64_t>((g * Cfg::kTapBytes) >> 4);
+            const uint64_t bdesc = bdesc_st + static_cast<uint64_t>((g * tapb) >> 4);
             const uint64_t adesc_tap = adesc_q + tap_off;
             const uint32_t accum = (wq | sg | g) != 0;
 #pragma unroll
             for (int t = 0; t < TILES_X; ++t) {
-              if (leader) mma_bf16_ss(acc + t * CO_PAD, adesc_tap + static_cast<uint64_t>(t * 8), bdesc, idesc, accum);
+              if (leader) mma_bf16_ss(acc + t * Cfg::kAccN, adesc_tap + static_cast<uint64_t>(t * 8), bdesc, idesc, accum);
             }
             // next tap: dx+1, wrapping to the next filter row
             if (++dx == S) { dx = 0; tap_off += (Cfg::kRowPitch - (S - 1) * 16) >> 4; }
@@ -713,7 +729,7 @@ hconv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const TcConvArgs a) 
           if (leader) tc_commit(bar_w_empty + 8 * st);
           if (++st == WSTAGES) { st = 0; ph ^= 1; }
         }
-        if (leader && last_use) tc_commit(bar_in_empty + 8 * q);
+        if (leader) tc_commit(bar_in_empty + 8 * q);
       }
       if (leader) tc_commit(bar_acc_full + 8 * s);
     }
@@ -752,7 +768,7 @@ hconv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const TcConvArgs a) 
         const int x = ux * (8 * TILES_X) + t * 8 + pcol;
         const bool ok = (y < a.H) && (x < a.W);
         const uint32_t taddr =
-            tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + s * Cfg::kAccCols + t * CO_PAD;
+            tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + s * Cfg::kAccCols + t * Cfg::kAccN;
         if constexpr (FUSE) {
           // integration in 16-channel pieces (accumulator columns, global inputs and parameters of one piece live
           // at a time); the new state stays in registers for the gate that follows
@@ -793,7 +809,7 @@ hconv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const TcConvArgs a) 
                 const uint64_t bd = make_smem_desc(gate_w, CO_PAD * 16, 128);
 #pragma unroll
                 for (int q = 0; q < KSTEPS; ++q)
-                  mma_bf16_ss(tmem_base + s * Cfg::kAccCols + t * CO_PAD, ad + static_cast<uint64_t>((q * 2 * 2048) >> 4),
+                  mma_bf16_ss(tmem_base + s * Cfg::kAccCols + t * Cfg::kAccN, ad + static_cast<uint64_t>((q * 2 * 2048) >> 4),
                               bd + static_cast<uint64_t>((q * 2 * CO_PAD * 16) >> 4), gdesc, q != 0);
                 tc_commit(bar_gate);
               }
@@ -822,6 +838,12 @@ hconv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const TcConvArgs a) 
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j) acc[c0 + j] = __uint_as_float(v[j]);
+          if constexpr (SPLIT3) {      // + the a_hi * w_lo products accumulated in columns [CO, 2 CO)
+            tmem_ld16(taddr + CO_PAD + c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[c0 + j] += __uint_as_float(v[j]);
+          }
         }
         if (ok) Epi::template apply<CO_PAD>(a, n, y, x, acc);
         }

@@ -94,10 +94,10 @@ struct DevBuf {
 };
 
 // ---------------------------------------------------------------- tensor-core conv dispatch
-template <int S, int KSTEPS, int CO_PAD, int TILES_X, int G, class Epi, bool SPLIT3 = false>
+template <int S, int KSTEPS, int CO_PAD, int TILES_X, int G, class Epi, bool SPLIT3 = false, int WS = 4>
 int launch_tc(const CUtensorMap& map, hgru::TcConvArgs a, cudaStream_t st) {
-  using Cfg = hgru::TcConvCfg<S, KSTEPS, CO_PAD, TILES_X, G, 4, SPLIT3>;
-  auto kern = hgru::hconv_tc_kernel<S, KSTEPS, CO_PAD, TILES_X, G, 4, Epi, SPLIT3>;
+  using Cfg = hgru::TcConvCfg<S, KSTEPS, CO_PAD, TILES_X, G, WS, SPLIT3>;
+  auto kern = hgru::hconv_tc_kernel<S, KSTEPS, CO_PAD, TILES_X, G, WS, Epi, SPLIT3>;
   SMEM_ATTR_ONCE(kern, Cfg::kSmemBytes);
   a.units_x = (a.W + 8 * TILES_X - 1) / (8 * TILES_X);
   a.units_y = (a.H + hgru::kTileRows - 1) / hgru::kTileRows;
@@ -164,10 +164,19 @@ int dispatch_tc_hconv(int S, int KP, const CUtensorMap& map, const hgru::TcConvA
   TC_CASES_S(Epi, 1, 1, 1)
   return fail(HGRU_E_UNSUPPORTED, "tensor-core conv: unsupported (S, padded channels)");
 }
-// 3x3 stem convs: bf16 hi + lo operand halves, three products per k-step (SPLIT3): fp32-class accuracy
+// 3x3 stem convs: bf16 hi + lo operand halves, three products per k-step (SPLIT3): fp32-class accuracy.
+// A SPLIT3 tile owns 2 * KP accumulator columns ([w_hi | w_lo] stacked along N), so two accumulator sets hold
+// 2 / 4 / 8 tiles of 8 columns at 64 / 32 / 16 channels.
+bool stem_geometry(int KP, TcGeom* g) {
+  if (!(KP == 16 || KP == 32 || KP == 64)) return false;
+  g->tiles_x = (KP == 64) ? 2 : (KP == 32) ? 4 : 8;
+  g->box_cols = 8 * g->tiles_x + 2;
+  g->box_rows = hgru::kTileRows + 2;
+  return true;
+}
 int dispatch_tc_stem(int KP, const CUtensorMap& map, const hgru::TcConvArgs& a, cudaStream_t st) {
-  if (KP == 64) return launch_tc<3, 4, 64, 4, 3, hgru::EpiBiasReluAffine, true>(map, a, st);
-  if (KP == 32) return launch_tc<3, 2, 32, 8, 9, hgru::EpiBiasReluAffine, true>(map, a, st);
+  if (KP == 64) return launch_tc<3, 4, 64, 2, 3, hgru::EpiBiasReluAffine, true>(map, a, st);
+  if (KP == 32) return launch_tc<3, 2, 32, 4, 9, hgru::EpiBiasReluAffine, true>(map, a, st);
   if (KP == 16) return launch_tc<3, 1, 16, 8, 9, hgru::EpiBiasReluAffine, true>(map, a, st);
   return fail(HGRU_E_UNSUPPORTED, "tensor-core stem conv: unsupported padded channel count");
 }
@@ -182,7 +191,7 @@ bool x3_geometry(int S, int KP, TcGeom* g) {
 }
 template <class Epi>
 int dispatch_tc_hconv_x3(int S, int KP, const CUtensorMap& map, const hgru::TcConvArgs& a, cudaStream_t st) {
-  if (S == 15 && KP == 64) return launch_tc<15, 4, 64, 1, 5, Epi, true>(map, a, st);
+  if (S == 15 && KP == 64) return launch_tc<15, 4, 64, 1, 3, Epi, true>(map, a, st);   // (wide stages: 3 taps each)
   if (S == 15 && KP == 32) return launch_tc<15, 2, 32, 4, 5, Epi, true>(map, a, st);
   if (S == 15 && KP == 16) return launch_tc<15, 1, 16, 8, 5, Epi, true>(map, a, st);
   return fail(HGRU_E_UNSUPPORTED, "bf16x3 conv: unsupported (S, padded channels)");
@@ -1084,7 +1093,7 @@ int pose_plan_create(int N, int HW, int C, int S, int T, int F, int O, int mode,
     const size_t wb = sizeof(__nv_bfloat16) * (3 * KP / 16) * 9 * 2 * KP * 8;        // [w_hi, w_lo, w_hi] per k-step
     A(p->wpk2, wb); A(p->wpk3, wb);
     TcGeom g;
-    if (!rc && !tc_geometry(3, KP, &g)) rc = fail(HGRU_E_UNSUPPORTED, "pose_plan_create: unsupported channel count for bf16 mode");
+    if (!rc && !stem_geometry(KP, &g)) rc = fail(HGRU_E_UNSUPPORTED, "pose_plan_create: unsupported channel count for bf16 mode");
     if (!rc && (hgru::make_act_tensor_map(&p->map_pool1, p->act_pool1.p, N, 2 * KP / 8, HW, HW, g.box_cols, g.box_rows) ||
                 hgru::make_act_tensor_map(&p->map_conv2, p->act_conv2.p, N, 2 * KP / 8, HW, HW, g.box_cols, g.box_rows)))
       rc = fail(HGRU_E_CUDA, "cuTensorMapEncodeTiled failed");

@@ -805,25 +805,37 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
   wpk[i] = __float2bfloat16(v);
 }
 
-// Weight packing for the SPLIT3 tensor-core conv: per 16-channel group three blocks
-// [w_hi, w_lo, w_hi] (hi = bf16(w), lo = bf16(w - hi)); layout [3*ksteps][taps][2][co_pad][8 ci].
+// Weight packing for the SPLIT3 tensor-core conv (hi = bf16(w), lo = bf16(w - hi)): per 16-channel group q
+//   [taps][2 chunks][2*co_pad n][8 ci]   n < co_pad: w_hi[.., co = n],  n >= co_pad: w_lo[.., co = n - co_pad]   (a_hi pass)
+//   [taps][2 chunks][co_pad n][8 ci]     w_hi                                                                  (a_lo pass)
+// i.e. 3 * taps * 2 * co_pad * 8 elements per group.
 __global__ void pack_weights_split3_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wpk,
                                            int taps, int k, int ksteps, int co_pad) {
   const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-  const size_t total = static_cast<size_t>(3 * ksteps) * taps * 2 * co_pad * 8;
-  if (i >= total) return;
-  const int j = i & 7;
-  size_t r = i >> 3;
-  const int co = r % co_pad; r /= co_pad;
-  const int ch = r & 1; r >>= 1;
-  const int tap = r % taps;
-  const int wq = r / taps;
-  const int q = wq / 3, part = wq % 3;
+  const size_t group = static_cast<size_t>(3) * taps * 2 * co_pad * 8;
+  if (i >= group * ksteps) return;
+  const int q = static_cast<int>(i / group);
+  size_t r = i - q * group;
+  const size_t wide_elems = static_cast<size_t>(taps) * 2 * (2 * co_pad) * 8;
+  int tap, ch, n, j, lo;
+  if (r < wide_elems) {
+    j = r & 7; r >>= 3;
+    n = r % (2 * co_pad); r /= (2 * co_pad);
+    ch = r & 1; tap = static_cast<int>(r >> 1);
+    lo = n >= co_pad;
+    if (lo) n -= co_pad;
+  } else {
+    r -= wide_elems;
+    j = r & 7; r >>= 3;
+    n = r % co_pad; r /= co_pad;
+    ch = r & 1; tap = static_cast<int>(r >> 1);
+    lo = 0;
+  }
   const int ci = q * 16 + ch * 8 + j;
   float v = 0.f;
-  if (ci < k && co < k) v = w[(static_cast<size_t>(tap) * k + ci) * k + co];
+  if (ci < k && n < k) v = w[(static_cast<size_t>(tap) * k + ci) * k + n];
   const __nv_bfloat16 hi = __float2bfloat16(v);
-  wpk[i] = (part == 1) ? __float2bfloat16(v - __bfloat162float(hi)) : hi;
+  wpk[i] = lo ? __float2bfloat16(v - __bfloat162float(hi)) : hi;
 }
 
 }  // namespace hgru
