@@ -45,9 +45,12 @@
 
 namespace hgru {
 
-template <int KP_, int T_, int KC_, int CS_>
+// GX3: the epilogue-issued 1x1 gate conv runs on bf16 hi/lo splits too (bf16x3 mode): staging tiles for both halves
+// of the new state, gate weights as [w_hi | w_lo] stacked along N plus w_hi (the SPLIT3 packing of hconv_tc.cuh).
+template <int KP_, int T_, int KC_, int CS_, bool GX3_ = false>
 struct StackCfg {
   static constexpr int KP = KP_, T = T_, KC = KC_, CS = CS_;
+  static constexpr bool GX3 = GX3_;
   static constexpr int S = 15, PAD = 7;
   static constexpr int KSTEPS = KP / 16;
   static constexpr int CG = KP / 8;
@@ -87,8 +90,9 @@ struct StackCfg {
 #endif
   static constexpr int ACT_PAD = REM ? 7 : 0;             // zero rows on top of every operand chunk plane
   static constexpr int PASS_STAGES = REM ? (S + S / 2 + 2) : S * KSTEPS;   // weight stages per tile pair
-  static constexpr int GATE_A_BYTES = CG * 128 * 16;      // staging tile of the new state (bf16, K-major)
-  static constexpr int GATE_W_BYTES = KSTEPS * 2 * KP * 16;
+  static constexpr int GATE_A_HALF = CG * 128 * 16;       // staging tile of the new state (bf16, K-major)
+  static constexpr int GATE_A_BYTES = GATE_A_HALF * (GX3 ? 2 : 1);      // (GX3: hi tile, lo tile)
+  static constexpr int GATE_W_BYTES = KSTEPS * 2 * KP * 16 * (GX3 ? 3 : 1);
   static constexpr int GATE_BYTES = GATE_A_BYTES + GATE_W_BYTES;
   // ring depth: as deep as the 227 KB allow (pair mode: half-size stages)
 #ifdef HGRU_STACK_WSTAGES
@@ -122,8 +126,9 @@ struct StackCfg {
 // Stacked weight packing: HWIO fp32 [15][15][k][k] -> bf16 [dy][q][rank][g][2 chunks][128/CS n'][8 ci],
 // n = rank*(128/CS) + n' = s*KC + c  <->  tap dx = T*g + T-1-s, output channel c
 // (zero where dx >= 15 or c, ci >= k).  `rank` = which CTA of a pair holds that half of B.
+// `lo_part` = 1 packs the bf16 remainder  bf16(w - bf16(w))  instead (second weight set of the bf16x3 mode).
 __global__ void pack_weights_stack_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wpk,
-                                          int k, int ksteps, int T, int KC, int NG, int CS) {
+                                          int k, int ksteps, int T, int KC, int NG, int CS, int lo_part = 0) {
   const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   const size_t total = static_cast<size_t>(15) * ksteps * NG * 2 * 128 * 8;
   if (i >= total) return;
@@ -142,7 +147,8 @@ __global__ void pack_weights_stack_kernel(const float* __restrict__ w, __nv_bflo
   const int ci = q * 16 + ch * 8 + j;
   float v = 0.f;
   if (s < T && dx >= 0 && dx < 15 && c < k && ci < k) v = w[((static_cast<size_t>(dy) * 15 + dx) * k + ci) * k + c];
-  wpk[i] = __float2bfloat16(v);
+  const __nv_bfloat16 hi = __float2bfloat16(v);
+  wpk[i] = lo_part ? __float2bfloat16(v - __bfloat162float(hi)) : hi;
 }
 
 // Same for the remainder-packed schedule (StackCfg::REM, KC = 25): [stage 24][g][2 chunks][128 n'][8 j] with the
@@ -152,7 +158,7 @@ __global__ void pack_weights_stack_kernel(const float* __restrict__ w, __nv_bflo
 //   stage 22               : chunk 0 = channels 16..23 of row 14, chunk 1 = channel 24 of rows 0..7
 //   stage 23               : chunk 0 = channel 24 of rows 8..14 (+ one zero), chunk 1 = zero
 __global__ void pack_weights_stack_rem_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wpk, int k,
-                                              int T, int KC, int NG) {
+                                              int T, int KC, int NG, int lo_part = 0) {
   const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   const size_t total = static_cast<size_t>(24) * NG * 2 * 128 * 8;
   if (i >= total) return;
@@ -172,7 +178,8 @@ __global__ void pack_weights_stack_rem_kernel(const float* __restrict__ w, __nv_
   float v = 0.f;
   if (dy >= 0 && s < T && dx >= 0 && dx < 15 && c < k && ci < k)
     v = w[((static_cast<size_t>(dy) * 15 + dx) * k + ci) * k + c];
-  wpk[i] = __float2bfloat16(v);
+  const __nv_bfloat16 hi = __float2bfloat16(v);
+  wpk[i] = lo_part ? __float2bfloat16(v - __bfloat162float(hi)) : hi;
 }
 
 namespace detail {
@@ -270,7 +277,7 @@ __device__ __forceinline__ void tmem_ld_range(uint32_t taddr, float (&v)[CN]) {
 
 // MMA issue loop of the stacked kernel.  The whole warp runs it convergently (addresses and descriptors
 // stay warp-uniform); one elected lane issues the tcgen05 instructions.
-template <class Cfg, bool PROF>
+template <class Cfg, bool PROF, int WSETS = 1>
 __device__ __forceinline__ void stack_mma_issuer(const TcConvArgs& a, uint32_t tmem_base, uint32_t win,
                                                  uint32_t w_buf, uint32_t bar_win_full, uint32_t bar_win_empty,
                                                  uint32_t bar_w_full, uint32_t bar_w_empty, uint32_t bar_acc_full,
@@ -363,28 +370,36 @@ __device__ __forceinline__ void stack_mma_issuer(const TcConvArgs& a, uint32_t t
         const uint64_t dB = make_smem_desc(win + 2 * CP, RP, RP) + tile_off;                  // chunk 2 @ dy, dy+1
         const uint64_t dC = make_smem_desc(win + 2 * CP + 14 * RP, CP - 14 * RP, RP) + tile_off;   // chunk 2 @ 14 | P @ 0
         const uint64_t dD = make_smem_desc(win + 3 * CP + 8 * RP, RP, RP) + tile_off;         // P @ 8 | (zero weights)
-        for (int dy = 0; dy < Cfg::S; ++dy) issue_stage(a_tile0 + static_cast<uint64_t>((dy * RP) >> 4), dy == 0);
-        // chunk planes 0-1 are not read again by this unit: hand them to the window producer already
-        if (last_pass && leader && valid) tc_commit(bar_win_empty);
-        if (!part1_ready) {        // planes 2-3 of this unit were loading under the stages above
-          if constexpr (PROF) t0 = clock64();
-          if (valid) mbar_wait_warp(bar_win_full + 8, vit & 1);
-          if constexpr (PROF) t_win += clock64() - t0;
-          tc_fence_after();
-          part1_ready = true;
+        // (WSETS = 2: the same operand schedule twice, against the w_hi and then the w_lo weight set)
+#pragma unroll 1
+        for (int ws = 0; ws < WSETS; ++ws) {
+          const bool last_set = ws + 1 == WSETS;
+          for (int dy = 0; dy < Cfg::S; ++dy)
+            issue_stage(a_tile0 + static_cast<uint64_t>((dy * RP) >> 4), (ws | dy) == 0);
+          // chunk planes 0-1 are not read again by this unit: hand them to the window producer already
+          if (last_set && last_pass && leader && valid) tc_commit(bar_win_empty);
+          if (!part1_ready) {        // planes 2-3 of this unit were loading under the stages above
+            if constexpr (PROF) t0 = clock64();
+            if (valid) mbar_wait_warp(bar_win_full + 8, vit & 1);
+            if constexpr (PROF) t_win += clock64() - t0;
+            tc_fence_after();
+            part1_ready = true;
+          }
+          for (int i = 0; i < Cfg::S / 2; ++i) issue_stage(dB + static_cast<uint64_t>((2 * i * RP) >> 4), false);
+          issue_stage(dC, false);
+          issue_stage(dD, false);
+          if (last_set && last_pass && leader && valid) tc_commit(bar_win_empty + 8);
         }
-        for (int i = 0; i < Cfg::S / 2; ++i) issue_stage(dB + static_cast<uint64_t>((2 * i * RP) >> 4), false);
-        issue_stage(dC, false);
-        issue_stage(dD, false);
-        if (last_pass && leader && valid) tc_commit(bar_win_empty + 8);
       } else {
-        // stage order: filter row dy, then k-step q
-        for (int dy = 0; dy < Cfg::S; ++dy) {
+        // stage order: (weight set,) filter row dy, then k-step q
+#pragma unroll 1
+        for (int ws = 0; ws < WSETS; ++ws)
+          for (int dy = 0; dy < Cfg::S; ++dy) {
 #pragma unroll
-          for (int q = 0; q < Cfg::KSTEPS; ++q)
-            issue_stage(a_tile0 + static_cast<uint64_t>((dy * Cfg::ROW_PITCH + q * 2 * Cfg::CHUNK_PITCH) >> 4),
-                        (dy | q) == 0);
-        }
+            for (int q = 0; q < Cfg::KSTEPS; ++q)
+              issue_stage(a_tile0 + static_cast<uint64_t>((dy * Cfg::ROW_PITCH + q * 2 * Cfg::CHUNK_PITCH) >> 4),
+                          (ws | dy | q) == 0);
+          }
       }
       if (leader) {
         if constexpr (CS > 1) {
@@ -421,7 +436,7 @@ __device__ __forceinline__ void stack_mma_issuer(const TcConvArgs& a, uint32_t t
 // carry), fused math, stores.  Two warpgroups split the channels so that each SM sub-partition has
 // two epilogue warps to overlap TMEM / global-memory latencies; they never need to talk to each
 // other (un-stacking and the integration math are per channel).
-template <class Cfg, class Epi, int C0, int CN, bool PROF>
+template <class Cfg, class Epi, int C0, int CN, bool PROF, bool PART = false>
 __device__ __forceinline__ void stack_epilogue(const TcConvArgs& a, uint32_t tmem_base, uint32_t bar_acc_full,
                                                uint32_t bar_acc_empty, uint32_t crank, int iters, int NT,
                                                int units_per_frame, int warp, int lane, bool profile,
@@ -466,6 +481,15 @@ __device__ __forceinline__ void stack_epilogue(const TcConvArgs& a, uint32_t tme
       const size_t pin = static_cast<size_t>(y) * a.W + x;
       typename Epi::template Pre<NCH> pre;
       if (store) Epi::template load<NCH, CN>(a, n, pin, C0, pre);
+      // second launch of a two-launch (bf16x3) conv: the first launch's sums of this pixel, requested now
+      float4 part[PART ? NCH / 4 : 1];
+      if constexpr (PART) {
+        if (store) {
+#pragma unroll
+          for (int i = 0; i < NCH / 4; ++i)
+            if (4 * i < CN) part[i] = ld_stream(a.partial + quad_off(a, n, (C0 >> 2) + i, pin));
+        }
+      }
       if constexpr (PROF) e0 = clock64();
       mbar_wait(bar_acc_full + 8 * slot, (tc >> 2) & 1);
       if constexpr (PROF) { const long long t = clock64(); e_wait += t - e0; e0 = t; }
@@ -506,6 +530,18 @@ __device__ __forceinline__ void stack_epilogue(const TcConvArgs& a, uint32_t tme
       }
 #pragma unroll
       for (int c = 0; c < CN; ++c) carry[c] = nxt[c];
+      if constexpr (PART) {
+        if (store) {
+#pragma unroll
+          for (int i = 0; i < NCH / 4; ++i)
+            if (4 * i < CN) {
+              out[4 * i] += part[i].x;
+              out[4 * i + 1] += part[i].y;
+              out[4 * i + 2] += part[i].z;
+              out[4 * i + 3] += part[i].w;
+            }
+        }
+      }
       if constexpr (PROF) { const long long t = clock64(); e_tm += t - e0; e0 = t; }
       if (!(gated && j >= 1)) {
         tc_fence_before();
@@ -528,6 +564,16 @@ __device__ __forceinline__ void stack_epilogue(const TcConvArgs& a, uint32_t tme
 #pragma unroll
             for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(hv[8 * i + 2 * q], hv[8 * i + 2 * q + 1]);
             *reinterpret_cast<uint4*>(stg + ((C0 >> 3) + i) * 2048 + m * 16) = *reinterpret_cast<const uint4*>(h);
+            if constexpr (Cfg::GX3) {      // the bf16 remainders, as a second tile
+              __nv_bfloat162 l[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float2 hf = __bfloat1622float2(h[q]);
+                l[q] = __floats2bfloat162_rn(hv[8 * i + 2 * q] - hf.x, hv[8 * i + 2 * q + 1] - hf.y);
+              }
+              *reinterpret_cast<uint4*>(stg + Cfg::GATE_A_HALF + ((C0 >> 3) + i) * 2048 + m * 16) =
+                  *reinterpret_cast<const uint4*>(l);
+            }
           }
         }
         if constexpr (PROF) { const long long t = clock64(); e_fin += t - e0; e0 = t; }
@@ -541,11 +587,26 @@ __device__ __forceinline__ void stack_epilogue(const TcConvArgs& a, uint32_t tme
           if (leader) {
             constexpr uint32_t gdesc = make_idesc(1, 128, KP);
             const uint64_t ad = make_smem_desc(gate_a, 2048, 128);
-            const uint64_t bd = make_smem_desc(gate_w, KP * 16, 128);
+            if constexpr (Cfg::GX3) {
+              // hi * [w_hi | w_lo] -> columns [0, 2 KP), then lo * w_hi added into columns [0, KP)
+              constexpr uint32_t gdesc_w = make_idesc(1, 128, 2 * KP);
+              const uint64_t ad_lo = make_smem_desc(gate_a + Cfg::GATE_A_HALF, 2048, 128);
+              const uint64_t bd_w = make_smem_desc(gate_w, 2 * KP * 16, 128);
+              const uint64_t bd_n = make_smem_desc(gate_w + 4 * KP * 16, KP * 16, 128);
 #pragma unroll
-            for (int q = 0; q < Cfg::KSTEPS; ++q)
-              mma_bf16_ss(tmem_base + slot * Cfg::NPAD, ad + static_cast<uint64_t>((q * 2 * 2048) >> 4),
-                          bd + static_cast<uint64_t>((q * 2 * KP * 16) >> 4), gdesc, q != 0);
+              for (int q = 0; q < Cfg::KSTEPS; ++q) {
+                mma_bf16_ss(tmem_base + slot * Cfg::NPAD, ad + static_cast<uint64_t>((q * 2 * 2048) >> 4),
+                            bd_w + static_cast<uint64_t>((q * 6 * KP * 16) >> 4), gdesc_w, q != 0);
+                mma_bf16_ss(tmem_base + slot * Cfg::NPAD, ad_lo + static_cast<uint64_t>((q * 2 * 2048) >> 4),
+                            bd_n + static_cast<uint64_t>((q * 6 * KP * 16) >> 4), gdesc, 1u);
+              }
+            } else {
+              const uint64_t bd = make_smem_desc(gate_w, KP * 16, 128);
+#pragma unroll
+              for (int q = 0; q < Cfg::KSTEPS; ++q)
+                mma_bf16_ss(tmem_base + slot * Cfg::NPAD, ad + static_cast<uint64_t>((q * 2 * 2048) >> 4),
+                            bd + static_cast<uint64_t>((q * 2 * KP * 16) >> 4), gdesc, q != 0);
+            }
             tc_commit(bar_gate);
           }
           __syncwarp();
@@ -557,6 +618,15 @@ __device__ __forceinline__ void stack_epilogue(const TcConvArgs& a, uint32_t tme
         float gacc[NCH];
 #pragma unroll
         for (int c = 0; c < NCH; c += 8) detail::tmem_ld_f<8>(taddr + c, gacc + c);   // columns C0 + c of the slot
+        if constexpr (Cfg::GX3) {      // + the hi * w_lo products in columns [KP, 2 KP)
+#pragma unroll
+          for (int c = 0; c < NCH; c += 8) {
+            float g2[8];
+            detail::tmem_ld_f<8>(taddr + KP + c, g2);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) gacc[c + j] += g2[j];
+          }
+        }
         tc_fence_before();
         if (CS > 1 && crank != 0) mbar_arrive_cluster(lead_acc_empty + 8 * slot);
         else mbar_arrive(bar_acc_empty + 8 * slot);
@@ -585,12 +655,13 @@ __device__ __forceinline__ void stack_epilogue(const TcConvArgs& a, uint32_t tme
   }
 }
 
-template <int KP, int T, int KC, int CS, class Epi, bool PROF = false>
-__global__ void __launch_bounds__((StackCfg<KP, T, KC, CS>::NTHREADS), 1)
+template <int KP, int T, int KC, int CS, class Epi, bool PROF = false, int WSETS = 1, bool PART = false,
+          bool GX3 = false>
+__global__ void __launch_bounds__((StackCfg<KP, T, KC, CS, GX3>::NTHREADS), 1)
 hconv_stack_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap w_map,
                    const TcConvArgs a) {
   using namespace sm100;
-  using Cfg = StackCfg<KP, T, KC, CS>;
+  using Cfg = StackCfg<KP, T, KC, CS, GX3>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t win = base;
@@ -679,7 +750,7 @@ hconv_stack_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
       for (int it = 0; it < iters; ++it) {
         if (CS == 1 && it * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x) >= a.num_units) break;
         for (int pr = 0; pr < npairs; ++pr)
-          for (int sg = 0; sg < Cfg::PASS_STAGES; ++sg) {
+          for (int sg = 0; sg < Cfg::PASS_STAGES * WSETS; ++sg) {
             mbar_wait(bar_w_empty + 8 * st, ph ^ 1);
             if constexpr (CS > 1) {
               // both halves complete their bytes on the leader's barrier
@@ -740,7 +811,7 @@ hconv_stack_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
     // ---------------- MMA issuer (convergent warp, one elected lane issues) ----------------
     const long long clk0 = a.clk_out ? clock64() : 0;
     const unsigned long long ns0 = a.clk_out ? global_timer_ns() : 0ull;
-    stack_mma_issuer<Cfg, PROF>(a, tmem_base, win, w_buf, bar_win_full, bar_win_empty, bar_w_full, bar_w_empty,
+    stack_mma_issuer<Cfg, PROF, WSETS>(a, tmem_base, win, w_buf, bar_win_full, bar_win_empty, bar_w_full, bar_w_empty,
                                 bar_acc_full, bar_acc_empty, iters, NT, npairs);
     if (a.clk_out && lane == 0) {      // cycles / nanoseconds of this CTA's MMA loop = its SM clock in GHz
       a.clk_out[2 * blockIdx.x] = static_cast<unsigned long long>(clock64() - clk0);
@@ -753,7 +824,7 @@ hconv_stack_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
     ae.rho_t = par + 5 * KP;
     // ---------------- epilogue: NGRP warpgroups, 8-channel chunks each, the last one takes the rest ----------
 #define HGRU_STACK_EPI(C0_, CN_, FIRST_)                                                                          \
-  stack_epilogue<Cfg, Epi, C0_, CN_, PROF>(ae, tmem_base, bar_acc_full, bar_acc_empty, crank, iters, NT,           \
+  stack_epilogue<Cfg, Epi, C0_, CN_, PROF, PART>(ae, tmem_base, bar_acc_full, bar_acc_empty, crank, iters, NT,           \
                                            units_per_frame, warp, lane, FIRST_, smem_raw, gate_a, gate_w, bar_gate)
     if constexpr (Cfg::NGRP == 4) {
       if (warp < 8) HGRU_STACK_EPI(0, 8, true);

@@ -118,9 +118,16 @@ struct TcConvArgs {
   // the stacked kernel (StackCfg::REM): act_pad zero rows on top of every chunk plane, and the last chunk
   // holds channel KP-8 at the 8 rows y..y+7.  0 = plain chunked layout.
   int act_pad;
-  // operand tensors written by this launch carry bf16 hi AND lo halves (chunk planes [0,CG) and [CG,2CG)):
-  // the SPLIT3 kernels of the bf16x3 mode read both (mutually exclusive with act_pad)
+  // operand tensors written by this launch carry bf16 hi AND lo halves.  1: chunk planes [0,CG) and [CG,2CG) of one
+  // tensor (the SPLIT3 kernels of hconv_tc.cuh read both through one window; not with act_pad).  2: two separate
+  // tensors in the stacked kernel's layout (act_pad honoured), the lo tensor lo_off elements behind the hi one (the
+  // bf16x3 mode on the tap-stacked kernel reads them in two launches).
   int split_out;
+  size_t lo_off;
+  // bf16x3 on the tap-stacked kernel: the conv is two launches.  The first (EpiPartial, a_hi window, weight sets
+  // w_hi then w_lo accumulated in TMEM) writes its un-stacked fp32 sums to `out`; the second (a_lo window, w_hi) adds
+  // them back from `partial` before the integration epilogue.  nullptr: the ordinary single launch.
+  const float* partial;
   // Launch chaining (stacked kernel): per-frame completion counters.  A unit of frame n may touch that frame's
   // tensors once wait_flags[n] == flag_target (all units of the frame finished in the previous launch), and adds 1
   // to done_flags[n] when its own stores are out.  nullptr = ordinary stream order.
@@ -207,6 +214,8 @@ __device__ __forceinline__ void store_chunk_bf16(__nv_bfloat16* base, int KP, in
 // Operand store that honours TcConvArgs::act_pad (remainder-packed layout, see StackCfg::REM): chunk planes
 // have act_pad zero rows on top; the last chunk is the row-packed plane P[y][x][j] = v(y + j, x) of channel
 // KP - 8, so this pixel's value goes to the 8 planes rows y - j (j = 0..7), element j.
+__device__ __forceinline__ void store_act_chunk1(const TcConvArgs& a, __nv_bfloat16* base, int n, int cg,
+                                                 size_t pin, const float* r);
 __device__ __forceinline__ void store_act_chunk(const TcConvArgs& a, __nv_bfloat16* base, int n, int cg,
                                                 size_t pin, const float* r) {
   if (a.split_out) {
@@ -216,10 +225,19 @@ __device__ __forceinline__ void store_act_chunk(const TcConvArgs& a, __nv_bfloat
       hi[j] = __bfloat162float(__float2bfloat16(r[j]));
       lo[j] = r[j] - hi[j];
     }
+    if (a.split_out == 2) {      // two tensors in the stacked kernel's own layout
+      store_act_chunk1(a, base, n, cg, pin, hi);
+      store_act_chunk1(a, base + a.lo_off, n, cg, pin, lo);
+      return;
+    }
     store_chunk_bf16(base, 2 * a.KP, a.H * a.W, n, cg, pin, hi);
     store_chunk_bf16(base, 2 * a.KP, a.H * a.W, n, (a.KP >> 3) + cg, pin, lo);
     return;
   }
+  store_act_chunk1(a, base, n, cg, pin, r);
+}
+__device__ __forceinline__ void store_act_chunk1(const TcConvArgs& a, __nv_bfloat16* base, int n, int cg,
+                                                 size_t pin, const float* r) {
   if (a.act_pad == 0) {
     store_chunk_bf16(base, a.KP, a.H * a.W, n, cg, pin, r);
     return;
@@ -264,6 +282,23 @@ struct EpiBias {
                                                float (&acc)[CO_PAD]) {
     Pre<CO_PAD> p;
     finish<CO_PAD>(a, n, static_cast<size_t>(y) * a.W + x, 0, acc, p);
+  }
+};
+// out = acc: the raw fp32 sums of a partial convolution (first launch of a two-launch bf16x3 conv on the stacked kernel)
+struct EpiPartial {
+  static constexpr bool kGate = false;
+  template <int NCH> struct Pre {};
+  template <int NCH, int NREAL = NCH>
+  __device__ static __forceinline__ void load(const TcConvArgs&, int, size_t, int, Pre<NCH>&) {}
+  template <int NCH, int NREAL = NCH>
+  __device__ static __forceinline__ void gate(const TcConvArgs&, int, size_t, int, const float*, const float*) {}
+  template <int NCH, int NREAL = NCH>
+  __device__ static __forceinline__ void finish(const TcConvArgs& a, int n, size_t pin, int c0,
+                                                const float* acc, const Pre<NCH>&, float* = nullptr) {
+#pragma unroll
+    for (int c = 0; c < NCH; c += 4)
+      if (c < NREAL)
+        st_stream(a.out + quad_off(a, n, (c0 + c) >> 2, pin), make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]));
   }
 };
 // out = relu(acc + bias) * scale + shift  (conv_layer + inference batch-norm, hgru_pose.py:61-80),

@@ -218,10 +218,14 @@ bool stack_geometry(int S, int KP, int k, StackGeom* g) {
   return true;
 }
 
-template <int KP, int T, int KC, class Epi>
+template <int KP, int T, int KC, class Epi, int WSETS = 1, bool PART = false>
 int launch_stack(const CUtensorMap& map, hgru::TcConvArgs a, cudaStream_t st) {
-  using Cfg = hgru::StackCfg<KP, T, KC, 1>;
-  auto kern = hgru::hconv_stack_kernel<KP, T, KC, 1, Epi>;
+  // The second launch of a bf16x3 conv (PART) is also the one whose epilogue issues the gate, on hi/lo splits (GX3)
+  // -- except at 32 channels, where the two staging tiles do not fit next to a 3-stage weight ring: that
+  // configuration keeps its gates in the exact SIMT kernel.
+  constexpr bool GX3 = PART && !(KP == 32 && T == 4);
+  using Cfg = hgru::StackCfg<KP, T, KC, 1, GX3>;
+  auto kern = hgru::hconv_stack_kernel<KP, T, KC, 1, Epi, false, WSETS, PART, GX3>;
   SMEM_ATTR_ONCE(kern, Cfg::SMEM_BYTES);
   a.units_x = (a.W + 63) / 64;
   a.units_y = (a.H + hgru::kTileRows - 1) / hgru::kTileRows;
@@ -242,11 +246,11 @@ int launch_stack(const CUtensorMap& map, hgru::TcConvArgs a, cudaStream_t st) {
   return 0;
 }
 
-template <class Epi>
+template <class Epi, int WSETS = 1, bool PART = false>
 int dispatch_stack(int KP, int T, const CUtensorMap& map, const hgru::TcConvArgs& a, cudaStream_t st) {
-  if (KP == 32 && T == 5) return launch_stack<32, 5, 25, Epi>(map, a, st);
-  if (KP == 32 && T == 4) return launch_stack<32, 4, 32, Epi>(map, a, st);
-  if (KP == 16 && T == 8) return launch_stack<16, 8, 16, Epi>(map, a, st);
+  if (KP == 32 && T == 5) return launch_stack<32, 5, 25, Epi, WSETS, PART>(map, a, st);
+  if (KP == 32 && T == 4) return launch_stack<32, 4, 32, Epi, WSETS, PART>(map, a, st);
+  if (KP == 16 && T == 8) return launch_stack<16, 8, 16, Epi, WSETS, PART>(map, a, st);
   return fail(HGRU_E_UNSUPPORTED, "stacked conv: unsupported configuration");
 }
 
@@ -373,6 +377,8 @@ struct hgru_plan_s {
   bool chain = false;
   int group_frames = 0;             // chained launches walk the batch in groups of this many frames (0 = whole batch)
   CUtensorMap mapA, mapH1;          // SxS halo-window boxes (horizontal convs)
+  CUtensorMap mapA_lo, mapH1_lo;    // bf16x3 on the stacked kernel: the lo halves are tensors of their own
+  size_t lo_off = 0;                // ... lo_off elements behind the hi tensors
   CUtensorMap mapH1_g, mapH2_g;     // 1x1 boxes (gate convs)
   // readout operand emitted by the last H2 epilogue (set by the pose plan; nullptr for the bare layer)
   __nv_bfloat16* fc_a = nullptr;
@@ -422,6 +428,42 @@ static int hgru_plan_init(hgru_plan_s* p, int N, int H, int W, int k, int S, int
         (rc = p->p_r.alloc(sizeof(float) * S * S * p->KP * p->KP)))
       return rc;
   } else if (mode == HGRU_MODE_BF16X3) {
+    StackGeom sg;
+    const char* ns = getenv("HGRU_X3_NO_STACK");      // development switch: the hconv_tc SPLIT3 kernel at every width
+    if (stack_geometry(S, p->KP, k, &sg) && !(ns && ns[0] == '1')) {
+      // Narrow layers: the tap-stacked kernel, two launches per conv.  The first reads the a_lo operand against w_hi
+      // and leaves fp32 sums in C; the second reads a_hi against the weight sets w_hi and w_lo (accumulated in TMEM),
+      // adds C and runs the integration epilogue -- the launch with the heavy epilogue is the one with twice the MMAs
+      // to hide it behind.  Operands are two tensors (hi, lo) in the stacked kernel's layout.
+      p->stacked = true;
+      p->stack_T = sg.T;
+      p->act_pad = sg.act_pad;
+      const int HA = H + p->act_pad;
+      const size_t tb = static_cast<size_t>(N) * p->CG * HA * W * 8 * sizeof(__nv_bfloat16);
+      p->lo_off = tb / sizeof(__nv_bfloat16);
+      if ((rc = p->actA.alloc(2 * tb)) || (rc = p->actH1.alloc(2 * tb)) || (rc = p->C.alloc(act))) return rc;
+      CUDA_TRY(cudaMemset(p->actA.p, 0, 2 * tb));
+      CUDA_TRY(cudaMemset(p->actH1.p, 0, 2 * tb));
+      const size_t set = sizeof(__nv_bfloat16) * sg.stages * sg.NG * 2 * 128 * 8;
+      if ((rc = p->wpk.alloc(2 * set))) return rc;
+      // 1x1 gate weights in the SPLIT3 packing ([w_hi | w_lo] wide block + w_hi per 16 input channels)
+      const size_t gw = sizeof(__nv_bfloat16) * 3 * (p->KP / 16) * 2 * p->KP * 8;
+      if ((rc = p->wpk_i.alloc(gw)) || (rc = p->wpk_o.alloc(gw))) return rc;
+      {
+        const char* nc = getenv("HGRU_NO_CHAIN");
+        p->chain = !(nc && nc[0] == '1');
+        if (p->chain && (rc = p->flags.alloc(sizeof(int) * 4 * static_cast<size_t>(T) * N))) return rc;
+      }
+      const int box_chunks = sg.act_pad ? p->CG / 2 : p->CG;
+      char* a0 = static_cast<char*>(p->actA.p);
+      char* h0 = static_cast<char*>(p->actH1.p);
+      if (hgru::make_act_tensor_map(&p->mapA, a0, N, p->CG, HA, W, sg.box_cols, sg.box_rows, box_chunks) ||
+          hgru::make_act_tensor_map(&p->mapA_lo, a0 + tb, N, p->CG, HA, W, sg.box_cols, sg.box_rows, box_chunks) ||
+          hgru::make_act_tensor_map(&p->mapH1, h0, N, p->CG, HA, W, sg.box_cols, sg.box_rows, box_chunks) ||
+          hgru::make_act_tensor_map(&p->mapH1_lo, h0 + tb, N, p->CG, HA, W, sg.box_cols, sg.box_rows, box_chunks))
+        return fail(HGRU_E_CUDA, "cuTensorMapEncodeTiled failed");
+      return 0;
+    }
     TcGeom g;
     if (!x3_geometry(S, p->KP, &g))
       return fail(HGRU_E_UNSUPPORTED, "hgru_plan_create: bf16x3 mode supports S = 15 and k <= 64");
@@ -509,6 +551,20 @@ static int hgru_set_params_impl(hgru_plan_s* p, const float* p_r, const float* i
   const int taps = p->S * p->S;
   if (p->mode == HGRU_MODE_FP32) {
     pad_hwio_kernel<<<nblk(static_cast<size_t>(taps) * KP * KP), 256, 0, st>>>(p_r, p->p_r.as<float>(), taps, k, KP);
+  } else if (p->mode == HGRU_MODE_BF16X3 && p->stacked) {
+    StackGeom sg;
+    stack_geometry(p->S, KP, k, &sg);
+    const size_t ts = static_cast<size_t>(sg.stages) * sg.NG * 2 * 128 * 8;      // elements of one weight set
+    for (int part = 0; part < 2; ++part) {      // set 0 = bf16(w), set 1 = bf16(w - bf16(w))
+      __nv_bfloat16* dst = p->wpk.as<__nv_bfloat16>() + part * ts;
+      if (sg.act_pad)
+        hgru::pack_weights_stack_rem_kernel<<<nblk(ts), 256, 0, st>>>(p_r, dst, k, sg.T, sg.KC, sg.NG, part);
+      else
+        hgru::pack_weights_stack_kernel<<<nblk(ts), 256, 0, st>>>(p_r, dst, k, sg.ksteps, sg.T, sg.KC, sg.NG, 1, part);
+    }
+    const size_t tg = static_cast<size_t>(3 * (KP / 16)) * 2 * KP * 8;
+    hgru::pack_weights_split3_kernel<<<nblk(tg), 256, 0, st>>>(i_r, p->wpk_i.as<__nv_bfloat16>(), 1, k, KP / 16, KP);
+    hgru::pack_weights_split3_kernel<<<nblk(tg), 256, 0, st>>>(o_r, p->wpk_o.as<__nv_bfloat16>(), 1, k, KP / 16, KP);
   } else if (p->mode == HGRU_MODE_BF16X3) {
     const int ksteps = KP / 16;
     const size_t total = static_cast<size_t>(3 * ksteps) * taps * 2 * KP * 8;
@@ -748,6 +804,89 @@ static int hgru_run_bf16x3(hgru_plan_s* p, const float* Xp, const float* H2_init
   hgru::TcConvArgs base{};
   base.N = p->N; base.H = p->H; base.W = p->W; base.KP = KP; base.kreal = p->k;
   base.split_out = 1;
+  if (p->stacked) {
+    // ---- narrow layers: the tap-stacked kernel, two launches per conv (see hgru_plan_init) ----
+    base.split_out = 2; base.lo_off = p->lo_off; base.act_pad = p->act_pad;
+    // Launches are chained per frame like the bf16 path's (4 per timestep here); not with traces, and not where the
+    // gates are separate SIMT launches (32 channels, see launch_stack).
+    const bool fused_gate = !(KP == 32 && p->stack_T == 4);
+    const bool chain = fused_gate && p->chain && !H1_trace && !H2_trace;
+    int* flags = chain ? p->flags.as<int>() : nullptr;
+    if (chain) CUDA_TRY(cudaMemsetAsync(flags, 0, p->flags.bytes, st));
+    auto set_flags = [&](hgru::TcConvArgs& a, int l) {
+      if (!chain) return;
+      a.done_flags = flags + static_cast<size_t>(l) * p->N;
+      a.wait_flags = l > 0 ? flags + static_cast<size_t>(l - 1) * p->N : nullptr;
+    };
+    auto gate_in = [&]() {
+      // circuit_input gate (hgru_module.py:696-711), exact fp32: operand A = split(sigmoid(H2 *1x1 i_r + i_b) . H2)
+      hgru::gate_quad_split_kernel<<<nblk(p->npix, hgru::kInitPix), 256, gsmem, st>>>(
+          p->H2.as<float>(), p->i_r.as<float>(), p->vec(V_IB), nullptr, p->actA.as<__nv_bfloat16>(), p->npix, p->k,
+          KP, HW, p->lo_off, p->W, p->act_pad);
+      ++p->launches;
+    };
+    gate_in();      // first timestep; with fused gates the later ones come from the H2 launch's epilogue
+    if (chain) p->timer.begin(st);
+    for (int t = 0; t < p->T; ++t) {
+      if (!fused_gate && t > 0) gate_in();
+      // C1 conv (:714-718, 657): a_lo * w_hi -> C, then a_hi * (w_hi, w_lo) + C + input_integration (:795-804) -> H1
+      // [fused: + circuit_output gate (:729-740) on hi/lo splits of H1 -> G2]
+      if (!chain) p->timer.begin(st);
+      hgru::TcConvArgs a = base;
+      a.wpk = p->wpk.as<__nv_bfloat16>(); a.out = p->C.as<float>();
+      set_flags(a, 4 * t);
+      if ((rc = dispatch_stack<hgru::EpiPartial, 1>(KP, p->stack_T, p->mapA_lo, a, st))) return rc;
+      a = base;
+      a.wpk = p->wpk.as<__nv_bfloat16>(); a.partial = p->C.as<float>();
+      a.bias = p->vec(V_LBIAS); a.X = Xp; a.H2 = p->H2.as<float>(); a.v0 = p->vec(V_BETA); a.v1 = p->vec(V_NU);
+      a.out = p->H1.as<float>(); a.out_bf16 = p->actH1.as<__nv_bfloat16>();
+      a.gate_wpk = p->wpk_o.as<__nv_bfloat16>(); a.gate_bias = p->vec(V_OB); a.gate_out = p->G.as<float>();
+      a.do_gate = fused_gate ? 1 : 0;
+      set_flags(a, 4 * t + 1);
+      if ((rc = dispatch_stack<hgru::EpiH1, 2, true>(KP, p->stack_T, p->mapA, a, st))) return rc;
+      if (!chain) p->timer.end(st);
+      if (!fused_gate) {
+        // circuit_output gate (:729-740): G2 = sigmoid(H1 *1x1 o_r + o_b), exact fp32
+        hgru::gate_quad_split_kernel<<<nblk(p->npix, hgru::kInitPix), 256, gsmem, st>>>(
+            p->H1.as<float>(), p->o_r.as<float>(), p->vec(V_OB), p->G.as<float>(), nullptr, p->npix, p->k, KP, HW);
+        ++p->launches;
+      }
+      // C2 conv (:746-750, 657) + output_integration + rho (:806-823, 847-849) -> H2 in place
+      // [fused: + the next timestep's circuit_input gate -> operand A (hi, lo)]
+      if (!chain) p->timer.begin(st);
+      a = base;
+      a.wpk = p->wpk.as<__nv_bfloat16>(); a.out = p->C.as<float>();
+      set_flags(a, 4 * t + 2);
+      if ((rc = dispatch_stack<hgru::EpiPartial, 1>(KP, p->stack_T, p->mapH1_lo, a, st))) return rc;
+      a = base;
+      a.wpk = p->wpk.as<__nv_bfloat16>(); a.partial = p->C.as<float>();
+      a.bias = p->vec(V_LBIAS); a.H1 = p->H1.as<float>(); a.G = p->G.as<float>(); a.H2 = p->H2.as<float>();
+      a.v0 = p->vec(V_GAMMA); a.v1 = p->vec(V_KAPPA); a.v2 = p->vec(V_OMEGA);
+      a.rho_t = p->rho.as<float>() + t;
+      a.gate_wpk = p->wpk_i.as<__nv_bfloat16>(); a.gate_bias = p->vec(V_IB);
+      a.gate_act_out = p->actA.as<__nv_bfloat16>();
+      a.do_gate = (fused_gate && t + 1 < p->T) ? 1 : 0;
+      if (t + 1 == p->T && p->fc_a) {
+        a.fc_a = p->fc_a; a.fc_scale = p->fc_scale; a.fc_shift = p->fc_shift; a.fc_kpad = p->fc_kpad;
+      }
+      set_flags(a, 4 * t + 3);
+      if ((rc = dispatch_stack<hgru::EpiH2, 2, true>(KP, p->stack_T, p->mapH1, a, st))) return rc;
+      if (!chain) p->timer.end(st);
+      else if (t + 1 == p->T) p->timer.end(st, 2 * p->T);      // chained: one interval, counted as 2T convs
+      p->launches += 4;
+      if (H1_trace) {
+        hgru::quad_to_nhwc_kernel<<<nblk(p->npix * p->k), 256, 0, st>>>(
+            p->H1.as<float>(), H1_trace + static_cast<size_t>(t) * p->npix * p->k, p->npix, p->k, KP, HW);
+        ++p->launches;
+      }
+      if (H2_trace) {
+        hgru::quad_to_nhwc_kernel<<<nblk(p->npix * p->k), 256, 0, st>>>(
+            p->H2.as<float>(), H2_trace + static_cast<size_t>(t) * p->npix * p->k, p->npix, p->k, KP, HW);
+        ++p->launches;
+      }
+    }
+    return 0;
+  }
   for (int t = 0; t < p->T; ++t) {
     // circuit_input gate (hgru_module.py:696-711): operand A = split(sigmoid(H2 *1x1 i_r + i_b) . H2)
     hgru::gate_quad_split_kernel<<<nblk(p->npix, hgru::kInitPix), 256, gsmem, st>>>(

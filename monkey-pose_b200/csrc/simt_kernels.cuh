@@ -554,10 +554,27 @@ init_state_gate_kernel(const float* __restrict__ h0 /*[npix][k] or nullptr = zer
 //                                  out_act = bf16 hi | lo of g . in   when out_act != nullptr  (gated operand)
 // Same tiling as init_state_gate_kernel: 256 pixels per block, thread = 4 pixels x 8 output channels.
 // ------------------------------------------------------------------------------------------------
+// `lo_off` > 0: the operand goes to TWO tensors in the tap-stacked kernel's layout instead (hi at out_act, lo lo_off
+// elements behind it; `act_pad` zero rows on top of every chunk plane of width W, and with act_pad > 0 the last chunk
+// is the row-packed plane P[y][x][j] = v(y + j, x) of channel KP - 8: see StackCfg::REM in hconv_stack.cuh).
+__device__ __forceinline__ void st8_stacked(__nv_bfloat16* base, int n, int cg, int CG, size_t pin, int HW, int W,
+                                            int act_pad, const F8& v) {
+  const size_t plane = static_cast<size_t>(HW) + static_cast<size_t>(act_pad) * W;
+  const size_t pp = pin + static_cast<size_t>(act_pad) * W;
+  __nv_bfloat16* o = base + ((static_cast<size_t>(n) * CG + cg) * plane + pp) * 8;
+  if (act_pad == 0 || cg != CG - 1) {
+    st8_bf16(o, v);
+  } else {
+    const __nv_bfloat16 b = __float2bfloat16(v.v[0]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j - static_cast<ptrdiff_t>(j) * W * 8] = b;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 gate_quad_split_kernel(const float* __restrict__ inq, const float* __restrict__ wg /*[KP][KP]*/,
                        const float* __restrict__ bg, float* __restrict__ out_g, __nv_bfloat16* __restrict__ out_act,
-                       size_t npix, int k, int KP, int HW) {
+                       size_t npix, int k, int KP, int HW, size_t lo_off = 0, int W = 0, int act_pad = 0) {
   extern __shared__ float smem_f[];
   float* wsm = smem_f;                 // [KP][KP]
   float* xin = smem_f + KP * KP;       // [kInitPix][KP+1]
@@ -615,7 +632,10 @@ gate_quad_split_kernel(const float* __restrict__ inq, const float* __restrict__ 
         *reinterpret_cast<float4*>(o) = make_float4(g.v[0], g.v[1], g.v[2], g.v[3]);
         *reinterpret_cast<float4*>(o + static_cast<size_t>(HW) * 4) = make_float4(g.v[4], g.v[5], g.v[6], g.v[7]);
       }
-      if (out_act) {
+      if (out_act && lo_off) {
+        st8_stacked(out_act, static_cast<int>(n), cg, CG, pin, HW, W, act_pad, hi);
+        st8_stacked(out_act + lo_off, static_cast<int>(n), cg, CG, pin, HW, W, act_pad, lo);
+      } else if (out_act) {
         st8_bf16(chunk_ptr(out_act, static_cast<int>(n), cg, pin, HW, 2 * CG), hi);
         st8_bf16(chunk_ptr(out_act, static_cast<int>(n), CG + cg, pin, HW, 2 * CG), lo);
       }
