@@ -25,6 +25,7 @@
 // of one frame); two TMEM accumulator sets so unit u's epilogue overlaps unit u+1's MMAs.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include "sm100_ptx.cuh"
@@ -158,6 +159,30 @@ __device__ __forceinline__ size_t quad_off(const TcConvArgs& a, int n, int quad,
   return ((static_cast<size_t>(n) * (a.KP >> 2) + quad) * (static_cast<size_t>(a.H) * a.W) + pin) * 4;
 }
 
+// H1 and G2 of the fused bf16 pipeline travel between its two launches as fp16 "oct-chunked" tensors
+// [n][c/8][y][x][8] (one 16-byte access per pixel and 8 channels): both are bounded (tanh / sigmoid outputs), fp16
+// keeps 11 significand bits of them, and their rounding (<= 4.9e-4 relative) sits well below the bf16 rounding of the
+// conv operands the same launches consume (2e-3); state (H2), drive (X) and all arithmetic stay fp32.  The fp32-class
+// modes (fp32, bf16x3) keep fp32 tensors.
+__device__ __forceinline__ size_t oct_off(const TcConvArgs& a, int n, int oct, size_t pin) {
+  return ((static_cast<size_t>(n) * (a.KP >> 3) + oct) * (static_cast<size_t>(a.H) * a.W) + pin) * 8;
+}
+__device__ __forceinline__ uint4 pack_half8(const float* r) {
+  __half2 h[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(r[2 * j], r[2 * j + 1]);
+  return *reinterpret_cast<const uint4*>(h);
+}
+__device__ __forceinline__ void unpack_half8(const uint4& u, float* r) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __half22float2(h[j]);
+    r[2 * j] = f.x;
+    r[2 * j + 1] = f.y;
+  }
+}
+
 // streaming accesses of the epilogues: every state byte is touched once per launch, so keep it out of
 // L1 (whose SRAM and datapath the UMMA operand fetch needs)
 __device__ __forceinline__ float4 ld_stream(const float* p) {
@@ -177,6 +202,15 @@ __device__ __forceinline__ float4 ld_stream_rw(const float* p) {   // data also 
 #endif
   asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
                : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ uint4 ld_stream_u4(const void* p) {
+  uint4 r;
+#ifdef HGRU_DBG_NO_GLOBAL
+  return make_uint4(0u, 0u, 0u, 0u);
+#endif
+  asm volatile("ld.global.L1::no_allocate.v4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
   return r;
 }
 __device__ __forceinline__ void st_stream(float* p, const float4& v) {
@@ -342,7 +376,8 @@ struct EpiBiasReluAffine {
 // input_integration fused into the C1 conv (hgru_module.py:657, 795-804):
 //   C1 = acc + lateral_bias;  H1 = tanh(X - (beta*H2 + nu) * C1)
 // writes H1 fp32 and its bf16 chunked operand copy.  bias = lateral_bias, v0 = beta, v1 = nu.
-struct EpiH1 {
+template <bool HALF>
+struct EpiH1T {
   static constexpr bool kGate = true;
   template <int NCH>
   struct Pre { float4 x[NCH / 4], h[NCH / 4]; };
@@ -364,17 +399,38 @@ struct EpiH1 {
   template <int NCH, int NREAL = NCH>
   __device__ static __forceinline__ void gate(const TcConvArgs& a, int n, size_t pin, int c0, const float* gacc,
                                               const float*) {
+    if constexpr (HALF) {
 #pragma unroll
-    for (int c = 0; c < NCH; c += 4) {
-      float g[4] = {0.f, 0.f, 0.f, 0.f};
-      if (c < NREAL) {
-        const float4 b = ld_par4(a.gate_bias + c0 + c);
-        const float bv[4] = {b.x, b.y, b.z, b.w};
+      for (int c = 0; c < NCH; c += 8) {
+        if (c >= NREAL) continue;                 // a chunk of layout padding is never read back
+        float g[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (c + j < NREAL && c0 + c + j < a.kreal) g[j] = fast_sigmoid(gacc[c + j] + bv[j]);
+        for (int h = 0; h < 2; ++h) {
+          float bv[4] = {0.f, 0.f, 0.f, 0.f};
+          if (c + 4 * h < NREAL) {
+            const float4 b = ld_par4(a.gate_bias + c0 + c + 4 * h);
+            bv[0] = b.x; bv[1] = b.y; bv[2] = b.z; bv[3] = b.w;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            g[4 * h + j] = (c + 4 * h + j < NREAL && c0 + c + 4 * h + j < a.kreal)
+                               ? fast_sigmoid(gacc[c + 4 * h + j] + bv[j]) : 0.f;
+        }
+        st_stream(reinterpret_cast<__half*>(a.gate_out) + oct_off(a, n, (c0 + c) >> 3, pin), pack_half8(g));
       }
-      st_stream(a.gate_out + quad_off(a, n, (c0 + c) >> 2, pin), make_float4(g[0], g[1], g[2], g[3]));
+    } else {
+#pragma unroll
+      for (int c = 0; c < NCH; c += 4) {
+        float g[4] = {0.f, 0.f, 0.f, 0.f};
+        if (c < NREAL) {
+          const float4 b = ld_par4(a.gate_bias + c0 + c);
+          const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (c + j < NREAL && c0 + c + j < a.kreal) g[j] = fast_sigmoid(gacc[c + j] + bv[j]);
+        }
+        st_stream(a.gate_out + quad_off(a, n, (c0 + c) >> 2, pin), make_float4(g[0], g[1], g[2], g[3]));
+      }
     }
   }
   template <int NCH, int NREAL = NCH>
@@ -407,8 +463,12 @@ struct EpiH1 {
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         if (c0 + c + j >= a.kreal) r[j] = 0.f;
-      st_stream(a.out + quad_off(a, n, (c0 + c) >> 2, pin), make_float4(r[0], r[1], r[2], r[3]));
-      st_stream(a.out + quad_off(a, n, ((c0 + c) >> 2) + 1, pin), make_float4(r[4], r[5], r[6], r[7]));
+      if constexpr (HALF) {
+        st_stream(reinterpret_cast<__half*>(a.out) + oct_off(a, n, (c0 + c) >> 3, pin), pack_half8(r));
+      } else {
+        st_stream(a.out + quad_off(a, n, (c0 + c) >> 2, pin), make_float4(r[0], r[1], r[2], r[3]));
+        st_stream(a.out + quad_off(a, n, ((c0 + c) >> 2) + 1, pin), make_float4(r[4], r[5], r[6], r[7]));
+      }
       store_act_chunk(a, a.out_bf16, n, (c0 + c) >> 3, pin, r);
       if (hout) {
 #pragma unroll
@@ -429,25 +489,45 @@ struct EpiH1 {
     }
   }
 };
+using EpiH1 = EpiH1T<false>;
+using EpiH1h = EpiH1T<true>;      // fused bf16 pipeline: H1 and G2 leave as fp16
 // output_integration + adaptation fused into the C2 conv (hgru_module.py:657, 806-823, 847-849):
 //   C2 = acc + lateral_bias; e = gamma*C2; Ht = tanh(kappa*(H1+e) + omega*(H1*e));
 //   H2 = (G2*H2 + (1-G2)*Ht) * rho_t      (in place) + bf16 chunked copy of the new H2.
 // bias = lateral_bias, v0 = gamma, v1 = kappa, v2 = omega.
-struct EpiH2 {
+template <bool HALF>
+struct EpiH2T {
   static constexpr bool kGate = true;
+  // HALF: h1 / g hold the raw 16-byte fp16 chunks (8 channels each) until `finish` unpacks them
   template <int NCH>
   struct Pre { float4 h1[NCH / 4], g[NCH / 4], h2[NCH / 4]; };
   template <int NCH, int NREAL = NCH>
   __device__ static __forceinline__ void load(const TcConvArgs& a, int n, size_t pin, int c0, Pre<NCH>& p) {
+    if constexpr (HALF) {
 #pragma unroll
-    for (int i = 0; i < NCH / 4; ++i) {
-      if (4 * i < NREAL) {
-        const size_t o = quad_off(a, n, (c0 >> 2) + i, pin);
-        p.h1[i] = ld_stream(a.H1 + o);
-        p.g[i] = ld_stream(a.G + o);
-        p.h2[i] = ld_stream_rw(a.H2 + o);
-      } else {
-        p.h1[i] = p.g[i] = p.h2[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < NCH / 8; ++i) {
+        if (8 * i < NREAL) {
+          const size_t o = oct_off(a, n, (c0 >> 3) + i, pin);
+          const uint4 uh = ld_stream_u4(reinterpret_cast<const __half*>(a.H1) + o);
+          const uint4 ug = ld_stream_u4(reinterpret_cast<const __half*>(a.G) + o);
+          p.h1[2 * i] = make_float4(__uint_as_float(uh.x), __uint_as_float(uh.y), __uint_as_float(uh.z), __uint_as_float(uh.w));
+          p.g[2 * i] = make_float4(__uint_as_float(ug.x), __uint_as_float(ug.y), __uint_as_float(ug.z), __uint_as_float(ug.w));
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NCH / 4; ++i)
+        p.h2[i] = (4 * i < NREAL) ? ld_stream_rw(a.H2 + quad_off(a, n, (c0 >> 2) + i, pin)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+#pragma unroll
+      for (int i = 0; i < NCH / 4; ++i) {
+        if (4 * i < NREAL) {
+          const size_t o = quad_off(a, n, (c0 >> 2) + i, pin);
+          p.h1[i] = ld_stream(a.H1 + o);
+          p.g[i] = ld_stream(a.G + o);
+          p.h2[i] = ld_stream_rw(a.H2 + o);
+        } else {
+          p.h1[i] = p.g[i] = p.h2[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
     }
   }
@@ -480,11 +560,26 @@ struct EpiH2 {
 #pragma unroll
     for (int c = 0; c < NCH; c += 8) {
       float r[8];
+      float h1h[8], gh[8];      // HALF: this chunk's fp16 inputs, unpacked
+      if constexpr (HALF) {
+        if (c < NREAL) {
+          const float4 uh = p.h1[c >> 2], ug = p.g[c >> 2];
+          unpack_half8(make_uint4(__float_as_uint(uh.x), __float_as_uint(uh.y), __float_as_uint(uh.z), __float_as_uint(uh.w)), h1h);
+          unpack_half8(make_uint4(__float_as_uint(ug.x), __float_as_uint(ug.y), __float_as_uint(ug.z), __float_as_uint(ug.w)), gh);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) h1h[j] = gh[j] = 0.f;
+        }
+      }
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int i = (c >> 2) + h, cc = c0 + c + 4 * h;
         const float4 h1 = p.h1[i], g = p.g[i], h2 = p.h2[i];
-        const float h1v[4] = {h1.x, h1.y, h1.z, h1.w}, gv[4] = {g.x, g.y, g.z, g.w};
+        float h1v[4] = {h1.x, h1.y, h1.z, h1.w}, gv[4] = {g.x, g.y, g.z, g.w};
+        if constexpr (HALF) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { h1v[j] = h1h[4 * h + j]; gv[j] = gh[4 * h + j]; }
+        }
         const float h2v[4] = {h2.x, h2.y, h2.z, h2.w};
         float lbv[4] = {0.f, 0.f, 0.f, 0.f}, gav[4] = {0.f, 0.f, 0.f, 0.f}, kav[4] = {0.f, 0.f, 0.f, 0.f};
         float omv[4] = {0.f, 0.f, 0.f, 0.f};
@@ -512,7 +607,8 @@ struct EpiH2 {
       for (int j = 0; j < 8; ++j)
         if (c0 + c + j >= a.kreal) r[j] = 0.f;
       st_stream(a.H2 + quad_off(a, n, (c0 + c) >> 2, pin), make_float4(r[0], r[1], r[2], r[3]));
-      st_stream(a.H2 + quad_off(a, n, ((c0 + c) >> 2) + 1, pin), make_float4(r[4], r[5], r[6], r[7]));
+      if (c + 4 < NREAL)      // (a quad of pure layout padding is never read back: it stays at its initial zeros)
+        st_stream(a.H2 + quad_off(a, n, ((c0 + c) >> 2) + 1, pin), make_float4(r[4], r[5], r[6], r[7]));
       if (a.out_bf16) store_chunk_bf16(a.out_bf16, a.KP, a.H * a.W, n, (c0 + c) >> 3, pin, r);
       if (a.fc_a) {
         // last timestep: emit the fc_1 operand (channel-major K order c*HW + pin, bf16 hi/lo split)
@@ -548,6 +644,8 @@ struct EpiH2 {
     }
   }
 };
+using EpiH2 = EpiH2T<false>;
+using EpiH2h = EpiH2T<true>;
 // mix gate as a 1x1 tensor-core conv (hgru_module.py:729-740): G2 = sigmoid(acc + o_b) -> fp32.
 struct EpiGateOut {
   template <int CO_PAD>

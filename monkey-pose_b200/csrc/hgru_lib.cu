@@ -3,6 +3,7 @@
 #include "../../include/hgru_b200.h"
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -694,6 +695,7 @@ static int hgru_run_bf16(hgru_plan_s* p, const float* Xp, const float* H2_init_n
   const bool fused = p->stacked || p->fused_tc;
   // (development switch: weight ring of 5 stages x 3 taps instead of 3 stages x 5 taps for the fused 64-channel kernel)
   static const bool ring35 = [] { const char* e = getenv("HGRU_F64_RING35"); return e && e[0] == '1'; }();
+  static const bool fp32_hg = [] { const char* e = getenv("HGRU_FP32_HG"); return e && e[0] == '1'; }();
   // Chained launches (see TcConvArgs::wait_flags): launch l waits per frame on launch l-1's counters instead of on
   // the whole grid.  Not with traces (their copy kernels sit between the launches).
   const bool chain = fused && p->chain && !H1_trace && !H2_trace;
@@ -731,9 +733,12 @@ static int hgru_run_bf16(hgru_plan_s* p, const float* Xp, const float* H2_init_n
     set_flags(a, 2 * t);
     a.pdl = (chain && t == 0 && n0 > 0) ? 1 : 0;      // follows the previous group's last launch: nothing to wait for
     if (!chain) p->timer.begin(st);
-    if ((rc = p->stacked    ? dispatch_stack<hgru::EpiH1>(KP, p->stack_T, p->mapA, a, st)
-              : p->fused_tc ? (ring35 ? launch_tc_fused64<hgru::EpiH1, 3, 5>(p->mapA, a, st)
-                                      : launch_tc_fused64<hgru::EpiH1>(p->mapA, a, st))
+    // (fused pipeline: H1 and G2 travel to the H2 launch as fp16, EpiH1h / EpiH2h; development switch
+    // HGRU_FP32_HG=1: as fp32 on the stacked kernel, for A/B runs)
+    if ((rc = (p->stacked && fp32_hg) ? dispatch_stack<hgru::EpiH1>(KP, p->stack_T, p->mapA, a, st)
+              : p->stacked  ? dispatch_stack<hgru::EpiH1h>(KP, p->stack_T, p->mapA, a, st)
+              : p->fused_tc ? (ring35 ? launch_tc_fused64<hgru::EpiH1h, 3, 5>(p->mapA, a, st)
+                                      : launch_tc_fused64<hgru::EpiH1h>(p->mapA, a, st))
                             : dispatch_tc_hconv<hgru::EpiH1>(p->S, KP, p->mapA, a, st)))
       return rc;
     if (!chain) p->timer.end(st);
@@ -762,9 +767,10 @@ static int hgru_run_bf16(hgru_plan_s* p, const float* Xp, const float* H2_init_n
     }
     set_flags(a, 2 * t + 1);
     if (!chain) p->timer.begin(st);
-    if ((rc = p->stacked    ? dispatch_stack<hgru::EpiH2>(KP, p->stack_T, p->mapH1, a, st)
-              : p->fused_tc ? (ring35 ? launch_tc_fused64<hgru::EpiH2, 3, 5>(p->mapH1, a, st)
-                                      : launch_tc_fused64<hgru::EpiH2>(p->mapH1, a, st))
+    if ((rc = (p->stacked && fp32_hg) ? dispatch_stack<hgru::EpiH2>(KP, p->stack_T, p->mapH1, a, st)
+              : p->stacked  ? dispatch_stack<hgru::EpiH2h>(KP, p->stack_T, p->mapH1, a, st)
+              : p->fused_tc ? (ring35 ? launch_tc_fused64<hgru::EpiH2h, 3, 5>(p->mapH1, a, st)
+                                      : launch_tc_fused64<hgru::EpiH2h>(p->mapH1, a, st))
                             : dispatch_tc_hconv<hgru::EpiH2>(p->S, KP, p->mapH1, a, st)))
       return rc;
     if (!chain) p->timer.end(st);
@@ -772,8 +778,11 @@ static int hgru_run_bf16(hgru_plan_s* p, const float* Xp, const float* H2_init_n
     //                                                                     counted as 2T passes over the whole batch
     ++p->launches;
     if (H1_trace) {
-      hgru::quad_to_nhwc_kernel<<<nblk(p->npix * p->k), 256, 0, st>>>(
-          p->H1.as<float>(), H1_trace + static_cast<size_t>(t) * p->npix * p->k, p->npix, p->k, KP, HW);
+      float* dst = H1_trace + static_cast<size_t>(t) * p->npix * p->k;
+      if (fused && !(p->stacked && fp32_hg))      // H1 is an fp16 oct-chunked tensor in the fused pipeline
+        hgru::oct_half_to_nhwc_kernel<<<nblk(p->npix * p->k), 256, 0, st>>>(p->H1.as<__half>(), dst, p->npix, p->k, KP, HW);
+      else
+        hgru::quad_to_nhwc_kernel<<<nblk(p->npix * p->k), 256, 0, st>>>(p->H1.as<float>(), dst, p->npix, p->k, KP, HW);
       ++p->launches;
     }
     if (H2_trace) {

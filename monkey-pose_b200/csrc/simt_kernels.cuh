@@ -3,6 +3,7 @@
 // Reference call sites are cited per kernel (paths relative to /root/reference).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -438,6 +439,17 @@ quad_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, size_
   const size_t p = i / k;
   const size_t n = p / HW, pin = p - n * HW;
   out[i] = in[((n * (KP >> 2) + (c >> 2)) * HW + pin) * 4 + (c & 3)];
+}
+
+// fp16 oct-chunked [n][c/8][pix][8] (H1 / G2 of the fused bf16 pipeline, see hconv_tc.cuh) -> fp32 NHWC
+__global__ void __launch_bounds__(256)
+oct_half_to_nhwc_kernel(const __half* __restrict__ in, float* __restrict__ out, size_t npix, int k, int KP, int HW) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;   // over [npix][k]
+  if (i >= npix * k) return;
+  const int c = i % k;
+  const size_t p = i / k;
+  const size_t n = p / HW, pin = p - n * HW;
+  out[i] = __half2float(in[((n * (KP >> 3) + (c >> 3)) * HW + pin) * 8 + (c & 7)]);
 }
 
 // bf16 hi | lo chunk planes [n][2*CG][pix][8] (the operand copies of the tensor-core stem) -> fp32 NHWC
