@@ -143,6 +143,9 @@ def main():
              gains={(15, 15, 25, 25): 5.0, (1, 32, 32, 25): 10.0})
     gen_hgru(hm, aux, "S15_k32_T16_stress", n=1, h=20, w=24, k=32, S=15, T=16, seed=16, f32_steps=True,
              gains={(15, 15, 32, 32): 4.0, (1, 20, 24, 32): 10.0})
+    # the reference's own width (64 channels: the plain tcgen05 conv kernel with epilogue-issued gates), small map
+    gen_hgru(hm, aux, "S15_k64_T3_stress", n=1, h=16, w=20, k=64, S=15, T=3, seed=17, f32_steps=True,
+             gains={(15, 15, 64, 64): 4.0, (1, 16, 20, 64): 10.0})
     gen_pose_layers(pm, seed=21)
 
 

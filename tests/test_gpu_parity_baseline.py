@@ -77,10 +77,11 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 @pytest.mark.parametrize("mode", ["bf16", "bf16x3", "fp32"])
-@pytest.mark.parametrize("tag", ["S15_k25_T8", "S15_k25_T8_stress", "S15_k32_T16_stress"])
+@pytest.mark.parametrize("tag", ["S15_k25_T8", "S15_k25_T8_stress", "S15_k32_T16_stress", "S15_k64_T3_stress"])
 def test_baseline_width_goldens_from_the_reference_source(tag, mode):
     """Numbers computed by the reference's own hgru_module.py statements (tests/golden/make_golden.py) at 25 channels /
-    T = 8 -- the remainder-packed tap-stacked kernel -- and 32 channels / T = 16, every timestep."""
+    T = 8 -- the remainder-packed tap-stacked kernel --, 32 channels / T = 16 and 64 channels (the reference's own width:
+    the plain tcgen05 conv kernel with epilogue-issued gates), every timestep."""
     z = np.load(os.path.join(GOLDEN, "hgru_ref_%s.npz" % tag))
     T, S = int(z["T"]), int(z["S"])
     params = {n: z["var:contextual_circuit/" + n] for n in onp.HGRU_PARAM_NAMES}
