@@ -426,6 +426,8 @@ def neighbour_stages(a, m, torch, mp, init_mod):
                   np.clip(np.minimum(y0 + hb, h) - np.maximum(y0, 0), 0, None)).sum())
     crop_bytes = 4.0 * win_px + 4.0 * B * 128 * 128
     crop_gpu_ms, crop_wall_ms, _ = ev_time(lambda: tmd.prepare_data_test(frames_dev, coms_norm, md, Cfg()))
+    coms_f32_dev = torch.as_tensor(coms_norm.astype(np.float32)).cuda()
+    crop_dev_ms, crop_dev_wall_ms, _ = ev_time(lambda: tmd.prepare_data_test(frames_dev, coms_f32_dev, md, Cfg()))
     # the kernel alone, through the C ABI, parameters already on the device
     lib = mp._lib.load()
     _, zf, _ = md._windows_batch(np.asarray(coms), h, w, (128, 128))
@@ -450,10 +452,13 @@ def neighbour_stages(a, m, torch, mp, init_mod):
     attn_flops = 2.0 * B * (128 * 128 * 9 * 64 + 64 * 64 * 9 * 64 * 128 + 32 * 32 * 9 * 128 * 256 +
                             16 * 16 * 9 * 256 * 512 + 8 * 8 * 25 * 512 * 1024 + 16384 * 1024 + 1024 * 3)
 
+    coms_norm_dev = torch.as_tensor(coms_norm.astype(np.float32)).cuda()
+
     def chain():
         f = frames_pin.cuda(non_blocking=True)
         am.build(f, 3)                               # its output would drive the crop; fixed centres keep it valid
-        p, cs, _ = tmd.prepare_data_test(f, coms_norm, md, Cfg())
+        # centres as a device tensor: window arithmetic, crop, network and post-processing without a host round trip
+        p, cs, _ = tmd.prepare_data_test(f, coms_norm_dev, md, Cfg())
         xyz, _ = md.getAbsoluteCoordinates_batch(m.build(p, 69), cs, 600.0)
         return xyz.cpu()
 
@@ -468,9 +473,11 @@ def neighbour_stages(a, m, torch, mp, init_mod):
             "crop": {"kernel_ms": crop_kernel_ms, "algorithmic_bytes": crop_bytes, "GB/s": crop_gbs,
                      "frac_of_hbm": (crop_gbs / hbm) if hbm else None,
                      "api_ms": crop_gpu_ms, "api_wall_ms": crop_wall_ms,
+                     "api_device_windows_ms": crop_dev_ms, "api_device_windows_wall_ms": crop_dev_wall_ms,
                      "note": "kernel_ms: crop_area3d_forward alone (C ABI, parameters on the device); api_ms: "
                              "prepare_data_test = host window arithmetic (comToBounds) + parameter upload + "
-                             "kernel; frames resident in HBM"},
+                             "kernel; api_device_windows_ms: the same with the centres of mass as a CUDA tensor "
+                             "(crop_windows_forward + crop_area3d_forward, no host round trip); frames resident in HBM"},
             "post": {"gpu_ms": post_gpu_ms, "wall_ms": post_wall_ms,
                      "note": "x600 + CoM, xyz->uvd, mean joint error; 23 joints per frame, latency-bound"},
             "attention_cnn": {"gpu_ms": attn_gpu_ms, "frames_per_s": B / (attn_gpu_ms * 1e-3),

@@ -169,6 +169,18 @@ HGRU_API int crop_area3d_forward(const float* frames_dev, int N, int H, int W, f
                                  const int* iparams_dev, const float* zparams_dev, float background,
                                  double out_divisor, float* out_dev, int dh, int dw, void* stream);
 
+/* The window arithmetic itself on the device: comToBounds (tf_monkeydetector.py:193-206) + the resize / paste integers
+ * and the 3x3 joint transform of cropArea3D (:309-362) for a batch, in explicitly rounded IEEE double operations in the
+ * reference's evaluation order (the integers equal the host's).  Centres of mass: com_in_dev [N][3] double (u, v, d mm)
+ * when given, else attention outputs tr_dev [N][3] float32 times (s0, s1, s2) = (image height, width, max depth) as
+ * prepare_data_test scales them (train_cnn_networks_hgru.py:66-68).  Outputs: coms [N][3] double, iparams [N][8] and
+ * zparams [N][2] as crop_area3d_forward takes them, Ms [N][3][3] double, invalid [N] (1: the window misses the frame;
+ * that frame's crop is all background).  (dw, dh) = destination size; cube in mm. */
+HGRU_API int crop_windows_forward(const float* tr_dev, const double* com_in_dev, double s0, double s1, double s2,
+                                  int N, int H, int W, int dw, int dh, double fx, double fy, double cube_x,
+                                  double cube_y, double cube_z, double* coms_dev, int* iparams_dev,
+                                  float* zparams_dev, double* Ms_dev, int* invalid_dev, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Post-processing (the step right after the pose network).
  * pose_postprocess_forward: out_put [N,3J] (normalised) -> xyz [N,J,3] = out*scale + uvdtoxyz(com),

@@ -68,6 +68,9 @@ SIGNATURES = {
                                       ctypes.c_ulonglong, ctypes.c_float, _P, _P, _P, _P, _P]),
     "crop_area3d_forward": (_I, [_P, _I, _I, _I, ctypes.c_float, _P, _P, ctypes.c_float, ctypes.c_double, _P,
                                  _I, _I, _P]),
+    "crop_windows_forward": (_I, [_P, _P, ctypes.c_double, ctypes.c_double, ctypes.c_double, _I, _I, _I, _I, _I,
+                                  ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                  _P, _P, _P, _P, _P, _P]),
     "pose_postprocess_forward": (_I, [_P, _P, _I, _I, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                       ctypes.c_double, ctypes.c_float, _P, _P, _P]),
     "joint_error_forward": (_I, [_P, _P, _I, _I, _P, _P, _P, _P]),

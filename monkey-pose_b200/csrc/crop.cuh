@@ -42,4 +42,64 @@ crop_area3d_kernel(const float* __restrict__ frames, float frame_scale, const in
   out[idx] = static_cast<float>(static_cast<double>(v) / out_div);
 }
 
+
+// Window arithmetic of the crop on the device (tfMonkeyDetector.comToBounds + the resize / paste integers and the
+// 3x3 transform of cropArea3D, tf_monkeydetector.py:193-206, 309-362), so that attention output -> crop needs no
+// host round trip.  One thread per frame; every operation is an explicitly rounded IEEE double operation in the
+// order the reference's numpy expressions evaluate them (no FMA contraction), so the integers are the host's.
+//   tr [N][3] float32: the attention CNN's output (u / height, v / width, d / max depth as the reference reads it);
+//   coms = double(tr) * tr_scale (train_cnn_networks_hgru.py:66-68).  com_in (double [N][3]) overrides tr when given.
+// A window that misses the frame gets resized size 0 (an all-background patch) and invalid[n] = 1.
+__global__ void __launch_bounds__(128)
+crop_windows_kernel(const float* __restrict__ tr, const double* __restrict__ com_in, double s0, double s1, double s2,
+                    int N, int H, int W, int dw, int dh, double fx, double fy, double cx, double cy, double cz,
+                    double* __restrict__ coms, int* __restrict__ ip, float* __restrict__ zp, double* __restrict__ Ms,
+                    int* __restrict__ invalid) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  double c0, c1, c2;
+  if (com_in) {
+    c0 = com_in[3 * n]; c1 = com_in[3 * n + 1]; c2 = com_in[3 * n + 2];
+  } else {
+    c0 = __dmul_rn(static_cast<double>(tr[3 * n]), s0);
+    c1 = __dmul_rn(static_cast<double>(tr[3 * n + 1]), s1);
+    c2 = __dmul_rn(static_cast<double>(tr[3 * n + 2]), s2);
+  }
+  coms[3 * n] = c0; coms[3 * n + 1] = c1; coms[3 * n + 2] = c2;
+  const double hx = cx / 2., hy = cy / 2., hz = cz / 2.;
+  const double zstart = __dsub_rn(c2, hz), zend = __dadd_rn(c2, hz);
+  // floor((c * z / f -+ size / 2) / z * f)
+  const double ax = __ddiv_rn(__dmul_rn(c0, c2), fx), ay = __ddiv_rn(__dmul_rn(c1, c2), fy);
+  const double fxs = floor(__dmul_rn(__ddiv_rn(__dsub_rn(ax, hx), c2), fx));
+  const double fxe = floor(__dmul_rn(__ddiv_rn(__dadd_rn(ax, hx), c2), fx));
+  const double fys = floor(__dmul_rn(__ddiv_rn(__dsub_rn(ay, hy), c2), fy));
+  const double fye = floor(__dmul_rn(__ddiv_rn(__dadd_rn(ay, hy), c2), fy));
+  const bool finite = isfinite(c0) && isfinite(c1) && isfinite(c2) && isfinite(fxs) && isfinite(fxe) &&
+                      isfinite(fys) && isfinite(fye) && fabs(fxs) < 1e9 && fabs(fxe) < 1e9 && fabs(fys) < 1e9 &&
+                      fabs(fye) < 1e9;
+  long long xstart = finite ? static_cast<long long>(fxs) : 0, xend = finite ? static_cast<long long>(fxe) : 1;
+  long long ystart = finite ? static_cast<long long>(fys) : 0, yend = finite ? static_cast<long long>(fye) : 1;
+  const bool bad = !finite || xend <= 0 || yend <= 0 || xstart >= W || ystart >= H || xend <= xstart || yend <= ystart;
+  if (bad) { xstart = 0; ystart = 0; xend = 1; yend = 1; }
+  const long long wb = xend - xstart, hb = yend - ystart;
+  long long szx, szy;
+  if (wb > hb) { szx = dw; szy = hb * dw / wb; } else { szx = wb * dh / hb; szy = dh; }      // (positive: // == /)
+  if (bad) { szx = 0; szy = 0; }
+  const double sc = (hb > wb) ? __ddiv_rn(static_cast<double>(szy), static_cast<double>(hb))
+                              : __ddiv_rn(static_cast<double>(szx), static_cast<double>(wb));
+  const long long xs = static_cast<long long>(floor(__dsub_rn(dw / 2., szx / 2.)));
+  const long long ys = static_cast<long long>(floor(__dsub_rn(dh / 2., szy / 2.)));
+  int* q = ip + 8 * n;
+  q[0] = static_cast<int>(xstart); q[1] = static_cast<int>(ystart); q[2] = static_cast<int>(wb); q[3] = static_cast<int>(hb);
+  q[4] = static_cast<int>(szx); q[5] = static_cast<int>(szy); q[6] = static_cast<int>(xs); q[7] = static_cast<int>(ys);
+  zp[2 * n] = static_cast<float>(zstart);
+  zp[2 * n + 1] = static_cast<float>(zend);
+  // M = off @ scale @ trans written out (the products only ever add exact zeros)
+  double* M = Ms + 9 * n;
+  M[0] = sc; M[1] = 0.; M[2] = __dadd_rn(__dmul_rn(sc, -static_cast<double>(xstart)), static_cast<double>(xs));
+  M[3] = 0.; M[4] = sc; M[5] = __dadd_rn(__dmul_rn(sc, -static_cast<double>(ystart)), static_cast<double>(ys));
+  M[6] = 0.; M[7] = 0.; M[8] = 1.;
+  invalid[n] = bad ? 1 : 0;
+}
+
 }  // namespace hgru

@@ -1419,6 +1419,18 @@ int crop_area3d_forward(const float* frames, int N, int H, int W, float frame_sc
   return 0;
 }
 
+int crop_windows_forward(const float* tr, const double* com_in, double s0, double s1, double s2, int N, int H, int W,
+                         int dw, int dh, double fx, double fy, double cube_x, double cube_y, double cube_z,
+                         double* coms, int* iparams, float* zparams, double* Ms, int* invalid, void* stream) {
+  if ((!tr && !com_in) || !coms || !iparams || !zparams || !Ms || !invalid)
+    return fail(HGRU_E_INVALID, "crop_windows_forward: null pointer");
+  if (N < 1 || H < 1 || W < 1 || dw < 1 || dh < 1) return fail(HGRU_E_INVALID, "crop_windows_forward: non-positive shape");
+  hgru::crop_windows_kernel<<<nblk(N, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      tr, com_in, s0, s1, s2, N, H, W, dw, dh, fx, fy, cube_x, cube_y, cube_z, coms, iparams, zparams, Ms, invalid);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 int pose_postprocess_forward(const float* out_put, const double* com_uvd, int N, int J, double fx, double fy,
                              double ux, double uy, float scale, float* xyz, float* uvd, void* stream) {
   if (!out_put || !com_uvd || !xyz || !uvd) return fail(HGRU_E_INVALID, "pose_postprocess_forward: null pointer");

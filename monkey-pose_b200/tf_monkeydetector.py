@@ -88,7 +88,10 @@ class tfMonkeyDetector(object):
             raise RuntimeError("out_put must be a [N,3J] torch CUDA tensor (no CPU fallback)")
         out_put = out_put.to(torch.float32).contiguous()
         N, J = int(out_put.shape[0]), int(out_put.shape[1]) // 3
-        com_d = torch.as_tensor(numpy.asarray(coms, numpy.float64).reshape(N, 3)).cuda()
+        if torch.is_tensor(coms) and coms.is_cuda:          # centres of mass already on the device (device crop path)
+            com_d = coms.to(torch.float64).reshape(N, 3).contiguous()
+        else:
+            com_d = torch.as_tensor(numpy.asarray(coms, numpy.float64).reshape(N, 3)).cuda()
         xyz = torch.empty((N, J, 3), device=out_put.device, dtype=torch.float32)
         uvd = torch.empty_like(xyz)
         _lib.check(_lib.load().pose_postprocess_forward(
@@ -179,6 +182,50 @@ class tfMonkeyDetector(object):
             float(out_divisor), out.data_ptr(), int(dsize[1]), int(dsize[0]), _stream()), "crop_area3d_forward")
         return out, list(Ms), list(coms)
 
+    def cropArea3D_batch_device(self, frames, tr=None, tr_scale=(1.0, 1.0, 1.0), coms=None, dsize=(128, 128),
+                                frame_scale=1.0, out_divisor=1.0):
+        """cropArea3D_batch with the window arithmetic on the device too (`crop_windows_forward`): no host round trip
+        between the attention CNN and the crop.  Centres of mass either as `coms` (CUDA float64 [N,3]; u, v, d mm) or
+        as attention outputs `tr` (CUDA float32 [N,3]) times `tr_scale` (train_cnn_networks_hgru.py:66-68).
+        Returns (patches, Ms, coms) as CUDA tensors ([N,dh,dw] float32, [N,3,3] float64, [N,3] float64);
+        `self.last_invalid_dev` (CUDA int32 [N]) flags frames whose window misses the frame (all-background patch)."""
+        if len(dsize) != 2:
+            raise ValueError("dsize must be a 2D bounding box")
+        if not (torch.is_tensor(frames) and frames.is_cuda and frames.dim() == 3):
+            raise RuntimeError("frames must be a [N,H,W] torch CUDA tensor (no CPU fallback)")
+        frames = frames.to(torch.float32).contiguous()
+        N, H, W = [int(v) for v in frames.shape]
+        dev = frames.device
+        if coms is not None:
+            if not (torch.is_tensor(coms) and coms.is_cuda):
+                raise RuntimeError("coms must be a CUDA tensor on the device path")
+            coms = coms.to(torch.float64).reshape(N, 3).contiguous()
+        elif tr is not None:
+            if not (torch.is_tensor(tr) and tr.is_cuda):
+                raise RuntimeError("tr must be a CUDA tensor on the device path")
+            tr = tr.to(torch.float32).reshape(N, 3).contiguous()
+        else:
+            raise ValueError("give coms or tr")
+        coms_out = torch.empty((N, 3), device=dev, dtype=torch.float64)
+        ip = torch.empty((N, 8), device=dev, dtype=torch.int32)
+        zp = torch.empty((N, 2), device=dev, dtype=torch.float32)
+        Ms = torch.empty((N, 3, 3), device=dev, dtype=torch.float64)
+        inv = torch.empty((N,), device=dev, dtype=torch.int32)
+        out = torch.empty((N, dsize[1], dsize[0]), device=dev, dtype=torch.float32)
+        lib = _lib.load()
+        _lib.check(lib.crop_windows_forward(
+            tr.data_ptr() if coms is None else None, coms.data_ptr() if coms is not None else None,
+            float(tr_scale[0]), float(tr_scale[1]), float(tr_scale[2]), N, H, W, int(dsize[0]), int(dsize[1]),
+            float(self.fx), float(self.fy), float(self.cube[0]), float(self.cube[1]), float(self.cube[2]),
+            coms_out.data_ptr(), ip.data_ptr(), zp.data_ptr(), Ms.data_ptr(), inv.data_ptr(), _stream()),
+            "crop_windows_forward")
+        _lib.check(lib.crop_area3d_forward(
+            frames.data_ptr(), N, H, W, float(frame_scale), ip.data_ptr(), zp.data_ptr(), float(self.maxDepth),
+            float(out_divisor), out.data_ptr(), int(dsize[1]), int(dsize[0]), _stream()), "crop_area3d_forward")
+        self.last_invalid_dev = inv
+        self._last_windows_dev = (ip, zp)
+        return out, Ms, coms_out
+
     def cropArea3D(self, dpt, com=None, dsize=(128, 128), docom=False):
         """tf_monkeydetector.py:292-365 for one frame [H,W] (mm): (patch, M, com)."""
         if com is None or docom:
@@ -194,10 +241,16 @@ def prepare_data_test(image_np, tr_res, md, config):
     and attention outputs tr_res [N,3] -> (patches [N,128,128,1] CUDA, coms, Ms)."""
     if image_np.dim() == 4:
         image_np = image_np[..., 0]
+    ts = config.image_target_size
+    if torch.is_tensor(tr_res) and tr_res.is_cuda:
+        # attention outputs still on the device: the whole stage stays there (coms and Ms come back as CUDA tensors)
+        patches, Ms, coms = md.cropArea3D_batch_device(
+            image_np, tr=tr_res, tr_scale=(config.image_orig_size[0], config.image_orig_size[1], config.image_max_depth),
+            dsize=(ts[1], ts[0]), frame_scale=config.image_max_depth, out_divisor=config.image_max_depth)
+        return patches[..., None], coms, Ms
     tr = numpy.asarray(tr_res, numpy.float64)
     scale = numpy.array([config.image_orig_size[0], config.image_orig_size[1], config.image_max_depth], numpy.float64)
     coms = tr * scale
-    ts = config.image_target_size
     patches, Ms, coms = md.cropArea3D_batch(image_np, coms, dsize=(ts[1], ts[0]),
                                             frame_scale=config.image_max_depth,
                                             out_divisor=config.image_max_depth)

@@ -325,6 +325,41 @@ def test_crop_stage_vs_oracle_at_batch_size_and_feeds_the_model():
     assert out.shape == (4, 69) and torch.isfinite(out).all()
 
 
+def test_crop_window_arithmetic_on_the_device_equals_the_host():
+    """prepare_data_test with the attention outputs as a CUDA tensor: comToBounds + the resize / paste integers + the
+    joint transform are computed by crop_windows_forward.  Same patches, centres, matrices and invalid flags as the
+    host (numpy float64) path, bit for bit -- including centres whose window misses the frame."""
+    from monkey_pose_b200 import tf_monkeydetector as tmd
+    rng = np.random.default_rng(11)
+    n, h, w = 300, 424, 512
+    base = np.round(rng.uniform(600, 4000, size=(4, h, w)) / 8) * 8
+    frames = torch.as_tensor((base[rng.integers(0, 4, n)] / 10000.0).astype(np.float32)).cuda()
+    tr = np.stack([rng.uniform(-0.2, 1.4, n), rng.uniform(-0.2, 1.2, n), rng.uniform(0.03, 0.5, n)], 1).astype(np.float32)
+    tr[7] = [np.nan, 0.5, 0.2]
+    tr[8] = [0.5, 0.5, 0.0]
+    md_h = tmd.tfMonkeyDetector(365.456, 365.456, 256, 212, [800, 800, 1200], 200, 10000)
+    md_d = tmd.tfMonkeyDetector(365.456, 365.456, 256, 212, [800, 800, 1200], 200, 10000)
+    with np.errstate(all="ignore"):
+        p_h, c_h, M_h = tmd.prepare_data_test(frames, tr, md_h, _Cfg())
+    p_d, c_d, M_d = tmd.prepare_data_test(frames, torch.as_tensor(tr).cuda(), md_d, _Cfg())
+    bad_h = np.zeros(n, bool)
+    bad_h[md_h.last_invalid] = True
+    bad_d = md_d.last_invalid_dev.cpu().numpy().astype(bool)
+    assert np.array_equal(bad_h, bad_d) and 10 < bad_h.sum() < n - 10
+    assert torch.equal(p_h, p_d)
+    good = ~bad_h
+    assert np.array_equal(np.asarray(c_h)[good], c_d.cpu().numpy()[good])
+    assert np.array_equal(np.asarray(M_h)[good], M_d.cpu().numpy()[good])
+    ip_d, zp_d = md_d._last_windows_dev
+    ints, z, _ = md_h._windows_batch(np.asarray(c_h), h, w, (128, 128))
+    assert np.array_equal(ip_d.cpu().numpy()[good], ints[good]) and np.array_equal(zp_d.cpu().numpy()[good], z[good])
+    # the device centres feed the post-processing directly
+    out = torch.rand(n, 69, device="cuda") - 0.5
+    xyz_h, uvd_h = md_h.getAbsoluteCoordinates_batch(out, c_h, 600.0)
+    xyz_d, uvd_d = md_d.getAbsoluteCoordinates_batch(out, c_d, 600.0)
+    assert torch.equal(xyz_h[good], xyz_d[good]) and torch.equal(uvd_h[good], uvd_d[good])
+
+
 # ---- post-processing (SURVEY 8f rank 2) -------------------------------------------------------------
 def test_postprocess_bit_exact_against_reference_golden():
     from monkey_pose_b200 import pose_evaluation as pe
