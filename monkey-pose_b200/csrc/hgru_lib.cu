@@ -1,6 +1,6 @@
 // libhgru_b200.so -- plans, parameter packing, kernel orchestration and the C ABI declared in
 // include/hgru_b200.h.  Pure CUDA runtime; no framework types cross this boundary.
-#include "../../include/hgru_b200.h"
+#include "lib_common.cuh"
 
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -16,7 +16,6 @@
 #include "crop.cuh"
 #include "gate_tc.cuh"
 #include "gemm_tc.cuh"
-#include "hconv_stack.cuh"
 #include "post.cuh"
 #include "hconv_tc.cuh"
 #include "layers.cuh"
@@ -27,56 +26,20 @@
 #include "tc_host.cuh"
 
 namespace {
-
 thread_local std::string g_err;
 int g_timing = 0;
+}  // namespace
 
+namespace hgru_host {
 int fail(int code, const std::string& msg) {
   g_err = msg;
   return code;
 }
+}  // namespace hgru_host
 
-#define CUDA_TRY(expr)                                                                        \
-  do {                                                                                        \
-    cudaError_t e_ = (expr);                                                                  \
-    if (e_ != cudaSuccess)                                                                    \
-      return fail(HGRU_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));           \
-  } while (0)
+using namespace hgru_host;
 
-// Function attributes (the dynamic shared-memory opt-in) and the SM count belong to a DEVICE, and one process may
-// drive several: remember per device what was done / read, not per process.
-struct PerDeviceOnce {
-  std::atomic<unsigned long long> mask{0};
-  bool seen(int dev) const { return dev >= 0 && dev < 64 && ((mask.load(std::memory_order_acquire) >> dev) & 1ull); }
-  void mark(int dev) { if (dev >= 0 && dev < 64) mask.fetch_or(1ull << dev, std::memory_order_release); }
-};
-#define SMEM_ATTR_ONCE(kern, bytes)                                                                       \
-  do {                                                                                                    \
-    static PerDeviceOnce once_;                                                                           \
-    int dev_ = 0;                                                                                         \
-    CUDA_TRY(cudaGetDevice(&dev_));                                                                       \
-    if (!once_.seen(dev_)) {      /* (idempotent: a race only sets the attribute twice) */                \
-      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));           \
-      once_.mark(dev_);                                                                                   \
-    }                                                                                                     \
-  } while (0)
-
-// multiprocessor count of the current device
-inline int sm_count(int* out) {
-  static std::atomic<int> cache[64];
-  int dev = 0;
-  CUDA_TRY(cudaGetDevice(&dev));
-  int v = (dev >= 0 && dev < 64) ? cache[dev].load(std::memory_order_relaxed) : 0;
-  if (!v) {
-    CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
-    if (dev >= 0 && dev < 64) cache[dev].store(v, std::memory_order_relaxed);
-  }
-  *out = v;
-  return 0;
-}
-
-inline unsigned nblk(size_t n, int b = 256) { return static_cast<unsigned>((n + b - 1) / b); }
-inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+namespace {
 
 struct DevBuf {
   void* p = nullptr;
@@ -93,167 +56,6 @@ struct DevBuf {
   }
   template <class T> T* as() const { return static_cast<T*>(p); }
 };
-
-// ---------------------------------------------------------------- tensor-core conv dispatch
-template <int S, int KSTEPS, int CO_PAD, int TILES_X, int G, class Epi, bool SPLIT3 = false, int WS = 4>
-int launch_tc(const CUtensorMap& map, hgru::TcConvArgs a, cudaStream_t st) {
-  using Cfg = hgru::TcConvCfg<S, KSTEPS, CO_PAD, TILES_X, G, WS, SPLIT3>;
-  auto kern = hgru::hconv_tc_kernel<S, KSTEPS, CO_PAD, TILES_X, G, WS, Epi, SPLIT3>;
-  SMEM_ATTR_ONCE(kern, Cfg::kSmemBytes);
-  a.units_x = (a.W + 8 * TILES_X - 1) / (8 * TILES_X);
-  a.units_y = (a.H + hgru::kTileRows - 1) / hgru::kTileRows;
-  a.num_units = a.N * a.units_x * a.units_y;
-  int sms = 0, rc = sm_count(&sms);
-  if (rc) return rc;
-  const int grid = a.num_units < sms ? a.num_units : sms;
-  kern<<<grid, 256, Cfg::kSmemBytes, st>>>(map, a);
-  CUDA_TRY(cudaGetLastError());
-  return 0;
-}
-
-// 64 channels, 15x15 (the reference's own width): the same kernel with the 1x1 gate convs issued from its epilogue
-// and the launches of a forward chained per frame (TcConvCfg FUSE) -- two launches per timestep.  Three weight
-// stages instead of four make room for the gate's staging tile and weights.
-template <class Epi, int G = 5, int WS = 3>
-int launch_tc_fused64(const CUtensorMap& map, hgru::TcConvArgs a, cudaStream_t st) {
-  using Cfg = hgru::TcConvCfg<15, 4, 64, 4, G, WS, false, true>;
-  auto kern = hgru::hconv_tc_kernel<15, 4, 64, 4, G, WS, Epi, false, true>;
-  SMEM_ATTR_ONCE(kern, Cfg::kSmemBytes);
-  a.units_x = (a.W + 31) / 32;
-  a.units_y = (a.H + hgru::kTileRows - 1) / hgru::kTileRows;
-  a.num_units = a.N * a.units_x * a.units_y;
-  a.flag_target = a.units_x * a.units_y;
-  int sms = 0, rc = sm_count(&sms);
-  if (rc) return rc;
-  const int grid = a.num_units < sms ? a.num_units : sms;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = Cfg::kSmemBytes; cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = (a.wait_flags || a.pdl) ? 1 : 0;
-  CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, map, a));
-  return 0;
-}
-
-struct TcGeom { int tiles_x, box_cols, box_rows; };
-// geometry of the window box for a given (S, KP): must match the template instances below
-bool tc_geometry(int S, int KP, TcGeom* g) {
-  if (!(S == 1 || S == 3 || S == 5 || S == 7 || S == 15)) return false;
-  if (!(KP == 16 || KP == 32 || KP == 64)) return false;
-  g->tiles_x = (KP == 64) ? 4 : 8;
-  g->box_cols = 8 * g->tiles_x + S - 1;
-  g->box_rows = hgru::kTileRows + S - 1;
-  return true;
-}
-
-// (S, KP) instances.  KP -> (KSTEPS, TILES_X): 64 -> (4,4), 32 -> (2,8), 16 -> (1,8); G taps per stage.
-#define TC_CASE(Epi_, S_, KP_, KS_, TX_, G_) \
-  if (S == S_ && KP == KP_) return launch_tc<S_, KS_, KP_, TX_, G_, Epi_>(map, a, st);
-#define TC_CASES_S(Epi_, S_, G64_, G32_)  \
-  TC_CASE(Epi_, S_, 64, 4, 4, G64_)       \
-  TC_CASE(Epi_, S_, 32, 2, 8, G32_)       \
-  TC_CASE(Epi_, S_, 16, 1, 8, G32_)
-
-// the horizontal convs with the fused integration epilogues
-template <class Epi>
-int dispatch_tc_hconv(int S, int KP, const CUtensorMap& map, const hgru::TcConvArgs& a, cudaStream_t st) {
-  TC_CASES_S(Epi, 15, 5, 15)
-  TC_CASES_S(Epi, 7, 7, 7)
-  TC_CASES_S(Epi, 5, 5, 5)
-  TC_CASES_S(Epi, 3, 9, 9)
-  TC_CASES_S(Epi, 1, 1, 1)
-  return fail(HGRU_E_UNSUPPORTED, "tensor-core conv: unsupported (S, padded channels)");
-}
-// 3x3 stem convs: bf16 hi + lo operand halves, three products per k-step (SPLIT3): fp32-class accuracy.
-// A SPLIT3 tile owns 2 * KP accumulator columns ([w_hi | w_lo] stacked along N), so two accumulator sets hold
-// 2 / 4 / 8 tiles of 8 columns at 64 / 32 / 16 channels.
-bool stem_geometry(int KP, TcGeom* g) {
-  if (!(KP == 16 || KP == 32 || KP == 64)) return false;
-  g->tiles_x = (KP == 64) ? 2 : (KP == 32) ? 4 : 8;
-  g->box_cols = 8 * g->tiles_x + 2;
-  g->box_rows = hgru::kTileRows + 2;
-  return true;
-}
-int dispatch_tc_stem(int KP, const CUtensorMap& map, const hgru::TcConvArgs& a, cudaStream_t st) {
-  if (KP == 64) return launch_tc<3, 4, 64, 2, 3, hgru::EpiBiasReluAffine, true>(map, a, st);
-  if (KP == 32) return launch_tc<3, 2, 32, 4, 9, hgru::EpiBiasReluAffine, true>(map, a, st);
-  if (KP == 16) return launch_tc<3, 1, 16, 8, 9, hgru::EpiBiasReluAffine, true>(map, a, st);
-  return fail(HGRU_E_UNSUPPORTED, "tensor-core stem conv: unsupported padded channel count");
-}
-// bf16x3 mode: the 15x15 horizontal convs on hi/lo operand splits (window holds both halves, so the unit is
-// narrower the more channels there are: 8 / 4 / 1 tiles of 8 columns for 16 / 32 / 64 channels).
-bool x3_geometry(int S, int KP, TcGeom* g) {
-  if (S != 15 || !(KP == 16 || KP == 32 || KP == 64)) return false;
-  g->tiles_x = (KP == 64) ? 1 : (KP == 32) ? 4 : 8;     // 64 channels: hi + lo windows only fit one 8-column tile
-  g->box_cols = 8 * g->tiles_x + S - 1;
-  g->box_rows = hgru::kTileRows + S - 1;
-  return true;
-}
-template <class Epi>
-int dispatch_tc_hconv_x3(int S, int KP, const CUtensorMap& map, const hgru::TcConvArgs& a, cudaStream_t st) {
-  if (S == 15 && KP == 64) return launch_tc<15, 4, 64, 1, 3, Epi, true>(map, a, st);   // (wide stages: 3 taps each)
-  if (S == 15 && KP == 32) return launch_tc<15, 2, 32, 4, 5, Epi, true>(map, a, st);
-  if (S == 15 && KP == 16) return launch_tc<15, 1, 16, 8, 5, Epi, true>(map, a, st);
-  return fail(HGRU_E_UNSUPPORTED, "bf16x3 conv: unsupported (S, padded channels)");
-}
-#undef TC_CASES_S
-#undef TC_CASE
-
-// ---------------------------------------------------------------- tap-stacked conv (k <= 32, S = 15)
-struct StackGeom { int T, KC, NG, ksteps, box_cols, box_rows, stages, act_pad; };
-bool stack_geometry(int S, int KP, int k, StackGeom* g) {
-  if (S != 15) return false;
-  if (KP == 32 && k <= 25) { g->T = 5; g->KC = 25; }
-  else if (KP == 32) { g->T = 4; g->KC = 32; }
-  else if (KP == 16) { g->T = 8; g->KC = 16; }
-  else return false;
-  g->NG = (15 + g->T - 1) / g->T;
-  g->ksteps = KP / 16;
-  g->box_cols = 64 + g->T * (g->NG - 1) + 8;
-  g->box_rows = hgru::kTileRows + 14;
-  // KC = 25: remainder-packed K schedule (hgru::StackCfg::REM) -- 24 weight stages, 7 pad rows per plane
-  const bool rem = hgru::StackCfg<32, 5, 25, 1>::REM && g->KC == 25;
-  g->stages = rem ? hgru::StackCfg<32, 5, 25, 1>::PASS_STAGES : 15 * g->ksteps;
-  g->act_pad = rem ? hgru::StackCfg<32, 5, 25, 1>::ACT_PAD : 0;
-  return true;
-}
-
-template <int KP, int T, int KC, class Epi, int WSETS = 1, bool PART = false>
-int launch_stack(const CUtensorMap& map, hgru::TcConvArgs a, cudaStream_t st) {
-  // The second launch of a bf16x3 conv (PART) is also the one whose epilogue issues the gate, on hi/lo splits (GX3)
-  // -- except at 32 channels, where the two staging tiles do not fit next to a 3-stage weight ring: that
-  // configuration keeps its gates in the exact SIMT kernel.
-  constexpr bool GX3 = PART && !(KP == 32 && T == 4);
-  using Cfg = hgru::StackCfg<KP, T, KC, 1, GX3>;
-  auto kern = hgru::hconv_stack_kernel<KP, T, KC, 1, Epi, false, WSETS, PART, GX3>;
-  SMEM_ATTR_ONCE(kern, Cfg::SMEM_BYTES);
-  a.units_x = (a.W + 63) / 64;
-  a.units_y = (a.H + hgru::kTileRows - 1) / hgru::kTileRows;
-  a.num_units = a.N * a.units_x * a.units_y;
-  int sms = 0, rc = sm_count(&sms);
-  if (rc) return rc;
-  const int grid = a.num_units < sms ? a.num_units : sms;
-  a.flag_target = a.units_x * a.units_y;
-  // A launch that waits on the previous launch's per-frame counters is chained to it (programmatic dependent
-  // launch): its CTAs take SMs as the previous launch's CTAs exit instead of waiting for the whole grid.
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(Cfg::NTHREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = (a.wait_flags || a.pdl) ? 1 : 0;
-  CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, map, map, a));     // (w_map is only read in pair mode)
-  return 0;
-}
-
-template <class Epi, int WSETS = 1, bool PART = false>
-int dispatch_stack(int KP, int T, const CUtensorMap& map, const hgru::TcConvArgs& a, cudaStream_t st) {
-  if (KP == 32 && T == 5) return launch_stack<32, 5, 25, Epi, WSETS, PART>(map, a, st);
-  if (KP == 32 && T == 4) return launch_stack<32, 4, 32, Epi, WSETS, PART>(map, a, st);
-  if (KP == 16 && T == 8) return launch_stack<16, 8, 16, Epi, WSETS, PART>(map, a, st);
-  return fail(HGRU_E_UNSUPPORTED, "stacked conv: unsupported configuration");
-}
 
 // ---------------------------------------------------------------- 1x1 gate convs (light kernel)
 template <int KP, class Epi>
@@ -557,11 +359,8 @@ static int hgru_set_params_impl(hgru_plan_s* p, const float* p_r, const float* i
     stack_geometry(p->S, KP, k, &sg);
     const size_t ts = static_cast<size_t>(sg.stages) * sg.NG * 2 * 128 * 8;      // elements of one weight set
     for (int part = 0; part < 2; ++part) {      // set 0 = bf16(w), set 1 = bf16(w - bf16(w))
-      __nv_bfloat16* dst = p->wpk.as<__nv_bfloat16>() + part * ts;
-      if (sg.act_pad)
-        hgru::pack_weights_stack_rem_kernel<<<nblk(ts), 256, 0, st>>>(p_r, dst, k, sg.T, sg.KC, sg.NG, part);
-      else
-        hgru::pack_weights_stack_kernel<<<nblk(ts), 256, 0, st>>>(p_r, dst, k, sg.ksteps, sg.T, sg.KC, sg.NG, 1, part);
+      int rc = stack_pack_weights(p_r, p->wpk.as<__nv_bfloat16>() + part * ts, k, sg, part, st);
+      if (rc) return rc;
     }
     const size_t tg = static_cast<size_t>(3 * (KP / 16)) * 2 * KP * 8;
     hgru::pack_weights_split3_kernel<<<nblk(tg), 256, 0, st>>>(i_r, p->wpk_i.as<__nv_bfloat16>(), 1, k, KP / 16, KP);
@@ -575,13 +374,8 @@ static int hgru_set_params_impl(hgru_plan_s* p, const float* p_r, const float* i
     const size_t total = static_cast<size_t>(ksteps) * taps * 2 * KP * 8;
     StackGeom sg;
     if (p->stacked && stack_geometry(p->S, KP, k, &sg)) {
-      const size_t ts = static_cast<size_t>(sg.stages) * sg.NG * 2 * 128 * 8;
-      if (sg.act_pad)
-        hgru::pack_weights_stack_rem_kernel<<<nblk(ts), 256, 0, st>>>(p_r, p->wpk.as<__nv_bfloat16>(), k, sg.T,
-                                                                     sg.KC, sg.NG);
-      else
-        hgru::pack_weights_stack_kernel<<<nblk(ts), 256, 0, st>>>(p_r, p->wpk.as<__nv_bfloat16>(), k, sg.ksteps,
-                                                                 sg.T, sg.KC, sg.NG, 1);
+      int rc = stack_pack_weights(p_r, p->wpk.as<__nv_bfloat16>(), k, sg, 0, st);
+      if (rc) return rc;
     } else {
       hgru::pack_weights_kernel<<<nblk(total), 256, 0, st>>>(p_r, p->wpk.as<__nv_bfloat16>(), taps, k, ksteps, KP);
     }
@@ -693,8 +487,8 @@ static int hgru_run_bf16(hgru_plan_s* p, const float* Xp, const float* H2_init_n
   p->state_ready = false;
   ++p->launches;
   const bool fused = p->stacked || p->fused_tc;
-  // (development switch: weight ring of 5 stages x 3 taps instead of 3 stages x 5 taps for the fused 64-channel kernel)
-  static const bool ring35 = [] { const char* e = getenv("HGRU_F64_RING35"); return e && e[0] == '1'; }();
+  // (a weight ring of 5 stages x 3 taps instead of 3 stages x 5 taps for the fused 64-channel kernel measured the
+  // same: profiles/r02_bench_k64_fused_ring_5x3taps.json)
   static const bool fp32_hg = [] { const char* e = getenv("HGRU_FP32_HG"); return e && e[0] == '1'; }();
   // Chained launches (see TcConvArgs::wait_flags): launch l waits per frame on launch l-1's counters instead of on
   // the whole grid.  Not with traces (their copy kernels sit between the launches).
@@ -735,11 +529,9 @@ static int hgru_run_bf16(hgru_plan_s* p, const float* Xp, const float* H2_init_n
     if (!chain) p->timer.begin(st);
     // (fused pipeline: H1 and G2 travel to the H2 launch as fp16, EpiH1h / EpiH2h; development switch
     // HGRU_FP32_HG=1: as fp32 on the stacked kernel, for A/B runs)
-    if ((rc = (p->stacked && fp32_hg) ? dispatch_stack<hgru::EpiH1>(KP, p->stack_T, p->mapA, a, st)
-              : p->stacked  ? dispatch_stack<hgru::EpiH1h>(KP, p->stack_T, p->mapA, a, st)
-              : p->fused_tc ? (ring35 ? launch_tc_fused64<hgru::EpiH1h, 3, 5>(p->mapA, a, st)
-                                      : launch_tc_fused64<hgru::EpiH1h>(p->mapA, a, st))
-                            : dispatch_tc_hconv<hgru::EpiH1>(p->S, KP, p->mapA, a, st)))
+    if ((rc = p->stacked    ? stack_launch(fp32_hg ? EPI_H1 : EPI_H1_HALF, 1, false, KP, p->stack_T, p->mapA, a, st)
+              : p->fused_tc ? tc_fused64_launch(EPI_H1_HALF, p->mapA, a, st)
+                            : tc_hconv_launch(EPI_H1, p->S, KP, p->mapA, a, st)))
       return rc;
     if (!chain) p->timer.end(st);
     ++p->launches;
@@ -767,11 +559,9 @@ static int hgru_run_bf16(hgru_plan_s* p, const float* Xp, const float* H2_init_n
     }
     set_flags(a, 2 * t + 1);
     if (!chain) p->timer.begin(st);
-    if ((rc = (p->stacked && fp32_hg) ? dispatch_stack<hgru::EpiH2>(KP, p->stack_T, p->mapH1, a, st)
-              : p->stacked  ? dispatch_stack<hgru::EpiH2h>(KP, p->stack_T, p->mapH1, a, st)
-              : p->fused_tc ? (ring35 ? launch_tc_fused64<hgru::EpiH2h, 3, 5>(p->mapH1, a, st)
-                                      : launch_tc_fused64<hgru::EpiH2h>(p->mapH1, a, st))
-                            : dispatch_tc_hconv<hgru::EpiH2>(p->S, KP, p->mapH1, a, st)))
+    if ((rc = p->stacked    ? stack_launch(fp32_hg ? EPI_H2 : EPI_H2_HALF, 1, false, KP, p->stack_T, p->mapH1, a, st)
+              : p->fused_tc ? tc_fused64_launch(EPI_H2_HALF, p->mapH1, a, st)
+                            : tc_hconv_launch(EPI_H2, p->S, KP, p->mapH1, a, st)))
       return rc;
     if (!chain) p->timer.end(st);
     else if (t + 1 == p->T && last_group) p->timer.end(st, 2 * p->T);   // chained: one interval around all launches,
@@ -844,7 +634,7 @@ static int hgru_run_bf16x3(hgru_plan_s* p, const float* Xp, const float* H2_init
       hgru::TcConvArgs a = base;
       a.wpk = p->wpk.as<__nv_bfloat16>(); a.out = p->C.as<float>();
       set_flags(a, 4 * t);
-      if ((rc = dispatch_stack<hgru::EpiPartial, 1>(KP, p->stack_T, p->mapA_lo, a, st))) return rc;
+      if ((rc = stack_launch(EPI_PARTIAL, 1, false, KP, p->stack_T, p->mapA_lo, a, st))) return rc;
       a = base;
       a.wpk = p->wpk.as<__nv_bfloat16>(); a.partial = p->C.as<float>();
       a.bias = p->vec(V_LBIAS); a.X = Xp; a.H2 = p->H2.as<float>(); a.v0 = p->vec(V_BETA); a.v1 = p->vec(V_NU);
@@ -852,7 +642,7 @@ static int hgru_run_bf16x3(hgru_plan_s* p, const float* Xp, const float* H2_init
       a.gate_wpk = p->wpk_o.as<__nv_bfloat16>(); a.gate_bias = p->vec(V_OB); a.gate_out = p->G.as<float>();
       a.do_gate = fused_gate ? 1 : 0;
       set_flags(a, 4 * t + 1);
-      if ((rc = dispatch_stack<hgru::EpiH1, 2, true>(KP, p->stack_T, p->mapA, a, st))) return rc;
+      if ((rc = stack_launch(EPI_H1, 2, true, KP, p->stack_T, p->mapA, a, st))) return rc;
       if (!chain) p->timer.end(st);
       if (!fused_gate) {
         // circuit_output gate (:729-740): G2 = sigmoid(H1 *1x1 o_r + o_b), exact fp32
@@ -866,7 +656,7 @@ static int hgru_run_bf16x3(hgru_plan_s* p, const float* Xp, const float* H2_init
       a = base;
       a.wpk = p->wpk.as<__nv_bfloat16>(); a.out = p->C.as<float>();
       set_flags(a, 4 * t + 2);
-      if ((rc = dispatch_stack<hgru::EpiPartial, 1>(KP, p->stack_T, p->mapH1_lo, a, st))) return rc;
+      if ((rc = stack_launch(EPI_PARTIAL, 1, false, KP, p->stack_T, p->mapH1_lo, a, st))) return rc;
       a = base;
       a.wpk = p->wpk.as<__nv_bfloat16>(); a.partial = p->C.as<float>();
       a.bias = p->vec(V_LBIAS); a.H1 = p->H1.as<float>(); a.G = p->G.as<float>(); a.H2 = p->H2.as<float>();
@@ -879,7 +669,7 @@ static int hgru_run_bf16x3(hgru_plan_s* p, const float* Xp, const float* H2_init
         a.fc_a = p->fc_a; a.fc_scale = p->fc_scale; a.fc_shift = p->fc_shift; a.fc_kpad = p->fc_kpad;
       }
       set_flags(a, 4 * t + 3);
-      if ((rc = dispatch_stack<hgru::EpiH2, 2, true>(KP, p->stack_T, p->mapH1, a, st))) return rc;
+      if ((rc = stack_launch(EPI_H2, 2, true, KP, p->stack_T, p->mapH1, a, st))) return rc;
       if (!chain) p->timer.end(st);
       else if (t + 1 == p->T) p->timer.end(st, 2 * p->T);      // chained: one interval, counted as 2T convs
       p->launches += 4;
@@ -907,7 +697,7 @@ static int hgru_run_bf16x3(hgru_plan_s* p, const float* Xp, const float* H2_init
     a.v0 = p->vec(V_BETA); a.v1 = p->vec(V_NU);
     a.out = p->H1.as<float>(); a.out_bf16 = p->actH1.as<__nv_bfloat16>();
     p->timer.begin(st);
-    if ((rc = dispatch_tc_hconv_x3<hgru::EpiH1>(p->S, KP, p->mapA, a, st))) return rc;
+    if ((rc = tc_x3_launch(EPI_H1, p->S, KP, p->mapA, a, st))) return rc;
     p->timer.end(st);
     // circuit_output gate (:729-740): G2 = sigmoid(H1 *1x1 o_r + o_b), exact fp32
     hgru::gate_quad_split_kernel<<<nblk(p->npix, hgru::kInitPix), 256, gsmem, st>>>(
@@ -922,7 +712,7 @@ static int hgru_run_bf16x3(hgru_plan_s* p, const float* Xp, const float* H2_init
       a.fc_a = p->fc_a; a.fc_scale = p->fc_scale; a.fc_shift = p->fc_shift; a.fc_kpad = p->fc_kpad;
     }
     p->timer.begin(st);
-    if ((rc = dispatch_tc_hconv_x3<hgru::EpiH2>(p->S, KP, p->mapH1, a, st))) return rc;
+    if ((rc = tc_x3_launch(EPI_H2, p->S, KP, p->mapH1, a, st))) return rc;
     p->timer.end(st);
     p->launches += 4;
     if (H1_trace) {
@@ -1068,11 +858,11 @@ static int pose_forward_impl(pose_plan_s* p, const float* depth, const float* H2
     a.wpk = p->wpk2.as<__nv_bfloat16>(); a.bias = p->b2.as<float>();
     a.scale = p->bn_scale(1); a.shift = p->bn_shift(1);
     a.out = nullptr; a.out_bf16 = p->act_conv2.as<__nv_bfloat16>();      // (no fp32 copy: see pose_plan_create)
-    if ((rc = dispatch_tc_stem(KP, p->map_pool1, a, st))) return rc;
+    if ((rc = tc_stem_launch(KP, p->map_pool1, a, st))) return rc;
     a.wpk = p->wpk3.as<__nv_bfloat16>(); a.bias = p->b3.as<float>();
     a.scale = p->bn_scale(2); a.shift = p->bn_shift(2);
     a.out = h->Xp.as<float>(); a.out_bf16 = nullptr;
-    if ((rc = dispatch_tc_stem(KP, p->map_conv2, a, st))) return rc;
+    if ((rc = tc_stem_launch(KP, p->map_conv2, a, st))) return rc;
   } else {
     if ((rc = dispatch_simt_conv(3, p->pool1.as<float>(), p->w2.as<float>(), p->b2.as<float>(), p->bn_scale(1),
                                  p->bn_shift(1), p->conv2.as<float>(), N, HW, HW, KP, KP, 1, st)))
