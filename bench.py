@@ -463,6 +463,10 @@ def neighbour_stages(a, m, torch, mp, init_mod):
         return xyz.cpu()
 
     chain_gpu_ms, chain_wall_ms, _ = ev_time(chain, 3)
+    # the same chain through the package's pipeline helper: upload in four pieces on a copy stream, the attention CNN
+    # on each piece as it lands
+    pipe = mp.FramesToJoints(am, m, md, Cfg(), cube_z=1200.0, chunks=4)
+    _, pipe_wall_ms, _ = ev_time(lambda: pipe(frames_pin, centres=coms_norm_dev), 3)
     hbm = None
     try:
         hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs")
@@ -486,6 +490,9 @@ def neighbour_stages(a, m, torch, mp, init_mod):
                               "note": "attn_model_struct.build at 64..1024 channels: resize + 5 x (conv, relu, "
                                       "pool, batch-norm) + 2 fc; convs 2-5 as implicit tcgen05 GEMMs (4-D TMA boxes of the NHWC "
                                       "activation per tap) with bf16 hi/lo splits (3 MMAs per k-step)"},
+            "frames_to_joints_pipelined_e2e": {"value": B / (pipe_wall_ms * 1e-3), "unit": UNIT, "wall_ms": pipe_wall_ms,
+                                               "note": "monkey_pose_b200.FramesToJoints: same stages, upload in 4 pieces "
+                                                       "on a copy stream under the attention CNN"},
             "frames_to_joints_e2e": {"value": B / (chain_wall_ms * 1e-3), "unit": UNIT, "wall_ms": chain_wall_ms,
                                      "stages": "H2D frames, attention CNN, crop, hGRU pose net, post-processing, "
                                                "D2H joints",

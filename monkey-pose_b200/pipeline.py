@@ -1,0 +1,76 @@
+"""Camera frames -> joints on the device: the inference loop of the reference (`test_model` / `eval_model_on_real_data`,
+train_cnn_networks_hgru.py:264-419 -- attention CNN, `prepare_data_test`, pose network, x cube[2]/2,
+`getAbsoluteCoordinates`, one frame at a time through two `sess.run` calls and a host crop) for a whole batch with no
+host round trip between the stages, and with the upload of the frames overlapped with the attention CNN:
+
+    frames (pinned host, [N,H,W] float32 in [0,1])
+      --H2D in `chunks` pieces on a copy stream-->  attention CNN per piece as it lands  -->  centres of mass (device)
+      --> window arithmetic + crop (device) --> pose network (fused tensor-core forward) --> absolute joints (device)
+      --D2H--> xyz, uvd [N,23,3]
+
+Everything numerical runs in libhgru_b200.so; this module only orders the calls on two CUDA streams.  No CPU fallback.
+"""
+import torch
+
+from .tf_monkeydetector import prepare_data_test
+
+
+class FramesToJoints(object):
+    """attn: `attn_model_struct`, pose: `model` (parameters loaded), md: `tfMonkeyDetector`, config: an object with
+    `image_orig_size`, `image_target_size`, `image_max_depth` (the reference's `monkeyConfig`), cube_z: seqconfig
+    ['cube'][2] (mm).  `chunks`: pieces the upload is cut into (the attention CNN starts on piece c while piece c+1 is
+    on the bus); 1 = plain stream order."""
+
+    def __init__(self, attn, pose, md, config, cube_z=1200.0, num_joints=23, chunks=4):
+        self.attn, self.pose, self.md, self.config = attn, pose, md, config
+        self.scale = float(cube_z) / 2.0
+        self.out_dims = 3 * int(num_joints)
+        self.chunks = int(chunks)
+        self._copy_stream = None
+        self._frames_dev = None
+        self._events = None
+
+    def _buffers(self, shape, device):
+        if self._frames_dev is None or tuple(self._frames_dev.shape) != tuple(shape):
+            self._frames_dev = torch.empty(shape, device=device, dtype=torch.float32)
+            self._tr = torch.empty((shape[0], 3), device=device, dtype=torch.float32)
+            self._copy_stream = torch.cuda.Stream(device=device)
+            self._events = [torch.cuda.Event() for _ in range(max(1, self.chunks))]
+        return self._frames_dev
+
+    def __call__(self, frames, centres=None):
+        """frames: [N,H,W] float32, pinned host memory (or a CUDA tensor: then nothing is uploaded).
+        centres: optional CUDA float32 [N,3] replacing the attention CNN's output (it still runs).
+        Returns (xyz, uvd): [N,J,3] float32 on the host (pinned), camera-space mm and image-space (u, v, d)."""
+        if frames.dim() == 4:
+            frames = frames[..., 0]
+        N = int(frames.shape[0])
+        main = torch.cuda.current_stream()
+        if frames.is_cuda:
+            dev_frames, pieces = frames.to(torch.float32).contiguous(), [(0, N)]
+            self._buffers(frames.shape, frames.device)
+        else:
+            dev_frames = self._buffers(frames.shape, torch.device("cuda", torch.cuda.current_device()))
+            # equal pieces only (one attention plan serves them all); small or indivisible batches go up in one piece
+            nch = self.chunks if (self.chunks > 1 and N >= 4 * self.chunks and N % self.chunks == 0) else 1
+            per = (N + nch - 1) // nch
+            pieces = [(lo, min(lo + per, N)) for lo in range(0, N, per)]
+            self._copy_stream.wait_stream(main)                 # the previous call's readers are done with the buffer
+            with torch.cuda.stream(self._copy_stream):
+                for i, (lo, hi) in enumerate(pieces):
+                    dev_frames[lo:hi].copy_(frames[lo:hi], non_blocking=True)
+                    self._events[i].record(self._copy_stream)
+        for i, (lo, hi) in enumerate(pieces):
+            if not frames.is_cuda:
+                main.wait_event(self._events[i])
+            self._tr[lo:hi] = self.attn.build(dev_frames[lo:hi], 3)                  # train_cnn_networks_hgru.py:281-283
+        tr = self._tr if centres is None else centres
+        patches, coms, _ = prepare_data_test(dev_frames, tr, self.md, self.config)   # :284 (window arithmetic on device)
+        out = self.pose.build(patches, self.out_dims)                                # :291-294
+        xyz, uvd = self.md.getAbsoluteCoordinates_batch(out, coms, self.scale)       # :295-298
+        xyz_h = torch.empty(xyz.shape, dtype=torch.float32, pin_memory=True)
+        uvd_h = torch.empty(uvd.shape, dtype=torch.float32, pin_memory=True)
+        xyz_h.copy_(xyz, non_blocking=True)
+        uvd_h.copy_(uvd, non_blocking=True)
+        main.synchronize()
+        return xyz_h, uvd_h

@@ -360,6 +360,42 @@ def test_crop_window_arithmetic_on_the_device_equals_the_host():
     assert torch.equal(xyz_h[good], xyz_d[good]) and torch.equal(uvd_h[good], uvd_d[good])
 
 
+def test_frames_to_joints_pipeline_equals_the_stage_by_stage_sequence():
+    """FramesToJoints (chunked upload on a copy stream, attention CNN per chunk, device-side window arithmetic, pose
+    network, absolute coordinates) against the same stages called one after the other on resident frames: bitwise."""
+    from monkey_pose_b200 import tf_monkeydetector as tmd
+    rng = np.random.default_rng(21)
+    n, h, w = 16, 424, 512
+    base = np.round(rng.uniform(600, 4000, size=(4, h, w)) / 8) * 8
+    frames_np = (base[rng.integers(0, 4, n)] / 10000.0).astype(np.float32)
+    centres = np.stack([rng.uniform(0.3, 0.9, n), rng.uniform(0.25, 0.7, n), rng.uniform(0.1, 0.3, n)], 1).astype(np.float32)
+    md = tmd.tfMonkeyDetector(365.456, 365.456, 256, 212, [800, 800, 1200], 200, 10000)
+    am = mp.attn_model_struct()
+    am.widths, am.fc_hidden = (8, 8, 8, 8, 8), 16
+    am.load_params(init.attn_params(widths=am.widths, fc_hidden=16, out=3, seed=8))
+    pm = mp.model()
+    pm.channels, pm.timesteps, pm.fc_hidden = 25, 2, 32
+    pm.hidden_state = init.hidden_init((n, 64, 64, 25), seed=5)
+    pm.load_params(init.pose_params(channels=25, S=15, T=2, hw=64, fc_hidden=32, out=69, seed=3, stress=4.0))
+    c_dev = torch.as_tensor(centres).cuda()
+    pipe = mp.FramesToJoints(am, pm, md, _Cfg(), cube_z=1200.0, chunks=4)
+    xyz, uvd = pipe(torch.as_tensor(frames_np).pin_memory(), centres=c_dev)
+    xyz2, uvd2 = pipe(torch.as_tensor(frames_np).pin_memory(), centres=c_dev)          # buffers are reused
+    assert torch.equal(xyz, xyz2) and torch.equal(uvd, uvd2)
+    # the attention CNN ran on every chunk (its split-K layout follows the batch size, so chunks of 4 frames and one
+    # batch of 16 agree to rounding, not bit for bit)
+    f_dev = torch.as_tensor(frames_np).cuda()
+    tr_ref = am.build(f_dev, 3)
+    assert torch.allclose(pipe._tr, tr_ref, rtol=1e-4, atol=1e-6)
+    p, cs, _ = tmd.prepare_data_test(f_dev, c_dev, md, _Cfg())
+    x_ref, u_ref = md.getAbsoluteCoordinates_batch(pm.build(p, 69), cs, 600.0)
+    assert torch.equal(xyz, x_ref.cpu()) and torch.equal(uvd, u_ref.cpu())
+    assert xyz.shape == (n, 23, 3) and torch.isfinite(xyz).all()
+    # driven by the attention output itself (random-init: most windows miss the frame -> background patches, still finite)
+    xyz3, _ = pipe(torch.as_tensor(frames_np).pin_memory())
+    assert torch.isfinite(xyz3).all()
+
+
 # ---- post-processing (SURVEY 8f rank 2) -------------------------------------------------------------
 def test_postprocess_bit_exact_against_reference_golden():
     from monkey_pose_b200 import pose_evaluation as pe
