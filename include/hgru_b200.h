@@ -148,6 +148,10 @@ HGRU_API int layer_conv2d_forward(const float* x_dev, int N, int H, int W, int C
 HGRU_API int layer_max_pool2x2_forward(const float* x_dev, int N, int H, int W, int C, float* out_dev, void* stream);
 HGRU_API int layer_fc_forward(const float* x_dev, int M, int K, const float* weights_dev, const float* biases_dev,
                               int F, float* out_dev, void* stream);
+/* tf.image.resize_images(x, [OH, OW]) of the attention CNN (train_cnn_networks_hgru.py:442): TF 1.x bilinear,
+ * align_corners = false, float32 without fused multiply-adds (bit-exact); x [N,H,W] -> out [N,OH,OW]. */
+HGRU_API int layer_resize_bilinear_forward(const float* x_dev, int N, int H, int W, int OH, int OW, float* out_dev,
+                                           void* stream);
 HGRU_API int layer_batch_norm_forward(const float* x_dev, size_t rows, int C, const float* gamma_dev,
                                       const float* beta_dev, const float* moving_mean_dev,
                                       const float* moving_var_dev, float epsilon, int training, int relu_first,

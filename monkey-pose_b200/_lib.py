@@ -64,6 +64,7 @@ SIGNATURES = {
     "layer_conv2d_forward": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _P, _I, _P, _P]),
     "layer_max_pool2x2_forward": (_I, [_P, _I, _I, _I, _I, _P, _P]),
     "layer_fc_forward": (_I, [_P, _I, _I, _P, _P, _I, _P, _P]),
+    "layer_resize_bilinear_forward": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
     "layer_batch_norm_forward": (_I, [_P, ctypes.c_size_t, _I, _P, _P, _P, _P, ctypes.c_float, _I, _I, ctypes.c_float,
                                       ctypes.c_ulonglong, ctypes.c_float, _P, _P, _P, _P, _P]),
     "crop_area3d_forward": (_I, [_P, _I, _I, _I, ctypes.c_float, _P, _P, ctypes.c_float, ctypes.c_double, _P,

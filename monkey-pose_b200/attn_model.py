@@ -5,8 +5,12 @@
 (:615-633).  `depth` is a torch CUDA tensor [N,H,W,1] (or [N,H,W]) instead of a tf.Tensor; the forward runs in
 libhgru_b200.so (`attn_*` entry points of include/hgru_b200.h) -- there is no CPU fallback.
 
-Inference mode only: `train_mode=True` (dropout + batch statistics, :504-505) raises NotImplementedError.
-Non-reference knobs: `widths`, `fc_hidden` (defaults = the reference's 64..1024 / 1024), `seed`.
+`train_mode` in (None, False): the fused tensor-core pipeline, inference-mode batch norm (moving statistics).
+`train_mode=True` -- what the reference passes both in training (:117) and, as committed, in
+`eval_model_on_real_data` (:360) -- composes the graph layer by layer from the class's own layer methods
+(`monkey_pose_b200.layers.LayerOps`): batch statistics in the six batch norms, dropout keep 0.7 after relu(afc_1)
+with the documented counter-based mask, moving-statistics updates in `updated_moving_stats`.  Forward only.
+Non-reference knobs: `widths`, `fc_hidden` (defaults = the reference's 64..1024 / 1024), `seed`, `dropout_seed`.
 """
 import ctypes
 
@@ -16,11 +20,13 @@ import torch
 from . import _lib
 from . import initialization as init
 from .hgru_module import _as_dev, _stream
+from .layers import LayerOps
 
 _BN_FIELDS = ("gamma", "beta", "moving_mean", "moving_variance")
 
 
-class attn_model_struct:
+class attn_model_struct(LayerOps):
+    _bn_scopes = init.ATTN_BN_SCOPES
 
     def __init__(self, trainable=True):
         self.trainable = trainable
@@ -32,6 +38,7 @@ class attn_model_struct:
         self.widths = (64, 128, 256, 512, 1024)     # :443, :456, :469, :482, :495
         self.fc_hidden = 1024                        # :501 (and hard-coded again at :522)
         self.seed = 42
+        self.dropout_seed = 1234
         self._plan = None
         self._plan_key = None
         self._dev_params = None
@@ -76,17 +83,6 @@ class attn_model_struct:
         self.load_params(flat)
         return sorted(flat)
 
-    def get_var(self, initial_value, name, idx, var_name, in_size=None, out_size=None):
-        """:615-633: value from data_dict[name][idx] when present, else the initial value; registered in
-        var_dict[(name, idx)]."""
-        if self.data_dict is not None and name in self.data_dict:
-            value = self.data_dict[name][idx]
-        else:
-            value = initial_value
-        var = _as_dev(value)
-        self.var_dict[(name, idx)] = var
-        return var
-
     def _materialise(self, output_shape):
         fresh = init.attn_params(self.widths, self.fc_hidden, output_shape, self.seed)
         P = {}
@@ -108,8 +104,6 @@ class attn_model_struct:
     def build(self, depth, output_shape, batch_norm=None, train_mode=None):
         """:440-525.  depth [N,H,W,1] / [N,H,W] torch CUDA float32 (already divided by image_max_depth, as every
         caller does, e.g. train_cnn_networks.py:115-116); sets and returns `out_put` [N, output_shape]."""
-        if train_mode:
-            raise NotImplementedError("attn_model_struct: training mode (dropout, batch statistics) is not built")
         if not (torch.is_tensor(depth) and depth.is_cuda):
             raise RuntimeError("attn_model_struct.build needs a torch CUDA tensor (there is no CPU fallback)")
         if depth.dim() == 4:
@@ -120,6 +114,11 @@ class attn_model_struct:
             raise ValueError("depth must be [N,H,W,1] or [N,H,W]")
         depth = depth.to(torch.float32).contiguous()
         N, H, W = [int(v) for v in depth.shape]
+        if train_mode:
+            return self._build_layerwise(depth, int(output_shape), train_mode)
+        for nme in ("pool1", "pool2", "pool3", "pool4", "pool5", "fc1", "relu1", "conv1", "conv2", "conv3", "conv4",
+                    "conv5"):
+            self.__dict__.pop(nme, None)           # tensors of an earlier training-mode build
         lib = _lib.load()
         if self._dev_params is None:
             self._dev_params = self._materialise(int(output_shape))
@@ -154,6 +153,37 @@ class attn_model_struct:
         self.fcout = out
         self.out_put = out
         return out
+
+    def _build_layerwise(self, depth, output_shape, train_mode):
+        """:440-525 statement by statement on the layer methods (batch norm over the last axis of the fc tensor, R-D5)."""
+        self.updated_moving_stats = {}
+        complete = self.data_dict is not None and all(
+            n in self.data_dict for n in [c for c, _ in init.ATTN_CONV] + ["afc_1", "afc_out"] + list(init.ATTN_BN_SCOPES))
+        if not complete:
+            self._defaults = init.attn_params(self.widths, self.fc_hidden, output_shape, self.seed)
+        else:
+            self._defaults = None
+        x = self.resize_images(depth, [128, 128])                                                   # :442
+        cin = 1
+        for i, ((name, fs), co) in enumerate(zip(init.ATTN_CONV, self.widths)):
+            if self.data_dict is not None and name in self.data_dict:
+                co = int(np.asarray(self.data_dict[name][0]).shape[3])
+            conv = self.conv_layer(x, cin, co, name, filter_size=fs)                                 # :443 ...
+            setattr(self, "conv%d" % (i + 1), conv)
+            x = self.batch_normalization(self.max_pool(conv, "apool_%d" % (i + 1)), i, train_mode)   # :444-454 ...
+            setattr(self, "pool%d" % (i + 1), x)
+            cin = co
+        in_size = int(np.prod([int(v) for v in x.shape[1:]]))
+        fch = self.fc_hidden
+        if self.data_dict is not None and "afc_1" in self.data_dict:
+            fch = int(np.asarray(self.data_dict["afc_1"][0]).shape[1])
+        self.fc1 = self.fc_layer(x, in_size, fch, "afc_1")                                           # :501
+        self.relu1 = self.batch_normalization(self.fc1, 5, train_mode, relu_first=True,              # :502-513
+                                              dropout_keep=0.7 if train_mode is True else 1.0)
+        self.fcout = self.fc_layer(self.relu1, fch, output_shape, "afc_out")                         # :524
+        self.out_put = self.fcout
+        self.gpu_launches = 1 + 5 * 4 + 2 + 2
+        return self.out_put
 
     def activation(self, name):
         """Intermediate tensors of the last build(): 'resized', 'pool1'..'pool5' (after batch-norm, :444-499),

@@ -1275,6 +1275,17 @@ int layer_fc_forward(const float* x, int M, int K, const float* weights, const f
   return 0;
 }
 
+int layer_resize_bilinear_forward(const float* x, int N, int H, int W, int OH, int OW, float* out, void* stream) {
+  if (!x || !out) return fail(HGRU_E_INVALID, "layer_resize_bilinear_forward: null pointer");
+  if (N < 1 || H < 1 || W < 1 || OH < 1 || OW < 1) return fail(HGRU_E_INVALID, "layer_resize_bilinear_forward: non-positive shape");
+  const size_t total = static_cast<size_t>(N) * OH * OW;
+  // TF 1.x: scale = in / out in float32 (kernels/resize_bilinear_op.cc CalculateResizeScale)
+  const float sh = static_cast<float>(H) / static_cast<float>(OH), sw = static_cast<float>(W) / static_cast<float>(OW);
+  hgru::resize_bilinear_kernel<<<nblk(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, out, N, H, W, OH, OW, sh, sw);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 int layer_batch_norm_forward(const float* x, size_t rows, int C, const float* gamma, const float* beta,
                              const float* moving_mean, const float* moving_var, float eps, int training,
                              int relu_first, float dropout_keep, unsigned long long dropout_seed, float momentum,

@@ -46,24 +46,32 @@ def resize_bilinear_tf1(x, oh, ow):
     return (top + (bot - top) * yl).astype(np.float32)
 
 
-def _bn(x, P, scope, eps):
+def _bn(x, P, scope, eps, train_mode=False):
+    if train_mode:      # tf.layers.batch_normalization(training=True): statistics of the batch
+        return onp.batch_norm_training(x, P[scope + "/gamma"], P[scope + "/beta"], eps)
     return onp.batch_norm_inference(x, P[scope + "/gamma"], P[scope + "/beta"], P[scope + "/moving_mean"],
                                     P[scope + "/moving_variance"], eps)
 
 
-def attn_forward(frames, params, eps=1e-5, trace=False):
+def attn_forward(frames, params, eps=1e-5, trace=False, train_mode=False, dropout_keep=None, dropout_seed=0):
     """frames [N,H,W,1] (depth / image_max_depth); params keyed by the reference's variable names
     (`aconv_1/aconv_1_filters`, ..., `afc_out/afc_out_biases`, `batch_normalization[_i]/...`).  Returns
-    out_put [N,3] (float64), plus the intermediate activations when trace."""
+    out_put [N,3] (float64), plus the intermediate activations when trace.  train_mode: batch statistics in the six
+    batch norms (:446-513, `training=train_mode`); dropout (:504-505) only when `dropout_keep` is given, with the
+    documented counter-based mask (hgru_oracle_np.dropout_keep_mask)."""
     P = params
     acts = {"resized": resize_bilinear_tf1(frames, 128, 128)}
     x = acts["resized"].astype(np.float64)
     for i, name in enumerate(CONV_NAMES):
         conv = onp.conv_layer(x, P["%s/%s_filters" % (name, name)], P["%s/%s_biases" % (name, name)])   # conv+bias+relu
-        x = _bn(onp.max_pool_2x2(conv), P, BN_SCOPES[i], eps)
+        x = _bn(onp.max_pool_2x2(conv), P, BN_SCOPES[i], eps, train_mode)
         acts["pool%d" % (i + 1)] = x
     fc1 = onp.fc_layer(x, P["afc_1/afc_1_weights"], P["afc_1/afc_1_biases"])
-    relu1 = _bn(np.maximum(fc1, 0.0), P, BN_SCOPES[5], eps)
+    r = np.maximum(fc1, 0.0)
+    if dropout_keep is not None and dropout_keep < 1.0:
+        keep = onp.dropout_keep_mask(r.size, dropout_keep, dropout_seed).reshape(r.shape)
+        r = np.where(keep, r / np.float64(np.float32(dropout_keep)), 0.0)
+    relu1 = _bn(r, P, BN_SCOPES[5], eps, train_mode)
     out = onp.fc_layer(relu1, P["afc_out/afc_out_weights"], P["afc_out/afc_out_biases"])
     acts.update(fc1=fc1, relu1=relu1, out_put=out)
     return (out, acts) if trace else out

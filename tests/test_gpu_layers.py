@@ -106,6 +106,35 @@ def test_train_mode_forward_vs_oracle(mode):
     assert onp.rel_err(out_inf.cpu().numpy(), ref_inf)[0] < tol
 
 
+def test_attention_cnn_train_mode_forward_vs_oracle():
+    """attn_model_struct.build(train_mode=True) -- what the reference passes in training (train_cnn_networks_hgru.py:117)
+    and, as committed, in eval_model_on_real_data (:360): batch statistics in the six batch norms, dropout after
+    relu(afc_1), composed from the class's layer methods (incl. the bit-exact TF-1.x bilinear resize)."""
+    from oracle import attn_oracle_np as anp
+    N, H, W, widths, F = 5, 96, 80, (8, 24, 16, 40, 32), 64
+    P = init.attn_params(widths, F, 3, seed=5, random_bn=True)
+    rng = np.random.default_rng(3)
+    frames = rng.uniform(0.06, 0.4, size=(N, H, W, 1)).astype(np.float32)
+    frames[rng.uniform(size=frames.shape) < 0.05] = 0.0
+    m = mp.attn_model_struct()
+    m.dropout_seed = 77
+    m.load_params(P)
+    out = m.build(torch.as_tensor(frames).cuda(), 3, train_mode=True)
+    ref, acts = anp.attn_forward(frames, P, trace=True, train_mode=True, dropout_keep=0.7, dropout_seed=77)
+    assert np.array_equal(m.resize_images(torch.as_tensor(frames).cuda(), [128, 128]).cpu().numpy(), acts["resized"])
+    for k in ("pool1", "pool3", "pool5"):
+        assert onp.rel_err(getattr(m, k).cpu().numpy(), acts[k])[0] < 1e-4, k
+    assert onp.rel_err(m.fc1.cpu().numpy(), acts["fc1"])[0] < 1e-4
+    assert onp.rel_err(m.relu1.cpu().numpy(), acts["relu1"])[0] < 1e-4
+    assert onp.rel_err(out.cpu().numpy(), ref)[0] < 1e-4
+    assert set(m.updated_moving_stats) == set(init.ATTN_BN_SCOPES)
+    # inference mode afterwards: the fused pipeline, moving statistics
+    out_inf = m.build(torch.as_tensor(frames).cuda(), 3)
+    ref_inf = anp.attn_forward(frames, P)
+    assert onp.rel_err(out_inf.cpu().numpy(), ref_inf)[0] < 1e-4
+    assert onp.rel_err(m.pool5.cpu().numpy(), anp.attn_forward(frames, P, trace=True)[1]["pool5"])[0] < 1e-4
+
+
 def test_attribute_surface_after_inference_build():
     """conv1, pool1, conv2, conv3, hgru, fc1, relu1, fc4, out_put (hgru_pose.py:50-105) -- batch-normalised where
     the reference re-assigns them -- materialised on first access after the fused forward."""

@@ -459,8 +459,6 @@ def test_attn_model_vs_oracle(cfg):
     assert onp.rel_err(out.cpu().numpy(), ref.numpy())[0] < 1e-4
     # determinism + the error convention of the mirror
     assert torch.equal(out, m.build(torch.as_tensor(frames).cuda(), 3))
-    with pytest.raises(NotImplementedError):
-        m.build(torch.as_tensor(frames).cuda(), 3, train_mode=True)
     with pytest.raises(RuntimeError):
         m.build(torch.as_tensor(frames), 3)
 
