@@ -467,6 +467,9 @@ def neighbour_stages(a, m, torch, mp, init_mod):
     # on each piece as it lands
     pipe = mp.FramesToJoints(am, m, md, Cfg(), cube_z=1200.0, chunks=4)
     _, pipe_wall_ms, _ = ev_time(lambda: pipe(frames_pin, centres=coms_norm_dev), 3)
+    # ... and fed raw 16-bit millimetre frames (what a depth camera delivers; thresholds + normalisation on the device)
+    raw_pin = torch.from_numpy(np.round(frames_np * 10000.0).astype(np.uint16).view(np.int16)).pin_memory()
+    _, pipe16_wall_ms, _ = ev_time(lambda: pipe(raw_pin, centres=coms_norm_dev), 3)
     hbm = None
     try:
         hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs")
@@ -493,6 +496,9 @@ def neighbour_stages(a, m, torch, mp, init_mod):
             "frames_to_joints_pipelined_e2e": {"value": B / (pipe_wall_ms * 1e-3), "unit": UNIT, "wall_ms": pipe_wall_ms,
                                                "note": "monkey_pose_b200.FramesToJoints: same stages, upload in 4 pieces "
                                                        "on a copy stream under the attention CNN"},
+            "frames_to_joints_pipelined_raw16_e2e": {"value": B / (pipe16_wall_ms * 1e-3), "unit": UNIT,
+                                                     "wall_ms": pipe16_wall_ms, "h2d_bytes": int(raw_pin.numel() * 2),
+                                                     "note": "the same fed raw 16-bit depth (mm): half the upload"},
             "frames_to_joints_e2e": {"value": B / (chain_wall_ms * 1e-3), "unit": UNIT, "wall_ms": chain_wall_ms,
                                      "stages": "H2D frames, attention CNN, crop, hGRU pose net, post-processing, "
                                                "D2H joints",

@@ -173,6 +173,14 @@ HGRU_API int crop_area3d_forward(const float* frames_dev, int N, int H, int W, f
                                  const int* iparams_dev, const float* zparams_dev, float background,
                                  double out_divisor, float* out_dev, int dh, int dw, void* stream);
 
+/* Raw 16-bit depth frames (millimetres) -> float32 frames in [0, 1]: the pre-processing of the reference's real-data
+ * loop (eval_model_on_real_data, train_cnn_networks_hgru.py:381-386: `im[im < 1000] = 10000; im[im > 3000] = 10000`)
+ * + the division by image_max_depth (:359, :392), on the device: out[i] = (raw[i] < near || raw[i] > far ? fill :
+ * raw[i]) / max_depth, quotient in double, rounded once to float32.  count = number of pixels. */
+HGRU_API int depth_preprocess_forward(const unsigned short* raw_dev, size_t count, unsigned int near_mm,
+                                      unsigned int far_mm, double fill, double max_depth, float* out_dev,
+                                      void* stream);
+
 /* The window arithmetic itself on the device: comToBounds (tf_monkeydetector.py:193-206) + the resize / paste integers
  * and the 3x3 joint transform of cropArea3D (:309-362) for a batch, in explicitly rounded IEEE double operations in the
  * reference's evaluation order (the integers equal the host's).  Centres of mass: com_in_dev [N][3] double (u, v, d mm)

@@ -69,6 +69,8 @@ SIGNATURES = {
                                       ctypes.c_ulonglong, ctypes.c_float, _P, _P, _P, _P, _P]),
     "crop_area3d_forward": (_I, [_P, _I, _I, _I, ctypes.c_float, _P, _P, ctypes.c_float, ctypes.c_double, _P,
                                  _I, _I, _P]),
+    "depth_preprocess_forward": (_I, [_P, ctypes.c_size_t, ctypes.c_uint, ctypes.c_uint, ctypes.c_double,
+                                      ctypes.c_double, _P, _P]),
     "crop_windows_forward": (_I, [_P, _P, ctypes.c_double, ctypes.c_double, ctypes.c_double, _I, _I, _I, _I, _I,
                                   ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                   _P, _P, _P, _P, _P, _P]),

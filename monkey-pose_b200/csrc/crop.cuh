@@ -43,6 +43,21 @@ crop_area3d_kernel(const float* __restrict__ frames, float frame_scale, const in
 }
 
 
+// Raw depth frames (16-bit millimetres, as a depth camera delivers them and as the reference's real-data loop loads
+// them) -> the float32 frames in [0, 1] the networks and the crop stage take: values outside [near, far] are replaced by
+// `fill` and the result is divided by max_depth (eval_model_on_real_data, train_cnn_networks_hgru.py:381-386 + the
+// `/ config.image_max_depth` of :359 / :392).  Half the PCIe bytes of uploading float32 frames.  The quotient is formed
+// in double and rounded once to float32, as numpy's `im / 10000.` followed by the float32 feed does.
+__global__ void __launch_bounds__(256)
+depth_preprocess_kernel(const unsigned short* __restrict__ raw, size_t n, unsigned int near_mm, unsigned int far_mm,
+                        double fill, double max_depth, float* __restrict__ out) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const unsigned int v = raw[i];
+  const double d = (v < near_mm || v > far_mm) ? fill : static_cast<double>(v);
+  out[i] = static_cast<float>(__ddiv_rn(d, max_depth));
+}
+
 // Window arithmetic of the crop on the device (tfMonkeyDetector.comToBounds + the resize / paste integers and the
 // 3x3 transform of cropArea3D, tf_monkeydetector.py:193-206, 309-362), so that attention output -> crop needs no
 // host round trip.  One thread per frame; every operation is an explicitly rounded IEEE double operation in the

@@ -1209,6 +1209,16 @@ int crop_area3d_forward(const float* frames, int N, int H, int W, float frame_sc
   return 0;
 }
 
+int depth_preprocess_forward(const unsigned short* raw, size_t count, unsigned int near_mm, unsigned int far_mm,
+                             double fill, double max_depth, float* out, void* stream) {
+  if (!raw || !out) return fail(HGRU_E_INVALID, "depth_preprocess_forward: null pointer");
+  if (count < 1 || !(max_depth > 0.0)) return fail(HGRU_E_INVALID, "depth_preprocess_forward: bad size or divisor");
+  hgru::depth_preprocess_kernel<<<nblk(count), 256, 0, static_cast<cudaStream_t>(stream)>>>(raw, count, near_mm, far_mm,
+                                                                                         fill, max_depth, out);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 int crop_windows_forward(const float* tr, const double* com_in, double s0, double s1, double s2, int N, int H, int W,
                          int dw, int dh, double fx, double fy, double cube_x, double cube_y, double cube_z,
                          double* coms, int* iparams, float* zparams, double* Ms, int* invalid, void* stream) {

@@ -3,7 +3,7 @@ train_cnn_networks_hgru.py:264-419 -- attention CNN, `prepare_data_test`, pose n
 `getAbsoluteCoordinates`, one frame at a time through two `sess.run` calls and a host crop) for a whole batch with no
 host round trip between the stages, and with the upload of the frames overlapped with the attention CNN:
 
-    frames (pinned host, [N,H,W] float32 in [0,1])
+    frames (pinned host, [N,H,W] float32 in [0,1] -- or raw 16-bit millimetres, converted on the device)
       --H2D in `chunks` pieces on a copy stream-->  attention CNN per piece as it lands  -->  centres of mass (device)
       --> window arithmetic + crop (device) --> pose network (fused tensor-core forward) --> absolute joints (device)
       --D2H--> xyz, uvd [N,23,3]
@@ -12,7 +12,7 @@ Everything numerical runs in libhgru_b200.so; this module only orders the calls 
 """
 import torch
 
-from .tf_monkeydetector import prepare_data_test
+from .tf_monkeydetector import prepare_data_test, preprocess_real_depth
 
 
 class FramesToJoints(object):
@@ -21,11 +21,13 @@ class FramesToJoints(object):
     ['cube'][2] (mm).  `chunks`: pieces the upload is cut into (the attention CNN starts on piece c while piece c+1 is
     on the bus); 1 = plain stream order."""
 
-    def __init__(self, attn, pose, md, config, cube_z=1200.0, num_joints=23, chunks=4):
+    def __init__(self, attn, pose, md, config, cube_z=1200.0, num_joints=23, chunks=4, near=1000, far=3000):
         self.attn, self.pose, self.md, self.config = attn, pose, md, config
         self.scale = float(cube_z) / 2.0
         self.out_dims = 3 * int(num_joints)
         self.chunks = int(chunks)
+        self.near, self.far = int(near), int(far)      # raw 16-bit input: train_cnn_networks_hgru.py:383-384
+        self._raw_dev = None
         self._copy_stream = None
         self._frames_dev = None
         self._events = None
@@ -39,15 +41,20 @@ class FramesToJoints(object):
         return self._frames_dev
 
     def __call__(self, frames, centres=None):
-        """frames: [N,H,W] float32, pinned host memory (or a CUDA tensor: then nothing is uploaded).
+        """frames: [N,H,W] float32 in [0,1], pinned host memory (or a CUDA tensor: then nothing is uploaded) -- or raw
+        16-bit depth in millimetres (uint16 / int16, pinned host): half the upload, thresholded and normalised on the
+        device as eval_model_on_real_data does on the host (:381-386).
         centres: optional CUDA float32 [N,3] replacing the attention CNN's output (it still runs).
         Returns (xyz, uvd): [N,J,3] float32 on the host (pinned), camera-space mm and image-space (u, v, d)."""
         if frames.dim() == 4:
             frames = frames[..., 0]
         N = int(frames.shape[0])
         main = torch.cuda.current_stream()
+        raw16 = (not frames.is_floating_point()) and frames.element_size() == 2
         if frames.is_cuda:
-            dev_frames, pieces = frames.to(torch.float32).contiguous(), [(0, N)]
+            dev_frames = preprocess_real_depth(frames, self.near, self.far, max_depth=self.config.image_max_depth) \
+                if raw16 else frames.to(torch.float32).contiguous()
+            pieces = [(0, N)]
             self._buffers(frames.shape, frames.device)
         else:
             dev_frames = self._buffers(frames.shape, torch.device("cuda", torch.cuda.current_device()))
@@ -55,14 +62,21 @@ class FramesToJoints(object):
             nch = self.chunks if (self.chunks > 1 and N >= 4 * self.chunks and N % self.chunks == 0) else 1
             per = (N + nch - 1) // nch
             pieces = [(lo, min(lo + per, N)) for lo in range(0, N, per)]
+            if raw16 and (self._raw_dev is None or tuple(self._raw_dev.shape) != tuple(frames.shape)
+                          or self._raw_dev.dtype != frames.dtype):
+                self._raw_dev = torch.empty(frames.shape, device=dev_frames.device, dtype=frames.dtype)
+            target = self._raw_dev if raw16 else dev_frames
             self._copy_stream.wait_stream(main)                 # the previous call's readers are done with the buffer
             with torch.cuda.stream(self._copy_stream):
                 for i, (lo, hi) in enumerate(pieces):
-                    dev_frames[lo:hi].copy_(frames[lo:hi], non_blocking=True)
+                    target[lo:hi].copy_(frames[lo:hi], non_blocking=True)
                     self._events[i].record(self._copy_stream)
         for i, (lo, hi) in enumerate(pieces):
             if not frames.is_cuda:
                 main.wait_event(self._events[i])
+                if raw16:
+                    preprocess_real_depth(self._raw_dev[lo:hi], self.near, self.far,
+                                          max_depth=self.config.image_max_depth, out=dev_frames[lo:hi])
             self._tr[lo:hi] = self.attn.build(dev_frames[lo:hi], 3)                  # train_cnn_networks_hgru.py:281-283
         tr = self._tr if centres is None else centres
         patches, coms, _ = prepare_data_test(dev_frames, tr, self.md, self.config)   # :284 (window arithmetic on device)

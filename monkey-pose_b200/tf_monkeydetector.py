@@ -236,6 +236,22 @@ class tfMonkeyDetector(object):
         return out[0], Ms[0], coms[0]
 
 
+def preprocess_real_depth(raw, near=1000, far=3000, fill=10000.0, max_depth=10000.0, out=None):
+    """The pre-processing of the reference's real-data loop on the device (eval_model_on_real_data,
+    train_cnn_networks_hgru.py:381-386 and the `/ image_max_depth` of :359 / :392): raw 16-bit depth frames in
+    millimetres ([N,H,W] torch CUDA tensor of dtype uint16 or int16, the bits read as unsigned) -> float32 frames in
+    [0, 1] with everything outside [near, far] replaced by `fill`."""
+    if not (torch.is_tensor(raw) and raw.is_cuda and raw.element_size() == 2 and not raw.is_floating_point()):
+        raise RuntimeError("raw must be a 16-bit integer torch CUDA tensor (no CPU fallback)")
+    raw = raw.contiguous()
+    if out is None:
+        out = torch.empty(raw.shape, device=raw.device, dtype=torch.float32)
+    _lib.check(_lib.load().depth_preprocess_forward(raw.data_ptr(), raw.numel(), int(near), int(far), float(fill),
+                                                    float(max_depth), out.data_ptr(), _stream()),
+               "depth_preprocess_forward")
+    return out
+
+
 def prepare_data_test(image_np, tr_res, md, config):
     """train_cnn_networks_hgru.py:61-74 on the device: frames in [0,1] ([N,H,W] or [N,H,W,1], torch CUDA)
     and attention outputs tr_res [N,3] -> (patches [N,128,128,1] CUDA, coms, Ms)."""

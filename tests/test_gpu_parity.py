@@ -394,6 +394,18 @@ def test_frames_to_joints_pipeline_equals_the_stage_by_stage_sequence():
     # driven by the attention output itself (random-init: most windows miss the frame -> background patches, still finite)
     xyz3, _ = pipe(torch.as_tensor(frames_np).pin_memory())
     assert torch.isfinite(xyz3).all()
+    # raw 16-bit millimetre frames (the real-data loop, train_cnn_networks_hgru.py:381-386): thresholds and the division
+    # run on the device; same result as the host pre-processing followed by the float32 path, bit for bit
+    raw = np.round(frames_np * 10000.0).astype(np.uint16)
+    im = raw.astype(np.float64)
+    im[im < 1000] = 10000
+    im[im > 3000] = 10000
+    host_frames = (im / 10000.0).astype(np.float32)
+    dev = tmd.preprocess_real_depth(torch.from_numpy(raw.view(np.int16)).cuda())
+    assert np.array_equal(dev.cpu().numpy(), host_frames)
+    xa, ua = pipe(torch.from_numpy(raw.view(np.int16)).pin_memory(), centres=c_dev)
+    xb, ub = pipe(torch.as_tensor(host_frames).pin_memory(), centres=c_dev)
+    assert torch.equal(xa, xb) and torch.equal(ua, ub)
 
 
 # ---- post-processing -------------------------------------------------------------
