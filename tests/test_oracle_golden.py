@@ -101,3 +101,35 @@ def test_metric_restatement():
     b = np.zeros((2, 69))
     b[:, 0:3] = [3.0 / 600, 4.0 / 600, 0.0]        # one joint off by 5 mm in each frame
     assert abs(onp.mean_joint_error_mm(a, b) - 5.0 / 23) < 1e-12
+
+
+def test_training_mode_helpers_of_the_oracle():
+    """Dropout keep mask (the counter-based definition documented in include/hgru_b200.h) and the moving-statistics
+    update: deterministic, seed-dependent, the right keep fraction; batch-norm training = inference with the batch's
+    own statistics."""
+    m1 = onp.dropout_keep_mask(200000, 0.7, 1234)
+    m2 = onp.dropout_keep_mask(200000, 0.7, 1234)
+    m3 = onp.dropout_keep_mask(200000, 0.7, 1235)
+    assert np.array_equal(m1, m2) and not np.array_equal(m1, m3)
+    assert abs(m1.mean() - 0.7) < 0.005 and abs(m3.mean() - 0.7) < 0.005
+    assert onp.dropout_keep_mask(1000, 1.0, 5).all()
+    # element i of a longer mask equals element i of a shorter one (counter-based)
+    assert np.array_equal(onp.dropout_keep_mask(1000, 0.3, 9), onp.dropout_keep_mask(5000, 0.3, 9)[:1000])
+    rng = np.random.default_rng(0)
+    x = rng.normal(1.5, 2.0, size=(7, 5, 3, 4))
+    g, b = rng.uniform(0.5, 1.5, 4), rng.uniform(-1, 1, 4)
+    mean, var = x.mean(axis=(0, 1, 2)), x.var(axis=(0, 1, 2))
+    np.testing.assert_allclose(onp.batch_norm_training(x, g, b), onp.batch_norm_inference(x, g, b, mean, var), atol=1e-12)
+    mm, mv = onp.batch_norm_moving_update(x, np.zeros(4), np.ones(4), momentum=0.997)
+    n = 7 * 5 * 3
+    np.testing.assert_allclose(mm, 0.003 * mean, atol=1e-15)
+    np.testing.assert_allclose(mv, 0.997 + 0.003 * var * n / (n - 1), atol=1e-15)
+    # the model-level oracle with train_mode uses them
+    P = {k: v for k, v in __import__("monkey_pose_b200").initialization.pose_params(
+        channels=4, S=3, T=1, hw=4, fc_hidden=8, out=6, seed=1, random_bn=True).items()}
+    d = rng.uniform(0, 1, size=(3, 8, 8, 1)).astype(np.float32)
+    h0 = np.zeros((3, 4, 4, 4), np.float32)
+    a = onp.pose_forward(d, P, h0, timesteps=1, train_mode=True)
+    bb = onp.pose_forward(d, P, h0, timesteps=1, train_mode=True, dropout_keep=0.7, dropout_seed=3)
+    c = onp.pose_forward(d, P, h0, timesteps=1, train_mode=False)
+    assert a.shape == (3, 6) and not np.allclose(a, bb) and not np.allclose(a, c)
