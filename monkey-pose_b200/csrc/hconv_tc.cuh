@@ -62,8 +62,17 @@ struct TcConvCfg {
   static constexpr int kTapBytes = 2 * CO_PAD * 16;         // one (kstep, tap) weight block
   static constexpr int kTapBytesWide = SPLIT3 ? 2 * kTapBytes : kTapBytes;   // [w_hi | w_lo] stacked along N
   static constexpr int kGroupBytes = kTaps * (kTapBytesWide + kTapBytes);     // SPLIT3: both passes of a 16-channel group
-  static constexpr int kStageBytes = G * kTapBytesWide;
-  static constexpr int kStagesPerKstep = kTaps / G;
+  // PAIRTAP (the fused 64-channel 15x15 kernel): taps dx and dx + 8 of a filter row share their A operand -- window
+  // offset 8 t + dx serves tile t with tap dx AND tile t - 1 with tap dx + 8 -- and the accumulators of neighbouring
+  // tiles are neighbouring TMEM columns, so ONE N = 128 instruction with B = [W[dx+8] ; W[dx]] feeds both: 39
+  // instructions per filter row and k-step instead of 60, 21 of them at the full issue rate (an M = 128 MMA fetches
+  // the same 4 KB of A whatever its N; at N = 64 that fetch, not the math, sets the pace).  Weights are packed in
+  // 4 KB blocks [2 chunks][128 rows][8 ci]: block 0 = tap 7 (rows 64.. zero), block 1 + dx = rows 0-63 tap dx + 8,
+  // rows 64-127 tap dx; a ring stage = two blocks.
+  static constexpr bool kPairTap = FUSE;
+  static constexpr int kPairBlockBytes = 2 * 128 * 16;
+  static constexpr int kStageBytes = kPairTap ? 2 * kPairBlockBytes : G * kTapBytesWide;
+  static constexpr int kStagesPerKstep = kPairTap ? S * 4 : kTaps / G;
   static constexpr int kAccN = SPLIT3 ? 2 * CO_PAD : CO_PAD; // accumulator columns per tile
   static constexpr int kAccCols = TILES_X * kAccN;          // TMEM columns per accumulator set
   static constexpr int kGateABytes = FUSE ? (CO_PAD / 8) * 128 * 16 : 0;   // staging tile of the new state (bf16, K-major)
@@ -74,7 +83,8 @@ struct TcConvCfg {
   static constexpr int kAlign = FUSE ? 128 : 1024;
   static constexpr int kSmemBytes = kInBytes + WSTAGES * kStageBytes + kGateBytes + kNumBars * 8 + 16 + kAlign;
   static_assert(kSmemBytes <= 232448, "shared memory per CTA");
-  static_assert(kTaps % G == 0, "taps per stage must divide S*S");
+  static_assert(kPairTap || kTaps % G == 0, "taps per stage must divide S*S");
+  static_assert(!kPairTap || (S == 15 && CO_PAD == 64 && TILES_X == 4 && !SPLIT3), "paired-tap schedule: 64 channels, 15x15");
   static_assert(2 * kAccCols <= 512, "two accumulator sets must fit TMEM");
   static_assert(CO_PAD % 16 == 0 && CO_PAD >= 16 && kAccN <= 256, "UMMA N constraint (M=128)");
   static_assert(kChunkPitch % 16 == 0 && (kChunkPitch >> 4) < 16384, "LBO range");
@@ -768,11 +778,12 @@ hconv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const TcConvArgs a) 
         for (int q = 0; q < NW; ++q) {
           // SPLIT3 layout per 16-channel group: [taps] wide blocks ([w_hi | w_lo]) then [taps] w_hi blocks
           const bool wide = SPLIT3 && !(q & 1);
-          const uint32_t sbytes = G * (wide ? Cfg::kTapBytesWide : Cfg::kTapBytes);
+          const uint32_t sbytes = Cfg::kPairTap ? Cfg::kStageBytes : G * (wide ? Cfg::kTapBytesWide : Cfg::kTapBytes);
           const uint8_t* src = reinterpret_cast<const uint8_t*>(a.wpk) +
-                               (SPLIT3 ? static_cast<size_t>(q >> 1) * Cfg::kGroupBytes +
-                                             ((q & 1) ? static_cast<size_t>(Cfg::kTaps) * Cfg::kTapBytesWide : 0)
-                                       : static_cast<size_t>(q) * Cfg::kTaps * Cfg::kTapBytes);
+                               (Cfg::kPairTap ? static_cast<size_t>(q) * Cfg::kStagesPerKstep * Cfg::kStageBytes
+                                : SPLIT3 ? static_cast<size_t>(q >> 1) * Cfg::kGroupBytes +
+                                               ((q & 1) ? static_cast<size_t>(Cfg::kTaps) * Cfg::kTapBytesWide : 0)
+                                         : static_cast<size_t>(q) * Cfg::kTaps * Cfg::kTapBytes);
           for (int sg = 0; sg < Cfg::kStagesPerKstep; ++sg) {
             mbar_wait(bar_w_empty + 8 * st, ph ^ 1);
             mbar_arrive_expect_tx(bar_w_full + 8 * st, sbytes);
@@ -842,6 +853,42 @@ hconv_tc_kernel(const __grid_constant__ CUtensorMap in_map, const TcConvArgs a) 
         const uint64_t adesc_q = adesc0 + static_cast<uint64_t>((q * Cfg::kPartBytes) >> 4);
         uint32_t tap_off = 0;            // (dy * kRowPitch + dx * 16) >> 4, advanced incrementally
         uint32_t dx = 0;
+        if constexpr (Cfg::kPairTap) {
+          // ---- paired-tap schedule (see TcConvCfg::kPairTap): stage = blocks (2 sg', 2 sg' + 1) of filter row dy ----
+          constexpr uint32_t idesc_p = make_idesc(1, 128, 128);
+          const uint64_t bdesc0_p = make_smem_desc(w_buf, 2048, 128);      // block: chunk pitch 2 KB, 128 rows
+          for (int sg = 0; sg < Cfg::kStagesPerKstep; ++sg) {
+            const int dy = sg >> 2, sb = sg & 3;
+            mbar_wait_warp(bar_w_full + 8 * st, ph);
+            tc_fence_after();
+            const uint64_t a_row = adesc_q + static_cast<uint64_t>((dy * Cfg::kRowPitch) >> 4);
+            const uint64_t b_st = bdesc0_p + static_cast<uint64_t>((st * Cfg::kStageBytes) >> 4);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int blk = 2 * sb + h;
+              const uint64_t b_blk = b_st + static_cast<uint64_t>((h * Cfg::kPairBlockBytes) >> 4);
+              if (blk == 0) {
+                // tap 7 alone, every tile: the first instructions of a unit (they overwrite the accumulators)
+                const uint32_t accum = (wq | dy) != 0;
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                  if (leader) mma_bf16_ss(acc + t * 64, a_row + static_cast<uint64_t>(8 * t + 7), b_blk, idesc_n, accum);
+              } else {
+                const int pdx = blk - 1;      // rows 0-63 of the block: tap pdx + 8, rows 64-127: tap pdx
+                if (leader) {
+                  // tile 0 has no left neighbour for its low taps, tile 3 no right neighbour for its high taps
+                  mma_bf16_ss(acc, a_row + static_cast<uint64_t>(pdx), b_blk + (1024 >> 4), idesc_n, 1u);
+#pragma unroll
+                  for (int t = 1; t < 4; ++t)
+                    mma_bf16_ss(acc + (t - 1) * 64, a_row + static_cast<uint64_t>(8 * t + pdx), b_blk, idesc_p, 1u);
+                  mma_bf16_ss(acc + 3 * 64, a_row + static_cast<uint64_t>(24 + pdx + 8), b_blk, idesc_n, 1u);
+                }
+              }
+            }
+            if (leader) tc_commit(bar_w_empty + 8 * st);
+            if (++st == WSTAGES) { st = 0; ph ^= 1; }
+          }
+        } else
         for (int sg = 0; sg < Cfg::kStagesPerKstep; ++sg) {
           mbar_wait_warp(bar_w_full + 8 * st, ph);
           tc_fence_after();

@@ -292,6 +292,7 @@ static int hgru_plan_init(hgru_plan_s* p, int N, int H, int W, int k, int S, int
       const char* nf = getenv("HGRU_NO_FUSE64");      // development switch: the unfused four-launch pipeline
       p->fused_tc = !p->stacked && S == 15 && p->KP == 64 && !(nf && nf[0] == '1');
     }
+    if (p->fused_tc) wbytes = sizeof(__nv_bfloat16) * ksteps * 15 * 8 * 2 * 128 * 8;      // paired-tap blocks
     if (p->stacked || p->fused_tc) {
       // consecutive conv launches are chained through per-frame counters (HGRU_NO_CHAIN=1: plain stream order)
       const char* nc = getenv("HGRU_NO_CHAIN");
@@ -376,6 +377,9 @@ static int hgru_set_params_impl(hgru_plan_s* p, const float* p_r, const float* i
     if (p->stacked && stack_geometry(p->S, KP, k, &sg)) {
       int rc = stack_pack_weights(p_r, p->wpk.as<__nv_bfloat16>(), k, sg, 0, st);
       if (rc) return rc;
+    } else if (p->fused_tc) {
+      const size_t tp = static_cast<size_t>(ksteps) * 15 * 8 * 2 * 128 * 8;
+      hgru::pack_weights_pairtap_kernel<<<nblk(tp), 256, 0, st>>>(p_r, p->wpk.as<__nv_bfloat16>(), k, ksteps);
     } else {
       hgru::pack_weights_kernel<<<nblk(total), 256, 0, st>>>(p_r, p->wpk.as<__nv_bfloat16>(), taps, k, ksteps, KP);
     }

@@ -837,6 +837,32 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
   wpk[i] = __float2bfloat16(v);
 }
 
+// Weight packing for the paired-tap schedule of the fused 64-channel 15x15 kernel (TcConvCfg::kPairTap):
+// HWIO fp32 [15][15][k][k] -> bf16 [kstep q][dy][block b = 0..7][2 chunks][128 rows][8 ci]
+//   block 0: rows 0-63 = tap dx = 7 (output channels), rows 64-127 = zero
+//   block 1 + p (p = 0..6): rows 0-63 = tap dx = p + 8, rows 64-127 = tap dx = p
+__global__ void pack_weights_pairtap_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wpk, int k,
+                                            int ksteps) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  const size_t total = static_cast<size_t>(ksteps) * 15 * 8 * 2 * 128 * 8;
+  if (i >= total) return;
+  const int j = i & 7;
+  size_t r = i >> 3;
+  const int row = r % 128; r /= 128;
+  const int ch = r & 1; r >>= 1;
+  const int b = r % 8; r /= 8;
+  const int dy = r % 15;
+  const int q = static_cast<int>(r / 15);
+  int dx = -1;
+  if (b == 0) { if (row < 64) dx = 7; }
+  else dx = (row < 64) ? (b - 1 + 8) : (b - 1);
+  const int co = row & 63;
+  const int ci = q * 16 + ch * 8 + j;
+  float v = 0.f;
+  if (dx >= 0 && ci < k && co < k) v = w[((static_cast<size_t>(dy) * 15 + dx) * k + ci) * k + co];
+  wpk[i] = __float2bfloat16(v);
+}
+
 // Weight packing for the SPLIT3 tensor-core conv (hi = bf16(w), lo = bf16(w - hi)): per 16-channel group q
 //   [taps][2 chunks][2*co_pad n][8 ci]   n < co_pad: w_hi[.., co = n],  n >= co_pad: w_lo[.., co = n - co_pad]   (a_hi pass)
 //   [taps][2 chunks][co_pad n][8 ci]     w_hi                                                                  (a_lo pass)
