@@ -786,8 +786,9 @@ struct pose_plan_s {
   int fc_splits = 1, fc_kbps = 1, fc_kpad = 0;
   cudaStream_t copy_st = nullptr;                  // pose_forward_host: upload of the crops overlaps the initial-state pass
   cudaEvent_t ev_begin = nullptr;
-  static constexpr int kUploadChunks = 4;          // the crops are uploaded in frame chunks; conv_1 follows chunk by chunk
-  cudaEvent_t ev_chunk[kUploadChunks] = {nullptr, nullptr, nullptr, nullptr};
+  static constexpr int kUploadChunks = 4;          // the crops are uploaded in frame chunks; the stem follows chunk by chunk
+  static constexpr int kUploadChunkFrames = 32;    // ... of at least this many frames (smaller launches are latency-bound)
+  cudaEvent_t ev_chunk[kUploadChunks] = {};
   cudaStream_t side_st = nullptr;                  // the initial-state pass runs beside the stem (independent inputs)
   cudaEvent_t ev_fork = nullptr, ev_init = nullptr;
   float* bn_scale(int i) const { return bn.as<float>() + static_cast<size_t>(i) * 2 * bnw; }
@@ -839,14 +840,13 @@ static int pose_forward_impl(pose_plan_s* p, const float* depth, const float* H2
     CUDA_TRY(cudaEventRecord(p->ev_init, p->side_st));
     h->state_ready = true;
   }
-  // conv_1 + relu + pool_1 + BN (hgru_pose.py:50-60); frames are independent, so with a chunked upload
-  // (pose_forward_host) each chunk is processed as soon as it has landed
-  for (int c = 0; c < nchunks; ++c) {
-    const int per = (N + nchunks - 1) / nchunks;
-    const int n0 = c * per, nn = (n0 + per <= N ? per : N - n0);
-    if (nn <= 0) break;
-    if (chunk_ready) CUDA_TRY(cudaStreamWaitEvent(st, chunk_ready[c], 0));
-    const size_t pix = static_cast<size_t>(HW) * HW;
+  // conv_1 + relu + pool_1 + BN (hgru_pose.py:50-60), conv_2 + relu + BN (:61-70), conv_3 + relu + BN (:71-80; its
+  // output is X of the hGRU).  Frames are independent, so with a chunked upload (pose_forward_host) the stem of a
+  // chunk runs as soon as the chunk has landed, under the upload of the next one; per-frame results do not depend
+  // on the chunking.
+  const int per = (N + nchunks - 1) / nchunks;
+  const size_t pix = static_cast<size_t>(HW) * HW;
+  auto conv1 = [&](int n0, int nn) {
     float* o32 = tc ? nullptr : p->pool1.as<float>() + static_cast<size_t>(n0) * pix * KP;
     __nv_bfloat16* o16 = tc ? p->act_pool1.as<__nv_bfloat16>() + static_cast<size_t>(n0) * 2 * KP * pix : nullptr;
     hgru::stem_conv1_pool_bn_kernel<<<dim3(nblk(static_cast<size_t>(nn) * HW * ((HW + hgru::kStemPix - 1) / hgru::kStemPix)), KP / 8),
@@ -854,28 +854,37 @@ static int pose_forward_impl(pose_plan_s* p, const float* depth, const float* H2
         depth + static_cast<size_t>(n0) * 4 * pix, p->w1.as<float>(), p->b1.as<float>(), p->bn_scale(0), p->bn_shift(0),
         o32, o16, nn, HW, HW, C, KP, tc ? 1 : 0);
     ++p->launches;
-  }
-  // conv_2 + relu + BN (:61-70), conv_3 + relu + BN (:71-80); conv3 output is X of the hGRU
-  if (tc) {
+  };
+  auto conv23_tc = [&](int n0, int nn) -> int {
     hgru::TcConvArgs a{};
-    a.N = N; a.H = HW; a.W = HW; a.KP = KP; a.kreal = C;
+    a.N = nn; a.n0 = n0; a.H = HW; a.W = HW; a.KP = KP; a.kreal = C;
     a.wpk = p->wpk2.as<__nv_bfloat16>(); a.bias = p->b2.as<float>();
     a.scale = p->bn_scale(1); a.shift = p->bn_shift(1);
     a.out = nullptr; a.out_bf16 = p->act_conv2.as<__nv_bfloat16>();      // (no fp32 copy: see pose_plan_create)
-    if ((rc = tc_stem_launch(KP, p->map_pool1, a, st))) return rc;
+    int r = tc_stem_launch(KP, p->map_pool1, a, st);
+    if (r) return r;
     a.wpk = p->wpk3.as<__nv_bfloat16>(); a.bias = p->b3.as<float>();
     a.scale = p->bn_scale(2); a.shift = p->bn_shift(2);
     a.out = h->Xp.as<float>(); a.out_bf16 = nullptr;
-    if ((rc = tc_stem_launch(KP, p->map_conv2, a, st))) return rc;
-  } else {
+    p->launches += 2;
+    return tc_stem_launch(KP, p->map_conv2, a, st);
+  };
+  for (int c = 0; c < nchunks; ++c) {
+    const int n0 = c * per, nn = (n0 + per <= N ? per : N - n0);
+    if (nn <= 0) break;
+    if (chunk_ready) CUDA_TRY(cudaStreamWaitEvent(st, chunk_ready[c], 0));
+    conv1(n0, nn);
+    if (tc && (rc = conv23_tc(n0, nn))) return rc;
+  }
+  if (!tc) {
     if ((rc = dispatch_simt_conv(3, p->pool1.as<float>(), p->w2.as<float>(), p->b2.as<float>(), p->bn_scale(1),
                                  p->bn_shift(1), p->conv2.as<float>(), N, HW, HW, KP, KP, 1, st)))
       return rc;
     if ((rc = dispatch_simt_conv(3, p->conv2.as<float>(), p->w3.as<float>(), p->b3.as<float>(), p->bn_scale(2),
                                  p->bn_shift(2), h->Xp.as<float>(), N, HW, HW, KP, KP, 1, st)))
       return rc;
+    p->launches += 2;
   }
-  p->launches += 2;
   // hGRU (:81, R-D4)
   if (p->fc1_tc) {   // the last H2 epilogue writes the fc_1 operand directly
     h->fc_a = p->fc1_a.as<__nv_bfloat16>(); h->fc_scale = p->bn_scale(3); h->fc_shift = p->bn_shift(3);
@@ -1128,7 +1137,9 @@ int pose_forward_host(pose_plan_t p, const float* depth_host, const float* H2_in
   CUDA_TRY(cudaEventRecord(p->ev_begin, st));
   CUDA_TRY(cudaStreamWaitEvent(p->copy_st, p->ev_begin, 0));
   // frame chunks, one event each: conv_1 of chunk c runs while chunk c+1 is still on the bus
-  const int nchunks = p->N >= 4 * pose_plan_s::kUploadChunks ? pose_plan_s::kUploadChunks : 1;
+  int nchunks = p->N / pose_plan_s::kUploadChunkFrames;
+  if (const char* e = getenv("HGRU_UPLOAD_CHUNKS")) nchunks = atoi(e);      // development switch (A/B of the overlap)
+  nchunks = nchunks < 1 ? 1 : (nchunks > pose_plan_s::kUploadChunks ? pose_plan_s::kUploadChunks : nchunks);
   {
     const int per = (p->N + nchunks - 1) / nchunks;
     const size_t frame = static_cast<size_t>(4) * p->HW * p->HW;      // floats per 2HW x 2HW crop

@@ -231,10 +231,10 @@ def test_chained_layer_equals_traced_layer_on_ragged_shapes(shape):
     assert onp.rel_err(O_chained[:2].cpu().numpy(), ref.numpy())[0] < TOL["bf16"]
 
 
-@pytest.mark.parametrize("N,mode", [(2, "bf16"), (19, "bf16"), (17, "fp32")])
+@pytest.mark.parametrize("N,mode", [(2, "bf16"), (19, "bf16"), (75, "bf16"), (107, "bf16x3"), (75, "fp32")])
 def test_pose_host_entry_point_equals_device_entry_point(N, mode):
-    """Host buffers in / out (N >= 16: the crops go up in four frame chunks, ragged here, conv_1 chunk by chunk)
-    against the device-tensor entry point."""
+    """Host buffers in / out (N >= 64: the crops go up in chunks of >= 32 frames, ragged here, and the stem follows
+    chunk by chunk) against the device-tensor entry point."""
     m1, out_dev, *_ = _pose(mode, N, 16, 16, 2, 15, 64, host=False)
     m2, out_host, *_ = _pose(mode, N, 16, 16, 2, 15, 64, host=True)
     assert not out_host.is_cuda

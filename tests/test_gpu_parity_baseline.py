@@ -124,7 +124,7 @@ def _model(P, h0, channels, T, mode):
 def test_pose_forward_batch256_vs_fp64_oracle(stress, random_bn):
     """N = 256, 25 channels, T = 8, 15x15: bf16 forward of the full batch, checked on a frame subset against the fp64
     oracle (frames are independent); the fp32 and bf16x3 modes on the same frames against the fp32 budget; the host
-    entry point (crops uploaded in four chunks) against the device entry point."""
+    entry point (crops uploaded in four chunks, the stem following chunk by chunk) against the device entry point."""
     P, depth, h0, ref, acts = _pose_case(stress, random_bn)
     idx = list(SUBSET)
     m = _model(P, h0, 25, 8, "bf16")
