@@ -112,6 +112,10 @@ HGRU_API int pose_forward(pose_plan_t plan, const float* depth_dev, const float*
 HGRU_API int pose_forward_host(pose_plan_t plan, const float* depth_host, const float* H2_init_dev,
                       float* out_host, void* stream);
 
+/* aux['hidden_init'] = 'identity' (hgru_module.py:876-878: O_0 = X, the hGRU's own input): when on, H2_init_dev
+ * of the forward calls is ignored and the initial state is conv3 of the same forward.  Off by default. */
+HGRU_API int pose_set_hidden_init(pose_plan_t plan, int identity);
+
 /* Intermediate activations of the last pose_forward, by the reference's attribute names
  * ("pool1","conv2","conv3","hgru","fc1"; hgru_pose.py:50-105), copied into dst_dev in the
  * reference's layout ([N,HW,HW,C] / [N,F]).  For parity tests. */

@@ -55,6 +55,7 @@ SIGNATURES = {
     "pose_set_params": (_I, [_P, ctypes.POINTER(PoseParams), ctypes.c_float, _P]),
     "pose_forward": (_I, [_P, _P, _P, _P, _P]),
     "pose_forward_host": (_I, [_P, _P, _P, _P, _P]),
+    "pose_set_hidden_init": (_I, [_P, _I]),
     "pose_get_activation": (_I, [_P, ctypes.c_char_p, _P, _P]),
     "pose_plan_workspace_bytes": (ctypes.c_size_t, [_P]),
     "pose_plan_launch_count": (_I, [_P]),

@@ -780,6 +780,8 @@ struct pose_plan_s {
   DevBuf depth, pool1, conv2, w1, b1, w2, b2, w3, b3, fc1_w, fc1_b, fc2_w, fc2_b, bn, part, fc1, out;
   DevBuf act_pool1, act_conv2, wpk2, wpk3;         // tensor-core stem
   CUtensorMap map_pool1, map_conv2;
+  bool h0_identity = false;                        // hidden_init='identity': the initial state is conv3 (hgru_module.py:876-878)
+  DevBuf h0_tmp;                                   // ... in the reference's layout, filled after the stem
   DevBuf fc1_wt, fc1_a;                            // tensor-core fc_1: bf16 [F][K] weights, bf16 [N][K] input
   CUtensorMap map_fc_a, map_fc_b;
   bool fc1_tc = false;
@@ -798,7 +800,7 @@ struct pose_plan_s {
     return hg.workspace() + depth.bytes + pool1.bytes + conv2.bytes + w1.bytes + b1.bytes + w2.bytes +
            b2.bytes + w3.bytes + b3.bytes + fc1_w.bytes + fc1_b.bytes + fc2_w.bytes + fc2_b.bytes +
            bn.bytes + part.bytes + fc1.bytes + out.bytes + act_pool1.bytes + act_conv2.bytes +
-           wpk2.bytes + wpk3.bytes + fc1_wt.bytes + fc1_a.bytes;
+           wpk2.bytes + wpk3.bytes + fc1_wt.bytes + fc1_a.bytes + h0_tmp.bytes;
   }
 };
 
@@ -812,7 +814,7 @@ static void pose_plan_free(pose_plan_s* p) {
   if (p->ev_init) cudaEventDestroy(p->ev_init);
   DevBuf* all[] = {&p->depth, &p->pool1, &p->conv2, &p->w1, &p->b1, &p->w2, &p->b2, &p->w3, &p->b3,
                    &p->fc1_w, &p->fc1_b, &p->fc2_w, &p->fc2_b, &p->bn, &p->part, &p->fc1, &p->out,
-                   &p->act_pool1, &p->act_conv2, &p->wpk2, &p->wpk3, &p->fc1_wt, &p->fc1_a};
+                   &p->act_pool1, &p->act_conv2, &p->wpk2, &p->wpk3, &p->fc1_wt, &p->fc1_a, &p->h0_tmp};
   for (auto b : all) b->release();
 }
 
@@ -825,7 +827,10 @@ static int pose_forward_impl(pose_plan_s* p, const float* depth, const float* H2
   const bool tc = p->mode != HGRU_MODE_FP32;      // stem + fc_1 on tensor cores (hi/lo splits) in both bf16 modes
   int rc;
   p->launches = 0;
-  if (p->mode == HGRU_MODE_BF16) {
+  if (p->h0_identity && !p->h0_tmp.p) {
+    if (int r = p->h0_tmp.alloc(static_cast<size_t>(N) * HW * HW * C * sizeof(float))) return r;
+  }
+  if (p->mode == HGRU_MODE_BF16 && !p->h0_identity) {
     // the hGRU's initial-state pass does not depend on the crops: run it first (under their upload, when the
     // caller copies them on another stream)
     // ... and beside the stem: both are latency-bound passes of ~0.1 ms that leave most of the chip idle
@@ -890,7 +895,13 @@ static int pose_forward_impl(pose_plan_s* p, const float* depth, const float* H2
     h->fc_a = p->fc1_a.as<__nv_bfloat16>(); h->fc_scale = p->bn_scale(3); h->fc_shift = p->bn_shift(3);
     h->fc_kpad = p->fc_kpad;
   }
-  if (p->mode == HGRU_MODE_BF16) CUDA_TRY(cudaStreamWaitEvent(st, p->ev_init, 0));      // join the initial-state pass
+  if (p->h0_identity) {      // O_0 = X (hgru_module.py:876-878): conv3 in the reference's layout, then the usual path
+    state_to_nhwc(h, h->Xp.as<float>(), p->h0_tmp.as<float>(), st);
+    H2_init = p->h0_tmp.as<float>();
+    ++p->launches;
+  } else if (p->mode == HGRU_MODE_BF16) {
+    CUDA_TRY(cudaStreamWaitEvent(st, p->ev_init, 0));      // join the initial-state pass
+  }
   if ((rc = hgru_run_padded(h, h->Xp.as<float>(), H2_init, nullptr, nullptr, st))) return rc;
   p->launches += h->launches;
   // BN (:82-90) folded into the A-operand of fc_1 (:91); split-K partial sums
@@ -1155,6 +1166,12 @@ int pose_forward_host(pose_plan_t p, const float* depth_host, const float* H2_in
   if (rc) return rc;
   CUDA_TRY(cudaMemcpyAsync(out_host, p->out.p, p->out.bytes, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int pose_set_hidden_init(pose_plan_t p, int identity) {
+  if (!p) return fail(HGRU_E_INVALID, "pose_set_hidden_init: null plan");
+  p->h0_identity = identity != 0;
   return 0;
 }
 

@@ -256,9 +256,6 @@ class model(LayerOps):
         depth = depth.to(torch.float32).contiguous()
         for n in _LAZY_NAMES:
             self.__dict__.pop(n, None)
-        if self.aux.get('hidden_init', 'random') == 'identity' and self.hidden_state is None:
-            raise NotImplementedError("aux['hidden_init']='identity' is not on the path hgru_pose.py configures "
-                                      "(pass model.hidden_state explicitly)")
         if train_mode:
             self._need_cuda(depth, "build(train_mode=True)")
         N, hw = int(depth.shape[0]), int(depth.shape[1]) // 2
@@ -312,8 +309,11 @@ class model(LayerOps):
             if self._h0_cache is None or self._h0_cache[0] != hkey:
                 self._h0_cache = (hkey, _as_dev(init.hidden_init((N, hw, hw, self.channels), seed=self.seed + 7)))
             h0 = self._h0_cache[1]
-        elif self.aux.get('hidden_init') != 'zeros':
+        elif self.aux.get('hidden_init') not in ('zeros', 'identity'):
             raise RuntimeError("hidden_init must be 'random', 'zeros' or 'identity'")      # hgru_module.py:891-892
+        # 'identity': O_0 = X = conv3 of this forward (hgru_module.py:876-878), taken inside the library
+        identity = self.hidden_state is None and self.aux.get('hidden_init') == 'identity'
+        _lib.check(lib.pose_set_hidden_init(self._plan, 1 if identity else 0), "pose_set_hidden_init")
         self._h0 = h0
         h0_ptr = h0.data_ptr() if h0 is not None else None
         if depth.is_cuda:

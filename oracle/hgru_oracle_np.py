@@ -189,6 +189,8 @@ def pose_forward(depth, params, H2_init, timesteps=8, train_mode=False, eps=1e-5
     `batch_normalization[_i]/{gamma,beta,moving_mean,moving_variance}`).
     Dropout (hgru_pose.py:93-94) is random: excluded unless `dropout_keep` is given, in which case the documented
     counter-based mask (dropout_keep_mask) is applied to relu(fc1) before the batch norm, as the reference orders them.
+    H2_init: the initial state O_0 [N,64,64,k], or the reference's hidden_init names 'identity' (O_0 = X, the hGRU's
+    input conv3: hgru_module.py:876-878) / 'zeros' (:888-890).
     """
     P = params
     acts = {}
@@ -200,6 +202,10 @@ def pose_forward(depth, params, H2_init, timesteps=8, train_mode=False, eps=1e-5
     conv3 = _bn(conv_layer(conv2, P["conv_3/conv_3_filters"], P["conv_3/conv_3_biases"]),
                 P, BN_SCOPES[2], train_mode, eps)                                        # :71-80
     hp = {n: P["contextual_circuit/" + n] for n in HGRU_PARAM_NAMES}
+    if isinstance(H2_init, str):
+        if H2_init not in ("identity", "zeros"):
+            raise RuntimeError("hidden_init")                                            # hgru_module.py:891-892
+        H2_init = conv3.copy() if H2_init == "identity" else np.zeros_like(conv3)
     hgru = hgru_forward(conv3, H2_init, hp, timesteps)                                   # :81 (R-D4)
     hgru_bn = _bn(hgru, P, BN_SCOPES[3], train_mode, eps)                                # :82-90
     fc1 = fc_layer(hgru_bn, P["fc_1/fc_1_weights"], P["fc_1/fc_1_biases"])               # :91

@@ -84,7 +84,8 @@ def _bn(x, P, scope, dtype, eps, channel_dim):
 
 
 def pose_forward(depth, P, H2_init, timesteps=8, dtype=torch.float32, eps=1e-5, trace=False):
-    """hgru_pose.py:47-105, inference-mode BN, resolutions R-D4/R-D5/R-D6."""
+    """hgru_pose.py:47-105, inference-mode BN, resolutions R-D4/R-D5/R-D6.  H2_init: O_0 [N,HW,HW,k], or the reference's
+    hidden_init names 'identity' (O_0 = the hGRU's input, hgru_module.py:876-878) / 'zeros' (:888-890)."""
     with torch.no_grad():
         x = _t(depth, dtype).permute(0, 3, 1, 2).contiguous()
         c1 = torch.relu(_conv_same(x, _w(P["conv_1/conv_1_filters"], dtype))
@@ -97,7 +98,12 @@ def pose_forward(depth, P, H2_init, timesteps=8, dtype=torch.float32, eps=1e-5, 
                         + _t(P["conv_3/conv_3_biases"], dtype).reshape(1, -1, 1, 1))
         c3 = _bn(c3, P, BN_SCOPES[2], dtype, eps, 1)
         hp = _prep_hgru({n: P["contextual_circuit/" + n] for n in HGRU_PARAM_NAMES}, dtype)
-        h0 = _t(H2_init, dtype).permute(0, 3, 1, 2).contiguous()
+        if isinstance(H2_init, str):
+            if H2_init not in ("identity", "zeros"):
+                raise RuntimeError("hidden_init")                          # hgru_module.py:891-892
+            h0 = c3.clone() if H2_init == "identity" else torch.zeros_like(c3)
+        else:
+            h0 = _t(H2_init, dtype).permute(0, 3, 1, 2).contiguous()
         hg = hgru_forward_nchw(c3, h0, hp, timesteps)
         hb = _bn(hg, P, BN_SCOPES[3], dtype, eps, 1)
         flat = hb.permute(0, 2, 3, 1).reshape(hb.shape[0], -1)            # flatten order h,w,c

@@ -165,7 +165,7 @@ def test_attribute_surface_after_inference_build():
     assert isinstance(h, tuple) and len(h) == 3 and h[0].shape == (N, hw, hw, ch)
 
 
-def test_model_default_hidden_state_is_cached_and_identity_is_rejected():
+def test_model_default_hidden_state_is_cached_and_named_initial_states():
     m = mp.model()
     m.channels, m.timesteps, m.fc_hidden = 16, 1, 16
     d = torch.as_tensor(init.synthetic_depth(2, seed=1, size=32)).cuda()
@@ -175,11 +175,44 @@ def test_model_default_hidden_state_is_cached_and_identity_is_rejected():
     assert m._h0 is h0_first and torch.equal(a, b)          # the seeded O_0 is drawn once per shape
     m2 = mp.model()
     m2.channels, m2.timesteps, m2.fc_hidden = 16, 1, 16
-    m2.aux = dict(m2.aux, hidden_init="identity")
-    with pytest.raises(NotImplementedError):
-        m2.build(d, 5)
-    m2.aux["hidden_init"] = "zeros"
+    m2.aux = dict(m2.aux, hidden_init="zeros")
     assert torch.isfinite(m2.build(d, 5)).all() and m2._h0 is None
+    m2.aux["hidden_init"] = "bogus"
+    with pytest.raises(RuntimeError):
+        m2.build(d, 5)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16", "bf16x3"])
+@pytest.mark.parametrize("hidden_init", ["identity", "zeros"])
+def test_model_named_initial_state_vs_oracle(mode, hidden_init):
+    """aux['hidden_init'] = 'identity' (O_0 = X = conv3 of the same forward, hgru_module.py:876-878) and 'zeros'
+    (:888-890) through the fused forward, device and host entry points, against the fp64 oracle."""
+    N, ch, hw, T, S, F = 3, 25, 16, 3, 15, 32
+    P = init.pose_params(channels=ch, S=S, T=T, hw=hw, fc_hidden=F, out=69, seed=3, stress=4.0, random_bn=True)
+    depth = init.synthetic_depth(N, seed=2, size=2 * hw)
+    m = mp.model()
+    m.channels, m.timesteps, m.SSF, m.SSN, m.fc_hidden, m.compute_mode = ch, T, S, S, F, mode
+    m.aux = dict(m.aux, hidden_init=hidden_init)
+    m.load_params(P)
+    out = m.build(torch.as_tensor(depth).cuda(), 69)
+    ref, acts = otorch.pose_forward(depth, P, hidden_init, timesteps=T, dtype=torch.float64, trace=True)
+    tol = {"fp32": 1e-4, "bf16x3": 1e-4, "bf16": 1e-2}[mode]
+    e_h = onp.rel_err(m.activation("hgru").cpu().numpy(), acts["hgru"].numpy())[0]
+    e_o = onp.rel_err(out.cpu().numpy(), ref.numpy())[0]
+    print("hidden_init=%s %s: hgru rel %.3e, out_put rel %.3e" % (hidden_init, mode, e_h, e_o))
+    assert e_h < tol and e_o < tol
+    # the named state must matter (a silently ignored option would also pass a loose tolerance against itself)
+    other = otorch.pose_forward(depth, P, "zeros" if hidden_init == "identity" else "identity", timesteps=T,
+                                dtype=torch.float64)
+    assert onp.rel_err(other.numpy(), ref.numpy())[0] > 5 * tol
+    out_host = m.build(torch.as_tensor(depth).pin_memory(), 69)
+    assert torch.equal(out_host, out.cpu())
+    # an explicit hidden_state wins over the option, and switching back restores the named state
+    m.hidden_state = init.hidden_init((N, hw, hw, ch), seed=5)
+    o2 = m.build(torch.as_tensor(depth).cuda(), 69)
+    assert not torch.equal(o2, out)
+    m.hidden_state = None
+    assert torch.equal(m.build(torch.as_tensor(depth).cuda(), 69), out)
 
 
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])

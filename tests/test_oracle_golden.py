@@ -5,6 +5,7 @@ import os
 
 import numpy as np
 import pytest
+import torch
 
 from oracle import hgru_oracle_np as onp
 from oracle import hgru_oracle_torch as otorch
@@ -93,6 +94,13 @@ def test_numpy_and_torch_pose_forward_agree():
     assert np.abs(acts["hgru"]).max() > 1e-3
     assert onp.rel_err(b, a)[0] < 1e-5
     assert onp.mean_joint_error_mm(b, a) < 1e-2
+    # the reference's named initial states (hgru_module.py:876-878, 888-890): 'identity' is O_0 = conv3
+    for name, explicit in (("identity", acts["conv3"]), ("zeros", np.zeros_like(acts["conv3"]))):
+        n = onp.pose_forward(depth, P, name, timesteps=3)
+        assert np.array_equal(n, onp.pose_forward(depth, P, explicit, timesteps=3))
+        assert onp.rel_err(otorch.pose_forward(depth, P, name, timesteps=3, dtype=torch.float64).numpy(), n)[0] < 1e-12
+    with pytest.raises(RuntimeError):
+        onp.pose_forward(depth, P, "bogus", timesteps=3)
 
 
 def test_metric_restatement():
