@@ -436,8 +436,11 @@ __device__ __forceinline__ void stack_mma_issuer(const TcConvArgs& a, uint32_t t
 // carry), fused math, stores.  Two warpgroups split the channels so that each SM sub-partition has
 // two epilogue warps to overlap TMEM / global-memory latencies; they never need to talk to each
 // other (un-stacking and the integration math are per channel).
-template <class Cfg, class Epi, int C0, int CN, bool PROF, bool PART = false>
-__device__ __forceinline__ void stack_epilogue(const TcConvArgs& a, uint32_t tmem_base, uint32_t bar_acc_full,
+// C0 is a run-time value: warpgroups with the same channel count CN execute ONE copy of this code (the epilogue is
+// the bulk of the kernel's instructions, and per-group copies thrash the instruction caches: `stall_no_inst` was
+// 31 % of the H2 kernel's samples, profiles/r02_ncu_source_stalls_stack_k25_v39.txt).
+template <class Cfg, class Epi, int CN, bool PROF, bool PART = false>
+__device__ __forceinline__ void stack_epilogue(const TcConvArgs& a, const int C0, uint32_t tmem_base, uint32_t bar_acc_full,
                                                uint32_t bar_acc_empty, uint32_t crank, int iters, int NT,
                                                int units_per_frame, int warp, int lane, bool profile,
                                                uint8_t* smem_raw, uint32_t gate_a, uint32_t gate_w,
@@ -543,19 +546,21 @@ __device__ __forceinline__ void stack_epilogue(const TcConvArgs& a, uint32_t tme
         }
       }
       if constexpr (PROF) { const long long t = clock64(); e_tm += t - e0; e0 = t; }
-      if (!(gated && j >= 1)) {
+      const bool gate_follows = gated && j >= 1;
+      if (!gate_follows) {
         tc_fence_before();
         // accumulator drained: MMAs may reuse it (pair mode: the leader's barrier counts both CTAs)
         if (CS > 1 && crank != 0) mbar_arrive_cluster(lead_acc_empty + 8 * slot);
         else mbar_arrive(bar_acc_empty + 8 * slot);
-        if (store) Epi::template finish<NCH, CN>(a, n, pin, C0, out, pre);
-        if constexpr (PROF) { const long long t = clock64(); e_fin += t - e0; e0 = t; }
-      } else {
-        // ---- fused gate: new state -> bf16 staging tile -> 1x1 conv on the tensor core -> sigmoid ----
-        float hv[NCH];
+      }
+      // the fused math + stores: ONE inlined copy serves both paths (the new state also stays in registers for the gate)
+      float hv[NCH];
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) hv[c] = 0.f;
-        if (store) Epi::template finish<NCH, CN>(a, n, pin, C0, out, pre, hv);
+      for (int c = 0; c < NCH; ++c) hv[c] = 0.f;
+      if (store) Epi::template finish<NCH, CN>(a, n, pin, C0, out, pre, hv);
+      if constexpr (PROF) { const long long t = clock64(); e_fin += t - e0; e0 = t; }
+      if (gate_follows) {
+        // ---- fused gate: new state -> bf16 staging tile -> 1x1 conv on the tensor core -> sigmoid ----
         {
           uint8_t* stg = smem_raw + (gate_a - smem_u32(smem_raw));
 #pragma unroll
@@ -576,7 +581,6 @@ __device__ __forceinline__ void stack_epilogue(const TcConvArgs& a, uint32_t tme
             }
           }
         }
-        if constexpr (PROF) { const long long t = clock64(); e_fin += t - e0; e0 = t; }
         fence_proxy_async();          // staging writes -> visible to the async (tensor core) proxy
         tc_fence_before();            // our tcgen05.ld of this accumulator precede the barrier
         asm volatile("bar.sync 1, %0;" ::"n"(Cfg::NEPI) : "memory");
@@ -823,22 +827,14 @@ hconv_stack_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
     ae.bias = par; ae.v0 = par + KP; ae.v1 = par + 2 * KP; ae.v2 = par + 3 * KP; ae.gate_bias = par + 4 * KP;
     ae.rho_t = par + 5 * KP;
     // ---------------- epilogue: NGRP warpgroups, 8-channel chunks each, the last one takes the rest ----------
-#define HGRU_STACK_EPI(C0_, CN_, FIRST_)                                                                          \
-  stack_epilogue<Cfg, Epi, C0_, CN_, PROF, PART>(ae, tmem_base, bar_acc_full, bar_acc_empty, crank, iters, NT,           \
-                                           units_per_frame, warp, lane, FIRST_, smem_raw, gate_a, gate_w, bar_gate)
-    if constexpr (Cfg::NGRP == 4) {
-      if (warp < 8) HGRU_STACK_EPI(0, 8, true);
-      else if (warp < 12) HGRU_STACK_EPI(8, 8, false);
-      else if (warp < 16) HGRU_STACK_EPI(16, 8, false);
-      else HGRU_STACK_EPI(24, KC - 24, false);
-    } else if constexpr (Cfg::NGRP == 3) {
-      if (warp < 8) HGRU_STACK_EPI(0, 8, true);
-      else if (warp < 12) HGRU_STACK_EPI(8, 8, false);
-      else HGRU_STACK_EPI(16, KC - 16, false);
-    } else {
-      if (warp < 8) HGRU_STACK_EPI(0, 8, true);
-      else HGRU_STACK_EPI(8, KC - 8, false);
-    }
+#define HGRU_STACK_EPI(C0_, CN_)                                                                                 \
+  stack_epilogue<Cfg, Epi, CN_, PROF, PART>(ae, C0_, tmem_base, bar_acc_full, bar_acc_empty, crank, iters, NT,          \
+                                            units_per_frame, warp, lane, warp < 8, smem_raw, gate_a, gate_w, bar_gate)
+    // all groups but the last take 8 channels and share one copy of the code
+    constexpr int kLastGrp = Cfg::NGRP - 1;
+    const int grp = (warp - 4) >> 2;
+    if (grp < kLastGrp) HGRU_STACK_EPI(8 * grp, 8);
+    else HGRU_STACK_EPI(8 * kLastGrp, KC - 8 * kLastGrp);
 #undef HGRU_STACK_EPI
   }
 
