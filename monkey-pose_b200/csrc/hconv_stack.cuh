@@ -70,6 +70,8 @@ struct StackCfg {
   // stores) a warpgroup of its own.  It balances the groups (no more waiting at the gate barrier) but the fifth warp
   // per SM sub-partition slows the MMA issuer: +8 % cycles, same time (profiles/r01_stack_kernel_v27_ngrp4_ab.log).
   static constexpr int NGRP = (KC == 25) ? 4 : ((KC > 16) ? 3 : 2);
+#elif defined(HGRU_STACK_NGRP4_K32)
+  static constexpr int NGRP = (KC == 32) ? 4 : ((KC > 16) ? 3 : 2);      // development switch: 8/8/8/8 instead of 8/8/16
 #else
   static constexpr int NGRP = (KC > 16) ? 3 : 2;
 #endif
@@ -438,7 +440,7 @@ __device__ __forceinline__ void stack_mma_issuer(const TcConvArgs& a, uint32_t t
 // other (un-stacking and the integration math are per channel).
 // C0 is a run-time value: warpgroups with the same channel count CN execute ONE copy of this code (the epilogue is
 // the bulk of the kernel's instructions, and per-group copies thrash the instruction caches: `stall_no_inst` was
-// 31 % of the H2 kernel's samples, profiles/r02_ncu_source_stalls_stack_k25_v39.txt).
+// 31 % of the H2 kernel's samples, profiles/r02_ncu_source_stalls_stack_k25_v39_v40.txt).
 template <class Cfg, class Epi, int CN, bool PROF, bool PART = false>
 __device__ __forceinline__ void stack_epilogue(const TcConvArgs& a, const int C0, uint32_t tmem_base, uint32_t bar_acc_full,
                                                uint32_t bar_acc_empty, uint32_t crank, int iters, int NT,
