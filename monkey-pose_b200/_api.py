@@ -12,8 +12,8 @@ from .hgru_pose import model  # noqa: F401
 from .attn_model import attn_model_struct  # noqa: F401
 from . import tf_checkpoint  # noqa: F401
 from . import pipeline  # noqa: F401
-from .pipeline import FramesToJoints  # noqa: F401
+from .pipeline import FramesToJoints, StreamedForward  # noqa: F401
 
 __all__ = ["ContextualCircuit", "auxilliary_variables", "model", "attn_model_struct", "initialization",
            "hgru_module", "hgru_pose", "attn_model", "pose_evaluation", "sharding", "tf_monkeydetector",
-           "tf_checkpoint", "pipeline", "FramesToJoints", "_lib"]
+           "tf_checkpoint", "pipeline", "FramesToJoints", "StreamedForward", "_lib"]

@@ -88,3 +88,62 @@ class FramesToJoints(object):
         uvd_h.copy_(uvd, non_blocking=True)
         main.synchronize()
         return xyz_h, uvd_h
+
+
+class StreamedForward(object):
+    """A stream of host batches through `model.build`, double-buffered: while batch i runs, batch i+1 is copied to the
+    device on a second stream and the predictions of batch i-1 travel back -- the role the reference gives its input
+    queues (`tf.train.shuffle_batch(..., num_threads=2, capacity=...)`, data_loader.py:38, started by
+    `tf.train.start_queue_runners`, train_cnn_networks_hgru.py:200-201,309-310: the next batch is staged while
+    `sess.run` computes).  Per-batch results are bitwise those of `model.build(batch, output_shape)`; only the order
+    of the copies changes.  Everything numerical runs in libhgru_b200.so; no CPU fallback.
+
+        for out in StreamedForward(m, 69)(batches):      # batches: iterable of pinned [N,128,128,1] float32 tensors
+            ...                                          # out: [N,69] float32 on the host, in batch order
+    """
+
+    def __init__(self, pose, output_shape):
+        self.pose, self.output_shape = pose, int(output_shape)
+        self._shape = None
+
+    def _buffers(self, shape, device):
+        if self._shape != tuple(shape):
+            self._shape = tuple(shape)
+            self._dev = [torch.empty(shape, device=device, dtype=torch.float32) for _ in range(2)]
+            self._host = [torch.empty((shape[0], self.output_shape), dtype=torch.float32, pin_memory=True)
+                          for _ in range(2)]
+            self._copy = torch.cuda.Stream(device=device)
+            self._landed = [torch.cuda.Event() for _ in range(2)]
+            self._consumed = [torch.cuda.Event() for _ in range(2)]
+            self._done = [torch.cuda.Event() for _ in range(2)]
+
+    def __call__(self, batches):
+        device = torch.device("cuda", torch.cuda.current_device())
+        main = torch.cuda.current_stream()
+        pending = None                       # slot whose predictions are on their way back
+        for i, b in enumerate(batches):
+            if b.is_cuda:
+                raise ValueError("StreamedForward takes host batches (use model.build for device tensors)")
+            if b.dim() == 3:
+                b = b[..., None]
+            self._buffers(b.shape, device)
+            s = i & 1
+            if i >= 2:
+                self._copy.wait_event(self._consumed[s])         # batch i-2 has been read out of this buffer
+            else:
+                self._copy.wait_stream(main)
+            with torch.cuda.stream(self._copy):
+                self._dev[s].copy_(b, non_blocking=True)
+                self._landed[s].record(self._copy)
+            main.wait_event(self._landed[s])
+            out = self.pose.build(self._dev[s], self.output_shape)
+            self._consumed[s].record(main)
+            if pending is not None:                              # hand batch i-1 out while batch i runs
+                self._done[pending].synchronize()
+                yield self._host[pending].clone()
+            self._host[s].copy_(out, non_blocking=True)
+            self._done[s].record(main)
+            pending = s
+        if pending is not None:
+            self._done[pending].synchronize()
+            yield self._host[pending].clone()

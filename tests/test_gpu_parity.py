@@ -515,3 +515,24 @@ def test_bf16x3_pose_model_and_unsupported_shapes():
     assert onp.mean_joint_error_mm(out.cpu().numpy(), ref.numpy()) < 0.01
     with pytest.raises(NotImplementedError):          # only the 15x15 horizontal kernel is instantiated
         _pose("bf16x3", 1, 16, 16, 1, 5, 32)
+
+
+@pytest.mark.parametrize("mode", ["bf16", "fp32"])
+def test_streamed_forward_equals_batch_by_batch_build(mode):
+    """StreamedForward (upload of batch i+1 and read-back of batch i-1 around the forward of batch i) yields, in
+    order, bitwise what model.build returns for each host batch; buffers are reused safely over more than two
+    batches, and a second pass over the same object restarts cleanly."""
+    N, ch, hw, T, S, F = 5, 16, 16, 2, 15, 32
+    m, _, P, _, _ = _pose(mode, N, ch, hw, T, S, F)
+    batches = [torch.as_tensor(init.synthetic_depth(N, seed=10 + i, size=2 * hw)).pin_memory() for i in range(5)]
+    want = [m.build(b, 69).clone() for b in batches]
+    assert not torch.equal(want[0], want[1])
+    sf = mp.StreamedForward(m, 69)
+    for _ in range(2):
+        got = list(sf(iter(batches)))
+        assert len(got) == len(want)
+        for g, w in zip(got, want):
+            assert not g.is_cuda and torch.equal(g, w)
+    assert list(sf(iter([]))) == []
+    with pytest.raises(ValueError):
+        list(sf([batches[0].cuda()]))
