@@ -108,6 +108,9 @@ class StreamedForward(object):
 
     def _buffers(self, shape, device):
         if self._shape != tuple(shape):
+            if self._shape is not None:          # (the caller has drained the stream: see __call__)
+                self._copy.synchronize()
+                torch.cuda.current_stream().synchronize()
             self._shape = tuple(shape)
             self._dev = [torch.empty(shape, device=device, dtype=torch.float32) for _ in range(2)]
             self._host = [torch.empty((shape[0], self.output_shape), dtype=torch.float32, pin_memory=True)
@@ -121,11 +124,19 @@ class StreamedForward(object):
         device = torch.device("cuda", torch.cuda.current_device())
         main = torch.cuda.current_stream()
         pending = None                       # slot whose predictions are on their way back
-        for i, b in enumerate(batches):
+        i = 0                                # batches since the buffers were (re)made
+        for b in batches:
             if b.is_cuda:
                 raise ValueError("StreamedForward takes host batches (use model.build for device tensors)")
             if b.dim() == 3:
                 b = b[..., None]
+            if self._shape is not None and self._shape != tuple(b.shape):
+                # a new batch shape mid-stream: hand out what is in flight, then start over with new buffers
+                if pending is not None:
+                    self._done[pending].synchronize()
+                    yield self._host[pending].clone()
+                    pending = None
+                i = 0
             self._buffers(b.shape, device)
             s = i & 1
             if i >= 2:
@@ -144,6 +155,7 @@ class StreamedForward(object):
             self._host[s].copy_(out, non_blocking=True)
             self._done[s].record(main)
             pending = s
+            i += 1
         if pending is not None:
             self._done[pending].synchronize()
             yield self._host[pending].clone()

@@ -524,6 +524,7 @@ def test_streamed_forward_equals_batch_by_batch_build(mode):
     batches, and a second pass over the same object restarts cleanly."""
     N, ch, hw, T, S, F = 5, 16, 16, 2, 15, 32
     m, _, P, _, _ = _pose(mode, N, ch, hw, T, S, F)
+    m.hidden_state, m.aux = None, dict(m.aux, hidden_init="zeros")      # (any batch size: the ragged case below)
     batches = [torch.as_tensor(init.synthetic_depth(N, seed=10 + i, size=2 * hw)).pin_memory() for i in range(5)]
     want = [m.build(b, 69).clone() for b in batches]
     assert not torch.equal(want[0], want[1])
@@ -536,3 +537,10 @@ def test_streamed_forward_equals_batch_by_batch_build(mode):
     assert list(sf(iter([]))) == []
     with pytest.raises(ValueError):
         list(sf([batches[0].cuda()]))
+    # a ragged last batch (new shape mid-stream): what is in flight is handed out first, then new buffers
+    ragged = batches[:3] + [batches[3][:2]]
+    got = list(sf(iter(ragged)))
+    assert [tuple(g.shape) for g in got] == [(N, 69)] * 3 + [(2, 69)]
+    for g, w in zip(got[:3], want[:3]):
+        assert torch.equal(g, w)
+    assert torch.equal(got[3], m.build(batches[3][:2].contiguous().pin_memory(), 69))
