@@ -56,7 +56,10 @@ def test_hgru_matches_reference_golden_every_timestep(path, mode):
                                    (2, 40, 24, 25, 15, 3), (1, 33, 70, 25, 15, 2), (1, 18, 66, 24, 15, 2),
                                    (1, 64, 64, 17, 15, 2),
                                    # 33..48 channels are padded to 64 on the tensor-core paths
-                                   (2, 19, 21, 48, 15, 2)])
+                                   (2, 19, 21, 48, 15, 2),
+                                   # 64 channels (paired-tap schedule), ragged: the second 32-pixel unit of a row and
+                                   # the third 16-row unit of a frame are partly outside the image
+                                   (1, 37, 45, 64, 15, 2)])
 def test_hgru_seeded_cases_vs_oracle(shape, mode):
     """k = 64 (reference), 25 and 32 (BASELINE sweep), ragged H/W, tiny shapes; stress weights so
     tanh leaves its linear region."""
@@ -490,7 +493,7 @@ def test_bf16x3_mode_matches_reference_golden_every_timestep():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("shape", [(2, 64, 64, 25, 15, 2), (1, 20, 36, 32, 15, 3), (1, 33, 70, 16, 15, 2),
-                                   (1, 64, 64, 64, 15, 2), (2, 19, 21, 48, 15, 2)])
+                                   (1, 64, 64, 64, 15, 2), (2, 19, 21, 48, 15, 2), (1, 37, 45, 64, 15, 2)])
 def test_bf16x3_mode_seeded_cases_vs_oracle(shape):
     """Stress weights (tanh off its linear region): the split-bf16 tensor-core path stays inside the fp32 budget
     that plain bf16 misses by two orders of magnitude."""
