@@ -34,6 +34,14 @@ def test_library_exports_every_declared_symbol():
     assert set(_declared()) == set(_lib.SIGNATURES), "ctypes table out of sync with the header"
 
 
+def test_integration_doc_names_every_entry_point():
+    """INTEGRATION.md says, for every exported symbol, which reference interface it replaces (or that it is
+    introspection only)."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [n for n in _declared() if n not in doc]
+    assert not missing, missing
+
+
 def test_typed_load_and_pure_host_calls():
     from monkey_pose_b200 import _lib
     lib = _lib.load()
