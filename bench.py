@@ -67,7 +67,9 @@ def workload_config(a, n_gpus):
                                                  config_label(a.batch, a.channels, a.timesteps)),
             "global_batch": a.batch * n_gpus, "per_gpu_batch": a.batch, "channels": a.channels,
             "timesteps": a.timesteps, "h_kernel": 15, "hconv_arithmetic": a.mode,
-            "parallelism": "batch-sharded x%d, no data-path collective" % n_gpus,
+            "parallelism": "batch-sharded x%d, no data-path collective" % n_gpus + (
+                "; predictions all-gathered every step, asynchronously (complete inside the timed region)"
+                if n_gpus > 1 else ""),
             "cache": "per-step working set (%.0f MB of fp32 state per tensor) exceeds the 126 MB L2"
                      % (a.batch * 64 * 64 * max(16, (a.channels + 15) // 16 * 16) * 4 / 1e6)}
 
@@ -187,7 +189,7 @@ def run_ours(a):
     import torch.distributed as dist
     import monkey_pose_b200 as mp
     from monkey_pose_b200 import initialization as init
-    from monkey_pose_b200.sharding import gather_predictions
+    from monkey_pose_b200.sharding import PredictionGatherer
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -215,13 +217,15 @@ def run_ours(a):
             dist.barrier()
             torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, drain=None):
         sync()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()
         for _ in range(steps):
             fn()
+        if drain is not None:
+            drain()              # collectives still in flight are part of the job: the stream waits for them here
         e1.record()
         sync()
         t1 = time.perf_counter()
@@ -242,9 +246,17 @@ def run_ours(a):
     def measure(m, channels, timesteps, mode, B, depth_dev, depth_pin, steps, warmup, with_clocks, gather):
         """W warm-up steps, then K timed steps of the device-resident forward (+ the all-gather of the predictions
         when sharded), the conv kernels timed live; then the same through host buffers."""
+        # sharded: every step's predictions are all-gathered, asynchronously into one of two buffers, so a step does
+        # not wait for the collective (and through it for the slowest rank) before the next forward starts
+        gatherer = PredictionGatherer(B, 69, device="cuda") if (gather and world > 1) else None
+
         def step_dev():
             out = m.build(depth_dev, 69)
-            return gather_predictions(out, B * world) if (gather and world > 1) else out
+            if gatherer is not None:
+                gatherer.submit(out)
+                if os.environ.get("BENCH_SYNC_GATHER") == "1":      # A/B switch: wait for every step's collective
+                    gatherer.result()
+            return out
 
         def step_host():
             return m.build(depth_pin, 69)          # H2D of the crops + forward + D2H of the predictions
@@ -256,7 +268,7 @@ def run_ours(a):
             clocks.wait_ready()
         step_dev()  # the sampler start-up left rank 0's GPU idle: one more untimed step (every rank: it has a collective)
         lib.hgru_enable_kernel_timing(1)
-        ms_dev, t0, t1 = timed(step_dev, steps)
+        ms_dev, t0, t1 = timed(step_dev, steps, gatherer.drain if gatherer is not None else None)
         k_ms, k_n = ctypes.c_float(0), ctypes.c_int(0)
         lib.pose_plan_kernel_times(m._plan, ctypes.byref(k_ms), ctypes.byref(k_n))   # last step's hconv launches
         g_mean, g_min = ctypes.c_float(0), ctypes.c_float(0)
@@ -269,6 +281,8 @@ def run_ours(a):
             clk["sm_clock_in_kernel_ghz_min_cta"] = round(float(g_min.value), 4) if g_min.value else None
         launches = m.gpu_launches
         out_check = step_dev()
+        if gatherer is not None:
+            out_check = gatherer.result().clone()       # [world * B, 69], rank order = batch order
         assert torch.isfinite(out_check).all()
         ms_host = None
         if depth_pin is not None:
