@@ -181,7 +181,7 @@ def _free_port():
 def _shard_worker(rank, world, port, n_total, channels, T, out_path):
     """One process per shard (one per GPU when the box has several; NCCL then, else both on cuda:0 over gloo)."""
     import torch.distributed as dist
-    from monkey_pose_b200.sharding import gather_predictions, shard_bounds
+    from monkey_pose_b200.sharding import PredictionGatherer, gather_predictions, shard_bounds
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     multi = torch.cuda.device_count() >= world
@@ -198,6 +198,14 @@ def _shard_worker(rank, world, port, n_total, channels, T, out_path):
     out = m.build(torch.as_tensor(depth[lo:hi]).cuda(), 69)
     torch.cuda.synchronize()
     full = gather_predictions(out if multi else out.cpu(), n_total)
+    if n_total % world == 0:
+        # equal shards: the asynchronous double-buffered gather over three steps lands the same rows
+        g = PredictionGatherer(hi - lo, 69, device="cuda" if multi else "cpu")
+        for _ in range(3):
+            o = m.build(torch.as_tensor(depth[lo:hi]).cuda(), 69)
+            g.submit(o if multi else o.cpu())
+        g.drain()
+        assert torch.equal(g.result().cpu(), full.cpu())
     if rank == 0:
         np.save(out_path, full.cpu().numpy())
     dist.barrier()
