@@ -197,6 +197,23 @@ HGRU_API int crop_windows_forward(const float* tr_dev, const double* com_in_dev,
                                   double cube_y, double cube_z, double* coms_dev, int* iparams_dev,
                                   float* zparams_dev, double* Ms_dev, int* invalid_dev, void* stream);
 
+/* tfMonkeyDetector.calculateCoM (tf_monkeydetector.py:73-90) for a batch on the device: pixels outside
+ * [min_depth, max_depth] zeroed, (x, y) = centre of mass of the remaining mask, z = their mean depth.  The mean depth is a
+ * float32 numpy.sum in the reference; it is reproduced in numpy's pairwise order, so coms equals the host's bit for bit.
+ *   iparams_dev == zparams_dev == NULL: the image is each whole frame [H][W] times frame_scale -- what cropArea3D does
+ *     when no centre of mass is given (:307-308).
+ *   iparams_dev / zparams_dev as crop_windows_forward wrote them: the image is getCrop's z-clamped window (:208-244) and
+ *     the result gets the `docom` refinement of cropArea3D (:316-326): an all-zero centre of mass takes the window's
+ *     centre pixel as depth (300 if that is 0 too), then (xstart, ystart) is added.  Feed coms to crop_windows_forward
+ *     again for the refined window.
+ *   ws_dev: calculate_com_workspace_bytes(N, max_pixels) bytes; a window of more than max_pixels pixels gets a NaN
+ *     centre of mass and overflow[n] = 1.  coms_dev [N][3] double (u, v, d). */
+HGRU_API size_t calculate_com_workspace_bytes(int N, long long max_pixels);
+HGRU_API int calculate_com_forward(const float* frames_dev, int N, int H, int W, float frame_scale, float min_depth,
+                                   float max_depth, const int* iparams_dev, const float* zparams_dev,
+                                   long long max_pixels, void* ws_dev, double* coms_dev, int* overflow_dev,
+                                   void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Post-processing (the step right after the pose network).
  * pose_postprocess_forward: out_put [N,3J] (normalised) -> xyz [N,J,3] = out*scale + uvdtoxyz(com),
@@ -211,6 +228,28 @@ HGRU_API int pose_postprocess_forward(const float* out_put_dev, const double* co
 HGRU_API int joint_error_forward(const float* labels_dev, const float* results_dev, int N, int J,
                                  double* frame_mean_ws_dev, float* frame_max_ws_dev, double* result_dev,
                                  void* stream);
+
+/* The rest of the reference's metric file on the device (pose_evaluation.py:10-88), in numpy's own float32
+ * evaluation order (pairwise sums over contiguous axes, element-by-element sums over the others), so the values are
+ * bit-identical to the host functions' on float32 inputs, not merely close.
+ * joint_error_stats_forward: labels / results [N][J][3] float32 (mm) ->
+ *   err [N][J]      per-joint Euclidean error sqrt(((l - r)^2).sum(axis=2)), the expression every metric starts from;
+ *   frame_mean [N]  nanmean(err, axis=1) = getMeanErrors_N (:46-52), the statistic of getNumFramesWithinMeanDist (:72-78);
+ *   frame_max [N]   nanmax(err, axis=1), the statistic of getNumFramesWithinMaxDist (:63-69);
+ *   joint_mean [J]  nanmean(err[:, j]) = getJointMeanError(labels, results, j) (:81-88) for every joint;
+ *   summary [2]     {nanmean(frame_mean) = getMeanError_np / getMeanError_train (:10-15, :30-36),
+ *                    nanmax(err) = getMaxError_np / getMaxError (:18-23, :54-60)}.
+ *   skip_nan = 1: numpy's nan* functions (NaN joints left out); 0: the TensorFlow variants (a NaN propagates).
+ * joint_error_count_within_forward: *count = number of n with frame_stat[n] <= dist (:63-78).
+ * axis1_error_mean_forward: getMean_np / getMeanError (:26-28, :38-44): a, b [N][M][C] (C = 1 for rank-2 inputs)
+ *   -> rows_ws [N][C] = sqrt(((a - b)^2).sum(axis=1)), out [C] = (nan)mean over axis 0. */
+HGRU_API int joint_error_stats_forward(const float* labels_dev, const float* results_dev, int N, int J, int skip_nan,
+                                       float* err_dev, float* frame_mean_dev, float* frame_max_dev,
+                                       float* joint_mean_dev, float* summary_dev, void* stream);
+HGRU_API int joint_error_count_within_forward(const float* frame_stat_dev, int N, float dist, int* count_dev,
+                                              void* stream);
+HGRU_API int axis1_error_mean_forward(const float* a_dev, const float* b_dev, int N, int M, int C, int skip_nan,
+                                      float* rows_ws_dev, float* out_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Attention (centre-of-mass) CNN: the network right before the crop stage, reference

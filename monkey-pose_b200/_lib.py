@@ -75,9 +75,15 @@ SIGNATURES = {
     "crop_windows_forward": (_I, [_P, _P, ctypes.c_double, ctypes.c_double, ctypes.c_double, _I, _I, _I, _I, _I,
                                   ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                   _P, _P, _P, _P, _P, _P]),
+    "calculate_com_workspace_bytes": (ctypes.c_size_t, [_I, ctypes.c_longlong]),
+    "calculate_com_forward": (_I, [_P, _I, _I, _I, ctypes.c_float, ctypes.c_float, ctypes.c_float, _P, _P,
+                                   ctypes.c_longlong, _P, _P, _P, _P]),
     "pose_postprocess_forward": (_I, [_P, _P, _I, _I, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                       ctypes.c_double, ctypes.c_float, _P, _P, _P]),
     "joint_error_forward": (_I, [_P, _P, _I, _I, _P, _P, _P, _P]),
+    "joint_error_stats_forward": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "joint_error_count_within_forward": (_I, [_P, _I, ctypes.c_float, _P, _P]),
+    "axis1_error_mean_forward": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "attn_plan_create": (_I, [_I, _I, _I, ctypes.POINTER(_I), _I, _I, ctypes.POINTER(_P)]),
     "attn_plan_destroy": (_I, [_P]),
     "attn_set_params": (_I, [_P, ctypes.POINTER(AttnParams), ctypes.c_float, _P]),

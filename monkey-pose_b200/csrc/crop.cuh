@@ -7,6 +7,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "np_reduce.cuh"
+
 namespace hgru {
 
 // per-frame integers: xstart, ystart, wb, hb (source window), sz_w, sz_h (resized crop), xs, ys (paste offset)
@@ -115,6 +117,116 @@ crop_windows_kernel(const float* __restrict__ tr, const double* __restrict__ com
   M[3] = 0.; M[4] = sc; M[5] = __dadd_rn(__dmul_rn(sc, -static_cast<double>(ystart)), static_cast<double>(ys));
   M[6] = 0.; M[7] = 0.; M[8] = 1.;
   invalid[n] = bad ? 1 : 0;
+}
+
+// tfMonkeyDetector.calculateCoM (tf_monkeydetector.py:73-90) for a batch: depth outside [minDepth, maxDepth] zeroed,
+// centre of mass of the mask (scipy.ndimage.center_of_mass of dc > 0: integer sums, exact), mean depth =
+// dc.sum() / count_nonzero(dc).  dc.sum() is a float32 sum whose value depends on numpy's pairwise order, so the
+// blocks of numpy's tree are summed one per thread (np_block_sum) and combined level by level by heap index
+// (np_reduce.cuh): the result is the host's, bit for bit.  One CTA per frame.
+//   ip == nullptr: the image is the whole frame (cropArea3D with com=None, :307-308).
+//   ip / zp given (crop_windows_kernel's output): the image is getCrop's window (:208-244) -- the frame's pixels where
+//   the window overlaps it, zeros elsewhere, z-clamped -- and the result gets cropArea3D's `docom` treatment
+//   (:318-326): if the CoM is all zero take the window's centre pixel as depth (300 if that is zero too), then add
+//   (xstart, ystart).
+// heap [N][heap_cap] floats of workspace; a frame whose image needs more (window larger than the caller's bound) gets
+// a NaN centre of mass and overflow[n] = 1.
+struct ComImage {
+  const float* frame;
+  float scale, zs, ze, lo, hi;
+  int H, W, xstart, ystart, wb;
+  bool clamp;
+  // element i of the (virtual) image after getCrop's z clamp and calculateCoM's range test
+  __device__ __forceinline__ float crop_value(unsigned i, unsigned* row, unsigned* col) const {
+    const unsigned r = i / static_cast<unsigned>(wb), c = i - r * static_cast<unsigned>(wb);
+    *row = r; *col = c;
+    const int Y = ystart + static_cast<int>(r), X = xstart + static_cast<int>(c);
+    float v = 0.f;
+    if (Y >= 0 && Y < H && X >= 0 && X < W) v = __fmul_rn(frame[static_cast<size_t>(Y) * W + X], scale);
+    if (clamp && v != 0.f) {
+      if (v < zs) v = zs;
+      else if (v > ze) v = 0.f;
+    }
+    return v;
+  }
+  __device__ __forceinline__ float com_value(float v) const {
+    if (v < lo) v = 0.f;
+    if (v > hi) v = 0.f;
+    return v;
+  }
+};
+
+__global__ void __launch_bounds__(1024)
+calculate_com_kernel(const float* __restrict__ frames, int H, int W, float frame_scale, float min_depth,
+                     float max_depth, const int* __restrict__ ip, const float* __restrict__ zp, float* __restrict__ heap,
+                     unsigned heap_cap, double* __restrict__ coms, int* __restrict__ overflow) {
+  __shared__ unsigned long long s_stat[4];     // #(dc > 0), #(dc != 0), sum of columns, sum of rows over the mask
+  const int n = blockIdx.x;
+  const int tid = threadIdx.x, T = blockDim.x;
+  ComImage im;
+  im.frame = frames + static_cast<size_t>(n) * H * W;
+  im.scale = frame_scale; im.lo = min_depth; im.hi = max_depth; im.H = H; im.W = W;
+  int hb;
+  if (ip) {
+    const int* q = ip + 8 * n;
+    im.xstart = q[0]; im.ystart = q[1]; im.wb = q[2]; hb = q[3];
+    im.zs = zp[2 * n]; im.ze = zp[2 * n + 1]; im.clamp = true;
+  } else {
+    im.xstart = 0; im.ystart = 0; im.wb = W; hb = H; im.zs = 0.f; im.ze = 0.f; im.clamp = false;
+  }
+  const long long npx = static_cast<long long>(im.wb) * hb;
+  const int depth = np_pairwise_depth(npx);
+  if (npx < 1 || npx > 0x7fffffffLL || (2ull << depth) > heap_cap) {
+    if (tid == 0) {
+      coms[3 * n] = coms[3 * n + 1] = coms[3 * n + 2] = nan("");
+      overflow[n] = 1;
+    }
+    return;
+  }
+  if (tid < 4) s_stat[tid] = 0ull;
+  __syncthreads();
+  float* vals = heap + static_cast<size_t>(n) * heap_cap;
+  unsigned long long pos = 0, nz = 0, sx = 0, sy = 0;
+  np_tree_blocks([&](long long i) {
+    unsigned r, c;
+    const float v = im.com_value(im.crop_value(static_cast<unsigned>(i), &r, &c));
+    if (v > 0.f) { ++pos; sx += c; sy += r; }
+    if (v != 0.f) ++nz;
+    return v;
+  }, npx, tid, T, vals);
+  // the integer statistics do not depend on the order of addition
+  for (int o = 16; o > 0; o >>= 1) {
+    pos += __shfl_xor_sync(0xffffffffu, pos, o); nz += __shfl_xor_sync(0xffffffffu, nz, o);
+    sx += __shfl_xor_sync(0xffffffffu, sx, o);   sy += __shfl_xor_sync(0xffffffffu, sy, o);
+  }
+  if ((tid & 31) == 0) {
+    atomicAdd(&s_stat[0], pos); atomicAdd(&s_stat[1], nz); atomicAdd(&s_stat[2], sx); atomicAdd(&s_stat[3], sy);
+  }
+  __syncthreads();
+  for (int level = depth - 1; level >= 0; --level) {
+    np_tree_level(npx, level, tid, T, vals);
+    __syncthreads();
+  }
+  if (tid != 0) return;
+  overflow[n] = 0;
+  const double cnt = static_cast<double>(s_stat[0]), num = static_cast<double>(s_stat[1]);
+  double c0 = 0., c1 = 0., c2 = 0.;
+  if (s_stat[1] != 0ull) {
+    // cc = sums / count of the mask; com = (cc[1] * num, cc[0] * num, dc.sum()) / num, every step a rounded double op
+    c0 = __ddiv_rn(__dmul_rn(__ddiv_rn(static_cast<double>(s_stat[2]), cnt), num), num);
+    c1 = __ddiv_rn(__dmul_rn(__ddiv_rn(static_cast<double>(s_stat[3]), cnt), num), num);
+    c2 = __ddiv_rn(static_cast<double>(vals[1]), num);
+  }
+  if (ip) {
+    if (fabs(c0) <= 1e-8 && fabs(c1) <= 1e-8 && fabs(c2) <= 1e-8) {          // numpy.allclose(com, 0.)
+      unsigned r, c;
+      c2 = static_cast<double>(im.crop_value(static_cast<unsigned>(hb / 2) * im.wb + im.wb / 2, &r, &c));
+      if (fabs(c2) <= 1e-8) c2 = 300.;                                        // numpy.isclose(com[2], 0)
+    }
+    c0 = __dadd_rn(c0, static_cast<double>(im.xstart));
+    c1 = __dadd_rn(c1, static_cast<double>(im.ystart));
+  }
+  coms[3 * n] = c0; coms[3 * n + 1] = c1; coms[3 * n + 2] = c2;
 }
 
 }  // namespace hgru

@@ -1263,6 +1263,32 @@ int crop_windows_forward(const float* tr, const double* com_in, double s0, doubl
   return 0;
 }
 
+// heap slots per frame for images of up to max_pixels pixels: 2^(depth of numpy's pairwise tree + 1)
+static unsigned com_heap_slots(long long max_pixels) {
+  return 2u << hgru::np_pairwise_depth(max_pixels < 1 ? 1 : max_pixels);
+}
+size_t calculate_com_workspace_bytes(int N, long long max_pixels) {
+  if (N < 1 || max_pixels < 1 || max_pixels > 0x7fffffffLL) return 0;
+  return static_cast<size_t>(N) * com_heap_slots(max_pixels) * sizeof(float);
+}
+int calculate_com_forward(const float* frames, int N, int H, int W, float frame_scale, float min_depth, float max_depth,
+                          const int* iparams, const float* zparams, long long max_pixels, void* ws, double* coms,
+                          int* overflow, void* stream) {
+  if (!frames || !ws || !coms || !overflow) return fail(HGRU_E_INVALID, "calculate_com_forward: null pointer");
+  if ((iparams == nullptr) != (zparams == nullptr))
+    return fail(HGRU_E_INVALID, "calculate_com_forward: iparams and zparams go together");
+  if (N < 1 || H < 1 || W < 1) return fail(HGRU_E_INVALID, "calculate_com_forward: non-positive shape");
+  if (max_pixels < 1 || max_pixels > 0x7fffffffLL)
+    return fail(HGRU_E_INVALID, "calculate_com_forward: max_pixels must be in [1, 2^31)");
+  if (!iparams && static_cast<long long>(H) * W > max_pixels)
+    return fail(HGRU_E_INVALID, "calculate_com_forward: max_pixels is smaller than a frame");
+  hgru::calculate_com_kernel<<<N, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
+      frames, H, W, frame_scale, min_depth, max_depth, iparams, zparams, static_cast<float*>(ws),
+      com_heap_slots(max_pixels), coms, overflow);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 int pose_postprocess_forward(const float* out_put, const double* com_uvd, int N, int J, double fx, double fy,
                              double ux, double uy, float scale, float* xyz, float* uvd, void* stream) {
   if (!out_put || !com_uvd || !xyz || !uvd) return fail(HGRU_E_INVALID, "pose_postprocess_forward: null pointer");
@@ -1281,6 +1307,42 @@ int joint_error_forward(const float* labels, const float* results, int N, int J,
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   hgru::joint_error_frame_kernel<<<N, 128, 0, st>>>(labels, results, J, frame_mean_ws, frame_max_ws);
   hgru::joint_error_final_kernel<<<1, 32, 0, st>>>(frame_mean_ws, frame_max_ws, N, result);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int joint_error_stats_forward(const float* labels, const float* results, int N, int J, int skip_nan, float* err,
+                              float* frame_mean, float* frame_max, float* joint_mean, float* summary, void* stream) {
+  if (!labels || !results || !err || !frame_mean || !frame_max || !joint_mean || !summary)
+    return fail(HGRU_E_INVALID, "joint_error_stats_forward: null pointer");
+  if (N < 1 || J < 1) return fail(HGRU_E_INVALID, "joint_error_stats_forward: non-positive shape");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t NJ = static_cast<size_t>(N) * J;
+  hgru::joint_error_matrix_kernel<<<nblk(NJ), 256, 0, st>>>(labels, results, NJ, err);
+  hgru::joint_error_reduce_kernel<<<nblk(static_cast<size_t>(N) + J, 128), 128, 0, st>>>(err, N, J, skip_nan ? 1 : 0,
+                                                                                        frame_mean, frame_max, joint_mean);
+  hgru::joint_error_summary_kernel<<<1, 32, 0, st>>>(frame_mean, frame_max, N, skip_nan ? 1 : 0, summary);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int joint_error_count_within_forward(const float* frame_stat, int N, float dist, int* count, void* stream) {
+  if (!frame_stat || !count) return fail(HGRU_E_INVALID, "joint_error_count_within_forward: null pointer");
+  if (N < 1) return fail(HGRU_E_INVALID, "joint_error_count_within_forward: non-positive shape");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(cudaMemsetAsync(count, 0, sizeof(int), st));
+  hgru::count_within_kernel<<<nblk(N), 256, 0, st>>>(frame_stat, N, dist, count);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int axis1_error_mean_forward(const float* a, const float* b, int N, int M, int C, int skip_nan, float* rows_ws,
+                             float* out, void* stream) {
+  if (!a || !b || !rows_ws || !out) return fail(HGRU_E_INVALID, "axis1_error_mean_forward: null pointer");
+  if (N < 1 || M < 1 || C < 1) return fail(HGRU_E_INVALID, "axis1_error_mean_forward: non-positive shape");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  hgru::axis1_error_rows_kernel<<<nblk(static_cast<size_t>(N) * C), 256, 0, st>>>(a, b, N, M, C, rows_ws);
+  hgru::axis0_mean_kernel<<<nblk(C, 64), 64, 0, st>>>(rows_ws, N, C, skip_nan ? 1 : 0, out);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
