@@ -4,7 +4,12 @@ tf_monkeydetector.py:21-391, as used by `prepare_data_test`, train_cnn_networks_
 Same constructor and method names.  The camera / window arithmetic (a handful of scalars per frame)
 stays in numpy float64 exactly as the reference writes it; the per-pixel work -- slice, zero pad,
 z clamp, cv2 nearest-neighbour resize, paste, normalise -- runs in one CUDA kernel over the whole batch
-(`crop_area3d_forward`), bit-exact with the reference + OpenCV.  No CPU fallback.
+(`crop_area3d_forward`), bit-exact with the reference + OpenCV; the centre-of-mass estimate the reference
+falls back to when none is given, and its `docom` refinement (`calculateCoM`, :73-90, :307-333), run on the
+device too (`calculate_com_forward`), bit-exact as well.  No CPU fallback.
+
+Not mirrored: `checkImage` / `getNDValue` (:163-183) read `self.dpt`, which the reference's constructor no longer
+sets (and `getNDValue` drops into a debugger) -- they cannot run in the reference either.
 """
 import numpy
 
@@ -52,6 +57,56 @@ class tfMonkeyDetector(object):
         out[:, 1] = (j[:, 1] - self.uy) * j[:, 2] / (-self.fy)
         out[:, 2] = -j[:, 2]
         return out[0] if single else out
+
+    xyztouvd_np = xyztouvd          # tf_monkeydetector.py:116-136 (the reference's `xyztouvd` is its TF twin)
+
+    def calcCoMRenders(self, jnts):
+        """Centre of mass of a render's joints in 3-D (tf_monkeydetector.py:185-191)."""
+        jnts = numpy.asarray(jnts)
+        assert jnts.ndim == 2, 'input must be the 3D coordinates of all monkey joints'
+        return numpy.sum(jnts, axis=0) / jnts.shape[0]
+
+    def calculateCoMfrom3DJoints(self, jnts):
+        """Mean joint position [N,J,3] -> [N,3], projected to the image (tf_monkeydetector.py:66-71; the TF
+        projection has no z == 0 branch).  Label preparation: host arrays."""
+        com_3d = numpy.mean(numpy.asarray(jnts), axis=1)
+        u_s = self.ux - com_3d[:, 0] / com_3d[:, 2] * self.fx
+        v_s = self.uy + com_3d[:, 1] / com_3d[:, 2] * self.fy
+        return numpy.stack([u_s, v_s, -com_3d[:, 2]], axis=1)
+
+    # ---- centre of mass of a depth image (device; tf_monkeydetector.py:73-90) ---------------------------
+    def _max_window_pixels(self, H, W):
+        """The largest window comToBounds can ask for: a centre of mass at the near plane (:193-206)."""
+        near = max(float(self.minDepth), 1.0)
+        wb = int(numpy.ceil(self.cube[0] / near * self.fx)) + 2
+        hb = int(numpy.ceil(self.cube[1] / near * self.fy)) + 2
+        return min(max(wb * hb, H * W), 2 ** 31 - 1)
+
+    def calculateCoM_batch(self, frames, frame_scale=1.0, windows=None):
+        """calculateCoM for every frame of a [N,H,W] torch CUDA tensor (times frame_scale = mm) -> CUDA float64
+        [N,3] (x, y, mean depth), bit for bit the reference's values for float32 frames.  `windows` = (iparams,
+        zparams) CUDA tensors of `crop_windows_forward`: the centre of mass of each frame's z-clamped crop window
+        with cropArea3D's `docom` fallbacks and offset (:316-326) instead."""
+        if not (torch.is_tensor(frames) and frames.is_cuda and frames.dim() == 3):
+            raise RuntimeError("frames must be a [N,H,W] torch CUDA tensor (no CPU fallback)")
+        frames = frames.to(torch.float32).contiguous()
+        N, H, W = [int(v) for v in frames.shape]
+        lib = _lib.load()
+        max_px = self._max_window_pixels(H, W) if windows is not None else H * W
+        ws = torch.empty(int(lib.calculate_com_workspace_bytes(N, max_px)), device=frames.device, dtype=torch.uint8)
+        coms = torch.empty((N, 3), device=frames.device, dtype=torch.float64)
+        over = torch.empty((N,), device=frames.device, dtype=torch.int32)
+        ip, zp = windows if windows is not None else (None, None)
+        _lib.check(lib.calculate_com_forward(
+            frames.data_ptr(), N, H, W, float(frame_scale), float(self.minDepth), float(self.maxDepth),
+            ip.data_ptr() if ip is not None else None, zp.data_ptr() if zp is not None else None, max_px,
+            ws.data_ptr(), coms.data_ptr(), over.data_ptr(), _stream()), "calculate_com_forward")
+        self.last_com_overflow_dev = over
+        return coms
+
+    def calculateCoM(self, dpt):
+        """Centre of mass (x, y, z) of one depth image [H,W] in mm (tf_monkeydetector.py:73-90): numpy float64 [3]."""
+        return self.calculateCoM_batch(dpt[None]).cpu().numpy()[0]
 
     def comToBounds(self, com, size):
         zstart = com[2] - size[2] / 2.
@@ -183,10 +238,13 @@ class tfMonkeyDetector(object):
         return out, list(Ms), list(coms)
 
     def cropArea3D_batch_device(self, frames, tr=None, tr_scale=(1.0, 1.0, 1.0), coms=None, dsize=(128, 128),
-                                frame_scale=1.0, out_divisor=1.0):
+                                frame_scale=1.0, out_divisor=1.0, docom=False):
         """cropArea3D_batch with the window arithmetic on the device too (`crop_windows_forward`): no host round trip
-        between the attention CNN and the crop.  Centres of mass either as `coms` (CUDA float64 [N,3]; u, v, d mm) or
-        as attention outputs `tr` (CUDA float32 [N,3]) times `tr_scale` (train_cnn_networks_hgru.py:66-68).
+        between the attention CNN and the crop.  Centres of mass either as `coms` (CUDA float64 [N,3]; u, v, d mm), as
+        attention outputs `tr` (CUDA float32 [N,3]) times `tr_scale` (train_cnn_networks_hgru.py:66-68), or -- neither
+        given -- estimated from each frame by `calculateCoM` as the reference does (tf_monkeydetector.py:307-308).
+        `docom` adds the reference's second refinement (:316-333): the centre of mass of the first crop window
+        replaces the first estimate and the window is computed again.
         Returns (patches, Ms, coms) as CUDA tensors ([N,dh,dw] float32, [N,3,3] float64, [N,3] float64);
         `self.last_invalid_dev` (CUDA int32 [N]) flags frames whose window misses the frame (all-background patch)."""
         if len(dsize) != 2:
@@ -205,7 +263,7 @@ class tfMonkeyDetector(object):
                 raise RuntimeError("tr must be a CUDA tensor on the device path")
             tr = tr.to(torch.float32).reshape(N, 3).contiguous()
         else:
-            raise ValueError("give coms or tr")
+            coms = self.calculateCoM_batch(frames, frame_scale=frame_scale)
         coms_out = torch.empty((N, 3), device=dev, dtype=torch.float64)
         ip = torch.empty((N, 8), device=dev, dtype=torch.int32)
         zp = torch.empty((N, 2), device=dev, dtype=torch.float32)
@@ -213,12 +271,23 @@ class tfMonkeyDetector(object):
         inv = torch.empty((N,), device=dev, dtype=torch.int32)
         out = torch.empty((N, dsize[1], dsize[0]), device=dev, dtype=torch.float32)
         lib = _lib.load()
-        _lib.check(lib.crop_windows_forward(
-            tr.data_ptr() if coms is None else None, coms.data_ptr() if coms is not None else None,
-            float(tr_scale[0]), float(tr_scale[1]), float(tr_scale[2]), N, H, W, int(dsize[0]), int(dsize[1]),
-            float(self.fx), float(self.fy), float(self.cube[0]), float(self.cube[1]), float(self.cube[2]),
-            coms_out.data_ptr(), ip.data_ptr(), zp.data_ptr(), Ms.data_ptr(), inv.data_ptr(), _stream()),
-            "crop_windows_forward")
+
+        def windows(tr_, coms_):
+            _lib.check(lib.crop_windows_forward(
+                tr_.data_ptr() if coms_ is None else None, coms_.data_ptr() if coms_ is not None else None,
+                float(tr_scale[0]), float(tr_scale[1]), float(tr_scale[2]), N, H, W, int(dsize[0]), int(dsize[1]),
+                float(self.fx), float(self.fy), float(self.cube[0]), float(self.cube[1]), float(self.cube[2]),
+                coms_out.data_ptr(), ip.data_ptr(), zp.data_ptr(), Ms.data_ptr(), inv.data_ptr(), _stream()),
+                "crop_windows_forward")
+
+        windows(tr, coms)
+        if docom:
+            # a window that misses the frame has no crop to refine on: the reference's slicing is undefined there
+            # (the host path raises); its flag from the FIRST pass is kept
+            first_inv = inv.clone()
+            refined = self.calculateCoM_batch(frames, frame_scale=frame_scale, windows=(ip, zp))
+            windows(None, refined)
+            inv = torch.maximum(inv, first_inv)
         _lib.check(lib.crop_area3d_forward(
             frames.data_ptr(), N, H, W, float(frame_scale), ip.data_ptr(), zp.data_ptr(), float(self.maxDepth),
             float(out_divisor), out.data_ptr(), int(dsize[1]), int(dsize[0]), _stream()), "crop_area3d_forward")
@@ -227,13 +296,74 @@ class tfMonkeyDetector(object):
         return out, Ms, coms_out
 
     def cropArea3D(self, dpt, com=None, dsize=(128, 128), docom=False):
-        """tf_monkeydetector.py:292-365 for one frame [H,W] (mm): (patch, M, com)."""
+        """tf_monkeydetector.py:292-365 for one frame [H,W] (mm, torch CUDA): (patch, M, com).  Without `com` the
+        centre of mass is estimated from the frame (:307-308); `docom` refines it on the first crop (:316-333)."""
         if com is None or docom:
-            raise NotImplementedError("CoM estimation / refinement (calculateCoM) is not on the hot path: pass com")
+            if not (torch.is_tensor(dpt) and dpt.is_cuda and dpt.dim() == 2):
+                raise RuntimeError("dpt must be a [H,W] torch CUDA tensor (no CPU fallback)")
+            coms = None if com is None else torch.as_tensor(numpy.asarray(com, numpy.float64).reshape(1, 3)).cuda()
+            out, Ms, coms = self.cropArea3D_batch_device(dpt[None], coms=coms, dsize=dsize, docom=docom)
+            if int(self.last_invalid_dev[0].item()):
+                raise ValueError("crop window does not intersect the frame")
+            return out[0], Ms[0].cpu().numpy(), coms[0].cpu().numpy()
         out, Ms, coms = self.cropArea3D_batch(dpt[None], [com], dsize=dsize)
         if len(self.last_invalid):
             raise ValueError("crop window does not intersect the frame")
         return out[0], Ms[0], coms[0]
+
+    # ---- the crop's building blocks as stand-alone calls (tf_monkeydetector.py:208-290) ------------------
+    def _crop_call(self, img, ints, z, background, dsize):
+        """One frame through `crop_area3d_forward` with hand-made window integers."""
+        if not (torch.is_tensor(img) and img.is_cuda):
+            raise RuntimeError("the image must be a torch CUDA tensor (no CPU fallback)")
+        if img.dim() != 2:
+            raise NotImplementedError()
+        img = img.to(torch.float32).contiguous()
+        H, W = int(img.shape[0]), int(img.shape[1])
+        ip = torch.as_tensor(numpy.asarray([ints], numpy.int32)).cuda()
+        zp = torch.as_tensor(numpy.asarray([z], numpy.float32)).cuda()
+        out = torch.empty((1, dsize[1], dsize[0]), device=img.device, dtype=torch.float32)
+        _lib.check(_lib.load().crop_area3d_forward(
+            img.data_ptr(), 1, H, W, 1.0, ip.data_ptr(), zp.data_ptr(), float(background), 1.0, out.data_ptr(),
+            int(dsize[1]), int(dsize[0]), _stream()), "crop_area3d_forward")
+        return out[0]
+
+    def getCrop(self, dpt, xstart, xend, ystart, yend, zstart, zend, thresh_z=True):
+        """Crop the window out of a depth image [H,W], zero-padded where it leaves the image, clamped in z
+        (tf_monkeydetector.py:208-244): [yend - ystart, xend - xstart] CUDA float32."""
+        H, W = int(dpt.shape[0]), int(dpt.shape[1])
+        if xend <= 0 or yend <= 0 or xstart >= W or ystart >= H or xend <= xstart or yend <= ystart:
+            raise ValueError("crop window does not intersect the frame")
+        wb, hb = int(xend - xstart), int(yend - ystart)
+        z = (zstart, zend) if thresh_z is True else (-numpy.inf, numpy.inf)
+        return self._crop_call(dpt, (xstart, ystart, wb, hb, wb, hb, 0, 0), z, 0.0, (wb, hb))
+
+    def resizeCrop(self, crop, sz):
+        """cv2.resize(crop, sz, INTER_NEAREST) (tf_monkeydetector.py:246-261; sz = (width, height))."""
+        if self.resizeMethod != self.RESIZE_CV2_NN:
+            raise NotImplementedError("Unknown resize method!")
+        h, w = int(crop.shape[0]), int(crop.shape[1])
+        return self._crop_call(crop, (0, 0, w, h, int(sz[0]), int(sz[1]), 0, 0), (-numpy.inf, numpy.inf), 0.0,
+                               (int(sz[0]), int(sz[1])))
+
+    def applyCrop3D(self, dpt, com, size, dsize, thresh_z=True, background=None):
+        """Crop a `size` (mm) volume around `com` and paste it, resized, into a `background` image
+        (tf_monkeydetector.py:263-290).  `background` must be given: the reference's default, getNDValue, cannot run."""
+        if background is None:
+            raise ValueError("background must be given (the reference's getNDValue drops into a debugger)")
+        xstart, xend, ystart, yend, zstart, zend = self.comToBounds(com, size)
+        H, W = int(dpt.shape[0]), int(dpt.shape[1])
+        if xend <= 0 or yend <= 0 or xstart >= W or ystart >= H or xend <= xstart or yend <= ystart:
+            raise ValueError("crop window does not intersect the frame")
+        wb, hb = xend - xstart, yend - ystart
+        if wb > hb:
+            sz = (dsize[0], hb * dsize[0] // wb)
+        else:
+            sz = (wb * dsize[1] // hb, dsize[1])
+        xs = int(numpy.floor(dsize[0] / 2. - sz[0] / 2.))
+        ys = int(numpy.floor(dsize[1] / 2. - sz[1] / 2.))
+        z = (zstart, zend) if thresh_z is True else (-numpy.inf, numpy.inf)
+        return self._crop_call(dpt, (xstart, ystart, wb, hb, sz[0], sz[1], xs, ys), z, background, dsize)
 
 
 def preprocess_real_depth(raw, near=1000, far=3000, fill=10000.0, max_depth=10000.0, out=None):
