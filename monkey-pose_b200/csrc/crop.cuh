@@ -122,33 +122,55 @@ crop_windows_kernel(const float* __restrict__ tr, const double* __restrict__ com
 // tfMonkeyDetector.calculateCoM (tf_monkeydetector.py:73-90) for a batch: depth outside [minDepth, maxDepth] zeroed,
 // centre of mass of the mask (scipy.ndimage.center_of_mass of dc > 0: integer sums, exact), mean depth =
 // dc.sum() / count_nonzero(dc).  dc.sum() is a float32 sum whose value depends on numpy's pairwise order, so the
-// blocks of numpy's tree are summed one per thread (np_block_sum) and combined level by level by heap index
-// (np_reduce.cuh): the result is the host's, bit for bit.  One CTA per frame.
+// blocks of numpy's tree (np_reduce.cuh) are summed exactly as numpy sums them -- eight interleaved accumulators, here
+// eight lanes -- and combined level by level by heap index: the result is the host's, bit for bit.
 //   ip == nullptr: the image is the whole frame (cropArea3D with com=None, :307-308).
 //   ip / zp given (crop_windows_kernel's output): the image is getCrop's window (:208-244) -- the frame's pixels where
 //   the window overlaps it, zeros elsewhere, z-clamped -- and the result gets cropArea3D's `docom` treatment
 //   (:318-326): if the CoM is all zero take the window's centre pixel as depth (300 if that is zero too), then add
 //   (xstart, ystart).
-// heap [N][heap_cap] floats of workspace; a frame whose image needs more (window larger than the caller's bound) gets
-// a NaN centre of mass and overflow[n] = 1.
+// Two launches.  com_blocks_kernel is the HBM-bound one: grid (parts, N); a group of 8 lanes owns one block of numpy's
+// tree at a time (lane j = numpy's accumulator r[j], so a warp reads four 32-byte runs per load and every byte of a
+// frame exactly once), writes the block's sum to heap[n][heap index] and adds its integer statistics (counts, row and
+// column sums of the mask: order-free) to stats[n].  com_finish_kernel (one CTA per frame) combines the heap level by
+// level and does the few double operations of the reference in its order.
+// heap [N][heap_cap] floats, stats [N][4] uint64 (zeroed by the caller); a frame whose image needs a bigger heap
+// (window larger than the caller's bound) gets a NaN centre of mass and overflow[n] = 1.
 struct ComImage {
   const float* frame;
   float scale, zs, ze, lo, hi;
-  int H, W, xstart, ystart, wb;
-  bool clamp;
-  // element i of the (virtual) image after getCrop's z clamp and calculateCoM's range test
-  __device__ __forceinline__ float crop_value(unsigned i, unsigned* row, unsigned* col) const {
-    const unsigned r = i / static_cast<unsigned>(wb), c = i - r * static_cast<unsigned>(wb);
-    *row = r; *col = c;
-    const int Y = ystart + static_cast<int>(r), X = xstart + static_cast<int>(c);
-    float v = 0.f;
-    if (Y >= 0 && Y < H && X >= 0 && X < W) v = __fmul_rn(frame[static_cast<size_t>(Y) * W + X], scale);
-    if (clamp && v != 0.f) {
-      if (v < zs) v = zs;
-      else if (v > ze) v = 0.f;
+  int H, W, xstart, ystart, wb, hb;
+  bool window;
+  __device__ __forceinline__ void load(const float* frames, int n, int H_, int W_, float frame_scale, float min_depth,
+                                       float max_depth, const int* ip, const float* zp) {
+    frame = frames + static_cast<size_t>(n) * H_ * W_;
+    scale = frame_scale; lo = min_depth; hi = max_depth; H = H_; W = W_;
+    window = ip != nullptr;
+    if (window) {
+      const int* q = ip + 8 * n;
+      xstart = q[0]; ystart = q[1]; wb = q[2]; hb = q[3];
+      zs = zp[2 * n]; ze = zp[2 * n + 1];
+    } else {
+      xstart = 0; ystart = 0; wb = W_; hb = H_; zs = 0.f; ze = 0.f;
+    }
+  }
+  // pixel (r, c) of the image after getCrop's zero padding and z clamp
+  __device__ __forceinline__ float crop_value(int r, int c) const {
+    float v;
+    if (window) {
+      const int Y = ystart + r, X = xstart + c;
+      v = 0.f;
+      if (Y >= 0 && Y < H && X >= 0 && X < W) v = __fmul_rn(frame[static_cast<size_t>(Y) * W + X], scale);
+      if (v != 0.f) {
+        if (v < zs) v = zs;
+        else if (v > ze) v = 0.f;
+      }
+    } else {
+      v = __fmul_rn(frame[static_cast<size_t>(r) * W + c], scale);
     }
     return v;
   }
+  // calculateCoM's range test
   __device__ __forceinline__ float com_value(float v) const {
     if (v < lo) v = 0.f;
     if (v > hi) v = 0.f;
@@ -156,71 +178,210 @@ struct ComImage {
   }
 };
 
-__global__ void __launch_bounds__(1024)
-calculate_com_kernel(const float* __restrict__ frames, int H, int W, float frame_scale, float min_depth,
-                     float max_depth, const int* __restrict__ ip, const float* __restrict__ zp, float* __restrict__ heap,
-                     unsigned heap_cap, double* __restrict__ coms, int* __restrict__ overflow) {
-  __shared__ unsigned long long s_stat[4];     // #(dc > 0), #(dc != 0), sum of columns, sum of rows over the mask
+__device__ __forceinline__ bool com_frame_fits(const ComImage& im, unsigned heap_cap, long long* npx, int* depth) {
+  *npx = static_cast<long long>(im.wb) * im.hb;
+  if (*npx < 1 || *npx > 0x7fffffffLL) return false;
+  *depth = np_pairwise_depth(*npx);
+  return (2ull << *depth) <= heap_cap;
+}
+
+// One block of numpy's tree (8 <= len <= 128 pixels starting at pixel `off`) by a group of 8 lanes; lane j is numpy's
+// accumulator r[j].  Straight-line, predicated code: the lane's (up to) 16 pixels and its tail pixel are requested
+// first, all loads in flight together, then added in numpy's order.  WINDOW: the image is a crop window (bounds test,
+// z clamp), else the frame itself (pixel index = address).  Needs an image at least 8 pixels wide.
+template <bool WINDOW>
+__device__ __forceinline__ float com_block_sum8(const ComImage& im, unsigned off, int rb, int cb, int len, int lane,
+                                                unsigned gmask, unsigned& bpos, unsigned& bnz, unsigned& bsx,
+                                                unsigned& bsy) {
+  const int j = lane & 7, wb = im.wb;
+  const int full = len & ~7, tail = len & 7;
+  const int e0 = static_cast<int>(off) + j;
+  // (rb, cb) = row / column of the block's first pixel (kept by the caller from block to block: no division here)
+  int r0 = rb, c0 = cb + j;
+  if (c0 >= wb) { c0 -= wb; ++r0; }
+  auto fetch = [&](int e, int r, int c, bool on) -> float {
+    if (!WINDOW) return on ? __fmul_rn(im.frame[e], im.scale) : 0.f;
+    const int Y = im.ystart + r, X = im.xstart + c;
+    const bool inb = on && static_cast<unsigned>(Y) < static_cast<unsigned>(im.H) &&
+                     static_cast<unsigned>(X) < static_cast<unsigned>(im.W);
+    float v = inb ? __fmul_rn(im.frame[static_cast<size_t>(Y) * im.W + X], im.scale) : 0.f;
+    v = (v != 0.f && v < im.zs) ? im.zs : ((v > im.ze) ? 0.f : v);          // getCrop: clamp to the front face, drop the back
+    return v;
+  };
+  // tail pixel of this lane (numpy adds the len % 8 last pixels one by one at the end)
+  const int te = static_cast<int>(off) + full + j;
+  int tr = rb, tc = cb + full + j;
+  while (tc >= wb) { tc -= wb; ++tr; }
+  float tv = fetch(te, tr, tc, j < tail);
+  float v[16];
+  {
+    int r = r0, c = c0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      v[k] = fetch(e0 + 8 * k, r, c, 8 * k < full);
+      c += 8;
+      if (c >= wb) { c -= wb; ++r; }
+    }
+  }
+  float acc = 0.f;
+  if (wb >= 128) {
+    // at most one row change inside the block: the mask's row / column sums follow from two 16-bit masks
+    // (bit k = pixel k of this lane is in the mask / is non-zero) instead of three additions per pixel
+    unsigned mpos = 0u, mnz = 0u;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float raw = v[k];                                    // (an unused slot holds 0: it counts nothing)
+      const bool out = (raw < im.lo) || (raw > im.hi);           // calculateCoM's range test (a NaN stays)
+      const float x = out ? 0.f : raw;
+      if (!out && raw > 0.f) mpos |= 1u << k;
+      if (!out && raw != 0.f) mnz |= 1u << k;
+      acc = (k == 0) ? x : ((8 * k < full) ? __fadd_rn(acc, x) : acc);
+    }
+    const unsigned cnt = __popc(mpos);
+    const unsigned sumk = __popc(mpos & 0xAAAAu) + 2u * __popc(mpos & 0xCCCCu) + 4u * __popc(mpos & 0xF0F0u) +
+                          8u * __popc(mpos & 0xFF00u);
+    const int kw = (wb - c0 + 7) >> 3;                           // first pixel of this lane in the next row
+    const unsigned after = kw < 16 ? __popc(mpos >> kw) : 0u;
+    bpos += cnt;
+    bnz += __popc(mnz);
+    bsy += static_cast<unsigned>(r0) * cnt + after;
+    bsx += static_cast<unsigned>(c0) * cnt + 8u * sumk - static_cast<unsigned>(wb) * after;
+  } else {
+    int r = r0, c = c0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const bool on = 8 * k < full;
+      const float x = im.com_value(v[k]);
+      const bool p = on && x > 0.f;
+      bpos += p ? 1u : 0u; bsx += p ? static_cast<unsigned>(c) : 0u; bsy += p ? static_cast<unsigned>(r) : 0u;
+      bnz += (on && x != 0.f) ? 1u : 0u;
+      acc = (k == 0) ? x : (on ? __fadd_rn(acc, x) : acc);
+      c += 8;
+      if (c >= wb) { c -= wb; ++r; }
+    }
+  }
+  // ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7)): IEEE addition commutes, so every lane gets the same bits
+  acc = __fadd_rn(acc, __shfl_xor_sync(gmask, acc, 1));
+  acc = __fadd_rn(acc, __shfl_xor_sync(gmask, acc, 2));
+  acc = __fadd_rn(acc, __shfl_xor_sync(gmask, acc, 4));
+  tv = im.com_value(tv);
+  {
+    const bool p = j < tail && tv > 0.f;
+    bpos += p ? 1u : 0u; bsx += p ? static_cast<unsigned>(tc) : 0u; bsy += p ? static_cast<unsigned>(tr) : 0u;
+    bnz += (j < tail && tv != 0.f) ? 1u : 0u;
+  }
+  for (int i = 0; i < tail; ++i)                                  // one by one, in order (uniform over the group)
+    acc = __fadd_rn(acc, __shfl_sync(gmask, tv, (lane & 24) + i));
+  return acc;
+}
+
+// any block, pixel by pixel with a division each: images narrower than 8 pixels or shorter than 8 pixels in all
+// (degenerate windows); every lane of the group computes the same sum and the same counts, the caller keeps lane 0's
+struct ComSlowResult { float sum; unsigned pos, nz, sx, sy; };
+__device__ __noinline__ ComSlowResult com_block_sum_slow(ComImage im, unsigned off, int len) {
+  const int wb = im.wb;
+  ComSlowResult out = {0.f, 0u, 0u, 0u, 0u};
+  out.sum = np_block_sum([&](int i) {
+    const int e = static_cast<int>(off) + i, r = e / wb, c = e - r * wb;
+    const float v = im.com_value(im.crop_value(r, c));
+    if (v > 0.f) { ++out.pos; out.sx += static_cast<unsigned>(c); out.sy += static_cast<unsigned>(r); }
+    if (v != 0.f) ++out.nz;
+    return v;
+  }, len);
+  return out;
+}
+
+template <bool WINDOW>
+__global__ void __launch_bounds__(256)
+com_blocks_kernel(const float* __restrict__ frames, int H, int W, float frame_scale, float min_depth, float max_depth,
+                  const int* __restrict__ ip, const float* __restrict__ zp, float* __restrict__ heap, unsigned heap_cap,
+                  int leaves_log2, unsigned long long* __restrict__ stats) {
+  const int n = blockIdx.y;
+  ComImage im;
+  im.load(frames, n, H, W, frame_scale, min_depth, max_depth, WINDOW ? ip : nullptr, zp);
+  const long long npx64 = static_cast<long long>(im.wb) * im.hb;
+  if (npx64 < 1 || npx64 > 0x7fffffffLL) return;
+  const unsigned npx = static_cast<unsigned>(npx64);
+  const int depth = np_pairwise_depth32(npx);
+  if ((2ull << depth) > heap_cap) return;
+  float* vals = heap + static_cast<size_t>(n) * heap_cap;
+  const int lane = threadIdx.x & 31, j = lane & 7;
+  const unsigned gmask = 0xffu << (lane & 24);                    // the 8 lanes of this group
+  // group w of 2^L owns the blocks below the level-L node with path w: ~2^leaves_log2 consecutive blocks
+  // (np_host_worker_walk in devtools/np_reduce_host.cu is this loop on the host)
+  const int L = depth > leaves_log2 ? depth - leaves_log2 : 0;
+  const unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  unsigned bpos = 0, bnz = 0;                                     // per lane: < 2^31 pixels per image
+  unsigned long long sx = 0, sy = 0;
+  unsigned no, nl, nid;
+  if (w < (1u << L) && np_pairwise_worker_node(npx, L, w, &no, &nl, &nid)) {
+    int rb = static_cast<int>(no / static_cast<unsigned>(im.wb));      // row / column of the next block's first pixel
+    int cb = static_cast<int>(no - static_cast<unsigned>(rb) * static_cast<unsigned>(im.wb));
+    for (unsigned p = no; p < no + nl;) {
+      unsigned off; int len;
+      const unsigned id = np_pairwise_block_in(no, nl, nid, p, &off, &len);
+      unsigned bsx = 0, bsy = 0;                                  // a block holds at most 128 pixels: 32 bits are plenty
+      float res;
+      if (len >= 8 && im.wb >= 8) {
+        res = com_block_sum8<WINDOW>(im, off, rb, cb, len, lane, gmask, bpos, bnz, bsx, bsy);
+      } else {
+        const ComSlowResult sr = com_block_sum_slow(im, off, len);
+        res = sr.sum;
+        if (j == 0) { bpos += sr.pos; bnz += sr.nz; bsx = sr.sx; bsy = sr.sy; }
+      }
+      if (j == 0) vals[id] = res;
+      sx += bsx; sy += bsy;
+      p += static_cast<unsigned>(len);
+      cb += len;
+      while (cb >= im.wb) { cb -= im.wb; ++rb; }
+    }
+  }
+  unsigned long long pos = bpos, nz = bnz;
+  for (int o = 16; o > 0; o >>= 1) {
+    pos += __shfl_xor_sync(0xffffffffu, pos, o); nz += __shfl_xor_sync(0xffffffffu, nz, o);
+    sx += __shfl_xor_sync(0xffffffffu, sx, o);   sy += __shfl_xor_sync(0xffffffffu, sy, o);
+  }
+  if (lane == 0 && (pos | nz | sx | sy)) {
+    unsigned long long* st = stats + 4 * static_cast<size_t>(n);
+    atomicAdd(st, pos); atomicAdd(st + 1, nz); atomicAdd(st + 2, sx); atomicAdd(st + 3, sy);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+com_finish_kernel(const float* __restrict__ frames, int H, int W, float frame_scale, float min_depth, float max_depth,
+                  const int* __restrict__ ip, const float* __restrict__ zp, float* __restrict__ heap, unsigned heap_cap,
+                  const unsigned long long* __restrict__ stats, double* __restrict__ coms, int* __restrict__ overflow) {
   const int n = blockIdx.x;
   const int tid = threadIdx.x, T = blockDim.x;
   ComImage im;
-  im.frame = frames + static_cast<size_t>(n) * H * W;
-  im.scale = frame_scale; im.lo = min_depth; im.hi = max_depth; im.H = H; im.W = W;
-  int hb;
-  if (ip) {
-    const int* q = ip + 8 * n;
-    im.xstart = q[0]; im.ystart = q[1]; im.wb = q[2]; hb = q[3];
-    im.zs = zp[2 * n]; im.ze = zp[2 * n + 1]; im.clamp = true;
-  } else {
-    im.xstart = 0; im.ystart = 0; im.wb = W; hb = H; im.zs = 0.f; im.ze = 0.f; im.clamp = false;
-  }
-  const long long npx = static_cast<long long>(im.wb) * hb;
-  const int depth = np_pairwise_depth(npx);
-  if (npx < 1 || npx > 0x7fffffffLL || (2ull << depth) > heap_cap) {
+  im.load(frames, n, H, W, frame_scale, min_depth, max_depth, ip, zp);
+  long long npx; int depth;
+  if (!com_frame_fits(im, heap_cap, &npx, &depth)) {
     if (tid == 0) {
       coms[3 * n] = coms[3 * n + 1] = coms[3 * n + 2] = nan("");
       overflow[n] = 1;
     }
     return;
   }
-  if (tid < 4) s_stat[tid] = 0ull;
-  __syncthreads();
   float* vals = heap + static_cast<size_t>(n) * heap_cap;
-  unsigned long long pos = 0, nz = 0, sx = 0, sy = 0;
-  np_tree_blocks([&](long long i) {
-    unsigned r, c;
-    const float v = im.com_value(im.crop_value(static_cast<unsigned>(i), &r, &c));
-    if (v > 0.f) { ++pos; sx += c; sy += r; }
-    if (v != 0.f) ++nz;
-    return v;
-  }, npx, tid, T, vals);
-  // the integer statistics do not depend on the order of addition
-  for (int o = 16; o > 0; o >>= 1) {
-    pos += __shfl_xor_sync(0xffffffffu, pos, o); nz += __shfl_xor_sync(0xffffffffu, nz, o);
-    sx += __shfl_xor_sync(0xffffffffu, sx, o);   sy += __shfl_xor_sync(0xffffffffu, sy, o);
-  }
-  if ((tid & 31) == 0) {
-    atomicAdd(&s_stat[0], pos); atomicAdd(&s_stat[1], nz); atomicAdd(&s_stat[2], sx); atomicAdd(&s_stat[3], sy);
-  }
-  __syncthreads();
   for (int level = depth - 1; level >= 0; --level) {
     np_tree_level(npx, level, tid, T, vals);
     __syncthreads();
   }
   if (tid != 0) return;
   overflow[n] = 0;
-  const double cnt = static_cast<double>(s_stat[0]), num = static_cast<double>(s_stat[1]);
+  const unsigned long long* st = stats + 4 * static_cast<size_t>(n);
+  const double cnt = static_cast<double>(st[0]), num = static_cast<double>(st[1]);
   double c0 = 0., c1 = 0., c2 = 0.;
-  if (s_stat[1] != 0ull) {
+  if (st[1] != 0ull) {
     // cc = sums / count of the mask; com = (cc[1] * num, cc[0] * num, dc.sum()) / num, every step a rounded double op
-    c0 = __ddiv_rn(__dmul_rn(__ddiv_rn(static_cast<double>(s_stat[2]), cnt), num), num);
-    c1 = __ddiv_rn(__dmul_rn(__ddiv_rn(static_cast<double>(s_stat[3]), cnt), num), num);
+    c0 = __ddiv_rn(__dmul_rn(__ddiv_rn(static_cast<double>(st[2]), cnt), num), num);
+    c1 = __ddiv_rn(__dmul_rn(__ddiv_rn(static_cast<double>(st[3]), cnt), num), num);
     c2 = __ddiv_rn(static_cast<double>(vals[1]), num);
   }
-  if (ip) {
+  if (im.window) {
     if (fabs(c0) <= 1e-8 && fabs(c1) <= 1e-8 && fabs(c2) <= 1e-8) {          // numpy.allclose(com, 0.)
-      unsigned r, c;
-      c2 = static_cast<double>(im.crop_value(static_cast<unsigned>(hb / 2) * im.wb + im.wb / 2, &r, &c));
+      c2 = static_cast<double>(im.crop_value(im.hb / 2, im.wb / 2));
       if (fabs(c2) <= 1e-8) c2 = 300.;                                        // numpy.isclose(com[2], 0)
     }
     c0 = __dadd_rn(c0, static_cast<double>(im.xstart));

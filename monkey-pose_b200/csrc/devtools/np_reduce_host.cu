@@ -30,4 +30,27 @@ float np_host_tree_sum(const float* a, long long n, int T, long long* reads) {
 
 int np_host_depth(long long n) { return hgru::np_pairwise_depth(n); }
 
+// the kernel's work split: worker w of 2^L owns the subtree below the level-L node with path w; returns the number
+// of blocks visited, fails (-1) if a block is visited twice, skipped, out of order, or disagrees with the 64-bit walk
+long long np_host_worker_walk(long long n, int L) {
+  const unsigned npx = static_cast<unsigned>(n);
+  if (hgru::np_pairwise_depth32(npx) != hgru::np_pairwise_depth(n)) return -1;
+  long long visited = 0, covered = 0;
+  for (unsigned w = 0; w < (1u << L); ++w) {
+    unsigned no, nl, nid;
+    if (!hgru::np_pairwise_worker_node(npx, L, w, &no, &nl, &nid)) continue;
+    if (no != covered) return -1;                    // workers own consecutive slices
+    for (unsigned p = no; p < no + nl;) {
+      unsigned off; int len;
+      const unsigned id = hgru::np_pairwise_block_in(no, nl, nid, p, &off, &len);
+      long long off64; int len64;
+      if (hgru::np_pairwise_block_at(n, p, &off64, &len64) != id || off64 != off || len64 != len || off != p) return -1;
+      covered += len;
+      ++visited;
+      p += len;
+    }
+  }
+  return covered == n ? visited : -1;
+}
+
 }  // extern "C"

@@ -1267,9 +1267,10 @@ int crop_windows_forward(const float* tr, const double* com_in, double s0, doubl
 static unsigned com_heap_slots(long long max_pixels) {
   return 2u << hgru::np_pairwise_depth(max_pixels < 1 ? 1 : max_pixels);
 }
+// workspace: [N][4] uint64 statistics, then [N][heap slots] floats
 size_t calculate_com_workspace_bytes(int N, long long max_pixels) {
   if (N < 1 || max_pixels < 1 || max_pixels > 0x7fffffffLL) return 0;
-  return static_cast<size_t>(N) * com_heap_slots(max_pixels) * sizeof(float);
+  return static_cast<size_t>(N) * (4 * sizeof(unsigned long long) + com_heap_slots(max_pixels) * sizeof(float));
 }
 int calculate_com_forward(const float* frames, int N, int H, int W, float frame_scale, float min_depth, float max_depth,
                           const int* iparams, const float* zparams, long long max_pixels, void* ws, double* coms,
@@ -1277,14 +1278,30 @@ int calculate_com_forward(const float* frames, int N, int H, int W, float frame_
   if (!frames || !ws || !coms || !overflow) return fail(HGRU_E_INVALID, "calculate_com_forward: null pointer");
   if ((iparams == nullptr) != (zparams == nullptr))
     return fail(HGRU_E_INVALID, "calculate_com_forward: iparams and zparams go together");
-  if (N < 1 || H < 1 || W < 1) return fail(HGRU_E_INVALID, "calculate_com_forward: non-positive shape");
+  if (N < 1 || H < 1 || W < 1 || N > 65535) return fail(HGRU_E_INVALID, "calculate_com_forward: bad shape (1 <= N <= 65535)");
   if (max_pixels < 1 || max_pixels > 0x7fffffffLL)
     return fail(HGRU_E_INVALID, "calculate_com_forward: max_pixels must be in [1, 2^31)");
   if (!iparams && static_cast<long long>(H) * W > max_pixels)
     return fail(HGRU_E_INVALID, "calculate_com_forward: max_pixels is smaller than a frame");
-  hgru::calculate_com_kernel<<<N, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
-      frames, H, W, frame_scale, min_depth, max_depth, iparams, zparams, static_cast<float*>(ws),
-      com_heap_slots(max_pixels), coms, overflow);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  unsigned long long* stats = static_cast<unsigned long long*>(ws);
+  float* heap = reinterpret_cast<float*>(stats + 4 * static_cast<size_t>(N));
+  const unsigned slots = com_heap_slots(max_pixels);
+  CUDA_TRY(cudaMemsetAsync(stats, 0, 4 * sizeof(unsigned long long) * static_cast<size_t>(N), st));
+  // an 8-lane group per subtree of 2^leaves_log2 blocks (16 when the batch alone fills the GPU, 4 for a few frames);
+  // the grid covers the deepest tree the workspace allows, groups beyond a frame's own tree idle
+  const int leaves_log2 = N >= 32 ? 4 : 2;
+  const int max_depth_tree = hgru::np_pairwise_depth(iparams ? max_pixels : static_cast<long long>(H) * W);
+  const unsigned groups = 1u << (max_depth_tree > leaves_log2 ? max_depth_tree - leaves_log2 : 0);
+  const unsigned parts = (groups * 8u + 255u) / 256u;
+  if (iparams)
+    hgru::com_blocks_kernel<true><<<dim3(parts, N), 256, 0, st>>>(frames, H, W, frame_scale, min_depth, max_depth,
+                                                                 iparams, zparams, heap, slots, leaves_log2, stats);
+  else
+    hgru::com_blocks_kernel<false><<<dim3(parts, N), 256, 0, st>>>(frames, H, W, frame_scale, min_depth, max_depth,
+                                                                  iparams, zparams, heap, slots, leaves_log2, stats);
+  hgru::com_finish_kernel<<<N, 256, 0, st>>>(frames, H, W, frame_scale, min_depth, max_depth, iparams, zparams, heap,
+                                            slots, stats, coms, overflow);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

@@ -135,6 +135,50 @@ __host__ __device__ inline unsigned np_pairwise_block_at(long long n, long long 
   *off = o; *len = static_cast<int>(l);
   return id;
 }
+// the same walk in 32-bit unsigned arithmetic (n < 2^31): a shift and a mask per level instead of signed 64-bit
+// division -- the bandwidth-bound kernel calls it once per block
+__host__ __device__ inline unsigned np_pairwise_block_at32(unsigned n, unsigned p, unsigned* off, int* len) {
+  unsigned id = 1, o = 0, l = n;
+  while (l > static_cast<unsigned>(kNpBlock)) {
+    const unsigned n2 = (l >> 1) & ~7u;
+    if (p - o >= n2) { o += n2; l -= n2; id = 2 * id + 1; } else { l = n2; id = 2 * id; }
+  }
+  *off = o; *len = static_cast<int>(l);
+  return id;
+}
+__host__ __device__ inline int np_pairwise_depth32(unsigned n) {
+  int d = 0;
+  while (n > static_cast<unsigned>(kNpBlock)) { n -= (n >> 1) & ~7u; ++d; }
+  return d;
+}
+// Work split of the bandwidth-bound kernel: worker w of 2^L owns the subtree below the level-L node with path w (its
+// blocks are contiguous in memory, and finding the next one is a walk of a few levels, not of the whole tree).  A
+// block that sits ABOVE level L (ragged tree) goes to the worker whose remaining path bits are all zero.  False: this
+// worker owns nothing.
+__host__ __device__ inline bool np_pairwise_worker_node(unsigned n, int L, unsigned w, unsigned* off, unsigned* len,
+                                                        unsigned* id) {
+  unsigned o = 0, l = n, i = 1;
+  for (int b = L - 1; b >= 0; --b) {
+    if (l <= static_cast<unsigned>(kNpBlock)) {
+      if (w & ((2u << b) - 1u)) return false;
+      break;
+    }
+    const unsigned n2 = (l >> 1) & ~7u;
+    if ((w >> b) & 1u) { o += n2; l -= n2; i = 2 * i + 1; } else { l = n2; i = 2 * i; }
+  }
+  *off = o; *len = l; *id = i;
+  return true;
+}
+// the block that holds element p inside the node (o, l, id)
+__host__ __device__ inline unsigned np_pairwise_block_in(unsigned o, unsigned l, unsigned id, unsigned p, unsigned* off,
+                                                        int* len) {
+  while (l > static_cast<unsigned>(kNpBlock)) {
+    const unsigned n2 = (l >> 1) & ~7u;
+    if (p - o >= n2) { o += n2; l -= n2; id = 2 * id + 1; } else { l = n2; id = 2 * id; }
+  }
+  *off = o; *len = static_cast<int>(l);
+  return id;
+}
 __host__ __device__ inline bool np_pairwise_first_probe(long long off, long long p) {
   return (off + 63) / 64 * 64 == p;
 }

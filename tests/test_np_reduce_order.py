@@ -32,6 +32,8 @@ def host(tmp_path_factory):
     lib.np_host_tree_sum.argtypes = [fp, ctypes.c_longlong, ctypes.c_int, ctypes.POINTER(ctypes.c_longlong)]
     lib.np_host_depth.restype = ctypes.c_int
     lib.np_host_depth.argtypes = [ctypes.c_longlong]
+    lib.np_host_worker_walk.restype = ctypes.c_longlong
+    lib.np_host_worker_walk.argtypes = [ctypes.c_longlong, ctypes.c_int]
     return lib
 
 
@@ -94,3 +96,18 @@ def test_nanmean_matches_numpy(host):
         assert got == np.nanmean(np.ascontiguousarray(m[:, j]))
     allnan = np.full(4, np.nan, np.float32)
     assert np.isnan(host.np_host_nanmean(_ptr(allnan), 4, 1, 1))
+
+
+def test_worker_split_visits_every_block_once(host):
+    """The centre-of-mass kernel gives worker w of 2^L the subtree below the level-L node with path w (32-bit walk):
+    every block exactly once, in memory order, same blocks as the 64-bit walk -- also when L is deeper than parts of
+    the tree (blocks above level L) or than all of it."""
+    for n in SIZES + [2 ** 31 - 1, 128 * 2 ** 10, 128 * 2 ** 10 + 1, 129 * 2 ** 7 + 8]:
+        depth = host.np_host_depth(n)
+        for L in sorted({0, 1, max(depth - 4, 0), max(depth - 2, 0), depth, depth + 1, depth + 3}):
+            if L > 20:
+                continue
+            v = host.np_host_worker_walk(n, L)
+            assert v >= 1, (n, L)
+            if n > 128:
+                assert n / 128 <= v <= n / 64
