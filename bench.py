@@ -508,6 +508,21 @@ def neighbour_stages(a, m, torch, mp, init_mod):
         hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs")
     except Exception:
         pass
+    # the centre-of-mass estimate the crop stage falls back to without an attention output (calculateCoM on every
+    # frame, numpy's float32 summation order reproduced): one read of every frame, HBM-bound
+    try:
+        md.calculateCoM_batch(frames_dev, frame_scale=10000.0)
+        com_ms, _, _ = ev_time(lambda: md.calculateCoM_batch(frames_dev, frame_scale=10000.0), 10)
+        docom_ms, _, _ = ev_time(lambda: md.cropArea3D_batch_device(frames_dev, frame_scale=10000.0,
+                                                                    out_divisor=10000.0, docom=True), 5)
+        com_gbs = 4.0 * B * h * w / (com_ms * 1e-3) * 1e-9
+        com_stage = {"calculate_com_ms": com_ms, "algorithmic_bytes": 4.0 * B * h * w, "GB/s": com_gbs,
+                     "frac_of_hbm": (com_gbs / hbm) if hbm else None, "crop_with_estimated_and_refined_com_ms": docom_ms,
+                     "note": "calculate_com_forward (2 kernels + a 8 KB memset) on 424x512 frames resident in HBM; "
+                             "second figure: cropArea3D(com=None, docom=True) for the batch = CoM of the frame, "
+                             "window, CoM of the window, window, crop"}
+    except Exception as e:
+        com_stage = {"error": repr(e)}
     crop_gbs = crop_bytes / (crop_kernel_ms * 1e-3) * 1e-9
     return {"batch": B, "frame": [h, w],
             "crop": {"kernel_ms": crop_kernel_ms, "algorithmic_bytes": crop_bytes, "GB/s": crop_gbs,
@@ -518,6 +533,7 @@ def neighbour_stages(a, m, torch, mp, init_mod):
                              "prepare_data_test = host window arithmetic (comToBounds) + parameter upload + "
                              "kernel; api_device_windows_ms: the same with the centres of mass as a CUDA tensor "
                              "(crop_windows_forward + crop_area3d_forward, no host round trip); frames resident in HBM"},
+            "com_estimate": com_stage,
             "post": {"gpu_ms": post_gpu_ms, "wall_ms": post_wall_ms,
                      "note": "x600 + CoM, xyz->uvd, mean joint error; 23 joints per frame, latency-bound"},
             "attention_cnn": {"gpu_ms": attn_gpu_ms, "frames_per_s": B / (attn_gpu_ms * 1e-3),

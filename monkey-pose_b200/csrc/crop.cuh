@@ -292,7 +292,7 @@ __device__ __noinline__ ComSlowResult com_block_sum_slow(ComImage im, unsigned o
 }
 
 template <bool WINDOW>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, WINDOW ? 2 : 4)
 com_blocks_kernel(const float* __restrict__ frames, int H, int W, float frame_scale, float min_depth, float max_depth,
                   const int* __restrict__ ip, const float* __restrict__ zp, float* __restrict__ heap, unsigned heap_cap,
                   int leaves_log2, unsigned long long* __restrict__ stats) {
