@@ -129,13 +129,15 @@ crop_windows_kernel(const float* __restrict__ tr, const double* __restrict__ com
 //   the window overlaps it, zeros elsewhere, z-clamped -- and the result gets cropArea3D's `docom` treatment
 //   (:318-326): if the CoM is all zero take the window's centre pixel as depth (300 if that is zero too), then add
 //   (xstart, ystart).
-// Two launches.  com_blocks_kernel is the HBM-bound one: grid (parts, N); a group of 8 lanes owns one block of numpy's
-// tree at a time (lane j = numpy's accumulator r[j], so a warp reads four 32-byte runs per load and every byte of a
-// frame exactly once), writes the block's sum to heap[n][heap index] and adds its integer statistics (counts, row and
-// column sums of the mask: order-free) to stats[n].  com_finish_kernel (one CTA per frame) combines the heap level by
-// level and does the few double operations of the reference in its order.
-// heap [N][heap_cap] floats, stats [N][4] uint64 (zeroed by the caller); a frame whose image needs a bigger heap
-// (window larger than the caller's bound) gets a NaN centre of mass and overflow[n] = 1.
+// Two launches.  com_blocks_kernel is the HBM-bound one: grid (parts, N); a group of 8 lanes owns a subtree of numpy's
+// tree (2^leaves_log2 consecutive blocks below a level-L node) and sums it one block at a time (lane j = numpy's
+// accumulator r[j], so a warp reads four 32-byte runs per load and every byte of a frame exactly once), folding the block
+// sums into the node's sum as they come; it writes that to heap[n][heap index of the node] and adds its integer
+// statistics (counts, row and column sums of the mask: order-free) to stats[n].  com_finish_kernel (one CTA per frame)
+// combines the top L levels in shared memory and does the few double operations of the reference in its order.
+// heap [N][heap_cap] floats (heap_cap = 2^(L+1) for the largest image allowed), stats [N][4] uint64 (zeroed by the
+// caller); a frame whose image needs a bigger heap (window larger than the caller's bound) gets a NaN centre of mass
+// and overflow[n] = 1.
 struct ComImage {
   const float* frame;
   float scale, zs, ze, lo, hi;
@@ -177,13 +179,6 @@ struct ComImage {
     return v;
   }
 };
-
-__device__ __forceinline__ bool com_frame_fits(const ComImage& im, unsigned heap_cap, long long* npx, int* depth) {
-  *npx = static_cast<long long>(im.wb) * im.hb;
-  if (*npx < 1 || *npx > 0x7fffffffLL) return false;
-  *depth = np_pairwise_depth(*npx);
-  return (2ull << *depth) <= heap_cap;
-}
 
 // One block of numpy's tree (8 <= len <= 128 pixels starting at pixel `off`) by a group of 8 lanes; lane j is numpy's
 // accumulator r[j].  Straight-line, predicated code: the lane's (up to) 16 pixels and its tail pixel are requested
@@ -303,13 +298,13 @@ com_blocks_kernel(const float* __restrict__ frames, int H, int W, float frame_sc
   if (npx64 < 1 || npx64 > 0x7fffffffLL) return;
   const unsigned npx = static_cast<unsigned>(npx64);
   const int depth = np_pairwise_depth32(npx);
-  if ((2ull << depth) > heap_cap) return;
+  const int L = depth > leaves_log2 ? depth - leaves_log2 : 0;
+  if ((2ull << L) > heap_cap) return;
   float* vals = heap + static_cast<size_t>(n) * heap_cap;
   const int lane = threadIdx.x & 31, j = lane & 7;
   const unsigned gmask = 0xffu << (lane & 24);                    // the 8 lanes of this group
-  // group w of 2^L owns the blocks below the level-L node with path w: ~2^leaves_log2 consecutive blocks
-  // (np_host_worker_walk in devtools/np_reduce_host.cu is this loop on the host)
-  const int L = depth > leaves_log2 ? depth - leaves_log2 : 0;
+  // group w of 2^L owns the blocks below the level-L node with path w: ~2^leaves_log2 consecutive blocks, folded into
+  // the node's sum as they come (np_host_worker_sum in devtools/np_reduce_host.cu is this loop on the host)
   const unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
   unsigned bpos = 0, bnz = 0;                                     // per lane: < 2^31 pixels per image
   unsigned long long sx = 0, sy = 0;
@@ -317,9 +312,11 @@ com_blocks_kernel(const float* __restrict__ frames, int H, int W, float frame_sc
   if (w < (1u << L) && np_pairwise_worker_node(npx, L, w, &no, &nl, &nid)) {
     int rb = static_cast<int>(no / static_cast<unsigned>(im.wb));      // row / column of the next block's first pixel
     int cb = static_cast<int>(no - static_cast<unsigned>(rb) * static_cast<unsigned>(im.wb));
+    NpSubtreeSum node;
+    node.init();
     for (unsigned p = no; p < no + nl;) {
-      unsigned off; int len;
-      const unsigned id = np_pairwise_block_in(no, nl, nid, p, &off, &len);
+      unsigned off; int len, steps;
+      np_pairwise_block_in(no, nl, nid, p, &off, &len, &steps);
       unsigned bsx = 0, bsy = 0;                                  // a block holds at most 128 pixels: 32 bits are plenty
       float res;
       if (len >= 8 && im.wb >= 8) {
@@ -329,12 +326,13 @@ com_blocks_kernel(const float* __restrict__ frames, int H, int W, float frame_sc
         res = sr.sum;
         if (j == 0) { bpos += sr.pos; bnz += sr.nz; bsx = sr.sx; bsy = sr.sy; }
       }
-      if (j == 0) vals[id] = res;
+      node.push(res, steps);                                      // (every lane of the group holds the same bits)
       sx += bsx; sy += bsy;
       p += static_cast<unsigned>(len);
       cb += len;
       while (cb >= im.wb) { cb -= im.wb; ++rb; }
     }
+    if (j == 0) vals[nid] = node.total();
   }
   unsigned long long pos = bpos, nz = bnz;
   for (int o = 16; o > 0; o >>= 1) {
@@ -347,25 +345,39 @@ com_blocks_kernel(const float* __restrict__ frames, int H, int W, float frame_sc
   }
 }
 
+// One CTA per frame: the sums of the level-L nodes (and of blocks above that level) -> the top L levels of numpy's
+// tree, level by level in shared memory (2^(L+1) floats of dynamic shared memory), then the reference's few double
+// operations in its order.
 __global__ void __launch_bounds__(256)
 com_finish_kernel(const float* __restrict__ frames, int H, int W, float frame_scale, float min_depth, float max_depth,
-                  const int* __restrict__ ip, const float* __restrict__ zp, float* __restrict__ heap, unsigned heap_cap,
-                  const unsigned long long* __restrict__ stats, double* __restrict__ coms, int* __restrict__ overflow) {
+                  const int* __restrict__ ip, const float* __restrict__ zp, const float* __restrict__ heap,
+                  unsigned heap_cap, int leaves_log2, const unsigned long long* __restrict__ stats,
+                  double* __restrict__ coms, int* __restrict__ overflow) {
+  extern __shared__ float s_vals[];
   const int n = blockIdx.x;
   const int tid = threadIdx.x, T = blockDim.x;
   ComImage im;
   im.load(frames, n, H, W, frame_scale, min_depth, max_depth, ip, zp);
-  long long npx; int depth;
-  if (!com_frame_fits(im, heap_cap, &npx, &depth)) {
+  const long long npx = static_cast<long long>(im.wb) * im.hb;
+  const int depth = (npx >= 1 && npx <= 0x7fffffffLL) ? np_pairwise_depth32(static_cast<unsigned>(npx)) : 0;
+  const int L = depth > leaves_log2 ? depth - leaves_log2 : 0;
+  if (npx < 1 || npx > 0x7fffffffLL || (2ull << L) > heap_cap) {
     if (tid == 0) {
       coms[3 * n] = coms[3 * n + 1] = coms[3 * n + 2] = nan("");
       overflow[n] = 1;
     }
     return;
   }
-  float* vals = heap + static_cast<size_t>(n) * heap_cap;
-  for (int level = depth - 1; level >= 0; --level) {
-    np_tree_level(npx, level, tid, T, vals);
+  const float* vals = heap + static_cast<size_t>(n) * heap_cap;
+  // what the workers wrote: nodes of level L, and blocks that sit above it
+  for (unsigned id = 1u + tid; id < (2u << L); id += T) {
+    long long off, len;
+    const bool level_L = (id >> L) != 0u;
+    if (np_pairwise_node(npx, id, &off, &len) && (level_L || len <= kNpBlock)) s_vals[id] = vals[id];
+  }
+  __syncthreads();
+  for (int level = L - 1; level >= 0; --level) {
+    np_tree_level(npx, level, tid, T, s_vals);
     __syncthreads();
   }
   if (tid != 0) return;
@@ -377,7 +389,7 @@ com_finish_kernel(const float* __restrict__ frames, int H, int W, float frame_sc
     // cc = sums / count of the mask; com = (cc[1] * num, cc[0] * num, dc.sum()) / num, every step a rounded double op
     c0 = __ddiv_rn(__dmul_rn(__ddiv_rn(static_cast<double>(st[2]), cnt), num), num);
     c1 = __ddiv_rn(__dmul_rn(__ddiv_rn(static_cast<double>(st[3]), cnt), num), num);
-    c2 = __ddiv_rn(static_cast<double>(vals[1]), num);
+    c2 = __ddiv_rn(static_cast<double>(s_vals[1]), num);
   }
   if (im.window) {
     if (fabs(c0) <= 1e-8 && fabs(c1) <= 1e-8 && fabs(c2) <= 1e-8) {          // numpy.allclose(com, 0.)

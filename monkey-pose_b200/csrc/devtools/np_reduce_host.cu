@@ -30,27 +30,43 @@ float np_host_tree_sum(const float* a, long long n, int T, long long* reads) {
 
 int np_host_depth(long long n) { return hgru::np_pairwise_depth(n); }
 
-// the kernel's work split: worker w of 2^L owns the subtree below the level-L node with path w; returns the number
-// of blocks visited, fails (-1) if a block is visited twice, skipped, out of order, or disagrees with the 64-bit walk
-long long np_host_worker_walk(long long n, int L) {
+// the kernel's work split: worker w of 2^L owns the subtree below the level-L node with path w, sums its blocks
+// (np_block_sum) and folds them into the subtree's sum as they come (NpSubtreeSum); the top L levels are then combined
+// by heap index.  Returns the total; *visited = blocks seen, -1 if a block is visited twice, skipped, out of order, or
+// disagrees with the 64-bit walk.
+float np_host_worker_sum(const float* a, long long n, int L, long long* visited_out) {
   const unsigned npx = static_cast<unsigned>(n);
-  if (hgru::np_pairwise_depth32(npx) != hgru::np_pairwise_depth(n)) return -1;
   long long visited = 0, covered = 0;
+  bool ok = hgru::np_pairwise_depth32(npx) == hgru::np_pairwise_depth(n);
+  std::vector<float> vals(static_cast<size_t>(2) << L, -12345.f);
   for (unsigned w = 0; w < (1u << L); ++w) {
     unsigned no, nl, nid;
     if (!hgru::np_pairwise_worker_node(npx, L, w, &no, &nl, &nid)) continue;
-    if (no != covered) return -1;                    // workers own consecutive slices
+    if (no != covered) ok = false;                   // workers own consecutive slices
+    hgru::NpSubtreeSum st;
+    st.init();
     for (unsigned p = no; p < no + nl;) {
-      unsigned off; int len;
-      const unsigned id = hgru::np_pairwise_block_in(no, nl, nid, p, &off, &len);
+      unsigned off; int len, steps;
+      const unsigned id = hgru::np_pairwise_block_in(no, nl, nid, p, &off, &len, &steps);
       long long off64; int len64;
-      if (hgru::np_pairwise_block_at(n, p, &off64, &len64) != id || off64 != off || len64 != len || off != p) return -1;
+      if (hgru::np_pairwise_block_at(n, p, &off64, &len64) != id || off64 != off || len64 != len || off != p) ok = false;
+      st.push(hgru::np_block_sum([&](int i) { return a[off + i]; }, len), steps);
       covered += len;
       ++visited;
       p += len;
     }
+    if (st.n != 1) ok = false;
+    vals[nid] = st.total();
   }
-  return covered == n ? visited : -1;
+  for (int level = L - 1; level >= 0; --level) {
+    for (unsigned id = 1u << level; id < (2u << level); ++id) {
+      long long off, len;
+      // inner nodes above the workers' level: both children were written (by a worker, or by this loop)
+      if (hgru::np_pairwise_node(n, id, &off, &len) && len > hgru::kNpBlock) vals[id] = vals[2 * id] + vals[2 * id + 1];
+    }
+  }
+  if (visited_out) *visited_out = (ok && covered == n) ? visited : -1;
+  return vals[1];
 }
 
 }  // extern "C"

@@ -1263,14 +1263,22 @@ int crop_windows_forward(const float* tr, const double* com_in, double s0, doubl
   return 0;
 }
 
-// heap slots per frame for images of up to max_pixels pixels: 2^(depth of numpy's pairwise tree + 1)
-static unsigned com_heap_slots(long long max_pixels) {
-  return 2u << hgru::np_pairwise_depth(max_pixels < 1 ? 1 : max_pixels);
+// An 8-lane group sums a subtree of 2^leaves_log2 blocks of numpy's pairwise tree (16 when the batch alone fills the
+// GPU, 4 for a few frames); only the subtree sums reach the workspace: 2^(L + 1) heap slots per frame, L = the level
+// of those subtrees in the tree of the largest image allowed.
+// (deeper trees than 12 + that: bigger subtrees, so that the top levels always fit 32 KB of shared memory)
+static int com_leaves_log2(int N, long long max_pixels) {
+  const int d = hgru::np_pairwise_depth(max_pixels < 1 ? 1 : max_pixels);
+  return std::max(N >= 32 ? 4 : 2, d - 12);
+}
+static int com_top_levels(int N, long long max_pixels, long long pixels) {
+  const int d = hgru::np_pairwise_depth(pixels < 1 ? 1 : pixels), l = com_leaves_log2(N, max_pixels);
+  return d > l ? d - l : 0;
 }
 // workspace: [N][4] uint64 statistics, then [N][heap slots] floats
 size_t calculate_com_workspace_bytes(int N, long long max_pixels) {
   if (N < 1 || max_pixels < 1 || max_pixels > 0x7fffffffLL) return 0;
-  return static_cast<size_t>(N) * (4 * sizeof(unsigned long long) + com_heap_slots(max_pixels) * sizeof(float));
+  return static_cast<size_t>(N) * (4 * sizeof(unsigned long long) + (2u << com_top_levels(N, max_pixels, max_pixels)) * sizeof(float));
 }
 int calculate_com_forward(const float* frames, int N, int H, int W, float frame_scale, float min_depth, float max_depth,
                           const int* iparams, const float* zparams, long long max_pixels, void* ws, double* coms,
@@ -1286,22 +1294,23 @@ int calculate_com_forward(const float* frames, int N, int H, int W, float frame_
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   unsigned long long* stats = static_cast<unsigned long long*>(ws);
   float* heap = reinterpret_cast<float*>(stats + 4 * static_cast<size_t>(N));
-  const unsigned slots = com_heap_slots(max_pixels);
+  const int leaves_log2 = com_leaves_log2(N, max_pixels);
+  const int top = com_top_levels(N, max_pixels, max_pixels);
+  const unsigned slots = 2u << top;                               // <= 8192: 32 KB of shared memory in the second kernel
   CUDA_TRY(cudaMemsetAsync(stats, 0, 4 * sizeof(unsigned long long) * static_cast<size_t>(N), st));
-  // an 8-lane group per subtree of 2^leaves_log2 blocks (16 when the batch alone fills the GPU, 4 for a few frames);
-  // the grid covers the deepest tree the workspace allows, groups beyond a frame's own tree idle
-  const int leaves_log2 = N >= 32 ? 4 : 2;
-  const int max_depth_tree = hgru::np_pairwise_depth(iparams ? max_pixels : static_cast<long long>(H) * W);
-  const unsigned groups = 1u << (max_depth_tree > leaves_log2 ? max_depth_tree - leaves_log2 : 0);
-  const unsigned parts = (groups * 8u + 255u) / 256u;
+  // the grid covers the deepest tree the workspace allows (whole frames: the frame's own); groups beyond a frame's
+  // own tree idle
+  const int grid_levels = iparams ? top : com_top_levels(N, max_pixels, static_cast<long long>(H) * W);
+  const unsigned parts = ((1u << grid_levels) * 8u + 255u) / 256u;
   if (iparams)
     hgru::com_blocks_kernel<true><<<dim3(parts, N), 256, 0, st>>>(frames, H, W, frame_scale, min_depth, max_depth,
                                                                  iparams, zparams, heap, slots, leaves_log2, stats);
   else
     hgru::com_blocks_kernel<false><<<dim3(parts, N), 256, 0, st>>>(frames, H, W, frame_scale, min_depth, max_depth,
                                                                   iparams, zparams, heap, slots, leaves_log2, stats);
-  hgru::com_finish_kernel<<<N, 256, 0, st>>>(frames, H, W, frame_scale, min_depth, max_depth, iparams, zparams, heap,
-                                            slots, stats, coms, overflow);
+  hgru::com_finish_kernel<<<N, 256, slots * sizeof(float), st>>>(frames, H, W, frame_scale, min_depth, max_depth,
+                                                                iparams, zparams, heap, slots, leaves_log2, stats, coms,
+                                                                overflow);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

@@ -169,16 +169,36 @@ __host__ __device__ inline bool np_pairwise_worker_node(unsigned n, int L, unsig
   *off = o; *len = l; *id = i;
   return true;
 }
-// the block that holds element p inside the node (o, l, id)
+// the block that holds element p inside the node (o, l, id); *steps = its depth below that node
 __host__ __device__ inline unsigned np_pairwise_block_in(unsigned o, unsigned l, unsigned id, unsigned p, unsigned* off,
-                                                        int* len) {
+                                                        int* len, int* steps) {
+  int d = 0;
   while (l > static_cast<unsigned>(kNpBlock)) {
     const unsigned n2 = (l >> 1) & ~7u;
     if (p - o >= n2) { o += n2; l -= n2; id = 2 * id + 1; } else { l = n2; id = 2 * id; }
+    ++d;
   }
-  *off = o; *len = static_cast<int>(l);
+  *off = o; *len = static_cast<int>(l); *steps = d;
   return id;
 }
+// A worker's block sums arrive in memory order = left to right in its subtree: two neighbours of equal depth are the
+// two children of one node, so they are added on the spot and the sum moves one level up.  After the last block the
+// stack holds the subtree's sum -- numpy's additions, in numpy's order, without storing the blocks.
+struct NpSubtreeSum {
+  float v[34];                 // a tree of 2^31 elements is 25 levels deep
+  int d[34];
+  int n;
+  __host__ __device__ void init() { n = 0; }
+  __host__ __device__ void push(float x, int depth) {
+    v[n] = x; d[n] = depth; ++n;
+    while (n >= 2 && d[n - 1] == d[n - 2]) {
+      v[n - 2] = HGRU_NP_ADD(v[n - 2], v[n - 1]);
+      --d[n - 2];
+      --n;
+    }
+  }
+  __host__ __device__ float total() const { return v[0]; }      // valid once every block of the subtree is in
+};
 __host__ __device__ inline bool np_pairwise_first_probe(long long off, long long p) {
   return (off + 63) / 64 * 64 == p;
 }

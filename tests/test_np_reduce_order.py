@@ -32,8 +32,8 @@ def host(tmp_path_factory):
     lib.np_host_tree_sum.argtypes = [fp, ctypes.c_longlong, ctypes.c_int, ctypes.POINTER(ctypes.c_longlong)]
     lib.np_host_depth.restype = ctypes.c_int
     lib.np_host_depth.argtypes = [ctypes.c_longlong]
-    lib.np_host_worker_walk.restype = ctypes.c_longlong
-    lib.np_host_worker_walk.argtypes = [ctypes.c_longlong, ctypes.c_int]
+    lib.np_host_worker_sum.restype = ctypes.c_float
+    lib.np_host_worker_sum.argtypes = [fp, ctypes.c_longlong, ctypes.c_int, ctypes.POINTER(ctypes.c_longlong)]
     return lib
 
 
@@ -98,16 +98,20 @@ def test_nanmean_matches_numpy(host):
     assert np.isnan(host.np_host_nanmean(_ptr(allnan), 4, 1, 1))
 
 
-def test_worker_split_visits_every_block_once(host):
-    """The centre-of-mass kernel gives worker w of 2^L the subtree below the level-L node with path w (32-bit walk):
-    every block exactly once, in memory order, same blocks as the 64-bit walk -- also when L is deeper than parts of
-    the tree (blocks above level L) or than all of it."""
-    for n in SIZES + [2 ** 31 - 1, 128 * 2 ** 10, 128 * 2 ** 10 + 1, 129 * 2 ** 7 + 8]:
+def test_worker_split_sums_like_numpy(host):
+    """The centre-of-mass kernel gives worker w of 2^L the subtree below the level-L node with path w (32-bit walk),
+    folds the block sums into the subtree's sum as they come and combines the top L levels by heap index: every block
+    exactly once, in memory order, same blocks as the 64-bit walk, and the total is numpy's -- also when L is deeper
+    than parts of the tree (blocks above level L) or than all of it."""
+    rng = np.random.default_rng(3)
+    for n in SIZES + [128 * 2 ** 10, 128 * 2 ** 10 + 1, 129 * 2 ** 7 + 8, 1460 * 1461]:
+        a = (rng.uniform(0, 3000, n) * (rng.uniform(size=n) < 0.7)).astype(np.float32)
+        want = a.sum()
         depth = host.np_host_depth(n)
         for L in sorted({0, 1, max(depth - 4, 0), max(depth - 2, 0), depth, depth + 1, depth + 3}):
-            if L > 20:
-                continue
-            v = host.np_host_worker_walk(n, L)
-            assert v >= 1, (n, L)
+            visited = ctypes.c_longlong(0)
+            got = np.float32(host.np_host_worker_sum(_ptr(a), n, L, ctypes.byref(visited)))
+            assert visited.value >= 1, (n, L)
+            assert got == want, (n, L)
             if n > 128:
-                assert n / 128 <= v <= n / 64
+                assert n / 128 <= visited.value <= n / 64
