@@ -183,8 +183,10 @@ struct ComImage {
 // One block of numpy's tree (8 <= len <= 128 pixels starting at pixel `off`) by a group of 8 lanes; lane j is numpy's
 // accumulator r[j].  Straight-line, predicated code: the lane's (up to) 16 pixels and its tail pixel are requested
 // first, all loads in flight together, then added in numpy's order.  WINDOW: the image is a crop window (bounds test,
-// z clamp), else the frame itself (pixel index = address).  Needs an image at least 8 pixels wide.
-template <bool WINDOW>
+// z clamp), else the frame itself (pixel index = address).  POSLO: the near plane is positive (always, in the
+// reference's use), which makes "in range" and "in the mask" the same test.  Needs an image at least 8 pixels wide and
+// a block of at least 64 pixels (every block of an image of more than 128): the lane's first eight pixels always exist.
+template <bool WINDOW, bool POSLO>
 __device__ __forceinline__ float com_block_sum8(const ComImage& im, unsigned off, int rb, int cb, int len, int lane,
                                                 unsigned gmask, unsigned& bpos, unsigned& bnz, unsigned& bsx,
                                                 unsigned& bsy) {
@@ -213,13 +215,47 @@ __device__ __forceinline__ float com_block_sum8(const ComImage& im, unsigned off
     int r = r0, c = c0;
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-      v[k] = fetch(e0 + 8 * k, r, c, 8 * k < full);
+      v[k] = fetch(e0 + 8 * k, r, c, k < 8 || 8 * k < full);
       c += 8;
       if (c >= wb) { c -= wb; ++r; }
     }
   }
   float acc = 0.f;
-  if (wb >= 128) {
+  if (POSLO && wb >= 128) {
+    // lo > 0: a pixel that passes the range test is positive, hence in the mask and non-zero -- one test, one mask.
+    // Unused slots hold +0, fail the test and add +0 to a sum that is never -0 (its terms are +0, positive or NaN):
+    // no predicates.  Only a NaN pixel breaks the rule (numpy's comparisons are false for it, so it stays in the
+    // image: non-zero, but not > 0); it also turns the sum NaN, which is the cue to redo both masks exactly.
+    unsigned mpos = 0u;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float raw = v[k];
+      const bool out = (raw < im.lo) || (raw > im.hi);
+      const float x = out ? 0.f : raw;
+      if (!out) mpos |= 1u << k;
+      acc = (k == 0) ? x : __fadd_rn(acc, x);
+    }
+    unsigned mnz = mpos;
+    if (acc != acc) {
+      mpos = 0u; mnz = 0u;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const float raw = v[k];
+        const bool out = (raw < im.lo) || (raw > im.hi);
+        if (!out && raw > 0.f) mpos |= 1u << k;
+        if (!out && raw != 0.f) mnz |= 1u << k;
+      }
+    }
+    const unsigned cnt = __popc(mpos);
+    const unsigned sumk = __popc(mpos & 0xAAAAu) + 2u * __popc(mpos & 0xCCCCu) + 4u * __popc(mpos & 0xF0F0u) +
+                          8u * __popc(mpos & 0xFF00u);
+    const int kw = (wb - c0 + 7) >> 3;                           // first pixel of this lane in the next row
+    const unsigned after = kw < 16 ? __popc(mpos >> kw) : 0u;
+    bpos += cnt;
+    bnz += __popc(mnz);
+    bsy += static_cast<unsigned>(r0) * cnt + after;
+    bsx += static_cast<unsigned>(c0) * cnt + 8u * sumk - static_cast<unsigned>(wb) * after;
+  } else if (wb >= 128) {
     // at most one row change inside the block: the mask's row / column sums follow from two 16-bit masks
     // (bit k = pixel k of this lane is in the mask / is non-zero) instead of three additions per pixel
     unsigned mpos = 0u, mnz = 0u;
@@ -270,7 +306,7 @@ __device__ __forceinline__ float com_block_sum8(const ComImage& im, unsigned off
   return acc;
 }
 
-// any block, pixel by pixel with a division each: images narrower than 8 pixels or shorter than 8 pixels in all
+// any block, pixel by pixel with a division each: images narrower than 8 pixels or of at most 128 pixels in all
 // (degenerate windows); every lane of the group computes the same sum and the same counts, the caller keeps lane 0's
 struct ComSlowResult { float sum; unsigned pos, nz, sx, sy; };
 __device__ __noinline__ ComSlowResult com_block_sum_slow(ComImage im, unsigned off, int len) {
@@ -286,7 +322,7 @@ __device__ __noinline__ ComSlowResult com_block_sum_slow(ComImage im, unsigned o
   return out;
 }
 
-template <bool WINDOW>
+template <bool WINDOW, bool POSLO>
 __global__ void __launch_bounds__(256, WINDOW ? 2 : 4)
 com_blocks_kernel(const float* __restrict__ frames, int H, int W, float frame_scale, float min_depth, float max_depth,
                   const int* __restrict__ ip, const float* __restrict__ zp, float* __restrict__ heap, unsigned heap_cap,
@@ -319,8 +355,8 @@ com_blocks_kernel(const float* __restrict__ frames, int H, int W, float frame_sc
       np_pairwise_block_in(no, nl, nid, p, &off, &len, &steps);
       unsigned bsx = 0, bsy = 0;                                  // a block holds at most 128 pixels: 32 bits are plenty
       float res;
-      if (len >= 8 && im.wb >= 8) {
-        res = com_block_sum8<WINDOW>(im, off, rb, cb, len, lane, gmask, bpos, bnz, bsx, bsy);
+      if (len >= 64 && im.wb >= 8) {
+        res = com_block_sum8<WINDOW, POSLO>(im, off, rb, cb, len, lane, gmask, bpos, bnz, bsx, bsy);
       } else {
         const ComSlowResult sr = com_block_sum_slow(im, off, len);
         res = sr.sum;

@@ -1302,12 +1302,13 @@ int calculate_com_forward(const float* frames, int N, int H, int W, float frame_
   // own tree idle
   const int grid_levels = iparams ? top : com_top_levels(N, max_pixels, static_cast<long long>(H) * W);
   const unsigned parts = ((1u << grid_levels) * 8u + 255u) / 256u;
-  if (iparams)
-    hgru::com_blocks_kernel<true><<<dim3(parts, N), 256, 0, st>>>(frames, H, W, frame_scale, min_depth, max_depth,
-                                                                 iparams, zparams, heap, slots, leaves_log2, stats);
-  else
-    hgru::com_blocks_kernel<false><<<dim3(parts, N), 256, 0, st>>>(frames, H, W, frame_scale, min_depth, max_depth,
-                                                                  iparams, zparams, heap, slots, leaves_log2, stats);
+  const dim3 grid(parts, N);
+#define HGRU_COM_BLOCKS(WIN, POS)                                                                                   \
+  hgru::com_blocks_kernel<WIN, POS><<<grid, 256, 0, st>>>(frames, H, W, frame_scale, min_depth, max_depth, iparams, \
+                                                          zparams, heap, slots, leaves_log2, stats)
+  if (iparams) { if (min_depth > 0.f) HGRU_COM_BLOCKS(true, true); else HGRU_COM_BLOCKS(true, false); }
+  else         { if (min_depth > 0.f) HGRU_COM_BLOCKS(false, true); else HGRU_COM_BLOCKS(false, false); }
+#undef HGRU_COM_BLOCKS
   hgru::com_finish_kernel<<<N, 256, slots * sizeof(float), st>>>(frames, H, W, frame_scale, min_depth, max_depth,
                                                                 iparams, zparams, heap, slots, leaves_log2, stats, coms,
                                                                 overflow);

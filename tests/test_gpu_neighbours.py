@@ -176,3 +176,25 @@ def test_centre_of_mass_at_batch_size_vs_oracle():
             assert np.array_equal(c[i].cpu().numpy(), wc), (n, h, w, i)
             assert np.array_equal(p[i].cpu().numpy(), wp), (n, h, w, i)
             np.testing.assert_allclose(Ms[i].cpu().numpy(), wM, rtol=0, atol=1e-12)
+
+
+def test_centre_of_mass_nan_pixels_and_non_positive_near_plane():
+    """The kernel's fast path assumes a positive near plane and NaN-free blocks and falls back otherwise: a NaN pixel
+    (stays in the image: counted as non-zero, not in the mask, the depth sum turns NaN) and a detector whose near plane
+    is 0 or negative (zeros and negative depths then pass the range test) give the oracle's values."""
+    from monkey_pose_b200 import tf_monkeydetector as tmd
+    from oracle import crop_oracle_np as crop
+    rng = np.random.default_rng(21)
+    base = np.round(rng.uniform(-50, 11000, size=(4, 200, 333))).astype(np.float32)
+    base[rng.uniform(size=base.shape) < 0.1] = 0.0
+    base[1, 57, 100] = np.nan
+    base[3, 0, 0] = np.nan
+    base[3, 199, 332] = -0.0
+    for d1 in (200, 0, -10):
+        md = tmd.tfMonkeyDetector(365.456, 365.456, 256, 212, [800, 800, 1200], d1, 10000)
+        got = md.calculateCoM_batch(_dev(base)).cpu().numpy()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            want = np.stack([crop.calculate_com(base[i], d1, 10000) for i in range(4)])
+        assert np.array_equal(got, want, equal_nan=True), d1
+        assert np.isnan(got[1, 2]) and np.isfinite(got[1, :2]).all() and np.isfinite(got[0]).all()
