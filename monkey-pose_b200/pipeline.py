@@ -8,6 +8,10 @@ host round trip between the stages, and with the upload of the frames overlapped
       --> window arithmetic + crop (device) --> pose network (fused tensor-core forward) --> absolute joints (device)
       --D2H--> xyz, uvd [N,23,3]
 
+Without an attention network (`attn=None`) the centres come from the detector itself, as `cropArea3D` does when
+none is given (tf_monkeydetector.py:303-308: `calculateCoM` of each frame, optionally refined on the first crop,
+`docom`, :316-333) -- also on the device.
+
 Everything numerical runs in libhgru_b200.so; this module only orders the calls on two CUDA streams.  No CPU fallback.
 """
 import torch
@@ -16,13 +20,16 @@ from .tf_monkeydetector import prepare_data_test, preprocess_real_depth
 
 
 class FramesToJoints(object):
-    """attn: `attn_model_struct`, pose: `model` (parameters loaded), md: `tfMonkeyDetector`, config: an object with
+    """attn: `attn_model_struct` (or None: centres of mass estimated from the frames by the detector, refined on the
+    first crop when `docom`), pose: `model` (parameters loaded), md: `tfMonkeyDetector`, config: an object with
     `image_orig_size`, `image_target_size`, `image_max_depth` (the reference's `monkeyConfig`), cube_z: seqconfig
     ['cube'][2] (mm).  `chunks`: pieces the upload is cut into (the attention CNN starts on piece c while piece c+1 is
     on the bus); 1 = plain stream order."""
 
-    def __init__(self, attn, pose, md, config, cube_z=1200.0, num_joints=23, chunks=4, near=1000, far=3000):
+    def __init__(self, attn, pose, md, config, cube_z=1200.0, num_joints=23, chunks=4, near=1000, far=3000,
+                 docom=False):
         self.attn, self.pose, self.md, self.config = attn, pose, md, config
+        self.docom = bool(docom)
         self.scale = float(cube_z) / 2.0
         self.out_dims = 3 * int(num_joints)
         self.chunks = int(chunks)
@@ -77,9 +84,17 @@ class FramesToJoints(object):
                 if raw16:
                     preprocess_real_depth(self._raw_dev[lo:hi], self.near, self.far,
                                           max_depth=self.config.image_max_depth, out=dev_frames[lo:hi])
-            self._tr[lo:hi] = self.attn.build(dev_frames[lo:hi], 3)                  # train_cnn_networks_hgru.py:281-283
-        tr = self._tr if centres is None else centres
-        patches, coms, _ = prepare_data_test(dev_frames, tr, self.md, self.config)   # :284 (window arithmetic on device)
+            if self.attn is not None:
+                self._tr[lo:hi] = self.attn.build(dev_frames[lo:hi], 3)              # train_cnn_networks_hgru.py:281-283
+        if self.attn is None and centres is None:
+            # no attention output: the detector's own estimate (tf_monkeydetector.py:303-308, 316-333)
+            ts, md_ = self.config.image_target_size, self.config.image_max_depth
+            patches, _, coms = self.md.cropArea3D_batch_device(dev_frames, dsize=(ts[1], ts[0]), frame_scale=md_,
+                                                               out_divisor=md_, docom=self.docom)
+            patches = patches[..., None]
+        else:
+            tr = self._tr if centres is None else centres
+            patches, coms, _ = prepare_data_test(dev_frames, tr, self.md, self.config)   # :284 (windows on the device)
         out = self.pose.build(patches, self.out_dims)                                # :291-294
         xyz, uvd = self.md.getAbsoluteCoordinates_batch(out, coms, self.scale)       # :295-298
         xyz_h = torch.empty(xyz.shape, dtype=torch.float32, pin_memory=True)

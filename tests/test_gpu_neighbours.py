@@ -198,3 +198,34 @@ def test_centre_of_mass_nan_pixels_and_non_positive_near_plane():
             want = np.stack([crop.calculate_com(base[i], d1, 10000) for i in range(4)])
         assert np.array_equal(got, want, equal_nan=True), d1
         assert np.isnan(got[1, 2]) and np.isfinite(got[1, :2]).all() and np.isfinite(got[0]).all()
+
+
+def test_frames_to_joints_without_attention_network_uses_the_detector_estimate():
+    """FramesToJoints(attn=None): centres of mass from calculateCoM (+ docom) on the device; equals the stage-by-stage
+    sequence bit for bit, from pinned host frames (chunked upload) and from device frames."""
+    import monkey_pose_b200 as mp
+    from monkey_pose_b200 import initialization as init
+    from tests.golden.make_golden_com import MAX_DEPTH, frame_sets
+
+    class Cfg(object):
+        image_orig_size = [424, 512, 1]
+        image_target_size = [128, 128, 1]
+        image_max_depth = MAX_DEPTH
+
+    z = np.load(os.path.join(GOLDEN, "crop_ref.npz"))
+    frames = np.concatenate([frame_sets(z["frames"])["far"]] * 4)[:16]          # 16 frames: 4 upload pieces of 4
+    md = _detector()
+    m = mp.model()
+    m.channels, m.timesteps, m.fc_hidden, m.hidden_state = 25, 2, 64, None
+    m.aux["hidden_init"] = "zeros"
+    m.load_params(init.pose_params(channels=25, S=15, T=2, hw=64, fc_hidden=64, out=69, seed=3))
+    for docom in (False, True):
+        pipe = mp.FramesToJoints(None, m, md, Cfg(), cube_z=1200.0, chunks=4, docom=docom)
+        xyz, uvd = pipe(torch.as_tensor(frames).pin_memory())
+        F = _dev(frames)
+        patches, _, coms = md.cropArea3D_batch_device(F, frame_scale=MAX_DEPTH, out_divisor=MAX_DEPTH, docom=docom)
+        want_xyz, want_uvd = md.getAbsoluteCoordinates_batch(m.build(patches[..., None], 69), coms, 600.0)
+        assert torch.equal(xyz, want_xyz.cpu()) and torch.equal(uvd, want_uvd.cpu())
+        xyz2, uvd2 = pipe(F)
+        assert torch.equal(xyz2, xyz) and torch.equal(uvd2, uvd)
+        assert torch.isfinite(xyz).all()
