@@ -149,6 +149,24 @@ HGRU_API int pose_plan_sm_clock_ghz(pose_plan_t plan, float* ghz_mean, float* gh
  * ------------------------------------------------------------------------------------------ */
 HGRU_API int layer_conv2d_forward(const float* x_dev, int N, int H, int W, int Cin, const float* filters_dev, int S,
                                   int Cout, const float* biases_dev, int relu, float* out_dev, void* stream);
+/* The circuit's per-timestep building blocks as stand-alone exact-fp32 ops, for callers that compose `full()`
+ * (hgru_module.py:825-857) themselves through ContextualCircuit.circuit_input / circuit_output / input_integration /
+ * output_integration; hgru_forward never runs them (it runs the fused tensor-core pipeline).  Tensors [rows][k]
+ * channels-last (rows = n*h*w); the 15x15 convolution between them is layer_conv2d_forward with lateral_bias as bias.
+ *   circuit_gate_forward: gate = sigmoid(x *1x1 w + b) (:696-707, 729-740; w [k][k] in x out); gated (nullable) = x . gate
+ *     (:709-711).
+ *   circuit_input_integration_forward: I = tanh(xi X - (beta . O + nu) . P) (:795-804).
+ *   circuit_output_integration_forward: O' = G . O + (1 - G) . tanh(kappa . (zeta I + gamma . P) + omega . (zeta I .
+ *     gamma . P)) (:806-823), times *rho_dev when given (full()'s `O * rho[i0]`, :847-849). */
+HGRU_API int circuit_gate_forward(const float* x_dev, size_t rows, int k, const float* w_dev, const float* b_dev,
+                                  float* gate_dev, float* gated_dev, void* stream);
+HGRU_API int circuit_input_integration_forward(const float* X_dev, const float* O_dev, const float* P_dev,
+                                               const float* beta_dev, const float* nu_dev, float xi, size_t rows, int k,
+                                               float* I_dev, void* stream);
+HGRU_API int circuit_output_integration_forward(const float* I_dev, const float* P_dev, const float* O_dev,
+                                                const float* G_dev, const float* gamma_dev, const float* kappa_dev,
+                                                const float* omega_dev, float zeta, const float* rho_dev, size_t rows,
+                                                int k, float* O_out_dev, void* stream);
 HGRU_API int layer_max_pool2x2_forward(const float* x_dev, int N, int H, int W, int C, float* out_dev, void* stream);
 HGRU_API int layer_fc_forward(const float* x_dev, int M, int K, const float* weights_dev, const float* biases_dev,
                               int F, float* out_dev, void* stream);

@@ -63,6 +63,10 @@ SIGNATURES = {
     "pose_plan_kernel_times": (_I, [_P, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_I)]),
     "pose_plan_sm_clock_ghz": (_I, [_P, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
     "layer_conv2d_forward": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _P, _I, _P, _P]),
+    "circuit_gate_forward": (_I, [_P, ctypes.c_size_t, _I, _P, _P, _P, _P, _P]),
+    "circuit_input_integration_forward": (_I, [_P, _P, _P, _P, _P, ctypes.c_float, ctypes.c_size_t, _I, _P, _P]),
+    "circuit_output_integration_forward": (_I, [_P, _P, _P, _P, _P, _P, _P, ctypes.c_float, _P, ctypes.c_size_t, _I,
+                                                _P, _P]),
     "layer_max_pool2x2_forward": (_I, [_P, _I, _I, _I, _I, _P, _P]),
     "layer_fc_forward": (_I, [_P, _I, _I, _P, _P, _I, _P, _P]),
     "layer_resize_bilinear_forward": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),

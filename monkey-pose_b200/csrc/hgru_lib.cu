@@ -1387,6 +1387,35 @@ int layer_conv2d_forward(const float* x, int N, int H, int W, int Cin, const flo
   return 0;
 }
 
+int circuit_gate_forward(const float* x, size_t rows, int k, const float* w, const float* b, float* gate, float* gated,
+                         void* stream) {
+  if (!x || !w || !b || !gate) return fail(HGRU_E_INVALID, "circuit_gate_forward: null pointer");
+  if (rows < 1 || k < 1) return fail(HGRU_E_INVALID, "circuit_gate_forward: non-positive shape");
+  hgru::circuit_gate_kernel<<<nblk(rows * k), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, w, b, gate, gated, rows, k);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+int circuit_input_integration_forward(const float* X, const float* O, const float* P, const float* beta,
+                                      const float* nu, float xi, size_t rows, int k, float* I, void* stream) {
+  if (!X || !O || !P || !beta || !nu || !I) return fail(HGRU_E_INVALID, "circuit_input_integration_forward: null pointer");
+  if (rows < 1 || k < 1) return fail(HGRU_E_INVALID, "circuit_input_integration_forward: non-positive shape");
+  hgru::circuit_input_integration_kernel<<<nblk(rows * k), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      X, O, P, beta, nu, xi, rows * k, k, I);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+int circuit_output_integration_forward(const float* I, const float* P, const float* O, const float* G,
+                                       const float* gamma, const float* kappa, const float* omega, float zeta,
+                                       const float* rho, size_t rows, int k, float* O_out, void* stream) {
+  if (!I || !P || !O || !G || !gamma || !kappa || !omega || !O_out)
+    return fail(HGRU_E_INVALID, "circuit_output_integration_forward: null pointer");
+  if (rows < 1 || k < 1) return fail(HGRU_E_INVALID, "circuit_output_integration_forward: non-positive shape");
+  hgru::circuit_output_integration_kernel<<<nblk(rows * k), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      I, P, O, G, gamma, kappa, omega, zeta, rho, rows * k, k, O_out);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 int layer_max_pool2x2_forward(const float* x, int N, int H, int W, int C, float* out, void* stream) {
   if (!x || !out) return fail(HGRU_E_INVALID, "layer_max_pool2x2_forward: null pointer");
   if (N < 1 || H < 1 || W < 1 || C < 1) return fail(HGRU_E_INVALID, "layer_max_pool2x2_forward: non-positive shape");

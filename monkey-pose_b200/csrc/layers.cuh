@@ -175,4 +175,54 @@ bn_inference_kernel(const float* __restrict__ x, float* __restrict__ y, size_t t
   y[i] = (v - __ldg(mean + c)) * sc + __ldg(beta + c);
 }
 
+// ---- the circuit's per-timestep building blocks (hgru_module.py:692-823) as stand-alone exact-fp32 ops -------------
+// What a caller composing `full()` by hand gets (ContextualCircuit.circuit_input / circuit_output / input_integration /
+// output_integration / full); `build()` never runs them -- it runs the fused tensor-core pipeline.  Tensors are
+// [rows][k] channels-last (rows = n*h*w); the 15x15 convolution between them is conv2d_direct_kernel.
+
+// gate = sigmoid(x *1x1 w + b) (:696-707, 729-740); gated = x . gate when asked for (:709-711).  One thread per
+// (row, output channel).
+__global__ void __launch_bounds__(256)
+circuit_gate_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                    float* __restrict__ gate, float* __restrict__ gated, size_t rows, int k) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= rows * k) return;
+  const int co = static_cast<int>(i % k);
+  const float* xr = x + (i / k) * k;
+  float acc = 0.f;
+  for (int ci = 0; ci < k; ++ci) acc = fmaf(__ldg(xr + ci), __ldg(w + static_cast<size_t>(ci) * k + co), acc);
+  const float g = 1.f / (1.f + expf(-(acc + __ldg(b + co))));
+  gate[i] = g;
+  if (gated) gated[i] = xr[co] * g;
+}
+
+// I = tanh(xi * X - (beta . O + nu) . P) (:795-804, gru_gates: no mixing with the old I)
+__global__ void __launch_bounds__(256)
+circuit_input_integration_kernel(const float* __restrict__ X, const float* __restrict__ O, const float* __restrict__ P,
+                                 const float* __restrict__ beta, const float* __restrict__ nu, float xi, size_t total,
+                                 int k, float* __restrict__ I) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int c = static_cast<int>(i % k);
+  I[i] = tanhf(xi * X[i] - (__ldg(beta + c) * O[i] + __ldg(nu + c)) * P[i]);
+}
+
+// O' = G . O + (1 - G) . tanh(kappa . (zeta I + gamma . P) + omega . (zeta I . gamma . P)) (:806-823), times *rho when a
+// pointer is given (the `O * rho[i0]` of full(), :847-849)
+__global__ void __launch_bounds__(256)
+circuit_output_integration_kernel(const float* __restrict__ I, const float* __restrict__ P, const float* __restrict__ O,
+                                  const float* __restrict__ G, const float* __restrict__ gamma,
+                                  const float* __restrict__ kappa, const float* __restrict__ omega, float zeta,
+                                  const float* __restrict__ rho, size_t total, int k, float* __restrict__ out) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int c = static_cast<int>(i % k);
+  const float zi = zeta * I[i];
+  const float e = __ldg(gamma + c) * P[i];
+  const float s = tanhf(__ldg(kappa + c) * (zi + e) + __ldg(omega + c) * (zi * e));
+  const float g = G[i];
+  const float o = g * O[i] + (1.f - g) * s;
+  out[i] = rho ? o * __ldg(rho) : o;
+}
+
 }  // namespace hgru

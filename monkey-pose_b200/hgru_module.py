@@ -287,6 +287,154 @@ class ContextualCircuit(object):
                     weights['%s_%s' % (k, wk)] = self[wv[wak]]
         return weights
 
+    # -- the per-timestep methods (hgru_module.py:505-861) -----------------------------------------------------------
+    # Stand-alone, exact fp32, unfused: what a caller stepping the circuit by hand gets (call prepare_tensors() first,
+    # as the reference's build() does).  build() itself runs the fused tensor-core pipeline, never these.
+    def _rows(self, t):
+        if not (torch.is_tensor(t) and t.is_cuda and t.dim() == 4 and int(t.shape[3]) == self.k):
+            raise RuntimeError("expected a [n,h,w,%d] torch CUDA tensor (no CPU fallback)" % self.k)
+        t = t.to(torch.float32).contiguous()
+        return t, int(t.shape[0]) * int(t.shape[1]) * int(t.shape[2])
+
+    def _conv2d(self, data, weights, bias):
+        """Stride-1 SAME cross-correlation + bias (None: zeros) through the stand-alone exact conv kernel."""
+        w_shape = [int(w) for w in weights.shape]
+        data = data.to(torch.float32).contiguous()
+        weights = _as_dev(weights).contiguous()
+        n, h, w = [int(v) for v in data.shape[:3]]
+        out = torch.empty((n, h, w, w_shape[3]), device=data.device, dtype=torch.float32)
+        if bias is None:
+            bias = torch.zeros(w_shape[3], device=data.device, dtype=torch.float32)
+        _lib.check(_lib.load().layer_conv2d_forward(
+            data.data_ptr(), n, h, w, w_shape[2], weights.data_ptr(), w_shape[0], w_shape[3],
+            bias.contiguous().data_ptr(), 0, out.data_ptr(), _stream()), "layer_conv2d_forward")
+        return out
+
+    def conv_2d_op(self, data, weight_key, out_key=None, weights=None, symmetric_weights=False, rectify=None):
+        """2D convolutions, return or assign activity as attribute (hgru_module.py:505-581).  `symmetric_weights` only
+        changes the gradient in the reference (:521-535); the forward is a plain stride-1 SAME cross-correlation."""
+        if weights is None:
+            weights = self[weight_key]
+        if rectify is not None:
+            weights = rectify(weights, 0)
+        w_shape = [int(w) for w in weights.shape]
+        if len(w_shape) > 1 and int(w_shape[-2]) > 1:
+            if self.atrous_convolutions:
+                raise NotImplementedError('atrous_convolutions (not on the path hgru_pose.py configures)')
+            if len(w_shape) != 4 or w_shape[0] != w_shape[1] or w_shape[0] % 2 == 0:
+                raise NotImplementedError('conv_2d_op: square odd HWIO filters only')
+            if not (torch.is_tensor(data) and data.is_cuda and data.dim() == 4 and int(data.shape[3]) == w_shape[2]):
+                raise RuntimeError("data must be a [n,h,w,%d] torch CUDA tensor (no CPU fallback)" % w_shape[2])
+            activities = self._conv2d(data, weights, None)
+        elif len(w_shape) > 1 and int(w_shape[-2]) == 1:
+            raise NotImplementedError('separable spatial convolutions (hgru_module.py:549-570) are not on the hot path')
+        else:
+            raise RuntimeError                                          # hgru_module.py:571-572
+        if out_key is None:
+            return activities
+        setattr(self, out_key, activities)
+
+    def p_convolution(self, data, key, rectification):
+        """Apply the eCRF association field convolution (hgru_module.py:615-624)."""
+        p_weights = self[key]
+        if self.rectify_weights == True:  # noqa: E712 (the reference's own test)
+            p_weights = rectification(p_weights, 0)
+        return self.conv_2d_op(data=data, weight_key=key, weights=p_weights, symmetric_weights=self.symmetric_weights)
+
+    def process_p(self, data, key, rectification, full=True):
+        """Wrapper for eCRF operations: the association-field convolution + lateral_bias (hgru_module.py:626-658)."""
+        if not full:
+            raise NotImplementedError('1x1 tuning convolutions (association_field=False) are not on the hot path')
+        if isinstance(self.p_shape[0], list):
+            raise NotImplementedError('hierarchical_convolutions are not on the hot path')
+        if self.rectify_weights == True:  # noqa: E712
+            return self.p_convolution(data=data, key=key, rectification=rectification) + self.lateral_bias
+        # p_convolution (:615-624) with `+ lateral_bias` (:657) as the convolution kernel's bias: same rounding, one pass
+        if not (torch.is_tensor(data) and data.is_cuda and data.dim() == 4 and int(data.shape[3]) == self.k):
+            raise RuntimeError("data must be a [n,h,w,%d] torch CUDA tensor (no CPU fallback)" % self.k)
+        return self._conv2d(data, self[key], self.lateral_bias.reshape(-1))
+
+    def _gate(self, x, wkey, bkey, gated):
+        x, rows = self._rows(x)
+        g = torch.empty_like(x)
+        xg = torch.empty_like(x) if gated else None
+        _lib.check(_lib.load().circuit_gate_forward(
+            x.data_ptr(), rows, self.k, self[wkey].data_ptr(), self[bkey].data_ptr(), g.data_ptr(),
+            xg.data_ptr() if gated else None, _stream()), "circuit_gate_forward")
+        return g, xg
+
+    def circuit_input(self, O):
+        """Circuit input operates on recurrent output (O): (P, I_update) (hgru_module.py:692-724).  The gate is
+        applied to a copy, as in the reference's graph (the caller's O is unchanged)."""
+        if self.train and self.dropout is not None:
+            raise NotImplementedError
+        I_update, gated = self._gate(O, self.weight_dict['I']['r']['weight'], self.weight_dict['I']['r']['bias'],
+                                     bool(self.gru_gates))
+        P = self.process_p(data=gated if self.gru_gates else O, key=self.weight_dict['P']['r']['weight'],
+                           rectification=None, full=self.association_field)
+        if self.rectify_weights == False:  # noqa: E712
+            P = torch.clamp(P, max=0)
+        return P, I_update
+
+    def circuit_output(self, I):
+        """Circuit output operates on recurrent input (I): (P, O_update) (hgru_module.py:726-756)."""
+        if self.train and self.dropout is not None:
+            raise NotImplementedError
+        O_update, gated = self._gate(I, self.weight_dict['O']['r']['weight'], self.weight_dict['O']['r']['bias'],
+                                     bool(self.output_gru_gates))
+        P = self.process_p(data=gated if self.output_gru_gates else I, key=self.weight_dict['P']['r']['weight'],
+                           rectification=None, full=self.association_field)
+        if self.rectify_weights == False:  # noqa: E712
+            P = torch.clamp(P, min=0)
+        return P, O_update
+
+    def input_integration(self, P, I, O, I_update):
+        """Integration on the input: tanh(xi X - (beta O + nu) P) (hgru_module.py:795-804)."""
+        if not self.gru_gates:
+            raise NotImplementedError('gru_gates=False (not on the path hgru_pose.py configures)')
+        P, rows = self._rows(P)
+        O, _ = self._rows(O)
+        out = torch.empty_like(P)
+        _lib.check(_lib.load().circuit_input_integration_forward(
+            self.X.data_ptr(), O.data_ptr(), P.data_ptr(), self.beta.data_ptr(), self.nu.data_ptr(), float(self.xi),
+            rows, self.k, out.data_ptr(), _stream()), "circuit_input_integration_forward")
+        return out
+
+    def output_integration(self, P, I, O, O_update, _rho=None):
+        """Integration on the output (hgru_module.py:806-823): multiplicative excitation, mixed with the old O by the
+        output gate."""
+        if not self.multiplicative_excitation or self.output_gru_gates:
+            raise NotImplementedError('additive gating / output_gru_gates (not on the path hgru_pose.py configures)')
+        P, rows = self._rows(P)
+        I, _ = self._rows(I)
+        O, _ = self._rows(O)
+        G, _ = self._rows(O_update)
+        out = torch.empty_like(P)
+        _lib.check(_lib.load().circuit_output_integration_forward(
+            I.data_ptr(), P.data_ptr(), O.data_ptr(), G.data_ptr(), self.gamma.data_ptr(), self.kappa.data_ptr(),
+            self.omega.data_ptr(), float(self.zeta), _rho.data_ptr() if _rho is not None else None, rows, self.k,
+            out.data_ptr(), _stream()), "circuit_output_integration_forward")
+        return out
+
+    def full(self, i0, O, I, store_O=None, store_I=None):
+        """Contextual circuit body: one timestep (hgru_module.py:825-857).  Returns (i0 + 1, O, I, store_I, store_O)."""
+        P, I_update = self.circuit_input(O)
+        I = getattr(self, self.ii)(P=P, I=I, O=O, I_update=I_update)
+        P, O_update = self.circuit_output(I)
+        if self.adapation:
+            rho_i = self.rho.reshape(-1)[int(i0):int(i0) + 1]          # tf.gather(self.rho, i0): O * rho[i0] (:847-849)
+            O = getattr(self, self.oi)(P=P, I=I, O=O, O_update=O_update, _rho=rho_i)
+        else:
+            O = getattr(self, self.oi)(P=P, I=I, O=O, O_update=O_update)
+        if self.store_states:
+            raise NotImplementedError('store_states (use build(trace=True))')
+        i0 += 1
+        return i0, O, I, store_I, store_O
+
+    def condition(self, i0, O, I, store_I, store_O):
+        """While loop halting condition (hgru_module.py:859-861)."""
+        return i0 < self.timesteps
+
     # -- forward -----------------------------------------------------------------------------
     def _initial_state(self):
         if self._hidden_state is not None:

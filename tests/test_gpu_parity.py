@@ -549,3 +549,45 @@ def test_streamed_forward_equals_batch_by_batch_build(mode):
     for g, w in zip(got[:3], want[:3]):
         assert torch.equal(g, w)
     assert torch.equal(got[3], m.build(batches[3][:2].contiguous().pin_memory(), 69))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", HGRU_FILES, ids=[os.path.basename(p) for p in HGRU_FILES])
+def test_stepping_the_circuit_by_hand_matches_reference_golden(path):
+    """The reference's per-timestep methods (circuit_input, input_integration, circuit_output, output_integration,
+    full, condition; hgru_module.py:692-861) as stand-alone exact-fp32 ops: driving `full()` in a Python loop
+    reproduces the reference-produced H1 / H2 of every timestep, and the fused `build()` of the same circuit."""
+    z = np.load(path)
+    T, S = int(z["T"]), int(z["S"])
+    if z["X"].shape[3] > 32 and z["X"].shape[1] * z["X"].shape[2] > 1024:
+        pytest.skip("direct 15x15 convolution at 64 channels: covered by the smaller fixtures")
+    params = {n: z["var:contextual_circuit/" + n] for n in onp.HGRU_PARAM_NAMES}
+    cc = mp.ContextualCircuit(X=torch.as_tensor(z["X"]).cuda(), timesteps=T, SRF=1, SSN=S, SSF=S, aux=POSE_AUX,
+                              params=params, hidden_state=z["O0"], compute_mode="fp32")
+    cc.prepare_tensors()
+    O = torch.as_tensor(z["O0"]).cuda()
+    I = torch.zeros_like(O)
+    i0, store_I, store_O = 0, None, None
+    while cc.condition(i0, O, I, store_I, store_O):
+        O_before = O.clone()
+        t = i0
+        i0, O, I, store_I, store_O = cc.full(i0, O, I, store_O, store_I)
+        assert onp.rel_err(I.cpu().numpy(), z["I_steps"][:, t])[0] < 1e-5, t
+        assert onp.rel_err(O.cpu().numpy(), z["O_steps"][:, t])[0] < 1e-5, t
+        assert torch.equal(O_before, O_before.clone()) and O.data_ptr() != O_before.data_ptr()
+    assert i0 == T
+    assert onp.rel_err(O.cpu().numpy(), z["O_final"])[0] < 1e-5
+    fused, _, _ = cc.build()
+    assert onp.rel_err(O.cpu().numpy(), fused.cpu().numpy())[0] < 1e-5
+    # the pieces on their own: the gate leaves its input alone, conv_2d_op is the plain cross-correlation
+    O0 = torch.as_tensor(z["O0"]).cuda()
+    keep = O0.clone()
+    P, G1 = cc.circuit_input(O0)
+    assert torch.equal(O0, keep)
+    ref_P = onp.conv2d_same(z["O0"].astype(np.float64) * G1.cpu().numpy().astype(np.float64),
+                            params["p_r"].astype(np.float64)) + params["lateral_bias"].astype(np.float64)
+    assert onp.rel_err(P.cpu().numpy(), ref_P)[0] < 1e-5
+    plain = cc.conv_2d_op(data=O0, weight_key="p_r")
+    assert onp.rel_err((plain + cc.lateral_bias).cpu().numpy(), cc.process_p(O0, "p_r", None).cpu().numpy())[0] < 1e-6
+    cc.conv_2d_op(data=O0, weight_key="i_r", out_key="I_r")
+    assert tuple(cc.I_r.shape) == tuple(O0.shape)

@@ -1,5 +1,7 @@
 """CPU: host-side mirror of the reference interface -- option handling, error behaviour, parameter
 shapes, sharding arithmetic.  (No kernels run here.)"""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -154,3 +156,36 @@ def test_product_build_defines_no_development_switch():
             for name in re.findall(r"#\s*define\s+(HGRU_(?:DBG|STACK)_\w+)", src):
                 assert name == "HGRU_STACK_EPI", (fn, name)      # (a local helper macro, not a switch)
     assert {"HGRU_STACK_NO_REM", "HGRU_STACK_NGRP4", "HGRU_DBG_NO_GLOBAL"} <= switches
+
+
+def test_circuit_step_methods_mirror_the_reference_signatures():
+    """ContextualCircuit exposes the reference's per-timestep methods (hgru_module.py:505-861) with the same argument
+    names and order; they need CUDA tensors (no CPU fallback)."""
+    import inspect
+    import re
+    src = open("/root/reference/hgru_module.py").read() if os.path.exists("/root/reference/hgru_module.py") else None
+    want = {
+        "conv_2d_op": ["self", "data", "weight_key", "out_key", "weights", "symmetric_weights", "rectify"],
+        "p_convolution": ["self", "data", "key", "rectification"],
+        "process_p": ["self", "data", "key", "rectification", "full"],
+        "circuit_input": ["self", "O"],
+        "circuit_output": ["self", "I"],
+        "input_integration": ["self", "P", "I", "O", "I_update"],
+        "output_integration": ["self", "P", "I", "O", "O_update"],
+        "full": ["self", "i0", "O", "I", "store_O", "store_I"],
+        "condition": ["self", "i0", "O", "I", "store_I", "store_O"],
+    }
+    for name, args in want.items():
+        got = [a for a in inspect.signature(getattr(mp.ContextualCircuit, name)).parameters if not a.startswith("_")]
+        assert got == args, (name, got)
+        if src is not None:                      # this container only: the table above IS the reference's
+            m = re.search(r"def %s\(([^)]*)\)" % name, src)
+            ref = [a.split("=")[0].strip() for a in m.group(1).replace("\n", " ").split(",") if a.strip()]
+            assert ref == args, (name, ref)
+    cc = mp.ContextualCircuit(X=torch.zeros(1, 8, 8, 4), timesteps=2, SRF=1, SSN=15, SSF=15, aux=mp.model().aux)
+    assert cc.condition(0, None, None, None, None) and not cc.condition(2, None, None, None, None)
+    with pytest.raises(RuntimeError):
+        cc.k = 4
+        cc.lateral_bias = torch.zeros(1, 1, 1, 4)
+        cc.p_r = torch.zeros(15, 15, 4, 4)
+        cc.process_p(torch.zeros(1, 8, 8, 4), "p_r", None)          # host tensor: fails loudly
