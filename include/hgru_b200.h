@@ -168,6 +168,15 @@ HGRU_API int circuit_output_integration_forward(const float* I_dev, const float*
                                                 const float* omega_dev, float zeta, const float* rho_dev, size_t rows,
                                                 int k, float* O_out_dev, void* stream);
 HGRU_API int layer_max_pool2x2_forward(const float* x_dev, int N, int H, int W, int C, float* out_dev, void* stream);
+/* The model's remaining pooling / normalisation helpers (hgru_pose.py:120-132; declared by the reference, not called
+ * by its build()): tf.nn.max_pool / avg_pool with ksize = stride = ksize, SAME (max_pool_4: ksize 4; avg_pool: ksize 2,
+ * average = 1; padding is left out of an average's count) -> out [N][ceil(H/k)][ceil(W/k)][C]; and `batchnorm` =
+ * tf.nn.moments over axis 0 + tf.nn.batch_normalization without scale / offset: x [N][inner] -> (x - mean_n) *
+ * rsqrt(var_n + epsilon) per inner index. */
+HGRU_API int layer_pool_same_forward(const float* x_dev, int N, int H, int W, int C, int ksize, int average,
+                                     float* out_dev, void* stream);
+HGRU_API int layer_batchnorm_moments0_forward(const float* x_dev, int N, size_t inner, float epsilon, float* out_dev,
+                                              void* stream);
 HGRU_API int layer_fc_forward(const float* x_dev, int M, int K, const float* weights_dev, const float* biases_dev,
                               int F, float* out_dev, void* stream);
 /* tf.image.resize_images(x, [OH, OW]) of the attention CNN (train_cnn_networks_hgru.py:442): TF 1.x bilinear,

@@ -68,6 +68,8 @@ SIGNATURES = {
     "circuit_output_integration_forward": (_I, [_P, _P, _P, _P, _P, _P, _P, ctypes.c_float, _P, ctypes.c_size_t, _I,
                                                 _P, _P]),
     "layer_max_pool2x2_forward": (_I, [_P, _I, _I, _I, _I, _P, _P]),
+    "layer_pool_same_forward": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "layer_batchnorm_moments0_forward": (_I, [_P, _I, ctypes.c_size_t, ctypes.c_float, _P, _P]),
     "layer_fc_forward": (_I, [_P, _I, _I, _P, _P, _I, _P, _P]),
     "layer_resize_bilinear_forward": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
     "layer_batch_norm_forward": (_I, [_P, ctypes.c_size_t, _I, _P, _P, _P, _P, ctypes.c_float, _I, _I, ctypes.c_float,

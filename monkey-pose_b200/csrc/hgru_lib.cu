@@ -1425,6 +1425,25 @@ int layer_max_pool2x2_forward(const float* x, int N, int H, int W, int C, float*
   return 0;
 }
 
+int layer_pool_same_forward(const float* x, int N, int H, int W, int C, int ksize, int average, float* out,
+                            void* stream) {
+  if (!x || !out) return fail(HGRU_E_INVALID, "layer_pool_same_forward: null pointer");
+  if (N < 1 || H < 1 || W < 1 || C < 1 || ksize < 1) return fail(HGRU_E_INVALID, "layer_pool_same_forward: non-positive shape");
+  const size_t total = static_cast<size_t>(N) * ((H + ksize - 1) / ksize) * ((W + ksize - 1) / ksize) * C;
+  hgru::pool_same_kernel<<<nblk(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, out, N, H, W, C, ksize,
+                                                                                     average ? 1 : 0);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int layer_batchnorm_moments0_forward(const float* x, int N, size_t inner, float epsilon, float* out, void* stream) {
+  if (!x || !out) return fail(HGRU_E_INVALID, "layer_batchnorm_moments0_forward: null pointer");
+  if (N < 1 || inner < 1) return fail(HGRU_E_INVALID, "layer_batchnorm_moments0_forward: non-positive shape");
+  hgru::batchnorm_moments0_kernel<<<nblk(inner), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, N, inner, epsilon, out);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 int layer_fc_forward(const float* x, int M, int K, const float* weights, const float* biases, int F, float* out,
                      void* stream) {
   if (!x || !weights || !biases || !out) return fail(HGRU_E_INVALID, "layer_fc_forward: null pointer");

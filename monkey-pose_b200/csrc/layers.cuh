@@ -59,6 +59,55 @@ max_pool2x2_kernel(const float* __restrict__ x, float* __restrict__ out, int N, 
   out[i] = m;
 }
 
+// tf.nn.max_pool / tf.nn.avg_pool with ksize = stride = k, SAME (the model's max_pool_4 and avg_pool helpers,
+// hgru_pose.py:124-132): output ceil(H/k) x ceil(W/k); TF pads pad_total = out*k - H, pad_total / 2 of it before;
+// padding never wins a max and is left out of an average's count.
+__global__ void __launch_bounds__(256)
+pool_same_kernel(const float* __restrict__ x, float* __restrict__ out, int N, int H, int W, int C, int k, int avg) {
+  const int Ho = (H + k - 1) / k, Wo = (W + k - 1) / k;
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  const size_t total = static_cast<size_t>(N) * Ho * Wo * C;
+  if (i >= total) return;
+  const int c = static_cast<int>(i % C);
+  const size_t pix = i / C;
+  const int xo = static_cast<int>(pix % Wo);
+  const int yo = static_cast<int>((pix / Wo) % Ho);
+  const int n = static_cast<int>(pix / (static_cast<size_t>(Wo) * Ho));
+  const int py = (Ho * k - H) / 2, px = (Wo * k - W) / 2;
+  float m = -INFINITY, sum = 0.f;
+  int cnt = 0;
+  for (int dy = 0; dy < k; ++dy)
+    for (int dx = 0; dx < k; ++dx) {
+      const int y = yo * k + dy - py, xq = xo * k + dx - px;
+      if (y < 0 || y >= H || xq < 0 || xq >= W) continue;
+      const float v = __ldg(x + ((static_cast<size_t>(n) * H + y) * W + xq) * C + c);
+      m = fmaxf(m, v); sum += v; ++cnt;
+    }
+  out[i] = avg ? sum / static_cast<float>(cnt) : m;
+}
+
+// The model's `batchnorm` helper (hgru_pose.py:120-122): tf.nn.moments over axis 0 (the batch, separately for every
+// position and channel) and tf.nn.batch_normalization without scale / offset: (x - mean) * rsqrt(var + eps).
+// x [N][inner]; one thread per inner index.
+__global__ void __launch_bounds__(256)
+batchnorm_moments0_kernel(const float* __restrict__ x, int N, size_t inner, float eps, float* __restrict__ out) {
+  const size_t j = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (j >= inner) return;
+  double s = 0.0;
+  for (int n = 0; n < N; ++n) s += static_cast<double>(x[static_cast<size_t>(n) * inner + j]);
+  const float mean = static_cast<float>(s / N);
+  double q = 0.0;
+  for (int n = 0; n < N; ++n) {
+    const double d = static_cast<double>(x[static_cast<size_t>(n) * inner + j]) - static_cast<double>(mean);
+    q += d * d;
+  }
+  const float inv = rsqrtf(static_cast<float>(q / N) + eps);
+  for (int n = 0; n < N; ++n) {
+    const size_t i = static_cast<size_t>(n) * inner + j;
+    out[i] = x[i] * inv + (-mean * inv);
+  }
+}
+
 // x [M][K] @ w [K][F] + b [F]: block = 64 outputs j of one row m... one thread per (m, j), K walked in chunks whose
 // fp32 partial sums are added in double (K is 262 144 for fc_1).
 __global__ void __launch_bounds__(256)

@@ -108,6 +108,33 @@ class LayerOps(object):
                    "layer_max_pool2x2_forward")
         return out
 
+    def _pool(self, bottom, ksize, average, what):
+        x = self._need_cuda(bottom, what)
+        N, H, W, C = [int(v) for v in x.shape]
+        out = torch.empty((N, (H + ksize - 1) // ksize, (W + ksize - 1) // ksize, C), device=x.device,
+                          dtype=torch.float32)
+        _lib.check(_lib.load().layer_pool_same_forward(x.data_ptr(), N, H, W, C, ksize, 1 if average else 0,
+                                                       out.data_ptr(), _stream()), "layer_pool_same_forward")
+        return out
+
+    def avg_pool(self, bottom, name):
+        """hgru_pose.py:124-127: tf.nn.avg_pool 2x2, stride 2, SAME (declared by the reference, unused by its build)."""
+        return self._pool(bottom, 2, True, "avg_pool")
+
+    def max_pool_4(self, bottom, name):
+        """hgru_pose.py:129-132: tf.nn.max_pool 4x4, stride 4, SAME (declared by the reference, unused by its build)."""
+        return self._pool(bottom, 4, False, "max_pool_4")
+
+    def batchnorm(self, layer):
+        """hgru_pose.py:120-122: moments over axis 0, normalised without scale / offset, epsilon 1e-3 (declared by the
+        reference, unused by its build)."""
+        x = self._need_cuda(layer, "batchnorm")
+        N = int(x.shape[0])
+        out = torch.empty_like(x)
+        _lib.check(_lib.load().layer_batchnorm_moments0_forward(x.data_ptr(), N, x.numel() // N, 1e-3, out.data_ptr(),
+                                                                _stream()), "layer_batchnorm_moments0_forward")
+        return out
+
     def fc_layer(self, bottom, in_size, out_size, name):
         """hgru_pose.py:156-163: reshape(bottom, [-1, in_size]) @ weights + biases."""
         x = self._need_cuda(bottom, "fc_layer").reshape(-1, int(in_size))

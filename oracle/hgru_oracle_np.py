@@ -59,6 +59,33 @@ def max_pool_2x2(x):
     return x.reshape(n, h // 2, 2, w // 2, 2, c).max(axis=(2, 4))
 
 
+def pool_same(x, k, average=False):
+    """tf.nn.max_pool / tf.nn.avg_pool with ksize = stride = k, SAME -- the model's max_pool_4 (k = 4) and avg_pool
+    (k = 2) helpers, hgru_pose.py:124-132.  TF pads out*k - H in all, half of it (rounded down) before; padding never
+    wins a max and is left out of an average's count."""
+    x = np.asarray(x, F64)
+    n, h, w, c = x.shape
+    ho, wo = -(-h // k), -(-w // k)
+    py, px = (ho * k - h) // 2, (wo * k - w) // 2
+    out = np.zeros((n, ho, wo, c), F64)
+    for yo in range(ho):
+        for xo in range(wo):
+            y0, y1 = max(yo * k - py, 0), min(yo * k - py + k, h)
+            x0, x1 = max(xo * k - px, 0), min(xo * k - px + k, w)
+            win = x[:, y0:y1, x0:x1, :]
+            out[:, yo, xo, :] = win.mean(axis=(1, 2)) if average else win.max(axis=(1, 2))
+    return out
+
+
+def batchnorm_moments0(x, eps=1e-3):
+    """The model's `batchnorm` helper (hgru_pose.py:120-122): tf.nn.moments(layer, [0]) and
+    tf.nn.batch_normalization(layer, m, v, None, None, 1e-3)."""
+    x = np.asarray(x, F64)
+    m = x.mean(axis=0)
+    v = ((x - m) ** 2).mean(axis=0)
+    return (x - m) / np.sqrt(v + eps)
+
+
 def batch_norm_inference(x, gamma, beta, mean, var, eps=1e-5):
     """tf.layers.batch_normalization(training=False) over the last axis -- hgru_pose.py:52-60 etc."""
     return (np.asarray(x, F64) - mean) / np.sqrt(np.asarray(var, F64) + eps) * gamma + beta

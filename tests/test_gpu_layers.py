@@ -295,3 +295,22 @@ def test_checkpoint_import_feeds_the_device_path_bitwise(tmp_path):
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
     ref = otorch.pose_forward(depth.cpu().numpy(), P, h0, timesteps=T, dtype=torch.float64).numpy()
     assert onp.rel_err(outs[0][0].cpu().numpy(), ref)[0] < 1e-2
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 8, 5), (3, 9, 13, 4), (1, 6, 7, 3), (2, 1, 2, 2)])
+def test_declared_but_unused_helpers_of_the_model(shape):
+    """max_pool_4, avg_pool and batchnorm (hgru_pose.py:120-132): the reference declares them and its build() never
+    calls them; they exist as stand-alone ops with TensorFlow's SAME-pooling semantics (padding split before / after,
+    left out of an average's count) and moments over the batch axis."""
+    rng = np.random.default_rng(shape[1] * 31 + shape[2])
+    x = rng.standard_normal(shape).astype(np.float32)
+    m = mp.model()
+    X = torch.as_tensor(x).cuda()
+    got = m.max_pool_4(X, "p").cpu().numpy()
+    assert got.shape == onp.pool_same(x, 4).shape and np.array_equal(got, onp.pool_same(x, 4).astype(np.float32))
+    assert onp.rel_err(m.avg_pool(X, "a").cpu().numpy(), onp.pool_same(x, 2, average=True))[0] < 1e-6
+    assert np.array_equal(m.max_pool(X, "q").cpu().numpy(), onp.pool_same(x, 2).astype(np.float32))   # the 2x2 kernel agrees
+    if shape[0] > 1:
+        assert onp.rel_err(m.batchnorm(X).cpu().numpy(), onp.batchnorm_moments0(x))[0] < 1e-5
+    with pytest.raises(RuntimeError):
+        m.avg_pool(torch.as_tensor(x), "a")

@@ -141,3 +141,18 @@ def test_training_mode_helpers_of_the_oracle():
     bb = onp.pose_forward(d, P, h0, timesteps=1, train_mode=True, dropout_keep=0.7, dropout_seed=3)
     c = onp.pose_forward(d, P, h0, timesteps=1, train_mode=False)
     assert a.shape == (3, 6) and not np.allclose(a, bb) and not np.allclose(a, c)
+
+
+def test_same_pooling_and_batch_moments_known_answers():
+    """TensorFlow's SAME pooling (hgru_pose.py:124-137): pad_total = out*k - H, half of it before; padding never wins
+    a max and is not counted by an average; `batchnorm` (:120-122) normalises over the batch axis."""
+    x = np.arange(1, 1 + 5 * 6, dtype=np.float64).reshape(1, 5, 6, 1)
+    assert np.array_equal(onp.pool_same(x, 2)[0, :, :, 0], onp.max_pool_2x2(np.pad(x, ((0, 0), (0, 1), (0, 0), (0, 0)),
+                                                                                    constant_values=-1))[0, :, :, 0])
+    p4 = onp.pool_same(x, 4)[0, :, :, 0]            # 5 -> 2 rows (pad 3: 1 before), 6 -> 2 columns (pad 2: 1 before)
+    assert p4.shape == (2, 2)
+    assert p4[0, 0] == x[0, 2, 2, 0] and p4[1, 1] == x[0, 4, 5, 0] and p4[0, 1] == x[0, 2, 5, 0]
+    a2 = onp.pool_same(x, 2, average=True)[0, :, :, 0]
+    assert a2[0, 0] == x[0, :2, :2, 0].mean() and a2[2, 0] == x[0, 4, :2, 0].mean()      # last row: 2 values, not 4
+    b = onp.batchnorm_moments0(np.array([[1.0, 10.0], [3.0, 10.0]]), eps=0.0 + 1e-3)
+    assert abs(b[0, 0] + 1 / np.sqrt(1 + 1e-3)) < 1e-12 and b[0, 1] == 0.0
