@@ -115,3 +115,23 @@ def test_worker_split_sums_like_numpy(host):
             assert got == want, (n, L)
             if n > 128:
                 assert n / 128 <= visited.value <= n / 64
+
+
+def test_random_sizes_and_splits_property(host):
+    """Property test (hypothesis): for any length, any values and any worker level the device formulation's total is
+    numpy's float32 sum."""
+    hyp = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(n=st.integers(1, 40000), level=st.integers(0, 12), seed=st.integers(0, 2 ** 31 - 1),
+           scale=st.sampled_from([1e-3, 1.0, 3e4]))
+    def check(n, level, seed, scale):
+        a = (np.random.default_rng(seed).standard_normal(n) * scale).astype(np.float32)
+        visited = ctypes.c_longlong(0)
+        got = np.float32(host.np_host_worker_sum(_ptr(a), n, level, ctypes.byref(visited)))
+        assert visited.value >= 1
+        assert got == a.sum()
+        assert np.float32(host.np_host_pairwise_sum(_ptr(a), n)) == a.sum()
+
+    check()
