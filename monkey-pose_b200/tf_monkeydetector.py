@@ -74,6 +74,19 @@ class tfMonkeyDetector(object):
         v_s = self.uy + com_3d[:, 1] / com_3d[:, 2] * self.fy
         return numpy.stack([u_s, v_s, -com_3d[:, 2]], axis=1)
 
+    def relative_labels(self, jnts_xyz, coms):
+        """The label half of the reference's `prepare_data` (train_cnn_networks_hgru.py:51-56) for a batch: joints
+        [N,J,3] (camera space, mm) relative to each frame's centre of mass (`getRelativeCoordinates`, :372-385), as
+        float32, divided by cube[2] / 2 and clipped to [-1, 1] -> numpy float64 [N, 3J] (the reference fills a
+        float64 array).  A few dozen numbers per frame: host numpy, the reference's own operations."""
+        j = numpy.asarray(jnts_xyz)
+        coms = numpy.asarray(coms.cpu() if torch.is_tensor(coms) else coms, numpy.float64).reshape(j.shape[0], 3)
+        out = numpy.zeros((j.shape[0], j.shape[1] * j.shape[2]))
+        for im in range(j.shape[0]):
+            rel = j[im] - self.uvdtoxyz(coms[im])
+            out[im] = numpy.clip(numpy.asarray(numpy.reshape(rel, (-1,)), dtype='float32') / (self.cube[2] / 2.), -1, 1)
+        return out
+
     # ---- centre of mass of a depth image (device; tf_monkeydetector.py:73-90) ---------------------------
     def _max_window_pixels(self, H, W):
         """The largest window comToBounds can ask for: a centre of mass at the near plane (:193-206)."""
@@ -401,3 +414,12 @@ def prepare_data_test(image_np, tr_res, md, config):
                                             frame_scale=config.image_max_depth,
                                             out_divisor=config.image_max_depth)
     return patches[..., None], coms, Ms
+
+
+def prepare_data(image_np, image_label_shaped, tr_res, md, config, show=False):
+    """train_cnn_networks_hgru.py:40-59, the training-time twin of `prepare_data_test`: the same crops (on the device)
+    plus the normalised relative joint labels -> (patches [N,128,128,1] CUDA, rel_labels numpy [N, 3J])."""
+    if show:
+        raise NotImplementedError("plotting is not part of the port")
+    patches, coms, _ = prepare_data_test(image_np, tr_res, md, config)
+    return patches, md.relative_labels(image_label_shaped, coms)

@@ -46,6 +46,17 @@ def main():
     batch[:, 3, 2] = -1500.0                                  # the TF projection has no z == 0 branch
     out["jnts_batch"] = batch
     out["calculateCoMfrom3DJoints"] = np.asarray(md.calculateCoMfrom3DJoints(batch))
+    # the label half of prepare_data (train_cnn_networks_hgru.py:51-56) for two frames, restated line by line on the
+    # reference's own methods (the trainer module itself imports the whole training stack)
+    coms = np.array([com_uvd, [301.0, 150.5, 2410.0]])
+    far = batch.copy()
+    far[1] *= np.float32(3.0)                                 # some joints beyond the cube: the clip to [-1, 1] acts
+    rel_labels = np.zeros((2, J * 3))
+    for im in range(2):
+        jnts_uvd = md.xyztouvd_np(far[im])
+        rel_jnts_xyz, rel_jnts_uvd = md.getRelativeCoordinates(far[im], jnts_uvd, coms[im], M)
+        rel_labels[im] = np.clip(np.asarray(np.reshape(rel_jnts_xyz, (J * 3,)), dtype='float32') / (md.cube[2] / 2.), -1, 1)
+    out["label_jnts"], out["label_coms"], out["rel_labels"] = far, coms, rel_labels
     path = os.path.join(HERE, "detector_host_ref.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, {k: (np.asarray(v).shape, np.asarray(v).dtype) for k, v in out.items()})

@@ -38,3 +38,12 @@ def test_largest_window_bound_covers_the_near_plane():
     xs, xe, ys, ye, _, _ = md.comToBounds(np.array([256.0, 212.0, float(md.minDepth)]), md.cube)
     assert (xe - xs) * (ye - ys) <= md._max_window_pixels(424, 512)
     assert md._max_window_pixels(4000, 4000) == 4000 * 4000
+
+
+def test_relative_labels_of_prepare_data_match_the_reference():
+    """The label half of the training-time `prepare_data` (train_cnn_networks_hgru.py:51-56)."""
+    z = np.load(GOLDEN)
+    md = tmd.tfMonkeyDetector(*CAMERA)
+    got = md.relative_labels(z["label_jnts"], z["label_coms"])
+    assert got.dtype == np.float64 and np.array_equal(got, z["rel_labels"])
+    assert got.min() == -1.0 or got.max() == 1.0                   # the clip acts on this fixture
