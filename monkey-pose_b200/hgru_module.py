@@ -435,6 +435,37 @@ class ContextualCircuit(object):
         """While loop halting condition (hgru_module.py:859-861)."""
         return i0 < self.timesteps
 
+    # -- declared by the reference, not on the path hgru_pose.py configures (SURVEY.md 8 a19): same names, and the
+    #    reference's own error type for an unimplemented option
+    def _off_path(self, what, lines):
+        raise NotImplementedError('%s (hgru_module.py:%s) is declared by the reference but not on the path '
+                                  'hgru_pose.py configures' % (what, lines))
+
+    def symmetric_weights(self, w, name):
+        """hgru_module.py:165-170 (shadowed in the reference by the boolean option of the same name, :163)."""
+        self._off_path('symmetric_weights()', '165-170')
+
+    def apply_tuning(self, data, wm, nl=False, rectify=None):
+        self._off_path('apply_tuning', '583-603')
+
+    def zoneout(self, dropout):
+        self._off_path('zoneout', '605-613')
+
+    def hierarchical_convolutions(self, data, key, rectification):
+        self._off_path('hierarchical_convolutions', '660-690')
+
+    def mely_input_integration(self, P, I, O, I_update):
+        self._off_path('mely_input_integration', '758-767')
+
+    def mely_output_integration(self, P, I, O, O_update):
+        self._off_path('mely_output_integration', '769-773')
+
+    def input_integration_control(self, P, I, O, I_update):
+        self._off_path('input_integration_control', '775-780')
+
+    def output_integration_control(self, P, I, O, O_update):
+        self._off_path('output_integration_control', '782-793')
+
     # -- forward -----------------------------------------------------------------------------
     def _initial_state(self):
         if self._hidden_state is not None:
