@@ -156,3 +156,20 @@ def test_same_pooling_and_batch_moments_known_answers():
     assert a2[0, 0] == x[0, :2, :2, 0].mean() and a2[2, 0] == x[0, 4, :2, 0].mean()      # last row: 2 values, not 4
     b = onp.batchnorm_moments0(np.array([[1.0, 10.0], [3.0, 10.0]]), eps=0.0 + 1e-3)
     assert abs(b[0, 0] + 1 / np.sqrt(1 + 1e-3)) < 1e-12 and b[0, 1] == 0.0
+
+
+def test_leaf_convolution_against_a_second_independent_implementation():
+    """The oracle's conv2d_same (numpy) and the torch-CPU oracle agree with scipy.signal.correlate2d -- a third party's
+    definition of a zero-padded 'same' cross-correlation -- for odd filters, several channels and non-square images."""
+    signal = pytest.importorskip("scipy.signal")
+    rng = np.random.default_rng(8)
+    for (h, w, ci, co, f) in ((9, 7, 3, 2, 3), (16, 11, 2, 3, 15), (5, 5, 1, 1, 1), (12, 20, 4, 4, 7)):
+        x = rng.standard_normal((2, h, w, ci))
+        k = rng.standard_normal((f, f, ci, co))
+        want = np.zeros((2, h, w, co))
+        for n in range(2):
+            for o in range(co):
+                for i in range(ci):
+                    want[n, :, :, o] += signal.correlate2d(x[n, :, :, i], k[:, :, i, o], mode="same", boundary="fill")
+        got = onp.conv2d_same(x, k)
+        assert np.abs(got - want).max() < 1e-11
