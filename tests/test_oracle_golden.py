@@ -173,3 +173,34 @@ def test_leaf_convolution_against_a_second_independent_implementation():
                     want[n, :, :, o] += signal.correlate2d(x[n, :, :, i], k[:, :, i, o], mode="same", boundary="fill")
         got = onp.conv2d_same(x, k)
         assert np.abs(got - want).max() < 1e-11
+
+
+def test_leaf_normalisation_and_pooling_against_torch_functional():
+    """tf.layers.batch_normalization (inference and training forward, moving-statistics update) and SAME pooling as
+    the numpy oracle restates them, against torch.nn.functional's independent implementations."""
+    import torch.nn.functional as F
+    rng = np.random.default_rng(9)
+    x = rng.standard_normal((4, 6, 10, 5))
+    gamma, beta = rng.uniform(0.5, 1.5, 5), rng.standard_normal(5)
+    mean, var = rng.standard_normal(5), rng.uniform(0.5, 2.0, 5)
+    xt = torch.as_tensor(x).permute(0, 3, 1, 2)
+    t = lambda a: torch.as_tensor(a)                                            # noqa: E731
+    want = F.batch_norm(xt, t(mean), t(var), t(gamma), t(beta), training=False, eps=1e-5).permute(0, 2, 3, 1).numpy()
+    assert np.abs(onp.batch_norm_inference(x, gamma, beta, mean, var, eps=1e-5) - want).max() < 1e-12
+    rm, rv = t(mean.copy()), t(var.copy())
+    want = F.batch_norm(xt, rm, rv, t(gamma), t(beta), training=True, momentum=1 - 0.997, eps=1e-5)
+    got = onp.batch_norm_training(x, gamma, beta, eps=1e-5)
+    got = got[0] if isinstance(got, tuple) else got
+    assert np.abs(got - want.permute(0, 2, 3, 1).numpy()).max() < 1e-12
+    # pooling: 2x2 / stride 2 on even sizes, and the general SAME rule on odd ones (torch: explicit -inf padding)
+    assert np.array_equal(onp.max_pool_2x2(x), F.max_pool2d(xt, 2, 2).permute(0, 2, 3, 1).numpy())
+    y = rng.standard_normal((2, 7, 9, 3))
+    yt = torch.as_tensor(y).permute(0, 3, 1, 2)
+    for k in (2, 4):
+        ho, wo = -(-7 // k), -(-9 // k)
+        py, px = ho * k - 7, wo * k - 9
+        padded = F.pad(yt, (px // 2, px - px // 2, py // 2, py - py // 2), value=float("-inf"))
+        assert np.array_equal(onp.pool_same(y, k), F.max_pool2d(padded, k, k).permute(0, 2, 3, 1).numpy())
+    ones = F.pad(torch.ones_like(yt), (0, 1, 0, 1))
+    avg = F.avg_pool2d(F.pad(yt, (0, 1, 0, 1)), 2, 2) * 4 / (F.avg_pool2d(ones, 2, 2) * 4)
+    assert np.abs(onp.pool_same(y, 2, average=True) - avg.permute(0, 2, 3, 1).numpy()).max() < 1e-12
