@@ -84,3 +84,19 @@ def test_header_is_plain_c():
         assert r.returncode == 0, r.stderr
         out = subprocess.run([exe], capture_output=True, text=True)
         assert out.returncode == 0 and int(out.stdout.strip()) >= 100, (out.stdout, out.stderr)
+
+
+def test_documents_cite_only_evidence_files_that_exist():
+    """Every `r01_… / r02_…` evidence file named in DESIGN.md, README.md, INTEGRATION.md and profiles/README.md is
+    present under profiles/ (shell-style wildcards allowed)."""
+    import glob
+    import re
+    missing = []
+    for doc in ("DESIGN.md", "README.md", "INTEGRATION.md", os.path.join("profiles", "README.md")):
+        text = open(os.path.join(ROOT, doc)).read()
+        for m in re.finditer(r"`((?:profiles/)?r0[12]_[A-Za-z0-9_.*?-]+)`", text):
+            name = m.group(1)
+            path = os.path.join(ROOT, name if name.startswith("profiles/") else os.path.join("profiles", name))
+            if not glob.glob(path):
+                missing.append((doc, name))
+    assert not missing, missing
